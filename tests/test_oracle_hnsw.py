@@ -1,0 +1,81 @@
+"""HNSW restatement: structural invariants and the reference's recall tests on its own fixtures
+(core/idx/trees/hnsw/mod.rs:1039-1184; fixtures = first rows of tests/data/hnsw-random-*.gz,
+committed under tests/golden/ by tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _recall(ingest, nq, ext, keep, efs_expect):
+    data = np.load(os.path.join(G, "hnsw_ingest_1000x20.f64.npy"))[:ingest].astype(np.float32)
+    qs = np.load(os.path.join(G, "hnsw_query_300x20.f64.npy"))[:nq].astype(np.float32)
+    # new_params(20, F32, Euclidean, m=8, efc=100, ext, keep, ..)  -> m0 = 2m, ml = 1/ln(m)
+    h = O.Hnsw(20, "euclidean", m=8, efc=100, extend_candidates=ext, keep_pruned_connections=keep, seed=42)
+    for v in data:
+        h.insert(v)
+    assert len(h) == ingest and h.check_props()
+    for efs, expected in efs_expect:
+        total = 0.0
+        for q in qs:
+            ids, dist = h.search(q, 10, efs)
+            b = O.KnnResultBuilder(10)  # add_graph_results: one doc per element (docs = row ids)
+            for d, e in zip(dist, ids):
+                if b.check_add(d):
+                    b.add_graph_result(d, [int(e)])
+            res = b.collect()
+            assert len(res) == 10
+            bi, bd = O.vec_knn_f32(data, q, "euclidean", 10)
+            brute = list(zip(bd.tolist(), bi.tolist()))
+            rec = len({x[1] for x in res} & {x[1] for x in brute}) / 10.0
+            if rec == 1.0:
+                assert res == brute  # hnsw/mod.rs:1119-1123
+            total += rec
+        recall = total / len(qs)
+        assert recall >= expected, (efs, recall)
+
+
+def test_recall_euclidean():
+    _recall(1000, 300, False, False, [(10, 0.98), (40, 1.0)])
+
+
+def test_recall_euclidean_keep_pruned_connections():
+    _recall(750, 200, False, True, [(10, 0.98), (40, 1.0)])
+
+
+def test_recall_euclidean_full():
+    _recall(500, 100, True, True, [(10, 0.98), (40, 1.0)])
+
+
+@pytest.mark.parametrize("metric", ["euclidean", "cosine", "manhattan", "chebyshev"])
+@pytest.mark.parametrize("flags", [(False, False), (True, False), (False, True), (True, True)])
+def test_small_collections_invariants(metric, flags):
+    # tests_hnsw (hnsw/mod.rs:752-791): 30 random vectors, insert then search each -> itself is found
+    rng = np.random.default_rng(1)
+    data = rng.uniform(-20, 20, (30, 5)).astype(np.float32)
+    h = O.Hnsw(5, metric, m=4, efc=500, extend_candidates=flags[0], keep_pruned_connections=flags[1], seed=9)
+    for v in data:
+        h.insert(v)
+        assert h.check_props()
+    for i, v in enumerate(data):
+        ids, dist = h.search(v, 1, 500)
+        assert ids[0] == i and dist[0] <= 1e-6
+
+
+def test_csr_export_walk_equals_builder_walk():
+    rng = np.random.default_rng(2)
+    data = rng.uniform(-1, 1, (400, 12)).astype(np.float32)
+    h = O.Hnsw(12, "cosine", m=6, efc=60, seed=3)
+    for v in data:
+        h.insert(v)
+    g = h.export()
+    assert len(g["layers"]) >= 2
+    for q in rng.uniform(-1, 1, (20, 12)).astype(np.float32):
+        a = h.search(q, 10, 32)
+        vis, exp = h.counters()
+        b = O.hnsw_search_csr(g, q, 10, 32)
+        assert list(a[0]) == list(b[0]) and list(a[1]) == list(b[1]) and b[2] == (vis, exp)
