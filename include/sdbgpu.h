@@ -1,0 +1,167 @@
+/*
+ * sdbgpu.h -- C ABI of the B200-native KNN / HNSW / graph-expansion engine.
+ *
+ * This is the drop-in boundary for SurrealDB's vector-similarity and graph-scan hot path
+ * (SURVEY.md section 8b).  The reference has NO FFI of its own (pure Rust), so each
+ * entry point below names the Rust-internal seam it replaces; INTEGRATION.md shows the
+ * `extern "C"` block and the operator wrappers a maintainer adds behind a `gpu-knn` cargo feature.
+ * Paths are relative to surrealdb/core/src in the reference checkout.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types cross the boundary.
+ *  - every function is thread-safe per handle family: concurrent searches on one corpus/hnsw/graph
+ *    handle are serialised internally (one in-flight search per handle); mutation
+ *    (append/finalize) must not race with searches -- the same RW discipline the reference applies
+ *    to its HNSW graph (idx/trees/hnsw/index.rs:55,224,350).
+ *  - errors: integer status + thread-local message (sdb_last_error); nothing unwinds across the ABI.
+ *  - "rows" are scan positions: the caller appends vectors in the reference's scan order (record-key
+ *    byte order, i.e. what TableScan yields) and maps returned row numbers back to RecordIds.
+ *  - NO CPU FALLBACK: if no CUDA device is usable every entry point fails with SDB_ECUDA.
+ */
+#ifndef SDBGPU_H
+#define SDBGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sdb_ctx sdb_ctx;       /* one CUDA device: streams, scratch, TMA driver entry points   */
+typedef struct sdb_corpus sdb_corpus; /* device-resident N x D vector column (+ norms, screen copy)    */
+typedef struct sdb_hnsw sdb_hnsw;     /* device-resident HNSW layers (CSR) + element vectors           */
+typedef struct sdb_graph sdb_graph;   /* device-resident CSR adjacency of one (direction, edge table)  */
+
+typedef enum {
+  SDB_OK = 0,
+  SDB_EINVAL = 1,     /* bad argument                                                               */
+  SDB_EDIM = 2,       /* dimension mismatch -> Error::InvalidVectorDimension (idx/trees/vector.rs:643) */
+  SDB_ENOMEM = 3,
+  SDB_ECUDA = 4,      /* CUDA runtime/driver failure, or no sm_100 device                           */
+  SDB_ECANCELLED = 5, /* cancel flag observed -> Error::QueryCancelled (exec/operators/knn_topk.rs:186) */
+  SDB_EUNSUPPORTED = 6,
+  SDB_EOVERFLOW = 7   /* caller-provided output capacity too small                                  */
+} sdb_status;
+
+/* catalog::Distance (catalog/schema/index.rs:247-284).  Round 1 implements COSINE and EUCLIDEAN
+ * (the two metrics BASELINE.json's north_star names); the others return SDB_EUNSUPPORTED. */
+typedef enum {
+  SDB_CHEBYSHEV = 0,
+  SDB_COSINE = 1,
+  SDB_EUCLIDEAN = 2,
+  SDB_HAMMING = 3,
+  SDB_JACCARD = 4,
+  SDB_MANHATTAN = 5,
+  SDB_MINKOWSKI = 6,
+  SDB_PEARSON = 7
+} sdb_metric;
+
+/* element type of the rows handed to sdb_corpus_append (catalog VectorType, index.rs:321-334).
+ * Brute-force KnnTopK holds Vec<Number>: F64 covers arbitrary Number::Float rows, F32 covers rows whose
+ * values are f32-representable (the BASELINE configs) and enables the low-precision screen. */
+typedef enum { SDB_F32 = 0, SDB_F64 = 1 } sdb_dtype;
+
+/* which screening kernel sdb_knn_bruteforce uses (results are identical for all; this only moves
+ * the performance point).  AUTO: <= 8 queries -> streaming SIMT f32 kernel, else tcgen05 bf16. */
+typedef enum { SDB_SCREEN_AUTO = 0, SDB_SCREEN_SIMT_F32 = 1, SDB_SCREEN_TC_BF16 = 2, SDB_SCREEN_NONE_EXACT = 3 } sdb_screen;
+
+/* counters of the last brute-force call on a corpus (diagnostics / bench roofline arithmetic) */
+typedef struct {
+  uint32_t screen_used;      /* sdb_screen actually run                                        */
+  uint32_t n_passes;         /* threshold-refinement passes of the screen                      */
+  uint32_t n_fallback;       /* queries re-run through the exact kernel (verification failed)  */
+  uint32_t n_special_rows;   /* rows with zero / non-finite norm (always exact-ranked)         */
+  uint64_t n_candidates;     /* candidates appended by the screen over all passes              */
+  uint64_t n_reranked;       /* exact f64 distances computed by the re-rank kernel             */
+  uint64_t kernel_launches;  /* kernels launched by this call                                  */
+  float screen_ms;           /* device time of the screening kernels (CUDA events)             */
+  float total_ms;            /* device time of the whole call                                  */
+} sdb_knn_stats;
+
+/* ---- context -------------------------------------------------------------------------------- */
+sdb_status sdb_ctx_create(int device, sdb_ctx** out);
+void sdb_ctx_destroy(sdb_ctx*);
+const char* sdb_last_error(void); /* thread-local; valid until the next call on this thread */
+const char* sdb_version(void);
+void* sdb_pinned_alloc(size_t bytes); /* cudaHostAlloc: staging buffers for append / queries */
+void sdb_pinned_free(void*);
+/* total kernels launched through this context since creation (bench's gpu_launches) */
+uint64_t sdb_ctx_kernel_launches(const sdb_ctx*);
+/* the cudaStream_t every kernel of this context is launched on (so a harness can bracket calls with
+ * CUDA events on the launching stream) */
+void* sdb_ctx_stream(const sdb_ctx*);
+
+/* ---- brute-force KNN: replaces KnnTopK::execute (exec/operators/knn_topk.rs:166-267) and the
+ *      legacy QueryExecutor::knn (idx/planner/executor.rs:283-311) ----------------------------- */
+sdb_status sdb_corpus_create(sdb_ctx*, uint32_t dim, sdb_dtype, sdb_metric, uint64_t capacity_rows, sdb_corpus** out);
+void sdb_corpus_destroy(sdb_corpus*);
+/* rows: host memory (pinned preferred), row-major n x dim of the corpus dtype, in scan order. */
+sdb_status sdb_corpus_append(sdb_corpus*, const void* rows, uint64_t n);
+/* same, rows already in device memory of this context's device */
+sdb_status sdb_corpus_append_device(sdb_corpus*, const void* d_rows, uint64_t n);
+/* synthetic rows generated in HBM by the counter-based generator shared with the oracle
+ * (element (r, c) = gen(seed, (first_row + r) * dim + c)); bench/test input only. */
+sdb_status sdb_corpus_append_synthetic(sdb_corpus*, uint64_t seed, uint64_t first_row, uint64_t n);
+/* rows the reference would skip (field missing / non-numeric / dimension mismatch:
+ * extract_vector, knn_topk.rs:274-288; residual WHERE filter, planner/select.rs:1642-1652).
+ * skip[i] != 0 excludes row i.  May be called again to change the mask. */
+sdb_status sdb_corpus_set_skip(sdb_corpus*, const uint8_t* skip, uint64_t n);
+/* builds per-row exact f64 magnitudes, f32 screening norms, the bf16 screen copy and the special-row
+ * list.  Must be called after the last append and before searching. */
+sdb_status sdb_corpus_finalize(sdb_corpus*);
+uint64_t sdb_corpus_rows(const sdb_corpus*);
+sdb_status sdb_corpus_set_screen(sdb_corpus*, sdb_screen);
+/* queries: nq x dim f64 (the reference's query is Vec<Number>; Number::Float values).
+ * out_rows / out_dist: nq x k, nearest first, ties by scan order; out_count[q] <= k.
+ * cancel_flag (nullable) is polled between kernel phases.  */
+sdb_status sdb_knn_bruteforce(sdb_corpus*, const double* queries, uint32_t nq, uint32_t k, uint64_t* out_rows,
+                              double* out_dist, uint32_t* out_count, const volatile int* cancel_flag);
+/* device-resident variant: d_queries / d_out_* are device pointers; results are complete when the
+ * call returns.  row_base is added to every returned row (global id of a row-sharded corpus). */
+sdb_status sdb_knn_bruteforce_device(sdb_corpus*, const double* d_queries, uint32_t nq, uint32_t k,
+                                     uint64_t row_base, uint64_t* d_out_rows, double* d_out_dist,
+                                     uint32_t* d_out_count);
+sdb_status sdb_knn_last_stats(const sdb_corpus*, sdb_knn_stats* out);
+/* merges `n_lists` per-shard result lists (each nq x k; list l's entry j of query q is valid iff
+ * j < d_counts[l*stride_counts + q]) into the global top-k by (distance, row); all pointers are device
+ * pointers.  stride_* = distance in ELEMENTS between consecutive lists (0 = dense: nq*k, nq*k, nq), so the
+ * lists can sit inside the per-rank blocks of ONE NCCL all-gather buffer.  This is the merge step after
+ * the all-gather of per-shard candidates. */
+sdb_status sdb_topk_merge_device(sdb_ctx*, uint32_t n_lists, uint32_t nq, uint32_t k, const uint64_t* d_rows,
+                                 const double* d_dist, const uint32_t* d_counts, uint64_t stride_rows,
+                                 uint64_t stride_dist, uint64_t stride_counts, uint64_t* d_out_rows,
+                                 double* d_out_dist, uint32_t* d_out_count);
+
+/* ---- HNSW search: replaces Hnsw::knn_search (idx/trees/hnsw/mod.rs:459-482) called from
+ *      HnswIndex::search_graph (idx/trees/hnsw/index.rs:341-364) ------------------------------- */
+/* vectors: n_elems x dim f32 (element id = row).  Layer l adjacency is CSR over element ids;
+ * row_ptr[l] has n_elems+1 entries; neighbours keep the stored order (graph.rs:104-125). */
+sdb_status sdb_hnsw_load(sdb_ctx*, uint32_t dim, sdb_metric, uint64_t n_elems, const float* vectors,
+                         uint32_t n_layers, const uint64_t* const* row_ptr, const uint32_t* const* col_idx,
+                         int64_t entry_point, sdb_hnsw** out);
+void sdb_hnsw_destroy(sdb_hnsw*);
+/* queries nq x dim f32; out nq x k (element id, f64 distance) ascending; out_counters (nullable)
+ * nq x 2 = {distance evaluations, expanded nodes} per query. */
+sdb_status sdb_hnsw_search(sdb_hnsw*, const float* queries, uint32_t nq, uint32_t k, uint32_t ef,
+                           uint64_t* out_elems, double* out_dist, uint32_t* out_count, uint64_t* out_counters);
+
+/* ---- graph expansion: replaces GraphEdgeScan::execute (exec/operators/scan/graph.rs:168-283)
+ *      driven by LookupPart (exec/parts/lookup.rs:139-170) and the +collect recursion
+ *      (exec/operators/recursion/collect.rs:74-143) -------------------------------------------- */
+sdb_status sdb_graph_load_csr(sdb_ctx*, uint64_t n_rows, const uint64_t* row_ptr, const uint32_t* col_idx,
+                              sdb_graph** out);
+void sdb_graph_destroy(sdb_graph*);
+/* applies hops[0..n_hops) in order to the frontier (multiset semantics: duplicates kept, frontier
+ * order preserved, per-source limit honoured; 0 = no limit).  *out_ids is library-owned host
+ * memory (free with sdb_free). */
+sdb_status sdb_graph_expand(sdb_graph* const* hops, uint32_t n_hops, const uint32_t* frontier, uint64_t n_frontier,
+                            uint32_t per_source_limit, uint32_t** out_ids, uint64_t* out_n);
+/* +collect BFS: first-seen dedup, emits from min_depth, start only marked seen when inclusive. */
+sdb_status sdb_graph_collect(sdb_graph*, const uint32_t* start, uint64_t n_start, uint32_t min_depth,
+                             uint32_t max_depth, int inclusive, uint32_t** out_ids, uint64_t* out_n);
+void sdb_free(void*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

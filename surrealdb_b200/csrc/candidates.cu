@@ -1,0 +1,359 @@
+// candidates.cu -- everything between the screening kernels and the answer:
+//   prep_queries : f64 queries -> f32 / bf16 screen copies, exact |q|, special-query flags
+//   cand_compact : per query keep the best k' screened candidates, tighten the threshold tau
+//   cand_rerank  : exact f64 distances (the reference's arithmetic, op for op) of the survivors
+//   cand_final   : order by (distance, scan position), emit top-k, PROVE that no unscreened row could
+//                  belong to it (error-bound check) or flag the query for the exact kernel.
+#include "exactmath.cuh"
+#include "internal.cuh"
+#include "rowwalk.cuh"
+
+namespace sdb {
+
+// ------------------------------------------------------------------------------------------------
+__global__ void prep_queries_kernel(const double* __restrict__ q64, uint32_t dim, uint32_t dim_pad, int metric,
+                                    float* __restrict__ q32, __nv_bfloat16* __restrict__ qbf, double* __restrict__ qmag,
+                                    uint32_t* __restrict__ qflags, uint32_t nq) {
+  const uint32_t q = blockIdx.x;
+  __shared__ uint32_t s_flags;
+  if (threadIdx.x == 0) s_flags = 0;
+  __syncthreads();
+  uint32_t fl = 0;
+  if (q < nq) {
+    for (uint32_t c = threadIdx.x; c < dim_pad; c += blockDim.x) {
+      const double v = c < dim ? q64[(size_t)q * dim + c] : 0.0;
+      const float f = (float)v;
+      if (c < dim) q32[(size_t)q * dim + c] = f;
+      if (qbf) qbf[(size_t)q * dim_pad + c] = __float2bfloat16_rn(f);
+      if (v != v) fl |= 3u;               // NaN input: exact path, positive-NaN propagation
+      else if (!isfinite(f)) fl |= 1u;    // inf or beyond f32 range: the screen cannot bound its error
+    }
+  } else {  // padding queries of the bf16 operand tile
+    for (uint32_t c = threadIdx.x; c < dim_pad; c += blockDim.x)
+      if (qbf) qbf[(size_t)q * dim_pad + c] = __float2bfloat16_rn(0.f);
+  }
+  if (fl) atomicOr(&s_flags, fl);
+  __syncthreads();
+  if (threadIdx.x == 0 && q < nq) {
+    double s = 0.0;  // magnitude(): sequential f64, fnc/util/math/vector.rs:301-314
+    for (uint32_t c = 0; c < dim; c++) {
+      const double v = q64[(size_t)q * dim + c];
+      s = __dadd_rn(s, __dmul_rn(v, v));
+    }
+    const double m = __dsqrt_rn(s);
+    qmag[q] = m;
+    uint32_t f = s_flags;
+    if (metric == SDB_COSINE && (!(m > 0.0) || !isfinite(m))) f |= 1u;
+    if (metric != SDB_COSINE && !isfinite(m)) f |= 1u;
+    qflags[q] = f;
+  }
+}
+
+static sdb_status ensure_scratch(Corpus* c, uint32_t nq, uint32_t cap, uint32_t kp) {
+  const uint32_t nq_pad = (nq + 127) / 128 * 128;
+  if (c->sc_nq >= nq_pad && c->sc_cap >= cap && c->sc_kp >= kp) return SDB_OK;
+  cudaFree(c->d_q64); cudaFree(c->d_q32); cudaFree(c->d_qbf16); cudaFree(c->d_qmag); cudaFree(c->d_qflags);
+  cudaFree(c->d_tau); cudaFree(c->d_cand); cudaFree(c->d_cand_cnt); cudaFree(c->d_flags);
+  cudaFree(c->d_rr_key); cudaFree(c->d_rr_dist); cudaFree(c->d_rr_row);
+  c->sc_nq = c->sc_cap = c->sc_kp = 0;
+  const uint32_t nqa = nq_pad > c->sc_nq ? nq_pad : c->sc_nq;
+  const uint32_t capa = cap;
+  c->rr_stride = kp + SPECIAL_CAP;
+  SDB_CUDA(cudaMalloc(&c->d_q64, sizeof(double) * (size_t)nqa * c->dim));
+  SDB_CUDA(cudaMalloc(&c->d_q32, sizeof(float) * (size_t)nqa * c->dim));
+  SDB_CUDA(cudaMalloc(&c->d_qbf16, sizeof(__nv_bfloat16) * (size_t)nqa * c->dim_pad));
+  SDB_CUDA(cudaMalloc(&c->d_qmag, sizeof(double) * nqa));
+  SDB_CUDA(cudaMalloc(&c->d_qflags, sizeof(uint32_t) * nqa));
+  SDB_CUDA(cudaMalloc(&c->d_tau, sizeof(float) * nqa));
+  SDB_CUDA(cudaMalloc(&c->d_cand, sizeof(Cand) * (size_t)nqa * capa));
+  SDB_CUDA(cudaMalloc(&c->d_cand_cnt, sizeof(uint32_t) * nqa));
+  SDB_CUDA(cudaMalloc(&c->d_flags, sizeof(uint32_t) * nqa));
+  SDB_CUDA(cudaMalloc(&c->d_rr_key, sizeof(uint64_t) * (size_t)nqa * c->rr_stride));
+  SDB_CUDA(cudaMalloc(&c->d_rr_dist, sizeof(double) * (size_t)nqa * c->rr_stride));
+  SDB_CUDA(cudaMalloc(&c->d_rr_row, sizeof(uint32_t) * (size_t)nqa * c->rr_stride));
+  c->sc_nq = nqa;
+  c->sc_cap = capa;
+  c->sc_kp = kp;
+  return SDB_OK;
+}
+
+sdb_status scratch_for(Corpus* c, uint32_t nq, uint32_t cap, uint32_t kp) { return ensure_scratch(c, nq, cap, kp); }
+
+sdb_status prep_queries(Corpus* c, const double* d_queries, uint32_t nq, cudaStream_t st) {
+  // d_queries may alias c->d_q64 (host entry point copies there first)
+  if (d_queries != c->d_q64)
+    SDB_CUDA(cudaMemcpyAsync(c->d_q64, d_queries, sizeof(double) * (size_t)nq * c->dim, cudaMemcpyDeviceToDevice, st));
+  const uint32_t nq_pad = (nq + 127) / 128 * 128;
+  prep_queries_kernel<<<nq_pad, 128, 0, st>>>(c->d_q64, c->dim, c->dim_pad, (int)c->metric, c->d_q32, c->d_qbf16,
+                                              c->d_qmag, c->d_qflags, nq);
+  count_launch(c->ctx);
+  SDB_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void cand_reset_kernel(float* tau, uint32_t* cnt, uint32_t* flags, uint32_t nq) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nq) {
+    tau[i] = __int_as_float(0xff800000);  // -inf
+    cnt[i] = 0;
+    flags[i] = 0;
+  }
+}
+sdb_status cand_reset(Corpus* c, uint32_t nq, cudaStream_t st) {
+  cand_reset_kernel<<<(nq + 255) / 256, 256, 0, st>>>(c->d_tau, c->d_cand_cnt, c->d_flags, nq);
+  count_launch(c->ctx);
+  SDB_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
+
+// block-wide bitonic sort of n (power of two) u64 keys in shared memory; DESC = descending
+template <bool DESC>
+__device__ void bitonic_sort_u64(uint64_t* s, uint32_t n) {
+  for (uint32_t k = 2; k <= n; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t ixj = i ^ j;
+        if (ixj > i) {
+          const uint64_t a = s[i], b = s[ixj];
+          const bool up = ((i & k) == 0);
+          const bool swap = DESC ? (up ? a < b : a > b) : (up ? a > b : a < b);
+          if (swap) {
+            s[i] = b;
+            s[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// keep the best kp candidates of each query, tau = score of the kp-th (if that many exist)
+__global__ void __launch_bounds__(1024) cand_compact_kernel(Cand* __restrict__ cand, uint32_t* __restrict__ cnt,
+                                                            float* __restrict__ tau, uint32_t* __restrict__ flags,
+                                                            uint32_t cap, uint32_t kp) {
+  extern __shared__ uint64_t s_keys[];
+  const uint32_t q = blockIdx.x;
+  uint32_t n = cnt[q];
+  if (n <= kp && n <= cap) return;  // nothing to drop, tau unchanged (uniform per block)
+  if (n > cap) {
+    if (threadIdx.x == 0) flags[q] |= 1u;  // candidates were dropped: this query must be re-run exactly
+    n = cap;
+  }
+  Cand* cq = cand + (size_t)q * cap;
+  uint32_t p2 = 1;
+  while (p2 < n) p2 <<= 1;
+  for (uint32_t i = threadIdx.x; i < p2; i += blockDim.x) {
+    uint64_t key = 0;  // padding sorts last (real keys have the top bit pattern of f32_key >= 0x0080...)
+    if (i < n) key = ((uint64_t)f32_key(cq[i].score) << 32) | (uint64_t)(0xFFFFFFFFu - cq[i].row);
+    s_keys[i] = key;
+  }
+  __syncthreads();
+  bitonic_sort_u64<true>(s_keys, p2);
+  const uint32_t keep = n < kp ? n : kp;
+  for (uint32_t i = threadIdx.x; i < keep; i += blockDim.x) {
+    const uint64_t key = s_keys[i];
+    uint32_t fk = (uint32_t)(key >> 32);
+    fk = (fk >> 31) ? (fk & 0x7fffffffu) : ~fk;
+    Cand cd;
+    cd.score = __uint_as_float(fk);
+    cd.row = 0xFFFFFFFFu - (uint32_t)key;
+    cq[i] = cd;
+    if (i == kp - 1) tau[q] = cd.score;
+  }
+  if (threadIdx.x == 0) cnt[q] = keep;
+}
+
+sdb_status cand_compact(Corpus* c, uint32_t nq, uint32_t kp, cudaStream_t st) {
+  const size_t smem = sizeof(uint64_t) * c->sc_cap;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SDB_CUDA(cudaFuncSetAttribute(cand_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  cand_compact_kernel<<<nq, 1024, smem, st>>>(c->d_cand, c->d_cand_cnt, c->d_tau, c->d_flags, c->sc_cap, kp);
+  count_launch(c->ctx);
+  SDB_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// exact re-rank: one block per query, each warp takes 32 entries (candidates, then the special rows)
+constexpr uint32_t QCHUNK = 1024;  // query columns staged in shared memory per step
+
+template <typename T, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) cand_rerank_kernel(
+    const T* __restrict__ rows, uint32_t dim, int metric, const double* __restrict__ mag,
+    const double* __restrict__ q64, const double* __restrict__ qmag, const uint32_t* __restrict__ qflags,
+    const Cand* __restrict__ cand, const uint32_t* __restrict__ cnt, uint32_t cap, const uint32_t* __restrict__ special,
+    uint32_t n_special, uint64_t* __restrict__ rr_key, double* __restrict__ rr_dist, uint32_t* __restrict__ rr_row,
+    uint32_t rr_stride) {
+  __shared__ T tile[WARPS][32][33];
+  __shared__ double s_q[QCHUNK];
+  const uint32_t q = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t n_c = cnt[q] < cap ? cnt[q] : cap;
+  const uint32_t n_e = n_c + n_special;
+  const bool q_nan = (qflags[q] & 2u) != 0;
+  const double qm = qmag[q];
+  for (uint32_t e0 = 0; e0 < n_e; e0 += WARPS * 32) {  // uniform per block
+    const uint32_t e = e0 + warp * 32 + lane;
+    uint32_t my_row = NO_ROW;
+    if (e < n_c) my_row = cand[(size_t)q * cap + e].row;
+    else if (e < n_e) my_row = special[e - n_c];
+    ExactAcc acc;
+    for (uint32_t cb = 0; cb < dim; cb += QCHUNK) {
+      const uint32_t cw = dim - cb < QCHUNK ? dim - cb : QCHUNK;
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < cw; i += blockDim.x) s_q[i] = q64[(size_t)q * dim + cb + i];
+      __syncthreads();
+      // walk columns [cb, cb+cw) of the 32 rows of this warp
+      const T* base = rows + cb;
+      for (uint32_t c0 = 0; c0 < cw; c0 += 32) {
+        const uint32_t c = c0 + lane;
+#pragma unroll 8
+        for (int r = 0; r < 32; r++) {
+          const uint32_t row = __shfl_sync(0xffffffffu, my_row, r);
+          T v = T(0);
+          if (row != NO_ROW && c < cw) v = __ldg(base + (size_t)row * dim + c);
+          tile[warp][r][lane] = v;
+        }
+        __syncwarp();
+        if (my_row != NO_ROW) {
+          const uint32_t lim = cw - c0 < 32u ? cw - c0 : 32u;
+          if (metric == SDB_COSINE) {
+            for (uint32_t j = 0; j < lim; j++) acc.cosine_step((double)tile[warp][lane][j], s_q[c0 + j]);
+          } else {
+            for (uint32_t j = 0; j < lim; j++) acc.euclid_step((double)tile[warp][lane][j], s_q[c0 + j]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (my_row != NO_ROW) {
+      const double d = metric == SDB_COSINE ? cosine_finish(acc, mag[my_row], qm, q_nan) : euclid_finish(acc, q_nan);
+      const size_t o = (size_t)q * rr_stride + e;
+      rr_key[o] = dist_key(d);
+      rr_dist[o] = d;
+      rr_row[o] = my_row;
+    }
+  }
+}
+
+sdb_status cand_rerank(Corpus* c, uint32_t nq, cudaStream_t st) {
+  if (c->dtype == SDB_F32)
+    cand_rerank_kernel<float, 4><<<nq, 128, 0, st>>>((const float*)c->d_rows, c->dim, (int)c->metric, c->d_mag,
+                                                     c->d_q64, c->d_qmag, c->d_qflags, c->d_cand, c->d_cand_cnt,
+                                                     c->sc_cap, c->d_special, c->n_special, c->d_rr_key,
+                                                     c->d_rr_dist, c->d_rr_row, c->rr_stride);
+  else
+    cand_rerank_kernel<double, 4><<<nq, 128, 0, st>>>((const double*)c->d_rows, c->dim, (int)c->metric, c->d_mag,
+                                                      c->d_q64, c->d_qmag, c->d_qflags, c->d_cand, c->d_cand_cnt,
+                                                      c->sc_cap, c->d_special, c->n_special, c->d_rr_key,
+                                                      c->d_rr_dist, c->d_rr_row, c->rr_stride);
+  count_launch(c->ctx);
+  SDB_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// final ordering + proof.  Entries sorted ascending by (Number::cmp key, row) -- exactly the
+// DistanceEntry order of KnnTopK (knn_topk.rs:61-73): nearest first, earlier scan position wins ties.
+__global__ void __launch_bounds__(1024) cand_final_kernel(
+    const uint64_t* __restrict__ rr_key, const double* __restrict__ rr_dist, const uint32_t* __restrict__ rr_row,
+    uint32_t rr_stride, const uint32_t* __restrict__ cnt, uint32_t cap, uint32_t n_special,
+    const float* __restrict__ tau, const double* __restrict__ qmag, uint32_t* __restrict__ flags, int metric,
+    float eps_rel, float max_norm, uint32_t k, uint32_t kp, uint64_t row_base, uint64_t* __restrict__ out_rows,
+    double* __restrict__ out_dist, uint32_t* __restrict__ out_count) {
+  extern __shared__ uint64_t s_mem[];
+  const uint32_t q = blockIdx.x;
+  const uint32_t n_c = cnt[q] < cap ? cnt[q] : cap;
+  const uint32_t n_e = n_c + n_special;
+  uint32_t p2 = 1;
+  while (p2 < n_e) p2 <<= 1;
+  uint64_t* s_key = s_mem;                       // [p2] distance key
+  uint64_t* s_idx = s_mem + p2;                  // [p2] (row << 32 | entry) -- secondary order by row
+  // composite 96-bit sort done as two stable-equivalent passes: sort by (key, row) using a 64-bit
+  // rank trick: first sort entries by row (unique), then a bitonic sort on key with row as tiebreak
+  // would need 128-bit compares; instead pack: rank-by-row r (< 2^11) into the low bits of an index
+  // word and compare (key, idx) lexicographically below.
+  for (uint32_t i = threadIdx.x; i < p2; i += blockDim.x) {
+    if (i < n_e) {
+      s_key[i] = rr_key[(size_t)q * rr_stride + i];
+      s_idx[i] = ((uint64_t)rr_row[(size_t)q * rr_stride + i] << 32) | i;
+    } else {
+      s_key[i] = ~0ull;
+      s_idx[i] = ~0ull;
+    }
+  }
+  __syncthreads();
+  for (uint32_t kk = 2; kk <= p2; kk <<= 1) {
+    for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = threadIdx.x; i < p2; i += blockDim.x) {
+        const uint32_t ixj = i ^ j;
+        if (ixj > i) {
+          const uint64_t ka = s_key[i], kb = s_key[ixj], ia = s_idx[i], ib = s_idx[ixj];
+          const bool a_gt_b = ka > kb || (ka == kb && ia > ib);
+          const bool up = ((i & kk) == 0);
+          if (up ? a_gt_b : !a_gt_b) {
+            s_key[i] = kb; s_key[ixj] = ka;
+            s_idx[i] = ib; s_idx[ixj] = ia;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const uint32_t n_out = n_e < k ? n_e : k;
+  for (uint32_t i = threadIdx.x; i < n_out; i += blockDim.x) {
+    const uint32_t e = (uint32_t)s_idx[i];
+    out_rows[(size_t)q * k + i] = row_base + (uint64_t)(s_idx[i] >> 32);
+    out_dist[(size_t)q * k + i] = rr_dist[(size_t)q * rr_stride + e];
+  }
+  if (threadIdx.x == 0) {
+    out_count[q] = n_out;
+    // ---- proof that no row outside the candidate set can enter the top-k ----
+    uint32_t fl = flags[q];
+    const float t = tau[q];
+    if (t > __int_as_float(0xff800000) && n_e >= k && k > 0) {  // tau == -inf: every screened-in row is a candidate
+      const double qm = qmag[q];
+      const uint64_t kth = s_key[k - 1];
+      bool ok;
+      if (metric == SDB_COSINE) {
+        // non-candidate: score = dot~ * (1/|x|)~ <= tau  =>  sim <= tau/|q| + eps  =>  dist >= 1 - tau/|q| - eps
+        const double bound = 1.0 - (double)t / qm - (double)eps_rel - 1e-9;
+        ok = dist_key(bound) > kth;
+      } else {
+        // score = 2 dot~ - |x|^2~ <= tau  =>  d^2 = |x|^2 - 2 dot + |q|^2 >= -tau + |q|^2 - eps_e
+        const double mn = (double)max_norm;
+        const double eps_e = 2.0 * (double)eps_rel * qm * mn + 4.8e-7 * (mn * mn + 2.0 * qm * mn) + 1e-30;
+        const double L = -(double)t + qm * qm - eps_e;
+        ok = L > 0.0 && dist_key(sqrt(L) * (1.0 - 1e-12)) > kth;
+      }
+      if (!ok) fl |= 2u;
+    }
+    if (fl & 1u) fl |= 2u;  // overflowed candidate buffer => exact re-run
+    flags[q] = fl;
+  }
+}
+
+sdb_status cand_final(Corpus* c, uint32_t nq, uint32_t k, uint32_t kp, float eps_rel, uint64_t row_base,
+                      uint64_t* d_out_rows, double* d_out_dist, uint32_t* d_out_count, cudaStream_t st) {
+  uint32_t p2 = 1;
+  while (p2 < kp + SPECIAL_CAP) p2 <<= 1;
+  const size_t smem = sizeof(uint64_t) * 2 * p2;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SDB_CUDA(cudaFuncSetAttribute(cand_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  cand_final_kernel<<<nq, 1024, smem, st>>>(c->d_rr_key, c->d_rr_dist, c->d_rr_row, c->rr_stride, c->d_cand_cnt,
+                                            c->sc_cap, c->n_special, c->d_tau, c->d_qmag, c->d_flags,
+                                            (int)c->metric, eps_rel, c->max_norm, k, kp, row_base, d_out_rows,
+                                            d_out_dist, d_out_count);
+  count_launch(c->ctx);
+  SDB_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
+
+}  // namespace sdb

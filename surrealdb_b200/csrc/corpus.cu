@@ -1,0 +1,109 @@
+// corpus.cu -- device-resident vector column: per-row exact magnitudes, screening norms, bf16 screen
+// copy, special-row list.  Data layout in HBM:
+//   rows   [cap][dim]        f32|f64  master copy (exact re-rank reads it; the SIMT screen streams it)
+//   bf16   [cap][dim_pad]    bf16     screen copy, K-major rows = tcgen05 "B" operand via TMA
+//   mag    [cap]             f64      sqrt(sum x^2), the reference's `magnitude()` arithmetic
+//   snorm  [cap]             f32      cosine: 1/|x|, euclid: |x|^2, NaN => row never screened in
+#include "internal.cuh"
+#include "rowwalk.cuh"
+
+namespace sdb {
+
+// magnitude_squared: v.iter().map(|a| a.to_float().powi(2)).sum::<f64>()   fnc/util/math/vector.rs:301-303
+template <typename T, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) finalize_rows_kernel(const T* __restrict__ rows, uint32_t dim, uint64_t n,
+                                                            int metric, const uint8_t* __restrict__ skip,
+                                                            double* __restrict__ mag, float* __restrict__ snorm,
+                                                            uint32_t* __restrict__ special, uint32_t* special_cnt,
+                                                            uint32_t* max_norm_bits) {
+  __shared__ T tile[WARPS][32][33];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint64_t warps_total = (uint64_t)gridDim.x * WARPS;
+  for (uint64_t base = ((uint64_t)blockIdx.x * WARPS + warp) * 32; base < n; base += warps_total * 32) {
+    const uint64_t r = base + lane;
+    const uint32_t my_row = r < n ? (uint32_t)r : NO_ROW;
+    double s = 0.0;
+    warp_walk_rows<T>(rows, dim, my_row, tile[warp], [&](uint32_t, T x) {
+      const double xd = (double)x;
+      s = __dadd_rn(s, __dmul_rn(xd, xd));
+    });
+    if (my_row == NO_ROW) continue;
+    const double m = __dsqrt_rn(s);
+    mag[r] = m;
+    const bool skipped = skip && skip[r];
+    float sn;
+    bool is_special;
+    if (metric == SDB_COSINE) {
+      is_special = !(m > 0.0) || !isfinite(m);  // zero / NaN / inf norm: distance is NaN or needs exact care
+      sn = (float)(1.0 / m);
+    } else {
+      is_special = !isfinite(s);
+      sn = (float)s;
+      if (!isfinite(sn)) is_special = true;  // |x|^2 overflows f32: rank exactly
+    }
+    if (skipped) {
+      sn = __int_as_float(0x7fc00000);
+    } else if (is_special) {
+      sn = __int_as_float(0x7fc00000);
+      const uint32_t pos = atomicAdd(special_cnt, 1u);
+      if (pos < (uint32_t)SPECIAL_CAP) special[pos] = (uint32_t)r;
+    } else {
+      atomicMax(max_norm_bits, __float_as_uint((float)m) + 1u);  // +1 ulp: upper bound after rounding
+    }
+    snorm[r] = sn;
+  }
+}
+
+__global__ void to_bf16_kernel(const float* __restrict__ rows, uint32_t dim, uint32_t dim_pad, uint64_t n,
+                               uint64_t n_pad, __nv_bfloat16* __restrict__ out) {
+  const uint64_t total = n_pad * dim_pad;
+  const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+    const uint64_t r = i / dim_pad;
+    const uint32_t c = (uint32_t)(i % dim_pad);
+    float v = (r < n && c < dim) ? rows[r * dim + c] : 0.f;
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+sdb_status corpus_finalize_device(Corpus* c) {
+  Ctx* ctx = c->ctx;
+  cudaStream_t st = ctx->stream;
+  uint32_t* d_tmp = nullptr;  // [0] special count, [1] max-norm bits
+  SDB_CUDA(cudaMalloc(&d_tmp, 8));
+  SDB_CUDA(cudaMemsetAsync(d_tmp, 0, 8, st));
+  if (!c->d_special) SDB_CUDA(cudaMalloc(&c->d_special, sizeof(uint32_t) * SPECIAL_CAP));
+  if (c->n) {
+    const int grid = ctx->sm_count * 8;
+    if (c->dtype == SDB_F32)
+      finalize_rows_kernel<float, 8><<<grid, 256, 0, st>>>((const float*)c->d_rows, c->dim, c->n, (int)c->metric,
+                                                        c->d_skip, c->d_mag, c->d_snorm, c->d_special, d_tmp,
+                                                        d_tmp + 1);
+    else
+      finalize_rows_kernel<double, 4><<<grid * 2, 128, 0, st>>>((const double*)c->d_rows, c->dim, c->n, (int)c->metric,
+                                                         c->d_skip, c->d_mag, c->d_snorm, c->d_special, d_tmp,
+                                                         d_tmp + 1);
+    count_launch(ctx);
+    SDB_CUDA(cudaGetLastError());
+    if (c->dtype == SDB_F32 && c->d_bf16) {
+      const uint64_t n_pad = (c->n + TILE_ROWS - 1) / TILE_ROWS * TILE_ROWS;
+      to_bf16_kernel<<<ctx->sm_count * 16, 256, 0, st>>>((const float*)c->d_rows, c->dim, c->dim_pad, c->n,
+                                                         n_pad, c->d_bf16);
+      count_launch(ctx);
+      SDB_CUDA(cudaGetLastError());
+    }
+  }
+  uint32_t h[2] = {0, 0};
+  SDB_CUDA(cudaMemcpyAsync(h, d_tmp, 8, cudaMemcpyDeviceToHost, st));
+  SDB_CUDA(cudaStreamSynchronize(st));
+  SDB_CUDA(cudaFree(d_tmp));
+  c->special_overflow = h[0] > (uint32_t)SPECIAL_CAP;
+  c->n_special = h[0] > (uint32_t)SPECIAL_CAP ? (uint32_t)SPECIAL_CAP : h[0];
+  float mn;
+  memcpy(&mn, &h[1], 4);
+  c->max_norm = mn;
+  c->finalized = true;
+  return SDB_OK;
+}
+
+}  // namespace sdb

@@ -1,0 +1,262 @@
+// exact.cu -- KX: exact brute force for ONE query over the whole corpus, in the reference's own f64
+// arithmetic (fnc/util/math/vector.rs:65-83,279-314), followed by an exact radix selection of the k
+// smallest (distance key, scan position) pairs.  Used for
+//   * F64 corpora and SDB_SCREEN_NONE_EXACT,
+//   * queries the screens cannot bound (zero / non-finite query norm),
+//   * queries whose screened result failed the error-bound proof or overflowed its candidate buffer.
+// It never approximates, so the library's answer does not depend on the screens being right.
+#include "exactmath.cuh"
+#include "internal.cuh"
+#include "rowwalk.cuh"
+
+namespace sdb {
+
+constexpr uint32_t EX_QCHUNK = 1024;
+constexpr uint64_t KEY_SKIPPED = ~0ull;  // never produced by dist_key(canonical value)
+
+template <typename T, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) exact_keys_kernel(const T* __restrict__ rows, uint32_t dim, uint64_t n,
+                                                                int metric, const double* __restrict__ mag,
+                                                                const uint8_t* __restrict__ skip,
+                                                                const double* __restrict__ q64 /* this query */,
+                                                                const double* __restrict__ qmag_p,
+                                                                const uint32_t* __restrict__ qflags_p,
+                                                                uint64_t* __restrict__ keys) {
+  __shared__ T tile[WARPS][32][33];
+  __shared__ double s_q[EX_QCHUNK];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool q_nan = (*qflags_p & 2u) != 0;
+  const double qm = *qmag_p;
+  const uint64_t rows_per_block = (uint64_t)WARPS * 32;
+  for (uint64_t b0 = (uint64_t)blockIdx.x * rows_per_block; b0 < n; b0 += (uint64_t)gridDim.x * rows_per_block) {
+    const uint64_t r = b0 + warp * 32 + lane;
+    const uint32_t my_row = r < n ? (uint32_t)r : NO_ROW;
+    ExactAcc acc;
+    for (uint32_t cb = 0; cb < dim; cb += EX_QCHUNK) {
+      const uint32_t cw = dim - cb < EX_QCHUNK ? dim - cb : EX_QCHUNK;
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < cw; i += blockDim.x) s_q[i] = q64[cb + i];
+      __syncthreads();
+      const T* base = rows + cb;
+      for (uint32_t c0 = 0; c0 < cw; c0 += 32) {
+        const uint32_t c = c0 + lane;
+#pragma unroll 8
+        for (int rr = 0; rr < 32; rr++) {
+          const uint32_t row = __shfl_sync(0xffffffffu, my_row, rr);
+          T v = T(0);
+          if (row != NO_ROW && c < cw) v = __ldg(base + (size_t)row * dim + c);
+          tile[warp][rr][lane] = v;
+        }
+        __syncwarp();
+        if (my_row != NO_ROW) {
+          const uint32_t lim = cw - c0 < 32u ? cw - c0 : 32u;
+          if (metric == SDB_COSINE) {
+            for (uint32_t j = 0; j < lim; j++) acc.cosine_step((double)tile[warp][lane][j], s_q[c0 + j]);
+          } else {
+            for (uint32_t j = 0; j < lim; j++) acc.euclid_step((double)tile[warp][lane][j], s_q[c0 + j]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (my_row != NO_ROW) {
+      uint64_t key;
+      if (skip && skip[r]) key = KEY_SKIPPED;
+      else {
+        const double d = metric == SDB_COSINE ? cosine_finish(acc, mag[r], qm, q_nan) : euclid_finish(acc, q_nan);
+        key = dist_key(d);
+      }
+      keys[r] = key;
+    }
+  }
+}
+
+// ---- exact radix select over the 96-bit composite (key, row), MSB first, 12 passes of 8 bits --------
+struct SelState {
+  uint64_t prefix_key;
+  uint32_t prefix_row;
+  uint32_t remaining;  // rank (1-based) still to locate inside the current prefix bucket
+  uint32_t k_eff;      // min(k, #valid rows)
+  uint32_t out_count;  // gather cursor
+  uint32_t hist[256];
+};
+
+__global__ void sel_init_kernel(SelState* st, uint32_t k) {
+  if (threadIdx.x == 0) {
+    st->prefix_key = 0;
+    st->prefix_row = 0;
+    st->remaining = k;
+    st->k_eff = k;
+    st->out_count = 0;
+  }
+  st->hist[threadIdx.x] = 0;
+}
+
+__global__ void __launch_bounds__(256) sel_hist_kernel(const uint64_t* __restrict__ keys, uint64_t n, uint32_t pass,
+                                                       SelState* st) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  if (st->k_eff != 0) {
+    const uint64_t pk = st->prefix_key;
+    const uint32_t pr = st->prefix_row;
+    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+      const uint64_t key = keys[i];
+      if (key == KEY_SKIPPED) continue;
+      uint32_t digit;
+      bool match;
+      if (pass < 8) {
+        const uint64_t hi_mask = pass == 0 ? 0ull : (~0ull << (64 - 8 * pass));
+        match = ((key ^ pk) & hi_mask) == 0;
+        digit = (uint32_t)(key >> (56 - 8 * pass)) & 255u;
+      } else {
+        const uint32_t p = pass - 8;
+        const uint32_t rmask = p == 0 ? 0u : (~0u << (32 - 8 * p));
+        const uint32_t row = (uint32_t)i;
+        match = key == pk && ((row ^ pr) & rmask) == 0;
+        digit = (row >> (24 - 8 * p)) & 255u;
+      }
+      if (match) atomicAdd(&h[digit], 1u);
+    }
+  }
+  __syncthreads();
+  if (h[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], h[threadIdx.x]);
+}
+
+__global__ void sel_scan_kernel(SelState* st, uint32_t pass) {  // one thread: 256 bins
+  if (threadIdx.x != 0) return;
+  if (pass == 0) {
+    uint64_t total = 0;
+    for (int d = 0; d < 256; d++) total += st->hist[d];
+    if (st->remaining > total) {
+      st->remaining = (uint32_t)total;
+      st->k_eff = (uint32_t)total;
+    }
+  }
+  if (st->k_eff != 0) {
+    uint32_t cum = 0;
+    int d = 0;
+    for (; d < 256; d++) {
+      if (cum + st->hist[d] >= st->remaining) break;
+      cum += st->hist[d];
+    }
+    st->remaining -= cum;
+    if (pass < 8) st->prefix_key |= (uint64_t)d << (56 - 8 * pass);
+    else st->prefix_row |= (uint32_t)d << (24 - 8 * (pass - 8));
+  }
+  for (int d = 0; d < 256; d++) st->hist[d] = 0;
+}
+
+__global__ void __launch_bounds__(256) sel_gather_kernel(const uint64_t* __restrict__ keys, uint64_t n, SelState* st,
+                                                         uint64_t* __restrict__ g_key, uint32_t* __restrict__ g_row) {
+  if (st->k_eff == 0) return;
+  const uint64_t pk = st->prefix_key;
+  const uint32_t pr = st->prefix_row;
+  const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+    const uint64_t key = keys[i];
+    if (key == KEY_SKIPPED) continue;
+    if (key < pk || (key == pk && (uint32_t)i <= pr)) {
+      const uint32_t pos = atomicAdd(&st->out_count, 1u);
+      g_key[pos] = key;
+      g_row[pos] = (uint32_t)i;
+    }
+  }
+}
+
+// sort the k_eff gathered pairs and write the query's output row (single block)
+__global__ void __launch_bounds__(1024) sel_emit_kernel(const SelState* st, const uint64_t* __restrict__ g_key,
+                                                        const uint32_t* __restrict__ g_row, uint32_t k,
+                                                        uint64_t row_base, uint64_t* __restrict__ out_rows,
+                                                        double* __restrict__ out_dist, uint32_t* __restrict__ out_count) {
+  extern __shared__ uint64_t s_mem[];
+  const uint32_t n = st->k_eff;
+  uint32_t p2 = 1;
+  while (p2 < n) p2 <<= 1;
+  uint64_t* s_key = s_mem;
+  uint64_t* s_row = s_mem + p2;
+  for (uint32_t i = threadIdx.x; i < p2; i += blockDim.x) {
+    s_key[i] = i < n ? g_key[i] : ~0ull;
+    s_row[i] = i < n ? (uint64_t)g_row[i] : ~0ull;
+  }
+  __syncthreads();
+  for (uint32_t kk = 2; kk <= p2; kk <<= 1)
+    for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = threadIdx.x; i < p2; i += blockDim.x) {
+        const uint32_t ixj = i ^ j;
+        if (ixj > i) {
+          const uint64_t ka = s_key[i], kb = s_key[ixj], ra = s_row[i], rb = s_row[ixj];
+          const bool a_gt_b = ka > kb || (ka == kb && ra > rb);
+          const bool up = ((i & kk) == 0);
+          if (up ? a_gt_b : !a_gt_b) {
+            s_key[i] = kb; s_key[ixj] = ka;
+            s_row[i] = rb; s_row[ixj] = ra;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint64_t key = s_key[i];
+    const uint64_t bits = (key >> 63) ? (key & 0x7fffffffffffffffull) : ~key;  // invert dist_key
+    out_rows[i] = row_base + s_row[i];
+    out_dist[i] = __longlong_as_double((long long)bits);
+  }
+  if (threadIdx.x == 0) *out_count = n;
+}
+
+sdb_status exact_query(Corpus* c, uint32_t q, uint32_t k, uint64_t row_base, uint64_t* d_out_rows,
+                       double* d_out_dist, uint32_t* d_out_count, cudaStream_t st) {
+  Ctx* ctx = c->ctx;
+  if (c->ex_cap < c->n || !c->d_ex_key) {
+    cudaFree(c->d_ex_key);
+    cudaFree(c->d_sel);
+    c->d_ex_key = nullptr;
+    c->d_sel = nullptr;
+    const uint64_t cap = c->cap > c->n ? c->cap : c->n;
+    SDB_CUDA(cudaMalloc(&c->d_ex_key, sizeof(uint64_t) * (cap ? cap : 1)));
+    // SelState + gather buffers (key u64[4096], row u32[4096])
+    SDB_CUDA(cudaMalloc(&c->d_sel, sizeof(SelState) + 4096 * 12 + 64));
+    c->ex_cap = cap;
+  }
+  if (k > 4096) {
+    set_error("exact path supports k <= 4096 (got %u)", k);
+    return SDB_EUNSUPPORTED;
+  }
+  SelState* sel = reinterpret_cast<SelState*>(c->d_sel);
+  uint64_t* g_key = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(c->d_sel) + ((sizeof(SelState) + 63) / 64) * 64);
+  uint32_t* g_row = reinterpret_cast<uint32_t*>(g_key + 4096);
+  const uint64_t n = c->n;
+  if (n) {
+    const int grid = ctx->sm_count * 8;
+    if (c->dtype == SDB_F32)
+      exact_keys_kernel<float, 4><<<grid, 128, 0, st>>>((const float*)c->d_rows, c->dim, n, (int)c->metric, c->d_mag,
+                                                        c->d_skip, c->d_q64 + (size_t)q * c->dim, c->d_qmag + q,
+                                                        c->d_qflags + q, c->d_ex_key);
+    else
+      exact_keys_kernel<double, 4><<<grid, 128, 0, st>>>((const double*)c->d_rows, c->dim, n, (int)c->metric,
+                                                         c->d_mag, c->d_skip, c->d_q64 + (size_t)q * c->dim,
+                                                         c->d_qmag + q, c->d_qflags + q, c->d_ex_key);
+    count_launch(ctx);
+  }
+  sel_init_kernel<<<1, 256, 0, st>>>(sel, k);
+  count_launch(ctx);
+  const int hgrid = ctx->sm_count * 4;
+  for (uint32_t pass = 0; pass < 12; pass++) {
+    sel_hist_kernel<<<hgrid, 256, 0, st>>>(c->d_ex_key, n, pass, sel);
+    sel_scan_kernel<<<1, 32, 0, st>>>(sel, pass);
+    count_launch(ctx, 2);
+  }
+  sel_gather_kernel<<<hgrid, 256, 0, st>>>(c->d_ex_key, n, sel, g_key, g_row);
+  uint32_t p2 = 1;
+  while (p2 < k) p2 <<= 1;
+  sel_emit_kernel<<<1, 1024, sizeof(uint64_t) * 2 * p2, st>>>(sel, g_key, g_row, k, row_base,
+                                                             d_out_rows + (size_t)q * k, d_out_dist + (size_t)q * k,
+                                                             d_out_count + q);
+  count_launch(ctx, 2);
+  SDB_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
+
+}  // namespace sdb

@@ -1,0 +1,40 @@
+// exactmath.cuh -- the reference's f64 arithmetic, op for op, with explicit round-to-nearest
+// intrinsics so nvcc can never contract a*b+c into an FMA (Rust/LLVM does not fuse either).
+//   cosine  : fnc/util/math/vector.rs:65-71, 279-281, 301-314
+//   euclid  : fnc/util/math/vector.rs:288-299
+// NaN sign convention = x86-64 hardware (where the reference runs): a GENERATED NaN (0/0, inf-inf,
+// inf*0) is the negative "real indefinite" 0xFFF8000000000000 and therefore sorts FIRST under
+// Number::cmp's total_cmp; a NaN that came in through the data (Rust f64::NAN, positive) propagates
+// as a positive NaN and sorts LAST.  Mixed cases are unpinned.
+#pragma once
+#include <cstdint>
+
+namespace sdb {
+
+struct ExactAcc {
+  double acc = 0.0;
+  bool nan_in = false;
+  __device__ __forceinline__ void cosine_step(double x, double q) {
+    nan_in |= (x != x);
+    acc = __dadd_rn(acc, __dmul_rn(x, q));
+  }
+  __device__ __forceinline__ void euclid_step(double x, double q) {
+    nan_in |= (x != x);
+    const double d = __dsub_rn(x, q);
+    acc = __dadd_rn(acc, __dmul_rn(d, d));
+  }
+};
+
+__device__ __forceinline__ double canon_nan(double r, bool nan_in) {
+  if (r != r) return __longlong_as_double(nan_in ? 0x7FF8000000000000ll : (long long)0xFFF8000000000000ull);
+  return r;
+}
+__device__ __forceinline__ double cosine_finish(const ExactAcc& a, double row_mag, double q_mag, bool q_nan) {
+  const double r = __dsub_rn(1.0, __ddiv_rn(a.acc, __dmul_rn(row_mag, q_mag)));
+  return canon_nan(r, a.nan_in || q_nan);
+}
+__device__ __forceinline__ double euclid_finish(const ExactAcc& a, bool q_nan) {
+  return canon_nan(__dsqrt_rn(a.acc), a.nan_in || q_nan);
+}
+
+}  // namespace sdb

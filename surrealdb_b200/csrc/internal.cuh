@@ -1,0 +1,157 @@
+// internal.cuh -- shared declarations of the sdbgpu library (not part of the ABI).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/sdbgpu.h"
+
+namespace sdb {
+
+void set_error(const char* fmt, ...);
+
+#define SDB_CUDA(call)                                                                      \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      ::sdb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return SDB_ECUDA;                                                                     \
+    }                                                                                       \
+  } while (0)
+#define SDB_TRY(call)                  \
+  do {                                 \
+    sdb_status s__ = (call);           \
+    if (s__ != SDB_OK) return s__;     \
+  } while (0)
+
+constexpr int TILE_ROWS = 256;    // screening tile = 256 corpus rows (one tcgen05 N=256 MMA tile)
+constexpr int PASS_RATIO = 8;     // geometric threshold-refinement schedule
+constexpr int SPECIAL_CAP = 1024; // rows with zero / non-finite norm handled by exact ranking
+
+// ---- ordered keys -------------------------------------------------------------------------------
+// Number::cmp on Floats (val/number.rs:620-633): -0.0 == 0.0, otherwise f64::total_cmp.
+__host__ __device__ inline uint64_t dist_key(double d) {
+  if (d == 0.0) d = 0.0;  // canonicalise -0.0
+  uint64_t b;
+#ifdef __CUDA_ARCH__
+  b = (uint64_t)__double_as_longlong(d);
+#else
+  memcpy(&b, &d, 8);
+#endif
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__host__ __device__ inline uint32_t f32_key(float f) {  // ascending key of a finite-or-inf float
+  uint32_t b;
+#ifdef __CUDA_ARCH__
+  b = __float_as_uint(f);
+#else
+  memcpy(&b, &f, 4);
+#endif
+  return (b >> 31) ? ~b : (b | 0x80000000u);
+}
+
+struct PassDesc {
+  uint32_t stride;  // tiles t = i * stride
+  uint32_t excl;    // 0: every i; else skip i % PASS_RATIO == 0 (already done by an earlier pass)
+  uint32_t count;   // number of tiles in this pass
+};
+__host__ __device__ inline uint32_t pass_tile(const PassDesc& p, uint32_t w) {
+  uint32_t i = p.excl ? (w / (PASS_RATIO - 1)) * PASS_RATIO + (w % (PASS_RATIO - 1)) + 1 : w;
+  return i * p.stride;
+}
+
+struct Ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  uint64_t launches = 0;
+  std::mutex mu;
+  void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled (driver entry point), resolved lazily
+};
+
+struct Cand {  // one screened candidate
+  float score; // larger = closer
+  uint32_t row;
+};
+
+struct Corpus {
+  Ctx* ctx = nullptr;
+  uint32_t dim = 0, dim_pad = 0;  // dim_pad: bf16 screen copy row length (multiple of 64)
+  sdb_dtype dtype = SDB_F32;
+  sdb_metric metric = SDB_COSINE;
+  sdb_screen screen = SDB_SCREEN_AUTO;
+  uint64_t cap = 0, n = 0;
+  bool finalized = false;
+  void* d_rows = nullptr;           // master copy, cap x dim (f32 or f64)
+  double* d_mag = nullptr;          // exact f64 magnitude per row (reference arithmetic)
+  float* d_snorm = nullptr;         // cosine: 1/|x| ; euclid: |x|^2 ; NaN = never a screen candidate
+  __nv_bfloat16* d_bf16 = nullptr;  // screen copy cap_pad x dim_pad (rows padded to TILE_ROWS)
+  uint8_t* d_skip = nullptr;        // optional skip mask
+  uint32_t* d_special = nullptr;    // rows ranked exactly on every query
+  uint32_t n_special = 0;
+  bool special_overflow = false;
+  float max_norm = 0.f;
+  // ---- search scratch (grown on demand) ----
+  uint32_t sc_nq = 0, sc_cap = 0, sc_kp = 0;
+  double* d_q64 = nullptr;
+  float* d_q32 = nullptr;
+  __nv_bfloat16* d_qbf16 = nullptr;
+  double* d_qmag = nullptr;
+  uint32_t* d_qflags = nullptr;  // bit0: query needs the exact path; bit1: query has NaN input
+  float* d_tau = nullptr;
+  Cand* d_cand = nullptr;
+  uint32_t* d_cand_cnt = nullptr;
+  uint32_t* d_flags = nullptr;   // per query: bit0 overflow, bit1 verification failed
+  uint64_t* d_rr_key = nullptr;  // re-rank results: nq x rr_stride
+  double* d_rr_dist = nullptr;
+  uint32_t* d_rr_row = nullptr;
+  uint32_t rr_stride = 0;
+  // exact path scratch
+  uint64_t* d_ex_key = nullptr;  // N keys
+  uint32_t* d_sel = nullptr;     // radix-select state
+  uint64_t ex_cap = 0;
+  // host-entry staging
+  uint64_t* d_out_rows = nullptr;
+  double* d_out_dist = nullptr;
+  uint32_t* d_out_count = nullptr;
+  double* d_in_q = nullptr;
+  size_t out_cap = 0, out_cap_q = 0;
+  sdb_knn_stats stats{};
+  std::mutex mu;
+};
+
+// ---- launch wrappers (defined in the .cu files) ---------------------------------------------------
+// corpus.cu
+sdb_status corpus_finalize_device(Corpus* c);
+// screen_simt.cu
+sdb_status screen_simt_pass(Corpus* c, uint32_t nq, const PassDesc& p, cudaStream_t st);
+// screen_tc.cu
+sdb_status screen_tc_pass(Corpus* c, uint32_t nq, const PassDesc& p, cudaStream_t st);
+bool screen_tc_available();
+// candidates.cu
+sdb_status scratch_for(Corpus* c, uint32_t nq, uint32_t cap, uint32_t kp);
+sdb_status prep_queries(Corpus* c, const double* d_queries, uint32_t nq, cudaStream_t st);
+sdb_status cand_reset(Corpus* c, uint32_t nq, cudaStream_t st);
+sdb_status cand_compact(Corpus* c, uint32_t nq, uint32_t kp, cudaStream_t st);
+sdb_status cand_rerank(Corpus* c, uint32_t nq, cudaStream_t st);
+sdb_status cand_final(Corpus* c, uint32_t nq, uint32_t k, uint32_t kp, float eps_rel, uint64_t row_base,
+                      uint64_t* d_out_rows, double* d_out_dist, uint32_t* d_out_count, cudaStream_t st);
+// exact.cu
+sdb_status exact_query(Corpus* c, uint32_t q, uint32_t k, uint64_t row_base, uint64_t* d_out_rows,
+                       double* d_out_dist, uint32_t* d_out_count, cudaStream_t st);
+// gen.cu
+sdb_status gen_fill_f32(Ctx* ctx, float* d_out, uint64_t seed, uint64_t first, uint64_t n, cudaStream_t st);
+
+inline void count_launch(Ctx* ctx, uint64_t n = 1) { ctx->launches += n; }
+
+}  // namespace sdb
+
+struct sdb_ctx : sdb::Ctx {};
+struct sdb_corpus : sdb::Corpus {};

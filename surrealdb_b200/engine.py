@@ -1,0 +1,131 @@
+"""Thin object wrappers over the C ABI handles (sdb_ctx, sdb_corpus)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+class Context:
+    """sdb_ctx: one CUDA device."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        L.check(L.lib().sdb_ctx_create(device, C.byref(self.h)))
+        self.device = device
+
+    def stream(self):
+        """raw cudaStream_t (int) all kernels of this context run on"""
+        return int(L.lib().sdb_ctx_stream(self.h) or 0)
+
+    def kernel_launches(self):
+        return int(L.lib().sdb_ctx_kernel_launches(self.h))
+
+    def close(self):
+        if self.h:
+            L.lib().sdb_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class VectorColumn:
+    """sdb_corpus: device-resident N x D column of one vector field, in scan order."""
+
+    def __init__(self, ctx, dim, metric="COSINE", dtype="F32", capacity=1 << 20):
+        self.ctx, self.dim, self.metric, self.dtype = ctx, int(dim), metric.upper(), dtype.upper()
+        self.h = C.c_void_p()
+        L.check(L.lib().sdb_corpus_create(ctx.h, self.dim, L.DTYPE[self.dtype], L.METRIC[self.metric],
+                                          int(capacity), C.byref(self.h)))
+
+    def __len__(self):
+        return int(L.lib().sdb_corpus_rows(self.h))
+
+    def append(self, rows):
+        npdt = np.float32 if self.dtype == "F32" else np.float64
+        rows = np.ascontiguousarray(rows, npdt)
+        if rows.ndim != 2 or rows.shape[1] != self.dim:
+            raise L.SdbError(L.SDB_EDIM, f"rows must be (n, {self.dim})")
+        L.check(L.lib().sdb_corpus_append(self.h, _ptr(rows), rows.shape[0]))
+
+    def append_device(self, dev_ptr, n):
+        L.check(L.lib().sdb_corpus_append_device(self.h, C.c_void_p(dev_ptr), int(n)))
+
+    def append_synthetic(self, seed, first_row, n):
+        L.check(L.lib().sdb_corpus_append_synthetic(self.h, int(seed), int(first_row), int(n)))
+
+    def set_skip(self, skip):
+        if skip is None:
+            L.check(L.lib().sdb_corpus_set_skip(self.h, None, 0))
+        else:
+            s = np.ascontiguousarray(skip, np.uint8)
+            L.check(L.lib().sdb_corpus_set_skip(self.h, _ptr(s), s.size))
+
+    def finalize(self):
+        L.check(L.lib().sdb_corpus_finalize(self.h))
+
+    def set_screen(self, name):
+        L.check(L.lib().sdb_corpus_set_screen(self.h, L.SCREEN[name.upper()]))
+
+    def knn(self, queries, k, cancel_flag=None):
+        """queries (nq, dim) float64 -> (rows u64 (nq,k), dist f64 (nq,k), count u32 (nq,))"""
+        q = np.ascontiguousarray(queries, np.float64)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.shape[1] != self.dim:
+            # Error::InvalidVectorDimension analogue; KnnTopK itself never raises it (it skips rows), the
+            # HNSW path does (idx/trees/vector.rs:643-652)
+            raise L.SdbError(L.SDB_EDIM, f"query dimension {q.shape[1]} != {self.dim}")
+        nq = q.shape[0]
+        rows = np.zeros((nq, max(k, 1)), np.uint64)
+        dist = np.zeros((nq, max(k, 1)), np.float64)
+        cnt = np.zeros(nq, np.uint32)
+        cf = None if cancel_flag is None else C.c_void_p(cancel_flag.ctypes.data)
+        L.check(L.lib().sdb_knn_bruteforce(self.h, _ptr(q), nq, int(k), _ptr(rows), _ptr(dist), _ptr(cnt), cf))
+        return rows[:, :k], dist[:, :k], cnt
+
+    def knn_device(self, d_queries, nq, k, row_base, d_out_rows, d_out_dist, d_out_count):
+        """all arguments are raw device pointers (ints); results complete on return."""
+        L.check(L.lib().sdb_knn_bruteforce_device(self.h, C.c_void_p(d_queries), int(nq), int(k), int(row_base),
+                                                  C.c_void_p(d_out_rows), C.c_void_p(d_out_dist),
+                                                  C.c_void_p(d_out_count)))
+
+    def stats(self):
+        s = L.KnnStats()
+        L.check(L.lib().sdb_knn_last_stats(self.h, C.byref(s)))
+        return {f[0]: getattr(s, f[0]) for f in L.KnnStats._fields_}
+
+    def close(self):
+        if self.h:
+            L.lib().sdb_corpus_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def topk_merge_device(ctx, n_lists, nq, k, d_rows, d_dist, d_counts, d_out_rows, d_out_dist, d_out_count,
+                      stride_rows=0, stride_dist=0, stride_counts=0):
+    L.check(L.lib().sdb_topk_merge_device(ctx.h, n_lists, nq, k, C.c_void_p(d_rows), C.c_void_p(d_dist),
+                                          C.c_void_p(d_counts), stride_rows, stride_dist, stride_counts,
+                                          C.c_void_p(d_out_rows), C.c_void_p(d_out_dist), C.c_void_p(d_out_count)))
+
+
+def shard_block_layout(nq, k):
+    """byte layout of one rank's result block inside the all-gather buffer:
+    rows u64[nq*k] | dist f64[nq*k] | count u32[nq] (padded to 16 bytes)."""
+    off_rows, off_dist = 0, nq * k * 8
+    off_cnt = 2 * nq * k * 8
+    size = (off_cnt + nq * 4 + 15) // 16 * 16
+    return off_rows, off_dist, off_cnt, size

@@ -1,0 +1,86 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol that
+include/sdbgpu.h declares, and refuses to compute without a GPU (no silent CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ensure_built():
+    import __graft_entry__ as g
+    so = os.path.join(ROOT, "surrealdb_b200", "csrc", "libsdbgpu.so")
+    if not os.path.exists(so):
+        g.build()
+    return so
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "sdbgpu.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(sdb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    so = _ensure_built()
+    lib = C.CDLL(so)
+    syms = header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/sdbgpu.h but not exported"
+
+
+def test_python_binding_lists_the_same_symbols():
+    _ensure_built()
+    from surrealdb_b200 import _lib
+    assert sorted(_lib.ABI_SYMBOLS) == header_symbols()
+    _lib.lib()  # argtypes resolve
+
+
+def test_no_cpu_fallback_without_gpu():
+    _ensure_built()
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from surrealdb_b200 import Context, SdbError
+    with pytest.raises(SdbError) as e:
+        Context(0)
+    assert "SDB_ECUDA" in str(e.value)
+
+
+def test_pass_schedule_covers_every_tile_once():
+    # host logic of the threshold-refinement schedule (csrc/api.cu build_passes / internal.cuh pass_tile)
+    R, TILE = 8, 256
+
+    def build(n_rows, cap):
+        T = (n_rows + TILE - 1) // TILE
+        if T == 0:
+            return []
+        max0 = cap // TILE
+        stride = 1
+        while (T + stride - 1) // stride > max0:
+            stride *= R
+        passes = [(stride, 0, (T + stride - 1) // stride)]
+        s = stride // R
+        while s >= 1:
+            M = (T + s - 1) // s
+            passes.append((s, 1, M - (M + R - 1) // R))
+            if s == 1:
+                break
+            s //= R
+        return passes
+
+    def tile(p, w):
+        stride, excl, _ = p
+        i = (w // (R - 1)) * R + (w % (R - 1)) + 1 if excl else w
+        return i * stride
+
+    for n_rows in (1, 255, 256, 257, 4096 * 256, 4096 * 256 + 1, 1_000_000, 10_000_000):
+        T = (n_rows + TILE - 1) // TILE
+        seen = []
+        for p in build(n_rows, 4096):
+            seen += [tile(p, w) for w in range(p[2])]
+        assert sorted(seen) == list(range(T)), n_rows
+        assert build(n_rows, 4096)[0][2] * TILE <= 4096

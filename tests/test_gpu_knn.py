@@ -1,0 +1,187 @@
+"""Parity of the CUDA brute-force KNN path (through the C ABI) with the CPU oracle: returned rows,
+their order and the f64 distances must be IDENTICAL (bit-exact), for every screen."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from surrealdb_b200 import Context
+    return Context(0)
+
+
+def make_col(ctx, corpus, metric, skip=None, screen=None):
+    from surrealdb_b200 import VectorColumn
+    dt = "F32" if corpus.dtype == np.float32 else "F64"
+    col = VectorColumn(ctx, corpus.shape[1], metric, dt, capacity=max(1, corpus.shape[0]))
+    if corpus.shape[0]:
+        col.append(corpus)
+    if skip is not None:
+        col.set_skip(skip)
+    col.finalize()
+    if screen:
+        col.set_screen(screen)
+    return col
+
+
+def check(col, corpus, queries, metric, k, skip=None):
+    rows, dist, cnt = col.knn(queries, k)
+    for q in range(queries.shape[0]):
+        r, d = O.knn_topk(corpus, queries[q], metric.lower(), k, skip=skip)
+        assert cnt[q] == r.size, (q, cnt[q], r.size)
+        assert list(rows[q, : cnt[q]]) == list(r), (q, rows[q], r)
+        assert dist[q, : cnt[q]].tobytes() == d.tobytes(), (q, dist[q], d)  # bit-exact incl. NaN sign
+
+
+@pytest.mark.parametrize("metric", ["COSINE", "EUCLIDEAN"])
+@pytest.mark.parametrize("dim", [7, 100, 128, 768])
+@pytest.mark.parametrize("screen", ["SIMT_F32", "TC_BF16", "NONE_EXACT"])
+def test_random_parity(ctx, metric, dim, screen):
+    rng = np.random.default_rng(dim * 7 + len(metric))
+    n = 20000 if dim <= 128 else 6000
+    corpus = rng.uniform(-1, 1, (n, dim)).astype(np.float32)
+    queries = rng.uniform(-1, 1, (11, dim))
+    col = make_col(ctx, corpus, metric, screen=screen)
+    nqs = (1, 3, 11) if screen != "NONE_EXACT" else (2,)
+    for nq in nqs:
+        for k in (1, 10, 100):
+            check(col, corpus, queries[:nq], metric, k)
+    st = col.stats()
+    if screen == "NONE_EXACT":
+        assert st["n_fallback"] == 2
+
+
+def test_c1_f64_single_query(ctx):
+    # BASELINE config 0: 100k x 128, values uniform(-20,20) as f64 (reference generator range), 1 query, k=10
+    rng = np.random.default_rng(0x5DB00000)
+    corpus = rng.uniform(-20, 20, (100_000, 128))
+    q = rng.uniform(-20, 20, (1, 128))
+    for metric in ("COSINE", "EUCLIDEAN"):
+        col = make_col(ctx, corpus, metric)
+        check(col, corpus, q, metric, 10)
+
+
+def test_language_test_vectors_through_operator(ctx):
+    # language-tests/tests/language/indexes/knn/bruteforce_knn_new_executor.surql
+    from surrealdb_b200 import Distance, KnnContext, KnnTopK
+    pts = [{"id": f"pts:{i+1}", "point": p} for i, p in enumerate([[10, 0], [2, 0], [3, 0], [100, 0], [50, 0]])]
+    kc = KnnContext()
+    op = KnnTopK(pts, "point", [1, 0], 2, Distance.Euclidean, ctx=ctx).with_knn_context(kc)
+    out = op.execute()
+    assert [r["id"] for r in out] == ["pts:2", "pts:3"]
+    assert kc == {"pts:2": 1.0, "pts:3": 2.0}
+    assert op.name() == "KnnTopK"
+    assert op.attrs() == [("field", "point"), ("k", "2"), ("distance", "Euclidean"), ("dimension", "2")]
+    # hnsw_knn_new_executor.surql brute-force leg: pts:3 has no `point` at first -> skipped
+    pts = [{"id": "pts:1", "point": [1, 2, 3, 4]}, {"id": "pts:2", "point": [4, 5, 6, 7]}, {"id": "pts:3"}]
+    kc = KnnContext()
+    out = KnnTopK(pts, "point", [2, 3, 4, 5], 2, Distance.Euclidean, ctx=ctx).with_knn_context(kc).execute()
+    assert [r["id"] for r in out] == ["pts:1", "pts:2"] and kc == {"pts:1": 2.0, "pts:2": 4.0}
+    # rows with a wrong dimension / non-numeric element are skipped, never an error (knn_topk.rs:199-210)
+    pts = [{"id": "a", "v": [1.0, 1.0]}, {"id": "b", "v": [1.0]}, {"id": "c", "v": ["x", 1.0]}, {"id": "d", "v": []},
+           {"id": "e", "v": [0.5, 0.0]}]
+    out = KnnTopK(pts, "v", [0.0, 0.0], 5, Distance.Euclidean, ctx=ctx).execute()
+    assert [r["id"] for r in out] == ["e", "a"]
+
+
+def test_edge_cases(ctx):
+    rng = np.random.default_rng(4)
+    dim = 16
+    corpus = rng.uniform(-1, 1, (300, dim)).astype(np.float32)
+    queries = rng.uniform(-1, 1, (3, dim))
+    for metric in ("COSINE", "EUCLIDEAN"):
+        col = make_col(ctx, corpus, metric)
+        check(col, corpus, queries, metric, 1000)  # k > n
+        rows, dist, cnt = col.knn(queries, 0)      # k == 0
+        assert list(cnt) == [0, 0, 0]
+        skip = (rng.uniform(0, 1, 300) < 0.5).astype(np.uint8)
+        col = make_col(ctx, corpus, metric, skip=skip)
+        check(col, corpus, queries, metric, 20, skip=skip)
+        col = make_col(ctx, corpus, metric, skip=np.ones(300, np.uint8))  # everything skipped
+        rows, dist, cnt = col.knn(queries, 5)
+        assert list(cnt) == [0, 0, 0]
+    from surrealdb_b200 import VectorColumn
+    col = VectorColumn(ctx, dim, "COSINE", "F32", capacity=8)  # empty corpus
+    col.finalize()
+    rows, dist, cnt = col.knn(queries, 5)
+    assert list(cnt) == [0, 0, 0]
+
+
+def test_ties_resolved_by_scan_order(ctx):
+    rng = np.random.default_rng(5)
+    base = rng.uniform(-1, 1, (50, 32)).astype(np.float32)
+    corpus = np.concatenate([base, base, base[::-1], base])  # exact duplicates => exact distance ties
+    queries = rng.uniform(-1, 1, (9, 32))
+    for metric in ("COSINE", "EUCLIDEAN"):
+        for screen in ("SIMT_F32", "TC_BF16"):
+            col = make_col(ctx, corpus, metric, screen=screen)
+            check(col, corpus, queries, metric, 10)
+            check(col, corpus, queries[:2], metric, 57)
+
+
+def test_zero_and_nan_rows_and_queries(ctx):
+    rng = np.random.default_rng(6)
+    corpus = rng.uniform(-1, 1, (500, 24)).astype(np.float32)
+    corpus[7] = 0.0          # zero vector: cosine distance = generated NaN (negative on x86-64) -> sorts first
+    corpus[100] = 0.0
+    corpus[33, 5] = np.nan   # data NaN (positive) -> sorts last
+    corpus[44, 0] = np.inf
+    queries = rng.uniform(-1, 1, (4, 24))
+    queries[1] = 0.0         # zero query: every cosine distance is NaN -> first k rows in scan order
+    queries[2, 3] = np.nan
+    for metric in ("COSINE", "EUCLIDEAN"):
+        for screen in ("SIMT_F32", "TC_BF16"):
+            col = make_col(ctx, corpus, metric, screen=screen)
+            check(col, corpus, queries, metric, 10)
+            check(col, corpus, queries, metric, 499)
+
+
+def test_adversarial_cluster_forces_exact_fallback(ctx):
+    # near-duplicate rows: the bf16/f32 screens cannot separate them, the proof fails and the exact kernel
+    # must take over -- results still identical to the oracle.
+    rng = np.random.default_rng(8)
+    center = rng.uniform(-1, 1, 64).astype(np.float32)
+    corpus = (center[None, :] + rng.normal(0, 1e-6, (30000, 64))).astype(np.float32)
+    queries = (center[None, :] + rng.normal(0, 1e-3, (12, 64))).astype(np.float64)
+    for screen in ("SIMT_F32", "TC_BF16"):
+        col = make_col(ctx, corpus, "COSINE", screen=screen)
+        check(col, corpus, queries, "COSINE", 10)
+    col = make_col(ctx, corpus, "EUCLIDEAN", screen="TC_BF16")
+    check(col, corpus, queries, "EUCLIDEAN", 10)
+
+
+def test_synthetic_generator_matches_oracle(ctx):
+    from surrealdb_b200 import VectorColumn
+    n, dim = 5000, 96
+    col = VectorColumn(ctx, dim, "COSINE", "F32", capacity=n)
+    col.append_synthetic(seed=77, first_row=1000, n=n)  # rows 1000.. of the global synthetic corpus
+    col.finalize()
+    corpus = O.gen_f32(77, 1000 * dim, n * dim).reshape(n, dim)
+    queries = O.gen_f32(78, 0, 5 * dim).reshape(5, dim).astype(np.float64)
+    check(col, corpus, queries, "COSINE", 10)
+
+
+def test_full_size_c2_sample_queries(ctx):
+    # BASELINE config 1 shape (1M x 768 f32, batch cosine k=10): full-size corpus on the GPU; the oracle
+    # checks a sample of the batch (one query costs it ~2 s), every query is checked for the
+    # size-independent properties (sorted, unique rows, count == k).
+    from surrealdb_b200 import VectorColumn
+    n, dim, nq, k = 1_000_000, 768, 64, 10
+    col = VectorColumn(ctx, dim, "COSINE", "F32", capacity=n)
+    col.append_synthetic(seed=0x5DB00001, first_row=0, n=n)
+    col.finalize()
+    queries = O.gen_f32(0x5DB0FFFF, 0, nq * dim).reshape(nq, dim).astype(np.float64)
+    rows, dist, cnt = col.knn(queries, k)
+    assert (cnt == k).all()
+    assert (np.diff(dist, axis=1) >= 0).all()
+    assert all(len(set(r)) == k for r in rows.tolist())
+    corpus = O.gen_f32(0x5DB00001, 0, n * dim).reshape(n, dim)
+    for q in (0, 31, 63):
+        r, d = O.knn_topk(corpus, queries[q], "cosine", k)
+        assert list(rows[q]) == list(r) and dist[q].tobytes() == d.tobytes()
+    rows1, dist1, _ = col.knn(queries[:3], k)  # streaming SIMT screen on the same corpus
+    assert rows1.tobytes() == rows[:3].tobytes() and dist1.tobytes() == dist[:3].tobytes()
