@@ -91,16 +91,15 @@ def cpu_sample(rows_total, dim, budget_s, threads):
     """bounded sample of the workload for the CPU arm: the first 262144 rows, and as many queries (a multiple
     of the thread count) as fit the time budget"""
     from surrealdb_b200.synthetic import gen_f32
-    per_row_s = 2.0e-6 * (dim / 768.0)  # measured: ~2 us per (query, row) per core for the f64 Number path
     sample_rows = int(min(rows_total, 262_144))
-    nq = int(max(1, round(budget_s / (sample_rows * per_row_s)))) * threads
+    nq = None  # decided by cpu_baseline's calibration run
     corpus = np.empty((sample_rows, dim), np.float32)
     step = 1 << 16
     for r0 in range(0, sample_rows, step):
         r1 = min(sample_rows, r0 + step)
         corpus[r0:r1] = gen_f32(SEED_CORPUS, r0 * dim, (r1 - r0) * dim).reshape(r1 - r0, dim)
-    queries = gen_f32(SEED_QUERY, 0, nq * dim).reshape(nq, dim).astype(np.float64)
-    return corpus, queries
+    queries = gen_f32(SEED_QUERY, 0, 64 * threads * dim).reshape(64 * threads, dim).astype(np.float64)
+    return corpus, queries, budget_s
 
 
 def cpu_baseline(rows_total, dim, k, budget_s=15.0, threads=None, sample=None):
@@ -109,8 +108,14 @@ def cpu_baseline(rows_total, dim, k, budget_s=15.0, threads=None, sample=None):
     sample; per-query cost is linear in rows, so the figure is scaled by sample_rows / rows_total."""
     from oracle import pyoracle as O
     threads = threads or os.cpu_count() or 1
-    corpus, queries = sample if sample is not None else cpu_sample(rows_total, dim, budget_s, threads)
-    sample_rows, nq = corpus.shape[0], queries.shape[0]
+    corpus, queries, budget_s = sample if sample is not None else cpu_sample(rows_total, dim, budget_s, threads)
+    sample_rows = corpus.shape[0]
+    t0 = time.perf_counter()  # calibration: one query per thread tells how many rounds fit the budget
+    O.knn_topk_batch(corpus, queries[:threads], "cosine", k, threads)
+    t_cal = time.perf_counter() - t0
+    rounds = int(max(1, min(64, budget_s // max(t_cal, 1e-3))))
+    nq = rounds * threads
+    queries = queries[:nq]
     t0 = time.perf_counter()
     O.knn_topk_batch(corpus, queries, "cosine", k, threads)
     dt = time.perf_counter() - t0

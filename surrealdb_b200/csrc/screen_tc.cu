@@ -1,9 +1,319 @@
-// screen_tc.cu -- K2: tcgen05 bf16 GEMM screen (placeholder until the kernel lands).
+// screen_tc.cu -- K2: tcgen05 bf16 GEMM screen with a fused threshold-filter epilogue (sm_100a only).
+//
+//   scores[q][x] = <q~, x~>  (bf16 operands, fp32 accumulation in TMEM), q = queries (M), x = corpus rows (N)
+//
+// One CTA = one SM, persistent over work items (corpus tile of 256 rows) x (block of 128 queries):
+//   warp 0      TMA producer : cp.async.bulk.tensor 2-D tiles (SWIZZLE_128B) of A (128 x 64) and B (256 x 64)
+//                              into a 4-stage shared-memory ring, completion on mbarriers
+//   warp 1      MMA issuer   : one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16)
+//                              accumulating into one of two 256-column TMEM stages; tcgen05.commit frees the
+//                              smem stage / publishes the accumulator
+//   warps 2..5  epilogue     : tcgen05.ld the accumulator (thread = query, 256 columns = corpus rows), scale by
+//                              the row's screening norm, compare with the query's threshold tau and append the
+//                              rare survivors to the query's candidate list -- the 128 x 256 score tile is never
+//                              written to memory (at 1024 x 10M it would be 41 GB).
+// The epilogue of tile i overlaps the MMAs of tile i+1 through the two TMEM stages.
+//
+// Replaces, as the *screen*, the distance loop of KnnTopK::execute (exec/operators/knn_topk.rs:185-228);
+// exactness is restored by candidates.cu (f64 re-rank + error-bound proof) and exact.cu.
+#include <cuda.h>
+
 #include "internal.cuh"
+
 namespace sdb {
-bool screen_tc_available() { return false; }
-sdb_status screen_tc_pass(Corpus*, uint32_t, const PassDesc&, cudaStream_t) {
-  set_error("tcgen05 screen not built");
-  return SDB_EUNSUPPORTED;
+
+namespace tc {
+constexpr uint32_t BLOCK_M = 128;   // queries per work item
+constexpr uint32_t BLOCK_N = 256;   // corpus rows per work item (= TILE_ROWS)
+constexpr uint32_t BLOCK_K = 64;    // bf16 elements per smem stage row = 128 bytes = one swizzle atom
+constexpr uint32_t UMMA_K = 16;
+constexpr uint32_t STAGES = 4;
+constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KB
+constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr uint32_t ACC_STAGES = 2;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t THREADS = 192;
+constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + ACC_STAGES * BLOCK_N * 4 + 256 + 1024;  // + align slack
+static_assert(BLOCK_N == TILE_ROWS, "screen tile must match the pass schedule tile");
+
+// instruction descriptor (cute::UMMA::InstrDescriptor bit layout): D=f32, A=B=bf16, both K-major
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((BLOCK_N >> 3) << 17) | ((BLOCK_M >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t c0, uint32_t c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);  // start address
+  d |= (uint64_t)1 << 16;                  // leading byte offset (unused for swizzled K-major; canonical 1)
+  d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset: next 8-row core-matrix group
+  d |= (uint64_t)1 << 46;                  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const float* __restrict__ snorm, uint32_t k_blocks, uint32_t n_mblocks, uint32_t nq, int metric,
+                 PassDesc pass, const float* __restrict__ tau, Cand* __restrict__ cand,
+                 uint32_t* __restrict__ cand_cnt, uint32_t cap) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operand tiles need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;                                  // [STAGES][128][64] bf16
+  uint8_t* smem_b = smem + STAGES * A_BYTES;               // [STAGES][256][64] bf16
+  float* s_snorm = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);  // [ACC_STAGES][256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_snorm + ACC_STAGES * BLOCK_N);
+  uint64_t* full_bar = bars;                      // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;            // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;        // [ACC_STAGES]
+  uint64_t* tempty_bar = bars + 2 * STAGES + ACC_STAGES;  // [ACC_STAGES]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES);
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t n_items = pass.count * n_mblocks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (uint32_t s = 0; s < STAGES; s++) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (uint32_t a = 0; a < ACC_STAGES; a++) {
+      mbar_init(smem_u32(&tfull_bar[a]), 1);
+      mbar_init(smem_u32(&tempty_bar[a]), 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM allocation (whole warp), address lands in shared memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const uint32_t tile = pass_tile(pass, w / n_mblocks);
+        const uint32_t mb = w % n_mblocks;
+        for (uint32_t kb = 0; kb < k_blocks; kb++, it++) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[s]);
+          mbar_expect_tx(fb, STAGE_BYTES);
+          tma_load_2d(smem_u32(smem_a + s * A_BYTES), &map_a, kb * BLOCK_K, mb * BLOCK_M, fb);
+          tma_load_2d(smem_u32(smem_b + s * B_BYTES), &map_b, kb * BLOCK_K, tile * BLOCK_N, fb);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t it = 0, j = 0;
+      for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, j++) {
+        const uint32_t a = j % ACC_STAGES, pa = (j / ACC_STAGES) & 1;
+        mbar_wait(smem_u32(&tempty_bar[a]), pa ^ 1);  // epilogue has drained this accumulator stage
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + a * BLOCK_N;
+        for (uint32_t kb = 0; kb < k_blocks; kb++, it++) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(smem_u32(&full_bar[s]), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = make_desc(smem_u32(smem_a + s * A_BYTES));
+          const uint64_t db = make_desc(smem_u32(smem_b + s * B_BYTES));
+#pragma unroll
+          for (uint32_t k = 0; k < BLOCK_K / UMMA_K; k++) {
+            // advance 32 bytes (16 bf16) inside the 128-byte swizzle atom: +2 in the (>>4) start-address field
+            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0);
+          }
+          umma_commit(smem_u32(&empty_bar[s]));  // smem stage reusable once these MMAs retire
+        }
+        umma_commit(smem_u32(&tfull_bar[a]));  // accumulator complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (4 warps, thread = query row of the tile) =====================
+    const uint32_t wq = warp & 3;            // TMEM lane quarter this warp may access
+    const uint32_t row_in_tile = wq * 32 + lane;
+    const uint32_t et = threadIdx.x - 64;    // 0..127
+    uint32_t j = 0;
+    for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, j++) {
+      const uint32_t tile = pass_tile(pass, w / n_mblocks);
+      const uint32_t mb = w % n_mblocks;
+      const uint32_t a = j % ACC_STAGES, pa = (j / ACC_STAGES) & 1;
+      const uint32_t q = mb * BLOCK_M + row_in_tile;
+      const float my_tau = q < nq ? __ldg(tau + q) : __int_as_float(0x7f800000);
+      // stage this tile's screening norms (the previous user of s_snorm[a] finished two items ago, before
+      // its tempty arrive, and every epilogue thread passes the named barrier below after that)
+      float* sn = s_snorm + a * BLOCK_N;
+      const size_t row0 = (size_t)tile * BLOCK_N;
+      sn[et] = __ldg(snorm + row0 + et);
+      sn[et + 128] = __ldg(snorm + row0 + 128 + et);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(smem_u32(&tfull_bar[a]), pa);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((wq * 32) << 16) + a * BLOCK_N;
+#pragma unroll 1
+      for (uint32_t c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c0, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          const float acc = __uint_as_float(v[i]);
+          const float nrm = sn[c0 + i];
+          const float s = metric == SDB_COSINE ? acc * nrm : fmaf(2.f, acc, -nrm);
+          if (s >= my_tau) {  // rare; NaN norms (skipped / special / padding rows) never pass
+            const uint32_t pos = atomicAdd(cand_cnt + q, 1u);
+            if (pos < cap) {
+              Cand cd;
+              cd.score = s;
+              cd.row = (uint32_t)(row0 + c0 + i);
+              cand[(size_t)q * cap + pos] = cd;
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[a]));
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+}  // namespace tc
+
+// ---- host side ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode(Ctx* ctx) {
+  if (!ctx->encode_tiled) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    ctx->encode_tiled = fn;
+  }
+  return reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled);
+}
+
+static sdb_status make_map(Ctx* ctx, CUtensorMap* map, const void* base, uint64_t rows, uint32_t dim_pad,
+                           uint32_t box_rows, bool stream_once) {
+  EncodeTiledFn enc = get_encode(ctx);
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled driver entry point not available");
+    return SDB_ECUDA;
+  }
+  cuuint64_t gdim[2] = {dim_pad, rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)dim_pad * 2};
+  cuuint32_t box[2] = {tc::BLOCK_K, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   stream_once ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return SDB_ECUDA;
+  }
+  return SDB_OK;
+}
+
+bool screen_tc_available() { return true; }
+
+sdb_status screen_tc_pass(Corpus* c, uint32_t nq, const PassDesc& p, cudaStream_t st) {
+  if (p.count == 0) return SDB_OK;
+  Ctx* ctx = c->ctx;
+  if (!c->d_bf16) {
+    set_error("tcgen05 screen needs the bf16 screen copy (F32 corpus)");
+    return SDB_EUNSUPPORTED;
+  }
+  const uint64_t n_pad = (c->n + TILE_ROWS - 1) / TILE_ROWS * TILE_ROWS;
+  const uint32_t nq_pad = (nq + tc::BLOCK_M - 1) / tc::BLOCK_M * tc::BLOCK_M;
+  CUtensorMap map_a, map_b;
+  SDB_TRY(make_map(ctx, &map_a, c->d_qbf16, nq_pad, c->dim_pad, tc::BLOCK_M, false));
+  SDB_TRY(make_map(ctx, &map_b, c->d_bf16, n_pad, c->dim_pad, tc::BLOCK_N, true));
+  static bool attr_set = false;
+  if (!attr_set) {
+    SDB_CUDA(cudaFuncSetAttribute(tc::screen_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    attr_set = true;
+  }
+  const uint32_t n_mblocks = nq_pad / tc::BLOCK_M;
+  const uint64_t n_items = (uint64_t)p.count * n_mblocks;
+  uint32_t grid = (uint32_t)ctx->sm_count;
+  if (grid > n_items) grid = (uint32_t)n_items;
+  tc::screen_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(map_a, map_b, c->d_snorm, c->dim_pad / tc::BLOCK_K,
+                                                                 n_mblocks, nq, (int)c->metric, p, c->d_tau, c->d_cand,
+                                                                 c->d_cand_cnt, c->sc_cap);
+  count_launch(ctx);
+  SDB_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
+
 }  // namespace sdb
