@@ -100,6 +100,16 @@ __global__ void cand_reset_kernel(float* tau, uint32_t* cnt, uint32_t* flags, ui
     flags[i] = 0;
   }
 }
+__global__ void cand_set_count_kernel(uint32_t* cnt, uint32_t nq, uint32_t value) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nq) cnt[i] = value;
+}
+sdb_status cand_set_count(Corpus* c, uint32_t nq, uint32_t value, cudaStream_t st) {
+  cand_set_count_kernel<<<(nq + 255) / 256, 256, 0, st>>>(c->d_cand_cnt, nq, value);
+  count_launch(c->ctx);
+  SDB_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
 sdb_status cand_reset(Corpus* c, uint32_t nq, cudaStream_t st) {
   cand_reset_kernel<<<(nq + 255) / 256, 256, 0, st>>>(c->d_tau, c->d_cand_cnt, c->d_flags, nq);
   count_launch(c->ctx);
@@ -134,24 +144,36 @@ __global__ void __launch_bounds__(1024) cand_compact_kernel(Cand* __restrict__ c
                                                             float* __restrict__ tau, uint32_t* __restrict__ flags,
                                                             uint32_t cap, uint32_t kp) {
   extern __shared__ uint64_t s_keys[];
+  __shared__ uint32_t s_valid;
   const uint32_t q = blockIdx.x;
   uint32_t n = cnt[q];
-  if (n <= kp && n <= cap) return;  // nothing to drop, tau unchanged (uniform per block)
   if (n > cap) {
     if (threadIdx.x == 0) flags[q] |= 1u;  // candidates were dropped: this query must be re-run exactly
     n = cap;
   }
+  if (threadIdx.x == 0) s_valid = 0;
+  __syncthreads();
   Cand* cq = cand + (size_t)q * cap;
   uint32_t p2 = 1;
   while (p2 < n) p2 <<= 1;
+  uint32_t my_valid = 0;
   for (uint32_t i = threadIdx.x; i < p2; i += blockDim.x) {
-    uint64_t key = 0;  // padding sorts last (real keys have the top bit pattern of f32_key >= 0x0080...)
-    if (i < n) key = ((uint64_t)f32_key(cq[i].score) << 32) | (uint64_t)(0xFFFFFFFFu - cq[i].row);
+    uint64_t key = 0;  // padding and NaN scores (skipped / special / padding rows written by pass 0) sort last
+    if (i < n) {
+      const float sc = cq[i].score;
+      if (sc == sc) {
+        key = ((uint64_t)f32_key(sc) << 32) | (uint64_t)(0xFFFFFFFFu - cq[i].row);
+        my_valid++;
+      }
+    }
     s_keys[i] = key;
   }
+  if (my_valid) atomicAdd(&s_valid, my_valid);
   __syncthreads();
+  const uint32_t valid = s_valid;
+  if (valid == n && n <= kp) return;  // nothing to drop, tau unchanged (uniform per block)
   bitonic_sort_u64<true>(s_keys, p2);
-  const uint32_t keep = n < kp ? n : kp;
+  const uint32_t keep = valid < kp ? valid : kp;
   for (uint32_t i = threadIdx.x; i < keep; i += blockDim.x) {
     const uint64_t key = s_keys[i];
     uint32_t fk = (uint32_t)(key >> 32);
@@ -264,7 +286,7 @@ __global__ void __launch_bounds__(1024) cand_final_kernel(
     uint32_t rr_stride, const uint32_t* __restrict__ cnt, uint32_t cap, uint32_t n_special,
     const float* __restrict__ tau, const double* __restrict__ qmag, uint32_t* __restrict__ flags, int metric,
     float eps_rel, float max_norm, uint32_t k, uint32_t kp, uint64_t row_base, uint64_t* __restrict__ out_rows,
-    double* __restrict__ out_dist, uint32_t* __restrict__ out_count) {
+    double* __restrict__ out_dist, uint32_t* __restrict__ out_count, int debug) {
   extern __shared__ uint64_t s_mem[];
   const uint32_t q = blockIdx.x;
   const uint32_t n_c = cnt[q] < cap ? cnt[q] : cap;
@@ -331,6 +353,9 @@ __global__ void __launch_bounds__(1024) cand_final_kernel(
         ok = L > 0.0 && dist_key(sqrt(L) * (1.0 - 1e-12)) > kth;
       }
       if (!ok) fl |= 2u;
+      if (debug && q == 0)
+        printf("[sdb final] q0 metric=%d tau=%g qmag=%g max_norm=%g eps_rel=%g n_e=%u kth_key=%llx ok=%d\n", metric,
+               (double)t, qm, (double)max_norm, (double)eps_rel, n_e, (unsigned long long)kth, (int)ok);
     }
     if (fl & 1u) fl |= 2u;  // overflowed candidate buffer => exact re-run
     flags[q] = fl;
@@ -350,7 +375,7 @@ sdb_status cand_final(Corpus* c, uint32_t nq, uint32_t k, uint32_t kp, float eps
   cand_final_kernel<<<nq, 1024, smem, st>>>(c->d_rr_key, c->d_rr_dist, c->d_rr_row, c->rr_stride, c->d_cand_cnt,
                                             c->sc_cap, c->n_special, c->d_tau, c->d_qmag, c->d_flags,
                                             (int)c->metric, eps_rel, c->max_norm, k, kp, row_base, d_out_rows,
-                                            d_out_dist, d_out_count);
+                                            d_out_dist, d_out_count, getenv("SDB_DEBUG") != nullptr);
   count_launch(c->ctx);
   SDB_CUDA(cudaGetLastError());
   return SDB_OK;

@@ -54,6 +54,12 @@ __global__ void __launch_bounds__(WARPS * 32) finalize_rows_kernel(const T* __re
   }
 }
 
+// rows in [n, cap_pad) are TMA padding of the last screening tile: NaN norm => never a candidate
+__global__ void pad_snorm_kernel(float* __restrict__ snorm, uint64_t n, uint64_t n_pad) {
+  const uint64_t i = n + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pad) snorm[i] = __int_as_float(0x7fc00000);
+}
+
 __global__ void to_bf16_kernel(const float* __restrict__ rows, uint32_t dim, uint32_t dim_pad, uint64_t n,
                                uint64_t n_pad, __nv_bfloat16* __restrict__ out) {
   const uint64_t total = n_pad * dim_pad;
@@ -73,6 +79,13 @@ sdb_status corpus_finalize_device(Corpus* c) {
   SDB_CUDA(cudaMalloc(&d_tmp, 8));
   SDB_CUDA(cudaMemsetAsync(d_tmp, 0, 8, st));
   if (!c->d_special) SDB_CUDA(cudaMalloc(&c->d_special, sizeof(uint32_t) * SPECIAL_CAP));
+  {
+    const uint64_t n_pad = (c->n + TILE_ROWS - 1) / TILE_ROWS * TILE_ROWS;
+    if (n_pad > c->n) {
+      pad_snorm_kernel<<<(unsigned)((n_pad - c->n + 255) / 256), 256, 0, st>>>(c->d_snorm, c->n, n_pad);
+      count_launch(ctx);
+    }
+  }
   if (c->n) {
     const int grid = ctx->sm_count * 8;
     if (c->dtype == SDB_F32)

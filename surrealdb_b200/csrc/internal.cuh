@@ -37,20 +37,27 @@ constexpr int SPECIAL_CAP = 1024; // rows with zero / non-finite norm handled by
 
 // ---- ordered keys -------------------------------------------------------------------------------
 // Number::cmp on Floats (val/number.rs:620-633): -0.0 == 0.0, otherwise f64::total_cmp.
-__host__ __device__ inline uint64_t dist_key(double d) {
-  if (d == 0.0) d = 0.0;  // canonicalise -0.0
+// All bit manipulation is done on integers obtained through an opaque move: nvcc otherwise rewrites
+// `bits(d) | signbit` into fneg(fabs(d)), implements it with a DADD, and the DADD canonicalises NaNs --
+// which silently destroyed the sign/payload of NaN distances (found on B200, round 1).
+__host__ __device__ inline uint64_t f64_bits(double d) {
   uint64_t b;
 #ifdef __CUDA_ARCH__
-  b = (uint64_t)__double_as_longlong(d);
+  asm volatile("mov.b64 %0, %1;" : "=l"(b) : "d"(d));
 #else
   memcpy(&b, &d, 8);
 #endif
+  return b;
+}
+__host__ __device__ inline uint64_t dist_key(double d) {
+  uint64_t b = f64_bits(d);
+  if ((b << 1) == 0) b = 0;  // canonicalise -0.0
   return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
-__host__ __device__ inline uint32_t f32_key(float f) {  // ascending key of a finite-or-inf float
+__host__ __device__ inline uint32_t f32_key(float f) {  // ascending key of a float (total order)
   uint32_t b;
 #ifdef __CUDA_ARCH__
-  b = __float_as_uint(f);
+  asm volatile("mov.b32 %0, %1;" : "=r"(b) : "f"(f));
 #else
   memcpy(&b, &f, 4);
 #endif
@@ -139,6 +146,7 @@ bool screen_tc_available();
 sdb_status scratch_for(Corpus* c, uint32_t nq, uint32_t cap, uint32_t kp);
 sdb_status prep_queries(Corpus* c, const double* d_queries, uint32_t nq, cudaStream_t st);
 sdb_status cand_reset(Corpus* c, uint32_t nq, cudaStream_t st);
+sdb_status cand_set_count(Corpus* c, uint32_t nq, uint32_t value, cudaStream_t st);
 sdb_status cand_compact(Corpus* c, uint32_t nq, uint32_t kp, cudaStream_t st);
 sdb_status cand_rerank(Corpus* c, uint32_t nq, cudaStream_t st);
 sdb_status cand_final(Corpus* c, uint32_t nq, uint32_t k, uint32_t kp, float eps_rel, uint64_t row_base,

@@ -8,7 +8,7 @@
 //   warp 1      MMA issuer   : one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16)
 //                              accumulating into one of two 256-column TMEM stages; tcgen05.commit frees the
 //                              smem stage / publishes the accumulator
-//   warps 2..5  epilogue     : tcgen05.ld the accumulator (thread = query, 256 columns = corpus rows), scale by
+//   warps 2..9  epilogue     : tcgen05.ld the accumulator (thread = query, 256 columns = corpus rows), scale by
 //                              the row's screening norm, compare with the query's threshold tau and append the
 //                              rare survivors to the query's candidate list -- the 128 x 256 score tile is never
 //                              written to memory (at 1024 x 10M it would be 41 GB).
@@ -33,7 +33,8 @@ constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KB
 constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr uint32_t ACC_STAGES = 2;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t THREADS = 192;
+constexpr uint32_t EPI_WARPS = 8;             // two warps per TMEM lane quarter, each takes half the columns
+constexpr uint32_t THREADS = 64 + EPI_WARPS * 32;
 constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + ACC_STAGES * BLOCK_N * 4 + 256 + 1024;  // + align slack
 static_assert(BLOCK_N == TILE_ROWS, "screen tile must match the pass schedule tile");
 
@@ -102,9 +103,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 
+template <bool COSINE>
 __global__ void __launch_bounds__(THREADS, 1)
 screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const float* __restrict__ snorm, uint32_t k_blocks, uint32_t n_mblocks, uint32_t nq, int metric,
+                 const float* __restrict__ snorm, uint32_t k_blocks, uint32_t n_mblocks, uint32_t nq,
                  PassDesc pass, const float* __restrict__ tau, Cand* __restrict__ cand,
                  uint32_t* __restrict__ cand_cnt, uint32_t cap) {
   extern __shared__ uint8_t smem_raw[];
@@ -132,7 +134,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     for (uint32_t a = 0; a < ACC_STAGES; a++) {
       mbar_init(smem_u32(&tfull_bar[a]), 1);
-      mbar_init(smem_u32(&tempty_bar[a]), 4);  // one arrive per epilogue warp
+      mbar_init(smem_u32(&tempty_bar[a]), EPI_WARPS);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -192,44 +194,68 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (4 warps, thread = query row of the tile) =====================
-    const uint32_t wq = warp & 3;            // TMEM lane quarter this warp may access
+    // ===================== epilogue (8 warps; thread = query row, warp pair splits the 256 columns) ==========
+    const uint32_t wq = warp & 3;                 // TMEM lane quarter this warp may access
+    const uint32_t half = (warp - 2) >> 2;        // 0: columns 0..127, 1: columns 128..255
     const uint32_t row_in_tile = wq * 32 + lane;
-    const uint32_t et = threadIdx.x - 64;    // 0..127
+    const uint32_t et = threadIdx.x - 64;         // 0..255
+    const bool pass0 = pass.excl == 0;            // tau = -inf everywhere: positions are deterministic, no atomics
     uint32_t j = 0;
     for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, j++) {
-      const uint32_t tile = pass_tile(pass, w / n_mblocks);
+      const uint32_t tidx = w / n_mblocks;
+      const uint32_t tile = pass_tile(pass, tidx);
       const uint32_t mb = w % n_mblocks;
       const uint32_t a = j % ACC_STAGES, pa = (j / ACC_STAGES) & 1;
       const uint32_t q = mb * BLOCK_M + row_in_tile;
       const float my_tau = q < nq ? __ldg(tau + q) : __int_as_float(0x7f800000);
-      // stage this tile's screening norms (the previous user of s_snorm[a] finished two items ago, before
-      // its tempty arrive, and every epilogue thread passes the named barrier below after that)
+      // stage this tile's screening norms (safe: every epilogue thread passed the named barrier of item j-1
+      // only after finishing item j-2, the previous user of s_snorm[a])
       float* sn = s_snorm + a * BLOCK_N;
       const size_t row0 = (size_t)tile * BLOCK_N;
       sn[et] = __ldg(snorm + row0 + et);
-      sn[et + 128] = __ldg(snorm + row0 + 128 + et);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(smem_u32(&tfull_bar[a]), pa);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + ((wq * 32) << 16) + a * BLOCK_N;
+      const uint32_t cbase = half * (BLOCK_N / 2);
+      const uint32_t taddr = tmem_base + ((wq * 32) << 16) + a * BLOCK_N + cbase;
+      Cand* my_cand = cand + (size_t)q * cap;
 #pragma unroll 1
-      for (uint32_t c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      for (uint32_t c0 = 0; c0 < BLOCK_N / 2; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float sc[32];
+        float m = __int_as_float(0xff800000);
 #pragma unroll
-        for (int i = 0; i < 32; i++) {
-          const float acc = __uint_as_float(v[i]);
-          const float nrm = sn[c0 + i];
-          const float s = metric == SDB_COSINE ? acc * nrm : fmaf(2.f, acc, -nrm);
-          if (s >= my_tau) {  // rare; NaN norms (skipped / special / padding rows) never pass
-            const uint32_t pos = atomicAdd(cand_cnt + q, 1u);
-            if (pos < cap) {
+        for (int i = 0; i < 32; i += 4) {
+          const float4 n4 = *reinterpret_cast<const float4*>(sn + cbase + c0 + i);
+          sc[i + 0] = COSINE ? __uint_as_float(v[i + 0]) * n4.x : fmaf(2.f, __uint_as_float(v[i + 0]), -n4.x);
+          sc[i + 1] = COSINE ? __uint_as_float(v[i + 1]) * n4.y : fmaf(2.f, __uint_as_float(v[i + 1]), -n4.y);
+          sc[i + 2] = COSINE ? __uint_as_float(v[i + 2]) * n4.z : fmaf(2.f, __uint_as_float(v[i + 2]), -n4.z);
+          sc[i + 3] = COSINE ? __uint_as_float(v[i + 3]) * n4.w : fmaf(2.f, __uint_as_float(v[i + 3]), -n4.w);
+          m = fmaxf(m, fmaxf(fmaxf(sc[i + 0], sc[i + 1]), fmaxf(sc[i + 2], sc[i + 3])));  // fmaxf drops NaNs
+        }
+        if (pass0) {
+          if (q < nq) {  // every (finite or NaN) score goes to its fixed slot; compaction drops the NaNs
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
               Cand cd;
-              cd.score = s;
-              cd.row = (uint32_t)(row0 + c0 + i);
-              cand[(size_t)q * cap + pos] = cd;
+              cd.score = sc[i];
+              cd.row = (uint32_t)(row0 + cbase + c0 + i);
+              my_cand[(size_t)tidx * BLOCK_N + cbase + c0 + i] = cd;
+            }
+          }
+        } else if (m >= my_tau) {  // rare: some element of this chunk survives the threshold
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            if (sc[i] >= my_tau) {
+              const uint32_t pos = atomicAdd(cand_cnt + q, 1u);
+              if (pos < cap) {
+                Cand cd;
+                cd.score = sc[i];
+                cd.row = (uint32_t)(row0 + cbase + c0 + i);
+                my_cand[pos] = cd;
+              }
             }
           }
         }
@@ -301,17 +327,24 @@ sdb_status screen_tc_pass(Corpus* c, uint32_t nq, const PassDesc& p, cudaStream_
   SDB_TRY(make_map(ctx, &map_b, c->d_bf16, n_pad, c->dim_pad, tc::BLOCK_N, true));
   static bool attr_set = false;
   if (!attr_set) {
-    SDB_CUDA(cudaFuncSetAttribute(tc::screen_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    SDB_CUDA(cudaFuncSetAttribute(tc::screen_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    SDB_CUDA(cudaFuncSetAttribute(tc::screen_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
     attr_set = true;
   }
   const uint32_t n_mblocks = nq_pad / tc::BLOCK_M;
   const uint64_t n_items = (uint64_t)p.count * n_mblocks;
   uint32_t grid = (uint32_t)ctx->sm_count;
   if (grid > n_items) grid = (uint32_t)n_items;
-  tc::screen_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(map_a, map_b, c->d_snorm, c->dim_pad / tc::BLOCK_K,
-                                                                 n_mblocks, nq, (int)c->metric, p, c->d_tau, c->d_cand,
-                                                                 c->d_cand_cnt, c->sc_cap);
+  if (c->metric == SDB_COSINE)
+    tc::screen_tc_kernel<true><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(map_a, map_b, c->d_snorm, c->dim_pad / tc::BLOCK_K,
+                                                                         n_mblocks, nq, p, c->d_tau, c->d_cand,
+                                                                         c->d_cand_cnt, c->sc_cap);
+  else
+    tc::screen_tc_kernel<false><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(map_a, map_b, c->d_snorm, c->dim_pad / tc::BLOCK_K,
+                                                                          n_mblocks, nq, p, c->d_tau, c->d_cand,
+                                                                          c->d_cand_cnt, c->sc_cap);
   count_launch(ctx);
+  if (p.excl == 0) SDB_TRY(cand_set_count(c, nq, p.count * TILE_ROWS, st));  // pass 0 wrote fixed slots
   SDB_CUDA(cudaGetLastError());
   return SDB_OK;
 }

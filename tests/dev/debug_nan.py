@@ -1,5 +1,5 @@
 import struct, sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from surrealdb_b200 import Context, VectorColumn
 rng = np.random.default_rng(6)

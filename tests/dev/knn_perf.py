@@ -16,7 +16,11 @@ for r0 in range(0, rows, 1 << 20):
 col.finalize()
 print(f"staged {rows} rows in {time.time()-t0:.2f}s", flush=True)
 dev = torch.device("cuda", 0)
-for screen, batches in (("SIMT_F32", (1, 4, 8)), ("TC_BF16", (16, 128, 1024, 4096))):
+cfgs = (("SIMT_F32", (1, 4, 8)), ("TC_BF16", (16, 128, 1024, 4096)))
+if len(sys.argv) > 3:
+    cfgs = ((sys.argv[2], (int(sys.argv[3]),)),)
+iters = int(sys.argv[4]) if len(sys.argv) > 4 else 5
+for screen, batches in cfgs:
     col.set_screen(screen)
     for b in batches:
         q = torch.from_numpy(gen_f32(99, 0, b * dim).reshape(b, dim).astype(np.float64)).to(dev)
@@ -24,12 +28,12 @@ for screen, batches in (("SIMT_F32", (1, 4, 8)), ("TC_BF16", (16, 128, 1024, 409
         o_d = torch.zeros((b, k), dtype=torch.float64, device=dev)
         o_c = torch.zeros((b,), dtype=torch.int32, device=dev)
         ms = []
-        for it in range(5):
+        for it in range(iters):
             col.knn_device(q.data_ptr(), b, k, 0, o_r.data_ptr(), o_d.data_ptr(), o_c.data_ptr())
             ms.append(col.stats())
         s = ms[-1]
-        best = min(m["total_ms"] for m in ms[1:])
-        bs = min(m["screen_ms"] for m in ms[1:])
+        best = min(m["total_ms"] for m in ms[-max(1, len(ms) - 1):])
+        bs = min(m["screen_ms"] for m in ms[-max(1, len(ms) - 1):])
         flops = 2.0 * b * rows * dim
         print(f"{screen} B={b}: total {best:.3f} ms screen {bs:.3f} ms -> {b/best*1e3:.0f} QPS, "
               f"screen {flops/bs/1e9:.1f} TFLOP/s, f32-stream-equiv {rows*dim*4*((b+7)//8 if screen=='SIMT_F32' else 1)/bs/1e6:.0f} GB/s, "
