@@ -184,10 +184,8 @@ def main():
     dev = torch.device("cuda", local)
 
     # ---- shard the corpus row-wise (contiguous blocks, tile aligned); global row id = base + local ----
-    per = (rows + world - 1) // world
-    per = (per + 255) // 256 * 256
-    base = min(rank * per, rows)
-    n_local = max(0, min(rows, base + per) - base)
+    from surrealdb_b200.sharding import shard_range
+    base, n_local = shard_range(rows, world, rank)
     ctx = Context(local)
     col = VectorColumn(ctx, dim, "COSINE", "F32", capacity=max(n_local, 1))
     chunk = 1 << 20

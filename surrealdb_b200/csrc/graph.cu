@@ -1,0 +1,431 @@
+// graph.cu -- K4: `->edge->node` expansion over device-resident CSR adjacency.
+//
+// Replaces the per-source KV prefix scans of GraphEdgeScan::execute (exec/operators/scan/graph.rs:214-279)
+// driven by LookupPart::evaluate_lookup (exec/parts/lookup.rs:139-170): for every frontier element, in
+// frontier order, emit its targets in stored (KV key) order -- duplicates kept, per-source limit honoured
+// (graph.rs:83,238,261).  Output position = exclusive prefix sum of the (limited) degrees, so the result is
+// order-identical to the reference no matter how the work is split.  The expand kernel is OUTPUT-centric
+// (each block owns a contiguous slice of the output and finds its sources by binary search), which balances
+// power-law degree distributions at warp/block level without any per-vertex special casing.
+// `+collect` (exec/operators/recursion/collect.rs:74-143) adds a first-seen de-duplication per BFS level.
+//
+// Algorithmic bytes per hop: 16|F| (two row_ptr reads per source) + 4|E_h| (col_idx) + 4|E_h| (output).
+#include "internal.cuh"
+
+namespace sdb {
+
+struct Graph {
+  Ctx* ctx = nullptr;
+  uint64_t n_rows = 0, n_edges = 0;
+  uint64_t* d_row_ptr = nullptr;
+  uint32_t* d_col_idx = nullptr;
+  std::mutex mu;
+};
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+// ---- exclusive prefix sum (u64), hierarchical ------------------------------------------------------
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out,
+                                                                 uint64_t n, uint64_t* __restrict__ tile_sums) {
+  __shared__ uint64_t s_warp[SCAN_THREADS / 32];
+  const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+  uint64_t v[SCAN_ITEMS];
+  uint64_t sum = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) {
+    v[i] = base + i < n ? in[base + i] : 0;
+    sum += v[i];
+  }
+  // inclusive scan of per-thread sums inside the block
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= (uint32_t)o) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint64_t w = lane < SCAN_THREADS / 32 ? s_warp[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < SCAN_THREADS / 32; o <<= 1) {
+      const uint64_t t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= (uint32_t)o) w += t;
+    }
+    if (lane < SCAN_THREADS / 32) s_warp[lane] = w;
+  }
+  __syncthreads();
+  uint64_t excl = inc - sum + (warp ? s_warp[warp - 1] : 0);
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) {
+    if (base + i < n) out[base + i] = excl;
+    excl += v[i];
+  }
+  if (threadIdx.x == SCAN_THREADS - 1 && tile_sums) tile_sums[blockIdx.x] = excl;
+}
+__global__ void scan_add_kernel(uint64_t* __restrict__ out, uint64_t n, const uint64_t* __restrict__ tile_off) {
+  const uint64_t i = (uint64_t)blockIdx.x * SCAN_TILE + threadIdx.x;
+  const uint64_t add = tile_off[blockIdx.x];
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    const uint64_t j = i + (uint64_t)k * SCAN_THREADS;
+    if (j < n) out[j] += add;
+  }
+}
+// out[0..n) = exclusive scan of in[0..n); *d_total = sum.  in/out may alias.
+static sdb_status exclusive_scan(Ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint64_t n, uint64_t* d_total,
+                                 cudaStream_t st) {
+  if (n == 0) {
+    SDB_CUDA(cudaMemsetAsync(d_total, 0, 8, st));
+    return SDB_OK;
+  }
+  const uint64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  uint64_t* d_sums = nullptr;
+  SDB_CUDA(cudaMallocAsync(&d_sums, sizeof(uint64_t) * (tiles + 1), st));
+  scan_tile_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(d_in, d_out, n, d_sums);
+  count_launch(ctx);
+  if (tiles > 1) {
+    SDB_TRY(exclusive_scan(ctx, d_sums, d_sums, tiles, d_total, st));
+    scan_add_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(d_out, n, d_sums);
+    count_launch(ctx);
+  } else {
+    SDB_CUDA(cudaMemcpyAsync(d_total, d_sums, 8, cudaMemcpyDeviceToDevice, st));
+  }
+  SDB_CUDA(cudaFreeAsync(d_sums, st));
+  SDB_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
+
+// ---- one hop -----------------------------------------------------------------------------------------
+__global__ void degree_kernel(const uint64_t* __restrict__ row_ptr, uint64_t n_rows, const uint32_t* __restrict__ frontier,
+                              uint64_t n_f, uint32_t limit, uint64_t* __restrict__ deg, uint32_t* __restrict__ err) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_f) return;
+  const uint32_t v = frontier[i];
+  if (v >= n_rows) {
+    *err = 1;
+    deg[i] = 0;
+    return;
+  }
+  uint64_t d = row_ptr[v + 1] - row_ptr[v];
+  if (limit && d > limit) d = limit;
+  deg[i] = d;
+}
+
+constexpr int EXP_THREADS = 256;
+constexpr int EXP_PER_THREAD = 8;
+constexpr int EXP_TILE = EXP_THREADS * EXP_PER_THREAD;  // outputs per block
+constexpr int EXP_SRC_MAX = EXP_TILE + 2;
+
+__device__ __forceinline__ uint64_t upper_bound_minus1(const uint64_t* a, uint64_t lo, uint64_t hi, uint64_t x) {
+  // largest i in [lo, hi) with a[i] <= x   (a is non-decreasing, a[lo] <= x)
+  while (hi - lo > 1) {
+    const uint64_t mid = lo + (hi - lo) / 2;
+    if (a[mid] <= x) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(EXP_THREADS) expand_kernel(const uint64_t* __restrict__ row_ptr,
+                                                             const uint32_t* __restrict__ col_idx,
+                                                             const uint32_t* __restrict__ frontier, uint64_t n_f,
+                                                             const uint64_t* __restrict__ off /* n_f + 1 */,
+                                                             uint64_t total, uint32_t* __restrict__ out) {
+  __shared__ uint64_t s_off[EXP_SRC_MAX];
+  __shared__ uint64_t s_row[EXP_SRC_MAX];
+  __shared__ uint64_t s_i0, s_i1;
+  const uint64_t o0 = (uint64_t)blockIdx.x * EXP_TILE;
+  const uint64_t o1 = o0 + EXP_TILE < total ? o0 + EXP_TILE : total;
+  if (threadIdx.x == 0) {
+    s_i0 = upper_bound_minus1(off, 0, n_f + 1, o0);
+    s_i1 = upper_bound_minus1(off, 0, n_f + 1, o1 - 1);
+  }
+  __syncthreads();
+  const uint64_t i0 = s_i0, i1 = s_i1;
+  const bool in_smem = (i1 - i0 + 2) <= (uint64_t)EXP_SRC_MAX;
+  if (in_smem) {
+    for (uint64_t t = threadIdx.x; t < i1 - i0 + 2; t += EXP_THREADS) {
+      const uint64_t i = i0 + t;
+      s_off[t] = off[i];  // i <= i1 + 1 <= n_f
+      s_row[t] = i < n_f ? row_ptr[frontier[i]] : 0;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < EXP_PER_THREAD; u++) {
+    const uint64_t o = o0 + (uint64_t)u * EXP_THREADS + threadIdx.x;  // coalesced output
+    if (o >= o1) break;
+    uint64_t src, start, rbeg;
+    if (in_smem) {
+      const uint64_t t = upper_bound_minus1(s_off, 0, i1 - i0 + 2, o);
+      src = i0 + t;
+      start = s_off[t];
+      rbeg = s_row[t];
+    } else {  // pathological: thousands of zero-degree sources inside this slice
+      src = upper_bound_minus1(off, i0, i1 + 2, o);
+      start = off[src];
+      rbeg = row_ptr[frontier[src]];
+    }
+    out[o] = __ldg(col_idx + rbeg + (o - start));
+    (void)src;
+  }
+}
+
+static sdb_status hop_device(Graph* g, const uint32_t* d_frontier, uint64_t n_f, uint32_t limit, uint32_t** d_out,
+                             uint64_t* n_out, cudaStream_t st) {
+  Ctx* ctx = g->ctx;
+  *d_out = nullptr;
+  *n_out = 0;
+  if (n_f == 0) return SDB_OK;
+  uint64_t* d_off = nullptr;
+  uint64_t* d_total = nullptr;
+  uint32_t* d_err = nullptr;
+  SDB_CUDA(cudaMallocAsync(&d_off, sizeof(uint64_t) * (n_f + 2), st));
+  d_total = d_off + n_f;  // off[n_f] = total: exactly the sentinel the expand kernel wants
+  SDB_CUDA(cudaMallocAsync(&d_err, 4, st));
+  SDB_CUDA(cudaMemsetAsync(d_err, 0, 4, st));
+  degree_kernel<<<(unsigned)((n_f + 255) / 256), 256, 0, st>>>(g->d_row_ptr, g->n_rows, d_frontier, n_f, limit, d_off, d_err);
+  count_launch(ctx);
+  SDB_TRY(exclusive_scan(ctx, d_off, d_off, n_f, d_total, st));
+  uint64_t total = 0;
+  uint32_t err = 0;
+  SDB_CUDA(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, st));
+  SDB_CUDA(cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, st));
+  SDB_CUDA(cudaStreamSynchronize(st));
+  if (err) {
+    cudaFreeAsync(d_off, st);
+    cudaFreeAsync(d_err, st);
+    set_error("graph expand: frontier id out of range (graph has %llu rows)", (unsigned long long)g->n_rows);
+    return SDB_EINVAL;
+  }
+  if (total > 0xFFFFFFF0ull) {
+    cudaFreeAsync(d_off, st);
+    cudaFreeAsync(d_err, st);
+    set_error("graph expand: %llu results exceed the 2^32 frontier limit", (unsigned long long)total);
+    return SDB_EOVERFLOW;
+  }
+  if (total) {
+    SDB_CUDA(cudaMallocAsync(d_out, sizeof(uint32_t) * total, st));
+    expand_kernel<<<(unsigned)((total + EXP_TILE - 1) / EXP_TILE), EXP_THREADS, 0, st>>>(g->d_row_ptr, g->d_col_idx, d_frontier,
+                                                                                       n_f, d_off, total, *d_out);
+    count_launch(ctx);
+  }
+  SDB_CUDA(cudaFreeAsync(d_off, st));
+  SDB_CUDA(cudaFreeAsync(d_err, st));
+  SDB_CUDA(cudaGetLastError());
+  *n_out = total;
+  return SDB_OK;
+}
+
+// ---- +collect: first-seen de-duplication of one BFS level ----------------------------------------------
+__global__ void collect_mark_kernel(const uint32_t* __restrict__ lvl, uint64_t n, const uint8_t* __restrict__ seen,
+                                    uint32_t* __restrict__ first_pos) {
+  const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const uint32_t v = lvl[p];
+  if (!seen[v]) atomicMin(first_pos + v, (uint32_t)p);
+}
+__global__ void collect_flag_kernel(const uint32_t* __restrict__ lvl, uint64_t n, const uint8_t* __restrict__ seen,
+                                    const uint32_t* __restrict__ first_pos, uint64_t* __restrict__ keep) {
+  const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const uint32_t v = lvl[p];
+  keep[p] = (!seen[v] && first_pos[v] == (uint32_t)p) ? 1 : 0;
+}
+__global__ void collect_compact_kernel(const uint32_t* __restrict__ lvl, uint64_t n, const uint64_t* __restrict__ pos /* n+1 */,
+                                       uint8_t* __restrict__ seen, uint32_t* __restrict__ first_pos,
+                                       uint32_t* __restrict__ next) {
+  const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  if (pos[p + 1] != pos[p]) {  // kept
+    const uint32_t v = lvl[p];
+    next[pos[p]] = v;
+    seen[v] = 1;
+    first_pos[v] = 0xFFFFFFFFu;
+  }
+}
+
+}  // namespace sdb
+
+struct sdb_graph : sdb::Graph {};
+using namespace sdb;
+
+extern "C" {
+
+sdb_status sdb_graph_load_csr(sdb_ctx* ctx, uint64_t n_rows, const uint64_t* row_ptr, const uint32_t* col_idx,
+                              sdb_graph** out) {
+  if (!ctx || !out || !row_ptr || n_rows >= 0xFFFFFFF0ull) return SDB_EINVAL;
+  *out = nullptr;
+  const uint64_t n_edges = row_ptr[n_rows];
+  if (n_edges && !col_idx) return SDB_EINVAL;
+  for (uint64_t i = 0; i < n_rows; i++)
+    if (row_ptr[i + 1] < row_ptr[i]) {
+      set_error("row_ptr is not non-decreasing at %llu", (unsigned long long)i);
+      return SDB_EINVAL;
+    }
+  SDB_CUDA(cudaSetDevice(ctx->device));
+  sdb_graph* g = new sdb_graph();
+  g->ctx = ctx;
+  g->n_rows = n_rows;
+  g->n_edges = n_edges;
+  cudaError_t e = cudaMalloc(&g->d_row_ptr, sizeof(uint64_t) * (n_rows + 1));
+  if (e == cudaSuccess) e = cudaMalloc(&g->d_col_idx, sizeof(uint32_t) * (n_edges ? n_edges : 1));
+  if (e != cudaSuccess) {
+    set_error("graph allocation failed: %s", cudaGetErrorString(e));
+    sdb_graph_destroy(g);
+    return SDB_ENOMEM;
+  }
+  SDB_CUDA(cudaMemcpyAsync(g->d_row_ptr, row_ptr, sizeof(uint64_t) * (n_rows + 1), cudaMemcpyHostToDevice, ctx->stream));
+  if (n_edges)
+    SDB_CUDA(cudaMemcpyAsync(g->d_col_idx, col_idx, sizeof(uint32_t) * n_edges, cudaMemcpyHostToDevice, ctx->stream));
+  SDB_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = g;
+  return SDB_OK;
+}
+
+void sdb_graph_destroy(sdb_graph* g) {
+  if (!g) return;
+  cudaSetDevice(g->ctx->device);
+  cudaFree(g->d_row_ptr);
+  cudaFree(g->d_col_idx);
+  delete g;
+}
+
+sdb_status sdb_graph_expand(sdb_graph* const* hops, uint32_t n_hops, const uint32_t* frontier, uint64_t n_frontier,
+                            uint32_t per_source_limit, uint32_t** out_ids, uint64_t* out_n) {
+  if (!hops || !n_hops || !out_ids || !out_n || (n_frontier && !frontier)) return SDB_EINVAL;
+  *out_ids = nullptr;
+  *out_n = 0;
+  for (uint32_t h = 0; h < n_hops; h++)
+    if (!hops[h]) return SDB_EINVAL;
+  Ctx* ctx = hops[0]->ctx;
+  std::lock_guard<std::mutex> guard(ctx->mu);
+  SDB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  uint32_t* d_f = nullptr;
+  uint64_t n_f = n_frontier;
+  if (n_f) {
+    SDB_CUDA(cudaMallocAsync(&d_f, sizeof(uint32_t) * n_f, st));
+    SDB_CUDA(cudaMemcpyAsync(d_f, frontier, sizeof(uint32_t) * n_f, cudaMemcpyHostToDevice, st));
+  }
+  for (uint32_t h = 0; h < n_hops && n_f; h++) {
+    uint32_t* d_next = nullptr;
+    uint64_t n_next = 0;
+    sdb_status s = hop_device(hops[h], d_f, n_f, per_source_limit, &d_next, &n_next, st);
+    cudaFreeAsync(d_f, st);
+    if (s != SDB_OK) {
+      if (d_next) cudaFreeAsync(d_next, st);
+      return s;
+    }
+    d_f = d_next;
+    n_f = n_next;
+  }
+  if (n_f) {
+    uint32_t* h_out = (uint32_t*)malloc(sizeof(uint32_t) * n_f);
+    if (!h_out) {
+      cudaFreeAsync(d_f, st);
+      return SDB_ENOMEM;
+    }
+    SDB_CUDA(cudaMemcpyAsync(h_out, d_f, sizeof(uint32_t) * n_f, cudaMemcpyDeviceToHost, st));
+    SDB_CUDA(cudaFreeAsync(d_f, st));
+    SDB_CUDA(cudaStreamSynchronize(st));
+    *out_ids = h_out;
+    *out_n = n_f;
+  } else {
+    SDB_CUDA(cudaStreamSynchronize(st));
+  }
+  return SDB_OK;
+}
+
+sdb_status sdb_graph_collect(sdb_graph* g, const uint32_t* start, uint64_t n_start, uint32_t min_depth,
+                             uint32_t max_depth, int inclusive, uint32_t** out_ids, uint64_t* out_n) {
+  if (!g || !out_ids || !out_n || (n_start && !start)) return SDB_EINVAL;
+  *out_ids = nullptr;
+  *out_n = 0;
+  Ctx* ctx = g->ctx;
+  std::lock_guard<std::mutex> guard(ctx->mu);
+  SDB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  for (uint64_t i = 0; i < n_start; i++)
+    if (start[i] >= g->n_rows) {
+      set_error("graph collect: start id out of range");
+      return SDB_EINVAL;
+    }
+  std::vector<uint32_t> result;
+  uint8_t* d_seen = nullptr;
+  uint32_t* d_first = nullptr;
+  SDB_CUDA(cudaMallocAsync(&d_seen, g->n_rows ? g->n_rows : 1, st));
+  SDB_CUDA(cudaMallocAsync(&d_first, sizeof(uint32_t) * (g->n_rows ? g->n_rows : 1), st));
+  SDB_CUDA(cudaMemsetAsync(d_seen, 0, g->n_rows ? g->n_rows : 1, st));
+  SDB_CUDA(cudaMemsetAsync(d_first, 0xFF, sizeof(uint32_t) * (g->n_rows ? g->n_rows : 1), st));
+  uint32_t* d_f = nullptr;
+  uint64_t n_f = n_start;
+  if (n_f) {
+    SDB_CUDA(cudaMallocAsync(&d_f, sizeof(uint32_t) * n_f, st));
+    SDB_CUDA(cudaMemcpyAsync(d_f, start, sizeof(uint32_t) * n_f, cudaMemcpyHostToDevice, st));
+  }
+  if (inclusive) {  // collect.rs:83-86: the start value is emitted and marked seen only when inclusive
+    const uint8_t one = 1;
+    for (uint64_t i = 0; i < n_start; i++) {
+      result.push_back(start[i]);
+      SDB_CUDA(cudaMemcpyAsync(d_seen + start[i], &one, 1, cudaMemcpyHostToDevice, st));
+    }
+    SDB_CUDA(cudaStreamSynchronize(st));
+  }
+  uint32_t depth = 0;
+  sdb_status rc = SDB_OK;
+  while (n_f && (max_depth == 0 || depth < max_depth)) {
+    uint32_t* d_lvl = nullptr;
+    uint64_t n_lvl = 0;
+    rc = hop_device(g, d_f, n_f, 0, &d_lvl, &n_lvl, st);
+    cudaFreeAsync(d_f, st);
+    d_f = nullptr;
+    n_f = 0;
+    if (rc != SDB_OK) break;
+    if (n_lvl) {
+      uint64_t* d_pos = nullptr;
+      SDB_CUDA(cudaMallocAsync(&d_pos, sizeof(uint64_t) * (n_lvl + 2), st));
+      const unsigned grid = (unsigned)((n_lvl + 255) / 256);
+      collect_mark_kernel<<<grid, 256, 0, st>>>(d_lvl, n_lvl, d_seen, d_first);
+      collect_flag_kernel<<<grid, 256, 0, st>>>(d_lvl, n_lvl, d_seen, d_first, d_pos);
+      count_launch(ctx, 2);
+      rc = exclusive_scan(ctx, d_pos, d_pos, n_lvl, d_pos + n_lvl, st);
+      if (rc != SDB_OK) break;
+      uint64_t n_next = 0;
+      SDB_CUDA(cudaMemcpyAsync(&n_next, d_pos + n_lvl, 8, cudaMemcpyDeviceToHost, st));
+      SDB_CUDA(cudaStreamSynchronize(st));
+      if (n_next) {
+        SDB_CUDA(cudaMallocAsync(&d_f, sizeof(uint32_t) * n_next, st));
+        collect_compact_kernel<<<grid, 256, 0, st>>>(d_lvl, n_lvl, d_pos, d_seen, d_first, d_f);
+        count_launch(ctx);
+        n_f = n_next;
+        if (depth + 1 >= min_depth) {  // nodes below min_depth are traversed but not emitted
+          const size_t o = result.size();
+          result.resize(o + n_next);
+          SDB_CUDA(cudaMemcpyAsync(result.data() + o, d_f, sizeof(uint32_t) * n_next, cudaMemcpyDeviceToHost, st));
+          SDB_CUDA(cudaStreamSynchronize(st));
+        }
+      }
+      SDB_CUDA(cudaFreeAsync(d_pos, st));
+      SDB_CUDA(cudaFreeAsync(d_lvl, st));
+    }
+    depth++;
+  }
+  if (d_f) cudaFreeAsync(d_f, st);
+  cudaFreeAsync(d_seen, st);
+  cudaFreeAsync(d_first, st);
+  SDB_CUDA(cudaStreamSynchronize(st));
+  if (rc != SDB_OK) return rc;
+  if (!result.empty()) {
+    uint32_t* h_out = (uint32_t*)malloc(sizeof(uint32_t) * result.size());
+    if (!h_out) return SDB_ENOMEM;
+    memcpy(h_out, result.data(), sizeof(uint32_t) * result.size());
+    *out_ids = h_out;
+    *out_n = result.size();
+  }
+  return SDB_OK;
+}
+
+}  // extern "C"

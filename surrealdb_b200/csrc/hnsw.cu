@@ -1,0 +1,532 @@
+// hnsw.cu -- K3: HNSW layer walk, one warp per query, strict-parity with the reference's sequential search.
+//
+// Replaces Hnsw::knn_search (idx/trees/hnsw/mod.rs:459-482): search_ep greedy descent (mod.rs:521-548) and
+// HnswLayer::search (hnsw/layer.rs:184-223) with its two DoublePriorityQueues (idx/trees/knn.rs:15-123) and
+// visited set.  Parity rules reproduced exactly:
+//   * candidates popped nearest-first, FIFO among equal distances; stop when nearest candidate > farthest kept
+//   * neighbours visited in STORED order; admitted iff d < f or |w| < ef; w trimmed with pop_last (newest of
+//     the farthest); f re-read after every admission
+//   * distances are the typed-f32 kernels of idx/trees/vector.rs:243-289: cosine = ndarray 8-lane f32 dot and
+//     sums, finished in f64; euclid = sequential f32 sum of squares, f64 sqrt (same op order as the oracle)
+// Batched candidate expansion: the <=32 neighbours of the popped candidate are de-duplicated against the
+// per-query visited table with warp-parallel CAS, their vectors are gathered with coalesced transposed loads
+// (one lane per neighbour walks its row in order), and only the admission step is serial.
+// Queue trick (result-neutral): once w is full, candidates farther than f can never be expanded (f only
+// shrinks), so they are dropped from the candidate array, which bounds it to 2*ef entries.
+//
+// Algorithmic bytes per query = visited * (4*dim + 4) + expanded * 4*deg, both counters are returned.
+#include "internal.cuh"
+#include "rowwalk.cuh"
+
+namespace sdb {
+
+struct Hnsw {
+  Ctx* ctx = nullptr;
+  uint32_t dim = 0;
+  sdb_metric metric = SDB_EUCLIDEAN;
+  uint64_t n = 0;
+  uint32_t n_layers = 0;
+  int64_t entry = -1;
+  float* d_vec = nullptr;
+  float* d_sumsq = nullptr;
+  std::vector<uint64_t*> rp;
+  std::vector<uint32_t*> ci;
+  const uint64_t** d_rp = nullptr;
+  const uint32_t** d_ci = nullptr;
+  uint64_t* d_visited = nullptr;
+  uint32_t table_log2 = 0, n_tables = 0;
+  uint32_t gen = 1;  // generations consumed so far (each warp uses gen_base + its own counter)
+  std::mutex mu;
+};
+
+constexpr int HN_WARPS = 4;
+constexpr uint64_t KEY_MAX = 0xFFEFFFFFFFFFFFFFull;  // dist_key(f64::MAX)
+
+__device__ __forceinline__ double key_to_double(uint64_t key) {
+  const uint64_t b = (key >> 63) ? (key & 0x7fffffffffffffffull) : ~key;
+  return __longlong_as_double((long long)b);
+}
+
+// ndarray-style 8-lane f32 sum of squares of one row (used at load time for every element, and per query)
+__global__ void hnsw_sumsq_kernel(const float* __restrict__ vec, uint32_t dim, uint64_t n, float* __restrict__ out) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const float* a = vec + r * dim;
+  float p[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint32_t i = 0;
+  for (; i + 8 <= dim; i += 8)
+#pragma unroll
+    for (int j = 0; j < 8; j++) p[j] = __fadd_rn(p[j], __fmul_rn(a[i + j], a[i + j]));
+  float s = 0.f;
+  s = __fadd_rn(s, __fadd_rn(p[0], p[4]));
+  s = __fadd_rn(s, __fadd_rn(p[1], p[5]));
+  s = __fadd_rn(s, __fadd_rn(p[2], p[6]));
+  s = __fadd_rn(s, __fadd_rn(p[3], p[7]));
+  for (; i < dim; i++) s = __fadd_rn(s, __fmul_rn(a[i], a[i]));
+  out[r] = s;
+}
+
+// distance of this lane's row (or NO_ROW) to the query held in shared memory; all 32 lanes must call.
+template <bool COSINE>
+__device__ __forceinline__ double warp_distance(const float* __restrict__ vec, const float* __restrict__ sumsq,
+                                                uint32_t dim, uint32_t my_row, const float* s_q, float q_sumsq,
+                                                float (*tile)[33]) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t d8 = dim & ~7u;
+  float p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0, p5 = 0, p6 = 0, p7 = 0, s = 0.f;
+  const uint32_t lim_all = COSINE ? d8 : dim;
+  for (uint32_t c0 = 0; c0 < lim_all; c0 += 32) {
+    const uint32_t c = c0 + lane;
+#pragma unroll 8
+    for (int r = 0; r < 32; r++) {
+      const uint32_t row = __shfl_sync(0xffffffffu, my_row, r);
+      float v = 0.f;
+      if (row != NO_ROW && c < lim_all) v = __ldg(vec + (size_t)row * dim + c);
+      tile[r][lane] = v;
+    }
+    __syncwarp();
+    if (my_row != NO_ROW) {
+      const uint32_t lim = lim_all - c0 < 32u ? lim_all - c0 : 32u;
+      if (COSINE) {
+        for (uint32_t jj = 0; jj < lim; jj += 8) {  // lim is a multiple of 8 here
+          const float* x = &tile[lane][jj];
+          const float* q = s_q + c0 + jj;
+          p0 = __fadd_rn(p0, __fmul_rn(x[0], q[0]));
+          p1 = __fadd_rn(p1, __fmul_rn(x[1], q[1]));
+          p2 = __fadd_rn(p2, __fmul_rn(x[2], q[2]));
+          p3 = __fadd_rn(p3, __fmul_rn(x[3], q[3]));
+          p4 = __fadd_rn(p4, __fmul_rn(x[4], q[4]));
+          p5 = __fadd_rn(p5, __fmul_rn(x[5], q[5]));
+          p6 = __fadd_rn(p6, __fmul_rn(x[6], q[6]));
+          p7 = __fadd_rn(p7, __fmul_rn(x[7], q[7]));
+        }
+      } else {
+        for (uint32_t j = 0; j < lim; j++) {
+          const float d = __fsub_rn(tile[lane][j], s_q[c0 + j]);
+          s = __fadd_rn(s, __fmul_rn(d, d));
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (my_row == NO_ROW) return 0.0;
+  if (COSINE) {
+    float dot = 0.f;
+    dot = __fadd_rn(dot, __fadd_rn(p0, p4));
+    dot = __fadd_rn(dot, __fadd_rn(p1, p5));
+    dot = __fadd_rn(dot, __fadd_rn(p2, p6));
+    dot = __fadd_rn(dot, __fadd_rn(p3, p7));
+    for (uint32_t c = d8; c < dim; c++) dot = __fadd_rn(dot, __fmul_rn(__ldg(vec + (size_t)my_row * dim + c), s_q[c]));
+    const double na = __dsqrt_rn((double)__ldg(sumsq + my_row));
+    const double nb = __dsqrt_rn((double)q_sumsq);
+    return __dsub_rn(1.0, __ddiv_rn((double)dot, __dmul_rn(na, nb)));
+  }
+  return __dsqrt_rn((double)s);
+}
+
+// sorted (ascending key, FIFO inside a key) array insert by the whole warp; entries live in [head, n)
+__device__ __forceinline__ uint32_t sorted_insert(uint64_t* keys, uint32_t* ids, uint32_t head, uint32_t n, uint64_t key,
+                                                  uint32_t id) {
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t cnt = 0;
+  for (uint32_t i = head + lane; i < n; i += 32) cnt += keys[i] <= key;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  const uint32_t pos = head + cnt;
+  for (uint32_t hi = n; hi > pos;) {  // shift [pos, n) up by one, top chunk first
+    const uint32_t lo = hi - pos > 32u ? hi - 32u : pos;
+    const uint32_t i = lo + lane;
+    uint64_t k = 0;
+    uint32_t v = 0;
+    if (i < hi) {
+      k = keys[i];
+      v = ids[i];
+    }
+    __syncwarp();
+    if (i < hi) {
+      keys[i + 1] = k;
+      ids[i + 1] = v;
+    }
+    __syncwarp();
+    hi = lo;
+  }
+  if (lane == 0) {
+    keys[pos] = key;
+    ids[pos] = id;
+  }
+  __syncwarp();
+  return n + 1;
+}
+
+struct HnswParams {
+  const float* vec;
+  const float* sumsq;
+  const uint64_t* const* rp;
+  const uint32_t* const* ci;
+  uint32_t dim, n_layers;
+  int64_t entry;
+  const float* queries;
+  uint32_t nq, k, ef;
+  uint64_t* visited;
+  uint32_t table_log2;
+  uint32_t gen_base, gens_per_warp;
+  uint64_t* out_elems;
+  double* out_dist;
+  uint32_t* out_count;
+  uint64_t* out_counters;
+  uint32_t* overflow;
+};
+
+template <bool COSINE>
+__global__ void __launch_bounds__(HN_WARPS * 32) hnsw_search_kernel(HnswParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ccap = 2 * P.ef + 34, wcap = P.ef + 2;
+  // per-warp shared layout
+  const size_t per_warp = sizeof(float) * ((P.dim + 3) & ~3u) + sizeof(float) * 32 * 33 + (sizeof(uint64_t) + sizeof(uint32_t)) * (ccap + wcap) + 64;
+  uint8_t* base = smem_raw + (size_t)warp * ((per_warp + 15) & ~size_t(15));
+  uint64_t* c_key = reinterpret_cast<uint64_t*>(base);
+  uint64_t* w_key = c_key + ccap;
+  float(*tile)[33] = reinterpret_cast<float(*)[33]>(w_key + wcap);
+  float* s_q = reinterpret_cast<float*>(tile) + 32 * 33;
+  uint32_t* c_id = reinterpret_cast<uint32_t*>(s_q + ((P.dim + 3) & ~3u));
+  uint32_t* w_id = c_id + ccap;
+
+  const uint32_t gwarp = blockIdx.x * HN_WARPS + warp;
+  const uint32_t n_warps = gridDim.x * HN_WARPS;
+  uint64_t* table = P.visited + ((size_t)gwarp << P.table_log2);
+  const uint32_t mask = (1u << P.table_log2) - 1u;
+  uint32_t gen = P.gen_base + gwarp * P.gens_per_warp;
+
+  for (uint32_t q = gwarp; q < P.nq; q += n_warps) {
+    // stage the query, its 8-lane sum of squares (cosine)
+    for (uint32_t c = lane; c < P.dim; c += 32) s_q[c] = P.queries[(size_t)q * P.dim + c];
+    __syncwarp();
+    float q_sumsq = 0.f;
+    if (COSINE) {
+      float p[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      uint32_t i = 0;
+      for (; i + 8 <= P.dim; i += 8)
+#pragma unroll
+        for (int j = 0; j < 8; j++) p[j] = __fadd_rn(p[j], __fmul_rn(s_q[i + j], s_q[i + j]));
+      q_sumsq = __fadd_rn(q_sumsq, __fadd_rn(p[0], p[4]));
+      q_sumsq = __fadd_rn(q_sumsq, __fadd_rn(p[1], p[5]));
+      q_sumsq = __fadd_rn(q_sumsq, __fadd_rn(p[2], p[6]));
+      q_sumsq = __fadd_rn(q_sumsq, __fadd_rn(p[3], p[7]));
+      for (; i < P.dim; i++) q_sumsq = __fadd_rn(q_sumsq, __fmul_rn(s_q[i], s_q[i]));
+    }
+    uint64_t n_visited = 0, n_expanded = 0;
+    uint32_t n_out = 0;
+    if (P.entry >= 0) {
+      uint32_t ep = (uint32_t)P.entry;
+      double ep_d = warp_distance<COSINE>(P.vec, P.sumsq, P.dim, lane == 0 ? ep : NO_ROW, s_q, q_sumsq, tile);
+      ep_d = __shfl_sync(0xffffffffu, ep_d, 0);
+      n_visited++;
+      for (int32_t layer = (int32_t)P.n_layers - 1; layer >= 0; layer--) {
+        const uint32_t ef = layer == 0 ? P.ef : 1u;
+        const uint64_t* rp = P.rp[layer];
+        const uint32_t* ci = P.ci[layer];
+        gen++;
+        // search_single: visited = {ep}; candidates = w = {(ep_d, ep)}        layer.rs:76-90
+        uint32_t head = 0, cn = 0, wn = 0;
+        {
+          const uint64_t my = ((uint64_t)gen << 32) | ep;
+          if (lane == 0) {
+            uint32_t slot = (ep * 2654435761u) & mask;
+            while ((table[slot] >> 32) == gen) slot = (slot + 1) & mask;
+            table[slot] = my;
+          }
+          __syncwarp();
+        }
+        cn = sorted_insert(c_key, c_id, head, cn, dist_key(ep_d), ep);
+        wn = sorted_insert(w_key, w_id, 0, wn, dist_key(ep_d), ep);
+        double fd = ep_d;  // w.peek_last_dist()
+        while (head < cn) {
+          const uint64_t ckey = c_key[head];
+          const uint32_t cid = c_id[head];
+          head++;
+          if (key_to_double(ckey) > fd) break;  // cq_dist > fq_dist
+          n_expanded++;
+          const uint64_t beg = rp[cid], end = rp[cid + 1];
+          for (uint64_t b0 = beg; b0 < end; b0 += 32) {
+            const uint32_t nb = b0 + lane < end ? __ldg(ci + b0 + lane) : NO_ROW;
+            bool is_new = false;
+            if (nb != NO_ROW) {  // visited.insert(e_id)
+              const uint64_t my = ((uint64_t)gen << 32) | nb;
+              uint32_t slot = (nb * 2654435761u) & mask;
+              for (uint32_t probes = 0;; probes++) {
+                const uint64_t cur = *reinterpret_cast<volatile uint64_t*>(table + slot);
+                if (cur == my) break;
+                if ((uint32_t)(cur >> 32) != gen) {
+                  const uint64_t old = atomicCAS(reinterpret_cast<unsigned long long*>(table + slot),
+                                                 (unsigned long long)cur, (unsigned long long)my);
+                  if (old == cur) {
+                    is_new = true;
+                    break;
+                  }
+                  if (old == my) break;
+                  if ((uint32_t)(old >> 32) != gen) continue;
+                }
+                if (probes > mask) {  // table full: report, treat as visited
+                  *P.overflow = 1;
+                  break;
+                }
+                slot = (slot + 1) & mask;
+              }
+            }
+            const uint32_t new_mask = __ballot_sync(0xffffffffu, is_new);
+            if (!new_mask) continue;
+            n_visited += __popc(new_mask);
+            const double d = warp_distance<COSINE>(P.vec, P.sumsq, P.dim, is_new ? nb : NO_ROW, s_q, q_sumsq, tile);
+            // admission in stored order                                     layer.rs:205-217
+            uint32_t m = new_mask;
+            while (m) {
+              const int i = __ffs(m) - 1;
+              m &= m - 1;
+              const double di = __shfl_sync(0xffffffffu, d, i);
+              const uint32_t idi = __shfl_sync(0xffffffffu, nb, i);
+              if (di < fd || wn < ef) {
+                const uint64_t key = dist_key(di);
+                if (cn >= ccap) {  // slide the live window down (or, if truly full, drop the farthest tie)
+                  if (head > 0) {
+                    for (uint32_t lo = head; lo < cn; lo += 32) {
+                      const uint32_t j = lo + lane;
+                      uint64_t kk = 0;
+                      uint32_t vv = 0;
+                      if (j < cn) { kk = c_key[j]; vv = c_id[j]; }
+                      __syncwarp();
+                      if (j < cn) { c_key[j - head] = kk; c_id[j - head] = vv; }
+                      __syncwarp();
+                    }
+                    cn -= head;
+                    head = 0;
+                  }
+                  if (cn >= ccap) {
+                    cn = ccap - 1;
+                    *P.overflow = 2;
+                  }
+                }
+                cn = sorted_insert(c_key, c_id, head, cn, key, idi);
+                wn = sorted_insert(w_key, w_id, 0, wn, key, idi);
+                if (wn > ef) wn--;  // pop_last
+                fd = key_to_double(w_key[wn - 1]);
+                if (wn == ef) {  // candidates beyond f can never be expanded any more
+                  const uint64_t fkey = w_key[wn - 1];
+                  while (cn > head && c_key[cn - 1] > fkey) cn--;
+                }
+              }
+            }
+          }
+        }
+        // next layer starts from w.peek_first()                                mod.rs:530-538
+        ep = w_id[0];
+        ep_d = key_to_double(w_key[0]);
+        if (layer == 0) {
+          n_out = wn < P.k ? wn : P.k;  // to_vec_limit(k)
+          for (uint32_t i = lane; i < n_out; i += 32) {
+            P.out_elems[(size_t)q * P.k + i] = w_id[i];
+            P.out_dist[(size_t)q * P.k + i] = key_to_double(w_key[i]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (lane == 0) {
+      P.out_count[q] = n_out;
+      if (P.out_counters) {
+        P.out_counters[2 * (size_t)q] = n_visited;
+        P.out_counters[2 * (size_t)q + 1] = n_expanded;
+      }
+    }
+  }
+}
+
+}  // namespace sdb
+
+struct sdb_hnsw : sdb::Hnsw {};
+using namespace sdb;
+
+extern "C" {
+
+void sdb_hnsw_destroy(sdb_hnsw* h) {
+  if (!h) return;
+  cudaSetDevice(h->ctx->device);
+  cudaFree(h->d_vec);
+  cudaFree(h->d_sumsq);
+  for (auto p : h->rp) cudaFree(p);
+  for (auto p : h->ci) cudaFree(p);
+  cudaFree(h->d_rp);
+  cudaFree(h->d_ci);
+  cudaFree(h->d_visited);
+  delete h;
+}
+
+sdb_status sdb_hnsw_load(sdb_ctx* ctx, uint32_t dim, sdb_metric metric, uint64_t n_elems, const float* vectors,
+                         uint32_t n_layers, const uint64_t* const* row_ptr, const uint32_t* const* col_idx,
+                         int64_t entry_point, sdb_hnsw** out) {
+  if (!ctx || !out || dim == 0 || dim > 65535 || n_elems >= 0xFFFFFFF0ull || (n_elems && !vectors) || !n_layers ||
+      !row_ptr || !col_idx || entry_point >= (int64_t)n_elems)
+    return SDB_EINVAL;
+  if (metric != SDB_COSINE && metric != SDB_EUCLIDEAN) {
+    set_error("hnsw: metric %d not implemented on the GPU path", (int)metric);
+    return SDB_EUNSUPPORTED;
+  }
+  *out = nullptr;
+  SDB_CUDA(cudaSetDevice(ctx->device));
+  sdb_hnsw* h = new sdb_hnsw();
+  h->ctx = ctx;
+  h->dim = dim;
+  h->metric = metric;
+  h->n = n_elems;
+  h->n_layers = n_layers;
+  h->entry = entry_point;
+  cudaStream_t st = ctx->stream;
+  auto fail = [&](const char* what) {
+    set_error("hnsw load: %s failed: %s", what, cudaGetErrorString(cudaGetLastError()));
+    sdb_hnsw_destroy(h);
+    return SDB_ENOMEM;
+  };
+  const uint64_t nn = n_elems ? n_elems : 1;
+  if (cudaMalloc(&h->d_vec, sizeof(float) * nn * dim) != cudaSuccess) return fail("vectors");
+  if (cudaMalloc(&h->d_sumsq, sizeof(float) * nn) != cudaSuccess) return fail("sumsq");
+  if (n_elems) SDB_CUDA(cudaMemcpyAsync(h->d_vec, vectors, sizeof(float) * n_elems * dim, cudaMemcpyHostToDevice, st));
+  std::vector<const uint64_t*> hrp;
+  std::vector<const uint32_t*> hci;
+  for (uint32_t l = 0; l < n_layers; l++) {
+    const uint64_t e = n_elems ? row_ptr[l][n_elems] : 0;
+    uint64_t* drp = nullptr;
+    uint32_t* dci = nullptr;
+    if (cudaMalloc(&drp, sizeof(uint64_t) * (n_elems + 1)) != cudaSuccess) return fail("row_ptr");
+    h->rp.push_back(drp);
+    if (cudaMalloc(&dci, sizeof(uint32_t) * (e ? e : 1)) != cudaSuccess) return fail("col_idx");
+    h->ci.push_back(dci);
+    SDB_CUDA(cudaMemcpyAsync(drp, row_ptr[l], sizeof(uint64_t) * (n_elems + 1), cudaMemcpyHostToDevice, st));
+    if (e) SDB_CUDA(cudaMemcpyAsync(dci, col_idx[l], sizeof(uint32_t) * e, cudaMemcpyHostToDevice, st));
+    hrp.push_back(drp);
+    hci.push_back(dci);
+  }
+  if (cudaMalloc(&h->d_rp, sizeof(void*) * n_layers) != cudaSuccess) return fail("layer table");
+  if (cudaMalloc(&h->d_ci, sizeof(void*) * n_layers) != cudaSuccess) return fail("layer table");
+  SDB_CUDA(cudaMemcpyAsync(h->d_rp, hrp.data(), sizeof(void*) * n_layers, cudaMemcpyHostToDevice, st));
+  SDB_CUDA(cudaMemcpyAsync(h->d_ci, hci.data(), sizeof(void*) * n_layers, cudaMemcpyHostToDevice, st));
+  if (n_elems) {
+    hnsw_sumsq_kernel<<<(unsigned)((n_elems + 127) / 128), 128, 0, st>>>(h->d_vec, dim, n_elems, h->d_sumsq);
+    count_launch(ctx);
+  }
+  SDB_CUDA(cudaStreamSynchronize(st));
+  SDB_CUDA(cudaGetLastError());
+  *out = h;
+  return SDB_OK;
+}
+
+sdb_status sdb_hnsw_search(sdb_hnsw* h, const float* queries, uint32_t nq, uint32_t k, uint32_t ef, uint64_t* out_elems,
+                           double* out_dist, uint32_t* out_count, uint64_t* out_counters) {
+  if (!h || (nq && (!queries || !out_count)) || (nq && k && (!out_elems || !out_dist))) return SDB_EINVAL;
+  if (nq == 0) return SDB_OK;
+  if (k == 0 || ef == 0) {  // to_vec_limit(0) underflows in the reference; we return nothing
+    memset(out_count, 0, sizeof(uint32_t) * nq);
+    return SDB_OK;
+  }
+  if (ef > 4096) {
+    set_error("hnsw: ef %u > 4096 unsupported", ef);
+    return SDB_EUNSUPPORTED;
+  }
+  Ctx* ctx = h->ctx;
+  std::lock_guard<std::mutex> guard(h->mu);
+  SDB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const uint32_t ccap = 2 * ef + 34, wcap = ef + 2;
+  size_t per_warp = sizeof(float) * ((h->dim + 3) & ~3u) + sizeof(float) * 32 * 33 + 12 * (size_t)(ccap + wcap) + 64;
+  per_warp = (per_warp + 15) & ~size_t(15);
+  const size_t smem = per_warp * HN_WARPS;
+  if (smem > 220 * 1024) {
+    set_error("hnsw: dim %u / ef %u need %zu bytes of shared memory per block", h->dim, ef, smem);
+    return SDB_EUNSUPPORTED;
+  }
+  auto kern = h->metric == SDB_COSINE ? hnsw_search_kernel<true> : hnsw_search_kernel<false>;
+  SDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  SDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, HN_WARPS * 32, smem));
+  if (per_sm < 1) per_sm = 1;
+  uint32_t grid = (uint32_t)(ctx->sm_count * per_sm);
+  if (grid > (nq + HN_WARPS - 1) / HN_WARPS) grid = (nq + HN_WARPS - 1) / HN_WARPS;
+  // visited tables: one per resident warp; 16 x the worst-case expansion of a typical walk, >= 2^13 slots
+  uint32_t tl = 13;
+  while ((1u << tl) < ef * 64u * 4u && tl < 20) tl++;
+  const uint32_t n_tables = grid * HN_WARPS;
+  if (!h->d_visited || h->table_log2 != tl || h->n_tables < n_tables) {
+    cudaFree(h->d_visited);
+    h->d_visited = nullptr;
+    SDB_CUDA(cudaMalloc(&h->d_visited, sizeof(uint64_t) * ((size_t)n_tables << tl)));
+    SDB_CUDA(cudaMemsetAsync(h->d_visited, 0, sizeof(uint64_t) * ((size_t)n_tables << tl), st));
+    h->table_log2 = tl;
+    h->n_tables = n_tables;
+    h->gen = 1;
+  }
+  const uint32_t q_per_warp = (nq + n_tables - 1) / n_tables;
+  const uint32_t gens_per_warp = q_per_warp * h->n_layers + 1;
+  if ((uint64_t)h->gen + (uint64_t)gens_per_warp * n_tables >= 0xFFFFFFF0ull) {  // generation counter wrap
+    SDB_CUDA(cudaMemsetAsync(h->d_visited, 0, sizeof(uint64_t) * ((size_t)h->n_tables << tl), st));
+    h->gen = 1;
+  }
+  float* d_q = nullptr;
+  uint64_t* d_elems = nullptr;
+  double* d_dist = nullptr;
+  uint32_t* d_cnt = nullptr;
+  uint64_t* d_ctr = nullptr;
+  uint32_t* d_ovf = nullptr;
+  SDB_CUDA(cudaMallocAsync(&d_q, sizeof(float) * (size_t)nq * h->dim, st));
+  SDB_CUDA(cudaMallocAsync(&d_elems, sizeof(uint64_t) * (size_t)nq * k, st));
+  SDB_CUDA(cudaMallocAsync(&d_dist, sizeof(double) * (size_t)nq * k, st));
+  SDB_CUDA(cudaMallocAsync(&d_cnt, sizeof(uint32_t) * nq, st));
+  SDB_CUDA(cudaMallocAsync(&d_ctr, sizeof(uint64_t) * 2 * nq, st));
+  SDB_CUDA(cudaMallocAsync(&d_ovf, 4, st));
+  SDB_CUDA(cudaMemsetAsync(d_ovf, 0, 4, st));
+  SDB_CUDA(cudaMemcpyAsync(d_q, queries, sizeof(float) * (size_t)nq * h->dim, cudaMemcpyHostToDevice, st));
+  HnswParams P;
+  P.vec = h->d_vec;
+  P.sumsq = h->d_sumsq;
+  P.rp = h->d_rp;
+  P.ci = h->d_ci;
+  P.dim = h->dim;
+  P.n_layers = h->n_layers;
+  P.entry = h->entry;
+  P.queries = d_q;
+  P.nq = nq;
+  P.k = k;
+  P.ef = ef;
+  P.visited = h->d_visited;
+  P.table_log2 = tl;
+  P.gen_base = h->gen;
+  P.gens_per_warp = gens_per_warp;
+  P.out_elems = d_elems;
+  P.out_dist = d_dist;
+  P.out_count = d_cnt;
+  P.out_counters = d_ctr;
+  P.overflow = d_ovf;
+  kern<<<grid, HN_WARPS * 32, smem, st>>>(P);
+  count_launch(ctx);
+  h->gen += gens_per_warp * n_tables;
+  uint32_t ovf = 0;
+  SDB_CUDA(cudaMemcpyAsync(out_elems, d_elems, sizeof(uint64_t) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
+  SDB_CUDA(cudaMemcpyAsync(out_dist, d_dist, sizeof(double) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
+  SDB_CUDA(cudaMemcpyAsync(out_count, d_cnt, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, st));
+  if (out_counters)
+    SDB_CUDA(cudaMemcpyAsync(out_counters, d_ctr, sizeof(uint64_t) * 2 * nq, cudaMemcpyDeviceToHost, st));
+  SDB_CUDA(cudaMemcpyAsync(&ovf, d_ovf, 4, cudaMemcpyDeviceToHost, st));
+  cudaFreeAsync(d_q, st);
+  cudaFreeAsync(d_elems, st);
+  cudaFreeAsync(d_dist, st);
+  cudaFreeAsync(d_cnt, st);
+  cudaFreeAsync(d_ctr, st);
+  cudaFreeAsync(d_ovf, st);
+  SDB_CUDA(cudaStreamSynchronize(st));
+  SDB_CUDA(cudaGetLastError());
+  if (ovf == 1) {
+    set_error("hnsw: visited table overflow (ef too large for the per-query table)");
+    return SDB_EOVERFLOW;
+  }
+  return SDB_OK;
+}
+
+}  // extern "C"

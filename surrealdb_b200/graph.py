@@ -1,0 +1,128 @@
+"""Host-side mirror of the graph-scan operators on top of the C ABI.
+
+  CsrGraph            sdb_graph: device CSR of one (direction, edge table)
+  GraphStore          what the Rust shim builds from the `~` edge-pointer keys (key/graph/mod.rs:122-137):
+                      per (direction, edge table) a CSR whose rows list, per source record, the targets in KV
+                      key order of the connecting edge records
+  GraphStore.lookup   LookupPart over a fused GraphEdgeScan chain (exec/parts/lookup.rs:139-170,
+                      exec/planner/idiom.rs:161-193): multiset, order-preserving
+  GraphStore.collect  `.{min..max+collect[+inclusive]}` (exec/operators/recursion/collect.rs:74-143)
+  GraphStore.recurse  default `.{min..max}` recursion (exec/operators/recursion/default.rs:75-133)
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+class CsrGraph:
+    def __init__(self, ctx, row_ptr, col_idx):
+        self.ctx = ctx
+        rp = np.ascontiguousarray(row_ptr, np.uint64)
+        ci = np.ascontiguousarray(col_idx, np.uint32)
+        self.n_rows = rp.size - 1
+        self.h = C.c_void_p()
+        L.check(L.lib().sdb_graph_load_csr(ctx.h, self.n_rows, C.c_void_p(rp.ctypes.data),
+                                           C.c_void_p(ci.ctypes.data) if ci.size else None, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            L.lib().sdb_graph_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _take(out, n):
+    if not out or n.value == 0:
+        return np.zeros(0, np.uint32)
+    arr = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint32)), shape=(n.value,)).copy()
+    L.lib().sdb_free(out)
+    return arr
+
+
+def expand(hops, frontier, per_source_limit=0):
+    """sdb_graph_expand: apply the CSR hops in order to the frontier (multiset semantics)."""
+    fr = np.ascontiguousarray(frontier, np.uint32)
+    arr = (C.c_void_p * len(hops))(*[g.h for g in hops])
+    out, n = C.c_void_p(), C.c_uint64()
+    L.check(L.lib().sdb_graph_expand(arr, len(hops), C.c_void_p(fr.ctypes.data) if fr.size else None, fr.size,
+                                     int(per_source_limit), C.byref(out), C.byref(n)))
+    return _take(out, n)
+
+
+def collect(graph, start, min_depth=1, max_depth=0, inclusive=False):
+    st = np.ascontiguousarray(start, np.uint32)
+    out, n = C.c_void_p(), C.c_uint64()
+    L.check(L.lib().sdb_graph_collect(graph.h, C.c_void_p(st.ctypes.data) if st.size else None, st.size, int(min_depth),
+                                      int(max_depth), int(bool(inclusive)), C.byref(out), C.byref(n)))
+    return _take(out, n)
+
+
+def _key_order(rid_key):
+    """storekey order of a RecordIdKey (val/record_id.rs:181-192): numbers (numeric) before strings (bytes)"""
+    if isinstance(rid_key, (int, np.integer)):
+        return (0, int(rid_key), b"")
+    return (1, 0, str(rid_key).encode())
+
+
+class GraphStore:
+    """CSR snapshots of a set of RELATE edges: relations = iterable of (src, edge_table, edge_id, dst) with
+    record ids like 'person:alice'."""
+
+    def __init__(self, ctx, relations):
+        self.ctx = ctx
+        rel = list(relations)
+        self.names = sorted({r[0] for r in rel} | {r[3] for r in rel})
+        self.idx = {n: i for i, n in enumerate(self.names)}
+        self._rel = rel
+        self._csr = {}
+
+    def csr(self, edge_table, direction):
+        key = (edge_table, direction)
+        if key not in self._csr:
+            adj = [[] for _ in self.names]
+            for src, tb, eid, dst in self._rel:
+                if tb != edge_table:
+                    continue
+                s, d = (src, dst) if direction == "out" else (dst, src)
+                adj[self.idx[s]].append((_key_order(eid), self.idx[d]))
+            rp, ci = [0], []
+            for a in adj:
+                a.sort()
+                ci += [t for _, t in a]
+                rp.append(len(ci))
+            self._csr[key] = CsrGraph(self.ctx, np.asarray(rp, np.uint64), np.asarray(ci, np.uint32))
+        return self._csr[key]
+
+    def ids(self, names):
+        return np.asarray([self.idx[n] for n in names], np.uint32)
+
+    def to_names(self, arr):
+        return [self.names[int(i)] for i in arr]
+
+    def lookup(self, start, hops, limit=0):
+        """start: record ids; hops: [(direction 'out'|'in', edge_table), ...] -> record ids (order + duplicates
+        as the reference returns them)"""
+        return self.to_names(expand([self.csr(tb, d) for d, tb in hops], self.ids(start), limit))
+
+    def collect(self, start, direction, edge_table, min_depth=1, max_depth=0, inclusive=False):
+        return self.to_names(collect(self.csr(edge_table, direction), self.ids([start]), min_depth, max_depth, inclusive))
+
+    def recurse(self, start, direction, edge_table, min_depth, max_depth):
+        """default recursion: repeat the hop until the bound, a dead end or a fixed point"""
+        g = self.csr(edge_table, direction)
+        cur = self.ids([start])
+        depth = 0
+        while depth < max_depth:
+            nxt = expand([g], cur)
+            depth += 1
+            if nxt.size == 0 or (nxt.size == cur.size and np.array_equal(nxt, cur)):
+                return self.to_names(cur) if depth > min_depth else None
+            cur = nxt
+        return self.to_names(cur) if depth >= min_depth else None

@@ -1,0 +1,78 @@
+"""Host-side mirror of the HNSW search path on top of the C ABI.
+
+  HnswIndex.load(...)                 what the Rust shim hands over after HnswFlavor::check_state
+                                      (idx/trees/hnsw/mod.rs:187-224): element vectors + per-layer adjacency
+  HnswIndex.search_graph(q, k, ef)    Hnsw::knn_search (hnsw/mod.rs:459-482) -> [(dist, element)] ascending
+  HnswIndex.knn_search(q, k, ef)      HnswIndex::knn_search (hnsw/index.rs:270-335) without pendings/filter:
+                                      element -> docs expansion through KnnResultBuilder semantics
+                                      (idx/trees/knn.rs:363-437): final order (distance, doc id), <= k
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+class HnswIndex:
+    def __init__(self, ctx, vectors, layers, entry_point, metric="EUCLIDEAN", elem_docs=None):
+        """vectors (n, dim) f32; layers = [(row_ptr u64[n+1], col_idx u32[e]), ...] layer 0 first;
+        elem_docs: optional list of doc-id lists per element (identical vectors share one element:
+        hnsw/docs.rs:161-176); default = one doc per element with the same id."""
+        vec = np.ascontiguousarray(vectors, np.float32)
+        self.n, self.dim = vec.shape
+        self.ctx, self.metric = ctx, metric.upper()
+        self.elem_docs = elem_docs
+        nl = len(layers)
+        rps = [np.ascontiguousarray(l[0], np.uint64) for l in layers]
+        cis = [np.ascontiguousarray(l[1] if len(l[1]) else np.zeros(1, np.uint32), np.uint32) for l in layers]
+        RP = (C.c_void_p * nl)(*[a.ctypes.data for a in rps])
+        CI = (C.c_void_p * nl)(*[a.ctypes.data for a in cis])
+        self.h = C.c_void_p()
+        L.check(L.lib().sdb_hnsw_load(ctx.h, self.dim, L.METRIC[self.metric], self.n, C.c_void_p(vec.ctypes.data), nl,
+                                      RP, CI, int(entry_point), C.byref(self.h)))
+
+    def search_graph(self, queries, k, ef, counters=False):
+        q = np.ascontiguousarray(queries, np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.shape[1] != self.dim:  # Error::InvalidVectorDimension  idx/trees/vector.rs:643-652
+            raise L.SdbError(L.SDB_EDIM, f"Incorrect vector dimension ({q.shape[1]}). Expected a vector of {self.dim} dimension.")
+        nq = q.shape[0]
+        ids = np.zeros((nq, max(k, 1)), np.uint64)
+        dist = np.zeros((nq, max(k, 1)), np.float64)
+        cnt = np.zeros(nq, np.uint32)
+        ctr = np.zeros((nq, 2), np.uint64)
+        L.check(L.lib().sdb_hnsw_search(self.h, C.c_void_p(q.ctypes.data), nq, int(k), int(ef), C.c_void_p(ids.ctypes.data),
+                                        C.c_void_p(dist.ctypes.data), C.c_void_p(cnt.ctypes.data),
+                                        C.c_void_p(ctr.ctypes.data)))
+        if counters:
+            return ids, dist, cnt, ctr
+        return ids, dist, cnt
+
+    def knn_search(self, query, k, ef):
+        """-> [(doc_id, distance)] ordered by (distance, doc id), at most k  (one query)"""
+        ids, dist, cnt = self.search_graph(np.asarray(query, np.float32)[None, :], k, ef)
+        res = []  # KnnResultBuilder: BTreeSet<(dist, doc)>, pop the largest when over k; check_add uses `>`
+        for j in range(int(cnt[0])):
+            d, e = float(dist[0, j]), int(ids[0, j])
+            if len(res) >= k and d > res[-1][0]:
+                continue
+            docs = [e] if self.elem_docs is None else self.elem_docs[e]
+            for doc in docs:
+                res.append((d, int(doc)))
+                res.sort()
+                if len(res) > k:
+                    res.pop()
+        return [(doc, d) for d, doc in res]
+
+    def close(self):
+        if self.h:
+            L.lib().sdb_hnsw_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,90 @@
+"""HNSW layer walk on the GPU (through the C ABI) vs the oracle's restatement of Hnsw::knn_search on the SAME
+graph: element ids, their order, the f64 distances and the visit counters must be identical."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from surrealdb_b200 import Context
+    return Context(0)
+
+
+def build(data, metric, m, efc, seed=1, **kw):
+    h = O.Hnsw(data.shape[1], metric, m=m, efc=efc, seed=seed, **kw)
+    for v in data:
+        h.insert(v)
+    assert h.check_props()
+    return h.export()
+
+
+@pytest.mark.parametrize("metric", ["euclidean", "cosine"])
+@pytest.mark.parametrize("dim", [5, 20, 96, 100])
+def test_walk_parity_random_graphs(ctx, metric, dim):
+    from surrealdb_b200.hnsw import HnswIndex
+    rng = np.random.default_rng(dim + len(metric))
+    data = rng.uniform(-20, 20, (1500, dim)).astype(np.float32)
+    g = build(data, metric, m=8, efc=60)
+    idx = HnswIndex(ctx, g["vectors"], g["layers"], g["entry_point"], metric)
+    queries = rng.uniform(-20, 20, (70, dim)).astype(np.float32)
+    for k, ef in ((10, 10), (10, 40), (1, 1), (25, 64), (10, 150)):
+        ids, dist, cnt, ctr = idx.search_graph(queries, k, ef, counters=True)
+        for q in range(queries.shape[0]):
+            oi, od, oc = O.hnsw_search_csr(g, queries[q], k, ef)
+            assert cnt[q] == oi.size
+            assert list(ids[q, : cnt[q]]) == list(oi), (k, ef, q)
+            assert dist[q, : cnt[q]].tobytes() == od.tobytes(), (k, ef, q)
+            assert (int(ctr[q, 0]), int(ctr[q, 1])) == oc, (k, ef, q)
+
+
+def test_reference_recall_fixture_through_gpu(ctx):
+    # the reference's recall test (hnsw/mod.rs:1144-1184) with the walk on the GPU: recall >= 0.98 @ef=10,
+    # == 1.0 @ef=40, and whenever recall is 1.0 the result equals brute force exactly
+    from surrealdb_b200.hnsw import HnswIndex
+    data = np.load(os.path.join(G, "hnsw_ingest_1000x20.f64.npy")).astype(np.float32)
+    qs = np.load(os.path.join(G, "hnsw_query_300x20.f64.npy")).astype(np.float32)
+    g = build(data, "euclidean", m=8, efc=100, seed=42)
+    idx = HnswIndex(ctx, g["vectors"], g["layers"], g["entry_point"], "EUCLIDEAN")
+    for efs, expected in ((10, 0.98), (40, 1.0)):
+        total = 0.0
+        for q in qs:
+            res = idx.knn_search(q, 10, efs)
+            assert len(res) == 10
+            bi, bd = O.vec_knn_f32(data, q, "euclidean", 10)
+            rec = len({d for d, _ in res} & set(bi.tolist())) / 10.0
+            if rec == 1.0:
+                assert [(d, x) for d, x in res] == list(zip(bi.tolist(), bd.tolist()))
+            total += rec
+        assert total / len(qs) >= expected
+
+
+def test_language_test_hnsw_vectors(ctx):
+    # language-tests/.../hnsw_knn_new_executor.surql: pts [1,2,3,4],[4,5,6,7],[8,9,10,11], <|2,100|> [2,3,4,5]
+    # -> pts:1 dist 2, pts:2 dist 4
+    from surrealdb_b200.hnsw import HnswIndex
+    data = np.array([[1, 2, 3, 4], [4, 5, 6, 7], [8, 9, 10, 11]], np.float32)
+    g = build(data, "euclidean", m=12, efc=500)
+    idx = HnswIndex(ctx, g["vectors"], g["layers"], g["entry_point"], "EUCLIDEAN")
+    assert idx.knn_search([2, 3, 4, 5], 2, 100) == [(0, 2.0), (1, 4.0)]
+
+
+def test_shared_elements_expand_to_docs_and_edge_cases(ctx):
+    from surrealdb_b200 import SdbError
+    from surrealdb_b200.hnsw import HnswIndex
+    data = np.array([[0, 0], [1, 0], [5, 5]], np.float32)
+    g = build(data, "euclidean", m=4, efc=10)
+    idx = HnswIndex(ctx, g["vectors"], g["layers"], g["entry_point"], "EUCLIDEAN", elem_docs=[[7, 3], [9], [1]])
+    assert idx.knn_search([0, 0], 2, 10) == [(3, 0.0), (7, 0.0)]        # (dist, doc) order, trimmed to k
+    assert idx.knn_search([0, 0], 3, 10) == [(3, 0.0), (7, 0.0), (9, 1.0)]
+    with pytest.raises(SdbError):
+        idx.search_graph(np.zeros((1, 3), np.float32), 1, 1)             # dimension mismatch
+    empty = HnswIndex(ctx, np.zeros((0, 2), np.float32), [(np.zeros(1, np.uint64), np.zeros(0, np.uint32))], -1)
+    ids, dist, cnt = empty.search_graph(np.zeros((2, 2), np.float32), 3, 5)
+    assert list(cnt) == [0, 0]
