@@ -1,0 +1,179 @@
+#!/usr/bin/env python
+"""Secondary measurements for the other rows of SURVEY.md section 8 (NOT the driver's headline line):
+
+  python bench_extra.py hnsw  [--rows N --dim D --queries Q --ef 64 --k 10]
+  python bench_extra.py graph [--log2-nodes 24 --edges E --sources 1024 --hops 3]
+
+Each prints one JSON line with the metric, a roofline object computed from in-kernel counters
+(HNSW: visited*(4D+4) + expanded*deg*4 bytes; graph: 16|F| + 8|E_h| per hop), and a cpu_baseline obtained by
+timing the oracle (port of the reference algorithm) on the host cores for the same inputs (bounded sample).
+"""
+import argparse
+import json
+import os
+import sys
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], "measured"
+    return 6650.0, "fallback"
+
+
+def dev_time_ms(ctx, fn):
+    import torch
+    st = torch.cuda.ExternalStream(ctx.stream())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0.record(st)
+    out = fn()
+    e1.record(st)
+    e1.synchronize()
+    return out, e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3
+
+
+def bench_hnsw(a):
+    import torch
+    from surrealdb_b200 import Context, HnswIndex, VectorColumn
+    from surrealdb_b200.hnsw_build import build_layers
+    ctx = Context(0)
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(0x5DB00003)
+    n, dim = a.rows, a.dim
+    centers = torch.nn.functional.normalize(torch.randn((4096, dim), generator=g, device=dev), dim=1)
+    def sample(cnt):
+        c = torch.randint(0, 4096, (cnt,), generator=g, device=dev)
+        return (centers[c] + 0.15 * torch.randn((cnt, dim), generator=g, device=dev)).contiguous()
+    x = sample(n)
+    queries = sample(a.queries)
+    t0 = time.perf_counter()
+    layers, entry, levels = build_layers(ctx, x, n, dim, "EUCLIDEAN", m=a.m, m0=2 * a.m, seed=7)
+    build_s = time.perf_counter() - t0
+    xh = x.cpu().numpy()
+    qh = queries.cpu().numpy()
+    idx = HnswIndex(ctx, xh, layers, entry, "EUCLIDEAN")
+    idx.search_graph(qh[:256], a.k, a.ef)  # warm-up
+    (ids, dist, cnt, ctr), ms, wall = dev_time_ms(ctx, lambda: idx.search_graph(qh, a.k, a.ef, counters=True))
+    deg0 = float(np.diff(layers[0][0].astype(np.int64)).mean())
+    visited, expanded = int(ctr[:, 0].sum()), int(ctr[:, 1].sum())
+    byts = visited * (4.0 * dim + 4.0) + expanded * deg0 * 4.0
+    # recall@k against exact brute force (f64 reference arithmetic) on the same corpus
+    col = VectorColumn(ctx, dim, "EUCLIDEAN", "F32", capacity=n)
+    col.append_device(x.data_ptr(), n)
+    col.finalize()
+    nr = min(a.queries, 2000)
+    rows, _, _ = col.knn(qh[:nr].astype(np.float64), a.k)
+    recall = float(np.mean([len(set(rows[i].tolist()) & set(ids[i, : cnt[i]].tolist())) / a.k for i in range(nr)]))
+    peak, src = peaks()
+    out = {"bench": "hnsw_search", "metric": f"HNSW KNN queries/sec (M={a.m}, M0={2*a.m}, ef={a.ef}, k={a.k})",
+           "value": a.queries / (wall * 1e-3), "unit": "queries/s", "device_ms": ms, "call_wall_ms": wall,
+           "recall_at_k": recall, "config": {"rows": n, "dim": dim, "queries": a.queries, "data": "4096-centroid gaussian mixture, sigma 0.15",
+                                              "graph": "GPU batch-built exact kNN layers (hnsw_build.py)", "build_s": build_s,
+                                              "layers": len(layers), "visited_per_query": visited / a.queries,
+                                              "expanded_per_query": expanded / a.queries},
+           "roofline": {"bound": "hbm", "kernel": "hnsw_search_kernel", "achieved": byts / (ms * 1e-3) / 1e9, "peak": peak,
+                        "unit": "GB/s", "frac": byts / (ms * 1e-3) / 1e9 / peak, "peak_source": src,
+                        "algorithmic_bytes": byts, "traffic": None}}
+    if not a.no_cpu:
+        from oracle import pyoracle as O
+        graph = {"vectors": xh, "layers": layers, "entry_point": entry, "metric": "euclidean"}
+        threads = os.cpu_count() or 1
+        nqc = min(a.queries, 8 * threads)
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(threads) as ex:
+            res = list(ex.map(lambda i: O.hnsw_search_csr(graph, qh[i], a.k, a.ef), range(nqc)))
+        dt = time.perf_counter() - t0
+        same = all(list(res[i][0]) == list(ids[i, : cnt[i]]) for i in range(nqc))
+        out["cpu_baseline"] = {"value": nqc / dt, "unit": "queries/s", "cores": threads, "kind": "port",
+                               "sample": f"{nqc} of the same queries, same graph, {threads} threads, {dt:.2f}s; "
+                                         f"results identical to the GPU walk: {same}"}
+    print(json.dumps(out), flush=True)
+
+
+def bench_graph(a):
+    import torch
+    from surrealdb_b200 import Context
+    from surrealdb_b200.graph import CsrGraph, collect, expand
+    ctx = Context(0)
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(0x5DB00005)
+    bits, E = a.log2_nodes, a.edges
+    n_nodes = 1 << bits
+    src = torch.zeros(E, dtype=torch.int64, device=dev)
+    dst = torch.zeros(E, dtype=torch.int64, device=dev)
+    for b in range(bits):  # R-MAT a,b,c,d = .57,.19,.19,.05
+        r = torch.rand(E, generator=g, device=dev)
+        src = (src << 1) | (r >= 0.76).long()
+        dst = (dst << 1) | (((r >= 0.57) & (r < 0.76)) | (r >= 0.95)).long()
+    key = torch.unique(src * n_nodes + dst)  # one edge per (src,dst); edge ids in (src,dst) order => KV order
+    src, dst = key // n_nodes, key % n_nodes
+    E = int(key.numel())
+    row_ptr = torch.zeros(n_nodes + 1, dtype=torch.int64, device=dev)
+    row_ptr[1:] = torch.cumsum(torch.bincount(src, minlength=n_nodes), 0)
+    rp = row_ptr.cpu().numpy().astype(np.uint64)
+    ci = dst.to(torch.int32).cpu().numpy().astype(np.uint32)
+    del src, dst, key
+    graph = CsrGraph(ctx, rp, ci)
+    deg = np.diff(rp.astype(np.int64))
+    rng = np.random.default_rng(11)
+    sources = rng.choice(np.nonzero(deg > 0)[0], a.sources, replace=False).astype(np.uint32)
+    expand([graph] * a.hops, sources[:8])  # warm-up
+    out_ids, ms, wall = dev_time_ms(ctx, lambda: expand([graph] * a.hops, sources))
+    # per-hop sizes for the algorithmic byte count
+    sizes = [int(sources.size)]
+    fr = sources
+    for h in range(a.hops - 1):
+        fr = expand([graph], fr)
+        sizes.append(int(fr.size))
+    sizes.append(int(out_ids.size))
+    byts = sum(16.0 * sizes[h] + 8.0 * sizes[h + 1] for h in range(a.hops))
+    (coll, cms, cwall) = dev_time_ms(ctx, lambda: collect(graph, sources[:1], 1, a.hops, False))
+    peak, srcp = peaks()
+    res = {"bench": "graph_expand", "metric": f"{a.hops}-hop ->edge->node multiset expansion, traversed edges/sec",
+           "value": sum(sizes[1:]) / (ms * 1e-3), "unit": "edges/s", "device_ms": ms, "call_wall_ms": wall,
+           "config": {"nodes": n_nodes, "edges": E, "sources": int(sources.size), "hops": a.hops, "frontier_sizes": sizes,
+                      "graph": "R-MAT (.57,.19,.19,.05), integer ids, adjacency in (src,dst)=edge-id order",
+                      "collect_bfs_from_1_source": {"device_ms": cms, "nodes": int(coll.size)}},
+           "roofline": {"bound": "hbm", "kernel": "expand_kernel (+degree/scan)", "achieved": byts / (ms * 1e-3) / 1e9,
+                        "peak": peak, "unit": "GB/s", "frac": byts / (ms * 1e-3) / 1e9 / peak, "peak_source": srcp,
+                        "algorithmic_bytes": byts, "traffic": None,
+                        "note": "device_ms covers H2D of the frontier, 3x(degree, scan, expand) and the D2H of the result"}}
+    if not a.no_cpu:
+        from oracle import pyoracle as O
+        t0 = time.perf_counter()
+        fr = sources
+        for h in range(a.hops):
+            fr = O.graph_hop(rp, ci, fr, 0)
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": sum(sizes[1:]) / dt, "unit": "edges/s", "cores": 1, "kind": "port",
+                               "sample": f"same frontier, {a.hops} hops, single thread (the reference expands one "
+                                         f"lookup chain per task), {dt:.3f}s; identical output: {bool(np.array_equal(fr, out_ids))}"}
+    print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("which", choices=["hnsw", "graph"])
+    ap.add_argument("--rows", type=int, default=1_000_000)
+    ap.add_argument("--dim", type=int, default=128)
+    ap.add_argument("--queries", type=int, default=10_000)
+    ap.add_argument("--ef", type=int, default=64)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--m", type=int, default=16)
+    ap.add_argument("--log2-nodes", type=int, default=24)
+    ap.add_argument("--edges", type=int, default=160_000_000)
+    ap.add_argument("--sources", type=int, default=1024)
+    ap.add_argument("--hops", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    {"hnsw": bench_hnsw, "graph": bench_graph}[a.which](a)
