@@ -127,13 +127,13 @@ def bench_graph(a):
     deg = np.diff(rp.astype(np.int64))
     rng = np.random.default_rng(11)
     sources = rng.choice(np.nonzero(deg > 0)[0], a.sources, replace=False).astype(np.uint32)
-    expand([graph] * a.hops, sources[:8])  # warm-up
-    out_ids, ms, wall = dev_time_ms(ctx, lambda: expand([graph] * a.hops, sources))
+    expand([graph] * a.hops, sources[:8], a.limit)  # warm-up
+    out_ids, ms, wall = dev_time_ms(ctx, lambda: expand([graph] * a.hops, sources, a.limit))
     # per-hop sizes for the algorithmic byte count
     sizes = [int(sources.size)]
     fr = sources
     for h in range(a.hops - 1):
-        fr = expand([graph], fr)
+        fr = expand([graph], fr, a.limit)
         sizes.append(int(fr.size))
     sizes.append(int(out_ids.size))
     byts = sum(16.0 * sizes[h] + 8.0 * sizes[h + 1] for h in range(a.hops))
@@ -141,7 +141,7 @@ def bench_graph(a):
     peak, srcp = peaks()
     res = {"bench": "graph_expand", "metric": f"{a.hops}-hop ->edge->node multiset expansion, traversed edges/sec",
            "value": sum(sizes[1:]) / (ms * 1e-3), "unit": "edges/s", "device_ms": ms, "call_wall_ms": wall,
-           "config": {"nodes": n_nodes, "edges": E, "sources": int(sources.size), "hops": a.hops, "frontier_sizes": sizes,
+           "config": {"nodes": n_nodes, "edges": E, "sources": int(sources.size), "hops": a.hops, "per_source_limit": a.limit, "frontier_sizes": sizes,
                       "graph": "R-MAT (.57,.19,.19,.05), integer ids, adjacency in (src,dst)=edge-id order",
                       "collect_bfs_from_1_source": {"device_ms": cms, "nodes": int(coll.size)}},
            "roofline": {"bound": "hbm", "kernel": "expand_kernel (+degree/scan)", "achieved": byts / (ms * 1e-3) / 1e9,
@@ -153,7 +153,7 @@ def bench_graph(a):
         t0 = time.perf_counter()
         fr = sources
         for h in range(a.hops):
-            fr = O.graph_hop(rp, ci, fr, 0)
+            fr = O.graph_hop(rp, ci, fr, a.limit)
         dt = time.perf_counter() - t0
         res["cpu_baseline"] = {"value": sum(sizes[1:]) / dt, "unit": "edges/s", "cores": 1, "kind": "port",
                                "sample": f"same frontier, {a.hops} hops, single thread (the reference expands one "
@@ -174,6 +174,7 @@ if __name__ == "__main__":
     ap.add_argument("--edges", type=int, default=160_000_000)
     ap.add_argument("--sources", type=int, default=1024)
     ap.add_argument("--hops", type=int, default=3)
+    ap.add_argument("--limit", type=int, default=32, help="GraphEdgeScan per-source limit (0 = none)")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
     {"hnsw": bench_hnsw, "graph": bench_graph}[a.which](a)

@@ -62,7 +62,7 @@ typedef enum {
 typedef enum { SDB_F32 = 0, SDB_F64 = 1 } sdb_dtype;
 
 /* which screening kernel sdb_knn_bruteforce uses (results are identical for all; this only moves
- * the performance point).  AUTO: <= 8 queries -> streaming SIMT f32 kernel, else tcgen05 bf16. */
+ * the performance point).  AUTO: tcgen05 bf16 (HBM-bound on half the bytes for small batches, tensor-bound for large ones). */
 typedef enum { SDB_SCREEN_AUTO = 0, SDB_SCREEN_SIMT_F32 = 1, SDB_SCREEN_TC_BF16 = 2, SDB_SCREEN_NONE_EXACT = 3 } sdb_screen;
 
 /* counters of the last brute-force call on a corpus (diagnostics / bench roofline arithmetic) */

@@ -55,7 +55,9 @@ static sdb_status knn_device_locked(Corpus* c, const double* d_queries, uint32_t
 
   // ---- choose the screen ----
   sdb_screen scr = c->screen;
-  if (scr == SDB_SCREEN_AUTO) scr = (nq <= 8 || !screen_tc_available()) ? SDB_SCREEN_SIMT_F32 : SDB_SCREEN_TC_BF16;
+  // AUTO: the bf16 tensor-core screen reads half the bytes of the f32 stream and is HBM-bound for small batches,
+  // so it wins at every batch size; the f32 SIMT stream stays selectable (SDB_SCREEN_SIMT_F32)
+  if (scr == SDB_SCREEN_AUTO) scr = screen_tc_available() ? SDB_SCREEN_TC_BF16 : SDB_SCREEN_SIMT_F32;
   if (scr == SDB_SCREEN_TC_BF16 && !screen_tc_available()) scr = SDB_SCREEN_SIMT_F32;
   if (c->dtype == SDB_F64 || c->special_overflow || k > 256) scr = SDB_SCREEN_NONE_EXACT;
   const uint32_t kp = k + (k > 54 ? k : 54);

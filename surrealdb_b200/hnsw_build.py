@@ -58,7 +58,7 @@ def build_layers(ctx, vectors_dev, n, dim, metric="EUCLIDEAN", m=16, m0=32, seed
             valid = np.arange(k)[None, :] < cnt[:, None]
             keep = valid & (r != (b0 + np.arange(b1 - b0))[:, None])  # drop self, keep nearest-first order
             order = np.argsort(~keep, axis=1, kind="stable")[:, :k_nb]
-            nbrs[b0:b1] = np.take_along_axis(r, order, axis=1)
+            nbrs[b0:b1, : order.shape[1]] = np.take_along_axis(r, order, axis=1)
             counts[b0:b1] = np.minimum(keep.sum(1), k_nb)
             if progress:
                 progress(l, b1, members.size)
