@@ -290,7 +290,7 @@ def main():
     # ---- HBM-bound regime (small batches), reported next to the headline: f32 streaming kernel and bf16 screen ----
     hbm_regime = []
     if world == 1:
-        for scr, b in (("SIMT_F32", 1), ("SIMT_F32", 8), ("TC_BF16", 16)):
+        for scr, b in (("SIMT_F32", 1), ("SIMT_F32", 8), ("TC_BF16", 16), ("TC_INT8", 16)):
             col.set_screen(scr)
             qd = q_dev[0][:b].contiguous()
             best = None
@@ -298,7 +298,7 @@ def main():
                 col.knn_device(qd.data_ptr(), b, k, base, o_rows.data_ptr(), o_dist.data_ptr(), o_cnt.data_ptr())
                 s = col.stats()
                 best = s if best is None or s["screen_ms"] < best["screen_ms"] else best
-            byts = n_local * (dim * (4.0 if scr == "SIMT_F32" else 2.0) + 4.0) + b * dim * 4.0
+            byts = n_local * (dim * {"SIMT_F32": 4.0, "TC_BF16": 2.0, "TC_INT8": 1.0}[scr] + 4.0) + b * dim * 4.0
             hbm_regime.append({"screen": scr, "batch": b, "screen_ms": best["screen_ms"], "total_ms": best["total_ms"],
                                "algorithmic_bytes": byts, "GBps": byts / (best["screen_ms"] * 1e-3) / 1e9,
                                "qps": b / (best["total_ms"] * 1e-3)})
@@ -310,14 +310,17 @@ def main():
         qps_e2e = batch * args.steps / (ms_e2e * 1e-3)
         scr_ms = float(np.mean(screen_ms))
         n_shard = n_local
-        screen_name = {1: "SIMT_F32", 2: "TC_BF16", 3: "NONE_EXACT"}.get(stats["screen_used"], "?")
-        if stats["screen_used"] == 2:
+        screen_name = {1: "SIMT_F32", 2: "TC_BF16", 3: "NONE_EXACT", 4: "TC_INT8"}.get(stats["screen_used"], "?")
+        if stats["screen_used"] in (2, 4):
             flops = 2.0 * batch * n_shard * dim
             ach = flops / (scr_ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "screen_tc_bf16 (tcgen05)", "achieved": ach,
-                    "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
-                    "peak_source": pk["source"] + " (sustained cuBLAS bf16)", "traffic": None,
-                    "algorithmic_flops_per_launch": flops}
+            i8 = stats["screen_used"] == 4
+            peak = pk["bf16_tflops_sustained"] * (2.0 if i8 else 1.0)
+            roof = {"bound": "tensor", "kernel": "screen_tc_kernel<cosine,int8> (tcgen05 kind::i8)" if i8 else "screen_tc_kernel (tcgen05 kind::f16 bf16)",
+                    "achieved": ach, "peak": peak, "unit": "TOP/s" if i8 else "TFLOP/s", "frac": ach / peak,
+                    "peak_source": pk["source"] + (" (2 x sustained cuBLAS bf16: the int8 tensor rate is twice the bf16 rate on B200; "
+                                                   "MEASURED_PEAKS.json has no int8 figure)" if i8 else " (sustained cuBLAS bf16)"),
+                    "traffic": None, "algorithmic_flops_per_launch": flops}
         else:
             passes_over_corpus = (batch + 7) // 8
             byts = passes_over_corpus * (n_shard * dim * 4.0 + n_shard * 4.0) + batch * dim * 4.0
@@ -331,7 +334,7 @@ def main():
                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic",
                "config": {"workload": args.workload, "rows": rows, "dim": dim, "batch": batch, "k": k,
-                          "metric": "cosine", "corpus_dtype": "f32 master + bf16 screen copy",
+                          "metric": "cosine", "corpus_dtype": "f32 master + bf16 and int8 screen copies",
                           "screen": screen_name, "exact_rerank": "f64 sequential (reference arithmetic)",
                           "sharding": f"rows/{world}", "l2": "corpus shard (>= 3.8 GB) is larger than L2; no flush needed",
                           "fallback_queries_in_timed_region": int(fallbacks)},

@@ -63,7 +63,13 @@ typedef enum { SDB_F32 = 0, SDB_F64 = 1 } sdb_dtype;
 
 /* which screening kernel sdb_knn_bruteforce uses (results are identical for all; this only moves
  * the performance point).  AUTO: tcgen05 bf16 (HBM-bound on half the bytes for small batches, tensor-bound for large ones). */
-typedef enum { SDB_SCREEN_AUTO = 0, SDB_SCREEN_SIMT_F32 = 1, SDB_SCREEN_TC_BF16 = 2, SDB_SCREEN_NONE_EXACT = 3 } sdb_screen;
+typedef enum {
+  SDB_SCREEN_AUTO = 0,
+  SDB_SCREEN_SIMT_F32 = 1,   /* f32 streaming SIMT kernel                                             */
+  SDB_SCREEN_TC_BF16 = 2,    /* tcgen05 kind::f16, bf16 operands                                        */
+  SDB_SCREEN_NONE_EXACT = 3, /* no screen: exact f64 kernel for every query                              */
+  SDB_SCREEN_TC_INT8 = 4     /* tcgen05 kind::i8, per-row int8 quantisation (cosine); falls back to bf16 */
+} sdb_screen;
 
 /* counters of the last brute-force call on a corpus (diagnostics / bench roofline arithmetic) */
 typedef struct {

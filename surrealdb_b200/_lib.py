@@ -15,7 +15,7 @@ STATUS_NAMES = ["SDB_OK", "SDB_EINVAL", "SDB_EDIM", "SDB_ENOMEM", "SDB_ECUDA", "
 METRIC = {"CHEBYSHEV": 0, "COSINE": 1, "EUCLIDEAN": 2, "HAMMING": 3, "JACCARD": 4, "MANHATTAN": 5,
           "MINKOWSKI": 6, "PEARSON": 7}
 DTYPE = {"F32": 0, "F64": 1}
-SCREEN = {"AUTO": 0, "SIMT_F32": 1, "TC_BF16": 2, "NONE_EXACT": 3}
+SCREEN = {"AUTO": 0, "SIMT_F32": 1, "TC_BF16": 2, "NONE_EXACT": 3, "TC_INT8": 4}
 
 # every symbol include/sdbgpu.h declares (tests/test_abi_symbols.py cross-checks this list with the header)
 ABI_SYMBOLS = [

@@ -54,26 +54,31 @@ static sdb_status knn_device_locked(Corpus* c, const double* d_queries, uint32_t
   SDB_CUDA(cudaEventRecord(ev[0], st));
 
   // ---- choose the screen ----
+  // AUTO: the tensor-core screens read 1/2 (bf16) or 1/4 (int8) of the bytes of the f32 stream and are HBM-bound for
+  // small batches, so they win at every batch size; int8 is used when the corpus quantises well enough for its
+  // error bound to be provable (cosine only); the f32 SIMT stream stays selectable (SDB_SCREEN_SIMT_F32).
+  const bool int8_ok = c->d_i8 && c->metric == SDB_COSINE && screen_tc_available();
   sdb_screen scr = c->screen;
-  // AUTO: the bf16 tensor-core screen reads half the bytes of the f32 stream and is HBM-bound for small batches,
-  // so it wins at every batch size; the f32 SIMT stream stays selectable (SDB_SCREEN_SIMT_F32)
-  if (scr == SDB_SCREEN_AUTO) scr = screen_tc_available() ? SDB_SCREEN_TC_BF16 : SDB_SCREEN_SIMT_F32;
+  if (scr == SDB_SCREEN_AUTO)
+    scr = !screen_tc_available() ? SDB_SCREEN_SIMT_F32 : (int8_ok && c->max_rel_qerr <= 0.006f ? SDB_SCREEN_TC_INT8 : SDB_SCREEN_TC_BF16);
+  if (scr == SDB_SCREEN_TC_INT8 && !int8_ok) scr = SDB_SCREEN_TC_BF16;
   if (scr == SDB_SCREEN_TC_BF16 && !screen_tc_available()) scr = SDB_SCREEN_SIMT_F32;
   if (c->dtype == SDB_F64 || c->special_overflow || k > 256) scr = SDB_SCREEN_NONE_EXACT;
-  const uint32_t kp = k + (k > 54 ? k : 54);
+  const uint32_t kp = k + (k > 54 ? k : 54) + (scr == SDB_SCREEN_TC_INT8 ? 64 : 0);  // looser screen => more slack
   uint32_t cap = 4096;
   while (cap < 16 * kp) cap <<= 1;
   SDB_TRY(scratch_for(c, nq, cap, kp));
   cap = c->sc_cap;
   SDB_TRY(prep_queries(c, d_queries, nq, st));
   std::vector<uint32_t> h_flags(nq, 2u), h_qflags(nq, 0u);
-  if (scr != SDB_SCREEN_NONE_EXACT) {
+  SDB_CUDA(cudaEventRecord(ev[1], st));
+  for (int attempt = 0; attempt < 2 && scr != SDB_SCREEN_NONE_EXACT; attempt++) {
     const float eps_rel = scr == SDB_SCREEN_SIMT_F32
                               ? (float)((c->dim / 16.0 + 16.0) * 1.1920929e-7)
                               : (float)(0.00390625 * 1.01 + c->dim * 4.76837158e-7 + 1e-5);
     std::vector<PassDesc> passes = build_passes(c->n, cap);
     SDB_TRY(cand_reset(c, nq, st));
-    SDB_CUDA(cudaEventRecord(ev[1], st));
+    SDB_TRY(set_bounds(c, nq, (int)scr, eps_rel, st));
     for (const PassDesc& p : passes) {
       if (cancel && *cancel) {
         cudaStreamSynchronize(st);
@@ -82,19 +87,25 @@ static sdb_status knn_device_locked(Corpus* c, const double* d_queries, uint32_t
         return SDB_ECANCELLED;
       }
       if (scr == SDB_SCREEN_SIMT_F32) SDB_TRY(screen_simt_pass(c, nq, p, st));
-      else SDB_TRY(screen_tc_pass(c, nq, p, st));
+      else SDB_TRY(screen_tc_pass(c, nq, p, scr == SDB_SCREEN_TC_INT8, st));
       SDB_TRY(cand_compact(c, nq, kp, st));
     }
     SDB_CUDA(cudaEventRecord(ev[2], st));
     SDB_TRY(cand_rerank(c, nq, st));
     SDB_TRY(cand_final(c, nq, k, kp, eps_rel, row_base, d_out_rows, d_out_dist, d_out_count, st));
     SDB_CUDA(cudaMemcpyAsync(h_flags.data(), c->d_flags, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, st));
-    stt.n_passes = (uint32_t)passes.size();
-    stt.n_reranked = (uint64_t)nq * (kp + c->n_special);
-  } else {
-    SDB_CUDA(cudaEventRecord(ev[1], st));
-    SDB_CUDA(cudaEventRecord(ev[2], st));
+    stt.n_passes += (uint32_t)passes.size();
+    stt.n_reranked += (uint64_t)nq * (kp + c->n_special);
+    if (scr != SDB_SCREEN_TC_INT8) break;
+    // precision ladder: if the int8 proof failed for more than a handful of queries, re-screen the batch in bf16
+    SDB_CUDA(cudaStreamSynchronize(st));
+    uint32_t n_fail = 0;
+    for (uint32_t q = 0; q < nq; q++) n_fail += (h_flags[q] & 2u) ? 1u : 0u;
+    if (n_fail <= 2 + nq / 64) break;
+    scr = SDB_SCREEN_TC_BF16;
+    stt.n_candidates += n_fail;  // (diagnostic: queries handed down the ladder)
   }
+  if (scr == SDB_SCREEN_NONE_EXACT) SDB_CUDA(cudaEventRecord(ev[2], st));
   SDB_CUDA(cudaMemcpyAsync(h_qflags.data(), c->d_qflags, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, st));
   SDB_CUDA(cudaStreamSynchronize(st));
   // ---- exact path for everything the screens could not prove ----
@@ -257,6 +268,7 @@ sdb_status sdb_corpus_create(sdb_ctx* ctx, uint32_t dim, sdb_dtype dt, sdb_metri
   c->ctx = ctx;
   c->dim = dim;
   c->dim_pad = (dim + 63) / 64 * 64;
+  c->dim_pad8 = (dim + 127) / 128 * 128;
   c->dtype = dt;
   c->metric = m;
   c->cap = cap;
@@ -266,6 +278,10 @@ sdb_status sdb_corpus_create(sdb_ctx* ctx, uint32_t dim, sdb_dtype dt, sdb_metri
   if (e == cudaSuccess) e = cudaMalloc(&c->d_mag, sizeof(double) * cap);
   if (e == cudaSuccess) e = cudaMalloc(&c->d_snorm, sizeof(float) * cap_pad);
   if (e == cudaSuccess && dt == SDB_F32) e = cudaMalloc(&c->d_bf16, sizeof(__nv_bfloat16) * cap_pad * c->dim_pad);
+  if (e == cudaSuccess && dt == SDB_F32 && m == SDB_COSINE) {
+    e = cudaMalloc(&c->d_i8, (size_t)cap_pad * c->dim_pad8);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_snorm8, sizeof(float) * cap_pad);
+  }
   if (e != cudaSuccess) {
     set_error("corpus allocation failed: %s", cudaGetErrorString(e));
     sdb_corpus_destroy(c);
@@ -277,7 +293,8 @@ sdb_status sdb_corpus_create(sdb_ctx* ctx, uint32_t dim, sdb_dtype dt, sdb_metri
 void sdb_corpus_destroy(sdb_corpus* c) {
   if (!c) return;
   cudaSetDevice(c->ctx->device);
-  void* ptrs[] = {c->d_rows, c->d_mag, c->d_snorm, c->d_bf16, c->d_skip, c->d_special, c->d_q64, c->d_q32,
+  void* ptrs[] = {c->d_i8, c->d_snorm8, c->d_q8, c->d_q8scale, c->d_q8err, c->d_bscale, c->d_beps,
+                  c->d_rows, c->d_mag, c->d_snorm, c->d_bf16, c->d_skip, c->d_special, c->d_q64, c->d_q32,
                   c->d_qbf16, c->d_qmag, c->d_qflags, c->d_tau, c->d_cand, c->d_cand_cnt, c->d_flags,
                   c->d_rr_key, c->d_rr_dist, c->d_rr_row, c->d_ex_key, c->d_sel, c->d_out_rows, c->d_out_dist,
                   c->d_out_count, c->d_in_q};
@@ -345,7 +362,7 @@ sdb_status sdb_corpus_finalize(sdb_corpus* c) {
   return corpus_finalize_device(c);
 }
 sdb_status sdb_corpus_set_screen(sdb_corpus* c, sdb_screen s) {
-  if (!c || (int)s < 0 || (int)s > 3) return SDB_EINVAL;
+  if (!c || (int)s < 0 || (int)s > 4) return SDB_EINVAL;
   c->screen = s;
   return SDB_OK;
 }

@@ -49,12 +49,82 @@ __global__ void prep_queries_kernel(const double* __restrict__ q64, uint32_t dim
   }
 }
 
+// symmetric int8 quantisation of the queries (same scheme as the corpus rows), one block per query
+__global__ void __launch_bounds__(128) prep_queries_i8_kernel(const float* __restrict__ q32, const double* __restrict__ qmag,
+                                                              uint32_t dim, uint32_t dim_pad8, uint32_t nq,
+                                                              int8_t* __restrict__ q8, float* __restrict__ q8scale,
+                                                              float* __restrict__ q8err) {
+  __shared__ float s_red[4];
+  const uint32_t q = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int8_t* o = q8 + (size_t)q * dim_pad8;
+  if (q >= nq) {
+    for (uint32_t c = threadIdx.x; c < dim_pad8; c += blockDim.x) o[c] = 0;
+    return;
+  }
+  const float* x = q32 + (size_t)q * dim;
+  float mx = 0.f;
+  for (uint32_t c = threadIdx.x; c < dim; c += blockDim.x) mx = fmaxf(mx, fabsf(x[c]));
+#pragma unroll
+  for (int o2 = 16; o2 > 0; o2 >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o2));
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+  __syncthreads();
+  const bool ok = mx > 0.f && isfinite(mx);
+  const float s = ok ? mx / 127.f : 1.f, inv = 1.f / s;
+  float err2 = 0.f;
+  for (uint32_t c = threadIdx.x; c < dim_pad8; c += blockDim.x) {
+    int v = 0;
+    if (ok && c < dim) {
+      v = __float2int_rn(x[c] * inv);
+      v = v > 127 ? 127 : (v < -127 ? -127 : v);
+      const float d = x[c] - (float)v * s;
+      err2 = fmaf(d, d, err2);
+    }
+    o[c] = (int8_t)v;
+  }
+#pragma unroll
+  for (int o2 = 16; o2 > 0; o2 >>= 1) err2 += __shfl_xor_sync(0xffffffffu, err2, o2);
+  if (lane == 0) s_red[warp] = err2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float e = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+    q8scale[q] = s;
+    // relative to the f64 norm; +2^-23 covers the f64 -> f32 rounding of the query itself; rounded up
+    q8err[q] = ok ? (sqrtf(e) / (float)qmag[q]) * 1.0001f + 2.4e-7f : 1.f;
+  }
+}
+
+// per-query (tau scale, rigorous error bound) of the screen that is about to run
+__global__ void set_bounds_kernel(float* bscale, float* beps, const float* q8scale, const float* q8err, uint32_t nq, int int8,
+                                  float eps_rel, float max_rel_qerr) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  if (int8) {
+    // sim = s_q * score / |q| + (s_q q8 . dx + dq . x) / (|q||x|);  |second term| <= (1 + e_q) e_x + e_q
+    const float eq = q8err[q];
+    bscale[q] = q8scale[q];
+    beps[q] = (1.f + eq) * max_rel_qerr + eq + 2e-6f;
+  } else {
+    bscale[q] = 1.f;
+    beps[q] = eps_rel;
+  }
+}
+sdb_status set_bounds(Corpus* c, uint32_t nq, int screen, float eps_rel, cudaStream_t st) {
+  set_bounds_kernel<<<(nq + 255) / 256, 256, 0, st>>>(c->d_bscale, c->d_beps, c->d_q8scale, c->d_q8err, nq,
+                                                      screen == SDB_SCREEN_TC_INT8, eps_rel, c->max_rel_qerr);
+  count_launch(c->ctx);
+  SDB_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
+
 static sdb_status ensure_scratch(Corpus* c, uint32_t nq, uint32_t cap, uint32_t kp) {
   const uint32_t nq_pad = (nq + 127) / 128 * 128;
   if (c->sc_nq >= nq_pad && c->sc_cap >= cap && c->sc_kp >= kp) return SDB_OK;
   cudaFree(c->d_q64); cudaFree(c->d_q32); cudaFree(c->d_qbf16); cudaFree(c->d_qmag); cudaFree(c->d_qflags);
   cudaFree(c->d_tau); cudaFree(c->d_cand); cudaFree(c->d_cand_cnt); cudaFree(c->d_flags);
   cudaFree(c->d_rr_key); cudaFree(c->d_rr_dist); cudaFree(c->d_rr_row);
+  cudaFree(c->d_q8); cudaFree(c->d_q8scale); cudaFree(c->d_q8err); cudaFree(c->d_bscale); cudaFree(c->d_beps);
   c->sc_nq = c->sc_cap = c->sc_kp = 0;
   const uint32_t nqa = nq_pad > c->sc_nq ? nq_pad : c->sc_nq;
   const uint32_t capa = cap;
@@ -71,6 +141,11 @@ static sdb_status ensure_scratch(Corpus* c, uint32_t nq, uint32_t cap, uint32_t 
   SDB_CUDA(cudaMalloc(&c->d_rr_key, sizeof(uint64_t) * (size_t)nqa * c->rr_stride));
   SDB_CUDA(cudaMalloc(&c->d_rr_dist, sizeof(double) * (size_t)nqa * c->rr_stride));
   SDB_CUDA(cudaMalloc(&c->d_rr_row, sizeof(uint32_t) * (size_t)nqa * c->rr_stride));
+  SDB_CUDA(cudaMalloc(&c->d_q8, (size_t)nqa * (c->dim_pad8 ? c->dim_pad8 : 128)));
+  SDB_CUDA(cudaMalloc(&c->d_q8scale, sizeof(float) * nqa));
+  SDB_CUDA(cudaMalloc(&c->d_q8err, sizeof(float) * nqa));
+  SDB_CUDA(cudaMalloc(&c->d_bscale, sizeof(float) * nqa));
+  SDB_CUDA(cudaMalloc(&c->d_beps, sizeof(float) * nqa));
   c->sc_nq = nqa;
   c->sc_cap = capa;
   c->sc_kp = kp;
@@ -87,6 +162,11 @@ sdb_status prep_queries(Corpus* c, const double* d_queries, uint32_t nq, cudaStr
   prep_queries_kernel<<<nq_pad, 128, 0, st>>>(c->d_q64, c->dim, c->dim_pad, (int)c->metric, c->d_q32, c->d_qbf16,
                                               c->d_qmag, c->d_qflags, nq);
   count_launch(c->ctx);
+  if (c->d_i8) {
+    prep_queries_i8_kernel<<<nq_pad, 128, 0, st>>>(c->d_q32, c->d_qmag, c->dim, c->dim_pad8, nq, c->d_q8, c->d_q8scale,
+                                                   c->d_q8err);
+    count_launch(c->ctx);
+  }
   SDB_CUDA(cudaGetLastError());
   return SDB_OK;
 }
@@ -284,7 +364,8 @@ sdb_status cand_rerank(Corpus* c, uint32_t nq, cudaStream_t st) {
 __global__ void __launch_bounds__(1024) cand_final_kernel(
     const uint64_t* __restrict__ rr_key, const double* __restrict__ rr_dist, const uint32_t* __restrict__ rr_row,
     uint32_t rr_stride, const uint32_t* __restrict__ cnt, uint32_t cap, uint32_t n_special,
-    const float* __restrict__ tau, const double* __restrict__ qmag, uint32_t* __restrict__ flags, int metric,
+    const float* __restrict__ tau, const double* __restrict__ qmag, const float* __restrict__ bscale,
+    const float* __restrict__ beps, uint32_t* __restrict__ flags, int metric,
     float eps_rel, float max_norm, uint32_t k, uint32_t kp, uint64_t row_base, uint64_t* __restrict__ out_rows,
     double* __restrict__ out_dist, uint32_t* __restrict__ out_count, int debug) {
   extern __shared__ uint64_t s_mem[];
@@ -343,7 +424,7 @@ __global__ void __launch_bounds__(1024) cand_final_kernel(
       bool ok;
       if (metric == SDB_COSINE) {
         // non-candidate: score = dot~ * (1/|x|)~ <= tau  =>  sim <= tau/|q| + eps  =>  dist >= 1 - tau/|q| - eps
-        const double bound = 1.0 - (double)t / qm - (double)eps_rel - 1e-9;
+        const double bound = 1.0 - (double)t * (double)bscale[q] / qm - (double)beps[q] - 1e-9;
         ok = dist_key(bound) > kth;
       } else {
         // score = 2 dot~ - |x|^2~ <= tau  =>  d^2 = |x|^2 - 2 dot + |q|^2 >= -tau + |q|^2 - eps_e
@@ -373,7 +454,7 @@ sdb_status cand_final(Corpus* c, uint32_t nq, uint32_t k, uint32_t kp, float eps
     attr_set = true;
   }
   cand_final_kernel<<<nq, 1024, smem, st>>>(c->d_rr_key, c->d_rr_dist, c->d_rr_row, c->rr_stride, c->d_cand_cnt,
-                                            c->sc_cap, c->n_special, c->d_tau, c->d_qmag, c->d_flags,
+                                            c->sc_cap, c->n_special, c->d_tau, c->d_qmag, c->d_bscale, c->d_beps, c->d_flags,
                                             (int)c->metric, eps_rel, c->max_norm, k, kp, row_base, d_out_rows,
                                             d_out_dist, d_out_count, getenv("SDB_DEBUG") != nullptr);
   count_launch(c->ctx);

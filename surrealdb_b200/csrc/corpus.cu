@@ -72,12 +72,61 @@ __global__ void to_bf16_kernel(const float* __restrict__ rows, uint32_t dim, uin
   }
 }
 
+// per-row symmetric int8 quantisation x8 = rn(x / s), s = max|x| / 127 (one warp per row)
+__global__ void __launch_bounds__(256) quantize_rows_kernel(const float* __restrict__ rows, uint32_t dim, uint32_t dim_pad8,
+                                                            uint64_t n, uint64_t n_pad, const double* __restrict__ mag,
+                                                            const float* __restrict__ snorm, int8_t* __restrict__ out,
+                                                            float* __restrict__ snorm8, uint32_t* max_rel_bits) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warps = (uint64_t)gridDim.x * 8;
+  for (uint64_t r = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < n_pad; r += warps) {
+    int8_t* o = out + r * dim_pad8;
+    if (r >= n) {
+      for (uint32_t c = lane; c < dim_pad8; c += 32) o[c] = 0;
+      if (lane == 0) snorm8[r] = __int_as_float(0x7fc00000);
+      continue;
+    }
+    const float* x = rows + r * dim;
+    float mx = 0.f;
+    for (uint32_t c = lane; c < dim; c += 32) mx = fmaxf(mx, fabsf(x[c]));
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o2));
+    const float sn = snorm[r];
+    const bool ok = (sn == sn) && mx > 0.f && isfinite(mx);  // NaN snorm: skipped / special row
+    const float s = ok ? mx / 127.f : 1.f;
+    const float inv = 1.f / s;
+    float err2 = 0.f;
+    for (uint32_t c = lane; c < dim_pad8; c += 32) {
+      int q = 0;
+      if (ok && c < dim) {
+        q = __float2int_rn(x[c] * inv);
+        q = q > 127 ? 127 : (q < -127 ? -127 : q);
+        const float d = x[c] - (float)q * s;
+        err2 = fmaf(d, d, err2);
+      }
+      o[c] = (int8_t)q;
+    }
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) err2 += __shfl_xor_sync(0xffffffffu, err2, o2);
+    if (lane == 0) {
+      if (ok) {
+        const float m = (float)mag[r];
+        snorm8[r] = s / m;
+        const float rel = sqrtf(err2) / m * 1.0001f + 1e-7f;  // rounded up
+        atomicMax(max_rel_bits, __float_as_uint(rel));
+      } else {
+        snorm8[r] = __int_as_float(0x7fc00000);
+      }
+    }
+  }
+}
+
 sdb_status corpus_finalize_device(Corpus* c) {
   Ctx* ctx = c->ctx;
   cudaStream_t st = ctx->stream;
-  uint32_t* d_tmp = nullptr;  // [0] special count, [1] max-norm bits
-  SDB_CUDA(cudaMalloc(&d_tmp, 8));
-  SDB_CUDA(cudaMemsetAsync(d_tmp, 0, 8, st));
+  uint32_t* d_tmp = nullptr;  // [0] special count, [1] max-norm bits, [2] max relative int8 error bits
+  SDB_CUDA(cudaMalloc(&d_tmp, 16));
+  SDB_CUDA(cudaMemsetAsync(d_tmp, 0, 16, st));
   if (!c->d_special) SDB_CUDA(cudaMalloc(&c->d_special, sizeof(uint32_t) * SPECIAL_CAP));
   {
     const uint64_t n_pad = (c->n + TILE_ROWS - 1) / TILE_ROWS * TILE_ROWS;
@@ -106,8 +155,15 @@ sdb_status corpus_finalize_device(Corpus* c) {
       SDB_CUDA(cudaGetLastError());
     }
   }
-  uint32_t h[2] = {0, 0};
-  SDB_CUDA(cudaMemcpyAsync(h, d_tmp, 8, cudaMemcpyDeviceToHost, st));
+  if (c->n && c->dtype == SDB_F32 && c->d_i8 && c->metric == SDB_COSINE) {
+    const uint64_t n_pad = (c->n + TILE_ROWS - 1) / TILE_ROWS * TILE_ROWS;
+    quantize_rows_kernel<<<ctx->sm_count * 8, 256, 0, st>>>((const float*)c->d_rows, c->dim, c->dim_pad8, c->n, n_pad,
+                                                            c->d_mag, c->d_snorm, c->d_i8, c->d_snorm8, d_tmp + 2);
+    count_launch(ctx);
+    SDB_CUDA(cudaGetLastError());
+  }
+  uint32_t h[3] = {0, 0, 0};
+  SDB_CUDA(cudaMemcpyAsync(h, d_tmp, 12, cudaMemcpyDeviceToHost, st));
   SDB_CUDA(cudaStreamSynchronize(st));
   SDB_CUDA(cudaFree(d_tmp));
   c->special_overflow = h[0] > (uint32_t)SPECIAL_CAP;
@@ -115,6 +171,7 @@ sdb_status corpus_finalize_device(Corpus* c) {
   float mn;
   memcpy(&mn, &h[1], 4);
   c->max_norm = mn;
+  memcpy(&c->max_rel_qerr, &h[2], 4);
   c->finalized = true;
   return SDB_OK;
 }

@@ -100,6 +100,10 @@ struct Corpus {
   double* d_mag = nullptr;          // exact f64 magnitude per row (reference arithmetic)
   float* d_snorm = nullptr;         // cosine: 1/|x| ; euclid: |x|^2 ; NaN = never a screen candidate
   __nv_bfloat16* d_bf16 = nullptr;  // screen copy cap_pad x dim_pad (rows padded to TILE_ROWS)
+  int8_t* d_i8 = nullptr;           // int8 screen copy cap_pad x dim_pad8 (per-row scale max|x|/127), cosine only
+  float* d_snorm8 = nullptr;        // (max|x|/127) / |x| ; NaN = never a candidate
+  uint32_t dim_pad8 = 0;            // multiple of 128
+  float max_rel_qerr = 0.f;         // max over rows of |x - dequant(x)| / |x|
   uint8_t* d_skip = nullptr;        // optional skip mask
   uint32_t* d_special = nullptr;    // rows ranked exactly on every query
   uint32_t n_special = 0;
@@ -112,6 +116,11 @@ struct Corpus {
   __nv_bfloat16* d_qbf16 = nullptr;
   double* d_qmag = nullptr;
   uint32_t* d_qflags = nullptr;  // bit0: query needs the exact path; bit1: query has NaN input
+  int8_t* d_q8 = nullptr;        // int8 queries nq_pad x dim_pad8
+  float* d_q8scale = nullptr;    // max|q|/127 per query
+  float* d_q8err = nullptr;      // |q - dequant(q)| / |q| per query
+  float* d_bscale = nullptr;     // per query: factor that turns tau into similarity*|q| units (1 or q8scale)
+  float* d_beps = nullptr;       // per query: rigorous screen error bound in cosine units
   float* d_tau = nullptr;
   Cand* d_cand = nullptr;
   uint32_t* d_cand_cnt = nullptr;
@@ -140,7 +149,7 @@ sdb_status corpus_finalize_device(Corpus* c);
 // screen_simt.cu
 sdb_status screen_simt_pass(Corpus* c, uint32_t nq, const PassDesc& p, cudaStream_t st);
 // screen_tc.cu
-sdb_status screen_tc_pass(Corpus* c, uint32_t nq, const PassDesc& p, cudaStream_t st);
+sdb_status screen_tc_pass(Corpus* c, uint32_t nq, const PassDesc& p, bool int8, cudaStream_t st);
 bool screen_tc_available();
 // candidates.cu
 sdb_status scratch_for(Corpus* c, uint32_t nq, uint32_t cap, uint32_t kp);
@@ -149,6 +158,7 @@ sdb_status cand_reset(Corpus* c, uint32_t nq, cudaStream_t st);
 sdb_status cand_set_count(Corpus* c, uint32_t nq, uint32_t value, cudaStream_t st);
 sdb_status cand_compact(Corpus* c, uint32_t nq, uint32_t kp, cudaStream_t st);
 sdb_status cand_rerank(Corpus* c, uint32_t nq, cudaStream_t st);
+sdb_status set_bounds(Corpus* c, uint32_t nq, int screen, float eps_rel, cudaStream_t st);
 sdb_status cand_final(Corpus* c, uint32_t nq, uint32_t k, uint32_t kp, float eps_rel, uint64_t row_base,
                       uint64_t* d_out_rows, double* d_out_dist, uint32_t* d_out_count, cudaStream_t st);
 // exact.cu

@@ -40,6 +40,8 @@ static_assert(BLOCK_N == TILE_ROWS, "screen tile must match the pass schedule ti
 
 // instruction descriptor (cute::UMMA::InstrDescriptor bit layout): D=f32, A=B=bf16, both K-major
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((BLOCK_N >> 3) << 17) | ((BLOCK_M >> 4) << 24);
+// kind::i8: D = s32 (c_format 2), A = B = signed 8-bit (format 1), K-major; UMMA_K = 32 (still 32 bytes per step)
+constexpr uint32_t IDESC_I8 = (2u << 4) | (1u << 7) | (1u << 10) | ((BLOCK_N >> 3) << 17) | ((BLOCK_M >> 4) << 24);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -73,6 +75,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -103,7 +113,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 
-template <bool COSINE>
+template <bool COSINE, bool INT8>
 __global__ void __launch_bounds__(THREADS, 1)
 screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const float* __restrict__ snorm, uint32_t k_blocks, uint32_t n_mblocks, uint32_t nq,
@@ -161,8 +171,8 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
           const uint32_t fb = smem_u32(&full_bar[s]);
           mbar_expect_tx(fb, STAGE_BYTES);
-          tma_load_2d(smem_u32(smem_a + s * A_BYTES), &map_a, kb * BLOCK_K, mb * BLOCK_M, fb);
-          tma_load_2d(smem_u32(smem_b + s * B_BYTES), &map_b, kb * BLOCK_K, tile * BLOCK_N, fb);
+          tma_load_2d(smem_u32(smem_a + s * A_BYTES), &map_a, kb * (INT8 ? 2 * BLOCK_K : BLOCK_K), mb * BLOCK_M, fb);
+          tma_load_2d(smem_u32(smem_b + s * B_BYTES), &map_b, kb * (INT8 ? 2 * BLOCK_K : BLOCK_K), tile * BLOCK_N, fb);
         }
       }
     }
@@ -185,7 +195,8 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
           for (uint32_t k = 0; k < BLOCK_K / UMMA_K; k++) {
             // advance 32 bytes (16 bf16) inside the 128-byte swizzle atom: +2 in the (>>4) start-address field
-            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0);
+            if (INT8) umma_i8(d_tmem, da + 2 * k, db + 2 * k, IDESC_I8, (kb | k) != 0);
+            else umma_bf16(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0);
           }
           umma_commit(smem_u32(&empty_bar[s]));  // smem stage reusable once these MMAs retire
         }
@@ -224,15 +235,16 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#define ACC(u) (INT8 ? __int2float_rn((int)(u)) : __uint_as_float(u))
         float sc[32];
         float m = __int_as_float(0xff800000);
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           const float4 n4 = *reinterpret_cast<const float4*>(sn + cbase + c0 + i);
-          sc[i + 0] = COSINE ? __uint_as_float(v[i + 0]) * n4.x : fmaf(2.f, __uint_as_float(v[i + 0]), -n4.x);
-          sc[i + 1] = COSINE ? __uint_as_float(v[i + 1]) * n4.y : fmaf(2.f, __uint_as_float(v[i + 1]), -n4.y);
-          sc[i + 2] = COSINE ? __uint_as_float(v[i + 2]) * n4.z : fmaf(2.f, __uint_as_float(v[i + 2]), -n4.z);
-          sc[i + 3] = COSINE ? __uint_as_float(v[i + 3]) * n4.w : fmaf(2.f, __uint_as_float(v[i + 3]), -n4.w);
+          sc[i + 0] = COSINE ? ACC(v[i + 0]) * n4.x : fmaf(2.f, ACC(v[i + 0]), -n4.x);
+          sc[i + 1] = COSINE ? ACC(v[i + 1]) * n4.y : fmaf(2.f, ACC(v[i + 1]), -n4.y);
+          sc[i + 2] = COSINE ? ACC(v[i + 2]) * n4.z : fmaf(2.f, ACC(v[i + 2]), -n4.z);
+          sc[i + 3] = COSINE ? ACC(v[i + 3]) * n4.w : fmaf(2.f, ACC(v[i + 3]), -n4.w);
           m = fmaxf(m, fmaxf(fmaxf(sc[i + 0], sc[i + 1]), fmaxf(sc[i + 2], sc[i + 3])));  // fmaxf drops NaNs
         }
         if (pass0) {
@@ -260,6 +272,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
         }
       }
+#undef ACC
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[a]));
@@ -290,17 +303,17 @@ static EncodeTiledFn get_encode(Ctx* ctx) {
 }
 
 static sdb_status make_map(Ctx* ctx, CUtensorMap* map, const void* base, uint64_t rows, uint32_t dim_pad,
-                           uint32_t box_rows, bool stream_once) {
+                           uint32_t box_rows, bool stream_once, bool int8 = false) {
   EncodeTiledFn enc = get_encode(ctx);
   if (!enc) {
     set_error("cuTensorMapEncodeTiled driver entry point not available");
     return SDB_ECUDA;
   }
   cuuint64_t gdim[2] = {dim_pad, rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)dim_pad * 2};
-  cuuint32_t box[2] = {tc::BLOCK_K, box_rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)dim_pad * (int8 ? 1 : 2)};
+  cuuint32_t box[2] = {int8 ? 2 * tc::BLOCK_K : tc::BLOCK_K, box_rows};  // 128 bytes per row either way
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+  CUresult r = enc(map, int8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    stream_once ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -313,36 +326,44 @@ static sdb_status make_map(Ctx* ctx, CUtensorMap* map, const void* base, uint64_
 
 bool screen_tc_available() { return true; }
 
-sdb_status screen_tc_pass(Corpus* c, uint32_t nq, const PassDesc& p, cudaStream_t st) {
+sdb_status screen_tc_pass(Corpus* c, uint32_t nq, const PassDesc& p, bool int8, cudaStream_t st) {
   if (p.count == 0) return SDB_OK;
   Ctx* ctx = c->ctx;
-  if (!c->d_bf16) {
-    set_error("tcgen05 screen needs the bf16 screen copy (F32 corpus)");
+  if (int8 ? (!c->d_i8 || c->metric != SDB_COSINE) : !c->d_bf16) {
+    set_error("tcgen05 screen: the %s screen copy is not available for this corpus", int8 ? "int8 (cosine only)" : "bf16");
     return SDB_EUNSUPPORTED;
   }
   const uint64_t n_pad = (c->n + TILE_ROWS - 1) / TILE_ROWS * TILE_ROWS;
   const uint32_t nq_pad = (nq + tc::BLOCK_M - 1) / tc::BLOCK_M * tc::BLOCK_M;
   CUtensorMap map_a, map_b;
-  SDB_TRY(make_map(ctx, &map_a, c->d_qbf16, nq_pad, c->dim_pad, tc::BLOCK_M, false));
-  SDB_TRY(make_map(ctx, &map_b, c->d_bf16, n_pad, c->dim_pad, tc::BLOCK_N, true));
+  if (int8) {
+    SDB_TRY(make_map(ctx, &map_a, c->d_q8, nq_pad, c->dim_pad8, tc::BLOCK_M, false, true));
+    SDB_TRY(make_map(ctx, &map_b, c->d_i8, n_pad, c->dim_pad8, tc::BLOCK_N, true, true));
+  } else {
+    SDB_TRY(make_map(ctx, &map_a, c->d_qbf16, nq_pad, c->dim_pad, tc::BLOCK_M, false));
+    SDB_TRY(make_map(ctx, &map_b, c->d_bf16, n_pad, c->dim_pad, tc::BLOCK_N, true));
+  }
   static bool attr_set = false;
   if (!attr_set) {
-    SDB_CUDA(cudaFuncSetAttribute(tc::screen_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-    SDB_CUDA(cudaFuncSetAttribute(tc::screen_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    SDB_CUDA(cudaFuncSetAttribute(tc::screen_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    SDB_CUDA(cudaFuncSetAttribute(tc::screen_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    SDB_CUDA(cudaFuncSetAttribute(tc::screen_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
     attr_set = true;
   }
   const uint32_t n_mblocks = nq_pad / tc::BLOCK_M;
   const uint64_t n_items = (uint64_t)p.count * n_mblocks;
   uint32_t grid = (uint32_t)ctx->sm_count;
   if (grid > n_items) grid = (uint32_t)n_items;
-  if (c->metric == SDB_COSINE)
-    tc::screen_tc_kernel<true><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(map_a, map_b, c->d_snorm, c->dim_pad / tc::BLOCK_K,
-                                                                         n_mblocks, nq, p, c->d_tau, c->d_cand,
-                                                                         c->d_cand_cnt, c->sc_cap);
+  const uint32_t k_blocks = int8 ? c->dim_pad8 / (2 * tc::BLOCK_K) : c->dim_pad / tc::BLOCK_K;
+  if (int8)
+    tc::screen_tc_kernel<true, true><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(map_a, map_b, c->d_snorm8, k_blocks, n_mblocks,
+                                                                               nq, p, c->d_tau, c->d_cand, c->d_cand_cnt, c->sc_cap);
+  else if (c->metric == SDB_COSINE)
+    tc::screen_tc_kernel<true, false><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(map_a, map_b, c->d_snorm, k_blocks, n_mblocks,
+                                                                                nq, p, c->d_tau, c->d_cand, c->d_cand_cnt, c->sc_cap);
   else
-    tc::screen_tc_kernel<false><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(map_a, map_b, c->d_snorm, c->dim_pad / tc::BLOCK_K,
-                                                                          n_mblocks, nq, p, c->d_tau, c->d_cand,
-                                                                          c->d_cand_cnt, c->sc_cap);
+    tc::screen_tc_kernel<false, false><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(map_a, map_b, c->d_snorm, k_blocks, n_mblocks,
+                                                                                 nq, p, c->d_tau, c->d_cand, c->d_cand_cnt, c->sc_cap);
   count_launch(ctx);
   if (p.excl == 0) SDB_TRY(cand_set_count(c, nq, p.count * TILE_ROWS, st));  // pass 0 wrote fixed slots
   SDB_CUDA(cudaGetLastError());

@@ -16,7 +16,7 @@ for r0 in range(0, rows, 1 << 20):
 col.finalize()
 print(f"staged {rows} rows in {time.time()-t0:.2f}s", flush=True)
 dev = torch.device("cuda", 0)
-cfgs = (("SIMT_F32", (1, 4, 8)), ("TC_BF16", (16, 128, 1024, 4096)))
+cfgs = (("SIMT_F32", (1, 4, 8)), ("TC_BF16", (16, 128, 1024, 4096)), ("TC_INT8", (16, 128, 1024, 4096)))
 if len(sys.argv) > 3:
     cfgs = ((sys.argv[2], (int(sys.argv[3]),)),)
 iters = int(sys.argv[4]) if len(sys.argv) > 4 else 5

@@ -12,7 +12,7 @@ for (n, dim, nq, k) in [(5000, 128, 200, 10), (70000, 768, 300, 10), (3000, 100,
     queries = gen_f32(12, 0, nq * dim).reshape(nq, dim).astype(np.float64)
     for metric in ("COSINE", "EUCLIDEAN"):
         col = VectorColumn(ctx, dim, metric, "F32", capacity=n)
-        col.append(corpus); col.finalize(); col.set_screen("TC_BF16")
+        col.append(corpus); col.finalize(); col.set_screen(os.environ.get("SCREEN", "TC_BF16"))
         t0 = time.time()
         rows, dist, cnt = col.knn(queries, k)
         st = col.stats()

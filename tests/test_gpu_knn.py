@@ -39,7 +39,7 @@ def check(col, corpus, queries, metric, k, skip=None):
 
 @pytest.mark.parametrize("metric", ["COSINE", "EUCLIDEAN"])
 @pytest.mark.parametrize("dim", [7, 100, 128, 768])
-@pytest.mark.parametrize("screen", ["SIMT_F32", "TC_BF16", "NONE_EXACT"])
+@pytest.mark.parametrize("screen", ["SIMT_F32", "TC_BF16", "TC_INT8", "NONE_EXACT"])
 def test_random_parity(ctx, metric, dim, screen):
     rng = np.random.default_rng(dim * 7 + len(metric))
     n = 20000 if dim <= 128 else 6000
@@ -117,7 +117,7 @@ def test_ties_resolved_by_scan_order(ctx):
     corpus = np.concatenate([base, base, base[::-1], base])  # exact duplicates => exact distance ties
     queries = rng.uniform(-1, 1, (9, 32))
     for metric in ("COSINE", "EUCLIDEAN"):
-        for screen in ("SIMT_F32", "TC_BF16"):
+        for screen in ("SIMT_F32", "TC_BF16", "TC_INT8"):
             col = make_col(ctx, corpus, metric, screen=screen)
             check(col, corpus, queries, metric, 10)
             check(col, corpus, queries[:2], metric, 57)
@@ -134,7 +134,7 @@ def test_zero_and_nan_rows_and_queries(ctx):
     queries[1] = 0.0         # zero query: every cosine distance is NaN -> first k rows in scan order
     queries[2, 3] = np.nan
     for metric in ("COSINE", "EUCLIDEAN"):
-        for screen in ("SIMT_F32", "TC_BF16"):
+        for screen in ("SIMT_F32", "TC_BF16", "TC_INT8"):
             col = make_col(ctx, corpus, metric, screen=screen)
             check(col, corpus, queries, metric, 10)
             check(col, corpus, queries, metric, 499)
@@ -147,7 +147,7 @@ def test_adversarial_cluster_forces_exact_fallback(ctx):
     center = rng.uniform(-1, 1, 64).astype(np.float32)
     corpus = (center[None, :] + rng.normal(0, 1e-6, (30000, 64))).astype(np.float32)
     queries = (center[None, :] + rng.normal(0, 1e-3, (12, 64))).astype(np.float64)
-    for screen in ("SIMT_F32", "TC_BF16"):
+    for screen in ("SIMT_F32", "TC_BF16", "TC_INT8"):
         col = make_col(ctx, corpus, "COSINE", screen=screen)
         check(col, corpus, queries, "COSINE", 10)
     col = make_col(ctx, corpus, "EUCLIDEAN", screen="TC_BF16")
@@ -183,5 +183,8 @@ def test_full_size_c2_sample_queries(ctx):
     for q in (0, 31, 63):
         r, d = O.knn_topk(corpus, queries[q], "cosine", k)
         assert list(rows[q]) == list(r) and dist[q].tobytes() == d.tobytes()
-    rows1, dist1, _ = col.knn(queries[:3], k)  # streaming SIMT screen on the same corpus
-    assert rows1.tobytes() == rows[:3].tobytes() and dist1.tobytes() == dist[:3].tobytes()
+    for screen in ("SIMT_F32", "TC_BF16", "TC_INT8"):  # every screen gives the same bits on the same corpus
+        col.set_screen(screen)
+        rows1, dist1, _ = col.knn(queries[:9], k)
+        assert rows1.tobytes() == rows[:9].tobytes() and dist1.tobytes() == dist[:9].tobytes(), screen
+        assert col.stats()["screen_used"] == {"SIMT_F32": 1, "TC_BF16": 2, "TC_INT8": 4}[screen]
