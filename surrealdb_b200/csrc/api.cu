@@ -88,7 +88,7 @@ static sdb_status knn_device_locked(Corpus* c, const double* d_queries, uint32_t
       }
       if (scr == SDB_SCREEN_SIMT_F32) SDB_TRY(screen_simt_pass(c, nq, p, st));
       else SDB_TRY(screen_tc_pass(c, nq, p, scr == SDB_SCREEN_TC_INT8, st));
-      SDB_TRY(cand_compact(c, nq, kp, st));
+      SDB_TRY(cand_compact(c, nq, kp, scr == SDB_SCREEN_TC_INT8, st));
     }
     SDB_CUDA(cudaEventRecord(ev[2], st));
     SDB_TRY(cand_rerank(c, nq, st));
@@ -278,10 +278,7 @@ sdb_status sdb_corpus_create(sdb_ctx* ctx, uint32_t dim, sdb_dtype dt, sdb_metri
   if (e == cudaSuccess) e = cudaMalloc(&c->d_mag, sizeof(double) * cap);
   if (e == cudaSuccess) e = cudaMalloc(&c->d_snorm, sizeof(float) * cap_pad);
   if (e == cudaSuccess && dt == SDB_F32) e = cudaMalloc(&c->d_bf16, sizeof(__nv_bfloat16) * cap_pad * c->dim_pad);
-  if (e == cudaSuccess && dt == SDB_F32 && m == SDB_COSINE) {
-    e = cudaMalloc(&c->d_i8, (size_t)cap_pad * c->dim_pad8);
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_snorm8, sizeof(float) * cap_pad);
-  }
+  if (e == cudaSuccess && dt == SDB_F32 && m == SDB_COSINE) e = cudaMalloc(&c->d_i8, (size_t)cap_pad * c->dim_pad8);
   if (e != cudaSuccess) {
     set_error("corpus allocation failed: %s", cudaGetErrorString(e));
     sdb_corpus_destroy(c);
@@ -293,7 +290,7 @@ sdb_status sdb_corpus_create(sdb_ctx* ctx, uint32_t dim, sdb_dtype dt, sdb_metri
 void sdb_corpus_destroy(sdb_corpus* c) {
   if (!c) return;
   cudaSetDevice(c->ctx->device);
-  void* ptrs[] = {c->d_i8, c->d_snorm8, c->d_q8, c->d_q8scale, c->d_q8err, c->d_bscale, c->d_beps,
+  void* ptrs[] = {c->d_i8, c->d_q8, c->d_q8scale, c->d_q8err, c->d_bscale, c->d_beps,
                   c->d_rows, c->d_mag, c->d_snorm, c->d_bf16, c->d_skip, c->d_special, c->d_q64, c->d_q32,
                   c->d_qbf16, c->d_qmag, c->d_qflags, c->d_tau, c->d_cand, c->d_cand_cnt, c->d_flags,
                   c->d_rr_key, c->d_rr_dist, c->d_rr_row, c->d_ex_key, c->d_sel, c->d_out_rows, c->d_out_dist,

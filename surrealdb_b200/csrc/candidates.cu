@@ -97,13 +97,13 @@ __global__ void __launch_bounds__(128) prep_queries_i8_kernel(const float* __res
 
 // per-query (tau scale, rigorous error bound) of the screen that is about to run
 __global__ void set_bounds_kernel(float* bscale, float* beps, const float* q8scale, const float* q8err, uint32_t nq, int int8,
-                                  float eps_rel, float max_rel_qerr) {
+                                  float eps_rel, float max_rel_qerr, float i8_scale) {
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nq) return;
   if (int8) {
-    // sim = s_q * score / |q| + (s_q q8 . dx + dq . x) / (|q||x|);  |second term| <= (1 + e_q) e_x + e_q
+    // sim = s_q * s * score / |q| + (s_q q8 . dx + dq . x^) ;  |second term| <= ((1 + e_q) e_x + e_q)
     const float eq = q8err[q];
-    bscale[q] = q8scale[q];
+    bscale[q] = q8scale[q] * i8_scale * 1.000001f;  // score = q8.x8; sim ~ s_q * s * score / |q|
     beps[q] = (1.f + eq) * max_rel_qerr + eq + 2e-6f;
   } else {
     bscale[q] = 1.f;
@@ -112,7 +112,7 @@ __global__ void set_bounds_kernel(float* bscale, float* beps, const float* q8sca
 }
 sdb_status set_bounds(Corpus* c, uint32_t nq, int screen, float eps_rel, cudaStream_t st) {
   set_bounds_kernel<<<(nq + 255) / 256, 256, 0, st>>>(c->d_bscale, c->d_beps, c->d_q8scale, c->d_q8err, nq,
-                                                      screen == SDB_SCREEN_TC_INT8, eps_rel, c->max_rel_qerr);
+                                                      screen == SDB_SCREEN_TC_INT8, eps_rel, c->max_rel_qerr, c->i8_scale);
   count_launch(c->ctx);
   SDB_CUDA(cudaGetLastError());
   return SDB_OK;
@@ -222,7 +222,7 @@ __device__ void bitonic_sort_u64(uint64_t* s, uint32_t n) {
 // keep the best kp candidates of each query, tau = score of the kp-th (if that many exist)
 __global__ void __launch_bounds__(1024) cand_compact_kernel(Cand* __restrict__ cand, uint32_t* __restrict__ cnt,
                                                             float* __restrict__ tau, uint32_t* __restrict__ flags,
-                                                            uint32_t cap, uint32_t kp) {
+                                                            uint32_t cap, uint32_t kp, const float* __restrict__ snorm) {
   extern __shared__ uint64_t s_keys[];
   __shared__ uint32_t s_valid;
   const uint32_t q = blockIdx.x;
@@ -240,7 +240,11 @@ __global__ void __launch_bounds__(1024) cand_compact_kernel(Cand* __restrict__ c
   for (uint32_t i = threadIdx.x; i < p2; i += blockDim.x) {
     uint64_t key = 0;  // padding and NaN scores (skipped / special / padding rows written by pass 0) sort last
     if (i < n) {
-      const float sc = cq[i].score;
+      float sc = cq[i].score;
+      if (snorm) {  // integer screens score invalid rows 0: the row's NaN screening norm marks them
+        const float sn = snorm[cq[i].row];
+        if (!(sn == sn)) sc = sn;
+      }
       if (sc == sc) {
         key = ((uint64_t)f32_key(sc) << 32) | (uint64_t)(0xFFFFFFFFu - cq[i].row);
         my_valid++;
@@ -267,14 +271,15 @@ __global__ void __launch_bounds__(1024) cand_compact_kernel(Cand* __restrict__ c
   if (threadIdx.x == 0) cnt[q] = keep;
 }
 
-sdb_status cand_compact(Corpus* c, uint32_t nq, uint32_t kp, cudaStream_t st) {
+sdb_status cand_compact(Corpus* c, uint32_t nq, uint32_t kp, bool drop_invalid, cudaStream_t st) {
   const size_t smem = sizeof(uint64_t) * c->sc_cap;
   static bool attr_set = false;
   if (!attr_set) {
     SDB_CUDA(cudaFuncSetAttribute(cand_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  cand_compact_kernel<<<nq, 1024, smem, st>>>(c->d_cand, c->d_cand_cnt, c->d_tau, c->d_flags, c->sc_cap, kp);
+  cand_compact_kernel<<<nq, 1024, smem, st>>>(c->d_cand, c->d_cand_cnt, c->d_tau, c->d_flags, c->sc_cap, kp,
+                                              drop_invalid ? c->d_snorm : nullptr);
   count_launch(c->ctx);
   SDB_CUDA(cudaGetLastError());
   return SDB_OK;

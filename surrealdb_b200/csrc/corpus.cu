@@ -72,52 +72,64 @@ __global__ void to_bf16_kernel(const float* __restrict__ rows, uint32_t dim, uin
   }
 }
 
-// per-row symmetric int8 quantisation x8 = rn(x / s), s = max|x| / 127 (one warp per row)
-__global__ void __launch_bounds__(256) quantize_rows_kernel(const float* __restrict__ rows, uint32_t dim, uint32_t dim_pad8,
-                                                            uint64_t n, uint64_t n_pad, const double* __restrict__ mag,
-                                                            const float* __restrict__ snorm, int8_t* __restrict__ out,
-                                                            float* __restrict__ snorm8, uint32_t* max_rel_bits) {
+// int8 screen copy (cosine): the NORMALISED rows x/|x| are quantised with ONE global scale s = gmax/127, so the
+// integer dot product q8.x8 is itself the screening score (no per-row weight in the epilogue):
+//   sim(q,x) = s_q * s * (q8.x8) / |q|  +  err,   |err| <= (1 + e_q) * e_x + e_q,   e_x = |x/|x| - s*x8|  (per row)
+// pass 1: gmax = max over valid rows of max_i |x_i| / |x|
+__global__ void __launch_bounds__(256) quantize_scan_kernel(const float* __restrict__ rows, uint32_t dim, uint64_t n,
+                                                            const double* __restrict__ mag, const float* __restrict__ snorm,
+                                                            uint32_t* gmax_bits) {
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t warps = (uint64_t)gridDim.x * 8;
-  for (uint64_t r = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < n_pad; r += warps) {
-    int8_t* o = out + r * dim_pad8;
-    if (r >= n) {
-      for (uint32_t c = lane; c < dim_pad8; c += 32) o[c] = 0;
-      if (lane == 0) snorm8[r] = __int_as_float(0x7fc00000);
-      continue;
-    }
+  float best = 0.f;
+  for (uint64_t r = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < n; r += warps) {
+    const float sn = snorm[r];
+    if (!(sn == sn)) continue;  // skipped / special
     const float* x = rows + r * dim;
     float mx = 0.f;
     for (uint32_t c = lane; c < dim; c += 32) mx = fmaxf(mx, fabsf(x[c]));
 #pragma unroll
     for (int o2 = 16; o2 > 0; o2 >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o2));
-    const float sn = snorm[r];
-    const bool ok = (sn == sn) && mx > 0.f && isfinite(mx);  // NaN snorm: skipped / special row
-    const float s = ok ? mx / 127.f : 1.f;
+    best = fmaxf(best, mx / (float)mag[r]);
+  }
+  if (lane == 0 && best > 0.f) atomicMax(gmax_bits, __float_as_uint(best));
+}
+// pass 2: x8 = clamp(rn(x / (|x| s)), +-127), e_x accumulated exactly as the residual norm (clipping included)
+__global__ void __launch_bounds__(256) quantize_rows_kernel(const float* __restrict__ rows, uint32_t dim, uint32_t dim_pad8,
+                                                            uint64_t n, uint64_t n_pad, const double* __restrict__ mag,
+                                                            const float* __restrict__ snorm, const uint32_t* gmax_bits,
+                                                            int8_t* __restrict__ out, uint32_t* max_rel_bits) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warps = (uint64_t)gridDim.x * 8;
+  const float gmax = __uint_as_float(*gmax_bits);
+  const float s = gmax > 0.f ? gmax / 127.f : 1.f;
+  for (uint64_t r = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < n_pad; r += warps) {
+    int8_t* o = out + r * dim_pad8;
+    const float sn = r < n ? snorm[r] : __int_as_float(0x7fc00000);
+    const bool ok = (sn == sn) && gmax > 0.f;
+    if (!ok) {  // zero row: scores 0, and compaction drops it through its NaN screening norm
+      for (uint32_t c = lane; c < dim_pad8; c += 32) o[c] = 0;
+      continue;
+    }
+    const float* x = rows + r * dim;
+    const float inv_norm = 1.f / (float)mag[r];
     const float inv = 1.f / s;
     float err2 = 0.f;
     for (uint32_t c = lane; c < dim_pad8; c += 32) {
       int q = 0;
-      if (ok && c < dim) {
-        q = __float2int_rn(x[c] * inv);
+      if (c < dim) {
+        const float xn = x[c] * inv_norm;
+        q = __float2int_rn(xn * inv);
         q = q > 127 ? 127 : (q < -127 ? -127 : q);
-        const float d = x[c] - (float)q * s;
+        const float d = xn - (float)q * s;
         err2 = fmaf(d, d, err2);
       }
       o[c] = (int8_t)q;
     }
 #pragma unroll
     for (int o2 = 16; o2 > 0; o2 >>= 1) err2 += __shfl_xor_sync(0xffffffffu, err2, o2);
-    if (lane == 0) {
-      if (ok) {
-        const float m = (float)mag[r];
-        snorm8[r] = s / m;
-        const float rel = sqrtf(err2) / m * 1.0001f + 1e-7f;  // rounded up
-        atomicMax(max_rel_bits, __float_as_uint(rel));
-      } else {
-        snorm8[r] = __int_as_float(0x7fc00000);
-      }
-    }
+    // + 2^-22: the f32 normalisation x * (1/|x|) is itself rounded; the whole figure is rounded up
+    if (lane == 0) atomicMax(max_rel_bits, __float_as_uint(sqrtf(err2) * 1.0001f + 5e-7f));
   }
 }
 
@@ -157,13 +169,15 @@ sdb_status corpus_finalize_device(Corpus* c) {
   }
   if (c->n && c->dtype == SDB_F32 && c->d_i8 && c->metric == SDB_COSINE) {
     const uint64_t n_pad = (c->n + TILE_ROWS - 1) / TILE_ROWS * TILE_ROWS;
+    quantize_scan_kernel<<<ctx->sm_count * 8, 256, 0, st>>>((const float*)c->d_rows, c->dim, c->n, c->d_mag, c->d_snorm,
+                                                            d_tmp + 3);
     quantize_rows_kernel<<<ctx->sm_count * 8, 256, 0, st>>>((const float*)c->d_rows, c->dim, c->dim_pad8, c->n, n_pad,
-                                                            c->d_mag, c->d_snorm, c->d_i8, c->d_snorm8, d_tmp + 2);
-    count_launch(ctx);
+                                                            c->d_mag, c->d_snorm, d_tmp + 3, c->d_i8, d_tmp + 2);
+    count_launch(ctx, 2);
     SDB_CUDA(cudaGetLastError());
   }
-  uint32_t h[3] = {0, 0, 0};
-  SDB_CUDA(cudaMemcpyAsync(h, d_tmp, 12, cudaMemcpyDeviceToHost, st));
+  uint32_t h[4] = {0, 0, 0, 0};
+  SDB_CUDA(cudaMemcpyAsync(h, d_tmp, 16, cudaMemcpyDeviceToHost, st));
   SDB_CUDA(cudaStreamSynchronize(st));
   SDB_CUDA(cudaFree(d_tmp));
   c->special_overflow = h[0] > (uint32_t)SPECIAL_CAP;
@@ -172,6 +186,11 @@ sdb_status corpus_finalize_device(Corpus* c) {
   memcpy(&mn, &h[1], 4);
   c->max_norm = mn;
   memcpy(&c->max_rel_qerr, &h[2], 4);
+  {
+    float gmax;
+    memcpy(&gmax, &h[3], 4);
+    c->i8_scale = gmax > 0.f ? gmax / 127.f : 1.f;
+  }
   c->finalized = true;
   return SDB_OK;
 }

@@ -101,9 +101,9 @@ struct Corpus {
   float* d_snorm = nullptr;         // cosine: 1/|x| ; euclid: |x|^2 ; NaN = never a screen candidate
   __nv_bfloat16* d_bf16 = nullptr;  // screen copy cap_pad x dim_pad (rows padded to TILE_ROWS)
   int8_t* d_i8 = nullptr;           // int8 screen copy cap_pad x dim_pad8 (per-row scale max|x|/127), cosine only
-  float* d_snorm8 = nullptr;        // (max|x|/127) / |x| ; NaN = never a candidate
   uint32_t dim_pad8 = 0;            // multiple of 128
-  float max_rel_qerr = 0.f;         // max over rows of |x - dequant(x)| / |x|
+  float max_rel_qerr = 0.f;         // max over rows of |x/|x| - s * x8|
+  float i8_scale = 1.f;             // global scale s of the int8 copy
   uint8_t* d_skip = nullptr;        // optional skip mask
   uint32_t* d_special = nullptr;    // rows ranked exactly on every query
   uint32_t n_special = 0;
@@ -156,7 +156,7 @@ sdb_status scratch_for(Corpus* c, uint32_t nq, uint32_t cap, uint32_t kp);
 sdb_status prep_queries(Corpus* c, const double* d_queries, uint32_t nq, cudaStream_t st);
 sdb_status cand_reset(Corpus* c, uint32_t nq, cudaStream_t st);
 sdb_status cand_set_count(Corpus* c, uint32_t nq, uint32_t value, cudaStream_t st);
-sdb_status cand_compact(Corpus* c, uint32_t nq, uint32_t kp, cudaStream_t st);
+sdb_status cand_compact(Corpus* c, uint32_t nq, uint32_t kp, bool drop_invalid, cudaStream_t st);
 sdb_status cand_rerank(Corpus* c, uint32_t nq, cudaStream_t st);
 sdb_status set_bounds(Corpus* c, uint32_t nq, int screen, float eps_rel, cudaStream_t st);
 sdb_status cand_final(Corpus* c, uint32_t nq, uint32_t k, uint32_t kp, float eps_rel, uint64_t row_base,

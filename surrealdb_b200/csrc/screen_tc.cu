@@ -211,68 +211,122 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t row_in_tile = wq * 32 + lane;
     const uint32_t et = threadIdx.x - 64;         // 0..255
     const bool pass0 = pass.excl == 0;            // tau = -inf everywhere: positions are deterministic, no atomics
+    const uint32_t cbase = half * (BLOCK_N / 2);
     uint32_t j = 0;
-    for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, j++) {
+    // the threshold of the first item; later items prefetch theirs while the current one is processed
+    uint32_t w = blockIdx.x;
+    float next_tau = __int_as_float(0x7f800000);
+    if (w < n_items) {
+      const uint32_t q0 = (w % n_mblocks) * BLOCK_M + row_in_tile;
+      if (q0 < nq) next_tau = __ldg(tau + q0);
+    }
+    for (; w < n_items; w += gridDim.x, j++) {
       const uint32_t tidx = w / n_mblocks;
       const uint32_t tile = pass_tile(pass, tidx);
       const uint32_t mb = w % n_mblocks;
       const uint32_t a = j % ACC_STAGES, pa = (j / ACC_STAGES) & 1;
       const uint32_t q = mb * BLOCK_M + row_in_tile;
-      const float my_tau = q < nq ? __ldg(tau + q) : __int_as_float(0x7f800000);
-      // stage this tile's screening norms (safe: every epilogue thread passed the named barrier of item j-1
-      // only after finishing item j-2, the previous user of s_snorm[a])
-      float* sn = s_snorm + a * BLOCK_N;
+      const float my_tau = next_tau;
+      {  // prefetch the next item's threshold (a global load whose latency would otherwise sit in front of the wait)
+        const uint32_t wn = w + gridDim.x;
+        next_tau = __int_as_float(0x7f800000);
+        if (wn < n_items) {
+          const uint32_t qn = (wn % n_mblocks) * BLOCK_M + row_in_tile;
+          if (qn < nq) next_tau = __ldg(tau + qn);
+        }
+      }
       const size_t row0 = (size_t)tile * BLOCK_N;
-      sn[et] = __ldg(snorm + row0 + et);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      float* sn = s_snorm + a * BLOCK_N;
+      if (!INT8) {
+        // stage this tile's screening norms (safe: every epilogue thread passed the named barrier of item j-1
+        // only after finishing item j-2, the previous user of s_snorm[a])
+        sn[et] = __ldg(snorm + row0 + et);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      // integer threshold for the int8 screen: acc >= tau  <=>  acc >= ceil(tau)
+      int tau_i = 0x7fffffff;
+      if (INT8) {
+        const float ct = ceilf(my_tau);
+        tau_i = ct >= 2147483520.f ? 0x7fffffff : (ct <= -2147483520.f ? (int)0x80000000 : (int)ct);
+      }
       mbar_wait(smem_u32(&tfull_bar[a]), pa);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t cbase = half * (BLOCK_N / 2);
       const uint32_t taddr = tmem_base + ((wq * 32) << 16) + a * BLOCK_N + cbase;
       Cand* my_cand = cand + (size_t)q * cap;
-#pragma unroll 1
-      for (uint32_t c0 = 0; c0 < BLOCK_N / 2; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c0, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#define ACC(u) (INT8 ? __int2float_rn((int)(u)) : __uint_as_float(u))
-        float sc[32];
-        float m = __int_as_float(0xff800000);
+      uint32_t va[32], vb[32];
+      tmem_ld32(taddr, va);
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 n4 = *reinterpret_cast<const float4*>(sn + cbase + c0 + i);
-          sc[i + 0] = COSINE ? ACC(v[i + 0]) * n4.x : fmaf(2.f, ACC(v[i + 0]), -n4.x);
-          sc[i + 1] = COSINE ? ACC(v[i + 1]) * n4.y : fmaf(2.f, ACC(v[i + 1]), -n4.y);
-          sc[i + 2] = COSINE ? ACC(v[i + 2]) * n4.z : fmaf(2.f, ACC(v[i + 2]), -n4.z);
-          sc[i + 3] = COSINE ? ACC(v[i + 3]) * n4.w : fmaf(2.f, ACC(v[i + 3]), -n4.w);
-          m = fmaxf(m, fmaxf(fmaxf(sc[i + 0], sc[i + 1]), fmaxf(sc[i + 2], sc[i + 3])));  // fmaxf drops NaNs
-        }
-        if (pass0) {
-          if (q < nq) {  // every (finite or NaN) score goes to its fixed slot; compaction drops the NaNs
+      for (uint32_t cc = 0; cc < BLOCK_N / 2 / 32; cc++) {
+        const uint32_t c0 = cc * 32;
+        uint32_t(&v)[32] = (cc & 1) ? vb : va;
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (cc + 1 < BLOCK_N / 2 / 32) tmem_ld32(taddr + c0 + 32, (cc & 1) ? va : vb);  // next chunk in flight
+        if (INT8) {
+          int m = (int)v[0];
+#pragma unroll
+          for (int i = 1; i < 32; i++) m = max(m, (int)v[i]);
+          if (pass0) {
+            if (q < nq) {
+#pragma unroll
+              for (int i = 0; i < 32; i++) {
+                Cand cd;
+                cd.score = __int2float_rn((int)v[i]);
+                cd.row = (uint32_t)(row0 + cbase + c0 + i);
+                my_cand[(size_t)tidx * BLOCK_N + cbase + c0 + i] = cd;
+              }
+            }
+          } else if (m >= tau_i) {  // rare
 #pragma unroll
             for (int i = 0; i < 32; i++) {
-              Cand cd;
-              cd.score = sc[i];
-              cd.row = (uint32_t)(row0 + cbase + c0 + i);
-              my_cand[(size_t)tidx * BLOCK_N + cbase + c0 + i] = cd;
+              if ((int)v[i] >= tau_i) {
+                const uint32_t pos = atomicAdd(cand_cnt + q, 1u);
+                if (pos < cap) {
+                  Cand cd;
+                  cd.score = __int2float_rn((int)v[i]);
+                  cd.row = (uint32_t)(row0 + cbase + c0 + i);
+                  my_cand[pos] = cd;
+                }
+              }
             }
           }
-        } else if (m >= my_tau) {  // rare: some element of this chunk survives the threshold
+        } else {
+          float sc[32];
+          float m = __int_as_float(0xff800000);
 #pragma unroll
-          for (int i = 0; i < 32; i++) {
-            if (sc[i] >= my_tau) {
-              const uint32_t pos = atomicAdd(cand_cnt + q, 1u);
-              if (pos < cap) {
+          for (int i = 0; i < 32; i += 4) {
+            const float4 n4 = *reinterpret_cast<const float4*>(sn + cbase + c0 + i);
+            sc[i + 0] = COSINE ? __uint_as_float(v[i + 0]) * n4.x : fmaf(2.f, __uint_as_float(v[i + 0]), -n4.x);
+            sc[i + 1] = COSINE ? __uint_as_float(v[i + 1]) * n4.y : fmaf(2.f, __uint_as_float(v[i + 1]), -n4.y);
+            sc[i + 2] = COSINE ? __uint_as_float(v[i + 2]) * n4.z : fmaf(2.f, __uint_as_float(v[i + 2]), -n4.z);
+            sc[i + 3] = COSINE ? __uint_as_float(v[i + 3]) * n4.w : fmaf(2.f, __uint_as_float(v[i + 3]), -n4.w);
+            m = fmaxf(m, fmaxf(fmaxf(sc[i + 0], sc[i + 1]), fmaxf(sc[i + 2], sc[i + 3])));  // fmaxf drops NaNs
+          }
+          if (pass0) {
+            if (q < nq) {  // every (finite or NaN) score goes to its fixed slot; compaction drops the NaNs
+#pragma unroll
+              for (int i = 0; i < 32; i++) {
                 Cand cd;
                 cd.score = sc[i];
                 cd.row = (uint32_t)(row0 + cbase + c0 + i);
-                my_cand[pos] = cd;
+                my_cand[(size_t)tidx * BLOCK_N + cbase + c0 + i] = cd;
+              }
+            }
+          } else if (m >= my_tau) {  // rare: some element of this chunk survives the threshold
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+              if (sc[i] >= my_tau) {
+                const uint32_t pos = atomicAdd(cand_cnt + q, 1u);
+                if (pos < cap) {
+                  Cand cd;
+                  cd.score = sc[i];
+                  cd.row = (uint32_t)(row0 + cbase + c0 + i);
+                  my_cand[pos] = cd;
+                }
               }
             }
           }
         }
       }
-#undef ACC
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[a]));
@@ -356,7 +410,7 @@ sdb_status screen_tc_pass(Corpus* c, uint32_t nq, const PassDesc& p, bool int8, 
   if (grid > n_items) grid = (uint32_t)n_items;
   const uint32_t k_blocks = int8 ? c->dim_pad8 / (2 * tc::BLOCK_K) : c->dim_pad / tc::BLOCK_K;
   if (int8)
-    tc::screen_tc_kernel<true, true><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(map_a, map_b, c->d_snorm8, k_blocks, n_mblocks,
+    tc::screen_tc_kernel<true, true><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(map_a, map_b, c->d_snorm, k_blocks, n_mblocks,
                                                                                nq, p, c->d_tau, c->d_cand, c->d_cand_cnt, c->sc_cap);
   else if (c->metric == SDB_COSINE)
     tc::screen_tc_kernel<true, false><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(map_a, map_b, c->d_snorm, k_blocks, n_mblocks,
