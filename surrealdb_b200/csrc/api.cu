@@ -88,7 +88,7 @@ static sdb_status knn_device_locked(Corpus* c, const double* d_queries, uint32_t
       }
       if (scr == SDB_SCREEN_SIMT_F32) SDB_TRY(screen_simt_pass(c, nq, p, st));
       else SDB_TRY(screen_tc_pass(c, nq, p, scr == SDB_SCREEN_TC_INT8, st));
-      SDB_TRY(cand_compact(c, nq, kp, scr == SDB_SCREEN_TC_INT8, st));
+      SDB_TRY(cand_compact(c, nq, kp, scr == SDB_SCREEN_TC_INT8, scr == SDB_SCREEN_SIMT_F32 ? 0u : c->last_slots, st));
     }
     SDB_CUDA(cudaEventRecord(ev[2], st));
     SDB_TRY(cand_rerank(c, nq, st));
@@ -96,7 +96,7 @@ static sdb_status knn_device_locked(Corpus* c, const double* d_queries, uint32_t
     SDB_CUDA(cudaMemcpyAsync(h_flags.data(), c->d_flags, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, st));
     stt.n_passes += (uint32_t)passes.size();
     stt.n_reranked += (uint64_t)nq * (kp + c->n_special);
-    if (scr != SDB_SCREEN_TC_INT8) break;
+    if (scr != SDB_SCREEN_TC_INT8 || getenv("SDB_TC_DBG")) break;
     // precision ladder: if the int8 proof failed for more than a handful of queries, re-screen the batch in bf16
     SDB_CUDA(cudaStreamSynchronize(st));
     uint32_t n_fail = 0;
@@ -291,7 +291,7 @@ void sdb_corpus_destroy(sdb_corpus* c) {
   if (!c) return;
   cudaSetDevice(c->ctx->device);
   void* ptrs[] = {c->d_i8, c->d_q8, c->d_q8scale, c->d_q8err, c->d_bscale, c->d_beps,
-                  c->d_rows, c->d_mag, c->d_snorm, c->d_bf16, c->d_skip, c->d_special, c->d_q64, c->d_q32,
+                  c->d_sub, c->d_sub_cnt, c->d_rows, c->d_mag, c->d_snorm, c->d_bf16, c->d_skip, c->d_special, c->d_q64, c->d_q32,
                   c->d_qbf16, c->d_qmag, c->d_qflags, c->d_tau, c->d_cand, c->d_cand_cnt, c->d_flags,
                   c->d_rr_key, c->d_rr_dist, c->d_rr_row, c->d_ex_key, c->d_sel, c->d_out_rows, c->d_out_dist,
                   c->d_out_count, c->d_in_q};

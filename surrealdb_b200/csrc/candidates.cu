@@ -124,6 +124,7 @@ static sdb_status ensure_scratch(Corpus* c, uint32_t nq, uint32_t cap, uint32_t 
   cudaFree(c->d_q64); cudaFree(c->d_q32); cudaFree(c->d_qbf16); cudaFree(c->d_qmag); cudaFree(c->d_qflags);
   cudaFree(c->d_tau); cudaFree(c->d_cand); cudaFree(c->d_cand_cnt); cudaFree(c->d_flags);
   cudaFree(c->d_rr_key); cudaFree(c->d_rr_dist); cudaFree(c->d_rr_row);
+  cudaFree(c->d_sub); cudaFree(c->d_sub_cnt);
   cudaFree(c->d_q8); cudaFree(c->d_q8scale); cudaFree(c->d_q8err); cudaFree(c->d_bscale); cudaFree(c->d_beps);
   c->sc_nq = c->sc_cap = c->sc_kp = 0;
   const uint32_t nqa = nq_pad > c->sc_nq ? nq_pad : c->sc_nq;
@@ -146,6 +147,10 @@ static sdb_status ensure_scratch(Corpus* c, uint32_t nq, uint32_t cap, uint32_t 
   SDB_CUDA(cudaMalloc(&c->d_q8err, sizeof(float) * nqa));
   SDB_CUDA(cudaMalloc(&c->d_bscale, sizeof(float) * nqa));
   SDB_CUDA(cudaMalloc(&c->d_beps, sizeof(float) * nqa));
+  c->sub_slots = 2 * (uint32_t)c->ctx->sm_count;
+  c->sub_cap = 16;
+  SDB_CUDA(cudaMalloc(&c->d_sub, sizeof(Cand) * (size_t)nqa * c->sub_slots * c->sub_cap));
+  SDB_CUDA(cudaMalloc(&c->d_sub_cnt, sizeof(uint32_t) * (size_t)nqa * c->sub_slots));
   c->sc_nq = nqa;
   c->sc_cap = capa;
   c->sc_kp = kp;
@@ -219,45 +224,53 @@ __device__ void bitonic_sort_u64(uint64_t* s, uint32_t n) {
   }
 }
 
-// keep the best kp candidates of each query, tau = score of the kp-th (if that many exist)
+// keep the best kp candidates of each query, tau = score of the kp-th (if that many exist).
+// Sources: the query's main list (previous survivors, pass-0 fixed slots, K1 atomic appends) plus, for the tensor
+// core screens, the thread-private sub-lists written by the epilogue threads (one per CTA and column half).
 __global__ void __launch_bounds__(1024) cand_compact_kernel(Cand* __restrict__ cand, uint32_t* __restrict__ cnt,
                                                             float* __restrict__ tau, uint32_t* __restrict__ flags,
-                                                            uint32_t cap, uint32_t kp, const float* __restrict__ snorm) {
+                                                            uint32_t cap, uint32_t kp, const float* __restrict__ snorm,
+                                                            const Cand* __restrict__ sub, const uint32_t* __restrict__ sub_cnt,
+                                                            uint32_t n_slots, uint32_t subcap) {
   extern __shared__ uint64_t s_keys[];
-  __shared__ uint32_t s_valid;
+  __shared__ uint32_t s_n, s_over;
   const uint32_t q = blockIdx.x;
-  uint32_t n = cnt[q];
-  if (n > cap) {
-    if (threadIdx.x == 0) flags[q] |= 1u;  // candidates were dropped: this query must be re-run exactly
-    n = cap;
+  uint32_t n_main = cnt[q];
+  if (threadIdx.x == 0) {
+    s_over = n_main > cap ? 1u : 0u;
+    s_n = 0;
   }
-  if (threadIdx.x == 0) s_valid = 0;
+  if (n_main > cap) n_main = cap;
   __syncthreads();
+  auto push = [&](Cand cd) {
+    float sc = cd.score;
+    if (snorm) {  // integer screens score invalid rows 0: the row's NaN screening norm marks them
+      const float sn = snorm[cd.row];
+      if (!(sn == sn)) sc = sn;
+    }
+    if (sc == sc) {  // NaN scores (skipped / special / padding rows) are dropped
+      const uint32_t i = atomicAdd(&s_n, 1u);
+      if (i < cap) s_keys[i] = ((uint64_t)f32_key(sc) << 32) | (uint64_t)(0xFFFFFFFFu - cd.row);
+      else s_over = 1u;
+    }
+  };
   Cand* cq = cand + (size_t)q * cap;
+  for (uint32_t i = threadIdx.x; i < n_main; i += blockDim.x) push(cq[i]);
+  for (uint32_t s = threadIdx.x; s < n_slots; s += blockDim.x) {
+    uint32_t c = sub_cnt[(size_t)q * n_slots + s];
+    if (c > subcap) c = subcap;  // the producer flagged the overflow
+    const Cand* sp = sub + ((size_t)q * n_slots + s) * subcap;
+    for (uint32_t e = 0; e < c; e++) push(sp[e]);
+  }
+  __syncthreads();
+  const uint32_t n = s_n < cap ? s_n : cap;
+  if (threadIdx.x == 0 && s_over) flags[q] |= 1u;  // candidates were dropped: this query must be re-run exactly
   uint32_t p2 = 1;
   while (p2 < n) p2 <<= 1;
-  uint32_t my_valid = 0;
-  for (uint32_t i = threadIdx.x; i < p2; i += blockDim.x) {
-    uint64_t key = 0;  // padding and NaN scores (skipped / special / padding rows written by pass 0) sort last
-    if (i < n) {
-      float sc = cq[i].score;
-      if (snorm) {  // integer screens score invalid rows 0: the row's NaN screening norm marks them
-        const float sn = snorm[cq[i].row];
-        if (!(sn == sn)) sc = sn;
-      }
-      if (sc == sc) {
-        key = ((uint64_t)f32_key(sc) << 32) | (uint64_t)(0xFFFFFFFFu - cq[i].row);
-        my_valid++;
-      }
-    }
-    s_keys[i] = key;
-  }
-  if (my_valid) atomicAdd(&s_valid, my_valid);
+  for (uint32_t i = n + threadIdx.x; i < p2; i += blockDim.x) s_keys[i] = 0;  // padding sorts last
   __syncthreads();
-  const uint32_t valid = s_valid;
-  if (valid == n && n <= kp) return;  // nothing to drop, tau unchanged (uniform per block)
   bitonic_sort_u64<true>(s_keys, p2);
-  const uint32_t keep = valid < kp ? valid : kp;
+  const uint32_t keep = n < kp ? n : kp;
   for (uint32_t i = threadIdx.x; i < keep; i += blockDim.x) {
     const uint64_t key = s_keys[i];
     uint32_t fk = (uint32_t)(key >> 32);
@@ -271,7 +284,7 @@ __global__ void __launch_bounds__(1024) cand_compact_kernel(Cand* __restrict__ c
   if (threadIdx.x == 0) cnt[q] = keep;
 }
 
-sdb_status cand_compact(Corpus* c, uint32_t nq, uint32_t kp, bool drop_invalid, cudaStream_t st) {
+sdb_status cand_compact(Corpus* c, uint32_t nq, uint32_t kp, bool drop_invalid, uint32_t n_slots, cudaStream_t st) {
   const size_t smem = sizeof(uint64_t) * c->sc_cap;
   static bool attr_set = false;
   if (!attr_set) {
@@ -279,7 +292,8 @@ sdb_status cand_compact(Corpus* c, uint32_t nq, uint32_t kp, bool drop_invalid, 
     attr_set = true;
   }
   cand_compact_kernel<<<nq, 1024, smem, st>>>(c->d_cand, c->d_cand_cnt, c->d_tau, c->d_flags, c->sc_cap, kp,
-                                              drop_invalid ? c->d_snorm : nullptr);
+                                              drop_invalid ? c->d_snorm : nullptr, c->d_sub, c->d_sub_cnt, n_slots,
+                                              c->sub_cap);
   count_launch(c->ctx);
   SDB_CUDA(cudaGetLastError());
   return SDB_OK;

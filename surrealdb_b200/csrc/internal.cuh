@@ -119,6 +119,9 @@ struct Corpus {
   int8_t* d_q8 = nullptr;        // int8 queries nq_pad x dim_pad8
   float* d_q8scale = nullptr;    // max|q|/127 per query
   float* d_q8err = nullptr;      // |q - dequant(q)| / |q| per query
+  Cand* d_sub = nullptr;         // thread-private candidate sub-lists of the tensor-core screens
+  uint32_t* d_sub_cnt = nullptr; // [nq][sub_slots]
+  uint32_t sub_slots = 0, sub_cap = 0, last_slots = 0;
   float* d_bscale = nullptr;     // per query: factor that turns tau into similarity*|q| units (1 or q8scale)
   float* d_beps = nullptr;       // per query: rigorous screen error bound in cosine units
   float* d_tau = nullptr;
@@ -156,7 +159,7 @@ sdb_status scratch_for(Corpus* c, uint32_t nq, uint32_t cap, uint32_t kp);
 sdb_status prep_queries(Corpus* c, const double* d_queries, uint32_t nq, cudaStream_t st);
 sdb_status cand_reset(Corpus* c, uint32_t nq, cudaStream_t st);
 sdb_status cand_set_count(Corpus* c, uint32_t nq, uint32_t value, cudaStream_t st);
-sdb_status cand_compact(Corpus* c, uint32_t nq, uint32_t kp, bool drop_invalid, cudaStream_t st);
+sdb_status cand_compact(Corpus* c, uint32_t nq, uint32_t kp, bool drop_invalid, uint32_t n_slots, cudaStream_t st);
 sdb_status cand_rerank(Corpus* c, uint32_t nq, cudaStream_t st);
 sdb_status set_bounds(Corpus* c, uint32_t nq, int screen, float eps_rel, cudaStream_t st);
 sdb_status cand_final(Corpus* c, uint32_t nq, uint32_t k, uint32_t kp, float eps_rel, uint64_t row_base,

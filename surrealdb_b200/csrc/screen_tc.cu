@@ -19,6 +19,7 @@
 #include <cuda.h>
 
 #include "internal.cuh"
+#include "tmem_ld_gen.cuh"
 
 namespace sdb {
 
@@ -35,7 +36,9 @@ constexpr uint32_t ACC_STAGES = 2;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t EPI_WARPS = 8;             // two warps per TMEM lane quarter, each takes half the columns
 constexpr uint32_t THREADS = 64 + EPI_WARPS * 32;
-constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + ACC_STAGES * BLOCK_N * 4 + 256 + 1024;  // + align slack
+constexpr uint32_t MAX_MBLOCKS = 16;           // queries per launch <= 2048 (the driver splits larger batches)
+constexpr uint32_t SUBCAP = 16;                // private candidate slots per (query, CTA, column half) and pass
+constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + ACC_STAGES * BLOCK_N * 4 + 256 + MAX_MBLOCKS * 256 * 4 + 1024;
 static_assert(BLOCK_N == TILE_ROWS, "screen tile must match the pass schedule tile");
 
 // instruction descriptor (cute::UMMA::InstrDescriptor bit layout): D=f32, A=B=bf16, both K-major
@@ -113,12 +116,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 
-template <bool COSINE, bool INT8>
+template <bool COSINE, bool INT8, int LDW>
 __global__ void __launch_bounds__(THREADS, 1)
 screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const float* __restrict__ snorm, uint32_t k_blocks, uint32_t n_mblocks, uint32_t nq,
                  PassDesc pass, const float* __restrict__ tau, Cand* __restrict__ cand,
-                 uint32_t* __restrict__ cand_cnt, uint32_t cap) {
+                 uint32_t* __restrict__ cand_cnt, uint32_t cap, Cand* __restrict__ sub, uint32_t* __restrict__ sub_cnt,
+                 uint32_t* __restrict__ flags, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -131,6 +135,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint64_t* tfull_bar = bars + 2 * STAGES;        // [ACC_STAGES]
   uint64_t* tempty_bar = bars + 2 * STAGES + ACC_STAGES;  // [ACC_STAGES]
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES);
+  uint32_t* s_cnt = s_tmem + 4;  // [n_mblocks][256] private append counters of the epilogue threads
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t n_items = pass.count * n_mblocks;
@@ -148,6 +153,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  for (uint32_t i = threadIdx.x; i < n_mblocks * 256; i += blockDim.x) s_cnt[i] = 0;
   if (warp == 1) {  // TMEM allocation (whole warp), address lands in shared memory
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
                  "n"(TMEM_COLS)
@@ -253,6 +259,71 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((wq * 32) << 16) + a * BLOCK_N + cbase;
       Cand* my_cand = cand + (size_t)q * cap;
+      const uint32_t n_slots = gridDim.x * 2;
+      uint32_t* my_cnt = s_cnt + mb * 256 + et;
+      Cand* my_sub = sub + ((size_t)q * n_slots + blockIdx.x * 2 + half) * SUBCAP;
+      if (dbg & 1) {
+        // (debug) no accumulator read-out at all: measures the TMA + MMA pipeline alone
+      } else if (dbg & 2) {
+        // (debug) accumulator read-out without any arithmetic
+        uint32_t vv[32];
+        uint32_t x = 0;
+#pragma unroll
+        for (uint32_t cc = 0; cc < 4; cc++) {
+          tmem_ld32(taddr + cc * 32, vv);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          x ^= vv[0] ^ vv[31];
+        }
+        if (x == 0x12345u) cand_cnt[0] = x;
+      } else if (dbg & 8) {
+        // (debug) read-out + max chain, no threshold test
+        uint32_t vv[32];
+        int mm = (int)0x80000000;
+#pragma unroll
+        for (uint32_t cc = 0; cc < 4; cc++) {
+          tmem_ld32(taddr + cc * 32, vv);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 32; i++) mm = max(mm, (int)vv[i]);
+        }
+        if (mm == 0x12345) cand_cnt[0] = mm;
+      } else if (dbg & 4) {
+        // (debug) no read-out, fixed 1000-cycle delay instead
+        const long long t0 = clock64();
+        while (clock64() - t0 < 1000) {}
+      } else if (INT8 && LDW == 128) {
+        // one 128-column load per warp and item (fewer, wider TMEM reads)
+        uint32_t v[128];
+        tmem_ld128(taddr, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        int m = (int)v[0];
+#pragma unroll
+        for (int i = 1; i < 128; i++) m = max(m, (int)v[i]);
+        if (pass0) {
+          if (q < nq) {
+#pragma unroll
+            for (int i = 0; i < 128; i++) {
+              Cand cd;
+              cd.score = __int2float_rn((int)v[i]);
+              cd.row = (uint32_t)(row0 + cbase + i);
+              my_cand[(size_t)tidx * BLOCK_N + cbase + i] = cd;
+            }
+          }
+        } else if (m >= tau_i) {
+#pragma unroll
+          for (int i = 0; i < 128; i++) {
+            if ((int)v[i] >= tau_i) {
+              const uint32_t pos = (*my_cnt)++;
+              if (pos < SUBCAP) {
+                Cand cd;
+                cd.score = __int2float_rn((int)v[i]);
+                cd.row = (uint32_t)(row0 + cbase + i);
+                my_sub[pos] = cd;
+              }
+            }
+          }
+        }
+      } else {
       uint32_t va[32], vb[32];
       tmem_ld32(taddr, va);
 #pragma unroll
@@ -279,12 +350,12 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
             for (int i = 0; i < 32; i++) {
               if ((int)v[i] >= tau_i) {
-                const uint32_t pos = atomicAdd(cand_cnt + q, 1u);
-                if (pos < cap) {
+                const uint32_t pos = (*my_cnt)++;  // thread-private: no atomics, no round trip
+                if (pos < SUBCAP) {
                   Cand cd;
                   cd.score = __int2float_rn((int)v[i]);
                   cd.row = (uint32_t)(row0 + cbase + c0 + i);
-                  my_cand[pos] = cd;
+                  my_sub[pos] = cd;
                 }
               }
             }
@@ -315,21 +386,34 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
             for (int i = 0; i < 32; i++) {
               if (sc[i] >= my_tau) {
-                const uint32_t pos = atomicAdd(cand_cnt + q, 1u);
-                if (pos < cap) {
+                const uint32_t pos = (*my_cnt)++;  // thread-private: no atomics, no round trip
+                if (pos < SUBCAP) {
                   Cand cd;
                   cd.score = sc[i];
                   cd.row = (uint32_t)(row0 + cbase + c0 + i);
-                  my_cand[pos] = cd;
+                  my_sub[pos] = cd;
                 }
               }
             }
           }
         }
       }
+      }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[a]));
+    }
+    // publish the private append counters: slot (CTA, column half) of every query this thread served
+    if (!pass0) {
+      const uint32_t n_slots = gridDim.x * 2;
+      for (uint32_t mb = 0; mb < n_mblocks; mb++) {
+        const uint32_t qq = mb * BLOCK_M + row_in_tile;
+        if (qq < nq) {
+          const uint32_t cnt = s_cnt[mb * 256 + et];
+          sub_cnt[(size_t)qq * n_slots + blockIdx.x * 2 + half] = cnt;
+          if (cnt > SUBCAP) atomicOr(flags + qq, 1u);  // private slots overflowed: exact re-run for this query
+        }
+      }
     }
   }
   __syncthreads();
@@ -388,38 +472,56 @@ sdb_status screen_tc_pass(Corpus* c, uint32_t nq, const PassDesc& p, bool int8, 
     return SDB_EUNSUPPORTED;
   }
   const uint64_t n_pad = (c->n + TILE_ROWS - 1) / TILE_ROWS * TILE_ROWS;
-  const uint32_t nq_pad = (nq + tc::BLOCK_M - 1) / tc::BLOCK_M * tc::BLOCK_M;
-  CUtensorMap map_a, map_b;
-  if (int8) {
-    SDB_TRY(make_map(ctx, &map_a, c->d_q8, nq_pad, c->dim_pad8, tc::BLOCK_M, false, true));
-    SDB_TRY(make_map(ctx, &map_b, c->d_i8, n_pad, c->dim_pad8, tc::BLOCK_N, true, true));
-  } else {
-    SDB_TRY(make_map(ctx, &map_a, c->d_qbf16, nq_pad, c->dim_pad, tc::BLOCK_M, false));
-    SDB_TRY(make_map(ctx, &map_b, c->d_bf16, n_pad, c->dim_pad, tc::BLOCK_N, true));
-  }
   static bool attr_set = false;
   if (!attr_set) {
-    SDB_CUDA(cudaFuncSetAttribute(tc::screen_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-    SDB_CUDA(cudaFuncSetAttribute(tc::screen_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-    SDB_CUDA(cudaFuncSetAttribute(tc::screen_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    SDB_CUDA(cudaFuncSetAttribute(tc::screen_tc_kernel<true, false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    SDB_CUDA(cudaFuncSetAttribute(tc::screen_tc_kernel<false, false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    SDB_CUDA(cudaFuncSetAttribute(tc::screen_tc_kernel<true, true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
     attr_set = true;
   }
-  const uint32_t n_mblocks = nq_pad / tc::BLOCK_M;
-  const uint64_t n_items = (uint64_t)p.count * n_mblocks;
-  uint32_t grid = (uint32_t)ctx->sm_count;
-  if (grid > n_items) grid = (uint32_t)n_items;
+  static const int dbg = getenv("SDB_TC_DBG") ? atoi(getenv("SDB_TC_DBG")) : 0;
+  CUtensorMap map_b;
+  if (int8) SDB_TRY(make_map(ctx, &map_b, c->d_i8, n_pad, c->dim_pad8, tc::BLOCK_N, true, true));
+  else SDB_TRY(make_map(ctx, &map_b, c->d_bf16, n_pad, c->dim_pad, tc::BLOCK_N, true));
   const uint32_t k_blocks = int8 ? c->dim_pad8 / (2 * tc::BLOCK_K) : c->dim_pad / tc::BLOCK_K;
-  if (int8)
-    tc::screen_tc_kernel<true, true><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(map_a, map_b, c->d_snorm, k_blocks, n_mblocks,
-                                                                               nq, p, c->d_tau, c->d_cand, c->d_cand_cnt, c->sc_cap);
-  else if (c->metric == SDB_COSINE)
-    tc::screen_tc_kernel<true, false><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(map_a, map_b, c->d_snorm, k_blocks, n_mblocks,
-                                                                                nq, p, c->d_tau, c->d_cand, c->d_cand_cnt, c->sc_cap);
-  else
-    tc::screen_tc_kernel<false, false><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(map_a, map_b, c->d_snorm, k_blocks, n_mblocks,
-                                                                                 nq, p, c->d_tau, c->d_cand, c->d_cand_cnt, c->sc_cap);
-  count_launch(ctx);
-  if (p.excl == 0) SDB_TRY(cand_set_count(c, nq, p.count * TILE_ROWS, st));  // pass 0 wrote fixed slots
+  // every launch uses the same grid so that the (CTA, half) slot numbering of the private sub-lists is stable
+  const uint32_t chunk_q = tc::MAX_MBLOCKS * tc::BLOCK_M;
+  uint32_t grid = (uint32_t)ctx->sm_count;
+  {
+    const uint32_t nq0 = nq < chunk_q ? nq : chunk_q;
+    const uint64_t items0 = (uint64_t)p.count * ((nq0 + tc::BLOCK_M - 1) / tc::BLOCK_M);
+    if (grid > items0) grid = (uint32_t)items0;
+  }
+  c->last_slots = grid * 2;
+  const uint32_t slots = c->last_slots;
+  for (uint32_t q0 = 0; q0 < nq; q0 += chunk_q) {
+    const uint32_t nqc = nq - q0 < chunk_q ? nq - q0 : chunk_q;
+    const uint32_t nq_pad = (nqc + tc::BLOCK_M - 1) / tc::BLOCK_M * tc::BLOCK_M;
+    const uint32_t n_mblocks = nq_pad / tc::BLOCK_M;
+    CUtensorMap map_a;
+    if (int8) SDB_TRY(make_map(ctx, &map_a, c->d_q8 + (size_t)q0 * c->dim_pad8, nq_pad, c->dim_pad8, tc::BLOCK_M, false, true));
+    else SDB_TRY(make_map(ctx, &map_a, c->d_qbf16 + (size_t)q0 * c->dim_pad, nq_pad, c->dim_pad, tc::BLOCK_M, false));
+    const float* tau = c->d_tau + q0;
+    Cand* cand = c->d_cand + (size_t)q0 * c->sc_cap;
+    uint32_t* ccnt = c->d_cand_cnt + q0;
+    Cand* sub = c->d_sub + (size_t)q0 * slots * tc::SUBCAP;
+    uint32_t* scnt = c->d_sub_cnt + (size_t)q0 * slots;
+    uint32_t* flags = c->d_flags + q0;
+    if (int8)
+      tc::screen_tc_kernel<true, true, 32><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(map_a, map_b, c->d_snorm, k_blocks, n_mblocks, nqc, p,
+                                                                                     tau, cand, ccnt, c->sc_cap, sub, scnt, flags, dbg);
+    else if (c->metric == SDB_COSINE)
+      tc::screen_tc_kernel<true, false, 32><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(map_a, map_b, c->d_snorm, k_blocks, n_mblocks, nqc, p,
+                                                                                      tau, cand, ccnt, c->sc_cap, sub, scnt, flags, dbg);
+    else
+      tc::screen_tc_kernel<false, false, 32><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(map_a, map_b, c->d_snorm, k_blocks, n_mblocks, nqc, p,
+                                                                                       tau, cand, ccnt, c->sc_cap, sub, scnt, flags, dbg);
+    count_launch(ctx);
+  }
+  if (p.excl == 0) {
+    SDB_TRY(cand_set_count(c, nq, p.count * TILE_ROWS, st));  // pass 0 wrote fixed slots of the main lists
+    c->last_slots = 0;                                         // ... and no private sub-lists
+  }
   SDB_CUDA(cudaGetLastError());
   return SDB_OK;
 }

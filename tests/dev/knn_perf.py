@@ -35,6 +35,8 @@ for screen, batches in cfgs:
         best = min(m["total_ms"] for m in ms[-max(1, len(ms) - 1):])
         bs = min(m["screen_ms"] for m in ms[-max(1, len(ms) - 1):])
         flops = 2.0 * b * rows * dim
+        if os.environ.get("SDB_TC_DBG"):
+            print("per-call screen_ms:", [round(m["screen_ms"], 3) for m in ms], "passes", [m["n_passes"] for m in ms])
         print(f"{screen} B={b}: total {best:.3f} ms screen {bs:.3f} ms -> {b/best*1e3:.0f} QPS, "
               f"screen {flops/bs/1e9:.1f} TFLOP/s, f32-stream-equiv {rows*dim*4*((b+7)//8 if screen=='SIMT_F32' else 1)/bs/1e6:.0f} GB/s, "
               f"passes {s['n_passes']} fallback {s['n_fallback']} launches {s['kernel_launches']}", flush=True)
