@@ -48,6 +48,10 @@ constexpr uint32_t IDESC_I8 = (2u << 4) | (1u << 7) | (1u << 10) | ((BLOCK_N >> 
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// work item w -> (corpus tile w / n_mb, query block): the query block is skewed by the tile index so that every CTA
+// serves every query block equally often (keeps the per-(query, CTA) private candidate sub-lists evenly filled)
+__device__ __forceinline__ uint32_t item_mb(uint32_t w, uint32_t n_mb) { return (w % n_mb + w / n_mb) % n_mb; }
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -171,7 +175,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       uint32_t it = 0;
       for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x) {
         const uint32_t tile = pass_tile(pass, w / n_mblocks);
-        const uint32_t mb = w % n_mblocks;
+        const uint32_t mb = item_mb(w, n_mblocks);
         for (uint32_t kb = 0; kb < k_blocks; kb++, it++) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
@@ -223,13 +227,13 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint32_t w = blockIdx.x;
     float next_tau = __int_as_float(0x7f800000);
     if (w < n_items) {
-      const uint32_t q0 = (w % n_mblocks) * BLOCK_M + row_in_tile;
+      const uint32_t q0 = item_mb(w, n_mblocks) * BLOCK_M + row_in_tile;
       if (q0 < nq) next_tau = __ldg(tau + q0);
     }
     for (; w < n_items; w += gridDim.x, j++) {
       const uint32_t tidx = w / n_mblocks;
       const uint32_t tile = pass_tile(pass, tidx);
-      const uint32_t mb = w % n_mblocks;
+      const uint32_t mb = item_mb(w, n_mblocks);
       const uint32_t a = j % ACC_STAGES, pa = (j / ACC_STAGES) & 1;
       const uint32_t q = mb * BLOCK_M + row_in_tile;
       const float my_tau = next_tau;
@@ -237,7 +241,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const uint32_t wn = w + gridDim.x;
         next_tau = __int_as_float(0x7f800000);
         if (wn < n_items) {
-          const uint32_t qn = (wn % n_mblocks) * BLOCK_M + row_in_tile;
+          const uint32_t qn = item_mb(wn, n_mblocks) * BLOCK_M + row_in_tile;
           if (qn < nq) next_tau = __ldg(tau + qn);
         }
       }
