@@ -355,11 +355,14 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int i = 0; i < 32; i++) {
               if ((int)v[i] >= tau_i) {
                 const uint32_t pos = (*my_cnt)++;  // thread-private: no atomics, no round trip
+                Cand cd;
+                cd.score = __int2float_rn((int)v[i]);
+                cd.row = (uint32_t)(row0 + cbase + c0 + i);
                 if (pos < SUBCAP) {
-                  Cand cd;
-                  cd.score = __int2float_rn((int)v[i]);
-                  cd.row = (uint32_t)(row0 + cbase + c0 + i);
                   my_sub[pos] = cd;
+                } else {  // private slots full (small passes run few CTAs): spill to the query's shared list
+                  const uint32_t p2 = atomicAdd(cand_cnt + q, 1u);
+                  if (p2 < cap) my_cand[p2] = cd;
                 }
               }
             }
@@ -391,11 +394,14 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int i = 0; i < 32; i++) {
               if (sc[i] >= my_tau) {
                 const uint32_t pos = (*my_cnt)++;  // thread-private: no atomics, no round trip
+                Cand cd;
+                cd.score = sc[i];
+                cd.row = (uint32_t)(row0 + cbase + c0 + i);
                 if (pos < SUBCAP) {
-                  Cand cd;
-                  cd.score = sc[i];
-                  cd.row = (uint32_t)(row0 + cbase + c0 + i);
                   my_sub[pos] = cd;
+                } else {  // private slots full (small passes run few CTAs): spill to the query's shared list
+                  const uint32_t p2 = atomicAdd(cand_cnt + q, 1u);
+                  if (p2 < cap) my_cand[p2] = cd;
                 }
               }
             }
@@ -415,7 +421,6 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (qq < nq) {
           const uint32_t cnt = s_cnt[mb * 256 + et];
           sub_cnt[(size_t)qq * n_slots + blockIdx.x * 2 + half] = cnt;
-          if (cnt > SUBCAP) atomicOr(flags + qq, 1u);  // private slots overflowed: exact re-run for this query
         }
       }
     }
