@@ -19,7 +19,6 @@
 #include <cuda.h>
 
 #include "internal.cuh"
-#include "tmem_ld_gen.cuh"
 
 namespace sdb {
 
@@ -120,13 +119,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 
-template <bool COSINE, bool INT8, int LDW>
+// out-of-line survivor append: keeps the (rare) slow path out of the unrolled epilogue body
+__device__ __noinline__ void append_survivor(Cand* my_sub, uint32_t* my_cnt, Cand* my_cand, uint32_t* cnt_q, uint32_t cap,
+                                             float score, uint32_t row) {
+  const uint32_t pos = (*my_cnt)++;  // thread-private counter in shared memory: no atomics, no round trip
+  Cand cd;
+  cd.score = score;
+  cd.row = row;
+  if (pos < SUBCAP) {
+    my_sub[pos] = cd;
+  } else {  // private slots full (small passes run few CTAs): spill to the query's shared list
+    const uint32_t p2 = atomicAdd(cnt_q, 1u);
+    if (p2 < cap) my_cand[p2] = cd;
+  }
+}
+
+template <bool COSINE, bool INT8, bool PASS0>
 __global__ void __launch_bounds__(THREADS, 1)
 screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const float* __restrict__ snorm, uint32_t k_blocks, uint32_t n_mblocks, uint32_t nq,
                  PassDesc pass, const float* __restrict__ tau, Cand* __restrict__ cand,
-                 uint32_t* __restrict__ cand_cnt, uint32_t cap, Cand* __restrict__ sub, uint32_t* __restrict__ sub_cnt,
-                 uint32_t* __restrict__ flags, int dbg) {
+                 uint32_t* __restrict__ cand_cnt, uint32_t cap, Cand* __restrict__ sub, uint32_t* __restrict__ sub_cnt) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -220,7 +233,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t half = (warp - 2) >> 2;        // 0: columns 0..127, 1: columns 128..255
     const uint32_t row_in_tile = wq * 32 + lane;
     const uint32_t et = threadIdx.x - 64;         // 0..255
-    const bool pass0 = pass.excl == 0;            // tau = -inf everywhere: positions are deterministic, no atomics
+    constexpr bool pass0 = PASS0;                 // pass 0: tau = -inf everywhere, positions are deterministic
     const uint32_t cbase = half * (BLOCK_N / 2);
     uint32_t j = 0;
     // the threshold of the first item; later items prefetch theirs while the current one is processed
@@ -266,68 +279,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint32_t n_slots = gridDim.x * 2;
       uint32_t* my_cnt = s_cnt + mb * 256 + et;
       Cand* my_sub = sub + ((size_t)q * n_slots + blockIdx.x * 2 + half) * SUBCAP;
-      if (dbg & 1) {
-        // (debug) no accumulator read-out at all: measures the TMA + MMA pipeline alone
-      } else if (dbg & 2) {
-        // (debug) accumulator read-out without any arithmetic
-        uint32_t vv[32];
-        uint32_t x = 0;
-#pragma unroll
-        for (uint32_t cc = 0; cc < 4; cc++) {
-          tmem_ld32(taddr + cc * 32, vv);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          x ^= vv[0] ^ vv[31];
-        }
-        if (x == 0x12345u) cand_cnt[0] = x;
-      } else if (dbg & 8) {
-        // (debug) read-out + max chain, no threshold test
-        uint32_t vv[32];
-        int mm = (int)0x80000000;
-#pragma unroll
-        for (uint32_t cc = 0; cc < 4; cc++) {
-          tmem_ld32(taddr + cc * 32, vv);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int i = 0; i < 32; i++) mm = max(mm, (int)vv[i]);
-        }
-        if (mm == 0x12345) cand_cnt[0] = mm;
-      } else if (dbg & 4) {
-        // (debug) no read-out, fixed 1000-cycle delay instead
-        const long long t0 = clock64();
-        while (clock64() - t0 < 1000) {}
-      } else if (INT8 && LDW == 128) {
-        // one 128-column load per warp and item (fewer, wider TMEM reads)
-        uint32_t v[128];
-        tmem_ld128(taddr, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        int m = (int)v[0];
-#pragma unroll
-        for (int i = 1; i < 128; i++) m = max(m, (int)v[i]);
-        if (pass0) {
-          if (q < nq) {
-#pragma unroll
-            for (int i = 0; i < 128; i++) {
-              Cand cd;
-              cd.score = __int2float_rn((int)v[i]);
-              cd.row = (uint32_t)(row0 + cbase + i);
-              my_cand[(size_t)tidx * BLOCK_N + cbase + i] = cd;
-            }
-          }
-        } else if (m >= tau_i) {
-#pragma unroll
-          for (int i = 0; i < 128; i++) {
-            if ((int)v[i] >= tau_i) {
-              const uint32_t pos = (*my_cnt)++;
-              if (pos < SUBCAP) {
-                Cand cd;
-                cd.score = __int2float_rn((int)v[i]);
-                cd.row = (uint32_t)(row0 + cbase + i);
-                my_sub[pos] = cd;
-              }
-            }
-          }
-        }
-      } else {
+      {
       uint32_t va[32], vb[32];
       tmem_ld32(taddr, va);
 #pragma unroll
@@ -354,16 +306,8 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
             for (int i = 0; i < 32; i++) {
               if ((int)v[i] >= tau_i) {
-                const uint32_t pos = (*my_cnt)++;  // thread-private: no atomics, no round trip
-                Cand cd;
-                cd.score = __int2float_rn((int)v[i]);
-                cd.row = (uint32_t)(row0 + cbase + c0 + i);
-                if (pos < SUBCAP) {
-                  my_sub[pos] = cd;
-                } else {  // private slots full (small passes run few CTAs): spill to the query's shared list
-                  const uint32_t p2 = atomicAdd(cand_cnt + q, 1u);
-                  if (p2 < cap) my_cand[p2] = cd;
-                }
+                append_survivor(my_sub, my_cnt, my_cand, cand_cnt + q, cap, __int2float_rn((int)v[i]),
+                                (uint32_t)(row0 + cbase + c0 + i));
               }
             }
           }
@@ -393,16 +337,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
             for (int i = 0; i < 32; i++) {
               if (sc[i] >= my_tau) {
-                const uint32_t pos = (*my_cnt)++;  // thread-private: no atomics, no round trip
-                Cand cd;
-                cd.score = sc[i];
-                cd.row = (uint32_t)(row0 + cbase + c0 + i);
-                if (pos < SUBCAP) {
-                  my_sub[pos] = cd;
-                } else {  // private slots full (small passes run few CTAs): spill to the query's shared list
-                  const uint32_t p2 = atomicAdd(cand_cnt + q, 1u);
-                  if (p2 < cap) my_cand[p2] = cd;
-                }
+                append_survivor(my_sub, my_cnt, my_cand, cand_cnt + q, cap, sc[i], (uint32_t)(row0 + cbase + c0 + i));
               }
             }
           }
@@ -483,12 +418,15 @@ sdb_status screen_tc_pass(Corpus* c, uint32_t nq, const PassDesc& p, bool int8, 
   const uint64_t n_pad = (c->n + TILE_ROWS - 1) / TILE_ROWS * TILE_ROWS;
   static bool attr_set = false;
   if (!attr_set) {
-    SDB_CUDA(cudaFuncSetAttribute(tc::screen_tc_kernel<true, false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-    SDB_CUDA(cudaFuncSetAttribute(tc::screen_tc_kernel<false, false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-    SDB_CUDA(cudaFuncSetAttribute(tc::screen_tc_kernel<true, true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+#define SET_SMEM(COS, I8)                                                                                                              \
+  SDB_CUDA(cudaFuncSetAttribute(tc::screen_tc_kernel<COS, I8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES)); \
+  SDB_CUDA(cudaFuncSetAttribute(tc::screen_tc_kernel<COS, I8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES))
+    SET_SMEM(true, false);
+    SET_SMEM(false, false);
+    SET_SMEM(true, true);
+#undef SET_SMEM
     attr_set = true;
   }
-  static const int dbg = getenv("SDB_TC_DBG") ? atoi(getenv("SDB_TC_DBG")) : 0;
   CUtensorMap map_b;
   if (int8) SDB_TRY(make_map(ctx, &map_b, c->d_i8, n_pad, c->dim_pad8, tc::BLOCK_N, true, true));
   else SDB_TRY(make_map(ctx, &map_b, c->d_bf16, n_pad, c->dim_pad, tc::BLOCK_N, true));
@@ -515,16 +453,19 @@ sdb_status screen_tc_pass(Corpus* c, uint32_t nq, const PassDesc& p, bool int8, 
     uint32_t* ccnt = c->d_cand_cnt + q0;
     Cand* sub = c->d_sub + (size_t)q0 * slots * tc::SUBCAP;
     uint32_t* scnt = c->d_sub_cnt + (size_t)q0 * slots;
-    uint32_t* flags = c->d_flags + q0;
-    if (int8)
-      tc::screen_tc_kernel<true, true, 32><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(map_a, map_b, c->d_snorm, k_blocks, n_mblocks, nqc, p,
-                                                                                     tau, cand, ccnt, c->sc_cap, sub, scnt, flags, dbg);
-    else if (c->metric == SDB_COSINE)
-      tc::screen_tc_kernel<true, false, 32><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(map_a, map_b, c->d_snorm, k_blocks, n_mblocks, nqc, p,
-                                                                                      tau, cand, ccnt, c->sc_cap, sub, scnt, flags, dbg);
-    else
-      tc::screen_tc_kernel<false, false, 32><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(map_a, map_b, c->d_snorm, k_blocks, n_mblocks, nqc, p,
-                                                                                       tau, cand, ccnt, c->sc_cap, sub, scnt, flags, dbg);
+#define LAUNCH_TC(COS, I8)                                                                                      \
+  do {                                                                                                         \
+    if (p.excl == 0)                                                                                           \
+      tc::screen_tc_kernel<COS, I8, true><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(                          \
+          map_a, map_b, c->d_snorm, k_blocks, n_mblocks, nqc, p, tau, cand, ccnt, c->sc_cap, sub, scnt);        \
+    else                                                                                                       \
+      tc::screen_tc_kernel<COS, I8, false><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(                         \
+          map_a, map_b, c->d_snorm, k_blocks, n_mblocks, nqc, p, tau, cand, ccnt, c->sc_cap, sub, scnt);        \
+  } while (0)
+    if (int8) LAUNCH_TC(true, true);
+    else if (c->metric == SDB_COSINE) LAUNCH_TC(true, false);
+    else LAUNCH_TC(false, false);
+#undef LAUNCH_TC
     count_launch(ctx);
   }
   if (p.excl == 0) {
