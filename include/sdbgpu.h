@@ -151,6 +151,17 @@ void sdb_hnsw_destroy(sdb_hnsw*);
 sdb_status sdb_hnsw_search(sdb_hnsw*, const float* queries, uint32_t nq, uint32_t k, uint32_t ef,
                            uint64_t* out_elems, double* out_dist, uint32_t* out_count, uint64_t* out_counters);
 
+/* Index-construction helper ("next" row): Heuristic::select, standard variant
+ * (idx/trees/hnsw/heuristic.rs:61-81,201-216), applied in parallel to pre-ranked candidate lists.
+ * d_vectors: n x dim f32 (device) of the layer's members; d_cand: n x kc candidate member indices, nearest first
+ * (e.g. the rows written by sdb_knn_bruteforce_device; the element itself is skipped), d_cand_cnt: valid entries per
+ * row.  For every element: if it has <= m_max candidates all are taken, otherwise candidates are visited nearest-first
+ * and e is accepted iff no already accepted r is closer to e than the element is (e_dist > dist(e,r) rejects), until
+ * m_max are accepted.  d_out: n x m_max member indices, d_out_cnt: accepted count.  All pointers are device pointers. */
+sdb_status sdb_hnsw_select_neighbors(sdb_ctx*, const float* d_vectors, uint32_t dim, sdb_metric, uint64_t row0, uint64_t n,
+                                     const uint64_t* d_cand, const uint32_t* d_cand_cnt, uint32_t kc, uint32_t m_max,
+                                     uint32_t* d_out, uint32_t* d_out_cnt);
+
 /* ---- graph expansion: replaces GraphEdgeScan::execute (exec/operators/scan/graph.rs:168-283)
  *      driven by LookupPart (exec/parts/lookup.rs:139-170) and the +collect recursion
  *      (exec/operators/recursion/collect.rs:74-143) -------------------------------------------- */

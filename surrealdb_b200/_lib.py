@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "sdb_ctx_kernel_launches", "sdb_ctx_stream", "sdb_corpus_create", "sdb_corpus_destroy", "sdb_corpus_append",
     "sdb_corpus_append_device", "sdb_corpus_append_synthetic", "sdb_corpus_set_skip", "sdb_corpus_finalize",
     "sdb_corpus_rows", "sdb_corpus_set_screen", "sdb_knn_bruteforce", "sdb_knn_bruteforce_device",
-    "sdb_knn_last_stats", "sdb_topk_merge_device", "sdb_hnsw_load", "sdb_hnsw_destroy", "sdb_hnsw_search",
+    "sdb_knn_last_stats", "sdb_topk_merge_device", "sdb_hnsw_load", "sdb_hnsw_destroy", "sdb_hnsw_search", "sdb_hnsw_select_neighbors",
     "sdb_graph_load_csr", "sdb_graph_destroy", "sdb_graph_expand", "sdb_graph_collect", "sdb_free",
 ]
 
@@ -81,6 +81,7 @@ def lib():
     L.sdb_hnsw_load.argtypes = [vp, u32, i32, u64, vp, u32, vp, vp, C.c_int64, C.POINTER(vp)]
     L.sdb_hnsw_destroy.argtypes = [vp]
     L.sdb_hnsw_search.argtypes = [vp, vp, u32, u32, u32, vp, vp, vp, vp]
+    L.sdb_hnsw_select_neighbors.argtypes = [vp, vp, u32, i32, u64, u64, vp, vp, u32, u32, vp, vp]
     L.sdb_graph_load_csr.argtypes = [vp, u64, vp, vp, C.POINTER(vp)]
     L.sdb_graph_destroy.argtypes = [vp]
     L.sdb_graph_expand.argtypes = [vp, u32, vp, u64, u32, C.POINTER(vp), C.POINTER(u64)]

@@ -341,6 +341,89 @@ __global__ void __launch_bounds__(HN_WARPS * 32) hnsw_search_kernel(HnswParams P
   }
 }
 
+// ---- construction helper: Heuristic::select over pre-ranked candidates, one warp per element ------------------------
+template <bool COSINE>
+__device__ __forceinline__ float warp_pair_dist(const float* a_smem, float a_n2, const float* __restrict__ b, uint32_t dim) {
+  const uint32_t lane = threadIdx.x & 31u;
+  float dot = 0.f, n2 = 0.f;
+  for (uint32_t c = lane; c < dim; c += 32) {
+    const float x = a_smem[c], y = __ldg(b + c);
+    if (COSINE) {
+      dot = fmaf(x, y, dot);
+      n2 = fmaf(y, y, n2);
+    } else {
+      const float d = x - y;
+      dot = fmaf(d, d, dot);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (COSINE) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+  }
+  return COSINE ? 1.f - dot * rsqrtf(a_n2 * n2) : dot;  // euclid: squared distance (same ordering)
+}
+
+template <bool COSINE>
+__global__ void __launch_bounds__(128) hnsw_select_kernel(const float* __restrict__ vec, uint32_t dim, uint64_t row0, uint64_t n,
+                                                          const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cand_cnt,
+                                                          uint32_t kc, uint32_t m_max, uint32_t* __restrict__ out,
+                                                          uint32_t* __restrict__ out_cnt) {
+  extern __shared__ float s_sel[];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s_q = s_sel + (size_t)warp * 2 * dim;
+  float* s_e = s_q + dim;
+  const uint64_t i = (uint64_t)blockIdx.x * 4 + warp;  // element index inside this batch
+  if (i >= n) return;
+  const uint64_t self = row0 + i;
+  const float* q = vec + self * dim;
+  float qn2 = 0.f;
+  for (uint32_t c = lane; c < dim; c += 32) {
+    const float x = __ldg(q + c);
+    s_q[c] = x;
+    qn2 = fmaf(x, x, qn2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) qn2 += __shfl_xor_sync(0xffffffffu, qn2, o);
+  __syncwarp();
+  const uint64_t* cl = cand + i * kc;
+  uint32_t nc = cand_cnt[i] < kc ? cand_cnt[i] : kc;
+  uint32_t n_real = 0;  // candidates other than the element itself
+  for (uint32_t j = 0; j < nc; j++) n_real += cl[j] != self;
+  uint32_t* o = out + i * m_max;
+  uint32_t acc = 0;
+  const bool take_all = n_real <= m_max;
+  for (uint32_t j = 0; j < nc && acc < m_max; j++) {
+    const uint64_t e = cl[j];
+    if (e == self) continue;
+    bool ok = true;
+    if (!take_all) {
+      const float* ev = vec + e * dim;
+      float en2 = 0.f;
+      for (uint32_t c = lane; c < dim; c += 32) {
+        const float x = __ldg(ev + c);
+        s_e[c] = x;
+        en2 = fmaf(x, x, en2);
+      }
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) en2 += __shfl_xor_sync(0xffffffffu, en2, o2);
+      __syncwarp();
+      const float e_dist = warp_pair_dist<COSINE>(s_q, qn2, ev, dim);
+      for (uint32_t r = 0; r < acc && ok; r++) {
+        const float r_dist = warp_pair_dist<COSINE>(s_e, en2, vec + (uint64_t)o[r] * dim, dim);
+        if (e_dist > r_dist) ok = false;  // is_closer: heuristic.rs:209-211
+      }
+      __syncwarp();
+    }
+    if (ok) {
+      if (lane == 0) o[acc] = (uint32_t)e;
+      acc++;
+      __syncwarp();
+    }
+  }
+  if (lane == 0) out_cnt[i] = acc;
+}
+
 }  // namespace sdb
 
 struct sdb_hnsw : sdb::Hnsw {};
@@ -416,6 +499,24 @@ sdb_status sdb_hnsw_load(sdb_ctx* ctx, uint32_t dim, sdb_metric metric, uint64_t
   SDB_CUDA(cudaStreamSynchronize(st));
   SDB_CUDA(cudaGetLastError());
   *out = h;
+  return SDB_OK;
+}
+
+sdb_status sdb_hnsw_select_neighbors(sdb_ctx* ctx, const float* d_vectors, uint32_t dim, sdb_metric metric, uint64_t row0,
+                                     uint64_t n, const uint64_t* d_cand, const uint32_t* d_cand_cnt, uint32_t kc,
+                                     uint32_t m_max, uint32_t* d_out, uint32_t* d_out_cnt) {
+  if (!ctx || !d_vectors || !d_cand || !d_cand_cnt || !d_out || !d_out_cnt || !dim || !kc || !m_max) return SDB_EINVAL;
+  if (metric != SDB_COSINE && metric != SDB_EUCLIDEAN) return SDB_EUNSUPPORTED;
+  if (n == 0) return SDB_OK;
+  std::lock_guard<std::mutex> guard(ctx->mu);
+  SDB_CUDA(cudaSetDevice(ctx->device));
+  const size_t smem = sizeof(float) * 2 * dim * 4;
+  auto kern = metric == SDB_COSINE ? hnsw_select_kernel<true> : hnsw_select_kernel<false>;
+  SDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)((n + 3) / 4), 128, smem, ctx->stream>>>(d_vectors, dim, row0, n, d_cand, d_cand_cnt, kc, m_max, d_out, d_out_cnt);
+  count_launch(ctx);
+  SDB_CUDA(cudaGetLastError());
+  SDB_CUDA(cudaStreamSynchronize(ctx->stream));
   return SDB_OK;
 }
 

@@ -24,13 +24,46 @@ def assign_levels(n, m, seed):
     return np.floor(-np.log(u) * ml).astype(np.int64)
 
 
-def build_layers(ctx, vectors_dev, n, dim, metric="EUCLIDEAN", m=16, m0=32, seed=1, batch=4096, progress=None):
+def _merge_reverse(fwd, cnt, m_max):
+    """bidirectional linking (graph.rs:52-64): every selected edge u->v also adds v->u; a node keeps its own
+    selection first (nearest first) and fills up with reverse edges until m_max."""
+    n = fwd.shape[0]
+    valid = np.arange(fwd.shape[1])[None, :] < cnt[:, None]
+    src = np.repeat(np.arange(n, dtype=np.int64), cnt)
+    dst = fwd[valid].astype(np.int64)
+    order = np.argsort(dst, kind="stable")
+    dst_s, src_s = dst[order], src[order]
+    start = np.searchsorted(dst_s, np.arange(n + 1))
+    rank = np.arange(dst_s.size) - start[dst_s]
+    keep = rank < m_max
+    rev = np.full((n, m_max), -1, np.int64)
+    rev[dst_s[keep], rank[keep]] = src_s[keep]
+    f = np.where(valid, fwd.astype(np.int64), -2)
+    for j in range(m_max):  # drop reverse edges that duplicate a forward edge
+        col = rev[:, j]
+        dup = (f == col[:, None]).any(1)
+        rev[dup, j] = -1
+    allc = np.concatenate([np.where(valid, fwd.astype(np.int64), -1), rev], axis=1)
+    ok = allc >= 0
+    order2 = np.argsort(~ok, axis=1, kind="stable")[:, :m_max]
+    out = np.take_along_axis(allc, order2, axis=1)
+    out_cnt = np.minimum(ok.sum(1), m_max)
+    return out, out_cnt
+
+
+def build_layers(ctx, vectors_dev, n, dim, metric="EUCLIDEAN", m=16, m0=32, seed=1, batch=4096, progress=None,
+                 heuristic=True):
     """vectors_dev: torch CUDA float32 tensor (n, dim).  -> (layers, entry_point, levels) with
-    layers = [(row_ptr u64[n+1], col_idx u32[e]), ...] (layer 0 first), element id = row index."""
+    layers = [(row_ptr u64[n+1], col_idx u32[e]), ...] (layer 0 first), element id = row index.
+    heuristic=True: candidates = 2*m_max nearest, pruned by Heuristic::select on the GPU
+    (sdb_hnsw_select_neighbors), then bidirectional linking; False: plain exact m_max-NN lists."""
+    import ctypes as C
     import torch
+    from . import _lib as L
     levels = assign_levels(n, m, seed)
     top = int(levels.max()) if n else 0
     layers = []
+    dev = vectors_dev.device
     for l in range(top + 1):
         members = np.nonzero(levels >= l)[0].astype(np.int64)
         k_nb = m0 if l == 0 else m
@@ -38,36 +71,47 @@ def build_layers(ctx, vectors_dev, n, dim, metric="EUCLIDEAN", m=16, m0=32, seed
         if members.size <= 1:
             layers.append((row_ptr, np.zeros(0, np.uint32)))
             continue
-        midx = torch.from_numpy(members).to(vectors_dev.device)
+        midx = torch.from_numpy(members).to(dev)
         sub = vectors_dev if members.size == n else vectors_dev.index_select(0, midx).contiguous()
         col = VectorColumn(ctx, dim, metric, "F32", capacity=members.size)
         col.append_device(sub.data_ptr(), members.size)
         col.finalize()
-        k = min(k_nb + 1, members.size)  # +1: the element itself comes back at distance 0
+        kc = min((2 * k_nb if heuristic else k_nb) + 1, members.size)  # +1: the element itself comes back too
         nbrs = np.zeros((members.size, k_nb), np.int64)
         counts = np.zeros(members.size, np.int64)
-        o_r = torch.zeros((batch, k), dtype=torch.int64, device=vectors_dev.device)
-        o_d = torch.zeros((batch, k), dtype=torch.float64, device=vectors_dev.device)
-        o_c = torch.zeros((batch,), dtype=torch.int32, device=vectors_dev.device)
+        o_r = torch.zeros((batch, kc), dtype=torch.int64, device=dev)
+        o_d = torch.zeros((batch, kc), dtype=torch.float64, device=dev)
+        o_c = torch.zeros((batch,), dtype=torch.int32, device=dev)
+        s_o = torch.zeros((batch, k_nb), dtype=torch.int32, device=dev)
+        s_c = torch.zeros((batch,), dtype=torch.int32, device=dev)
         for b0 in range(0, members.size, batch):
             b1 = min(members.size, b0 + batch)
             q = sub[b0:b1].to(torch.float64).contiguous()
-            col.knn_device(q.data_ptr(), b1 - b0, k, 0, o_r.data_ptr(), o_d.data_ptr(), o_c.data_ptr())
-            r = o_r[: b1 - b0].cpu().numpy()
-            cnt = o_c[: b1 - b0].cpu().numpy().astype(np.int64)
-            valid = np.arange(k)[None, :] < cnt[:, None]
-            keep = valid & (r != (b0 + np.arange(b1 - b0))[:, None])  # drop self, keep nearest-first order
-            order = np.argsort(~keep, axis=1, kind="stable")[:, :k_nb]
-            nbrs[b0:b1, : order.shape[1]] = np.take_along_axis(r, order, axis=1)
-            counts[b0:b1] = np.minimum(keep.sum(1), k_nb)
+            col.knn_device(q.data_ptr(), b1 - b0, kc, 0, o_r.data_ptr(), o_d.data_ptr(), o_c.data_ptr())
+            if heuristic:
+                L.check(L.lib().sdb_hnsw_select_neighbors(ctx.h, C.c_void_p(sub.data_ptr()), dim, L.METRIC[metric.upper()], b0,
+                                                          b1 - b0, C.c_void_p(o_r.data_ptr()), C.c_void_p(o_c.data_ptr()), kc, k_nb,
+                                                          C.c_void_p(s_o.data_ptr()), C.c_void_p(s_c.data_ptr())))
+                nbrs[b0:b1] = s_o[: b1 - b0].cpu().numpy()
+                counts[b0:b1] = s_c[: b1 - b0].cpu().numpy()
+            else:
+                r = o_r[: b1 - b0].cpu().numpy()
+                cnt = o_c[: b1 - b0].cpu().numpy().astype(np.int64)
+                valid = np.arange(kc)[None, :] < cnt[:, None]
+                keep = valid & (r != (b0 + np.arange(b1 - b0))[:, None])  # drop self, keep nearest-first order
+                order = np.argsort(~keep, axis=1, kind="stable")[:, :k_nb]
+                nbrs[b0:b1, : order.shape[1]] = np.take_along_axis(r, order, axis=1)
+                counts[b0:b1] = np.minimum(keep.sum(1), k_nb)
             if progress:
                 progress(l, b1, members.size)
         col.close()
+        if heuristic:
+            nbrs, counts = _merge_reverse(nbrs, counts, k_nb)
         deg = np.zeros(n, np.int64)
         deg[members] = counts
         row_ptr[1:] = np.cumsum(deg)
         col_idx = np.zeros(int(row_ptr[-1]), np.uint32)
-        flat = members[nbrs]  # local -> global element ids
+        flat = members[np.maximum(nbrs, 0)]  # local -> global element ids
         mask = np.arange(k_nb)[None, :] < counts[:, None]
         col_idx[:] = flat[mask].astype(np.uint32)
         layers.append((row_ptr, col_idx))

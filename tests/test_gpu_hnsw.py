@@ -88,3 +88,35 @@ def test_shared_elements_expand_to_docs_and_edge_cases(ctx):
     empty = HnswIndex(ctx, np.zeros((0, 2), np.float32), [(np.zeros(1, np.uint64), np.zeros(0, np.uint32))], -1)
     ids, dist, cnt = empty.search_graph(np.zeros((2, 2), np.float32), 3, 5)
     assert list(cnt) == [0, 0]
+
+
+def test_gpu_batch_builder_gives_a_searchable_graph(ctx):
+    # SURVEY 8f-2 "next" row: batch construction (exact kNN candidates + Heuristic::select on the GPU + reverse edges);
+    # not the reference's insertion order, so the check is structural + recall, and walk parity on the built graph.
+    import torch
+    from surrealdb_b200.hnsw import HnswIndex
+    from surrealdb_b200.hnsw_build import build_layers
+    n, dim = 6000, 24
+    g = torch.Generator(device="cuda").manual_seed(3)
+    centers = torch.randn((40, dim), generator=g, device="cuda")
+    x = (centers[torch.randint(0, 40, (n,), generator=g, device="cuda")] + 0.3 * torch.randn((n, dim), generator=g, device="cuda")).contiguous()
+    layers, entry, levels = build_layers(ctx, x, n, dim, "EUCLIDEAN", m=8, m0=16, seed=5)
+    xh = x.cpu().numpy()
+    for l, (rp, ci) in enumerate(layers):
+        deg = np.diff(rp.astype(np.int64))
+        assert deg.max() <= (16 if l == 0 else 8)
+        assert (ci < n).all()
+        rows = np.repeat(np.arange(n), deg)
+        assert (rows != ci).all()  # no self loops (check_hnsw_props, layer.rs:571-587)
+        assert (deg[levels < l] == 0).all()
+    idx = HnswIndex(ctx, xh, layers, entry, "EUCLIDEAN")
+    qs = (centers[torch.randint(0, 40, (200,), generator=g, device="cuda")] + 0.3 * torch.randn((200, dim), generator=g, device="cuda")).cpu().numpy()
+    ids, dist, cnt = idx.search_graph(qs, 10, 64)
+    graph = {"vectors": xh, "layers": layers, "entry_point": entry, "metric": "euclidean"}
+    hit = 0
+    for q in range(200):
+        oi, od, _ = O.hnsw_search_csr(graph, qs[q], 10, 64)
+        assert list(ids[q, : cnt[q]]) == list(oi) and dist[q, : cnt[q]].tobytes() == od.tobytes()
+        bi, _ = O.vec_knn_f32(xh, qs[q], "euclidean", 10)
+        hit += len(set(bi.tolist()) & set(ids[q, : cnt[q]].tolist()))
+    assert hit / 2000.0 >= 0.9
