@@ -73,38 +73,48 @@ def build_layers(ctx, vectors_dev, n, dim, metric="EUCLIDEAN", m=16, m0=32, seed
             continue
         midx = torch.from_numpy(members).to(dev)
         sub = vectors_dev if members.size == n else vectors_dev.index_select(0, midx).contiguous()
-        col = VectorColumn(ctx, dim, metric, "F32", capacity=members.size)
-        col.append_device(sub.data_ptr(), members.size)
-        col.finalize()
-        kc = min((2 * k_nb if heuristic else k_nb) + 1, members.size)  # +1: the element itself comes back too
+        kc_full = (2 * k_nb if heuristic else k_nb) + 1  # +1: the element itself comes back too
         nbrs = np.zeros((members.size, k_nb), np.int64)
         counts = np.zeros(members.size, np.int64)
-        o_r = torch.zeros((batch, kc), dtype=torch.int64, device=dev)
-        o_d = torch.zeros((batch, kc), dtype=torch.float64, device=dev)
+        o_r = torch.zeros((batch, kc_full), dtype=torch.int64, device=dev)
+        o_d = torch.zeros((batch, kc_full), dtype=torch.float64, device=dev)
         o_c = torch.zeros((batch,), dtype=torch.int32, device=dev)
         s_o = torch.zeros((batch, k_nb), dtype=torch.int32, device=dev)
         s_c = torch.zeros((batch,), dtype=torch.int32, device=dev)
-        for b0 in range(0, members.size, batch):
-            b1 = min(members.size, b0 + batch)
-            q = sub[b0:b1].to(torch.float64).contiguous()
-            col.knn_device(q.data_ptr(), b1 - b0, kc, 0, o_r.data_ptr(), o_d.data_ptr(), o_c.data_ptr())
-            if heuristic:
-                L.check(L.lib().sdb_hnsw_select_neighbors(ctx.h, C.c_void_p(sub.data_ptr()), dim, L.METRIC[metric.upper()], b0,
-                                                          b1 - b0, C.c_void_p(o_r.data_ptr()), C.c_void_p(o_c.data_ptr()), kc, k_nb,
-                                                          C.c_void_p(s_o.data_ptr()), C.c_void_p(s_c.data_ptr())))
-                nbrs[b0:b1] = s_o[: b1 - b0].cpu().numpy()
-                counts[b0:b1] = s_c[: b1 - b0].cpu().numpy()
-            else:
-                r = o_r[: b1 - b0].cpu().numpy()
-                cnt = o_c[: b1 - b0].cpu().numpy().astype(np.int64)
-                valid = np.arange(kc)[None, :] < cnt[:, None]
-                keep = valid & (r != (b0 + np.arange(b1 - b0))[:, None])  # drop self, keep nearest-first order
-                order = np.argsort(~keep, axis=1, kind="stable")[:, :k_nb]
-                nbrs[b0:b1, : order.shape[1]] = np.take_along_axis(r, order, axis=1)
-                counts[b0:b1] = np.minimum(keep.sum(1), k_nb)
-            if progress:
-                progress(l, b1, members.size)
-        col.close()
+        # "insertion order" emulation: element i (ids are assumed shuffled) draws its candidates from the prefix
+        # [0, 2^ceil(log2 i)) only, like an element inserted when the index held that many points -- early elements
+        # therefore keep long-range links, which is what makes the incremental HNSW navigable across clusters.
+        seg_lo = 0
+        seg_hi = min(members.size, 4096) if heuristic else members.size
+        while seg_lo < members.size:
+            col = VectorColumn(ctx, dim, metric, "F32", capacity=seg_hi)
+            col.append_device(sub.data_ptr(), seg_hi)
+            col.finalize()
+            kc = min(kc_full, seg_hi)
+            for b0 in range(seg_lo, seg_hi, batch):
+                b1 = min(seg_hi, b0 + batch)
+                q = sub[b0:b1].to(torch.float64).contiguous()
+                o_rv = o_r.view(-1)[: batch * kc].view(batch, kc)
+                o_dv = o_d.view(-1)[: batch * kc].view(batch, kc)
+                col.knn_device(q.data_ptr(), b1 - b0, kc, 0, o_rv.data_ptr(), o_dv.data_ptr(), o_c.data_ptr())
+                if heuristic:
+                    L.check(L.lib().sdb_hnsw_select_neighbors(ctx.h, C.c_void_p(sub.data_ptr()), dim, L.METRIC[metric.upper()],
+                                                              b0, b1 - b0, C.c_void_p(o_rv.data_ptr()), C.c_void_p(o_c.data_ptr()),
+                                                              kc, k_nb, C.c_void_p(s_o.data_ptr()), C.c_void_p(s_c.data_ptr())))
+                    nbrs[b0:b1] = s_o[: b1 - b0].cpu().numpy()
+                    counts[b0:b1] = s_c[: b1 - b0].cpu().numpy()
+                else:
+                    r = o_rv[: b1 - b0].cpu().numpy()
+                    cnt = o_c[: b1 - b0].cpu().numpy().astype(np.int64)
+                    valid = np.arange(kc)[None, :] < cnt[:, None]
+                    keep = valid & (r != (b0 + np.arange(b1 - b0))[:, None])  # drop self, keep nearest-first order
+                    order = np.argsort(~keep, axis=1, kind="stable")[:, :k_nb]
+                    nbrs[b0:b1, : order.shape[1]] = np.take_along_axis(r, order, axis=1)
+                    counts[b0:b1] = np.minimum(keep.sum(1), k_nb)
+                if progress:
+                    progress(l, b1, members.size)
+            col.close()
+            seg_lo, seg_hi = seg_hi, min(members.size, 2 * seg_hi)
         if heuristic:
             nbrs, counts = _merge_reverse(nbrs, counts, k_nb)
         deg = np.zeros(n, np.int64)
