@@ -157,10 +157,12 @@ sdb_status sdb_hnsw_search(sdb_hnsw*, const float* queries, uint32_t nq, uint32_
  * (e.g. the rows written by sdb_knn_bruteforce_device; the element itself is skipped), d_cand_cnt: valid entries per
  * row.  For every element: if it has <= m_max candidates all are taken, otherwise candidates are visited nearest-first
  * and e is accepted iff no already accepted r is closer to e than the element is (e_dist > dist(e,r) rejects), until
- * m_max are accepted.  d_out: n x m_max member indices, d_out_cnt: accepted count.  All pointers are device pointers. */
+ * m_max are accepted.  presorted = 0: the candidates are first ordered by their distance to the element
+ * (build_priority_list, layer.rs:389-405 -- the re-selection of an over-full node).  d_out: n x m_max member indices,
+ * d_out_cnt: accepted count.  All pointers are device pointers. */
 sdb_status sdb_hnsw_select_neighbors(sdb_ctx*, const float* d_vectors, uint32_t dim, sdb_metric, uint64_t row0, uint64_t n,
                                      const uint64_t* d_cand, const uint32_t* d_cand_cnt, uint32_t kc, uint32_t m_max,
-                                     uint32_t* d_out, uint32_t* d_out_cnt);
+                                     int presorted, uint32_t* d_out, uint32_t* d_out_cnt);
 
 /* ---- graph expansion: replaces GraphEdgeScan::execute (exec/operators/scan/graph.rs:168-283)
  *      driven by LookupPart (exec/parts/lookup.rs:139-170) and the +collect recursion

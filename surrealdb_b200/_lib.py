@@ -81,7 +81,7 @@ def lib():
     L.sdb_hnsw_load.argtypes = [vp, u32, i32, u64, vp, u32, vp, vp, C.c_int64, C.POINTER(vp)]
     L.sdb_hnsw_destroy.argtypes = [vp]
     L.sdb_hnsw_search.argtypes = [vp, vp, u32, u32, u32, vp, vp, vp, vp]
-    L.sdb_hnsw_select_neighbors.argtypes = [vp, vp, u32, i32, u64, u64, vp, vp, u32, u32, vp, vp]
+    L.sdb_hnsw_select_neighbors.argtypes = [vp, vp, u32, i32, u64, u64, vp, vp, u32, u32, i32, vp, vp]
     L.sdb_graph_load_csr.argtypes = [vp, u64, vp, vp, C.POINTER(vp)]
     L.sdb_graph_destroy.argtypes = [vp]
     L.sdb_graph_expand.argtypes = [vp, u32, vp, u64, u32, C.POINTER(vp), C.POINTER(u64)]

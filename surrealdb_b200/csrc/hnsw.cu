@@ -367,12 +367,14 @@ __device__ __forceinline__ float warp_pair_dist(const float* a_smem, float a_n2,
 template <bool COSINE>
 __global__ void __launch_bounds__(128) hnsw_select_kernel(const float* __restrict__ vec, uint32_t dim, uint64_t row0, uint64_t n,
                                                           const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cand_cnt,
-                                                          uint32_t kc, uint32_t m_max, uint32_t* __restrict__ out,
+                                                          uint32_t kc, uint32_t m_max, int presorted, uint32_t* __restrict__ out,
                                                           uint32_t* __restrict__ out_cnt) {
   extern __shared__ float s_sel[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* s_q = s_sel + (size_t)warp * 2 * dim;
+  float* s_q = s_sel + (size_t)warp * (2 * dim + 2 * kc);
   float* s_e = s_q + dim;
+  float* s_d = s_e + dim;                                   // [kc] distances (unsorted mode)
+  uint32_t* s_ord = reinterpret_cast<uint32_t*>(s_d + kc);  // [kc] visiting order
   const uint64_t i = (uint64_t)blockIdx.x * 4 + warp;  // element index inside this batch
   if (i >= n) return;
   const uint64_t self = row0 + i;
@@ -390,10 +392,28 @@ __global__ void __launch_bounds__(128) hnsw_select_kernel(const float* __restric
   uint32_t nc = cand_cnt[i] < kc ? cand_cnt[i] : kc;
   uint32_t n_real = 0;  // candidates other than the element itself
   for (uint32_t j = 0; j < nc; j++) n_real += cl[j] != self;
+  // visiting order: as given (nearest first) or by computed distance (build_priority_list, layer.rs:389-405)
+  if (presorted) {
+    for (uint32_t j = lane; j < nc; j += 32) s_ord[j] = j;
+  } else {
+    for (uint32_t j = 0; j < nc; j++) {
+      const float d = cl[j] == self ? 3.0e38f : warp_pair_dist<COSINE>(s_q, qn2, vec + cl[j] * dim, dim);
+      if (lane == 0) s_d[j] = d;
+    }
+    __syncwarp();
+    for (uint32_t j = lane; j < nc; j += 32) {
+      const float dj = s_d[j];
+      uint32_t rank = 0;
+      for (uint32_t t = 0; t < nc; t++) rank += (s_d[t] < dj) || (s_d[t] == dj && t < j);
+      s_ord[rank] = j;
+    }
+  }
+  __syncwarp();
   uint32_t* o = out + i * m_max;
   uint32_t acc = 0;
   const bool take_all = n_real <= m_max;
-  for (uint32_t j = 0; j < nc && acc < m_max; j++) {
+  for (uint32_t jj = 0; jj < nc && acc < m_max; jj++) {
+    const uint32_t j = s_ord[jj];
     const uint64_t e = cl[j];
     if (e == self) continue;
     bool ok = true;
@@ -510,10 +530,10 @@ sdb_status sdb_hnsw_select_neighbors(sdb_ctx* ctx, const float* d_vectors, uint3
   if (n == 0) return SDB_OK;
   std::lock_guard<std::mutex> guard(ctx->mu);
   SDB_CUDA(cudaSetDevice(ctx->device));
-  const size_t smem = sizeof(float) * 2 * dim * 4;
+  const size_t smem = sizeof(float) * (2 * (size_t)dim + 2 * kc) * 4;
   auto kern = metric == SDB_COSINE ? hnsw_select_kernel<true> : hnsw_select_kernel<false>;
   SDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)((n + 3) / 4), 128, smem, ctx->stream>>>(d_vectors, dim, row0, n, d_cand, d_cand_cnt, kc, m_max, d_out, d_out_cnt);
+  kern<<<(unsigned)((n + 3) / 4), 128, smem, ctx->stream>>>(d_vectors, dim, row0, n, d_cand, d_cand_cnt, kc, m_max, presorted, d_out, d_out_cnt);
   count_launch(ctx);
   SDB_CUDA(cudaGetLastError());
   SDB_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -24,7 +24,7 @@ def assign_levels(n, m, seed):
     return np.floor(-np.log(u) * ml).astype(np.int64)
 
 
-def _merge_reverse(fwd, cnt, m_max):
+def _merge_reverse(fwd, cnt, m_max, cap=None):
     """bidirectional linking (graph.rs:52-64): every selected edge u->v also adds v->u; a node keeps its own
     selection first (nearest first) and fills up with reverse edges until m_max."""
     n = fwd.shape[0]
@@ -35,6 +35,7 @@ def _merge_reverse(fwd, cnt, m_max):
     dst_s, src_s = dst[order], src[order]
     start = np.searchsorted(dst_s, np.arange(n + 1))
     rank = np.arange(dst_s.size) - start[dst_s]
+    cap = cap or m_max
     keep = rank < m_max
     rev = np.full((n, m_max), -1, np.int64)
     rev[dst_s[keep], rank[keep]] = src_s[keep]
@@ -45,9 +46,9 @@ def _merge_reverse(fwd, cnt, m_max):
         rev[dup, j] = -1
     allc = np.concatenate([np.where(valid, fwd.astype(np.int64), -1), rev], axis=1)
     ok = allc >= 0
-    order2 = np.argsort(~ok, axis=1, kind="stable")[:, :m_max]
+    order2 = np.argsort(~ok, axis=1, kind="stable")[:, :cap]
     out = np.take_along_axis(allc, order2, axis=1)
-    out_cnt = np.minimum(ok.sum(1), m_max)
+    out_cnt = np.minimum(ok.sum(1), cap)
     return out, out_cnt
 
 
@@ -100,7 +101,7 @@ def build_layers(ctx, vectors_dev, n, dim, metric="EUCLIDEAN", m=16, m0=32, seed
                 if heuristic:
                     L.check(L.lib().sdb_hnsw_select_neighbors(ctx.h, C.c_void_p(sub.data_ptr()), dim, L.METRIC[metric.upper()],
                                                               b0, b1 - b0, C.c_void_p(o_rv.data_ptr()), C.c_void_p(o_c.data_ptr()),
-                                                              kc, k_nb, C.c_void_p(s_o.data_ptr()), C.c_void_p(s_c.data_ptr())))
+                                                              kc, k_nb, 1, C.c_void_p(s_o.data_ptr()), C.c_void_p(s_c.data_ptr())))
                     nbrs[b0:b1] = s_o[: b1 - b0].cpu().numpy()
                     counts[b0:b1] = s_c[: b1 - b0].cpu().numpy()
                 else:
@@ -116,7 +117,18 @@ def build_layers(ctx, vectors_dev, n, dim, metric="EUCLIDEAN", m=16, m0=32, seed
             col.close()
             seg_lo, seg_hi = seg_hi, min(members.size, 2 * seg_hi)
         if heuristic:
-            nbrs, counts = _merge_reverse(nbrs, counts, k_nb)
+            # bidirectional edges, then re-select every over-full node among (own selection + reverse edges) ordered by
+            # distance -- layer.rs:362-378
+            union, ucnt = _merge_reverse(nbrs, counts, k_nb, cap=2 * k_nb)
+            u_dev = torch.from_numpy(np.maximum(union, 0).astype(np.int64)).to(dev)
+            c_dev = torch.from_numpy(ucnt.astype(np.int32)).to(dev)
+            r_o = torch.zeros((members.size, k_nb), dtype=torch.int32, device=dev)
+            r_c = torch.zeros((members.size,), dtype=torch.int32, device=dev)
+            L.check(L.lib().sdb_hnsw_select_neighbors(ctx.h, C.c_void_p(sub.data_ptr()), dim, L.METRIC[metric.upper()], 0,
+                                                      members.size, C.c_void_p(u_dev.data_ptr()), C.c_void_p(c_dev.data_ptr()),
+                                                      2 * k_nb, k_nb, 0, C.c_void_p(r_o.data_ptr()), C.c_void_p(r_c.data_ptr())))
+            nbrs = r_o.cpu().numpy().astype(np.int64)
+            counts = r_c.cpu().numpy().astype(np.int64)
         deg = np.zeros(n, np.int64)
         deg[members] = counts
         row_ptr[1:] = np.cumsum(deg)
