@@ -524,7 +524,7 @@ sdb_status sdb_hnsw_load(sdb_ctx* ctx, uint32_t dim, sdb_metric metric, uint64_t
 
 sdb_status sdb_hnsw_select_neighbors(sdb_ctx* ctx, const float* d_vectors, uint32_t dim, sdb_metric metric, uint64_t row0,
                                      uint64_t n, const uint64_t* d_cand, const uint32_t* d_cand_cnt, uint32_t kc,
-                                     uint32_t m_max, uint32_t* d_out, uint32_t* d_out_cnt) {
+                                     uint32_t m_max, int presorted, uint32_t* d_out, uint32_t* d_out_cnt) {
   if (!ctx || !d_vectors || !d_cand || !d_cand_cnt || !d_out || !d_out_cnt || !dim || !kc || !m_max) return SDB_EINVAL;
   if (metric != SDB_COSINE && metric != SDB_EUCLIDEAN) return SDB_EUNSUPPORTED;
   if (n == 0) return SDB_OK;
