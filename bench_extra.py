@@ -78,7 +78,7 @@ def bench_hnsw(a):
     out = {"bench": "hnsw_search", "metric": f"HNSW KNN queries/sec (M={a.m}, M0={2*a.m}, ef={a.ef}, k={a.k})",
            "value": a.queries / (wall * 1e-3), "unit": "queries/s", "device_ms": ms, "call_wall_ms": wall,
            "recall_at_k": recall, "config": {"rows": n, "dim": dim, "queries": a.queries, "data": "4096-centroid gaussian mixture, sigma 0.15",
-                                              "graph": "GPU batch-built exact kNN layers (hnsw_build.py)", "build_s": build_s,
+                                              "graph": "GPU batch-built layers: prefix kNN candidates + Heuristic::select + bidirectional re-selection (hnsw_build.py)", "build_s": build_s,
                                               "layers": len(layers), "visited_per_query": visited / a.queries,
                                               "expanded_per_query": expanded / a.queries},
            "roofline": {"bound": "hbm", "kernel": "hnsw_search_kernel", "achieved": byts / (ms * 1e-3) / 1e9, "peak": peak,
