@@ -188,3 +188,17 @@ def test_full_size_c2_sample_queries(ctx):
         rows1, dist1, _ = col.knn(queries[:9], k)
         assert rows1.tobytes() == rows[:9].tobytes() and dist1.tobytes() == dist[:9].tobytes(), screen
         assert col.stats()["screen_used"] == {"SIMT_F32": 1, "TC_BF16": 2, "TC_INT8": 4}[screen]
+
+
+def test_large_batches_are_chunked_correctly(ctx):
+    # batches above 2048 queries are split over several tcgen05 launches (private sub-list slots per chunk)
+    rng = np.random.default_rng(21)
+    corpus = rng.uniform(-1, 1, (9000, 64)).astype(np.float32)
+    queries = rng.uniform(-1, 1, (4500, 64))
+    for screen, metric in (("TC_BF16", "EUCLIDEAN"), ("TC_INT8", "COSINE"), ("TC_BF16", "COSINE")):
+        col = make_col(ctx, corpus, metric, screen=screen)
+        rows, dist, cnt = col.knn(queries, 65)
+        assert col.stats()["n_fallback"] <= 45
+        for q in list(range(0, 4500, 97)) + [2047, 2048, 4095, 4096, 4499]:
+            r, d = O.knn_topk(corpus, queries[q], metric.lower(), 65)
+            assert list(rows[q]) == list(r) and dist[q].tobytes() == d.tobytes(), (screen, metric, q)
