@@ -56,6 +56,7 @@ def bench_hnsw(a):
         return (centers[c] + 0.15 * torch.randn((cnt, dim), generator=g, device=dev)).contiguous()
     x = sample(n)
     queries = sample(a.queries)
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     layers, entry, levels = build_layers(ctx, x, n, dim, "EUCLIDEAN", m=a.m, m0=2 * a.m, seed=7)
     build_s = time.perf_counter() - t0
@@ -69,6 +70,7 @@ def bench_hnsw(a):
     byts = visited * (4.0 * dim + 4.0) + expanded * deg0 * 4.0
     # recall@k against exact brute force (f64 reference arithmetic) on the same corpus
     col = VectorColumn(ctx, dim, "EUCLIDEAN", "F32", capacity=n)
+    torch.cuda.synchronize()
     col.append_device(x.data_ptr(), n)
     col.finalize()
     nr = min(a.queries, 2000)

@@ -88,6 +88,7 @@ def build_layers(ctx, vectors_dev, n, dim, metric="EUCLIDEAN", m=16, m0=32, seed
         seg_lo = 0
         seg_hi = min(members.size, 4096) if heuristic else members.size
         while seg_lo < members.size:
+            torch.cuda.current_stream().synchronize()
             col = VectorColumn(ctx, dim, metric, "F32", capacity=seg_hi)
             col.append_device(sub.data_ptr(), seg_hi)
             col.finalize()
@@ -95,6 +96,7 @@ def build_layers(ctx, vectors_dev, n, dim, metric="EUCLIDEAN", m=16, m0=32, seed
             for b0 in range(seg_lo, seg_hi, batch):
                 b1 = min(seg_hi, b0 + batch)
                 q = sub[b0:b1].to(torch.float64).contiguous()
+                torch.cuda.current_stream().synchronize()  # torch wrote q on ITS stream; the library runs on its own
                 o_rv = o_r.view(-1)[: batch * kc].view(batch, kc)
                 o_dv = o_d.view(-1)[: batch * kc].view(batch, kc)
                 col.knn_device(q.data_ptr(), b1 - b0, kc, 0, o_rv.data_ptr(), o_dv.data_ptr(), o_c.data_ptr())
@@ -119,11 +121,16 @@ def build_layers(ctx, vectors_dev, n, dim, metric="EUCLIDEAN", m=16, m0=32, seed
         if heuristic:
             # bidirectional edges, then re-select every over-full node among (own selection + reverse edges) ordered by
             # distance -- layer.rs:362-378
+            if progress:
+                progress(l, -1, float(counts.mean()))
             union, ucnt = _merge_reverse(nbrs, counts, k_nb, cap=2 * k_nb)
+            if progress:
+                progress(l, -2, float(ucnt.mean()))
             u_dev = torch.from_numpy(np.maximum(union, 0).astype(np.int64)).to(dev)
             c_dev = torch.from_numpy(ucnt.astype(np.int32)).to(dev)
             r_o = torch.zeros((members.size, k_nb), dtype=torch.int32, device=dev)
             r_c = torch.zeros((members.size,), dtype=torch.int32, device=dev)
+            torch.cuda.current_stream().synchronize()
             L.check(L.lib().sdb_hnsw_select_neighbors(ctx.h, C.c_void_p(sub.data_ptr()), dim, L.METRIC[metric.upper()], 0,
                                                       members.size, C.c_void_p(u_dev.data_ptr()), C.c_void_p(c_dev.data_ptr()),
                                                       2 * k_nb, k_nb, 0, C.c_void_p(r_o.data_ptr()), C.c_void_p(r_c.data_ptr())))

@@ -21,6 +21,7 @@ def test_sharded_search_plus_merge_equals_unsharded():
     corpus[5000:5004] = corpus[100:104]  # cross-shard exact ties must resolve by global row
     queries = gen_f32(22, 0, nq * dim).reshape(nq, dim).astype(np.float64)
     qd = torch.from_numpy(queries).to(dev)
+    torch.cuda.synchronize()  # torch streams and the library stream are not ordered with each other
     off_rows, off_dist, off_cnt, blk = shard_block_layout(nq, k)
     gathered = torch.zeros(world * blk, dtype=torch.uint8, device=dev)
     for r in range(world):
