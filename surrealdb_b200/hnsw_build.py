@@ -53,11 +53,13 @@ def _merge_reverse(fwd, cnt, m_max, cap=None):
 
 
 def build_layers(ctx, vectors_dev, n, dim, metric="EUCLIDEAN", m=16, m0=32, seed=1, batch=4096, progress=None,
-                 heuristic=True):
+                 heuristic=True, prefix=False):
     """vectors_dev: torch CUDA float32 tensor (n, dim).  -> (layers, entry_point, levels) with
     layers = [(row_ptr u64[n+1], col_idx u32[e]), ...] (layer 0 first), element id = row index.
     heuristic=True: candidates = 2*m_max nearest, pruned by Heuristic::select on the GPU
-    (sdb_hnsw_select_neighbors), then bidirectional linking; False: plain exact m_max-NN lists."""
+    (sdb_hnsw_select_neighbors), then bidirectional linking and re-selection of over-full nodes; False: plain exact
+    m_max-NN lists.  prefix=True additionally restricts element i's candidates to the id prefix [0, 2^ceil(log2 i)),
+    emulating insertion order (better cross-cluster links on strongly clustered data, worse on diffuse data)."""
     import ctypes as C
     import torch
     from . import _lib as L
@@ -86,7 +88,7 @@ def build_layers(ctx, vectors_dev, n, dim, metric="EUCLIDEAN", m=16, m0=32, seed
         # [0, 2^ceil(log2 i)) only, like an element inserted when the index held that many points -- early elements
         # therefore keep long-range links, which is what makes the incremental HNSW navigable across clusters.
         seg_lo = 0
-        seg_hi = min(members.size, 4096) if heuristic else members.size
+        seg_hi = min(members.size, 4096) if (heuristic and prefix) else members.size
         while seg_lo < members.size:
             torch.cuda.current_stream().synchronize()
             col = VectorColumn(ctx, dim, metric, "F32", capacity=seg_hi)
