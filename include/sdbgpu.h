@@ -175,6 +175,10 @@ void sdb_graph_destroy(sdb_graph*);
  * memory (free with sdb_free). */
 sdb_status sdb_graph_expand(sdb_graph* const* hops, uint32_t n_hops, const uint32_t* frontier, uint64_t n_frontier,
                             uint32_t per_source_limit, uint32_t** out_ids, uint64_t* out_n);
+/* device-resident variant: d_frontier and *d_out_ids are device pointers; *d_out_ids is library-owned (sdb_device_free) */
+sdb_status sdb_graph_expand_device(sdb_graph* const* hops, uint32_t n_hops, const uint32_t* d_frontier, uint64_t n_frontier,
+                                   uint32_t per_source_limit, uint32_t** d_out_ids, uint64_t* out_n);
+void sdb_device_free(sdb_ctx*, void* d_ptr);
 /* +collect BFS: first-seen dedup, emits from min_depth, start only marked seen when inclusive. */
 sdb_status sdb_graph_collect(sdb_graph*, const uint32_t* start, uint64_t n_start, uint32_t min_depth,
                              uint32_t max_depth, int inclusive, uint32_t** out_ids, uint64_t* out_n);

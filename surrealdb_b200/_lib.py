@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "sdb_corpus_append_device", "sdb_corpus_append_synthetic", "sdb_corpus_set_skip", "sdb_corpus_finalize",
     "sdb_corpus_rows", "sdb_corpus_set_screen", "sdb_knn_bruteforce", "sdb_knn_bruteforce_device",
     "sdb_knn_last_stats", "sdb_topk_merge_device", "sdb_hnsw_load", "sdb_hnsw_destroy", "sdb_hnsw_search", "sdb_hnsw_select_neighbors",
-    "sdb_graph_load_csr", "sdb_graph_destroy", "sdb_graph_expand", "sdb_graph_collect", "sdb_free",
+    "sdb_graph_load_csr", "sdb_graph_destroy", "sdb_graph_expand", "sdb_graph_expand_device", "sdb_device_free", "sdb_graph_collect", "sdb_free",
 ]
 
 
@@ -85,6 +85,8 @@ def lib():
     L.sdb_graph_load_csr.argtypes = [vp, u64, vp, vp, C.POINTER(vp)]
     L.sdb_graph_destroy.argtypes = [vp]
     L.sdb_graph_expand.argtypes = [vp, u32, vp, u64, u32, C.POINTER(vp), C.POINTER(u64)]
+    L.sdb_graph_expand_device.argtypes = [vp, u32, vp, u64, u32, C.POINTER(vp), C.POINTER(u64)]
+    L.sdb_device_free.argtypes = [vp, vp]
     L.sdb_graph_collect.argtypes = [vp, vp, u64, u32, u32, i32, C.POINTER(vp), C.POINTER(u64)]
     L.sdb_free.argtypes = [vp]
     _lib = L

@@ -293,6 +293,61 @@ void sdb_graph_destroy(sdb_graph* g) {
   delete g;
 }
 
+// device-resident core: frontier and result stay in HBM (the result is library-owned: sdb_device_free)
+static sdb_status graph_expand_dev(sdb_graph* const* hops, uint32_t n_hops, const uint32_t* d_frontier, uint64_t n_frontier,
+                                   uint32_t per_source_limit, uint32_t** d_out, uint64_t* out_n, cudaStream_t st) {
+  uint32_t* d_f = nullptr;
+  uint64_t n_f = n_frontier;
+  bool owned = false;  // the caller's frontier is never freed
+  const uint32_t* cur = d_frontier;
+  for (uint32_t h = 0; h < n_hops && n_f; h++) {
+    uint32_t* d_next = nullptr;
+    uint64_t n_next = 0;
+    sdb_status s = hop_device(hops[h], cur, n_f, per_source_limit, &d_next, &n_next, st);
+    if (owned) cudaFreeAsync(d_f, st);
+    if (s != SDB_OK) {
+      if (d_next) cudaFreeAsync(d_next, st);
+      return s;
+    }
+    d_f = d_next;
+    cur = d_next;
+    owned = true;
+    n_f = n_next;
+  }
+  if (!owned && n_f) {  // zero hops: hand back a copy
+    SDB_CUDA(cudaMallocAsync(&d_f, sizeof(uint32_t) * n_f, st));
+    SDB_CUDA(cudaMemcpyAsync(d_f, d_frontier, sizeof(uint32_t) * n_f, cudaMemcpyDeviceToDevice, st));
+  }
+  if (n_f == 0 && owned && d_f) {
+    cudaFreeAsync(d_f, st);
+    d_f = nullptr;
+  }
+  *d_out = n_f ? d_f : nullptr;
+  *out_n = n_f;
+  return SDB_OK;
+}
+
+sdb_status sdb_graph_expand_device(sdb_graph* const* hops, uint32_t n_hops, const uint32_t* d_frontier, uint64_t n_frontier,
+                                   uint32_t per_source_limit, uint32_t** d_out_ids, uint64_t* out_n) {
+  if (!hops || !n_hops || !d_out_ids || !out_n || (n_frontier && !d_frontier)) return SDB_EINVAL;
+  *d_out_ids = nullptr;
+  *out_n = 0;
+  for (uint32_t h = 0; h < n_hops; h++)
+    if (!hops[h]) return SDB_EINVAL;
+  Ctx* ctx = hops[0]->ctx;
+  std::lock_guard<std::mutex> guard(ctx->mu);
+  SDB_CUDA(cudaSetDevice(ctx->device));
+  SDB_TRY(graph_expand_dev(hops, n_hops, d_frontier, n_frontier, per_source_limit, d_out_ids, out_n, ctx->stream));
+  SDB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SDB_OK;
+}
+
+void sdb_device_free(sdb_ctx* ctx, void* d_ptr) {
+  if (!ctx || !d_ptr) return;
+  cudaSetDevice(ctx->device);
+  cudaFreeAsync(d_ptr, ctx->stream);
+}
+
 sdb_status sdb_graph_expand(sdb_graph* const* hops, uint32_t n_hops, const uint32_t* frontier, uint64_t n_frontier,
                             uint32_t per_source_limit, uint32_t** out_ids, uint64_t* out_n) {
   if (!hops || !n_hops || !out_ids || !out_n || (n_frontier && !frontier)) return SDB_EINVAL;
@@ -304,24 +359,16 @@ sdb_status sdb_graph_expand(sdb_graph* const* hops, uint32_t n_hops, const uint3
   std::lock_guard<std::mutex> guard(ctx->mu);
   SDB_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
+  uint32_t* d_in = nullptr;
+  if (n_frontier) {
+    SDB_CUDA(cudaMallocAsync(&d_in, sizeof(uint32_t) * n_frontier, st));
+    SDB_CUDA(cudaMemcpyAsync(d_in, frontier, sizeof(uint32_t) * n_frontier, cudaMemcpyHostToDevice, st));
+  }
   uint32_t* d_f = nullptr;
-  uint64_t n_f = n_frontier;
-  if (n_f) {
-    SDB_CUDA(cudaMallocAsync(&d_f, sizeof(uint32_t) * n_f, st));
-    SDB_CUDA(cudaMemcpyAsync(d_f, frontier, sizeof(uint32_t) * n_f, cudaMemcpyHostToDevice, st));
-  }
-  for (uint32_t h = 0; h < n_hops && n_f; h++) {
-    uint32_t* d_next = nullptr;
-    uint64_t n_next = 0;
-    sdb_status s = hop_device(hops[h], d_f, n_f, per_source_limit, &d_next, &n_next, st);
-    cudaFreeAsync(d_f, st);
-    if (s != SDB_OK) {
-      if (d_next) cudaFreeAsync(d_next, st);
-      return s;
-    }
-    d_f = d_next;
-    n_f = n_next;
-  }
+  uint64_t n_f = 0;
+  sdb_status s = graph_expand_dev(hops, n_hops, d_in, n_frontier, per_source_limit, &d_f, &n_f, st);
+  if (d_in) cudaFreeAsync(d_in, st);
+  if (s != SDB_OK) return s;
   if (n_f) {
     uint32_t* h_out = (uint32_t*)malloc(sizeof(uint32_t) * n_f);
     if (!h_out) {

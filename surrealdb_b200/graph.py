@@ -56,6 +56,21 @@ def expand(hops, frontier, per_source_limit=0):
     return _take(out, n)
 
 
+def expand_device(ctx, hops, d_frontier, n_frontier, per_source_limit=0):
+    """sdb_graph_expand_device: frontier and result stay in HBM. -> (device pointer (int), count); free with
+    device_free(ctx, ptr)."""
+    arr = (C.c_void_p * len(hops))(*[g.h for g in hops])
+    out, n = C.c_void_p(), C.c_uint64()
+    L.check(L.lib().sdb_graph_expand_device(arr, len(hops), C.c_void_p(d_frontier), int(n_frontier), int(per_source_limit),
+                                            C.byref(out), C.byref(n)))
+    return (out.value or 0), n.value
+
+
+def device_free(ctx, ptr):
+    if ptr:
+        L.lib().sdb_device_free(ctx.h, C.c_void_p(ptr))
+
+
 def collect(graph, start, min_depth=1, max_depth=0, inclusive=False):
     st = np.ascontiguousarray(start, np.uint32)
     out, n = C.c_void_p(), C.c_uint64()
