@@ -236,6 +236,7 @@ void sdb_ctx_destroy(sdb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
   delete c;
 }
 uint64_t sdb_ctx_kernel_launches(const sdb_ctx* c) { return c ? c->launches : 0; }

@@ -375,9 +375,19 @@ sdb_status sdb_graph_expand(sdb_graph* const* hops, uint32_t n_hops, const uint3
       cudaFreeAsync(d_f, st);
       return SDB_ENOMEM;
     }
-    SDB_CUDA(cudaMemcpyAsync(h_out, d_f, sizeof(uint32_t) * n_f, cudaMemcpyDeviceToHost, st));
+    // device -> pinned staging (full PCIe rate) -> caller-owned pageable buffer
+    const size_t bytes = sizeof(uint32_t) * n_f;
+    if (ctx->h_stage_bytes < bytes) {
+      if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+      ctx->h_stage = nullptr;
+      ctx->h_stage_bytes = 0;
+      if (cudaHostAlloc(&ctx->h_stage, bytes, cudaHostAllocDefault) == cudaSuccess) ctx->h_stage_bytes = bytes;
+    }
+    void* dst = ctx->h_stage_bytes >= bytes ? ctx->h_stage : (void*)h_out;
+    SDB_CUDA(cudaMemcpyAsync(dst, d_f, bytes, cudaMemcpyDeviceToHost, st));
     SDB_CUDA(cudaFreeAsync(d_f, st));
     SDB_CUDA(cudaStreamSynchronize(st));
+    if (dst != (void*)h_out) memcpy(h_out, dst, bytes);
     *out_ids = h_out;
     *out_n = n_f;
   } else {

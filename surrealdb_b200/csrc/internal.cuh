@@ -81,6 +81,8 @@ struct Ctx {
   uint64_t launches = 0;
   std::mutex mu;
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled (driver entry point), resolved lazily
+  void* h_stage = nullptr;       // pinned staging buffer for large device->host results (grow-only)
+  size_t h_stage_bytes = 0;
 };
 
 struct Cand {  // one screened candidate
