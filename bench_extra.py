@@ -129,15 +129,22 @@ def bench_graph(a):
     deg = np.diff(rp.astype(np.int64))
     rng = np.random.default_rng(11)
     sources = rng.choice(np.nonzero(deg > 0)[0], a.sources, replace=False).astype(np.uint32)
-    expand([graph] * a.hops, sources[:8], a.limit)  # warm-up
-    out_ids, ms, wall = dev_time_ms(ctx, lambda: expand([graph] * a.hops, sources, a.limit))
+    expand([graph] * a.hops, sources, a.limit)  # warm-up at full size (memory pools, pinned staging)
+    best = None
+    for _ in range(3):
+        out_ids, ms, wall = dev_time_ms(ctx, lambda: expand([graph] * a.hops, sources, a.limit))
+        best = (ms, wall) if best is None or wall < best[1] else best
+    ms, wall = best
     # device-resident variant (frontier and result stay in HBM): isolates the degree/scan/expand kernels
     d_src = torch.from_numpy(sources.astype(np.int32)).to(dev)
     torch.cuda.synchronize()
     p0, _ = expand_device(ctx, [graph] * a.hops, d_src.data_ptr(), sources.size, a.limit)
     device_free(ctx, p0)
-    (pd, nd), ms_dev, wall_dev = dev_time_ms(ctx, lambda: expand_device(ctx, [graph] * a.hops, d_src.data_ptr(), sources.size, a.limit))
-    device_free(ctx, pd)
+    ms_dev = None
+    for _ in range(3):
+        (pd, nd), m1, _w = dev_time_ms(ctx, lambda: expand_device(ctx, [graph] * a.hops, d_src.data_ptr(), sources.size, a.limit))
+        device_free(ctx, pd)
+        ms_dev = m1 if ms_dev is None or m1 < ms_dev else ms_dev
     # per-hop sizes for the algorithmic byte count
     sizes = [int(sources.size)]
     fr = sources
