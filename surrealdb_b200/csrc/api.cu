@@ -229,6 +229,13 @@ sdb_status sdb_ctx_create(int device, sdb_ctx** out) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   SDB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  {  // keep stream-ordered allocations cached in the pool instead of returning them to the OS at every sync
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
   *out = c;
   return SDB_OK;
 }
