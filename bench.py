@@ -321,6 +321,14 @@ def main():
                     "peak_source": pk["source"] + (" (2 x sustained cuBLAS bf16: the int8 tensor rate is twice the bf16 rate on B200; "
                                                    "MEASURED_PEAKS.json has no int8 figure)" if i8 else " (sustained cuBLAS bf16)"),
                     "traffic": None, "algorithmic_flops_per_launch": flops}
+            try:  # DRAM traffic of the dominant launch, from the committed ncu capture (not re-measured here)
+                tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["screen_tc_int8" if i8 else "screen_tc_bf16"]
+                if rows == 10_000_000 and world == 1:
+                    roof["traffic"] = tr["bytes"]
+                    roof["traffic_note"] = ("dram read+write bytes of the largest of the 5 pass launches (7/8 of the tiles), ncu --set full, "
+                                            + tr["source"] + f"; algorithmic bytes of that launch {tr['algorithmic_bytes_same_launch']:.4g}")
+            except Exception:
+                pass
         else:
             passes_over_corpus = (batch + 7) // 8
             byts = passes_over_corpus * (n_shard * dim * 4.0 + n_shard * 4.0) + batch * dim * 4.0
@@ -331,7 +339,8 @@ def main():
                     "algorithmic_bytes_per_step": byts}
         out = {"metric": "KNN queries/sec @recall@10=1.0 (exact brute force)", "value": qps, "unit": "queries/s",
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_value / args.steps,
-               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": {4: "s8 screen + f64 exact", 2: "bf16 screen + f64 exact", 1: "f32 screen + f64 exact"}.get(stats["screen_used"], "f64"),
                "data": "synthetic",
                "config": {"workload": args.workload, "rows": rows, "dim": dim, "batch": batch, "k": k,
                           "metric": "cosine", "corpus_dtype": "f32 master + bf16 and int8 screen copies",
