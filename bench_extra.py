@@ -58,18 +58,18 @@ def bench_hnsw(a):
     queries = sample(a.queries)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    layers, entry, levels = build_layers(ctx, x, n, dim, "EUCLIDEAN", m=a.m, m0=2 * a.m, seed=7)
+    layers, entry, levels = build_layers(ctx, x, n, dim, a.metric.upper(), m=a.m, m0=2 * a.m, seed=7)
     build_s = time.perf_counter() - t0
     xh = x.cpu().numpy()
     qh = queries.cpu().numpy()
-    idx = HnswIndex(ctx, xh, layers, entry, "EUCLIDEAN")
+    idx = HnswIndex(ctx, xh, layers, entry, a.metric.upper())
     idx.search_graph(qh[:256], a.k, a.ef)  # warm-up
     (ids, dist, cnt, ctr), ms, wall = dev_time_ms(ctx, lambda: idx.search_graph(qh, a.k, a.ef, counters=True))
     deg0 = float(np.diff(layers[0][0].astype(np.int64)).mean())
     visited, expanded = int(ctr[:, 0].sum()), int(ctr[:, 1].sum())
     byts = visited * (4.0 * dim + 4.0) + expanded * deg0 * 4.0
     # recall@k against exact brute force (f64 reference arithmetic) on the same corpus
-    col = VectorColumn(ctx, dim, "EUCLIDEAN", "F32", capacity=n)
+    col = VectorColumn(ctx, dim, a.metric.upper(), "F32", capacity=n)
     torch.cuda.synchronize()
     col.append_device(x.data_ptr(), n)
     col.finalize()
@@ -79,7 +79,7 @@ def bench_hnsw(a):
     peak, src = peaks()
     out = {"bench": "hnsw_search", "metric": f"HNSW KNN queries/sec (M={a.m}, M0={2*a.m}, ef={a.ef}, k={a.k})",
            "value": a.queries / (wall * 1e-3), "unit": "queries/s", "device_ms": ms, "call_wall_ms": wall,
-           "recall_at_k": recall, "config": {"rows": n, "dim": dim, "queries": a.queries, "data": "4096-centroid gaussian mixture, sigma 0.15",
+           "recall_at_k": recall, "config": {"rows": n, "dim": dim, "queries": a.queries, "metric": a.metric.lower(), "data": "4096-centroid gaussian mixture, sigma 0.15",
                                               "graph": "GPU batch-built layers: prefix kNN candidates + Heuristic::select + bidirectional re-selection (hnsw_build.py)", "build_s": build_s,
                                               "layers": len(layers), "visited_per_query": visited / a.queries,
                                               "expanded_per_query": expanded / a.queries},
@@ -88,7 +88,7 @@ def bench_hnsw(a):
                         "algorithmic_bytes": byts, "traffic": None}}
     if not a.no_cpu:
         from oracle import pyoracle as O
-        graph = {"vectors": xh, "layers": layers, "entry_point": entry, "metric": "euclidean"}
+        graph = {"vectors": xh, "layers": layers, "entry_point": entry, "metric": a.metric.lower()}
         threads = os.cpu_count() or 1
         nqc = min(a.queries, 8 * threads)
         t0 = time.perf_counter()
@@ -188,6 +188,7 @@ if __name__ == "__main__":
     ap.add_argument("--ef", type=int, default=64)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--m", type=int, default=16)
+    ap.add_argument("--metric", default="euclidean", choices=["euclidean", "cosine"])
     ap.add_argument("--log2-nodes", type=int, default=24)
     ap.add_argument("--edges", type=int, default=160_000_000)
     ap.add_argument("--sources", type=int, default=1024)
