@@ -58,11 +58,19 @@ def bench_hnsw(a):
     queries = sample(a.queries)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    layers, entry, levels = build_layers(ctx, x, n, dim, a.metric.upper(), m=a.m, m0=2 * a.m, seed=7)
+    tl = [time.perf_counter()]
+    def prog(l, a1, b1):
+        if a1 < 0 or a1 == b1:
+            now = time.perf_counter()
+            print(f"[build] layer {l} stage {a1} value {b1} +{now - tl[0]:.1f}s", file=sys.stderr, flush=True)
+            tl[0] = now
+    layers, entry, levels = build_layers(ctx, x, n, dim, a.metric.upper(), m=a.m, m0=2 * a.m, seed=7, progress=prog)
+    print(f"[build] done {time.perf_counter() - t0:.1f}s", file=sys.stderr, flush=True)
     build_s = time.perf_counter() - t0
     xh = x.cpu().numpy()
     qh = queries.cpu().numpy()
     idx = HnswIndex(ctx, xh, layers, entry, a.metric.upper())
+    print(f"[load] index on device {time.perf_counter() - t0:.1f}s", file=sys.stderr, flush=True)
     idx.search_graph(qh[:256], a.k, a.ef)  # warm-up
     (ids, dist, cnt, ctr), ms, wall = dev_time_ms(ctx, lambda: idx.search_graph(qh, a.k, a.ef, counters=True))
     deg0 = float(np.diff(layers[0][0].astype(np.int64)).mean())
