@@ -53,7 +53,9 @@ def bench_hnsw(a):
     centers = torch.nn.functional.normalize(torch.randn((4096, dim), generator=g, device=dev), dim=1)
     def sample(cnt):
         c = torch.randint(0, 4096, (cnt,), generator=g, device=dev)
-        return (centers[c] + 0.15 * torch.randn((cnt, dim), generator=g, device=dev)).contiguous()
+        # sigma = TOTAL noise norm relative to the unit-norm centroid (per-coordinate sigma / sqrt(dim)); a per-coordinate
+        # 0.15 would bury the centroids under isotropic noise in high dimension and make every ANN method degenerate
+        return (centers[c] + (a.sigma / dim ** 0.5) * torch.randn((cnt, dim), generator=g, device=dev)).contiguous()
     x = sample(n)
     queries = sample(a.queries)
     torch.cuda.synchronize()
@@ -87,7 +89,7 @@ def bench_hnsw(a):
     peak, src = peaks()
     out = {"bench": "hnsw_search", "metric": f"HNSW KNN queries/sec (M={a.m}, M0={2*a.m}, ef={a.ef}, k={a.k})",
            "value": a.queries / (wall * 1e-3), "unit": "queries/s", "device_ms": ms, "call_wall_ms": wall,
-           "recall_at_k": recall, "config": {"rows": n, "dim": dim, "queries": a.queries, "metric": a.metric.lower(), "data": "4096-centroid gaussian mixture, sigma 0.15",
+           "recall_at_k": recall, "config": {"rows": n, "dim": dim, "queries": a.queries, "metric": a.metric.lower(), "data": f"4096 unit-norm centroids + gaussian noise of total norm {a.sigma}",
                                               "graph": "GPU batch-built layers: prefix kNN candidates + Heuristic::select + bidirectional re-selection (hnsw_build.py)", "build_s": build_s,
                                               "layers": len(layers), "visited_per_query": visited / a.queries,
                                               "expanded_per_query": expanded / a.queries},
@@ -197,6 +199,7 @@ if __name__ == "__main__":
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--m", type=int, default=16)
     ap.add_argument("--metric", default="euclidean", choices=["euclidean", "cosine"])
+    ap.add_argument("--sigma", type=float, default=0.15)
     ap.add_argument("--log2-nodes", type=int, default=24)
     ap.add_argument("--edges", type=int, default=160_000_000)
     ap.add_argument("--sources", type=int, default=1024)
