@@ -117,6 +117,11 @@ sdb_status sdb_corpus_set_skip(sdb_corpus*, const uint8_t* skip, uint64_t n);
 sdb_status sdb_corpus_finalize(sdb_corpus*);
 uint64_t sdb_corpus_rows(const sdb_corpus*);
 sdb_status sdb_corpus_set_screen(sdb_corpus*, sdb_screen);
+/* exact = 1 (default): results are proven identical to the reference (queries whose proof fails are re-run by the exact
+ * kernel).  exact = 0: opt-in approximate mode -- the exactly re-ranked best candidates of the screen are returned
+ * without the proof / fallback (used by the index builder, where near-duplicate clusters would otherwise send every
+ * query to the exact kernel). */
+sdb_status sdb_corpus_set_exact(sdb_corpus*, int exact);
 /* queries: nq x dim f64 (the reference's query is Vec<Number>; Number::Float values).
  * out_rows / out_dist: nq x k, nearest first, ties by scan order; out_count[q] <= k.
  * cancel_flag (nullable) is polled between kernel phases.  */

@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "sdb_ctx_create", "sdb_ctx_destroy", "sdb_last_error", "sdb_version", "sdb_pinned_alloc", "sdb_pinned_free",
     "sdb_ctx_kernel_launches", "sdb_ctx_stream", "sdb_corpus_create", "sdb_corpus_destroy", "sdb_corpus_append",
     "sdb_corpus_append_device", "sdb_corpus_append_synthetic", "sdb_corpus_set_skip", "sdb_corpus_finalize",
-    "sdb_corpus_rows", "sdb_corpus_set_screen", "sdb_knn_bruteforce", "sdb_knn_bruteforce_device",
+    "sdb_corpus_rows", "sdb_corpus_set_screen", "sdb_corpus_set_exact", "sdb_knn_bruteforce", "sdb_knn_bruteforce_device",
     "sdb_knn_last_stats", "sdb_topk_merge_device", "sdb_hnsw_load", "sdb_hnsw_destroy", "sdb_hnsw_search", "sdb_hnsw_select_neighbors",
     "sdb_graph_load_csr", "sdb_graph_destroy", "sdb_graph_expand", "sdb_graph_expand_device", "sdb_device_free", "sdb_graph_collect", "sdb_free",
 ]
@@ -74,6 +74,7 @@ def lib():
     L.sdb_corpus_rows.restype = u64
     L.sdb_corpus_rows.argtypes = [vp]
     L.sdb_corpus_set_screen.argtypes = [vp, i32]
+    L.sdb_corpus_set_exact.argtypes = [vp, i32]
     L.sdb_knn_bruteforce.argtypes = [vp, vp, u32, u32, vp, vp, vp, vp]
     L.sdb_knn_bruteforce_device.argtypes = [vp, vp, u32, u32, u64, vp, vp, vp]
     L.sdb_knn_last_stats.argtypes = [vp, C.POINTER(KnnStats)]

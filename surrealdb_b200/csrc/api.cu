@@ -96,7 +96,7 @@ static sdb_status knn_device_locked(Corpus* c, const double* d_queries, uint32_t
     SDB_CUDA(cudaMemcpyAsync(h_flags.data(), c->d_flags, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, st));
     stt.n_passes += (uint32_t)passes.size();
     stt.n_reranked += (uint64_t)nq * (kp + c->n_special);
-    if (scr != SDB_SCREEN_TC_INT8 || getenv("SDB_TC_DBG")) break;
+    if (scr != SDB_SCREEN_TC_INT8 || !c->exact) break;
     // precision ladder: if the int8 proof failed for more than a handful of queries, re-screen the batch in bf16
     SDB_CUDA(cudaStreamSynchronize(st));
     uint32_t n_fail = 0;
@@ -110,7 +110,7 @@ static sdb_status knn_device_locked(Corpus* c, const double* d_queries, uint32_t
   SDB_CUDA(cudaStreamSynchronize(st));
   // ---- exact path for everything the screens could not prove ----
   for (uint32_t q = 0; q < nq; q++) {
-    if ((h_flags[q] & 2u) || (h_qflags[q] & 1u)) {
+    if (((h_flags[q] & 2u) && c->exact) || (h_qflags[q] & 1u)) {
       if (cancel && *cancel) {
         for (auto& e : ev) cudaEventDestroy(e);
         set_error("query cancelled");
@@ -369,6 +369,11 @@ sdb_status sdb_corpus_finalize(sdb_corpus* c) {
 sdb_status sdb_corpus_set_screen(sdb_corpus* c, sdb_screen s) {
   if (!c || (int)s < 0 || (int)s > 4) return SDB_EINVAL;
   c->screen = s;
+  return SDB_OK;
+}
+sdb_status sdb_corpus_set_exact(sdb_corpus* c, int exact) {
+  if (!c) return SDB_EINVAL;
+  c->exact = exact != 0;
   return SDB_OK;
 }
 sdb_status sdb_knn_last_stats(const sdb_corpus* c, sdb_knn_stats* out) {

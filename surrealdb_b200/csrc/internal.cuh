@@ -96,6 +96,7 @@ struct Corpus {
   sdb_dtype dtype = SDB_F32;
   sdb_metric metric = SDB_COSINE;
   sdb_screen screen = SDB_SCREEN_AUTO;
+  bool exact = true;  // false: skip the proof / exact fallback (approximate mode)
   uint64_t cap = 0, n = 0;
   bool finalized = false;
   void* d_rows = nullptr;           // master copy, cap x dim (f32 or f64)

@@ -75,6 +75,10 @@ class VectorColumn:
     def set_screen(self, name):
         L.check(L.lib().sdb_corpus_set_screen(self.h, L.SCREEN[name.upper()]))
 
+    def set_exact(self, exact):
+        """False = opt-in approximate mode (no proof, no exact fallback)"""
+        L.check(L.lib().sdb_corpus_set_exact(self.h, int(bool(exact))))
+
     def knn(self, queries, k, cancel_flag=None):
         """queries (nq, dim) float64 -> (rows u64 (nq,k), dist f64 (nq,k), count u32 (nq,))"""
         q = np.ascontiguousarray(queries, np.float64)

@@ -94,6 +94,7 @@ def build_layers(ctx, vectors_dev, n, dim, metric="EUCLIDEAN", m=16, m0=32, seed
             col = VectorColumn(ctx, dim, metric, "F32", capacity=seg_hi)
             col.append_device(sub.data_ptr(), seg_hi)
             col.finalize()
+            col.set_exact(False)  # candidate generation does not need the exactness proof
             kc = min(kc_full, seg_hi)
             for b0 in range(seg_lo, seg_hi, batch):
                 b1 = min(seg_hi, b0 + batch)

@@ -202,3 +202,21 @@ def test_large_batches_are_chunked_correctly(ctx):
         for q in list(range(0, 4500, 97)) + [2047, 2048, 4095, 4096, 4499]:
             r, d = O.knn_topk(corpus, queries[q], metric.lower(), 65)
             assert list(rows[q]) == list(r) and dist[q].tobytes() == d.tobytes(), (screen, metric, q)
+
+
+def test_approximate_mode_skips_the_fallback_but_stays_accurate(ctx):
+    rng = np.random.default_rng(8)
+    center = rng.uniform(-1, 1, 64).astype(np.float32)
+    corpus = (center[None, :] + rng.normal(0, 1e-6, (30000, 64))).astype(np.float32)  # proof cannot succeed here
+    queries = (center[None, :] + rng.normal(0, 1e-3, (12, 64))).astype(np.float64)
+    col = make_col(ctx, corpus, "COSINE", screen="TC_BF16")
+    col.set_exact(False)
+    rows, dist, cnt = col.knn(queries, 10)
+    assert col.stats()["n_fallback"] == 0 and (cnt == 10).all()
+    assert (np.diff(dist, axis=1) >= 0).all()
+    col.set_exact(True)
+    rows2, dist2, _ = col.knn(queries, 10)
+    assert col.stats()["n_fallback"] > 0
+    for q in range(12):
+        r, d = O.knn_topk(corpus, queries[q], "cosine", 10)
+        assert list(rows2[q]) == list(r)
