@@ -66,7 +66,7 @@ def bench_hnsw(a):
             now = time.perf_counter()
             print(f"[build] layer {l} stage {a1} value {b1} +{now - tl[0]:.1f}s", file=sys.stderr, flush=True)
             tl[0] = now
-    layers, entry, levels = build_layers(ctx, x, n, dim, a.metric.upper(), m=a.m, m0=2 * a.m, seed=7, progress=prog)
+    layers, entry, levels = build_layers(ctx, x, n, dim, a.metric.upper(), m=a.m, m0=2 * a.m, seed=7, progress=prog, prefix=a.prefix)
     print(f"[build] done {time.perf_counter() - t0:.1f}s", file=sys.stderr, flush=True)
     build_s = time.perf_counter() - t0
     xh = x.cpu().numpy()
@@ -90,7 +90,7 @@ def bench_hnsw(a):
     out = {"bench": "hnsw_search", "metric": f"HNSW KNN queries/sec (M={a.m}, M0={2*a.m}, ef={a.ef}, k={a.k})",
            "value": a.queries / (wall * 1e-3), "unit": "queries/s", "device_ms": ms, "call_wall_ms": wall,
            "recall_at_k": recall, "config": {"rows": n, "dim": dim, "queries": a.queries, "metric": a.metric.lower(), "data": f"4096 unit-norm centroids + gaussian noise of total norm {a.sigma}",
-                                              "graph": "GPU batch-built layers: prefix kNN candidates + Heuristic::select + bidirectional re-selection (hnsw_build.py)", "build_s": build_s,
+                                              "graph": "GPU batch-built layers (hnsw_build.py): kNN candidates" + (" from id prefixes" if a.prefix else "") + " + Heuristic::select + bidirectional re-selection", "build_s": build_s,
                                               "layers": len(layers), "visited_per_query": visited / a.queries,
                                               "expanded_per_query": expanded / a.queries},
            "roofline": {"bound": "hbm", "kernel": "hnsw_search_kernel", "achieved": byts / (ms * 1e-3) / 1e9, "peak": peak,
@@ -200,6 +200,7 @@ if __name__ == "__main__":
     ap.add_argument("--m", type=int, default=16)
     ap.add_argument("--metric", default="euclidean", choices=["euclidean", "cosine"])
     ap.add_argument("--sigma", type=float, default=0.15)
+    ap.add_argument("--prefix", action="store_true", help="insertion-order (prefix) candidate sets in the batch builder")
     ap.add_argument("--log2-nodes", type=int, default=24)
     ap.add_argument("--edges", type=int, default=160_000_000)
     ap.add_argument("--sources", type=int, default=1024)
