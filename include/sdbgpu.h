@@ -133,6 +133,16 @@ sdb_status sdb_knn_bruteforce_device(sdb_corpus*, const double* d_queries, uint3
                                      uint64_t row_base, uint64_t* d_out_rows, double* d_out_dist,
                                      uint32_t* d_out_count);
 sdb_status sdb_knn_last_stats(const sdb_corpus*, sdb_knn_stats* out);
+/* ---- projected scalar vector functions over a whole column: replaces a per-row evaluation of
+ *      vector::distance::* / vector::similarity::* / vector::dot / vector::magnitude (fnc/vector.rs:25-143,
+ *      fnc/util/math/vector.rs:61-314) in `SELECT vector::similarity::cosine(emb, $q) FROM t`.
+ * fn: an sdb_metric id (= what Distance::compute returns for it: COSINE -> cosine DISTANCE, PEARSON -> the
+ * similarity; MINKOWSKI / JACCARD unsupported) or one of sdb_vector_fn.  out: host, one f64 per row in scan order,
+ * bit-identical to the reference's sequential f64 arithmetic; skipped rows get NaN.  query: host, dim doubles
+ * (ignored for SDB_FN_MAGNITUDE). */
+typedef enum { SDB_FN_SIMILARITY_COSINE = 16, SDB_FN_DOT = 17, SDB_FN_MAGNITUDE = 18 } sdb_vector_fn;
+sdb_status sdb_corpus_project(sdb_corpus*, const double* query, int fn, double* out);
+
 /* merges `n_lists` per-shard result lists (each nq x k; list l's entry j of query q is valid iff
  * j < d_counts[l*stride_counts + q]) into the global top-k by (distance, row); all pointers are device
  * pointers.  stride_* = distance in ELEMENTS between consecutive lists (0 = dense: nq*k, nq*k, nq), so the
@@ -151,6 +161,33 @@ sdb_status sdb_hnsw_load(sdb_ctx*, uint32_t dim, sdb_metric, uint64_t n_elems, c
                          uint32_t n_layers, const uint64_t* const* row_ptr, const uint32_t* const* col_idx,
                          int64_t entry_point, sdb_hnsw** out);
 void sdb_hnsw_destroy(sdb_hnsw*);
+
+/* ---- staging: the reference's persisted HNSW state -> device.  These replace the per-key
+ *      decode loops of HnswLayer::load (idx/trees/hnsw/layer.rs:526-540, UndirectedGraph::load_node
+ *      idx/trees/graph.rs:117-126) and HnswElements::get_vector (hnsw/elements.rs:95-128, Vector::from(
+ *      SerializedVector) idx/trees/vector.rs:93-103).  The caller range-scans the KV store and hands over the raw
+ *      VALUE bytes, concatenated: value i occupies blob[off[i] .. off[i+1]).  Blobs may be pageable or pinned host
+ *      memory.  *n_bad (nullable) counts values that failed validation (bad header, length != dim, target id out
+ *      of range, value not representable in the output type, edge to an unknown element); those values are skipped.
+ * He values: revisioned SerializedVector {F64,F32,I64,I32,I16}; elem_ids[i] = destination row (NULL: row i).
+ * d_out_rows: DEVICE buffer n_rows x dim of out_dtype (SDB_F32 / SDB_F64); d_present (device, nullable) gets 1 per
+ * decoded row. */
+sdb_status sdb_stage_decode_vectors(sdb_ctx*, const uint8_t* blob, const uint64_t* off, const uint64_t* elem_ids,
+                                    uint64_t n, uint32_t dim, sdb_dtype out_dtype, uint64_t n_rows, void* d_out_rows,
+                                    uint8_t* d_present, uint64_t* n_bad);
+/* Hn values of ONE layer (BE u16 count + BE u64 neighbour ids), node_ids[i] = the key's node id.  Output: CSR over
+ * element ids 0..n_elems-1 in stored neighbour order, first occurrence kept (DynamicSet::insert); host arrays owned
+ * by the library (sdb_free). */
+sdb_status sdb_stage_decode_nodes(sdb_ctx*, const uint8_t* blob, const uint64_t* off, const uint64_t* node_ids,
+                                  uint64_t n, uint64_t n_elems, uint64_t** out_row_ptr, uint32_t** out_col_idx,
+                                  uint64_t* n_bad);
+/* Both of the above fused with sdb_hnsw_load: raw He values + per-layer Hn values in, device-resident index out
+ * (no host-side CSR is ever materialised).  entry_point / n_layers come from the Hs state (hnsw/mod.rs:61-72). */
+sdb_status sdb_hnsw_load_staged(sdb_ctx*, uint32_t dim, sdb_metric, uint64_t n_elems, const uint8_t* vec_blob,
+                                const uint64_t* vec_off, const uint64_t* vec_ids, uint64_t n_vec, uint32_t n_layers,
+                                const uint8_t* const* node_blob, const uint64_t* const* node_off,
+                                const uint64_t* const* node_ids, const uint64_t* n_nodes, int64_t entry_point,
+                                sdb_hnsw** out, uint64_t* n_bad);
 /* queries nq x dim f32; out nq x k (element id, f64 distance) ascending; out_counters (nullable)
  * nq x 2 = {distance evaluations, expanded nodes} per query. */
 sdb_status sdb_hnsw_search(sdb_hnsw*, const float* queries, uint32_t nq, uint32_t k, uint32_t ef,

@@ -60,6 +60,7 @@ def lib():
         L.orc_f32row_cosine_distance.restype = C.c_double
         L.orc_f32row_euclidean.restype = C.c_double
         L.orc_f64_magnitude.restype = C.c_double
+        L.orc_f64_metric.restype = C.c_double
         L.orc_f32row_magnitude.restype = C.c_double
         L.orc_knn_topk.restype = C.c_size_t
         L.orc_nd_dot_f32.restype = C.c_float
@@ -125,6 +126,12 @@ def f64_cosine_distance(a, b):
     a = np.ascontiguousarray(a, np.float64)
     b = np.ascontiguousarray(b, np.float64)
     return lib().orc_f64_cosine_distance(_p(a, C.c_double), _p(b, C.c_double), C.c_size_t(a.size))
+
+
+def f64_metric(metric, a, b):
+    a = np.ascontiguousarray(a, np.float64)
+    b = np.ascontiguousarray(b, np.float64)
+    return lib().orc_f64_metric(C.c_int(METRICS[metric]), _p(a, C.c_double), _p(b, C.c_double), C.c_size_t(a.size))
 
 
 def f64_euclidean(a, b):
@@ -368,3 +375,44 @@ def gen_f32(seed, first, n):
     out = np.zeros(n, np.float32)
     lib().orc_gen_fill_f32(C.c_uint64(seed), C.c_uint64(first), C.c_uint64(n), _p(out, C.c_float))
     return out
+
+
+# ---------------------------------------------------------------- legacy KnnPriorityList (idx/planner/knn.rs:11-106)
+def knn_priority_list(dists, k):
+    """Restatement of the legacy two-pass brute force's first pass (pure Python: small cases only).
+    dists: distance per row in scan order (None = row skipped).  Returns (must, tie, left): rows every outcome
+    contains, the boundary tie group, and how many of the tie group the reference takes (arbitrary `HashSet` order,
+    knn.rs:85-93)."""
+    import bisect
+    keys, groups, docs = [], {}, set()   # BTreeMap<Number, HashSet<rid>>, docs: HashSet<rid>
+    def key(d):
+        a = np.float64(d)
+        if a == 0:
+            a = np.float64(0.0)           # Number::cmp: -0.0 == 0.0
+        b = int(a.view(np.uint64))
+        return (~b & 0xFFFFFFFFFFFFFFFF) if b >> 63 else (b | (1 << 63))
+    for rid, d in enumerate(dists):
+        if d is None:
+            continue
+        kd = key(d)
+        if len(docs) >= k and keys and not (keys[-1] > kd):     # check_add  knn.rs:44-52
+            continue
+        if kd not in groups:                                    # add  knn.rs:54-81
+            bisect.insort(keys, kd)
+            groups[kd] = [rid]
+            docs.add(rid)
+        else:
+            groups[kd].append(rid)                              # (docs is NOT updated here, as in the reference)
+        if len(docs) > k and len(docs) - len(groups[keys[-1]]) >= k:
+            for r in groups.pop(keys.pop()):
+                docs.discard(r)
+    must, left = [], k                                          # build  knn.rs:83-105
+    for kd in keys:
+        g = groups[kd]
+        if len(g) > left:
+            return must, g, left
+        must += g
+        left -= len(g)
+        if left == 0:
+            break
+    return must, [], 0

@@ -281,6 +281,52 @@ int orc_num_distance(int metric, double p, const orc_num* a, size_t na, const or
 DEF_FAST(orc_f64_cosine_distance, orc_f64_euclidean, orc_f64_magnitude, double)
 DEF_FAST(orc_f32row_cosine_distance, orc_f32row_euclidean, orc_f32row_magnitude, float)
 
+/* all-Float fast paths of the remaining Distance::compute metrics (same op order as orc_num_* on Floats);
+ * `row` is f32 or f64, `q` f64.  Used by orc_knn_topk for the metrics the GPU serves through its exact kernel. */
+#define DEF_MORE(SUFFIX, T)                                                                      \
+  static double fast_manhattan_##SUFFIX(const T* a, const double* b, size_t n) {                 \
+    double s = 0.0;                                                                              \
+    for (size_t i = 0; i < n; i++) s = s + fabs((double)a[i] - b[i]);                            \
+    return s;                                                                                    \
+  }                                                                                              \
+  static double fast_chebyshev_##SUFFIX(const T* a, const double* b, size_t n) {                 \
+    double m = -1.7976931348623157e308;                                                          \
+    for (size_t i = 0; i < n; i++) m = rust_fmax(m, fabs((double)a[i] - b[i]));                  \
+    return m;                                                                                    \
+  }                                                                                              \
+  static double fast_hamming_##SUFFIX(const T* a, const double* b, size_t n) {                   \
+    int64_t c = 0;                                                                               \
+    for (size_t i = 0; i < n; i++) c += !N_eq(N_f((double)a[i]), N_f(b[i]));                     \
+    return (double)c;                                                                            \
+  }                                                                                              \
+  static double fast_pearson_##SUFFIX(const T* a, const double* b, size_t n) {                   \
+    double s1 = 0.0, s2 = 0.0;                                                                   \
+    for (size_t i = 0; i < n; i++) s1 = s1 + (double)a[i];                                       \
+    for (size_t i = 0; i < n; i++) s2 = s2 + b[i];                                               \
+    const double m1 = n ? s1 / (double)n : NAN, m2 = n ? s2 / (double)n : NAN;                   \
+    double covar = 0.0, d1 = 0.0, d2 = 0.0;                                                      \
+    for (size_t i = 0; i < n; i++) covar += ((double)a[i] - m1) * (b[i] - m2);                   \
+    covar = covar / (double)n;                                                                   \
+    for (size_t i = 0; i < n; i++) { double x = (double)a[i] - m1; d1 += x * x; }                \
+    for (size_t i = 0; i < n; i++) { double x = b[i] - m2; d2 += x * x; }                        \
+    const double sd1 = n == 0 ? NAN : (n == 1 ? 0.0 : sqrt(d1 / (double)n));                     \
+    const double sd2 = n == 0 ? NAN : (n == 1 ? 0.0 : sqrt(d2 / (double)n));                     \
+    return covar / (sd1 * sd2);                                                                  \
+  }
+DEF_MORE(f64, double)
+DEF_MORE(f32, float)
+double orc_f64_metric(int metric, const double* a, const double* b, size_t n) {
+  switch (metric) {
+    case ORC_COSINE: return orc_f64_cosine_distance(a, b, n);
+    case ORC_EUCLIDEAN: return orc_f64_euclidean(a, b, n);
+    case ORC_MANHATTAN: return fast_manhattan_f64(a, b, n);
+    case ORC_CHEBYSHEV: return fast_chebyshev_f64(a, b, n);
+    case ORC_HAMMING: return fast_hamming_f64(a, b, n);
+    case ORC_PEARSON: return fast_pearson_f64(a, b, n);
+  }
+  return NAN;
+}
+
 /* ------------------------------------------------------------------------------------------
  * a4: KnnTopK                                         exec/operators/knn_topk.rs:166-267
  * Bounded selection with the DistanceEntry order: worst = max by (distance, seq); a new entry
@@ -299,10 +345,18 @@ static inline int topk_worse(const topk_ent* a, const topk_ent* b) { /* a is far
 static double row_distance(const void* corpus, int is_f64, size_t r, size_t dim, const double* q, int metric) {
   if (is_f64) {
     const double* row = (const double*)corpus + r * dim;
-    return metric == ORC_COSINE ? orc_f64_cosine_distance(row, q, dim) : orc_f64_euclidean(row, q, dim);
+    return orc_f64_metric(metric, row, q, dim);
   }
   const float* row = (const float*)corpus + r * dim;
-  return metric == ORC_COSINE ? orc_f32row_cosine_distance(row, q, dim) : orc_f32row_euclidean(row, q, dim);
+  switch (metric) {
+    case ORC_COSINE: return orc_f32row_cosine_distance(row, q, dim);
+    case ORC_EUCLIDEAN: return orc_f32row_euclidean(row, q, dim);
+    case ORC_MANHATTAN: return fast_manhattan_f32(row, q, dim);
+    case ORC_CHEBYSHEV: return fast_chebyshev_f32(row, q, dim);
+    case ORC_HAMMING: return fast_hamming_f32(row, q, dim);
+    case ORC_PEARSON: return fast_pearson_f32(row, q, dim);
+  }
+  return NAN;
 }
 static int topk_cmp_sort(const void* x, const void* y) {
   const topk_ent *a = (const topk_ent*)x, *b = (const topk_ent*)y;

@@ -76,6 +76,8 @@ double orc_f64_euclidean(const double* a, const double* b, size_t n);
 double orc_f32row_cosine_distance(const float* row, const double* q, size_t n);
 double orc_f32row_euclidean(const float* row, const double* q, size_t n);
 double orc_f64_magnitude(const double* a, size_t n);
+/* all-Float fast path of Distance::compute for COSINE, EUCLIDEAN, MANHATTAN, CHEBYSHEV, HAMMING, PEARSON */
+double orc_f64_metric(int metric, const double* a, const double* b, size_t n);
 double orc_f32row_magnitude(const float* a, size_t n);
 
 /* ---- a4: KnnTopK selection.  exec/operators/knn_topk.rs:166-267

@@ -15,6 +15,7 @@ STATUS_NAMES = ["SDB_OK", "SDB_EINVAL", "SDB_EDIM", "SDB_ENOMEM", "SDB_ECUDA", "
 METRIC = {"CHEBYSHEV": 0, "COSINE": 1, "EUCLIDEAN": 2, "HAMMING": 3, "JACCARD": 4, "MANHATTAN": 5,
           "MINKOWSKI": 6, "PEARSON": 7}
 DTYPE = {"F32": 0, "F64": 1}
+VECTOR_FN = {"SIMILARITY_COSINE": 16, "DOT": 17, "MAGNITUDE": 18}
 SCREEN = {"AUTO": 0, "SIMT_F32": 1, "TC_BF16": 2, "NONE_EXACT": 3, "TC_INT8": 4}
 
 # every symbol include/sdbgpu.h declares (tests/test_abi_symbols.py cross-checks this list with the header)
@@ -23,7 +24,7 @@ ABI_SYMBOLS = [
     "sdb_ctx_kernel_launches", "sdb_ctx_stream", "sdb_corpus_create", "sdb_corpus_destroy", "sdb_corpus_append",
     "sdb_corpus_append_device", "sdb_corpus_append_synthetic", "sdb_corpus_set_skip", "sdb_corpus_finalize",
     "sdb_corpus_rows", "sdb_corpus_set_screen", "sdb_corpus_set_exact", "sdb_knn_bruteforce", "sdb_knn_bruteforce_device",
-    "sdb_knn_last_stats", "sdb_topk_merge_device", "sdb_hnsw_load", "sdb_hnsw_destroy", "sdb_hnsw_search", "sdb_hnsw_select_neighbors",
+    "sdb_knn_last_stats", "sdb_corpus_project", "sdb_topk_merge_device", "sdb_hnsw_load", "sdb_hnsw_destroy", "sdb_stage_decode_vectors", "sdb_stage_decode_nodes", "sdb_hnsw_load_staged", "sdb_hnsw_search", "sdb_hnsw_select_neighbors",
     "sdb_graph_load_csr", "sdb_graph_destroy", "sdb_graph_expand", "sdb_graph_expand_device", "sdb_device_free", "sdb_graph_collect", "sdb_free",
 ]
 
@@ -77,10 +78,15 @@ def lib():
     L.sdb_corpus_set_exact.argtypes = [vp, i32]
     L.sdb_knn_bruteforce.argtypes = [vp, vp, u32, u32, vp, vp, vp, vp]
     L.sdb_knn_bruteforce_device.argtypes = [vp, vp, u32, u32, u64, vp, vp, vp]
+    L.sdb_corpus_project.argtypes = [vp, vp, i32, vp]
     L.sdb_knn_last_stats.argtypes = [vp, C.POINTER(KnnStats)]
     L.sdb_topk_merge_device.argtypes = [vp, u32, u32, u32, vp, vp, vp, u64, u64, u64, vp, vp, vp]
     L.sdb_hnsw_load.argtypes = [vp, u32, i32, u64, vp, u32, vp, vp, C.c_int64, C.POINTER(vp)]
     L.sdb_hnsw_destroy.argtypes = [vp]
+    L.sdb_stage_decode_vectors.argtypes = [vp, vp, vp, vp, u64, u32, i32, u64, vp, vp, C.POINTER(u64)]
+    L.sdb_stage_decode_nodes.argtypes = [vp, vp, vp, vp, u64, u64, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]
+    L.sdb_hnsw_load_staged.argtypes = [vp, u32, i32, u64, vp, vp, vp, u64, u32, vp, vp, vp, vp, C.c_int64, C.POINTER(vp),
+                                       C.POINTER(u64)]
     L.sdb_hnsw_search.argtypes = [vp, vp, u32, u32, u32, vp, vp, vp, vp]
     L.sdb_hnsw_select_neighbors.argtypes = [vp, vp, u32, i32, u64, u64, vp, vp, u32, u32, i32, vp, vp]
     L.sdb_graph_load_csr.argtypes = [vp, u64, vp, vp, C.POINTER(vp)]

@@ -63,7 +63,8 @@ static sdb_status knn_device_locked(Corpus* c, const double* d_queries, uint32_t
     scr = !screen_tc_available() ? SDB_SCREEN_SIMT_F32 : (int8_ok && c->max_rel_qerr <= 0.006f ? SDB_SCREEN_TC_INT8 : SDB_SCREEN_TC_BF16);
   if (scr == SDB_SCREEN_TC_INT8 && !int8_ok) scr = SDB_SCREEN_TC_BF16;
   if (scr == SDB_SCREEN_TC_BF16 && !screen_tc_available()) scr = SDB_SCREEN_SIMT_F32;
-  if (c->dtype == SDB_F64 || c->special_overflow || k > 256) scr = SDB_SCREEN_NONE_EXACT;
+  const bool screenable = c->metric == SDB_COSINE || c->metric == SDB_EUCLIDEAN;
+  if (c->dtype == SDB_F64 || c->special_overflow || k > 256 || !screenable) scr = SDB_SCREEN_NONE_EXACT;
   const uint32_t kp = k + (k > 54 ? k : 54) + (scr == SDB_SCREEN_TC_INT8 ? 64 : 0);  // looser screen => more slack
   uint32_t cap = 4096;
   while (cap < 16 * kp) cap <<= 1;
@@ -110,7 +111,7 @@ static sdb_status knn_device_locked(Corpus* c, const double* d_queries, uint32_t
   SDB_CUDA(cudaStreamSynchronize(st));
   // ---- exact path for everything the screens could not prove ----
   for (uint32_t q = 0; q < nq; q++) {
-    if (((h_flags[q] & 2u) && c->exact) || (h_qflags[q] & 1u)) {
+    if (((h_flags[q] & 2u) && (c->exact || scr == SDB_SCREEN_NONE_EXACT)) || (h_qflags[q] & 1u)) {
       if (cancel && *cancel) {
         for (auto& e : ev) cudaEventDestroy(e);
         set_error("query cancelled");
@@ -266,8 +267,12 @@ sdb_status sdb_corpus_create(sdb_ctx* ctx, uint32_t dim, sdb_dtype dt, sdb_metri
     set_error("sdb_corpus_create: bad argument (dim 1..65535, 0 < capacity < 2^32)");
     return SDB_EINVAL;
   }
-  if (m != SDB_COSINE && m != SDB_EUCLIDEAN) {
-    set_error("metric %d not implemented on the GPU path (COSINE and EUCLIDEAN are)", (int)m);
+  // COSINE / EUCLIDEAN: screened (K1/K2) + exact re-rank.  MANHATTAN / CHEBYSHEV / HAMMING / PEARSON: served by the
+  // exact kernel alone (sequential f64, bit-identical to Distance::compute).  MINKOWSKI (powf is not bit-reproducible
+  // across libm implementations) and JACCARD (set semantics, not a vector metric) stay on the reference's CPU path.
+  const bool screenable = m == SDB_COSINE || m == SDB_EUCLIDEAN;
+  if (!screenable && m != SDB_MANHATTAN && m != SDB_CHEBYSHEV && m != SDB_HAMMING && m != SDB_PEARSON) {
+    set_error("metric %d not implemented on the GPU path (MINKOWSKI and JACCARD stay on the CPU)", (int)m);
     return SDB_EUNSUPPORTED;
   }
   if (dt != SDB_F32 && dt != SDB_F64) return SDB_EINVAL;
@@ -285,7 +290,7 @@ sdb_status sdb_corpus_create(sdb_ctx* ctx, uint32_t dim, sdb_dtype dt, sdb_metri
   cudaError_t e = cudaMalloc(&c->d_rows, esz * cap * dim);
   if (e == cudaSuccess) e = cudaMalloc(&c->d_mag, sizeof(double) * cap);
   if (e == cudaSuccess) e = cudaMalloc(&c->d_snorm, sizeof(float) * cap_pad);
-  if (e == cudaSuccess && dt == SDB_F32) e = cudaMalloc(&c->d_bf16, sizeof(__nv_bfloat16) * cap_pad * c->dim_pad);
+  if (e == cudaSuccess && dt == SDB_F32 && screenable) e = cudaMalloc(&c->d_bf16, sizeof(__nv_bfloat16) * cap_pad * c->dim_pad);
   if (e == cudaSuccess && dt == SDB_F32 && m == SDB_COSINE) e = cudaMalloc(&c->d_i8, (size_t)cap_pad * c->dim_pad8);
   if (e != cudaSuccess) {
     set_error("corpus allocation failed: %s", cudaGetErrorString(e));
@@ -419,6 +424,37 @@ sdb_status sdb_knn_bruteforce(sdb_corpus* c, const double* queries, uint32_t nq,
     SDB_CUDA(cudaMemcpyAsync(out_dist, c->d_out_dist, sizeof(double) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
   }
   SDB_CUDA(cudaMemcpyAsync(out_count, c->d_out_count, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, st));
+  SDB_CUDA(cudaStreamSynchronize(st));
+  return SDB_OK;
+}
+
+sdb_status sdb_corpus_project(sdb_corpus* c, const double* query, int fn, double* out) {
+  const bool is_metric = fn == SDB_COSINE || fn == SDB_EUCLIDEAN || fn == SDB_MANHATTAN || fn == SDB_CHEBYSHEV ||
+                         fn == SDB_HAMMING || fn == SDB_PEARSON;
+  if (!c || !out || (!query && fn != SDB_FN_MAGNITUDE)) return SDB_EINVAL;
+  if (!is_metric && fn != SDB_FN_SIMILARITY_COSINE && fn != SDB_FN_DOT && fn != SDB_FN_MAGNITUDE) {
+    set_error("vector function %d not implemented on the GPU path", fn);
+    return SDB_EUNSUPPORTED;
+  }
+  std::lock_guard<std::mutex> g(c->mu);
+  if (!c->finalized) {
+    set_error("corpus not finalized (call sdb_corpus_finalize after the last append)");
+    return SDB_EINVAL;
+  }
+  if (c->n == 0) return SDB_OK;
+  SDB_CUDA(cudaSetDevice(c->ctx->device));
+  cudaStream_t st = c->ctx->stream;
+  double *d_q = nullptr, *d_vals = nullptr;
+  SDB_CUDA(cudaMallocAsync(&d_q, sizeof(double) * c->dim, st));
+  SDB_CUDA(cudaMallocAsync(&d_vals, sizeof(double) * c->n, st));
+  if (query) SDB_CUDA(cudaMemcpyAsync(d_q, query, sizeof(double) * c->dim, cudaMemcpyHostToDevice, st));
+  else SDB_CUDA(cudaMemsetAsync(d_q, 0, sizeof(double) * c->dim, st));
+  SDB_TRY(scratch_for(c, 1, 4096, 64));
+  SDB_TRY(prep_queries(c, d_q, 1, st));
+  SDB_TRY(exact_project(c, fn, d_vals, st));
+  SDB_CUDA(cudaMemcpyAsync(out, d_vals, sizeof(double) * c->n, cudaMemcpyDeviceToHost, st));
+  SDB_CUDA(cudaFreeAsync(d_q, st));
+  SDB_CUDA(cudaFreeAsync(d_vals, st));
   SDB_CUDA(cudaStreamSynchronize(st));
   return SDB_OK;
 }

@@ -21,52 +21,123 @@ __global__ void __launch_bounds__(WARPS * 32) exact_keys_kernel(const T* __restr
                                                                 const double* __restrict__ q64 /* this query */,
                                                                 const double* __restrict__ qmag_p,
                                                                 const uint32_t* __restrict__ qflags_p,
-                                                                uint64_t* __restrict__ keys) {
+                                                                uint64_t* __restrict__ keys,
+                                                                double* __restrict__ vals /* non-null: projection */) {
   __shared__ T tile[WARPS][32][33];
   __shared__ double s_q[EX_QCHUNK];
+  __shared__ double s_qstat[2];  // pearson: mean and (population) deviation of the query
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool q_nan = (*qflags_p & 2u) != 0;
   const double qm = *qmag_p;
+  // `metric` also takes the projection-only ids SDB_FN_SIMILARITY_COSINE / SDB_FN_DOT / SDB_FN_MAGNITUDE
+  if (metric == SDB_PEARSON && threadIdx.x == 0) {
+    // mean: fnc/util/math/mod.rs:54-69 ; deviation(sample=false): vector.rs:9-21 -- sequential, as the reference
+    double s = 0.0;
+    for (uint32_t i = 0; i < dim; i++) s = __dadd_rn(s, q64[i]);
+    const double m2 = __ddiv_rn(s, (double)dim);
+    double dv = 0.0;
+    for (uint32_t i = 0; i < dim; i++) {
+      const double x = __dsub_rn(q64[i], m2);
+      dv = __dadd_rn(dv, __dmul_rn(x, x));
+    }
+    s_qstat[0] = m2;
+    s_qstat[1] = dim == 1 ? 0.0 : __dsqrt_rn(__ddiv_rn(dv, (double)dim));
+  }
+  __syncthreads();
+  const int n_phase = metric == SDB_PEARSON ? 2 : 1;
   const uint64_t rows_per_block = (uint64_t)WARPS * 32;
   for (uint64_t b0 = (uint64_t)blockIdx.x * rows_per_block; b0 < n; b0 += (uint64_t)gridDim.x * rows_per_block) {
     const uint64_t r = b0 + warp * 32 + lane;
     const uint32_t my_row = r < n ? (uint32_t)r : NO_ROW;
     ExactAcc acc;
-    for (uint32_t cb = 0; cb < dim; cb += EX_QCHUNK) {
-      const uint32_t cw = dim - cb < EX_QCHUNK ? dim - cb : EX_QCHUNK;
-      __syncthreads();
-      for (uint32_t i = threadIdx.x; i < cw; i += blockDim.x) s_q[i] = q64[cb + i];
-      __syncthreads();
-      const T* base = rows + cb;
-      for (uint32_t c0 = 0; c0 < cw; c0 += 32) {
-        const uint32_t c = c0 + lane;
+    double m1 = 0.0;
+    bool nan_in = false;
+    if (metric == SDB_CHEBYSHEV) acc.acc = -1.7976931348623157e308;  // f64::MIN
+    for (int phase = 0; phase < n_phase; phase++) {
+      for (uint32_t cb = 0; cb < dim; cb += EX_QCHUNK) {
+        const uint32_t cw = dim - cb < EX_QCHUNK ? dim - cb : EX_QCHUNK;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < cw; i += blockDim.x) s_q[i] = q64[cb + i];
+        __syncthreads();
+        const T* base = rows + cb;
+        for (uint32_t c0 = 0; c0 < cw; c0 += 32) {
+          const uint32_t c = c0 + lane;
 #pragma unroll 8
-        for (int rr = 0; rr < 32; rr++) {
-          const uint32_t row = __shfl_sync(0xffffffffu, my_row, rr);
-          T v = T(0);
-          if (row != NO_ROW && c < cw) v = __ldg(base + (size_t)row * dim + c);
-          tile[warp][rr][lane] = v;
-        }
-        __syncwarp();
-        if (my_row != NO_ROW) {
-          const uint32_t lim = cw - c0 < 32u ? cw - c0 : 32u;
-          if (metric == SDB_COSINE) {
-            for (uint32_t j = 0; j < lim; j++) acc.cosine_step((double)tile[warp][lane][j], s_q[c0 + j]);
-          } else {
-            for (uint32_t j = 0; j < lim; j++) acc.euclid_step((double)tile[warp][lane][j], s_q[c0 + j]);
+          for (int rr = 0; rr < 32; rr++) {
+            const uint32_t row = __shfl_sync(0xffffffffu, my_row, rr);
+            T v = T(0);
+            if (row != NO_ROW && c < cw) v = __ldg(base + (size_t)row * dim + c);
+            tile[warp][rr][lane] = v;
           }
+          __syncwarp();
+          if (my_row != NO_ROW) {
+            const uint32_t lim = cw - c0 < 32u ? cw - c0 : 32u;
+            const T* t = tile[warp][lane];
+            switch (metric) {  // uniform across the block
+              case SDB_COSINE:
+              case SDB_FN_SIMILARITY_COSINE:
+              case SDB_FN_DOT:
+                for (uint32_t j = 0; j < lim; j++) acc.cosine_step((double)t[j], s_q[c0 + j]);
+                break;
+              case SDB_FN_MAGNITUDE: break;  // precomputed at finalize
+              case SDB_EUCLIDEAN:
+                for (uint32_t j = 0; j < lim; j++) acc.euclid_step((double)t[j], s_q[c0 + j]);
+                break;
+              case SDB_MANHATTAN:
+                for (uint32_t j = 0; j < lim; j++) acc.manhattan_step((double)t[j], s_q[c0 + j]);
+                break;
+              case SDB_CHEBYSHEV:
+                for (uint32_t j = 0; j < lim; j++) acc.chebyshev_step((double)t[j], s_q[c0 + j]);
+                break;
+              case SDB_HAMMING:
+                for (uint32_t j = 0; j < lim; j++) acc.hamming_step((double)t[j], s_q[c0 + j]);
+                break;
+              default:  // SDB_PEARSON
+                if (phase == 0) {
+                  for (uint32_t j = 0; j < lim; j++) acc.sum_step((double)t[j]);
+                } else {
+                  for (uint32_t j = 0; j < lim; j++) acc.pearson_step((double)t[j], s_q[c0 + j], m1, s_qstat[0]);
+                }
+                break;
+            }
+          }
+          __syncwarp();
         }
-        __syncwarp();
+      }
+      if (metric == SDB_PEARSON && phase == 0) {
+        m1 = __ddiv_rn(acc.acc, (double)dim);
+        nan_in = acc.nan_in;
+        acc.acc = 0.0;
       }
     }
     if (my_row != NO_ROW) {
       uint64_t key;
-      if (skip && skip[r]) key = KEY_SKIPPED;
-      else {
-        const double d = metric == SDB_COSINE ? cosine_finish(acc, mag[r], qm, q_nan) : euclid_finish(acc, q_nan);
+      if (skip && skip[r]) {
+        key = KEY_SKIPPED;
+        if (vals) vals[r] = __longlong_as_double(0x7FF8000000000000ll);
+      } else {
+        double d;
+        switch (metric) {
+          case SDB_COSINE: d = cosine_finish(acc, mag[r], qm, q_nan); break;
+          case SDB_FN_SIMILARITY_COSINE:  // vector.rs:65-71
+            d = canon_nan(__ddiv_rn(acc.acc, __dmul_rn(mag[r], qm)), acc.nan_in || q_nan);
+            break;
+          case SDB_FN_DOT: d = canon_nan(acc.acc, acc.nan_in || q_nan); break;  // vector.rs:279-281
+          case SDB_FN_MAGNITUDE: d = mag[r]; break;                             // vector.rs:301-314
+          case SDB_EUCLIDEAN: d = euclid_finish(acc, q_nan); break;
+          case SDB_MANHATTAN: d = canon_nan(acc.acc, acc.nan_in || q_nan); break;
+          case SDB_CHEBYSHEV:
+          case SDB_HAMMING: d = acc.acc; break;
+          default: {  // pearson: covar/len / (sd1 * sd2)
+            const double covar = __ddiv_rn(acc.acc, (double)dim);
+            const double sd1 = dim == 1 ? 0.0 : __dsqrt_rn(__ddiv_rn(acc.acc2, (double)dim));
+            d = canon_nan(__ddiv_rn(covar, __dmul_rn(sd1, s_qstat[1])), nan_in || q_nan);
+          }
+        }
         key = dist_key(d);
+        if (vals) vals[r] = d;
       }
-      keys[r] = key;
+      if (keys) keys[r] = key;
     }
   }
 }
@@ -233,11 +304,11 @@ sdb_status exact_query(Corpus* c, uint32_t q, uint32_t k, uint64_t row_base, uin
     if (c->dtype == SDB_F32)
       exact_keys_kernel<float, 4><<<grid, 128, 0, st>>>((const float*)c->d_rows, c->dim, n, (int)c->metric, c->d_mag,
                                                         c->d_skip, c->d_q64 + (size_t)q * c->dim, c->d_qmag + q,
-                                                        c->d_qflags + q, c->d_ex_key);
+                                                        c->d_qflags + q, c->d_ex_key, nullptr);
     else
       exact_keys_kernel<double, 4><<<grid, 128, 0, st>>>((const double*)c->d_rows, c->dim, n, (int)c->metric,
                                                          c->d_mag, c->d_skip, c->d_q64 + (size_t)q * c->dim,
-                                                         c->d_qmag + q, c->d_qflags + q, c->d_ex_key);
+                                                         c->d_qmag + q, c->d_qflags + q, c->d_ex_key, nullptr);
     count_launch(ctx);
   }
   sel_init_kernel<<<1, 256, 0, st>>>(sel, k);
@@ -255,6 +326,24 @@ sdb_status exact_query(Corpus* c, uint32_t q, uint32_t k, uint64_t row_base, uin
                                                              d_out_rows + (size_t)q * k, d_out_dist + (size_t)q * k,
                                                              d_out_count + q);
   count_launch(ctx, 2);
+  SDB_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
+
+
+// one reference-arithmetic value per row (projected scalar vector functions)
+sdb_status exact_project(Corpus* c, int fn, double* d_vals, cudaStream_t st) {
+  Ctx* ctx = c->ctx;
+  const uint64_t n = c->n;
+  if (!n) return SDB_OK;
+  const int grid = ctx->sm_count * 8;
+  if (c->dtype == SDB_F32)
+    exact_keys_kernel<float, 4><<<grid, 128, 0, st>>>((const float*)c->d_rows, c->dim, n, fn, c->d_mag, c->d_skip,
+                                                      c->d_q64, c->d_qmag, c->d_qflags, nullptr, d_vals);
+  else
+    exact_keys_kernel<double, 4><<<grid, 128, 0, st>>>((const double*)c->d_rows, c->dim, n, fn, c->d_mag, c->d_skip,
+                                                       c->d_q64, c->d_qmag, c->d_qflags, nullptr, d_vals);
+  count_launch(ctx);
   SDB_CUDA(cudaGetLastError());
   return SDB_OK;
 }

@@ -75,7 +75,7 @@ __global__ void scan_add_kernel(uint64_t* __restrict__ out, uint64_t n, const ui
   }
 }
 // out[0..n) = exclusive scan of in[0..n); *d_total = sum.  in/out may alias.
-static sdb_status exclusive_scan(Ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint64_t n, uint64_t* d_total,
+sdb_status exclusive_scan(Ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint64_t n, uint64_t* d_total,
                                  cudaStream_t st) {
   if (n == 0) {
     SDB_CUDA(cudaMemsetAsync(d_total, 0, 8, st));

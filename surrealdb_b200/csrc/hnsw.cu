@@ -449,6 +449,32 @@ __global__ void __launch_bounds__(128) hnsw_select_kernel(const float* __restric
 struct sdb_hnsw : sdb::Hnsw {};
 using namespace sdb;
 
+extern "C" void sdb_hnsw_destroy(sdb_hnsw* h);
+
+// common tail of the loaders: per-layer pointer tables + cached |x|^2
+static sdb_status hnsw_finish(sdb_hnsw* h, sdb_hnsw** out) {
+  Ctx* ctx = h->ctx;
+  cudaStream_t st = ctx->stream;
+  auto fail = [&](const char* what, sdb_status rc) {
+    set_error("hnsw load: %s failed: %s", what, cudaGetErrorString(cudaGetLastError()));
+    sdb_hnsw_destroy(h);
+    return rc;
+  };
+  const uint32_t n_layers = h->n_layers;
+  if (cudaMalloc(&h->d_rp, sizeof(void*) * n_layers) != cudaSuccess) return fail("layer table", SDB_ENOMEM);
+  if (cudaMalloc(&h->d_ci, sizeof(void*) * n_layers) != cudaSuccess) return fail("layer table", SDB_ENOMEM);
+  if (cudaMemcpyAsync(h->d_rp, h->rp.data(), sizeof(void*) * n_layers, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaMemcpyAsync(h->d_ci, h->ci.data(), sizeof(void*) * n_layers, cudaMemcpyHostToDevice, st) != cudaSuccess)
+    return fail("layer table copy", SDB_ECUDA);
+  if (h->n) {
+    hnsw_sumsq_kernel<<<(unsigned)((h->n + 127) / 128), 128, 0, st>>>(h->d_vec, h->dim, h->n, h->d_sumsq);
+    count_launch(ctx);
+  }
+  if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) return fail("finish", SDB_ECUDA);
+  *out = h;
+  return SDB_OK;
+}
+
 extern "C" {
 
 void sdb_hnsw_destroy(sdb_hnsw* h) {
@@ -493,8 +519,6 @@ sdb_status sdb_hnsw_load(sdb_ctx* ctx, uint32_t dim, sdb_metric metric, uint64_t
   if (cudaMalloc(&h->d_vec, sizeof(float) * nn * dim) != cudaSuccess) return fail("vectors");
   if (cudaMalloc(&h->d_sumsq, sizeof(float) * nn) != cudaSuccess) return fail("sumsq");
   if (n_elems) SDB_CUDA(cudaMemcpyAsync(h->d_vec, vectors, sizeof(float) * n_elems * dim, cudaMemcpyHostToDevice, st));
-  std::vector<const uint64_t*> hrp;
-  std::vector<const uint32_t*> hci;
   for (uint32_t l = 0; l < n_layers; l++) {
     const uint64_t e = n_elems ? row_ptr[l][n_elems] : 0;
     uint64_t* drp = nullptr;
@@ -505,21 +529,64 @@ sdb_status sdb_hnsw_load(sdb_ctx* ctx, uint32_t dim, sdb_metric metric, uint64_t
     h->ci.push_back(dci);
     SDB_CUDA(cudaMemcpyAsync(drp, row_ptr[l], sizeof(uint64_t) * (n_elems + 1), cudaMemcpyHostToDevice, st));
     if (e) SDB_CUDA(cudaMemcpyAsync(dci, col_idx[l], sizeof(uint32_t) * e, cudaMemcpyHostToDevice, st));
-    hrp.push_back(drp);
-    hci.push_back(dci);
   }
-  if (cudaMalloc(&h->d_rp, sizeof(void*) * n_layers) != cudaSuccess) return fail("layer table");
-  if (cudaMalloc(&h->d_ci, sizeof(void*) * n_layers) != cudaSuccess) return fail("layer table");
-  SDB_CUDA(cudaMemcpyAsync(h->d_rp, hrp.data(), sizeof(void*) * n_layers, cudaMemcpyHostToDevice, st));
-  SDB_CUDA(cudaMemcpyAsync(h->d_ci, hci.data(), sizeof(void*) * n_layers, cudaMemcpyHostToDevice, st));
-  if (n_elems) {
-    hnsw_sumsq_kernel<<<(unsigned)((n_elems + 127) / 128), 128, 0, st>>>(h->d_vec, dim, n_elems, h->d_sumsq);
-    count_launch(ctx);
+  return hnsw_finish(h, out);
+}
+
+sdb_status sdb_hnsw_load_staged(sdb_ctx* ctx, uint32_t dim, sdb_metric metric, uint64_t n_elems,
+                                const uint8_t* vec_blob, const uint64_t* vec_off, const uint64_t* vec_ids, uint64_t n_vec,
+                                uint32_t n_layers, const uint8_t* const* node_blob, const uint64_t* const* node_off,
+                                const uint64_t* const* node_ids, const uint64_t* n_nodes, int64_t entry_point,
+                                sdb_hnsw** out, uint64_t* n_bad) {
+  if (!ctx || !out || dim == 0 || dim > 65535 || n_elems >= 0xFFFFFFF0ull || !n_layers || !node_blob || !node_off ||
+      !node_ids || !n_nodes || entry_point >= (int64_t)n_elems || (n_vec && (!vec_blob || !vec_off)))
+    return SDB_EINVAL;
+  if (metric != SDB_COSINE && metric != SDB_EUCLIDEAN) {
+    set_error("hnsw: metric %d not implemented on the GPU path", (int)metric);
+    return SDB_EUNSUPPORTED;
   }
-  SDB_CUDA(cudaStreamSynchronize(st));
-  SDB_CUDA(cudaGetLastError());
-  *out = h;
-  return SDB_OK;
+  *out = nullptr;
+  std::lock_guard<std::mutex> guard(ctx->mu);
+  SDB_CUDA(cudaSetDevice(ctx->device));
+  sdb_hnsw* h = new sdb_hnsw();
+  h->ctx = ctx;
+  h->dim = dim;
+  h->metric = metric;
+  h->n = n_elems;
+  h->n_layers = n_layers;
+  h->entry = entry_point;
+  cudaStream_t st = ctx->stream;
+  const uint64_t nn = n_elems ? n_elems : 1;
+  uint64_t bad_total = 0, bad = 0;
+  sdb_status rc = SDB_OK;
+  if (cudaMalloc(&h->d_vec, sizeof(float) * nn * dim) != cudaSuccess ||
+      cudaMalloc(&h->d_sumsq, sizeof(float) * nn) != cudaSuccess) {
+    set_error("hnsw load: vector allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    rc = SDB_ENOMEM;
+  }
+  // elements without an He value keep all-zero vectors; they are unreachable unless an Hn value names them
+  if (rc == SDB_OK && cudaMemsetAsync(h->d_vec, 0, sizeof(float) * nn * dim, st) != cudaSuccess) rc = SDB_ECUDA;
+  if (rc == SDB_OK)
+    rc = stage_decode_vectors(ctx, vec_blob, vec_off, vec_ids, n_vec, dim, SDB_F32, n_elems, h->d_vec, nullptr, &bad, st);
+  bad_total += bad;
+  for (uint32_t l = 0; l < n_layers && rc == SDB_OK; l++) {
+    uint64_t* drp = nullptr;
+    uint32_t* dci = nullptr;
+    uint64_t ne = 0;
+    bad = 0;
+    rc = stage_decode_nodes(ctx, node_blob[l], node_off[l], node_ids[l], n_nodes[l], n_elems, &drp, &dci, &ne, &bad, st);
+    if (rc == SDB_OK) {
+      h->rp.push_back(drp);
+      h->ci.push_back(dci);
+      bad_total += bad;
+    }
+  }
+  if (n_bad) *n_bad = bad_total;
+  if (rc != SDB_OK) {
+    sdb_hnsw_destroy(h);
+    return rc;
+  }
+  return hnsw_finish(h, out);
 }
 
 sdb_status sdb_hnsw_select_neighbors(sdb_ctx* ctx, const float* d_vectors, uint32_t dim, sdb_metric metric, uint64_t row0,

@@ -171,7 +171,18 @@ sdb_status cand_final(Corpus* c, uint32_t nq, uint32_t k, uint32_t kp, float eps
 sdb_status exact_query(Corpus* c, uint32_t q, uint32_t k, uint64_t row_base, uint64_t* d_out_rows,
                        double* d_out_dist, uint32_t* d_out_count, cudaStream_t st);
 // gen.cu
+sdb_status exact_project(Corpus* c, int fn, double* d_vals, cudaStream_t st);
 sdb_status gen_fill_f32(Ctx* ctx, float* d_out, uint64_t seed, uint64_t first, uint64_t n, cudaStream_t st);
+
+// graph.cu: out[0..n) = exclusive scan of in[0..n); *d_total = sum (in/out may alias)
+sdb_status exclusive_scan(Ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint64_t n, uint64_t* d_total, cudaStream_t st);
+// stage.cu: He / Hn value decoders (host blobs in, device arrays out)
+sdb_status stage_decode_vectors(Ctx* ctx, const uint8_t* blob, const uint64_t* off, const uint64_t* ids, uint64_t n,
+                                uint32_t dim, sdb_dtype out_dtype, uint64_t n_rows, void* d_out, uint8_t* d_present,
+                                uint64_t* n_bad, cudaStream_t st);
+sdb_status stage_decode_nodes(Ctx* ctx, const uint8_t* blob, const uint64_t* off, const uint64_t* node_ids, uint64_t n,
+                              uint64_t n_elems, uint64_t** d_row_ptr_out, uint32_t** d_col_idx_out, uint64_t* n_edges,
+                              uint64_t* n_bad, cudaStream_t st);
 
 inline void count_launch(Ctx* ctx, uint64_t n = 1) { ctx->launches += n; }
 

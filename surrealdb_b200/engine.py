@@ -102,6 +102,21 @@ class VectorColumn:
                                                   C.c_void_p(d_out_rows), C.c_void_p(d_out_dist),
                                                   C.c_void_p(d_out_count)))
 
+    def project(self, fn, query=None):
+        """One value per row of `vector::<fn>(row, query)` in the reference's f64 arithmetic (fnc/vector.rs): fn is a
+        metric name ("EUCLIDEAN", "MANHATTAN", ... = vector::distance::*, "COSINE" = 1 - similarity, "PEARSON" =
+        vector::similarity::pearson) or "SIMILARITY_COSINE" / "DOT" / "MAGNITUDE"."""
+        fn = fn.upper()
+        code = L.VECTOR_FN[fn] if fn in L.VECTOR_FN else L.METRIC[fn]
+        out = np.zeros(len(self), np.float64)
+        q = None
+        if query is not None:
+            q = np.ascontiguousarray(query, np.float64)
+            if q.shape != (self.dim,):  # check_same_dimension  fnc/util/math/vector.rs:23-32
+                raise L.SdbError(L.SDB_EDIM, "The two vectors must be of the same dimension.")
+        L.check(L.lib().sdb_corpus_project(self.h, _ptr(q) if q is not None else None, code, _ptr(out)))
+        return out
+
     def stats(self):
         s = L.KnnStats()
         L.check(L.lib().sdb_knn_last_stats(self.h, C.byref(s)))

@@ -32,6 +32,37 @@ class HnswIndex:
         L.check(L.lib().sdb_hnsw_load(ctx.h, self.dim, L.METRIC[self.metric], self.n, C.c_void_p(vec.ctypes.data), nl,
                                       RP, CI, int(entry_point), C.byref(self.h)))
 
+    @classmethod
+    def from_kv(cls, ctx, dim, state_value, he_items, hn_items_per_layer, metric="EUCLIDEAN", elem_docs=None):
+        """Loads the index straight from raw KV values (staging.py): `state_value` = the Hs value, `he_items` =
+        [(element id, He value)], `hn_items_per_layer[l]` = [(node id, Hn value)] of layer l (0 first), each in key
+        order.  Decoding happens on the GPU (sdb_hnsw_load_staged).  Mirrors Hnsw::check_state + HnswLayer::load
+        (hnsw/mod.rs:187-224, hnsw/layer.rs:505-560) for indexes without legacy Hl chunks."""
+        from . import staging as S
+        st = S.parse_hnsw_state(state_value)
+        if st["layer0"]["chunks"] or any(l["chunks"] for l in st["layers"]):
+            raise L.SdbError(L.SDB_EUNSUPPORTED, "legacy Hl chunks present: run the reference's migration first")
+        nl = 1 + len(st["layers"])
+        if len(hn_items_per_layer) != nl:
+            raise L.SdbError(L.SDB_EINVAL, f"state names {nl} layers, {len(hn_items_per_layer)} given")
+        self = cls.__new__(cls)
+        self.ctx, self.metric, self.dim, self.elem_docs = ctx, metric.upper(), int(dim), elem_docs
+        self.n = int(st["next_element_id"])
+        vb, vo, vi = S.pack_values(he_items)
+        packs = [S.pack_values(it) for it in hn_items_per_layer]
+        NB = (C.c_void_p * nl)(*[p[0].ctypes.data for p in packs])
+        NO = (C.c_void_p * nl)(*[p[1].ctypes.data for p in packs])
+        NI = (C.c_void_p * nl)(*[p[2].ctypes.data for p in packs])
+        NN = (C.c_uint64 * nl)(*[len(it) for it in hn_items_per_layer])
+        self.h = C.c_void_p()
+        bad = C.c_uint64(0)
+        ep = -1 if st["enter_point"] is None else int(st["enter_point"])
+        L.check(L.lib().sdb_hnsw_load_staged(ctx.h, self.dim, L.METRIC[self.metric], self.n, C.c_void_p(vb.ctypes.data),
+                                             C.c_void_p(vo.ctypes.data), C.c_void_p(vi.ctypes.data), len(he_items), nl,
+                                             NB, NO, NI, NN, ep, C.byref(self.h), C.byref(bad)))
+        self.n_bad = bad.value
+        return self
+
     def search_graph(self, queries, k, ef, counters=False):
         q = np.ascontiguousarray(queries, np.float32)
         if q.ndim == 1:

@@ -21,6 +21,12 @@ class Distance:
     """catalog::Distance (catalog/schema/index.rs:247-284); Debug names as printed by EXPLAIN."""
     Cosine = "Cosine"
     Euclidean = "Euclidean"
+    Manhattan = "Manhattan"      # the next four are ranked by the exact kernel only (no screen)
+    Chebyshev = "Chebyshev"
+    Hamming = "Hamming"
+    Pearson = "Pearson"
+    Minkowski = "Minkowski"      # not on the GPU path: VectorColumn raises SDB_EUNSUPPORTED
+    Jaccard = "Jaccard"          # idem
 
 
 class KnnContext(dict):
@@ -116,6 +122,36 @@ class KnnTopK:
         rows, dist, cnt = self._column.knn(np.asarray([self.query_vector], np.float64), self.k)
         out = []
         for j in range(int(cnt[0])):
+            rec = self._records[int(rows[0, j])]
+            if self.knn_context is not None and isinstance(rec, dict) and "id" in rec:
+                self.knn_context.insert(rec["id"], float(dist[0, j]))
+            out.append(rec)
+        return out
+
+
+class KnnBruteForceLegacy(KnnTopK):
+    """The legacy two-pass brute force of the old executor: QueryExecutor::knn (idx/planner/executor.rs:283-311)
+    feeds every row's distance to a KnnPriorityList (idx/planner/knn.rs:11-106); the second pass re-iterates the
+    table and keeps the rows the list retained, so the result comes back in TABLE order, with the distances served
+    by vector::distance::knn() (fnc/vector.rs:79-101) from KnnBruteForceResults::get_dist.
+
+    The retained set is the k nearest; when several rows tie at the k-th distance the reference keeps an arbitrary
+    subset of that tie group (`HashSet` iteration order, knn.rs:85-93).  This mirror resolves the tie by scan order
+    (a valid outcome of the reference), which makes it the GPU top-k followed by a re-sort on scan position."""
+
+    def name(self):
+        return "KnnBruteForce"
+
+    def execute(self):
+        if self._column is None:
+            self._column = self._stage()
+        if self._column is None or self.k == 0:
+            return []
+        rows, dist, cnt = self._column.knn(np.asarray([self.query_vector], np.float64), self.k)
+        n = int(cnt[0])
+        order = np.argsort(rows[0, :n], kind="stable")
+        out = []
+        for j in order:
             rec = self._records[int(rows[0, j])]
             if self.knn_context is not None and isinstance(rec, dict) and "id" in rec:
                 self.knn_context.insert(rec["id"], float(dist[0, j]))

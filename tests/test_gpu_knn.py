@@ -220,3 +220,86 @@ def test_approximate_mode_skips_the_fallback_but_stays_accurate(ctx):
     for q in range(12):
         r, d = O.knn_topk(corpus, queries[q], "cosine", 10)
         assert list(rows2[q]) == list(r)
+
+
+@pytest.mark.parametrize("metric", ["MANHATTAN", "CHEBYSHEV", "HAMMING", "PEARSON"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_other_distance_metrics_through_the_exact_kernel(ctx, metric, dtype):
+    # Distance::compute catalog/schema/index.rs:287-303 -- the metrics without a screen are ranked by the exact kernel
+    rng = np.random.default_rng(len(metric) + (dtype == np.float64))
+    for dim in (1, 5, 33, 1100):
+        n = 3000
+        corpus = rng.integers(-3, 4, (n, dim)).astype(dtype) if metric == "HAMMING" else \
+            rng.uniform(-20, 20, (n, dim)).astype(dtype)
+        queries = rng.integers(-3, 4, (2, dim)).astype(np.float64) if metric == "HAMMING" else \
+            rng.uniform(-20, 20, (2, dim))
+        if dim >= 5:
+            corpus[7] = 0.0           # constant row: pearson 0/0 -> generated (negative) NaN sorts first
+            corpus[11, 0] = np.nan    # data NaN
+            corpus[13, 1] = -0.0
+        skip = np.zeros(n, np.uint8)
+        skip[5] = 1
+        col = make_col(ctx, corpus, metric, skip=skip)
+        for k in (1, 10, 300):
+            check(col, corpus, queries, metric, k, skip=skip)
+        assert col.stats()["n_fallback"] == 2
+
+
+def test_unsupported_metrics_fail_loudly(ctx):
+    from surrealdb_b200 import VectorColumn
+    for metric in ("MINKOWSKI", "JACCARD"):
+        with pytest.raises(Exception, match="not implemented on the GPU path"):
+            VectorColumn(ctx, 4, metric, "F32", capacity=4)
+
+
+def test_legacy_two_pass_bruteforce_returns_table_order(ctx):
+    # QueryExecutor::knn + KnnPriorityList (idx/planner/executor.rs:283-311, idx/planner/knn.rs:11-106)
+    from surrealdb_b200 import KnnBruteForceLegacy, KnnContext
+    rng = np.random.default_rng(8)
+    pts = rng.integers(-3, 4, (300, 4)).astype(np.float64)          # many exact ties
+    recs = [{"id": f"pts:{i}", "point": list(map(float, p))} for i, p in enumerate(pts)]
+    recs[5] = {"id": "pts:5", "point": "not a vector"}
+    q = [0.5, 0.0, 1.0, -1.0]
+    for k in (1, 7, 40):
+        kc = KnnContext()
+        out = KnnBruteForceLegacy(recs, "point", q, k, "Euclidean", ctx=ctx).with_knn_context(kc).execute()
+        d = [None if i == 5 else O.f64_euclidean(pts[i], np.asarray(q)) for i in range(len(recs))]
+        must, tie, left = O.knn_priority_list(d, k)
+        got = [int(r["id"].split(":")[1]) for r in out]
+        assert got == sorted(got) and len(got) == len(must) + left                  # table order, k rows
+        assert set(must) <= set(got) and set(got) - set(must) <= set(tie)
+        assert all(kc[f"pts:{r}"] == d[r] for r in got)                             # vector::distance::knn()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_projected_vector_functions_match_the_reference_arithmetic(ctx, dtype):
+    # SELECT vector::<fn>(emb, $q) FROM t  (fnc/vector.rs) as one columnar pass
+    rng = np.random.default_rng(21)
+    for dim in (3, 64, 257):
+        n = 700
+        corpus = rng.uniform(-20, 20, (n, dim)).astype(dtype)
+        corpus[3] = 0.0
+        corpus[4, 1] = np.nan
+        q = rng.uniform(-20, 20, dim)
+        skip = np.zeros(n, np.uint8)
+        skip[9] = 1
+        col = make_col(ctx, corpus, "COSINE", skip=skip)
+        c64 = corpus.astype(np.float64)
+        for fn in ("COSINE", "EUCLIDEAN", "MANHATTAN", "CHEBYSHEV", "HAMMING", "PEARSON"):
+            got = col.project(fn, q)
+            want = np.array([O.f64_metric(fn.lower(), c64[r], q) for r in range(n)])
+            want[9] = np.nan
+            assert got.tobytes() == want.tobytes(), fn
+        got = col.project("SIMILARITY_COSINE", q)
+        for r in (0, 1, 2, 3, 4, 50, n - 1):
+            st, v = O.num_metric("cosine_similarity", list(c64[r]), list(q))
+            assert np.float64(v).tobytes() == got[r].tobytes() or (np.isnan(v) and np.isnan(got[r])), r
+        got = col.project("DOT", q)
+        for r in (0, 1, 2, 3, 50, n - 1):
+            st, v = O.num_metric("dot", list(c64[r]), list(q))
+            assert float(v) == got[r], r
+        got = col.project("MAGNITUDE")
+        for r in (0, 1, 3, 50, n - 1):
+            assert O.num_magnitude(list(c64[r])) == got[r], r
+    with pytest.raises(Exception, match="same dimension"):
+        col.project("DOT", np.zeros(5))

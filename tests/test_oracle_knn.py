@@ -97,3 +97,20 @@ def test_batch_driver_equals_single():
     for i in range(7):
         r, d = O.knn_topk(corpus, qs[i], "cosine", 5)
         assert list(rows[i]) == list(r) and list(dist[i]) == list(d)
+
+
+def test_legacy_priority_list_keeps_the_k_nearest_with_an_arbitrary_boundary_tie():
+    # idx/planner/knn.rs:11-106 -- with distinct distances it is the plain top-k; ties at the boundary are a free choice
+    rng = np.random.default_rng(5)
+    for trial in range(200):
+        n, k = int(rng.integers(1, 40)), int(rng.integers(1, 8))
+        d = [float(x) for x in rng.integers(0, 6 if trial % 2 else 1000, n)]
+        must, tie, left = O.knn_priority_list(d, k)
+        order = sorted(range(n), key=lambda r: (d[r], r))
+        kth = d[order[min(k, n) - 1]]
+        assert sorted(must) == sorted(r for r in range(n) if d[r] < kth or (d[r] == kth and not tie))[:len(must)]
+        assert all(d[r] == kth for r in tie)
+        assert len(must) + left == min(k, n)
+        # KnnTopK's answer (ties by scan order) is one of the legacy path's possible answers
+        topk = set(order[:k])
+        assert set(must) <= topk and topk - set(must) <= set(tie)

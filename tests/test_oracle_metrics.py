@@ -163,3 +163,22 @@ def test_f32_lane_order_documented_shape():
     ref = 1.0 - float(np.dot(a.astype(np.float64), b.astype(np.float64))) / (
         np.linalg.norm(a.astype(np.float64)) * np.linalg.norm(b.astype(np.float64)))
     assert abs(got - ref) <= 1e-5 * max(1.0, abs(ref))
+
+
+@pytest.mark.parametrize("metric,num", [("manhattan", "manhattan"), ("chebyshev", "chebyshev"), ("hamming", "hamming"),
+                                        ("pearson", "pearson"), ("cosine", "cosine_distance"), ("euclidean", "euclidean")])
+def test_all_float_fast_metrics_equal_number_path(metric, num):
+    rng = np.random.default_rng(17)
+    for d in (1, 2, 9, 128):
+        a = rng.uniform(-20, 20, d)
+        b = rng.uniform(-20, 20, d)
+        if metric == "hamming":
+            b[::2] = a[::2]
+        st, v = O.num_metric(num, list(a), list(b))
+        got = O.f64_metric(metric, a, b)
+        assert (math.isnan(got) and math.isnan(float(v))) or got == float(v), (metric, d, got, v)
+    # the reference's own KATs through the fast path (function.rs)
+    assert O.f64_metric("manhattan", [1.1, 2, 3.3], [4, 5.5, 6.6]) == 9.7
+    assert O.f64_metric("chebyshev", [1.1, 2.2, 3], [4, 5.5, 6.6]) == 3.5999999999999996
+    assert O.f64_metric("pearson", [1, 2, 3, 4, 5], [1, 2.5, 3.5, 4.2, 5.1]) == 0.9894065340659606
+    assert O.f64_metric("hamming", [1.1, 2.2, -3.3], [1.1, 2, -3.3]) == 1.0
