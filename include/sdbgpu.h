@@ -161,6 +161,15 @@ sdb_status sdb_hnsw_load(sdb_ctx*, uint32_t dim, sdb_metric, uint64_t n_elems, c
                          uint32_t n_layers, const uint64_t* const* row_ptr, const uint32_t* const* col_idx,
                          int64_t entry_point, sdb_hnsw** out);
 void sdb_hnsw_destroy(sdb_hnsw*);
+/* Filtered search: replaces Hnsw::knn_search_with_filter (hnsw/mod.rs:488-515; HnswLayer::search_single_with_filter /
+ * search_with_filter / add_if_truthy, hnsw/layer.rs:111-149,226-306) when the WHERE condition has been evaluated
+ * ahead of time into a predicate mask: truthy[e] != 0 iff HnswTruthyDocumentFilter::check_any_doc_truthy
+ * (hnsw/filter.rs:52-136) holds for element e (host, n_elems bytes).  The descent through the upper layers is
+ * unfiltered, as in the reference.  SDB_EOVERFLOW = the filter is too selective for the on-chip candidate window
+ * (the caller keeps the CPU path for that query). */
+sdb_status sdb_hnsw_search_filtered(sdb_hnsw*, const float* queries, uint32_t nq, uint32_t k, uint32_t ef,
+                                    const uint8_t* truthy, uint64_t* out_elems, double* out_dist, uint32_t* out_count,
+                                    uint64_t* out_counters);
 
 /* ---- staging: the reference's persisted HNSW state -> device.  These replace the per-key
  *      decode loops of HnswLayer::load (idx/trees/hnsw/layer.rs:526-540, UndirectedGraph::load_node

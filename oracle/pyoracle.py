@@ -81,6 +81,7 @@ def lib():
         L.orc_hnsw_layer_edges.restype = C.c_size_t
         L.orc_hnsw_vectors.restype = C.c_void_p
         L.orc_hnsw_search_csr.restype = C.c_size_t
+        L.orc_hnsw_search_csr_filtered.restype = C.c_size_t
         L.orc_vec_knn_f32.restype = C.c_size_t
         L.orc_graph_hop.restype = C.c_uint64
         L.orc_graph_collect.restype = C.c_uint64
@@ -311,8 +312,9 @@ class Hnsw:
                 "metric": self.metric}
 
 
-def hnsw_search_csr(graph, q, k, ef):
-    """Hnsw::knn_search over an exported/imported graph. -> (ids, dist, (visited, expanded))"""
+def hnsw_search_csr(graph, q, k, ef, truthy=None):
+    """Hnsw::knn_search (truthy=None) / knn_search_with_filter (truthy = one byte per element) over an
+    exported/imported graph. -> (ids, dist, (visited, expanded))"""
     vec = np.ascontiguousarray(graph["vectors"], np.float32)
     n, dim = vec.shape
     nl = len(graph["layers"])
@@ -324,6 +326,15 @@ def hnsw_search_csr(graph, q, k, ef):
     ids = np.zeros(max(k, 1), np.uint64)
     dist = np.zeros(max(k, 1), np.float64)
     cnt = np.zeros(2, np.uint64)
+    if truthy is not None:
+        t = np.ascontiguousarray(truthy, np.uint8)
+        assert t.size == n
+        c = lib().orc_hnsw_search_csr_filtered(_p(vec, C.c_float), C.c_size_t(n), C.c_size_t(dim),
+                                               C.c_int(METRICS[graph["metric"]]), C.c_size_t(nl), RP, CI,
+                                               C.c_int64(graph["entry_point"]), _p(q, C.c_float), C.c_size_t(k),
+                                               C.c_size_t(ef), _p(t, C.c_uint8), _p(ids, C.c_uint64),
+                                               _p(dist, C.c_double), _p(cnt, C.c_uint64))
+        return ids[:c].copy(), dist[:c].copy(), (int(cnt[0]), int(cnt[1]))
     c = lib().orc_hnsw_search_csr(_p(vec, C.c_float), C.c_size_t(n), C.c_size_t(dim), C.c_int(METRICS[graph["metric"]]),
                                   C.c_size_t(nl), RP, CI, C.c_int64(graph["entry_point"]), _p(q, C.c_float),
                                   C.c_size_t(k), C.c_size_t(ef), _p(ids, C.c_uint64), _p(dist, C.c_double),

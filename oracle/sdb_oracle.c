@@ -901,6 +901,55 @@ static void layer_search(const float* vectors, size_t dim, int metric, const adj
     }
   }
 }
+/* HnswLayer::search_with_filter + add_if_truthy  layer.rs:226-306 (pending_docs = None).  `truthy[e]` restates
+ * HnswTruthyDocumentFilter::check_any_doc_truthy (hnsw/filter.rs:52-136) evaluated ahead of time per element. */
+static void layer_search_with_filter(const float* vectors, size_t dim, int metric, const adj_src* adj, const float* q,
+                                     orc_dpq* candidates, vset* visited, orc_dpq* w, size_t ef,
+                                     const uint8_t* truthy, uint64_t* counters) {
+  double fq = 1.7976931348623157e308;
+  if (w->n) fq = w->e[w->n - 1].d;
+  double cd;
+  uint64_t c;
+  while (dpq_pop_first(candidates, &cd, &c)) {
+    if (cd > fq) break;
+    const uint32_t* nb;
+    size_t deg = adj_get(adj, c, &nb);
+    if (deg == (size_t)-1) continue;
+    if (counters) counters[1]++;
+    for (size_t i = 0; i < deg; i++) {
+      uint64_t e = nb[i];
+      if (!vset_insert(visited, e)) continue;
+      double ed = orc_vec_distance_f32(metric, vectors + e * dim, q, dim);
+      if (counters) counters[0]++;
+      if (ed < fq || w->n < ef) {
+        dpq_push(candidates, ed, e);
+        if (truthy[e]) { /* add_if_truthy */
+          dpq_push(w, ed, e);
+          if (w->n > ef) {
+            double dd;
+            uint64_t ii;
+            dpq_pop_last(w, &dd, &ii);
+          }
+          fq = w->e[w->n - 1].d;
+        }
+      }
+    }
+  }
+}
+/* search_single_with_filter  layer.rs:111-149 */
+static void layer_search_single_with_filter(const float* vectors, size_t n, size_t dim, int metric, const adj_src* adj,
+                                            const float* q, double ep_dist, uint64_t ep, size_t ef,
+                                            const uint8_t* truthy, orc_dpq* w_out, uint64_t* counters, vset* visp) {
+  vset_reset(visp, n);
+  vset_insert(visp, ep);
+  orc_dpq cand;
+  dpq_init(&cand);
+  dpq_push(&cand, ep_dist, ep);
+  dpq_init(w_out);
+  if (truthy[ep]) dpq_push(w_out, ep_dist, ep);
+  layer_search_with_filter(vectors, dim, metric, adj, q, &cand, visp, w_out, ef, truthy, counters);
+  dpq_destroy(&cand);
+}
 /* search_single  layer.rs:76-90 : returns w (caller destroys) */
 static void layer_search_single(const float* vectors, size_t n, size_t dim, int metric, const adj_src* adj,
                                 const float* q, double ep_dist, uint64_t ep, size_t ef, orc_dpq* w_out,
@@ -1102,6 +1151,39 @@ uint64_t orc_hnsw_insert(orc_hnsw* h, const float* v) { return orc_hnsw_insert_l
 static size_t hnsw_search_csr_vs(const float*, size_t, size_t, int, size_t, const uint64_t* const*,
                                  const uint32_t* const*, int64_t, const float*, size_t, size_t, uint64_t*,
                                  double*, uint64_t*, vset*);
+/* Hnsw::knn_search_with_filter  hnsw/mod.rs:488-515 over an imported graph; truthy: one byte per element */
+size_t orc_hnsw_search_csr_filtered(const float* vectors, size_t n, size_t dim, int metric, size_t n_layers,
+                                    const uint64_t* const* row_ptr, const uint32_t* const* col_idx,
+                                    int64_t entry_point, const float* q, size_t k, size_t ef, const uint8_t* truthy,
+                                    uint64_t* out_ids, double* out_dist, uint64_t* counters) {
+  if (entry_point < 0 || k == 0) return 0;
+  vset lv;
+  memset(&lv, 0, sizeof(lv));
+  uint64_t ep = (uint64_t)entry_point;
+  double ep_dist = orc_vec_distance_f32(metric, vectors + ep * dim, q, dim);
+  if (counters) counters[0]++;
+  for (size_t l = n_layers - 1; l >= 1; l--) { /* search_ep is NOT filtered  hnsw/mod.rs:521-548 */
+    adj_src a = {NULL, row_ptr[l], col_idx[l]};
+    orc_dpq w;
+    layer_search_single(vectors, n, dim, metric, &a, q, ep_dist, ep, 1, &w, counters, &lv);
+    if (w.n) {
+      ep_dist = w.e[0].d;
+      ep = w.e[0].id;
+    }
+    dpq_destroy(&w);
+  }
+  adj_src a0 = {NULL, row_ptr[0], col_idx[0]};
+  orc_dpq w;
+  layer_search_single_with_filter(vectors, n, dim, metric, &a0, q, ep_dist, ep, ef, truthy, &w, counters, &lv);
+  size_t c = w.n < k ? w.n : k;
+  for (size_t i = 0; i < c; i++) {
+    out_ids[i] = w.e[i].id;
+    out_dist[i] = w.e[i].d;
+  }
+  dpq_destroy(&w);
+  free(lv.stamp);
+  return c;
+}
 size_t orc_hnsw_search_csr(const float* vectors, size_t n, size_t dim, int metric, size_t n_layers,
                            const uint64_t* const* row_ptr, const uint32_t* const* col_idx, int64_t entry_point,
                            const float* q, size_t k, size_t ef, uint64_t* out_ids, double* out_dist,

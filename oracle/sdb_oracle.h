@@ -150,6 +150,12 @@ size_t orc_hnsw_search_csr(const float* vectors, size_t n, size_t dim, int metri
                            const uint64_t* const* row_ptr, const uint32_t* const* col_idx,
                            int64_t entry_point, const float* q, size_t k, size_t ef,
                            uint64_t* out_ids, double* out_dist, uint64_t* counters /* [2] nullable */);
+/* Hnsw::knn_search_with_filter (hnsw/mod.rs:488-515, layer.rs:111-149,226-306) over an imported graph;
+ * truthy[e] != 0 iff any document of element e passes the WHERE condition (hnsw/filter.rs:52-136). */
+size_t orc_hnsw_search_csr_filtered(const float* vectors, size_t n, size_t dim, int metric, size_t n_layers,
+                                    const uint64_t* const* row_ptr, const uint32_t* const* col_idx,
+                                    int64_t entry_point, const float* q, size_t k, size_t ef, const uint8_t* truthy,
+                                    uint64_t* out_ids, double* out_dist, uint64_t* counters /* [2] nullable */);
 /* TestCollection::knn  hnsw/mod.rs:1186-1197: brute force through KnnResultBuilder, docs = row ids */
 size_t orc_vec_knn_f32(const float* corpus, size_t n, size_t dim, int metric, const float* q, size_t k,
                        uint64_t* out_ids, double* out_dist);

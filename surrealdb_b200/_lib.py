@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "sdb_ctx_kernel_launches", "sdb_ctx_stream", "sdb_corpus_create", "sdb_corpus_destroy", "sdb_corpus_append",
     "sdb_corpus_append_device", "sdb_corpus_append_synthetic", "sdb_corpus_set_skip", "sdb_corpus_finalize",
     "sdb_corpus_rows", "sdb_corpus_set_screen", "sdb_corpus_set_exact", "sdb_knn_bruteforce", "sdb_knn_bruteforce_device",
-    "sdb_knn_last_stats", "sdb_corpus_project", "sdb_topk_merge_device", "sdb_hnsw_load", "sdb_hnsw_destroy", "sdb_stage_decode_vectors", "sdb_stage_decode_nodes", "sdb_hnsw_load_staged", "sdb_hnsw_search", "sdb_hnsw_select_neighbors",
+    "sdb_knn_last_stats", "sdb_corpus_project", "sdb_topk_merge_device", "sdb_hnsw_load", "sdb_hnsw_destroy", "sdb_stage_decode_vectors", "sdb_stage_decode_nodes", "sdb_hnsw_load_staged", "sdb_hnsw_search", "sdb_hnsw_search_filtered", "sdb_hnsw_select_neighbors",
     "sdb_graph_load_csr", "sdb_graph_destroy", "sdb_graph_expand", "sdb_graph_expand_device", "sdb_device_free", "sdb_graph_collect", "sdb_free",
 ]
 
@@ -88,6 +88,7 @@ def lib():
     L.sdb_hnsw_load_staged.argtypes = [vp, u32, i32, u64, vp, vp, vp, u64, u32, vp, vp, vp, vp, C.c_int64, C.POINTER(vp),
                                        C.POINTER(u64)]
     L.sdb_hnsw_search.argtypes = [vp, vp, u32, u32, u32, vp, vp, vp, vp]
+    L.sdb_hnsw_search_filtered.argtypes = [vp, vp, u32, u32, u32, vp, vp, vp, vp, vp]
     L.sdb_hnsw_select_neighbors.argtypes = [vp, vp, u32, i32, u64, u64, vp, vp, u32, u32, i32, vp, vp]
     L.sdb_graph_load_csr.argtypes = [vp, u64, vp, vp, C.POINTER(vp)]
     L.sdb_graph_destroy.argtypes = [vp]

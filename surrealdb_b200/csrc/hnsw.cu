@@ -167,6 +167,8 @@ struct HnswParams {
   int64_t entry;
   const float* queries;
   uint32_t nq, k, ef;
+  uint32_t ccap;          // capacity of the candidate window (entries)
+  const uint8_t* truthy;  // non-null: knn_search_with_filter -- one byte per element (layer 0 only)
   uint64_t* visited;
   uint32_t table_log2;
   uint32_t gen_base, gens_per_warp;
@@ -181,7 +183,7 @@ template <bool COSINE>
 __global__ void __launch_bounds__(HN_WARPS * 32) hnsw_search_kernel(HnswParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t ccap = 2 * P.ef + 34, wcap = P.ef + 2;
+  const uint32_t ccap = P.ccap, wcap = P.ef + 2;
   // per-warp shared layout
   const size_t per_warp = sizeof(float) * ((P.dim + 3) & ~3u) + sizeof(float) * 32 * 33 + (sizeof(uint64_t) + sizeof(uint32_t)) * (ccap + wcap) + 64;
   uint8_t* base = smem_raw + (size_t)warp * ((per_warp + 15) & ~size_t(15));
@@ -238,9 +240,14 @@ __global__ void __launch_bounds__(HN_WARPS * 32) hnsw_search_kernel(HnswParams P
           }
           __syncwarp();
         }
+        // search_single_with_filter (layer.rs:111-149): w starts with ep only if one of its documents is truthy
+        const uint8_t* truthy = layer == 0 ? P.truthy : nullptr;
         cn = sorted_insert(c_key, c_id, head, cn, dist_key(ep_d), ep);
-        wn = sorted_insert(w_key, w_id, 0, wn, dist_key(ep_d), ep);
-        double fd = ep_d;  // w.peek_last_dist()
+        double fd = 1.7976931348623157e308;  // w.peek_last_dist().unwrap_or(f64::MAX)
+        if (!truthy || truthy[ep]) {
+          wn = sorted_insert(w_key, w_id, 0, wn, dist_key(ep_d), ep);
+          fd = ep_d;
+        }
         while (head < cn) {
           const uint64_t ckey = c_key[head];
           const uint32_t cid = c_id[head];
@@ -307,9 +314,11 @@ __global__ void __launch_bounds__(HN_WARPS * 32) hnsw_search_kernel(HnswParams P
                   }
                 }
                 cn = sorted_insert(c_key, c_id, head, cn, key, idi);
-                wn = sorted_insert(w_key, w_id, 0, wn, key, idi);
-                if (wn > ef) wn--;  // pop_last
-                fd = key_to_double(w_key[wn - 1]);
+                if (!truthy || truthy[idi]) {  // add_if_truthy  layer.rs:277-306
+                  wn = sorted_insert(w_key, w_id, 0, wn, key, idi);
+                  if (wn > ef) wn--;  // pop_last
+                  fd = key_to_double(w_key[wn - 1]);
+                }
                 if (wn == ef) {  // candidates beyond f can never be expanded any more
                   const uint64_t fkey = w_key[wn - 1];
                   while (cn > head && c_key[cn - 1] > fkey) cn--;
@@ -319,8 +328,10 @@ __global__ void __launch_bounds__(HN_WARPS * 32) hnsw_search_kernel(HnswParams P
           }
         }
         // next layer starts from w.peek_first()                                mod.rs:530-538
-        ep = w_id[0];
-        ep_d = key_to_double(w_key[0]);
+        if (wn) {
+          ep = w_id[0];
+          ep_d = key_to_double(w_key[0]);
+        }
         if (layer == 0) {
           n_out = wn < P.k ? wn : P.k;  // to_vec_limit(k)
           for (uint32_t i = lane; i < n_out; i += 32) {
@@ -607,8 +618,9 @@ sdb_status sdb_hnsw_select_neighbors(sdb_ctx* ctx, const float* d_vectors, uint3
   return SDB_OK;
 }
 
-sdb_status sdb_hnsw_search(sdb_hnsw* h, const float* queries, uint32_t nq, uint32_t k, uint32_t ef, uint64_t* out_elems,
-                           double* out_dist, uint32_t* out_count, uint64_t* out_counters) {
+static sdb_status hnsw_search_impl(sdb_hnsw* h, const float* queries, uint32_t nq, uint32_t k, uint32_t ef,
+                                   const uint8_t* truthy, uint64_t* out_elems, double* out_dist, uint32_t* out_count,
+                                   uint64_t* out_counters) {
   if (!h || (nq && (!queries || !out_count)) || (nq && k && (!out_elems || !out_dist))) return SDB_EINVAL;
   if (nq == 0) return SDB_OK;
   if (k == 0 || ef == 0) {  // to_vec_limit(0) underflows in the reference; we return nothing
@@ -623,7 +635,17 @@ sdb_status sdb_hnsw_search(sdb_hnsw* h, const float* queries, uint32_t nq, uint3
   std::lock_guard<std::mutex> guard(h->mu);
   SDB_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  const uint32_t ccap = 2 * ef + 34, wcap = ef + 2;
+  // unfiltered: live candidates are a subset of w plus ties, 2*ef+34 is ample.  Filtered: every admitted element is a
+  // candidate but only truthy ones enter w, so the window is sized for a selectivity down to ~1/16 (more = EOVERFLOW)
+  uint32_t ccap = 2 * ef + 34;
+  const uint32_t wcap = ef + 2;
+  if (truthy) {
+    ccap = 16 * ef + 34;
+    if (ccap < 1024) ccap = 1024;
+    const size_t fixed = sizeof(float) * ((h->dim + 3) & ~3u) + sizeof(float) * 32 * 33 + 12 * (size_t)wcap + 64 + 16;
+    const size_t room = (220 * 1024) / HN_WARPS;
+    if (fixed + 12 * (size_t)ccap > room) ccap = room > fixed + 12 * (2 * (size_t)ef + 34) ? (uint32_t)((room - fixed) / 12) : 2 * ef + 34;
+  }
   size_t per_warp = sizeof(float) * ((h->dim + 3) & ~3u) + sizeof(float) * 32 * 33 + 12 * (size_t)(ccap + wcap) + 64;
   per_warp = (per_warp + 15) & ~size_t(15);
   const size_t smem = per_warp * HN_WARPS;
@@ -641,6 +663,7 @@ sdb_status sdb_hnsw_search(sdb_hnsw* h, const float* queries, uint32_t nq, uint3
   // visited tables: one per resident warp; 16 x the worst-case expansion of a typical walk, >= 2^13 slots
   uint32_t tl = 13;
   while ((1u << tl) < ef * 64u * 4u && tl < 20) tl++;
+  if (truthy) tl = tl + 3 > 18 ? (tl > 18 ? tl : 18) : tl + 3;  // filtered walks visit ~1/selectivity more elements
   const uint32_t n_tables = grid * HN_WARPS;
   if (!h->d_visited || h->table_log2 != tl || h->n_tables < n_tables) {
     cudaFree(h->d_visited);
@@ -671,7 +694,14 @@ sdb_status sdb_hnsw_search(sdb_hnsw* h, const float* queries, uint32_t nq, uint3
   SDB_CUDA(cudaMallocAsync(&d_ovf, 4, st));
   SDB_CUDA(cudaMemsetAsync(d_ovf, 0, 4, st));
   SDB_CUDA(cudaMemcpyAsync(d_q, queries, sizeof(float) * (size_t)nq * h->dim, cudaMemcpyHostToDevice, st));
+  uint8_t* d_truthy = nullptr;
+  if (truthy) {
+    SDB_CUDA(cudaMallocAsync(&d_truthy, h->n ? h->n : 1, st));
+    SDB_CUDA(cudaMemcpyAsync(d_truthy, truthy, h->n, cudaMemcpyHostToDevice, st));
+  }
   HnswParams P;
+  P.ccap = ccap;
+  P.truthy = d_truthy;
   P.vec = h->d_vec;
   P.sumsq = h->d_sumsq;
   P.rp = h->d_rp;
@@ -708,13 +738,33 @@ sdb_status sdb_hnsw_search(sdb_hnsw* h, const float* queries, uint32_t nq, uint3
   cudaFreeAsync(d_cnt, st);
   cudaFreeAsync(d_ctr, st);
   cudaFreeAsync(d_ovf, st);
+  if (d_truthy) cudaFreeAsync(d_truthy, st);
   SDB_CUDA(cudaStreamSynchronize(st));
   SDB_CUDA(cudaGetLastError());
   if (ovf == 1) {
-    set_error("hnsw: visited table overflow (ef too large for the per-query table)");
+    set_error("hnsw: visited table overflow (ef too large, or filter too selective, for the per-query table)");
+    return SDB_EOVERFLOW;
+  }
+  if (ovf == 2) {
+    set_error("hnsw: candidate window overflow (filter too selective for ef %u): use the CPU path for this query", ef);
     return SDB_EOVERFLOW;
   }
   return SDB_OK;
+}
+
+sdb_status sdb_hnsw_search(sdb_hnsw* h, const float* queries, uint32_t nq, uint32_t k, uint32_t ef, uint64_t* out_elems,
+                           double* out_dist, uint32_t* out_count, uint64_t* out_counters) {
+  return hnsw_search_impl(h, queries, nq, k, ef, nullptr, out_elems, out_dist, out_count, out_counters);
+}
+
+sdb_status sdb_hnsw_search_filtered(sdb_hnsw* h, const float* queries, uint32_t nq, uint32_t k, uint32_t ef,
+                                    const uint8_t* truthy, uint64_t* out_elems, double* out_dist, uint32_t* out_count,
+                                    uint64_t* out_counters) {
+  if (!truthy) {
+    set_error("sdb_hnsw_search_filtered: truthy mask is NULL (use sdb_hnsw_search)");
+    return SDB_EINVAL;
+  }
+  return hnsw_search_impl(h, queries, nq, k, ef, truthy, out_elems, out_dist, out_count, out_counters);
 }
 
 }  // extern "C"

@@ -63,7 +63,8 @@ class HnswIndex:
         self.n_bad = bad.value
         return self
 
-    def search_graph(self, queries, k, ef, counters=False):
+    def search_graph(self, queries, k, ef, counters=False, truthy=None):
+        """truthy: optional predicate mask, one byte per element (Hnsw::knn_search_with_filter, hnsw/mod.rs:488-515)"""
         q = np.ascontiguousarray(queries, np.float32)
         if q.ndim == 1:
             q = q[None, :]
@@ -74,16 +75,35 @@ class HnswIndex:
         dist = np.zeros((nq, max(k, 1)), np.float64)
         cnt = np.zeros(nq, np.uint32)
         ctr = np.zeros((nq, 2), np.uint64)
-        L.check(L.lib().sdb_hnsw_search(self.h, C.c_void_p(q.ctypes.data), nq, int(k), int(ef), C.c_void_p(ids.ctypes.data),
-                                        C.c_void_p(dist.ctypes.data), C.c_void_p(cnt.ctypes.data),
-                                        C.c_void_p(ctr.ctypes.data)))
+        if truthy is not None:
+            t = np.ascontiguousarray(truthy, np.uint8)
+            if t.shape != (self.n,):
+                raise L.SdbError(L.SDB_EINVAL, f"predicate mask must have one byte per element ({self.n})")
+            L.check(L.lib().sdb_hnsw_search_filtered(self.h, C.c_void_p(q.ctypes.data), nq, int(k), int(ef),
+                                                     C.c_void_p(t.ctypes.data), C.c_void_p(ids.ctypes.data),
+                                                     C.c_void_p(dist.ctypes.data), C.c_void_p(cnt.ctypes.data),
+                                                     C.c_void_p(ctr.ctypes.data)))
+        else:
+            L.check(L.lib().sdb_hnsw_search(self.h, C.c_void_p(q.ctypes.data), nq, int(k), int(ef),
+                                            C.c_void_p(ids.ctypes.data), C.c_void_p(dist.ctypes.data),
+                                            C.c_void_p(cnt.ctypes.data), C.c_void_p(ctr.ctypes.data)))
         if counters:
             return ids, dist, cnt, ctr
         return ids, dist, cnt
 
-    def knn_search(self, query, k, ef):
-        """-> [(doc_id, distance)] ordered by (distance, doc id), at most k  (one query)"""
-        ids, dist, cnt = self.search_graph(np.asarray(query, np.float32)[None, :], k, ef)
+    def knn_search(self, query, k, ef, truthy_docs=None):
+        """-> [(doc_id, distance)] ordered by (distance, doc id), at most k  (one query).
+        truthy_docs: optional set of doc ids passing the WHERE condition (cond_filter of HnswIndex::knn_search,
+        hnsw/index.rs:270-335): an element enters the result if ANY of its docs is truthy
+        (HnswTruthyDocumentFilter::check_any_doc_truthy, hnsw/filter.rs:52-62); add_graph_results then adds ALL docs
+        of that element (hnsw/index.rs:454-475) -- the executor re-applies the WHERE clause downstream."""
+        truthy = None
+        if truthy_docs is not None:
+            truthy = np.zeros(self.n, np.uint8)
+            for e in range(self.n):
+                docs = [e] if self.elem_docs is None else self.elem_docs[e]
+                truthy[e] = any(d in truthy_docs for d in docs)
+        ids, dist, cnt = self.search_graph(np.asarray(query, np.float32)[None, :], k, ef, truthy=truthy)
         res = []  # KnnResultBuilder: BTreeSet<(dist, doc)>, pop the largest when over k; check_add uses `>`
         for j in range(int(cnt[0])):
             d, e = float(dist[0, j]), int(ids[0, j])

@@ -120,3 +120,50 @@ def test_gpu_batch_builder_gives_a_searchable_graph(ctx):
         bi, _ = O.vec_knn_f32(xh, qs[q], "euclidean", 10)
         hit += len(set(bi.tolist()) & set(ids[q, : cnt[q]].tolist()))
     assert hit / 2000.0 >= 0.75, hit / 2000.0
+
+
+@pytest.mark.parametrize("metric", ["euclidean", "cosine"])
+def test_filtered_walk_parity(ctx, metric):
+    # Hnsw::knn_search_with_filter (hnsw/mod.rs:488-515, layer.rs:226-306) with a precomputed predicate mask
+    from surrealdb_b200.hnsw import HnswIndex
+    rng = np.random.default_rng(77)
+    dim = 24
+    data = rng.uniform(-20, 20, (3000, dim)).astype(np.float32)
+    g = build(data, metric, m=8, efc=60)
+    idx = HnswIndex(ctx, g["vectors"], g["layers"], g["entry_point"], metric)
+    queries = rng.uniform(-20, 20, (48, dim)).astype(np.float32)
+    for sel in (1.0, 0.5, 0.2, 0.08, 0.0):
+        truthy = (rng.random(3000) < sel).astype(np.uint8)
+        for k, ef in ((10, 40), (3, 8), (10, 10)):
+            try:
+                ids, dist, cnt, ctr = idx.search_graph(queries, k, ef, counters=True, truthy=truthy)
+            except Exception as e:  # documented: a filter too selective for the on-chip window -> caller's CPU path
+                assert "SDB_EOVERFLOW" in str(e) and sel < 0.2, (sel, k, ef, str(e))
+                continue
+            for q in range(queries.shape[0]):
+                oi, od, oc = O.hnsw_search_csr(g, queries[q], k, ef, truthy=truthy)
+                assert cnt[q] == oi.size, (sel, k, ef, q)
+                assert list(ids[q, : cnt[q]]) == list(oi), (sel, k, ef, q)
+                assert dist[q, : cnt[q]].tobytes() == od.tobytes()
+                assert (int(ctr[q, 0]), int(ctr[q, 1])) == oc, (sel, k, ef, q)
+                assert all(truthy[int(e)] for e in ids[q, : cnt[q]])
+    # all-true mask == the unfiltered search
+    ones = np.ones(3000, np.uint8)
+    a = idx.search_graph(queries, 10, 40, truthy=ones)
+    b = idx.search_graph(queries, 10, 40)
+    assert a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes()
+
+
+def test_filtered_knn_search_expands_all_docs_of_truthy_elements(ctx):
+    from surrealdb_b200.hnsw import HnswIndex
+    rng = np.random.default_rng(5)
+    data = rng.uniform(-20, 20, (400, 8)).astype(np.float32)
+    g = build(data, "euclidean", m=8, efc=40)
+    elem_docs = [[2 * e, 2 * e + 1] for e in range(400)]      # two documents share every vector (docs.rs:161-176)
+    idx = HnswIndex(ctx, g["vectors"], g["layers"], g["entry_point"], "EUCLIDEAN", elem_docs=elem_docs)
+    truthy_docs = {2 * e for e in range(0, 400, 3)}
+    q = rng.uniform(-20, 20, 8).astype(np.float32)
+    res = idx.knn_search(q, 6, 40, truthy_docs=truthy_docs)
+    assert len(res) == 6
+    assert all((doc // 2) % 3 == 0 for doc, _ in res)          # every element has a truthy doc ...
+    assert any(doc % 2 == 1 for doc, _ in res)                 # ... and its other docs come along (index.rs:454-475)
