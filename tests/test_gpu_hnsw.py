@@ -162,8 +162,15 @@ def test_filtered_knn_search_expands_all_docs_of_truthy_elements(ctx):
     elem_docs = [[2 * e, 2 * e + 1] for e in range(400)]      # two documents share every vector (docs.rs:161-176)
     idx = HnswIndex(ctx, g["vectors"], g["layers"], g["entry_point"], "EUCLIDEAN", elem_docs=elem_docs)
     truthy_docs = {2 * e for e in range(0, 400, 3)}
-    q = rng.uniform(-20, 20, 8).astype(np.float32)
-    res = idx.knn_search(q, 6, 40, truthy_docs=truthy_docs)
-    assert len(res) == 6
-    assert all((doc // 2) % 3 == 0 for doc, _ in res)          # every element has a truthy doc ...
-    assert any(doc % 2 == 1 for doc, _ in res)                 # ... and its other docs come along (index.rs:454-475)
+    truthy = np.array([e % 3 == 0 for e in range(400)], np.uint8)
+    seen_pair = False
+    for q in rng.uniform(-20, 20, (20, 8)).astype(np.float32):
+        res = idx.knn_search(q, 6, 40, truthy_docs=truthy_docs)
+        # NB the reference may return fewer than k here: search_with_filter stops as soon as the nearest open
+        # candidate is farther than the farthest TRUTHY element found so far, even while w holds < ef (layer.rs:240-243)
+        oi, od, _ = O.hnsw_search_csr(g, q, 6, 40, truthy=truthy)
+        want = sorted((float(d), doc) for e, d in zip(oi, od) for doc in elem_docs[int(e)])[:6]
+        assert [(d, doc) for doc, d in res] == want
+        assert all((doc // 2) % 3 == 0 for doc, _ in res)          # every element has a truthy doc ...
+        seen_pair |= any(doc % 2 == 1 for doc, _ in res)           # ... and its other docs come along (index.rs:454-475)
+    assert seen_pair
