@@ -84,3 +84,34 @@ def test_pass_schedule_covers_every_tile_once():
             seen += [tile(p, w) for w in range(p[2])]
         assert sorted(seen) == list(range(T)), n_rows
         assert build(n_rows, 4096)[0][2] * TILE <= 4096
+
+
+def _build_c_driver(tmp_path):
+    import subprocess
+    so = _ensure_built()
+    exe = str(tmp_path / "abi_driver")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "abi_driver.c"), "-o", exe, so,
+                           "-Wl,-rpath," + os.path.dirname(so)])
+    return exe
+
+
+def test_header_is_plain_c_and_a_c_program_links(tmp_path):
+    import subprocess
+    import torch
+    exe = _build_c_driver(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    if not torch.cuda.is_available():
+        assert out.stdout.startswith("NO_GPU"), out.stdout  # refuses loudly, no CPU fallback
+
+
+@pytest.mark.gpu
+def test_c_driver_runs_the_three_paths_on_the_gpu(tmp_path):
+    import subprocess
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    exe = _build_c_driver(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ABI_DRIVER_OK" in out.stdout, (out.stdout, out.stderr)
