@@ -14,8 +14,26 @@ void set_error(const char* fmt, ...) {
 }
 
 
-static std::vector<PassDesc> build_passes(uint64_t n_rows, uint32_t cand_cap) {
+// schedule ratio: every pass looks at (R-1) x the rows seen so far; SDB_PASS_RATIO overrides it (tuning only)
+// Cost model (measured on B200): a pass costs a fixed ~0.1 ms (launch, pipeline fill, compaction)
+// plus the survivor appends, ~(R-1) * k' per query.  Large batches are append-dominated -> small R; small batches are
+// launch-dominated -> fewer, larger passes.
+static uint32_t pass_ratio(uint32_t nq) {
+  static int env = -1;
+  if (env < 0) {
+    env = 0;
+    if (const char* e = getenv("SDB_PASS_RATIO")) {
+      const int v = atoi(e);
+      if (v >= 2 && v <= 64) env = v;
+    }
+  }
+  if (env) return (uint32_t)env;
+  return nq >= 512 ? 4u : PASS_RATIO;
+}
+
+static std::vector<PassDesc> build_passes(uint64_t n_rows, uint32_t cand_cap, uint32_t nq) {
   std::vector<PassDesc> v;
+  const uint64_t PASS_RATIO = pass_ratio(nq);  // shadows the compile-time default
   const uint64_t T = (n_rows + TILE_ROWS - 1) / TILE_ROWS;
   if (T == 0) return v;
   const uint64_t max0 = cand_cap / TILE_ROWS;  // pass 0 appends every row it sees
@@ -25,7 +43,7 @@ static std::vector<PassDesc> build_passes(uint64_t n_rows, uint32_t cand_cap) {
   v.push_back(p0);
   for (uint64_t s = stride / PASS_RATIO; s >= 1; s /= PASS_RATIO) {
     const uint64_t M = (T + s - 1) / s;
-    PassDesc p{(uint32_t)s, 1u, (uint32_t)(M - (M + PASS_RATIO - 1) / PASS_RATIO)};
+    PassDesc p{(uint32_t)s, (uint32_t)PASS_RATIO, (uint32_t)(M - (M + PASS_RATIO - 1) / PASS_RATIO)};
     v.push_back(p);
     if (s == 1) break;
   }
@@ -67,7 +85,7 @@ static sdb_status knn_device_locked(Corpus* c, const double* d_queries, uint32_t
   if (c->dtype == SDB_F64 || c->special_overflow || k > 256 || !screenable) scr = SDB_SCREEN_NONE_EXACT;
   const uint32_t kp = k + (k > 54 ? k : 54) + (scr == SDB_SCREEN_TC_INT8 ? 64 : 0);  // looser screen => more slack
   uint32_t cap = 4096;
-  while (cap < 16 * kp) cap <<= 1;
+  while (cap < 2u * pass_ratio(nq) * kp && cap < 16384u) cap <<= 1;  // a pass appends ~(PASS_RATIO-1)*kp survivors per query
   SDB_TRY(scratch_for(c, nq, cap, kp));
   cap = c->sc_cap;
   SDB_TRY(prep_queries(c, d_queries, nq, st));
@@ -77,7 +95,7 @@ static sdb_status knn_device_locked(Corpus* c, const double* d_queries, uint32_t
     const float eps_rel = scr == SDB_SCREEN_SIMT_F32
                               ? (float)((c->dim / 16.0 + 16.0) * 1.1920929e-7)
                               : (float)(0.00390625 * 1.01 + c->dim * 4.76837158e-7 + 1e-5);
-    std::vector<PassDesc> passes = build_passes(c->n, cap);
+    std::vector<PassDesc> passes = build_passes(c->n, cap, nq);
     SDB_TRY(cand_reset(c, nq, st));
     SDB_TRY(set_bounds(c, nq, (int)scr, eps_rel, st));
     for (const PassDesc& p : passes) {

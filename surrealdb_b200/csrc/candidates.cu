@@ -224,10 +224,19 @@ __device__ void bitonic_sort_u64(uint64_t* s, uint32_t n) {
   }
 }
 
+__device__ __forceinline__ Cand key_to_cand(uint64_t key) {
+  uint32_t fk = (uint32_t)(key >> 32);
+  fk = (fk >> 31) ? (fk & 0x7fffffffu) : ~fk;
+  Cand cd;
+  cd.score = __uint_as_float(fk);
+  cd.row = 0xFFFFFFFFu - (uint32_t)key;
+  return cd;
+}
+
 // keep the best kp candidates of each query, tau = score of the kp-th (if that many exist).
 // Sources: the query's main list (previous survivors, pass-0 fixed slots, K1 atomic appends) plus, for the tensor
 // core screens, the thread-private sub-lists written by the epilogue threads (one per CTA and column half).
-__global__ void __launch_bounds__(1024) cand_compact_kernel(Cand* __restrict__ cand, uint32_t* __restrict__ cnt,
+__global__ void __launch_bounds__(256) cand_compact_kernel(Cand* __restrict__ cand, uint32_t* __restrict__ cnt,
                                                             float* __restrict__ tau, uint32_t* __restrict__ flags,
                                                             uint32_t cap, uint32_t kp, const float* __restrict__ snorm,
                                                             const Cand* __restrict__ sub, const uint32_t* __restrict__ sub_cnt,
@@ -265,23 +274,78 @@ __global__ void __launch_bounds__(1024) cand_compact_kernel(Cand* __restrict__ c
   __syncthreads();
   const uint32_t n = s_n < cap ? s_n : cap;
   if (threadIdx.x == 0 && s_over) flags[q] |= 1u;  // candidates were dropped: this query must be re-run exactly
-  uint32_t p2 = 1;
-  while (p2 < n) p2 <<= 1;
-  for (uint32_t i = n + threadIdx.x; i < p2; i += blockDim.x) s_keys[i] = 0;  // padding sorts last
-  __syncthreads();
-  bitonic_sort_u64<true>(s_keys, p2);
-  const uint32_t keep = n < kp ? n : kp;
-  for (uint32_t i = threadIdx.x; i < keep; i += blockDim.x) {
-    const uint64_t key = s_keys[i];
-    uint32_t fk = (uint32_t)(key >> 32);
-    fk = (fk >> 31) ? (fk & 0x7fffffffu) : ~fk;
-    Cand cd;
-    cd.score = __uint_as_float(fk);
-    cd.row = 0xFFFFFFFFu - (uint32_t)key;
-    cq[i] = cd;
-    if (i == kp - 1) tau[q] = cd.score;
+  if (n < kp) {  // nothing to drop: keep everything, tau stays where it is
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) cq[i] = key_to_cand(s_keys[i]);
+    if (threadIdx.x == 0) cnt[q] = n;
+    return;
   }
-  if (threadIdx.x == 0) cnt[q] = keep;
+  // ---- exact selection of the kp-th largest 64-bit key (keys are unique: the row is part of the key) by an MSB-first
+  //      radix select, 8 bits per round, instead of sorting the whole list (only the kept SET and tau are needed; the
+  //      re-rank orders the survivors by exact distance anyway).  Warp-aggregated histogram updates: the scores of one
+  //      query share their leading bytes, so plain shared-memory atomics would serialise on one bin.
+  __shared__ uint32_t s_hist[256];
+  __shared__ uint64_t s_prefix;
+  __shared__ uint32_t s_remaining, s_out;
+  if (threadIdx.x == 0) {
+    s_prefix = 0;
+    s_remaining = kp;
+    s_out = 0;
+  }
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t round = 0; round < 8; round++) {
+    const uint32_t shift = 56 - 8 * round;
+    if (threadIdx.x < 256) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t prefix = s_prefix;
+    for (uint32_t i0 = 0; i0 < n; i0 += blockDim.x) {  // uniform trip count: every lane reaches the match below
+      const uint32_t i = i0 + threadIdx.x;
+      uint32_t digit = 0xFFFFFFFFu;
+      if (i < n) {
+        const uint64_t key = s_keys[i];
+        if (round == 0 || (key >> (shift + 8)) == prefix) digit = (uint32_t)(key >> shift) & 255u;
+      }
+      const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+      if (digit != 0xFFFFFFFFu && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_hist[digit], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {  // one warp: find the digit d with  #(digits > d) < remaining <= #(digits >= d)
+      uint32_t c[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        c[j] = s_hist[255 - (lane * 8 + j)];  // lane 0 holds the 8 largest digits
+        sum += c[j];
+      }
+      uint32_t incl = sum;  // inclusive prefix over lanes (descending digits)
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
+      }
+      const uint32_t rem = s_remaining;
+      const uint32_t before = incl - sum;  // keys with a digit above this lane's range
+      if (before < rem && rem <= incl) {
+        uint32_t acc = before;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          if (acc < rem && rem <= acc + c[j]) {
+            s_prefix = (prefix << 8) | (uint64_t)(255 - (lane * 8 + j));
+            s_remaining = rem - acc;
+          }
+          acc += c[j];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const uint64_t kth = s_prefix;  // the kp-th largest key itself
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint64_t key = s_keys[i];
+    if (key >= kth) cq[atomicAdd(&s_out, 1u)] = key_to_cand(key);
+  }
+  if (threadIdx.x == 0) {
+    tau[q] = key_to_cand(kth).score;
+    cnt[q] = kp;
+  }
 }
 
 sdb_status cand_compact(Corpus* c, uint32_t nq, uint32_t kp, bool drop_invalid, uint32_t n_slots, cudaStream_t st) {
@@ -291,7 +355,8 @@ sdb_status cand_compact(Corpus* c, uint32_t nq, uint32_t kp, bool drop_invalid, 
     SDB_CUDA(cudaFuncSetAttribute(cand_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  cand_compact_kernel<<<nq, 1024, smem, st>>>(c->d_cand, c->d_cand_cnt, c->d_tau, c->d_flags, c->sc_cap, kp,
+  cand_compact_kernel<<<nq, 256, smem, st>>>(  // 256 threads: 7 blocks per SM, the whole batch is one wave
+      c->d_cand, c->d_cand_cnt, c->d_tau, c->d_flags, c->sc_cap, kp,
                                               drop_invalid ? c->d_snorm : nullptr, c->d_sub, c->d_sub_cnt, n_slots,
                                               c->sub_cap);
   count_launch(c->ctx);

@@ -32,7 +32,7 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 constexpr int TILE_ROWS = 256;    // screening tile = 256 corpus rows (one tcgen05 N=256 MMA tile)
-constexpr int PASS_RATIO = 8;     // geometric threshold-refinement schedule
+constexpr int PASS_RATIO = 8;     // default geometric threshold-refinement ratio (api.cu:pass_ratio picks per batch size)
 constexpr int SPECIAL_CAP = 1024; // rows with zero / non-finite norm handled by exact ranking
 
 // ---- ordered keys -------------------------------------------------------------------------------
@@ -66,11 +66,11 @@ __host__ __device__ inline uint32_t f32_key(float f) {  // ascending key of a fl
 
 struct PassDesc {
   uint32_t stride;  // tiles t = i * stride
-  uint32_t excl;    // 0: every i; else skip i % PASS_RATIO == 0 (already done by an earlier pass)
+  uint32_t excl;    // 0: every i; else = the schedule ratio R: skip i % R == 0 (already done by an earlier pass)
   uint32_t count;   // number of tiles in this pass
 };
 __host__ __device__ inline uint32_t pass_tile(const PassDesc& p, uint32_t w) {
-  uint32_t i = p.excl ? (w / (PASS_RATIO - 1)) * PASS_RATIO + (w % (PASS_RATIO - 1)) + 1 : w;
+  uint32_t i = p.excl ? (w / (p.excl - 1)) * p.excl + (w % (p.excl - 1)) + 1 : w;
   return i * p.stride;
 }
 

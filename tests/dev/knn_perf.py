@@ -28,7 +28,9 @@ for screen, batches in cfgs:
         o_d = torch.zeros((b, k), dtype=torch.float64, device=dev)
         o_c = torch.zeros((b,), dtype=torch.int32, device=dev)
         ms = []
-        if b > 64:  # guard: a broken screen sends every query to the (slow) exact kernel -- check on a small batch first
+        if os.environ.get('SDB_TC_DBG'):
+            col.set_exact(False)  # ablations produce garbage scores: never run the exact fallback
+        elif b > 64:  # guard: a broken screen sends every query to the (slow) exact kernel -- check on a small batch first
             col.knn_device(q.data_ptr(), 64, k, 0, o_r.data_ptr(), o_d.data_ptr(), o_c.data_ptr())
             if col.stats()["n_fallback"] > 6:
                 print(f"{screen} B={b}: ABORT, {col.stats()['n_fallback']} of 64 probe queries fell back", flush=True)
