@@ -120,17 +120,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 // out-of-line survivor append: keeps the (rare) slow path out of the unrolled epilogue body
-__device__ __noinline__ void append_survivor(Cand* my_sub, uint32_t* my_cnt, Cand* my_cand, uint32_t* cnt_q, uint32_t cap,
+__device__ __noinline__ void append_survivor(Cand* my_sub, uint32_t my_cnt_saddr, Cand* my_cand, uint32_t* cnt_q, uint32_t cap,
                                              float score, uint32_t row) {
-  const uint32_t pos = (*my_cnt)++;  // thread-private counter in shared memory: no atomics, no round trip
-  Cand cd;
-  cd.score = score;
-  cd.row = row;
+  // thread-private counter in shared memory (explicit shared-space access): no atomics, no round trip
+  uint32_t pos;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(pos) : "r"(my_cnt_saddr));
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(my_cnt_saddr), "r"(pos + 1));
+  const uint2 cd = make_uint2(__float_as_uint(score), row);  // = Cand{score, row}, one 8-byte store
   if (pos < SUBCAP) {
-    my_sub[pos] = cd;
+    *reinterpret_cast<uint2*>(my_sub + pos) = cd;
   } else {  // private slots full (small passes run few CTAs): spill to the query's shared list
     const uint32_t p2 = atomicAdd(cnt_q, 1u);
-    if (p2 < cap) my_cand[p2] = cd;
+    if (p2 < cap) *reinterpret_cast<uint2*>(my_cand + p2) = cd;
   }
 }
 
@@ -277,7 +278,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint32_t taddr = tmem_base + ((wq * 32) << 16) + a * BLOCK_N + cbase;
       Cand* my_cand = cand + (size_t)q * cap;
       const uint32_t n_slots = gridDim.x * 2;
-      uint32_t* my_cnt = s_cnt + mb * 256 + et;
+      const uint32_t my_cnt = smem_u32(s_cnt + mb * 256 + et);
       Cand* my_sub = sub + ((size_t)q * n_slots + blockIdx.x * 2 + half) * SUBCAP;
       {
       uint32_t va[32], vb[32];
@@ -289,9 +290,14 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (cc + 1 < BLOCK_N / 2 / 32) tmem_ld32(taddr + c0 + 32, (cc & 1) ? va : vb);  // next chunk in flight
         if (INT8) {
-          int m = (int)v[0];
+          int gm[4];  // maxima of the four groups of 8 columns: the slow path only scans groups that hold a survivor
 #pragma unroll
-          for (int i = 1; i < 32; i++) m = max(m, (int)v[i]);
+          for (int g = 0; g < 4; g++) {
+            gm[g] = (int)v[8 * g];
+#pragma unroll
+            for (int i = 1; i < 8; i++) gm[g] = max(gm[g], (int)v[8 * g + i]);
+          }
+          const int m = max(max(gm[0], gm[1]), max(gm[2], gm[3]));
           if (pass0) {
             if (q < nq) {
 #pragma unroll
@@ -304,16 +310,23 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
           } else if (m >= tau_i) {  // rare
 #pragma unroll
-            for (int i = 0; i < 32; i++) {
-              if ((int)v[i] >= tau_i) {
-                append_survivor(my_sub, my_cnt, my_cand, cand_cnt + q, cap, __int2float_rn((int)v[i]),
-                                (uint32_t)(row0 + cbase + c0 + i));
+            for (int g = 0; g < 4; g++) {
+              if (gm[g] >= tau_i) {
+#pragma unroll
+                for (int i = 8 * g; i < 8 * g + 8; i++) {
+                  if ((int)v[i] >= tau_i) {
+                    append_survivor(my_sub, my_cnt, my_cand, cand_cnt + q, cap, __int2float_rn((int)v[i]),
+                                    (uint32_t)(row0 + cbase + c0 + i));
+                  }
+                }
               }
             }
           }
         } else {
           float sc[32];
-          float m = __int_as_float(0xff800000);
+          float gmf[4];
+#pragma unroll
+          for (int g = 0; g < 4; g++) gmf[g] = __int_as_float(0xff800000);
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const float4 n4 = *reinterpret_cast<const float4*>(sn + cbase + c0 + i);
@@ -321,8 +334,9 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             sc[i + 1] = COSINE ? __uint_as_float(v[i + 1]) * n4.y : fmaf(2.f, __uint_as_float(v[i + 1]), -n4.y);
             sc[i + 2] = COSINE ? __uint_as_float(v[i + 2]) * n4.z : fmaf(2.f, __uint_as_float(v[i + 2]), -n4.z);
             sc[i + 3] = COSINE ? __uint_as_float(v[i + 3]) * n4.w : fmaf(2.f, __uint_as_float(v[i + 3]), -n4.w);
-            m = fmaxf(m, fmaxf(fmaxf(sc[i + 0], sc[i + 1]), fmaxf(sc[i + 2], sc[i + 3])));  // fmaxf drops NaNs
+            gmf[i >> 3] = fmaxf(gmf[i >> 3], fmaxf(fmaxf(sc[i + 0], sc[i + 1]), fmaxf(sc[i + 2], sc[i + 3])));  // fmaxf drops NaNs
           }
+          const float m = fmaxf(fmaxf(gmf[0], gmf[1]), fmaxf(gmf[2], gmf[3]));
           if (pass0) {
             if (q < nq) {  // every (finite or NaN) score goes to its fixed slot; compaction drops the NaNs
 #pragma unroll
@@ -335,9 +349,14 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
           } else if (m >= my_tau) {  // rare: some element of this chunk survives the threshold
 #pragma unroll
-            for (int i = 0; i < 32; i++) {
-              if (sc[i] >= my_tau) {
-                append_survivor(my_sub, my_cnt, my_cand, cand_cnt + q, cap, sc[i], (uint32_t)(row0 + cbase + c0 + i));
+            for (int g = 0; g < 4; g++) {
+              if (gmf[g] >= my_tau) {
+#pragma unroll
+                for (int i = 8 * g; i < 8 * g + 8; i++) {
+                  if (sc[i] >= my_tau) {
+                    append_survivor(my_sub, my_cnt, my_cand, cand_cnt + q, cap, sc[i], (uint32_t)(row0 + cbase + c0 + i));
+                  }
+                }
               }
             }
           }
