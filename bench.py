@@ -320,13 +320,16 @@ def main():
                     "achieved": ach, "peak": peak, "unit": "TOP/s" if i8 else "TFLOP/s", "frac": ach / peak,
                     "peak_source": pk["source"] + (" (2 x sustained cuBLAS bf16: the int8 tensor rate is twice the bf16 rate on B200; "
                                                    "MEASURED_PEAKS.json has no int8 figure)" if i8 else " (sustained cuBLAS bf16)"),
-                    "traffic": None, "algorithmic_flops_per_launch": flops}
+                    "traffic": None, "algorithmic_flops_per_launch": flops,
+                    "launch_note": f"the screen runs as {stats['n_passes']} launches of this kernel per step (threshold-refinement passes "
+                                   "over disjoint tile subsets); 'achieved' = flops of all of them / CUDA-event time of the whole screen "
+                                   "phase on the library stream (includes the compaction kernels between passes)"}
             try:  # DRAM traffic of the dominant launch, from the committed ncu capture (not re-measured here)
                 tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["screen_tc_int8" if i8 else "screen_tc_bf16"]
                 if rows == 10_000_000 and world == 1:
                     roof["traffic"] = tr["bytes"]
-                    roof["traffic_note"] = ("dram read+write bytes of the largest of the 5 pass launches (7/8 of the tiles), ncu --set full, "
-                                            + tr["source"] + f"; algorithmic bytes of that launch {tr['algorithmic_bytes_same_launch']:.4g}")
+                    roof["traffic_note"] = ("dram read+write bytes of ONE launch, ncu --set full: " + tr.get("launch", "largest pass launch")
+                                            + "; " + tr["source"] + f"; algorithmic bytes of that launch {tr['algorithmic_bytes_same_launch']:.4g}")
             except Exception:
                 pass
         else:
