@@ -35,12 +35,13 @@ def _merge_reverse(fwd, cnt, m_max, cap=None):
     dst_s, src_s = dst[order], src[order]
     start = np.searchsorted(dst_s, np.arange(n + 1))
     rank = np.arange(dst_s.size) - start[dst_s]
-    cap = cap or m_max
-    keep = rank < m_max
-    rev = np.full((n, m_max), -1, np.int64)
+    cap = cap or 2 * m_max
+    rev_cols = max(cap - m_max, m_max)  # reverse edges kept per node before the re-selection
+    keep = rank < rev_cols
+    rev = np.full((n, rev_cols), -1, np.int64)
     rev[dst_s[keep], rank[keep]] = src_s[keep]
     f = np.where(valid, fwd.astype(np.int64), -2)
-    for j in range(m_max):  # drop reverse edges that duplicate a forward edge
+    for j in range(rev_cols):  # drop reverse edges that duplicate a forward edge
         col = rev[:, j]
         dup = (f == col[:, None]).any(1)
         rev[dup, j] = -1
@@ -53,7 +54,7 @@ def _merge_reverse(fwd, cnt, m_max, cap=None):
 
 
 def build_layers(ctx, vectors_dev, n, dim, metric="EUCLIDEAN", m=16, m0=32, seed=1, batch=4096, progress=None,
-                 heuristic=True, prefix=False):
+                 heuristic=True, prefix=False, efc=150, rev_factor=4):
     """vectors_dev: torch CUDA float32 tensor (n, dim).  -> (layers, entry_point, levels) with
     layers = [(row_ptr u64[n+1], col_idx u32[e]), ...] (layer 0 first), element id = row index.
     heuristic=True: candidates = 2*m_max nearest, pruned by Heuristic::select on the GPU
@@ -76,7 +77,9 @@ def build_layers(ctx, vectors_dev, n, dim, metric="EUCLIDEAN", m=16, m0=32, seed
             continue
         midx = torch.from_numpy(members).to(dev)
         sub = vectors_dev if members.size == n else vectors_dev.index_select(0, midx).contiguous()
-        kc_full = (2 * k_nb if heuristic else k_nb) + 1  # +1: the element itself comes back too
+        # candidates per element: efc nearest (the reference selects among the efc results of its insertion search,
+        # layer.rs:352-358), +1 because the element itself comes back too
+        kc_full = (max(2 * k_nb, min(efc, 255)) if heuristic else k_nb) + 1
         nbrs = np.zeros((members.size, k_nb), np.int64)
         counts = np.zeros(members.size, np.int64)
         o_r = torch.zeros((batch, kc_full), dtype=torch.int64, device=dev)
@@ -126,7 +129,7 @@ def build_layers(ctx, vectors_dev, n, dim, metric="EUCLIDEAN", m=16, m0=32, seed
             # distance -- layer.rs:362-378
             if progress:
                 progress(l, -1, float(counts.mean()))
-            union, ucnt = _merge_reverse(nbrs, counts, k_nb, cap=2 * k_nb)
+            union, ucnt = _merge_reverse(nbrs, counts, k_nb, cap=rev_factor * k_nb)
             if progress:
                 progress(l, -2, float(ucnt.mean()))
             u_dev = torch.from_numpy(np.maximum(union, 0).astype(np.int64)).to(dev)
@@ -136,7 +139,7 @@ def build_layers(ctx, vectors_dev, n, dim, metric="EUCLIDEAN", m=16, m0=32, seed
             torch.cuda.current_stream().synchronize()
             L.check(L.lib().sdb_hnsw_select_neighbors(ctx.h, C.c_void_p(sub.data_ptr()), dim, L.METRIC[metric.upper()], 0,
                                                       members.size, C.c_void_p(u_dev.data_ptr()), C.c_void_p(c_dev.data_ptr()),
-                                                      2 * k_nb, k_nb, 0, C.c_void_p(r_o.data_ptr()), C.c_void_p(r_c.data_ptr())))
+                                                      rev_factor * k_nb, k_nb, 0, C.c_void_p(r_o.data_ptr()), C.c_void_p(r_c.data_ptr())))
             nbrs = r_o.cpu().numpy().astype(np.int64)
             counts = r_c.cpu().numpy().astype(np.int64)
         deg = np.zeros(n, np.int64)

@@ -8,7 +8,7 @@ from surrealdb_b200.hnsw_build import build_layers
 ctx = Context(0)
 n, dim, nq = 20000, 32, 500
 g = torch.Generator(device="cuda").manual_seed(3)
-for name, sigma, ncl in (("clustered", 0.3, 64), ("uniform", 0.0, 0)):
+for name, sigma, ncl in (("tight", 0.03, 256), ("clustered", 0.3, 64)):
     if ncl:
         centers = torch.randn((ncl, dim), generator=g, device="cuda")
         x = (centers[torch.randint(0, ncl, (n,), generator=g, device="cuda")] + sigma * torch.randn((n, dim), generator=g, device="cuda")).contiguous()
@@ -25,10 +25,10 @@ for name, sigma, ncl in (("clustered", 0.3, 64), ("uniform", 0.0, 0)):
     gref = h.export()
     t_ref = time.time() - t0
     graphs = {"reference-style (oracle insert)": (gref["layers"], gref["entry_point"])}
-    for heur in (False, True):
+    for heur, prefix in ((True, False), (True, True)):
         t0 = time.time()
-        layers, entry, _ = build_layers(ctx, x, n, dim, "EUCLIDEAN", m=16, m0=32, seed=5, heuristic=heur)
-        graphs[f"gpu batch heuristic={heur} ({time.time()-t0:.1f}s)"] = (layers, entry)
+        layers, entry, _ = build_layers(ctx, x, n, dim, "EUCLIDEAN", m=16, m0=32, seed=5, heuristic=heur, prefix=prefix)
+        graphs[f"gpu batch heuristic={heur} prefix={prefix} ({time.time()-t0:.1f}s)"] = (layers, entry)
     for gname, (layers, entry) in graphs.items():
         idx = HnswIndex(ctx, xh, layers, entry, "EUCLIDEAN")
         deg = np.diff(layers[0][0].astype(np.int64)).mean()
