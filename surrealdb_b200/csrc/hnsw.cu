@@ -75,13 +75,21 @@ __device__ __forceinline__ double warp_distance(const float* __restrict__ vec, c
   const uint32_t d8 = dim & ~7u;
   float p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0, p5 = 0, p6 = 0, p7 = 0, s = 0.f;
   const uint32_t lim_all = COSINE ? d8 : dim;
+  // Only a handful of the 32 neighbours of an expanded node are new (6 on average): compact them so that the
+  // transposing loads below loop over the valid rows only.  Row r of the tile belongs to the r-th valid lane; its
+  // element id is parked in the tile's padding column.
+  const uint32_t vmask = __ballot_sync(0xffffffffu, my_row != NO_ROW);
+  const uint32_t n_rows = __popc(vmask);
+  const uint32_t ci = __popc(vmask & ((1u << lane) - 1u));
+  if (my_row != NO_ROW) tile[ci][32] = __uint_as_float(my_row);
+  __syncwarp();
   for (uint32_t c0 = 0; c0 < lim_all; c0 += 32) {
     const uint32_t c = c0 + lane;
-#pragma unroll 8
-    for (int r = 0; r < 32; r++) {
-      const uint32_t row = __shfl_sync(0xffffffffu, my_row, r);
+#pragma unroll 4
+    for (uint32_t r = 0; r < n_rows; r++) {
+      const uint32_t row = __float_as_uint(tile[r][32]);  // broadcast read
       float v = 0.f;
-      if (row != NO_ROW && c < lim_all) v = __ldg(vec + (size_t)row * dim + c);
+      if (c < lim_all) v = __ldg(vec + (size_t)row * dim + c);
       tile[r][lane] = v;
     }
     __syncwarp();
@@ -89,7 +97,7 @@ __device__ __forceinline__ double warp_distance(const float* __restrict__ vec, c
       const uint32_t lim = lim_all - c0 < 32u ? lim_all - c0 : 32u;
       if (COSINE) {
         for (uint32_t jj = 0; jj < lim; jj += 8) {  // lim is a multiple of 8 here
-          const float* x = &tile[lane][jj];
+          const float* x = &tile[ci][jj];
           const float* q = s_q + c0 + jj;
           p0 = __fadd_rn(p0, __fmul_rn(x[0], q[0]));
           p1 = __fadd_rn(p1, __fmul_rn(x[1], q[1]));
@@ -102,7 +110,7 @@ __device__ __forceinline__ double warp_distance(const float* __restrict__ vec, c
         }
       } else {
         for (uint32_t j = 0; j < lim; j++) {
-          const float d = __fsub_rn(tile[lane][j], s_q[c0 + j]);
+          const float d = __fsub_rn(tile[ci][j], s_q[c0 + j]);
           s = __fadd_rn(s, __fmul_rn(d, d));
         }
       }
