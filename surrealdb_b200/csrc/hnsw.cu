@@ -75,47 +75,65 @@ __device__ __forceinline__ double warp_distance(const float* __restrict__ vec, c
   const uint32_t d8 = dim & ~7u;
   float p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0, p5 = 0, p6 = 0, p7 = 0, s = 0.f;
   const uint32_t lim_all = COSINE ? d8 : dim;
-  // Only a handful of the 32 neighbours of an expanded node are new (6 on average): compact them so that the
-  // transposing loads below loop over the valid rows only.  Row r of the tile belongs to the r-th valid lane; its
-  // element id is parked in the tile's padding column.
+  // Only a handful of the <=32 neighbours of an expanded node are new (6 on average): the valid rows are compacted and
+  // handled in rounds of 16; the 32 x 33 float scratch is viewed as 16 rows x (64 columns + 2 padding words), so one
+  // step moves 64 columns of every row of the round -- up to 32 independent loads per lane in flight per wait instead
+  // of 4 (the walk is bound by the latency of these fetches, see below).  The padding words park the compacted row ids.
+  float(*t)[66] = reinterpret_cast<float(*)[66]>(tile);
   const uint32_t vmask = __ballot_sync(0xffffffffu, my_row != NO_ROW);
   const uint32_t n_rows = __popc(vmask);
-  const uint32_t ci = __popc(vmask & ((1u << lane) - 1u));
-  if (my_row != NO_ROW) tile[ci][32] = __uint_as_float(my_row);
+  const uint32_t ci = __popc(vmask & ((1u << lane) - 1u));  // compact index of this lane's row
+  if (my_row != NO_ROW) t[ci & 15u][64 + (ci >> 4)] = __uint_as_float(my_row);
   __syncwarp();
-  for (uint32_t c0 = 0; c0 < lim_all; c0 += 32) {
-    const uint32_t c = c0 + lane;
-#pragma unroll 4
+  // ncu: ~85 % of the stall samples of the walk sit on the first use of the fetched vector elements, and the step loop
+  // would pay that latency once per step.  Ask for every line of every new row up front: the rows stream into L2 back
+  // to back (one DRAM page / TLB entry per row) while the first steps are consumed.
+  {
+    const uint32_t row_bytes = dim * 4u;
     for (uint32_t r = 0; r < n_rows; r++) {
-      const uint32_t row = __float_as_uint(tile[r][32]);  // broadcast read
-      float v = 0.f;
-      if (c < lim_all) v = __ldg(vec + (size_t)row * dim + c);
-      tile[r][lane] = v;
+      const char* base = reinterpret_cast<const char*>(vec + (size_t)__float_as_uint(t[r & 15u][64 + (r >> 4)]) * dim);
+      for (uint32_t off = lane * 128u; off < row_bytes; off += 32u * 128u)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
     }
-    __syncwarp();
-    if (my_row != NO_ROW) {
-      const uint32_t lim = lim_all - c0 < 32u ? lim_all - c0 : 32u;
-      if (COSINE) {
-        for (uint32_t jj = 0; jj < lim; jj += 8) {  // lim is a multiple of 8 here
-          const float* x = &tile[ci][jj];
-          const float* q = s_q + c0 + jj;
-          p0 = __fadd_rn(p0, __fmul_rn(x[0], q[0]));
-          p1 = __fadd_rn(p1, __fmul_rn(x[1], q[1]));
-          p2 = __fadd_rn(p2, __fmul_rn(x[2], q[2]));
-          p3 = __fadd_rn(p3, __fmul_rn(x[3], q[3]));
-          p4 = __fadd_rn(p4, __fmul_rn(x[4], q[4]));
-          p5 = __fadd_rn(p5, __fmul_rn(x[5], q[5]));
-          p6 = __fadd_rn(p6, __fmul_rn(x[6], q[6]));
-          p7 = __fadd_rn(p7, __fmul_rn(x[7], q[7]));
-        }
-      } else {
-        for (uint32_t j = 0; j < lim; j++) {
-          const float d = __fsub_rn(tile[ci][j], s_q[c0 + j]);
-          s = __fadd_rn(s, __fmul_rn(d, d));
+  }
+  for (uint32_t g0 = 0; g0 < n_rows; g0 += 16) {
+    const uint32_t nr = n_rows - g0 < 16u ? n_rows - g0 : 16u;
+    const bool mine = my_row != NO_ROW && (ci >> 4) == (g0 >> 4);
+    const float* x = t[ci & 15u];
+    for (uint32_t c0 = 0; c0 < lim_all; c0 += 64) {
+      const bool in0 = c0 + lane < lim_all, in1 = c0 + 32 + lane < lim_all;
+#pragma unroll 4
+      for (uint32_t r = 0; r < nr; r++) {
+        const float* src = vec + (size_t)__float_as_uint(t[r][64 + (g0 >> 4)]) * dim + c0 + lane;  // broadcast id read
+        const float v0 = in0 ? __ldg(src) : 0.f;
+        const float v1 = in1 ? __ldg(src + 32) : 0.f;
+        t[r][lane] = v0;
+        t[r][lane + 32] = v1;
+      }
+      __syncwarp();
+      if (mine) {
+        const uint32_t lim = lim_all - c0 < 64u ? lim_all - c0 : 64u;
+        if (COSINE) {
+          for (uint32_t jj = 0; jj < lim; jj += 8) {  // lim is a multiple of 8 here
+            const float* q = s_q + c0 + jj;
+            p0 = __fadd_rn(p0, __fmul_rn(x[jj + 0], q[0]));
+            p1 = __fadd_rn(p1, __fmul_rn(x[jj + 1], q[1]));
+            p2 = __fadd_rn(p2, __fmul_rn(x[jj + 2], q[2]));
+            p3 = __fadd_rn(p3, __fmul_rn(x[jj + 3], q[3]));
+            p4 = __fadd_rn(p4, __fmul_rn(x[jj + 4], q[4]));
+            p5 = __fadd_rn(p5, __fmul_rn(x[jj + 5], q[5]));
+            p6 = __fadd_rn(p6, __fmul_rn(x[jj + 6], q[6]));
+            p7 = __fadd_rn(p7, __fmul_rn(x[jj + 7], q[7]));
+          }
+        } else {
+          for (uint32_t j = 0; j < lim; j++) {
+            const float d = __fsub_rn(x[j], s_q[c0 + j]);
+            s = __fadd_rn(s, __fmul_rn(d, d));
+          }
         }
       }
+      __syncwarp();
     }
-    __syncwarp();
   }
   if (my_row == NO_ROW) return 0.0;
   if (COSINE) {
