@@ -322,6 +322,7 @@ __global__ void __launch_bounds__(256) cand_compact_kernel(Cand* __restrict__ ca
         if (lane >= (uint32_t)o) incl += t;
       }
       const uint32_t rem = s_remaining;
+      __syncwarp();  // every lane has read s_remaining before the selected lane overwrites it
       const uint32_t before = incl - sum;  // keys with a digit above this lane's range
       if (before < rem && rem <= incl) {
         uint32_t acc = before;

@@ -41,3 +41,43 @@ gr = CsrGraph(ctx, rp, ci)
 assert list(expand([gr, gr], [0, 3, 0])) == list(O.graph_hop(rp, ci, O.graph_hop(rp, ci, [0, 3, 0])))
 assert list(collect(gr, [0], 1, 0, False)) == list(O.graph_collect(rp, ci, [0], 1, 0, False))
 print("graph ok", flush=True)
+# ---- kernels added later in round 1: other metrics (exact kernel), projection, filtered walk, staging decoders
+from oracle import kvformats as K
+from surrealdb_b200 import staging as S
+import torch
+for metric in ("MANHATTAN", "CHEBYSHEV", "HAMMING", "PEARSON"):
+    col = VectorColumn(ctx, dim, metric, "F32", capacity=n)
+    col.append(corpus); col.finalize()
+    rows, dist, cnt = col.knn(queries[:2], k)
+    r, d = O.knn_topk(corpus, queries[0], metric.lower(), k)
+    assert list(rows[0]) == list(r) and dist[0].tobytes() == d.tobytes(), metric
+    col.close()
+col = VectorColumn(ctx, dim, "COSINE", "F32", capacity=n)
+col.append(corpus); col.finalize()
+for fn in ("SIMILARITY_COSINE", "DOT", "MAGNITUDE", "PEARSON"):
+    col.project(fn, queries[0])
+big = VectorColumn(ctx, dim, "COSINE", "F32", capacity=n)
+big.append(corpus); big.finalize(); big.set_screen("TC_INT8")
+qq = np.tile(queries, (15, 1))[:600]                      # batch >= 512: the R=4 schedule + radix-select compaction
+rows, dist, cnt = big.knn(qq, k)
+r, d = O.knn_topk(corpus, qq[599], "cosine", k)
+assert list(rows[599]) == list(r)
+print("metrics/project/large-batch ok", flush=True)
+truthy = (np.arange(600) % 3 == 0).astype(np.uint8)
+ids, dist, cnt, ctr = idx.search_graph(qs, 5, 24, counters=True, truthy=truthy)
+for q in range(20):
+    oi, od, oc = O.hnsw_search_csr(g, qs[q], 5, 24, truthy=truthy)
+    assert list(ids[q, :cnt[q]]) == list(oi)
+he = [(e, K.ser_vector("F32", g["vectors"][e])) for e in range(600)]
+hn = [[(e, K.node_to_val(ci_[rp_[e]:rp_[e + 1]])) for e in range(600) if rp_[e + 1] > rp_[e]] for rp_, ci_ in g["layers"]]
+state = K.hnsw_state(int(g["entry_point"]), 600, (1, 0), tuple((1, 0) for _ in g["layers"][1:]))
+idx2 = HnswIndex.from_kv(ctx, 16, state, he, hn, "EUCLIDEAN")
+ids2, dist2, cnt2 = idx2.search_graph(qs, 5, 24)
+ids1, dist1, cnt1 = idx.search_graph(qs, 5, 24)
+assert ids1.tobytes() == ids2.tobytes() and idx2.n_bad == 0
+out = torch.zeros((4, 7), dtype=torch.float64, device="cuda")
+items = [(i, K.ser_vector(v, np.arange(7) + i)) for i, v in enumerate(("F64", "I64", "I32", "I16"))]
+assert S.decode_vectors(ctx, items, 7, out.data_ptr(), 4, "F64") == 0
+torch.cuda.synchronize()
+assert out.cpu().numpy()[3].tolist() == [3, 4, 5, 6, 7, 8, 9]
+print("filtered walk / staging ok", flush=True)
