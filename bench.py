@@ -31,6 +31,8 @@ WORKLOADS = {
     "northstar_10Mx768_b1024_k10_cosine_bruteforce": (10_000_000, 768, 1024, 10),
     "c2_1Mx768_b1024_k10_cosine_bruteforce": (1_000_000, 768, 1024, 10),
     "tiny_100kx128_b64_k10_cosine_bruteforce": (100_000, 128, 64, 10),
+    # BASELINE config 4 (quoted there on 8 GPUs; 107 GB of corpus + screen copies still fit one B200)
+    "c4_10Mx1536_b4096_k100_cosine_bruteforce": (10_000_000, 1536, 4096, 100),
 }
 SEED_CORPUS = 0x5DB00002
 SEED_QUERY = 0x5DB0A000

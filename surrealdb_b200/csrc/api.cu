@@ -83,21 +83,44 @@ static sdb_status knn_device_locked(Corpus* c, const double* d_queries, uint32_t
   if (scr == SDB_SCREEN_TC_BF16 && !screen_tc_available()) scr = SDB_SCREEN_SIMT_F32;
   const bool screenable = c->metric == SDB_COSINE || c->metric == SDB_EUCLIDEAN;
   if (c->dtype == SDB_F64 || c->special_overflow || k > 256 || !screenable) scr = SDB_SCREEN_NONE_EXACT;
-  const uint32_t kp = k + (k > 54 ? k : 54) + (scr == SDB_SCREEN_TC_INT8 ? 64 : 0);  // looser screen => more slack
-  uint32_t cap = 4096;
-  while (cap < 2u * pass_ratio(nq) * kp && cap < 16384u) cap <<= 1;  // a pass appends ~(PASS_RATIO-1)*kp survivors per query
-  SDB_TRY(scratch_for(c, nq, cap, kp));
-  cap = c->sc_cap;
-  SDB_TRY(prep_queries(c, d_queries, nq, st));
+  // ---- the ladder: (screen, slack multiplier) rungs, cheapest first.  A rung is abandoned when the exactness proof
+  // fails for more than a handful of queries (each failure would otherwise cost a full f64 pass over the corpus in the
+  // exact kernel); the rung that worked is remembered per corpus so later batches start there.  More slack (k' x 4)
+  // lowers tau relative to the k-th distance -- what high-dimensional / large-k workloads with tightly packed
+  // similarities need (BASELINE config 4: 1536 dims, k = 100) -- at the price of 4x the survivor appends.
+  struct Rung { sdb_screen scr; uint32_t mult; };
+  std::vector<Rung> rungs;
+  if (scr == SDB_SCREEN_TC_INT8) rungs = {{SDB_SCREEN_TC_INT8, 1}, {SDB_SCREEN_TC_INT8, 4}, {SDB_SCREEN_TC_BF16, 4}};
+  else if (scr == SDB_SCREEN_TC_BF16) rungs = {{SDB_SCREEN_TC_BF16, 1}, {SDB_SCREEN_TC_BF16, 4}};
+  else if (scr == SDB_SCREEN_SIMT_F32) rungs = {{SDB_SCREEN_SIMT_F32, 1}};
+  if (rungs.empty()) {  // exact-only: the exact kernel still needs the prepared queries (f64 copy, |q|, flags)
+    SDB_TRY(scratch_for(c, nq, 4096, k + (k > 54 ? k : 54)));
+    SDB_TRY(prep_queries(c, d_queries, nq, st));
+  }
+  uint32_t rung = 0;
+  if (c->ladder_scr == scr && c->ladder_k == k && c->ladder_rung < rungs.size()) rung = c->ladder_rung;
   std::vector<uint32_t> h_flags(nq, 2u), h_qflags(nq, 0u);
   SDB_CUDA(cudaEventRecord(ev[1], st));
-  for (int attempt = 0; attempt < 2 && scr != SDB_SCREEN_NONE_EXACT; attempt++) {
-    const float eps_rel = scr == SDB_SCREEN_SIMT_F32
+  bool first = true;
+  for (; rung < rungs.size(); rung++) {
+    const sdb_screen rs = rungs[rung].scr;
+    uint32_t kp = k + (k > 54 ? k : 54) + (rs == SDB_SCREEN_TC_INT8 ? 64 : 0);  // looser screen => more slack
+    kp = kp * rungs[rung].mult;
+    if (kp > 1024u) kp = 1024u > 2 * k ? 1024u : 2 * k;
+    uint32_t cap = 4096;
+    while (cap < 2u * pass_ratio(nq) * kp && cap < 16384u) cap <<= 1;  // a pass appends ~(R-1)*kp survivors per query
+    const void* q_before = c->d_q64;
+    SDB_TRY(scratch_for(c, nq, cap, kp));
+    cap = c->sc_cap;
+    if (first || q_before != c->d_q64) SDB_TRY(prep_queries(c, d_queries, nq, st));  // (re)allocation drops the prepared queries
+    if (first) SDB_CUDA(cudaEventRecord(ev[1], st));
+    first = false;
+    const float eps_rel = rs == SDB_SCREEN_SIMT_F32
                               ? (float)((c->dim / 16.0 + 16.0) * 1.1920929e-7)
                               : (float)(0.00390625 * 1.01 + c->dim * 4.76837158e-7 + 1e-5);
     std::vector<PassDesc> passes = build_passes(c->n, cap, nq);
     SDB_TRY(cand_reset(c, nq, st));
-    SDB_TRY(set_bounds(c, nq, (int)scr, eps_rel, st));
+    SDB_TRY(set_bounds(c, nq, (int)rs, eps_rel, st));
     for (const PassDesc& p : passes) {
       if (cancel && *cancel) {
         cudaStreamSynchronize(st);
@@ -105,9 +128,9 @@ static sdb_status knn_device_locked(Corpus* c, const double* d_queries, uint32_t
         set_error("query cancelled");
         return SDB_ECANCELLED;
       }
-      if (scr == SDB_SCREEN_SIMT_F32) SDB_TRY(screen_simt_pass(c, nq, p, st));
-      else SDB_TRY(screen_tc_pass(c, nq, p, scr == SDB_SCREEN_TC_INT8, st));
-      SDB_TRY(cand_compact(c, nq, kp, scr == SDB_SCREEN_TC_INT8, scr == SDB_SCREEN_SIMT_F32 ? 0u : c->last_slots, st));
+      if (rs == SDB_SCREEN_SIMT_F32) SDB_TRY(screen_simt_pass(c, nq, p, st));
+      else SDB_TRY(screen_tc_pass(c, nq, p, rs == SDB_SCREEN_TC_INT8, st));
+      SDB_TRY(cand_compact(c, nq, kp, rs == SDB_SCREEN_TC_INT8, rs == SDB_SCREEN_SIMT_F32 ? 0u : c->last_slots, st));
     }
     SDB_CUDA(cudaEventRecord(ev[2], st));
     SDB_TRY(cand_rerank(c, nq, st));
@@ -115,14 +138,18 @@ static sdb_status knn_device_locked(Corpus* c, const double* d_queries, uint32_t
     SDB_CUDA(cudaMemcpyAsync(h_flags.data(), c->d_flags, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, st));
     stt.n_passes += (uint32_t)passes.size();
     stt.n_reranked += (uint64_t)nq * (kp + c->n_special);
-    if (scr != SDB_SCREEN_TC_INT8 || !c->exact) break;
-    // precision ladder: if the int8 proof failed for more than a handful of queries, re-screen the batch in bf16
+    scr = rs;
+    if (!c->exact || rung + 1 == rungs.size()) break;
     SDB_CUDA(cudaStreamSynchronize(st));
     uint32_t n_fail = 0;
     for (uint32_t q = 0; q < nq; q++) n_fail += (h_flags[q] & 2u) ? 1u : 0u;
     if (n_fail <= 2 + nq / 64) break;
-    scr = SDB_SCREEN_TC_BF16;
-    stt.n_candidates += n_fail;  // (diagnostic: queries handed down the ladder)
+    stt.n_candidates += n_fail;  // (diagnostic: queries handed up the ladder)
+  }
+  if (!rungs.empty()) {
+    c->ladder_scr = rungs[0].scr;
+    c->ladder_k = k;
+    c->ladder_rung = rung < rungs.size() ? rung : (uint32_t)rungs.size() - 1;
   }
   if (scr == SDB_SCREEN_NONE_EXACT) SDB_CUDA(cudaEventRecord(ev[2], st));
   SDB_CUDA(cudaMemcpyAsync(h_qflags.data(), c->d_qflags, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, st));

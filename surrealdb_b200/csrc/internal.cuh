@@ -97,6 +97,9 @@ struct Corpus {
   sdb_metric metric = SDB_COSINE;
   sdb_screen screen = SDB_SCREEN_AUTO;
   bool exact = true;  // false: skip the proof / exact fallback (approximate mode)
+  sdb_screen ladder_scr = SDB_SCREEN_AUTO;  // the screen the remembered rung belongs to
+  uint32_t ladder_k = 0;                    // ... and the k it was learnt for
+  uint32_t ladder_rung = 0;                 // rung of the (screen, slack) ladder the last batch settled on (api.cu)
   uint64_t cap = 0, n = 0;
   bool finalized = false;
   void* d_rows = nullptr;           // master copy, cap x dim (f32 or f64)

@@ -303,3 +303,24 @@ def test_projected_vector_functions_match_the_reference_arithmetic(ctx, dtype):
             assert O.num_magnitude(list(c64[r])) == got[r], r
     with pytest.raises(Exception, match="same dimension"):
         col.project("DOT", np.zeros(5))
+
+
+def test_slack_ladder_rescues_high_dimensional_large_k_batches(ctx):
+    # BASELINE config 4 shape (1536 dims, k=100) at a reduced row count: similarities are packed so tightly that the
+    # default slack cannot prove exactness; the ladder must widen k' (not send hundreds of queries to the exact kernel),
+    # remember the rung, and the answers must still be the oracle's bit for bit.
+    rng = np.random.default_rng(1536)
+    n, dim, nq, k = 200_000, 1536, 256, 100
+    corpus = rng.uniform(-1, 1, (n, dim)).astype(np.float32)
+    queries = rng.uniform(-1, 1, (nq, dim))
+    col = make_col(ctx, corpus, "COSINE")
+    rows, dist, cnt = col.knn(queries, k)
+    st1 = col.stats()
+    assert st1["n_fallback"] <= 2 + nq // 64, st1
+    for q in (0, 100, 255):
+        r, d = O.knn_topk(corpus, queries[q], "cosine", k)
+        assert list(rows[q, : cnt[q]]) == list(r) and dist[q, : cnt[q]].tobytes() == d.tobytes()
+    rows2, dist2, cnt2 = col.knn(queries, k)
+    st2 = col.stats()
+    assert st2["n_passes"] <= st1["n_passes"] and st2["n_fallback"] <= 2 + nq // 64   # starts on the remembered rung
+    assert rows2.tobytes() == rows.tobytes() and dist2.tobytes() == dist.tobytes()
