@@ -109,10 +109,10 @@ static sdb_status knn_device_locked(Corpus* c, const double* d_queries, uint32_t
     if (kp > 1024u) kp = 1024u > 2 * k ? 1024u : 2 * k;
     uint32_t cap = 4096;
     while (cap < 2u * pass_ratio(nq) * kp && cap < 16384u) cap <<= 1;  // a pass appends ~(R-1)*kp survivors per query
-    const void* q_before = c->d_q64;
+    const uint32_t gen_before = c->sc_gen;
     SDB_TRY(scratch_for(c, nq, cap, kp));
     cap = c->sc_cap;
-    if (first || q_before != c->d_q64) SDB_TRY(prep_queries(c, d_queries, nq, st));  // (re)allocation drops the prepared queries
+    if (first || gen_before != c->sc_gen) SDB_TRY(prep_queries(c, d_queries, nq, st));  // (re)allocation drops the prepared queries
     if (first) SDB_CUDA(cudaEventRecord(ev[1], st));
     first = false;
     const float eps_rel = rs == SDB_SCREEN_SIMT_F32

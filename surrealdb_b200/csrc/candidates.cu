@@ -127,6 +127,7 @@ static sdb_status ensure_scratch(Corpus* c, uint32_t nq, uint32_t cap, uint32_t 
   cudaFree(c->d_sub); cudaFree(c->d_sub_cnt);
   cudaFree(c->d_q8); cudaFree(c->d_q8scale); cudaFree(c->d_q8err); cudaFree(c->d_bscale); cudaFree(c->d_beps);
   c->sc_nq = c->sc_cap = c->sc_kp = 0;
+  c->sc_gen++;  // everything below is reallocated: prepared queries, candidate lists ... are gone
   const uint32_t nqa = nq_pad > c->sc_nq ? nq_pad : c->sc_nq;
   const uint32_t capa = cap;
   c->rr_stride = kp + SPECIAL_CAP;

@@ -98,6 +98,7 @@ struct Corpus {
   sdb_screen screen = SDB_SCREEN_AUTO;
   bool exact = true;  // false: skip the proof / exact fallback (approximate mode)
   sdb_screen ladder_scr = SDB_SCREEN_AUTO;  // the screen the remembered rung belongs to
+  uint32_t sc_gen = 0;                      // bumped whenever the per-query scratch is reallocated
   uint32_t ladder_k = 0;                    // ... and the k it was learnt for
   uint32_t ladder_rung = 0;                 // rung of the (screen, slack) ladder the last batch settled on (api.cu)
   uint64_t cap = 0, n = 0;
