@@ -67,8 +67,15 @@ static sdb_status knn_device_locked(Corpus* c, const double* d_queries, uint32_t
   }
   const uint64_t launches0 = ctx->launches;
   sdb_knn_stats stt{};
-  cudaEvent_t ev[4];
-  for (auto& e : ev) SDB_CUDA(cudaEventCreate(&e));
+  struct Events {  // destroyed on every return path
+    cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+    ~Events() {
+      for (auto& x : e)
+        if (x) cudaEventDestroy(x);
+    }
+  } evs;
+  cudaEvent_t* ev = evs.e;
+  for (auto& e : evs.e) SDB_CUDA(cudaEventCreate(&e));
   SDB_CUDA(cudaEventRecord(ev[0], st));
 
   // ---- choose the screen ----
@@ -124,7 +131,6 @@ static sdb_status knn_device_locked(Corpus* c, const double* d_queries, uint32_t
     for (const PassDesc& p : passes) {
       if (cancel && *cancel) {
         cudaStreamSynchronize(st);
-        for (auto& e : ev) cudaEventDestroy(e);
         set_error("query cancelled");
         return SDB_ECANCELLED;
       }
@@ -158,7 +164,6 @@ static sdb_status knn_device_locked(Corpus* c, const double* d_queries, uint32_t
   for (uint32_t q = 0; q < nq; q++) {
     if (((h_flags[q] & 2u) && (c->exact || scr == SDB_SCREEN_NONE_EXACT)) || (h_qflags[q] & 1u)) {
       if (cancel && *cancel) {
-        for (auto& e : ev) cudaEventDestroy(e);
         set_error("query cancelled");
         return SDB_ECANCELLED;
       }
@@ -170,7 +175,6 @@ static sdb_status knn_device_locked(Corpus* c, const double* d_queries, uint32_t
   SDB_CUDA(cudaStreamSynchronize(st));
   SDB_CUDA(cudaEventElapsedTime(&stt.screen_ms, ev[1], ev[2]));
   SDB_CUDA(cudaEventElapsedTime(&stt.total_ms, ev[0], ev[3]));
-  for (auto& e : ev) cudaEventDestroy(e);
   stt.screen_used = (uint32_t)scr;
   stt.n_special_rows = c->n_special;
   stt.kernel_launches = ctx->launches - launches0;
@@ -490,18 +494,25 @@ sdb_status sdb_corpus_project(sdb_corpus* c, const double* query, int fn, double
   SDB_CUDA(cudaSetDevice(c->ctx->device));
   cudaStream_t st = c->ctx->stream;
   double *d_q = nullptr, *d_vals = nullptr;
-  SDB_CUDA(cudaMallocAsync(&d_q, sizeof(double) * c->dim, st));
-  SDB_CUDA(cudaMallocAsync(&d_vals, sizeof(double) * c->n, st));
-  if (query) SDB_CUDA(cudaMemcpyAsync(d_q, query, sizeof(double) * c->dim, cudaMemcpyHostToDevice, st));
-  else SDB_CUDA(cudaMemsetAsync(d_q, 0, sizeof(double) * c->dim, st));
-  SDB_TRY(scratch_for(c, 1, 4096, 64));
-  SDB_TRY(prep_queries(c, d_q, 1, st));
-  SDB_TRY(exact_project(c, fn, d_vals, st));
-  SDB_CUDA(cudaMemcpyAsync(out, d_vals, sizeof(double) * c->n, cudaMemcpyDeviceToHost, st));
-  SDB_CUDA(cudaFreeAsync(d_q, st));
-  SDB_CUDA(cudaFreeAsync(d_vals, st));
-  SDB_CUDA(cudaStreamSynchronize(st));
-  return SDB_OK;
+  auto run = [&]() -> sdb_status {
+    SDB_CUDA(cudaMallocAsync(&d_q, sizeof(double) * c->dim, st));
+    SDB_CUDA(cudaMallocAsync(&d_vals, sizeof(double) * c->n, st));
+    if (query) SDB_CUDA(cudaMemcpyAsync(d_q, query, sizeof(double) * c->dim, cudaMemcpyHostToDevice, st));
+    else SDB_CUDA(cudaMemsetAsync(d_q, 0, sizeof(double) * c->dim, st));
+    SDB_TRY(scratch_for(c, 1, 4096, 64));
+    SDB_TRY(prep_queries(c, d_q, 1, st));
+    SDB_TRY(exact_project(c, fn, d_vals, st));
+    SDB_CUDA(cudaMemcpyAsync(out, d_vals, sizeof(double) * c->n, cudaMemcpyDeviceToHost, st));
+    return SDB_OK;
+  };
+  const sdb_status rc = run();
+  if (d_q) cudaFreeAsync(d_q, st);  // also on the error paths
+  if (d_vals) cudaFreeAsync(d_vals, st);
+  if (cudaStreamSynchronize(st) != cudaSuccess && rc == SDB_OK) {
+    set_error("sdb_corpus_project: %s", cudaGetErrorString(cudaGetLastError()));
+    return SDB_ECUDA;
+  }
+  return rc;
 }
 
 sdb_status sdb_topk_merge_device(sdb_ctx* ctx, uint32_t n_lists, uint32_t nq, uint32_t k, const uint64_t* d_rows,
