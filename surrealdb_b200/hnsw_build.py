@@ -1,13 +1,21 @@
 """Batch construction of an HNSW-shaped index on the GPU ("next" row).
 
-The reference builds its graph by serial insertion under a write lock (idx/trees/hnsw/mod.rs:230-394); that
-is not a data-parallel algorithm, so instead of porting it this builder uses the brute-force KNN engine:
-every layer l holds the elements whose level (floor(-ln U * ml), ml = 1/ln m -- the reference's level law,
-hnsw/mod.rs:263-266) is >= l, and each element's neighbours in layer l are its exact m (m0 on layer 0)
-nearest elements of that layer, found with the tcgen05 screen + exact re-rank.  The result is a valid input
-for the layer-walk kernel (same CSR format the reference's Hn records decode to); it is NOT the graph the
-reference would have built, so parity claims apply to the walk on a given graph, and quality is measured as
-recall against exact brute force.
+The reference builds its graph by serial insertion under a write lock (idx/trees/hnsw/mod.rs:230-394); that is not a
+data-parallel algorithm, so instead of porting it this builder works layer by layer on whole batches:
+
+  * levels follow the reference's law floor(-ln U * ml), ml = 1/ln m (hnsw/mod.rs:263-266); layer l holds the elements
+    of level >= l;
+  * candidates of an element = its efc (150) nearest elements of the layer, from the brute-force engine in approximate
+    mode -- the reference selects among the efc results of its insertion search (layer.rs:352-358); with prefix=True the
+    candidates come from the id prefix [0, 2^ceil(log2 i)) only, which emulates insertion order and keeps the long-range
+    links early elements get in the incremental algorithm;
+  * Heuristic::select (heuristic.rs:61-81,201-216) on the GPU (sdb_hnsw_select_neighbors) picks <= m_max of them;
+  * every selected edge is mirrored (graph.rs:52-64) and a node that ends up with more than m_max edges is re-selected
+    among its own picks plus up to (rev_factor-1)*m_max reverse edges ordered by distance (layer.rs:362-378).
+
+The result is a valid input for the layer-walk kernel (the same CSR the reference's Hn records decode to).  It is NOT
+the graph the reference would have built, so parity claims apply to the walk on a given graph; quality is measured as
+recall against exact brute force next to a reference-style (oracle) graph: tests/dev/hnsw_quality.py, DESIGN.md section 6.
 """
 import math
 
