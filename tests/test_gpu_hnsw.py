@@ -174,3 +174,22 @@ def test_filtered_knn_search_expands_all_docs_of_truthy_elements(ctx):
         assert all((doc // 2) % 3 == 0 for doc, _ in res)          # every element has a truthy doc ...
         seen_pair |= any(doc % 2 == 1 for doc, _ in res)           # ... and its other docs come along (index.rs:454-475)
     assert seen_pair
+
+
+def test_language_test_hnsw_goldens_through_gpu(ctx):
+    # hnsw_knn_with_condition_new_executor.surql and reproductions/7229_knn_k_distance_bypasses_hnsw.surql
+    from surrealdb_b200.hnsw import HnswIndex
+    h = O.Hnsw(1, "euclidean", m=12, efc=150, seed=3)
+    for v in (10, 20, 30, 40, 50, 60, 70):
+        h.insert(np.array([v], np.float32))
+    g = h.export()
+    elem_docs = [[i + 1] for i in range(7)]  # doc id = pts:<n>
+    idx = HnswIndex(ctx, g["vectors"], g["layers"], g["entry_point"], "EUCLIDEAN", elem_docs=elem_docs)
+    assert idx.knn_search([44.0], 2, 40, truthy_docs={1, 3, 5, 7}) == [(5, 6.0), (3, 14.0)]
+    assert idx.knn_search([44.0], 2, 40) == [(4, 4.0), (5, 6.0)]
+    h = O.Hnsw(4, "euclidean", m=12, efc=500, seed=3)
+    for v in ([1, 2, 3, 4], [4, 5, 6, 7], [8, 9, 10, 11]):
+        h.insert(np.array(v, np.float32))
+    g = h.export()
+    idx = HnswIndex(ctx, g["vectors"], g["layers"], g["entry_point"], "EUCLIDEAN", elem_docs=[[1], [2], [3]])
+    assert idx.knn_search([2.0, 3.0, 4.0, 5.0], 2, 100) == [(1, 2.0), (2, 4.0)]

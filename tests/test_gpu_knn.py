@@ -324,3 +324,23 @@ def test_slack_ladder_rescues_high_dimensional_large_k_batches(ctx):
     st2 = col.stats()
     assert st2["n_passes"] <= st1["n_passes"] and st2["n_fallback"] <= 2 + nq // 64   # starts on the remembered rung
     assert rows2.tobytes() == rows.tobytes() and dist2.tobytes() == dist.tobytes()
+
+
+def test_language_test_filtered_bruteforce_through_operator(ctx):
+    # bruteforce_knn_with_filter_new_executor.surql / bruteforce_knn_multisource_filter_new_executor.surql:
+    # TableScan [predicate: active = true] (or Union + Filter) feeds KnnTopK, which ranks the surviving rows
+    from surrealdb_b200 import KnnContext, KnnTopK
+    recs = [{"id": "pts:1", "point": [10, 0], "active": True}, {"id": "pts:2", "point": [2, 0], "active": False},
+            {"id": "pts:3", "point": [3, 0], "active": True}, {"id": "pts:4", "point": [100, 0], "active": True},
+            {"id": "pts:5", "point": [50, 0], "active": False}]
+    kc = KnnContext()
+    op = KnnTopK([r for r in recs if r["active"]], "point", [1, 0], 2, "Euclidean", ctx=ctx).with_knn_context(kc)
+    assert op.attrs() == [("field", "point"), ("k", "2"), ("distance", "Euclidean"), ("dimension", "2")]
+    out = op.execute()
+    assert [r["id"] for r in out] == ["pts:3", "pts:1"] and [kc[r["id"]] for r in out] == [2.0, 9.0]
+    multi = [{"id": "pts:1", "point": [10, 0], "active": True}, {"id": "pts:2", "point": [2, 0], "active": False},
+             {"id": "pts:3", "point": [3, 0], "active": True}, {"id": "pts2:1", "point": [1.5, 0], "active": False},
+             {"id": "pts2:2", "point": [4, 0], "active": True}]
+    kc = KnnContext()
+    out = KnnTopK([r for r in multi if r["active"]], "point", [1, 0], 2, "Euclidean", ctx=ctx).with_knn_context(kc).execute()
+    assert [r["id"] for r in out] == ["pts:3", "pts2:2"] and [kc[r["id"]] for r in out] == [2.0, 3.0]

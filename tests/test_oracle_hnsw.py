@@ -79,3 +79,23 @@ def test_csr_export_walk_equals_builder_walk():
         vis, exp = h.counters()
         b = O.hnsw_search_csr(g, q, 10, 32)
         assert list(a[0]) == list(b[0]) and list(a[1]) == list(b[1]) and b[2] == (vis, exp)
+
+
+def test_language_test_hnsw_goldens():
+    # language-tests/tests/language/indexes/knn/hnsw_knn_with_condition_new_executor.surql:
+    # 7 one-dimensional points, `WHERE flag = true AND point <|2,40|> [44]` -> pts:5 (6), pts:3 (14)
+    h = O.Hnsw(1, "euclidean", m=12, efc=150, seed=3)
+    for v in (10, 20, 30, 40, 50, 60, 70):
+        h.insert(np.array([v], np.float32))
+    g = h.export()
+    truthy = np.array([1, 0, 1, 0, 1, 0, 1], np.uint8)
+    ids, dist, _ = O.hnsw_search_csr(g, np.array([44], np.float32), 2, 40, truthy=truthy)
+    assert [int(i) + 1 for i in ids] == [5, 3] and list(dist) == [6.0, 14.0]
+    ids, dist, _ = O.hnsw_search_csr(g, np.array([44], np.float32), 2, 40)          # unfiltered: pts:4 (4), pts:5 (6)
+    assert [int(i) + 1 for i in ids] == [4, 5] and list(dist) == [4.0, 6.0]
+    # reproductions/7229_knn_k_distance_bypasses_hnsw.surql: <|2,100|> [2,3,4,5] -> pts:1 (2), pts:2 (4)
+    h = O.Hnsw(4, "euclidean", m=12, efc=500, seed=3)
+    for v in ([1, 2, 3, 4], [4, 5, 6, 7], [8, 9, 10, 11]):
+        h.insert(np.array(v, np.float32))
+    ids, dist = h.search(np.array([2, 3, 4, 5], np.float32), 2, 100)
+    assert [int(i) + 1 for i in ids] == [1, 2] and list(dist) == [2.0, 4.0]

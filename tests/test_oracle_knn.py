@@ -114,3 +114,19 @@ def test_legacy_priority_list_keeps_the_k_nearest_with_an_arbitrary_boundary_tie
         # KnnTopK's answer (ties by scan order) is one of the legacy path's possible answers
         topk = set(order[:k])
         assert set(must) <= topk and topk - set(must) <= set(tie)
+
+
+def test_language_test_filtered_bruteforce_goldens():
+    # language-tests/tests/language/indexes/knn/bruteforce_knn_with_filter_new_executor.surql: the predicate is
+    # applied by the scan below KnnTopK, so the operator only ever sees the active rows
+    pts = {1: ([10, 0], True), 2: ([2, 0], False), 3: ([3, 0], True), 4: ([100, 0], True), 5: ([50, 0], False)}
+    active = [(i, p) for i, (p, a) in pts.items() if a]
+    corpus = np.array([p for _, p in active], np.float64)
+    rows, dist = O.knn_topk(corpus, np.array([1.0, 0.0]), "euclidean", 2)
+    assert [active[int(r)][0] for r in rows] == [3, 1] and list(dist) == [2.0, 9.0]
+    # ... multisource variant (bruteforce_knn_multisource_filter_new_executor.surql): Union of two tables, then Filter
+    recs = [("pts:1", [10, 0], True), ("pts:2", [2, 0], False), ("pts:3", [3, 0], True),
+            ("pts2:1", [1.5, 0], False), ("pts2:2", [4, 0], True)]
+    act = [r for r in recs if r[2]]
+    rows, dist = O.knn_topk(np.array([r[1] for r in act], np.float64), np.array([1.0, 0.0]), "euclidean", 2)
+    assert [act[int(r)][0] for r in rows] == ["pts:3", "pts2:2"] and list(dist) == [2.0, 3.0]
