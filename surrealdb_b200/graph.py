@@ -98,21 +98,41 @@ class GraphStore:
         self._rel = rel
         self._csr = {}
 
+    def csr_arrays(self, edge_table, direction):
+        """(row_ptr, col_idx) of one `node <dir> edge_table <dir> node` step, neighbours in the order the reference's
+        KV scan yields them: per source the graph keys sort by (direction, edge table, edge record key)
+        (key/graph/mod.rs:122-137).  direction: 'out' (->), 'in' (<-) or 'both' (<->): GraphEdgeScan scans In, then
+        Out (exec/operators/scan/graph.rs:203-207), and the second `<->` of the pair yields both endpoints of every
+        edge record, In pointer (the edge's source node) first."""
+        adj = [[] for _ in self.names]
+        for src, tb, eid, dst in self._rel:
+            if tb != edge_table:
+                continue
+            ek = _key_order(eid)
+            s, d = self.idx[src], self.idx[dst]
+            if direction == "out":
+                adj[s].append(((1, ek, 0), d))
+            elif direction == "in":
+                adj[d].append(((0, ek, 0), s))
+            elif direction == "both":
+                adj[d].append(((0, ek, 0), s))  # edges pointing at d: [source, d]
+                adj[d].append(((0, ek, 1), d))
+                adj[s].append(((1, ek, 0), s))  # edges leaving s: [s, target]
+                adj[s].append(((1, ek, 1), d))
+            else:
+                raise ValueError(f"direction {direction!r}: expected 'out', 'in' or 'both'")
+        rp, ci = [0], []
+        for a in adj:
+            a.sort()
+            ci += [t for _, t in a]
+            rp.append(len(ci))
+        return np.asarray(rp, np.uint64), np.asarray(ci, np.uint32)
+
     def csr(self, edge_table, direction):
         key = (edge_table, direction)
         if key not in self._csr:
-            adj = [[] for _ in self.names]
-            for src, tb, eid, dst in self._rel:
-                if tb != edge_table:
-                    continue
-                s, d = (src, dst) if direction == "out" else (dst, src)
-                adj[self.idx[s]].append((_key_order(eid), self.idx[d]))
-            rp, ci = [0], []
-            for a in adj:
-                a.sort()
-                ci += [t for _, t in a]
-                rp.append(len(ci))
-            self._csr[key] = CsrGraph(self.ctx, np.asarray(rp, np.uint64), np.asarray(ci, np.uint32))
+            rp, ci = self.csr_arrays(edge_table, direction)
+            self._csr[key] = CsrGraph(self.ctx, rp, ci)
         return self._csr[key]
 
     def ids(self, names):

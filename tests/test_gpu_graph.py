@@ -126,3 +126,14 @@ def test_edge_cases(ctx):
     g = CsrGraph(ctx, rp, ci)
     fr = np.arange(n, dtype=np.uint32)
     assert np.array_equal(expand([g], fr), O.graph_hop(rp, ci, fr, 0))
+
+
+def test_language_test_bidirectional(store):
+    # language-tests/tests/language/graph/traversal_bidirectional.surql (results 0-2): `<->knows<->person`
+    from test_oracle_graph import BIDIRECTIONAL
+    for start, want in BIDIRECTIONAL.items():
+        assert fmt(store.lookup([start], [("both", "knows")])) == want, start
+    # two bidirectional hops in one fused call equal two single calls (multiset expansion keeps order and duplicates)
+    one = store.lookup(["person:alice"], [("both", "knows")])
+    two = store.lookup(["person:alice"], [("both", "knows"), ("both", "knows")])
+    assert two == [x for n in one for x in store.lookup([n], [("both", "knows")])]

@@ -120,3 +120,27 @@ def test_per_source_limit_and_empty():
     assert list(O.graph_hop(rp, ci, [0, 2, 0], 2)) == [1, 2, 0, 1, 1, 2]
     assert list(O.graph_hop(rp, ci, [1], 0)) == []
     assert list(O.graph_hop(rp, ci, [], 0)) == []
+
+
+BIDIRECTIONAL = {  # language-tests/tests/language/graph/traversal_bidirectional.surql, results 0-2
+    "person:alice": "[person:bob, person:alice, person:charlie, person:alice, person:alice, person:bob, person:alice, person:ceo]",
+    "person:lead_infra": "[person:lead_frontend, person:lead_infra, person:lead_infra, person:lead_frontend]",
+    "person:dir_platform": "[person:dir_product, person:dir_platform, person:dir_platform, person:dir_product]",
+}
+
+
+def test_bidirectional_traversal_matches_language_test():
+    # `<->knows<->person`: GraphEdgeScan scans Dir::In then Dir::Out (scan/graph.rs:203-207); the product's host-side
+    # CSR builder (no GPU needed for the arrays) must yield the reference's order, duplicates included
+    from surrealdb_b200.graph import GraphStore
+    rel = [(r["src"], r["edge_tb"], r["edge_id"], r["dst"]) for r in G["relations"]]
+    store = GraphStore(None, rel)
+    rp, ci = store.csr_arrays("knows", "both")
+    for start, want in BIDIRECTIONAL.items():
+        fr = O.graph_hop(rp, ci if ci.size else np.zeros(1, np.uint32), store.ids([start]))
+        assert "[" + ", ".join(store.to_names(fr)) + "]" == want, start
+    # the one-directional arrays equal this file's own restatement of the key order
+    for d in ("out", "in"):
+        rp2, ci2 = store.csr_arrays("knows", d)
+        ref = csr("knows", d)
+        assert store.names == ref.names and rp2.tolist() == ref.row_ptr.tolist() and ci2.tolist() == ref.col_idx.tolist()
