@@ -101,14 +101,14 @@ class GraphStore:
     def csr_arrays(self, edge_table, direction):
         """(row_ptr, col_idx) of one `node <dir> edge_table <dir> node` step, neighbours in the order the reference's
         KV scan yields them: per source the graph keys sort by (direction, edge table, edge record key)
-        (key/graph/mod.rs:122-137).  direction: 'out' (->), 'in' (<-) or 'both' (<->): GraphEdgeScan scans In, then
+        (key/graph/mod.rs:122-137).  edge_table=None is the `?` wildcard (all edge tables, scan/graph.rs:303-311).  direction: 'out' (->), 'in' (<-) or 'both' (<->): GraphEdgeScan scans In, then
         Out (exec/operators/scan/graph.rs:203-207), and the second `<->` of the pair yields both endpoints of every
         edge record, In pointer (the edge's source node) first."""
         adj = [[] for _ in self.names]
         for src, tb, eid, dst in self._rel:
-            if tb != edge_table:
+            if edge_table is not None and tb != edge_table:  # None = the `?` wildcard: every edge table, in key order
                 continue
-            ek = _key_order(eid)
+            ek = (tb.encode(), _key_order(eid))  # `ft` (the edge table) sorts before `fk` (the edge record key)
             s, d = self.idx[src], self.idx[dst]
             if direction == "out":
                 adj[s].append(((1, ek, 0), d))

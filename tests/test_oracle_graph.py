@@ -144,3 +144,17 @@ def test_bidirectional_traversal_matches_language_test():
         rp2, ci2 = store.csr_arrays("knows", d)
         ref = csr("knows", d)
         assert store.names == ref.names and rp2.tolist() == ref.row_ptr.tolist() and ci2.tolist() == ref.col_idx.tolist()
+
+
+def test_wildcard_edge_tables_match_language_test():
+    # language-tests/tests/language/graph/wildcards.surql, results 1 and 3: `->?->?` / `<-?<-?` scan every edge table of
+    # the source in key order (edge table name, then edge record key)
+    from surrealdb_b200.graph import GraphStore
+    store = GraphStore(None, [(r["src"], r["edge_tb"], r["edge_id"], r["dst"]) for r in G["relations"]])
+    want_out = ("[skill:go, skill:postgresql, skill:redis, skill:rust, person:bob, person:ceo, person:bob, "
+                "person:lead_infra, project:auth, project:database]")
+    want_in = "[person:bob, person:charlie, person:lead_infra]"
+    for direction, want in (("out", want_out), ("in", want_in)):
+        rp, ci = store.csr_arrays(None, direction)
+        fr = O.graph_hop(rp, ci, store.ids(["person:alice"]))
+        assert "[" + ", ".join(store.to_names(fr)) + "]" == want, direction
