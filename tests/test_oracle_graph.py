@@ -158,3 +158,24 @@ def test_wildcard_edge_tables_match_language_test():
         rp, ci = store.csr_arrays(None, direction)
         fr = O.graph_hop(rp, ci, store.ids(["person:alice"]))
         assert "[" + ", ".join(store.to_names(fr)) + "]" == want, direction
+
+
+def test_bounded_cycles_and_inclusive_collect_match_language_tests():
+    # language-tests/tests/language/graph/cycles_bounded.surql (results 0-5): default recursion through the
+    # alice -> bob -> charlie -> alice cycle keeps duplicates and returns the frontier at the depth bound
+    k = csr("knows")
+    a = [k.idx["person:alice"]]
+    want = ["[person:bob, person:ceo, person:alice, person:dana, person:charlie]",
+            "[person:bob, person:ceo]",
+            "[person:alice, person:charlie, person:dana]",
+            "[person:alice, person:charlie, person:dana, person:bob, person:ceo, person:charlie, person:alice, person:dana, "
+            "person:bob, person:ceo, person:alice, person:dana, person:charlie, person:bob, person:ceo, person:charlie, "
+            "person:alice, person:charlie, person:dana, person:alice, person:dana]"]
+    for (lo, hi), w in zip(((1, 3), (1, 1), (2, 2), (1, 6)), want):
+        assert fmt(k, O.graph_recurse_default(k.row_ptr, k.col_idx, a, lo, hi)) == w, (lo, hi)
+    assert fmt(k, O.graph_recurse_default(k.row_ptr, k.col_idx, [k.idx["person:dir_platform"]], 1, 3)) == "[person:dir_product]"
+    assert fmt(k, O.graph_recurse_default(k.row_ptr, k.col_idx, [k.idx["person:lead_infra"]], 1, 3)) == "[person:lead_frontend]"
+    # path_inclusive.surql result 0: `.{..+collect+inclusive}->reports_to->person` emits the start node first
+    r = csr("reports_to")
+    got = O.graph_collect(r.row_ptr, r.col_idx, [r.idx["person:alice"]], 1, 256, True)
+    assert fmt(r, got) == "[person:alice, person:lead_infra, person:dir_platform, person:vp_eng, person:ceo]"
