@@ -268,7 +268,11 @@ class Hnsw:
                                                 C.c_uint64(seed)))
 
     def __del__(self):
-        lib().orc_hnsw_free(self.h)
+        try:
+            if getattr(self, "h", None):
+                lib().orc_hnsw_free(self.h)
+        except Exception:  # interpreter shutdown
+            pass
 
     def insert(self, v, level=None):
         v = np.ascontiguousarray(v, np.float32)

@@ -99,3 +99,20 @@ def test_language_test_hnsw_goldens():
         h.insert(np.array(v, np.float32))
     ids, dist = h.search(np.array([2, 3, 4, 5], np.float32), 2, 100)
     assert [int(i) + 1 for i in ids] == [1, 2] and list(dist) == [2.0, 4.0]
+
+
+def test_simple_hnsw_of_the_reference():
+    # idx/trees/hnsw/mod.rs:1001-1037 test_simple_hnsw: 11 two-dimensional points, m = 3 (m0 = 6), efc = 500,
+    # extend_candidates + keep_pruned_connections; knn_search((-2,-3), k = 10, ef = 501) must return 10 results
+    pts = [(-2, -3), (-2, 1), (-4, 3), (-3, 1), (-1, 1), (-2, 3), (3, 0), (-1, -2), (-2, 2), (-4, -2), (0, 3)]
+    for seed in range(8):  # the level assignment is random in the reference too: the property holds for every draw
+        h = O.Hnsw(2, "euclidean", m=3, m0=6, efc=500, extend_candidates=True, keep_pruned_connections=True, seed=seed)
+        for p in pts:
+            h.insert(np.array(p, np.float32))
+        assert h.check_props()
+        ids, dist = h.search(np.array([-2, -3], np.float32), 10, 501)
+        assert len(ids) == 10 and ids[0] == 0 and dist[0] == 0.0
+        assert list(dist) == sorted(dist)
+        # with ef >= n the walk sees every connected element: the result is the exact top-10
+        bi, bd = O.vec_knn_f32(np.array(pts, np.float32), np.array([-2, -3], np.float32), "euclidean", 10)
+        assert list(dist) == list(bd)
