@@ -7,7 +7,7 @@ hand-written sm_100a CUDA in surrealdb_b200/csrc.
 from ._lib import SdbError, SO_PATH  # noqa: F401
 from .engine import Context, VectorColumn  # noqa: F401
 from .operators import Distance, KnnBruteForceLegacy, KnnContext, KnnTopK  # noqa: F401
-from .graph import CsrGraph, GraphStore  # noqa: F401
+from .graph import CsrGraph, GraphEdgeScan, GraphStore  # noqa: F401
 from .hnsw import HnswIndex  # noqa: F401
 
 __version__ = "0.1.0"

@@ -8,6 +8,8 @@
                       exec/planner/idiom.rs:161-193): multiset, order-preserving
   GraphStore.collect  `.{min..max+collect[+inclusive]}` (exec/operators/recursion/collect.rs:74-143)
   GraphStore.recurse  default `.{min..max}` recursion (exec/operators/recursion/default.rs:75-133)
+  GraphEdgeScan       the operator itself: new(input, direction, edge_tables, output_mode, version).with_limit(n)
+                      (exec/operators/scan/graph.rs:89-147) -- name(), attrs(), execute()
 """
 import ctypes as C
 
@@ -101,14 +103,23 @@ class GraphStore:
     def csr_arrays(self, edge_table, direction):
         """(row_ptr, col_idx) of one `node <dir> edge_table <dir> node` step, neighbours in the order the reference's
         KV scan yields them: per source the graph keys sort by (direction, edge table, edge record key)
-        (key/graph/mod.rs:122-137).  edge_table=None is the `?` wildcard (all edge tables, scan/graph.rs:303-311).  direction: 'out' (->), 'in' (<-) or 'both' (<->): GraphEdgeScan scans In, then
+        (key/graph/mod.rs:122-137).  edge_table=None is the `?` wildcard (all edge tables, scan/graph.rs:303-311); a tuple of
+        names = one key range per table, scanned in the listed order (scan/graph.rs:312-324).  direction: 'out' (->), 'in' (<-) or 'both' (<->): GraphEdgeScan scans In, then
         Out (exec/operators/scan/graph.rs:203-207), and the second `<->` of the pair yields both endpoints of every
         edge record, In pointer (the edge's source node) first."""
         adj = [[] for _ in self.names]
         for src, tb, eid, dst in self._rel:
-            if edge_table is not None and tb != edge_table:  # None = the `?` wildcard: every edge table, in key order
-                continue
-            ek = (tb.encode(), _key_order(eid))  # `ft` (the edge table) sorts before `fk` (the edge record key)
+            if edge_table is None:  # the `?` wildcard: one range over every edge table, i.e. key order by table name
+                tkey = tb.encode()
+            elif isinstance(edge_table, (tuple, list)):  # one range per listed table, scanned in the listed order
+                if tb not in edge_table:
+                    continue
+                tkey = list(edge_table).index(tb)
+            else:
+                if tb != edge_table:
+                    continue
+                tkey = 0
+            ek = (tkey, _key_order(eid))  # `ft` (the edge table) sorts before `fk` (the edge record key)
             s, d = self.idx[src], self.idx[dst]
             if direction == "out":
                 adj[s].append(((1, ek, 0), d))
@@ -129,11 +140,15 @@ class GraphStore:
         return np.asarray(rp, np.uint64), np.asarray(ci, np.uint32)
 
     def csr(self, edge_table, direction):
-        key = (edge_table, direction)
+        key = (tuple(edge_table) if isinstance(edge_table, list) else edge_table, direction)
         if key not in self._csr:
             rp, ci = self.csr_arrays(edge_table, direction)
             self._csr[key] = CsrGraph(self.ctx, rp, ci)
         return self._csr[key]
+
+    def expand_snapshot(self, edge_table, direction, frontier, per_source_limit=0):
+        """one GraphEdgeScan step over the snapshot of (edge tables, direction) on the GPU"""
+        return expand([self.csr(edge_table, direction)], frontier, per_source_limit)
 
     def ids(self, names):
         return np.asarray([self.idx[n] for n in names], np.uint32)
@@ -161,3 +176,48 @@ class GraphStore:
                 return self.to_names(cur) if depth > min_depth else None
             cur = nxt
         return self.to_names(cur) if depth >= min_depth else None
+
+
+class GraphEdgeScan:
+    """Mirror of the reference operator (exec/operators/scan/graph.rs:89-147):
+    `GraphEdgeScan::new(input, direction, edge_tables, output_mode, version)` + `.with_limit(n)`, `name()`, `attrs()`,
+    `execute()`.  `input` yields the source record ids (what the child operator streams); the result is the target
+    record id of every matching edge pointer, per source in KV key order, duplicates kept -- served by one
+    sdb_graph_expand over the CSR snapshot of (direction, edge tables).  Range bounds on an edge table, `version`
+    (time travel) and output modes other than TargetId are the cases INTEGRATION.md leaves on the KV path."""
+
+    DIRECTIONS = {"->": "out", "<-": "in", "<->": "both"}
+
+    def __init__(self, input, direction, edge_tables, output_mode="TargetId", version=None, store=None):
+        if direction not in self.DIRECTIONS:
+            raise L.SdbError(L.SDB_EUNSUPPORTED, f"direction {direction!r} is not served by the GPU snapshot")
+        if output_mode != "TargetId" or version is not None:
+            raise L.SdbError(L.SDB_EUNSUPPORTED, "only GraphScanOutput::TargetId without VERSION is served by the GPU snapshot")
+        self.input, self.direction, self.edge_tables = input, direction, list(edge_tables)
+        self.output_mode, self.version, self.limit, self.store = output_mode, version, None, store
+
+    def with_limit(self, limit):
+        self.limit = int(limit)
+        return self
+
+    def name(self):
+        return "GraphEdgeScan"
+
+    def attrs(self):
+        a = [("direction", self.direction), ("tables", ", ".join(self.edge_tables) if self.edge_tables else "*"),
+             ("output", self.output_mode)]
+        if self.limit is not None:
+            a.append(("limit", str(self.limit)))
+        return a
+
+    def _snapshot(self):
+        tables = None if not self.edge_tables else (self.edge_tables[0] if len(self.edge_tables) == 1 else tuple(self.edge_tables))
+        return tables, self.DIRECTIONS[self.direction]
+
+    def execute(self):
+        tables, d = self._snapshot()
+        sources = list(self.input)
+        unknown = [s for s in sources if s not in self.store.idx]  # a record without edges has no graph keys: no output
+        frontier = self.store.ids([s for s in sources if s in self.store.idx])
+        del unknown
+        return self.store.to_names(self.store.expand_snapshot(tables, d, frontier, self.limit or 0))

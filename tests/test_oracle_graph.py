@@ -179,3 +179,36 @@ def test_bounded_cycles_and_inclusive_collect_match_language_tests():
     r = csr("reports_to")
     got = O.graph_collect(r.row_ptr, r.col_idx, [r.idx["person:alice"]], 1, 256, True)
     assert fmt(r, got) == "[person:alice, person:lead_infra, person:dir_platform, person:vp_eng, person:ceo]"
+
+
+def test_graph_edge_scan_operator_mirror(monkeypatch):
+    # the reference's own unit test (exec/operators/scan/graph.rs:415-440) on the mirror, plus execute() with the GPU
+    # step replaced by the oracle hop over the SAME CSR arrays (the ctypes call itself is covered by test_gpu_graph.py)
+    from surrealdb_b200.graph import GraphEdgeScan, GraphStore
+    scan = GraphEdgeScan([], "->", ["knows", "follows"], "TargetId", None)
+    assert scan.name() == "GraphEdgeScan"
+    attrs = scan.attrs()
+    assert ("direction", "->") in attrs and any(k == "tables" and "knows" in v for k, v in attrs)
+    assert GraphEdgeScan([], "<->", [], "TargetId").with_limit(3).attrs() == \
+        [("direction", "<->"), ("tables", "*"), ("output", "TargetId"), ("limit", "3")]
+    store = GraphStore(None, [(r["src"], r["edge_tb"], r["edge_id"], r["dst"]) for r in G["relations"]])
+
+    def cpu_step(self, edge_table, direction, frontier, per_source_limit=0):
+        rp, ci = self.csr_arrays(edge_table, direction)
+        return O.graph_hop(rp, ci if ci.size else np.zeros(1, np.uint32), frontier, per_source_limit)
+    monkeypatch.setattr(GraphStore, "expand_snapshot", cpu_step)
+    # wildcards.surql result 1, traversal_bidirectional.surql result 0, traversal_forward-style single table
+    assert GraphEdgeScan(["person:alice"], "->", [], store=store).execute() == \
+        ["skill:go", "skill:postgresql", "skill:redis", "skill:rust", "person:bob", "person:ceo", "person:bob",
+         "person:lead_infra", "project:auth", "project:database"]
+    assert GraphEdgeScan(["person:alice"], "<->", ["knows"], store=store).execute() == \
+        ["person:bob", "person:alice", "person:charlie", "person:alice", "person:alice", "person:bob", "person:alice", "person:ceo"]
+    # two listed tables: one key range per table, in the LISTED order (not the key order of the table names)
+    ab = GraphEdgeScan(["person:alice"], "->", ["works_on", "knows"], store=store).execute()
+    assert ab == ["project:auth", "project:database", "person:bob", "person:ceo"]
+    # per-source limit and a source without any edge key
+    assert GraphEdgeScan(["person:alice", "nobody:1", "person:bob"], "->", ["knows"], store=store).with_limit(1).execute() == \
+        ["person:bob", GraphEdgeScan(["person:bob"], "->", ["knows"], store=store).execute()[0]]
+    import pytest
+    with pytest.raises(Exception, match="not served by the GPU snapshot"):
+        GraphEdgeScan([], "<~", ["knows"])
