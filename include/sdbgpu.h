@@ -40,11 +40,12 @@ typedef enum {
   SDB_ECUDA = 4,      /* CUDA runtime/driver failure, or no sm_100 device                           */
   SDB_ECANCELLED = 5, /* cancel flag observed -> Error::QueryCancelled (exec/operators/knn_topk.rs:186) */
   SDB_EUNSUPPORTED = 6,
-  SDB_EOVERFLOW = 7   /* caller-provided output capacity too small                                  */
+  SDB_EOVERFLOW = 7,  /* caller-provided output capacity too small / too many batches in flight      */
+  SDB_ENCCL = 8       /* NCCL failure (multi-GPU entry points)                                      */
 } sdb_status;
 
-/* catalog::Distance (catalog/schema/index.rs:247-284).  Round 1 implements COSINE and EUCLIDEAN
- * (the two metrics BASELINE.json's north_star names); the others return SDB_EUNSUPPORTED. */
+/* catalog::Distance (catalog/schema/index.rs:247-284).  COSINE and EUCLIDEAN are screened on the tensor cores and
+ * re-ranked exactly; the other six run through the exact kernel (sequential f64, Distance::compute op for op). */
 typedef enum {
   SDB_CHEBYSHEV = 0,
   SDB_COSINE = 1,
@@ -68,7 +69,7 @@ typedef enum {
   SDB_SCREEN_SIMT_F32 = 1,   /* f32 streaming SIMT kernel                                             */
   SDB_SCREEN_TC_BF16 = 2,    /* tcgen05 kind::f16, bf16 operands                                        */
   SDB_SCREEN_NONE_EXACT = 3, /* no screen: exact f64 kernel for every query                              */
-  SDB_SCREEN_TC_INT8 = 4     /* tcgen05 kind::i8, per-row int8 quantisation (cosine); falls back to bf16 */
+  SDB_SCREEN_TC_INT8 = 4     /* tcgen05 kind::i8, int8 copy of the normalised rows (cosine); falls back to bf16 */
 } sdb_screen;
 
 /* counters of the last brute-force call on a corpus (diagnostics / bench roofline arithmetic) */
@@ -77,7 +78,7 @@ typedef struct {
   uint32_t n_passes;         /* threshold-refinement passes of the screen                      */
   uint32_t n_fallback;       /* queries re-run through the exact kernel (verification failed)  */
   uint32_t n_special_rows;   /* rows with zero / non-finite norm (always exact-ranked)         */
-  uint64_t n_candidates;     /* candidates appended by the screen over all passes              */
+  uint64_t n_candidates;     /* largest candidate set of any query of the batch                */
   uint64_t n_reranked;       /* exact f64 distances computed by the re-rank kernel             */
   uint64_t kernel_launches;  /* kernels launched by this call                                  */
   float screen_ms;           /* device time of the screening kernels (CUDA events)             */
@@ -116,7 +117,14 @@ sdb_status sdb_corpus_set_skip(sdb_corpus*, const uint8_t* skip, uint64_t n);
  * list.  Must be called after the last append and before searching. */
 sdb_status sdb_corpus_finalize(sdb_corpus*);
 uint64_t sdb_corpus_rows(const sdb_corpus*);
+/* copies rows [first_row, first_row + n) of the device-resident master copy back to host memory (n x dim of the
+ * corpus dtype): lets a harness check results against exactly the bytes the kernels read */
+sdb_status sdb_corpus_read_rows(sdb_corpus*, uint64_t first_row, uint64_t n, void* out);
 sdb_status sdb_corpus_set_screen(sdb_corpus*, sdb_screen);
+/* schedule of the tensor-core screens (results are identical; tuning / A-B only).  streaming = 1 (default): a scored
+ * sample seeds the thresholds, then ONE launch streams the rest of the corpus while refiner warps raise the thresholds
+ * inside the kernel.  streaming = 0: the multi-pass schedule (a launch + a selection kernel per geometric pass). */
+sdb_status sdb_corpus_set_schedule(sdb_corpus*, int streaming);
 /* exact = 1 (default): results are proven identical to the reference (queries whose proof fails are re-run by the exact
  * kernel).  exact = 0: opt-in approximate mode -- the exactly re-ranked best candidates of the screen are returned
  * without the proof / fallback (used by the index builder, where near-duplicate clusters would otherwise send every
@@ -133,6 +141,49 @@ sdb_status sdb_knn_bruteforce_device(sdb_corpus*, const double* d_queries, uint3
                                      uint64_t row_base, uint64_t* d_out_rows, double* d_out_dist,
                                      uint32_t* d_out_count);
 sdb_status sdb_knn_last_stats(const sdb_corpus*, sdb_knn_stats* out);
+
+/* ---- asynchronous batches.  submit enqueues a whole batch (query preparation, screen, exact re-rank, proof, result
+ * copy) on the context's stream WITHOUT any host synchronisation and returns a ticket; wait blocks until that batch is
+ * complete (and, for the rare query whose proof failed, runs the exact kernel).  Up to 4 batches may be in flight per
+ * corpus, so the host can prepare / transfer batch i+1 while batch i computes -- the shape in which concurrent
+ * SurrealQL queries arrive at KnnTopK::execute (one operator instance per query, exec/operators/knn_topk.rs:166).
+ * Buffers handed to submit must stay valid until the matching wait returns.  Host variant: `queries` and `out_*` are
+ * host buffers (pinned for overlap); the H2D copy runs on a separate copy stream.  Tickets complete in any order. */
+sdb_status sdb_knn_submit(sdb_corpus*, const double* queries, uint32_t nq, uint32_t k, uint64_t* out_rows,
+                          double* out_dist, uint32_t* out_count, uint32_t* ticket);
+sdb_status sdb_knn_submit_device(sdb_corpus*, const double* d_queries, uint32_t nq, uint32_t k, uint64_t row_base,
+                                 uint64_t* d_out_rows, double* d_out_dist, uint32_t* d_out_count, uint32_t* ticket);
+sdb_status sdb_knn_wait(sdb_corpus*, uint32_t ticket);
+
+/* ---- multi-GPU brute force: the corpus is row-sharded, every shard searches its rows, ONE NCCL
+ * all-gather moves the per-shard top-k blocks and a merge kernel on every rank produces the global top-k by
+ * (distance, global row).  NCCL lives inside the library (bound at run time with dlopen, so single-GPU users need
+ * none); everything is enqueued on the context's stream without host synchronisation.
+ *   one process per GPU : rank 0 calls sdb_comm_unique_id and hands the 128 bytes to the other ranks out of band;
+ *                         every rank calls sdb_comm_init_rank on its context (collective).
+ *   one process, N GPUs : sdb_ctx_create_multi creates the N contexts and their communicator (ncclCommInitAll);
+ *                         sdb_knn_sharded_multi drives all shards from the calling thread.
+ * A corpus becomes a shard by sdb_corpus_set_row_base(first global row).  sdb_knn_sharded_* are COLLECTIVE: every
+ * rank must call them with the same queries, nq and k, in the same order.  Exactness across ranks: each block carries
+ * the number of queries its rank must still repair on the host (failed proof, special queries); every rank sees every
+ * header after the all-gather, so all ranks agree on whether a repair round (local exact re-runs, second all-gather
+ * and merge) is needed -- no extra collective. */
+#define SDB_COMM_ID_BYTES 128
+sdb_status sdb_comm_unique_id(uint8_t* id128);
+sdb_status sdb_comm_init_rank(sdb_ctx*, int nranks, int rank, const uint8_t* id128);
+int sdb_comm_size(const sdb_ctx*);
+int sdb_comm_rank(const sdb_ctx*);
+sdb_status sdb_ctx_create_multi(const int* devices, int ndev, sdb_ctx** out /* [ndev] */);
+sdb_status sdb_corpus_set_row_base(sdb_corpus*, uint64_t first_global_row);
+sdb_status sdb_knn_sharded_submit(sdb_corpus*, const double* queries, uint32_t nq, uint32_t k, uint64_t* out_rows,
+                                  double* out_dist, uint32_t* out_count, uint32_t* ticket);
+sdb_status sdb_knn_sharded_submit_device(sdb_corpus*, const double* d_queries, uint32_t nq, uint32_t k,
+                                         uint64_t* d_out_rows, double* d_out_dist, uint32_t* d_out_count,
+                                         uint32_t* ticket);
+sdb_status sdb_knn_sharded_wait(sdb_corpus*, uint32_t ticket);
+/* one process, N GPUs: shards[i] lives on the i-th context of sdb_ctx_create_multi; queries / out_* are host buffers */
+sdb_status sdb_knn_sharded_multi(sdb_corpus* const* shards, int n_shards, const double* queries, uint32_t nq, uint32_t k,
+                                 uint64_t* out_rows, double* out_dist, uint32_t* out_count);
 /* ---- projected scalar vector functions over a whole column: replaces a per-row evaluation of
  *      vector::distance::* / vector::similarity::* / vector::dot / vector::magnitude (fnc/vector.rs:25-143,
  *      fnc/util/math/vector.rs:61-314) in `SELECT vector::similarity::cosine(emb, $q) FROM t`.

@@ -9,9 +9,11 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "csrc", "libsdbgpu.so")
 
-SDB_OK, SDB_EINVAL, SDB_EDIM, SDB_ENOMEM, SDB_ECUDA, SDB_ECANCELLED, SDB_EUNSUPPORTED, SDB_EOVERFLOW = range(8)
+(SDB_OK, SDB_EINVAL, SDB_EDIM, SDB_ENOMEM, SDB_ECUDA, SDB_ECANCELLED, SDB_EUNSUPPORTED, SDB_EOVERFLOW,
+ SDB_ENCCL) = range(9)
 STATUS_NAMES = ["SDB_OK", "SDB_EINVAL", "SDB_EDIM", "SDB_ENOMEM", "SDB_ECUDA", "SDB_ECANCELLED",
-                "SDB_EUNSUPPORTED", "SDB_EOVERFLOW"]
+                "SDB_EUNSUPPORTED", "SDB_EOVERFLOW", "SDB_ENCCL"]
+COMM_ID_BYTES = 128
 METRIC = {"CHEBYSHEV": 0, "COSINE": 1, "EUCLIDEAN": 2, "HAMMING": 3, "JACCARD": 4, "MANHATTAN": 5,
           "MINKOWSKI": 6, "PEARSON": 7}
 DTYPE = {"F32": 0, "F64": 1}
@@ -23,8 +25,11 @@ ABI_SYMBOLS = [
     "sdb_ctx_create", "sdb_ctx_destroy", "sdb_last_error", "sdb_version", "sdb_pinned_alloc", "sdb_pinned_free",
     "sdb_ctx_kernel_launches", "sdb_ctx_stream", "sdb_corpus_create", "sdb_corpus_destroy", "sdb_corpus_append",
     "sdb_corpus_append_device", "sdb_corpus_append_synthetic", "sdb_corpus_set_skip", "sdb_corpus_finalize",
-    "sdb_corpus_rows", "sdb_corpus_set_screen", "sdb_corpus_set_exact", "sdb_knn_bruteforce", "sdb_knn_bruteforce_device",
-    "sdb_knn_last_stats", "sdb_corpus_project", "sdb_topk_merge_device", "sdb_hnsw_load", "sdb_hnsw_destroy", "sdb_stage_decode_vectors", "sdb_stage_decode_nodes", "sdb_hnsw_load_staged", "sdb_hnsw_search", "sdb_hnsw_search_filtered", "sdb_hnsw_select_neighbors",
+    "sdb_corpus_rows", "sdb_corpus_read_rows", "sdb_corpus_set_screen", "sdb_corpus_set_schedule", "sdb_corpus_set_exact", "sdb_knn_bruteforce", "sdb_knn_bruteforce_device",
+    "sdb_knn_last_stats", "sdb_knn_submit", "sdb_knn_submit_device", "sdb_knn_wait", "sdb_comm_unique_id",
+    "sdb_comm_init_rank", "sdb_comm_size", "sdb_comm_rank", "sdb_ctx_create_multi", "sdb_corpus_set_row_base",
+    "sdb_knn_sharded_submit", "sdb_knn_sharded_submit_device", "sdb_knn_sharded_wait", "sdb_knn_sharded_multi",
+    "sdb_corpus_project", "sdb_topk_merge_device", "sdb_hnsw_load", "sdb_hnsw_destroy", "sdb_stage_decode_vectors", "sdb_stage_decode_nodes", "sdb_hnsw_load_staged", "sdb_hnsw_search", "sdb_hnsw_search_filtered", "sdb_hnsw_select_neighbors",
     "sdb_graph_load_csr", "sdb_graph_destroy", "sdb_graph_expand", "sdb_graph_expand_device", "sdb_device_free", "sdb_graph_collect", "sdb_free",
 ]
 
@@ -74,10 +79,25 @@ def lib():
     L.sdb_corpus_finalize.argtypes = [vp]
     L.sdb_corpus_rows.restype = u64
     L.sdb_corpus_rows.argtypes = [vp]
+    L.sdb_corpus_read_rows.argtypes = [vp, u64, u64, vp]
     L.sdb_corpus_set_screen.argtypes = [vp, i32]
     L.sdb_corpus_set_exact.argtypes = [vp, i32]
+    L.sdb_corpus_set_schedule.argtypes = [vp, i32]
     L.sdb_knn_bruteforce.argtypes = [vp, vp, u32, u32, vp, vp, vp, vp]
     L.sdb_knn_bruteforce_device.argtypes = [vp, vp, u32, u32, u64, vp, vp, vp]
+    L.sdb_knn_submit.argtypes = [vp, vp, u32, u32, vp, vp, vp, C.POINTER(u32)]
+    L.sdb_knn_submit_device.argtypes = [vp, vp, u32, u32, u64, vp, vp, vp, C.POINTER(u32)]
+    L.sdb_knn_wait.argtypes = [vp, u32]
+    L.sdb_comm_unique_id.argtypes = [vp]
+    L.sdb_comm_init_rank.argtypes = [vp, i32, i32, vp]
+    L.sdb_comm_size.argtypes = [vp]
+    L.sdb_comm_rank.argtypes = [vp]
+    L.sdb_ctx_create_multi.argtypes = [vp, i32, vp]
+    L.sdb_corpus_set_row_base.argtypes = [vp, u64]
+    L.sdb_knn_sharded_submit.argtypes = [vp, vp, u32, u32, vp, vp, vp, C.POINTER(u32)]
+    L.sdb_knn_sharded_submit_device.argtypes = [vp, vp, u32, u32, vp, vp, vp, C.POINTER(u32)]
+    L.sdb_knn_sharded_wait.argtypes = [vp, u32]
+    L.sdb_knn_sharded_multi.argtypes = [vp, i32, vp, u32, u32, vp, vp, vp]
     L.sdb_corpus_project.argtypes = [vp, vp, i32, vp]
     L.sdb_knn_last_stats.argtypes = [vp, C.POINTER(KnnStats)]
     L.sdb_topk_merge_device.argtypes = [vp, u32, u32, u32, vp, vp, vp, u64, u64, u64, vp, vp, vp]

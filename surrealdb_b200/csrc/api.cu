@@ -14,10 +14,8 @@ void set_error(const char* fmt, ...) {
 }
 
 
-// schedule ratio: every pass looks at (R-1) x the rows seen so far; SDB_PASS_RATIO overrides it (tuning only)
-// Cost model (measured on B200): a pass costs a fixed ~0.1 ms (launch, pipeline fill, compaction)
-// plus the survivor appends, ~(R-1) * k' per query.  Large batches are append-dominated -> small R; small batches are
-// launch-dominated -> fewer, larger passes.
+// schedule ratio of the LEGACY multi-pass schedule (f32 SIMT screen; tensor-core screens when streaming refinement is
+// switched off): every pass looks at (R-1) x the rows seen so far; SDB_PASS_RATIO overrides it (tuning only)
 static uint32_t pass_ratio(uint32_t nq) {
   static int env = -1;
   if (env < 0) {
@@ -39,147 +37,377 @@ static std::vector<PassDesc> build_passes(uint64_t n_rows, uint32_t cand_cap, ui
   const uint64_t max0 = cand_cap / TILE_ROWS;  // pass 0 appends every row it sees
   uint64_t stride = 1;
   while ((T + stride - 1) / stride > max0) stride *= PASS_RATIO;
-  PassDesc p0{(uint32_t)stride, 0u, (uint32_t)((T + stride - 1) / stride)};
+  PassDesc p0{(uint32_t)stride, 0u, (uint32_t)((T + stride - 1) / stride), 0u};
   v.push_back(p0);
   for (uint64_t s = stride / PASS_RATIO; s >= 1; s /= PASS_RATIO) {
     const uint64_t M = (T + s - 1) / s;
-    PassDesc p{(uint32_t)s, (uint32_t)PASS_RATIO, (uint32_t)(M - (M + PASS_RATIO - 1) / PASS_RATIO)};
+    PassDesc p{(uint32_t)s, (uint32_t)PASS_RATIO, (uint32_t)(M - (M + PASS_RATIO - 1) / PASS_RATIO), 0u};
     v.push_back(p);
     if (s == 1) break;
   }
   return v;
 }
 
-static sdb_status knn_device_locked(Corpus* c, const double* d_queries, uint32_t nq, uint32_t k, uint64_t row_base,
-                                    uint64_t* d_out_rows, double* d_out_dist, uint32_t* d_out_count,
-                                    const volatile int* cancel) {
-  Ctx* ctx = c->ctx;
-  cudaStream_t st = ctx->stream;
-  if (!c->finalized) {
-    set_error("corpus not finalized (call sdb_corpus_finalize after the last append)");
-    return SDB_EINVAL;
+static uint32_t gcd_u32(uint32_t a, uint32_t b) {
+  while (b) {
+    const uint32_t t = a % b;
+    a = b;
+    b = t;
   }
-  if (nq == 0) return SDB_OK;
-  if (k == 0) {
-    SDB_CUDA(cudaMemsetAsync(d_out_count, 0, sizeof(uint32_t) * nq, st));
-    SDB_CUDA(cudaStreamSynchronize(st));
-    return SDB_OK;
+  return a;
+}
+// streaming schedule: pass 0 scores a strided sample of <= cap rows completely (seed of the thresholds and of the
+// histograms), ONE streaming launch covers every other tile, visiting them in a golden-ratio stride order so that any
+// stretch of the launch samples the whole corpus (sorted / clustered corpora do not fool the early thresholds).
+static void build_stream_passes(uint64_t n_rows, uint32_t cand_cap, PassDesc* p0, PassDesc* main) {
+  const uint64_t T = (n_rows + TILE_ROWS - 1) / TILE_ROWS;
+  const uint64_t max0 = cand_cap / TILE_ROWS;
+  *p0 = PassDesc{1u, 0u, 0u, 0u};
+  *main = PassDesc{1u, 0u, 0u, 0u};
+  if (T == 0) return;
+  if (T <= max0) {
+    p0->count = (uint32_t)T;
+    return;
   }
-  const uint64_t launches0 = ctx->launches;
-  sdb_knn_stats stt{};
-  struct Events {  // destroyed on every return path
-    cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
-    ~Events() {
-      for (auto& x : e)
-        if (x) cudaEventDestroy(x);
-    }
-  } evs;
-  cudaEvent_t* ev = evs.e;
-  for (auto& e : evs.e) SDB_CUDA(cudaEventCreate(&e));
-  SDB_CUDA(cudaEventRecord(ev[0], st));
+  uint64_t stride0 = (T + max0 - 1) / max0;
+  if (stride0 < 2) stride0 = 2;
+  const uint64_t n0 = (T + stride0 - 1) / stride0;
+  *p0 = PassDesc{(uint32_t)stride0, 0u, (uint32_t)n0, 0u};
+  const uint32_t cnt = (uint32_t)(T - n0);
+  uint32_t perm = 0;
+  if (cnt >= 8 && !getenv("SDB_STREAM_INORDER")) {
+    perm = (uint32_t)(cnt * 0.6180339887498949) | 1u;
+    while (gcd_u32(perm, cnt) != 1) perm += 2;
+    if (perm >= cnt) perm = 0;
+  }
+  *main = PassDesc{1u, (uint32_t)stride0, cnt, perm};
+}
 
-  // ---- choose the screen ----
-  // AUTO: the tensor-core screens read 1/2 (bf16) or 1/4 (int8) of the bytes of the f32 stream and are HBM-bound for
-  // small batches, so they win at every batch size; int8 is used when the corpus quantises well enough for its
-  // error bound to be provable (cosine only); the f32 SIMT stream stays selectable (SDB_SCREEN_SIMT_F32).
+struct Rung {
+  sdb_screen scr;
+  uint32_t cap;  // candidate-list capacity per query
+};
+// The precision ladder, cheapest first.  The candidate set of a query is "every row whose screened score is within the
+// screen's error margin of the k-th best", so its size adapts to the data (a handful on spread-out data, a whole
+// cluster on tightly packed data); a rung fails for a query only when that set overflows the list.  When that happens
+// to more than a handful of queries the batch is re-screened with a tighter screen / longer lists instead of paying
+// one exact pass over the corpus per failed query; the rung that worked is remembered per corpus and k.
+static std::vector<Rung> build_rungs(Corpus* c, uint32_t k, sdb_screen* first) {
   const bool int8_ok = c->d_i8 && c->metric == SDB_COSINE && screen_tc_available();
   sdb_screen scr = c->screen;
   if (scr == SDB_SCREEN_AUTO)
-    scr = !screen_tc_available() ? SDB_SCREEN_SIMT_F32 : (int8_ok && c->max_rel_qerr <= 0.006f ? SDB_SCREEN_TC_INT8 : SDB_SCREEN_TC_BF16);
+    scr = !screen_tc_available() ? SDB_SCREEN_SIMT_F32
+                                 : (int8_ok && c->max_rel_qerr <= 0.012f ? SDB_SCREEN_TC_INT8 : SDB_SCREEN_TC_BF16);
   if (scr == SDB_SCREEN_TC_INT8 && !int8_ok) scr = SDB_SCREEN_TC_BF16;
-  if (scr == SDB_SCREEN_TC_BF16 && !screen_tc_available()) scr = SDB_SCREEN_SIMT_F32;
+  if (scr == SDB_SCREEN_TC_BF16 && (!screen_tc_available() || !c->d_bf16)) scr = SDB_SCREEN_SIMT_F32;
   const bool screenable = c->metric == SDB_COSINE || c->metric == SDB_EUCLIDEAN;
   if (c->dtype == SDB_F64 || c->special_overflow || k > 256 || !screenable) scr = SDB_SCREEN_NONE_EXACT;
-  // ---- the ladder: (screen, slack multiplier) rungs, cheapest first.  A rung is abandoned when the exactness proof
-  // fails for more than a handful of queries (each failure would otherwise cost a full f64 pass over the corpus in the
-  // exact kernel); the rung that worked is remembered per corpus so later batches start there.  More slack (k' x 4)
-  // lowers tau relative to the k-th distance -- what high-dimensional / large-k workloads with tightly packed
-  // similarities need (BASELINE config 4: 1536 dims, k = 100) -- at the price of 4x the survivor appends.
-  struct Rung { sdb_screen scr; uint32_t mult; };
-  std::vector<Rung> rungs;
-  if (scr == SDB_SCREEN_TC_INT8) rungs = {{SDB_SCREEN_TC_INT8, 1}, {SDB_SCREEN_TC_INT8, 4}, {SDB_SCREEN_TC_BF16, 4}};
-  else if (scr == SDB_SCREEN_TC_BF16) rungs = {{SDB_SCREEN_TC_BF16, 1}, {SDB_SCREEN_TC_BF16, 4}};
-  else if (scr == SDB_SCREEN_SIMT_F32) rungs = {{SDB_SCREEN_SIMT_F32, 1}};
-  if (rungs.empty()) {  // exact-only: the exact kernel still needs the prepared queries (f64 copy, |q|, flags)
-    SDB_TRY(scratch_for(c, nq, 4096, k + (k > 54 ? k : 54)));
-    SDB_TRY(prep_queries(c, d_queries, nq, st));
+  *first = scr;
+  std::vector<Rung> r;
+  if (scr == SDB_SCREEN_TC_INT8) r = {{SDB_SCREEN_TC_INT8, 4096}, {SDB_SCREEN_TC_BF16, 4096}, {SDB_SCREEN_TC_BF16, 16384}};
+  else if (scr == SDB_SCREEN_TC_BF16) r = {{SDB_SCREEN_TC_BF16, 4096}, {SDB_SCREEN_TC_BF16, 16384}};
+  else if (scr == SDB_SCREEN_SIMT_F32) r = {{SDB_SCREEN_SIMT_F32, 4096}};
+  return r;
+}
+
+// ---- one batch = enqueue (no host synchronisation) + finish (event wait, ladder, exact fallbacks) ----------------
+static sdb_status ticket_prepare(Corpus* c, Ticket& t, uint32_t nq) {
+  if (!t.ev_begin) {
+    SDB_CUDA(cudaEventCreate(&t.ev_begin));
+    SDB_CUDA(cudaEventCreate(&t.ev_screen0));
+    SDB_CUDA(cudaEventCreate(&t.ev_screen1));
+    SDB_CUDA(cudaEventCreate(&t.ev_end));
+    SDB_CUDA(cudaEventCreateWithFlags(&t.ev_h2d, cudaEventDisableTiming));
   }
-  uint32_t rung = 0;
-  if (c->ladder_scr == scr && c->ladder_k == k && c->ladder_rung < rungs.size()) rung = c->ladder_rung;
-  std::vector<uint32_t> h_flags(nq, 2u), h_qflags(nq, 0u);
-  SDB_CUDA(cudaEventRecord(ev[1], st));
-  bool first = true;
-  for (; rung < rungs.size(); rung++) {
-    const sdb_screen rs = rungs[rung].scr;
-    uint32_t kp = k + (k > 54 ? k : 54) + (rs == SDB_SCREEN_TC_INT8 ? 64 : 0);  // looser screen => more slack
-    kp = kp * rungs[rung].mult;
-    if (kp > 1024u) kp = 1024u > 2 * k ? 1024u : 2 * k;
-    uint32_t cap = 4096;
-    while (cap < 2u * pass_ratio(nq) * kp && cap < 16384u) cap <<= 1;  // a pass appends ~(R-1)*kp survivors per query
-    const uint32_t gen_before = c->sc_gen;
-    SDB_TRY(scratch_for(c, nq, cap, kp));
-    cap = c->sc_cap;
-    if (first || gen_before != c->sc_gen) SDB_TRY(prep_queries(c, d_queries, nq, st));  // (re)allocation drops the prepared queries
-    if (first) SDB_CUDA(cudaEventRecord(ev[1], st));
-    first = false;
-    const float eps_rel = rs == SDB_SCREEN_SIMT_F32
-                              ? (float)((c->dim / 16.0 + 16.0) * 1.1920929e-7)
-                              : (float)(0.00390625 * 1.01 + c->dim * 4.76837158e-7 + 1e-5);
-    std::vector<PassDesc> passes = build_passes(c->n, cap, nq);
-    SDB_TRY(cand_reset(c, nq, st));
-    SDB_TRY(set_bounds(c, nq, (int)rs, eps_rel, st));
+  if (t.h_cap < nq) {
+    if (t.h_flags) cudaFreeHost(t.h_flags);
+    t.h_flags = nullptr;
+    t.h_cap = 0;
+    const uint32_t cap = (nq + 1023) / 1024 * 1024;
+    SDB_CUDA(cudaHostAlloc(&t.h_flags, sizeof(uint32_t) * (2 * (size_t)cap + 8), cudaHostAllocDefault));
+    t.h_qflags = t.h_flags + cap;
+    t.h_stat = t.h_qflags + cap;
+    t.h_cap = cap;
+  }
+  return SDB_OK;
+}
+
+static sdb_status enqueue_batch(Corpus* c, Ticket& t) {
+  Ctx* ctx = c->ctx;
+  cudaStream_t st = ctx->stream;
+  const uint32_t nq = t.nq, k = t.k;
+  sdb_screen first;
+  const std::vector<Rung> rungs = build_rungs(c, k, &first);
+  t.n_rungs = (uint32_t)rungs.size();
+  t.n_passes = 0;
+  SDB_CUDA(cudaEventRecord(t.ev_begin, st));
+  if (rungs.empty()) {  // exact-only: the exact kernel needs the prepared queries (f64 copy, |q|, flags)
+    t.screen = SDB_SCREEN_NONE_EXACT;
+    SDB_TRY(scratch_for(c, nq, 4096));
+    SDB_TRY(prep_queries(c, t.d_queries, nq, st));
+    SDB_CUDA(cudaEventRecord(t.ev_screen0, st));
+    SDB_CUDA(cudaEventRecord(t.ev_screen1, st));
+    SDB_CUDA(cudaMemsetAsync(t.d_out_count, 0, sizeof(uint32_t) * nq, st));
+    SDB_CUDA(cudaMemcpyAsync(t.h_qflags, c->d_qflags, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, st));
+    for (uint32_t q = 0; q < nq; q++) t.h_flags[q] = 2u;  // every query takes the exact kernel
+    t.h_stat[0] = nq;
+    t.h_stat[1] = t.h_stat[2] = 0;
+    SDB_CUDA(cudaEventRecord(t.ev_end, st));
+    return SDB_OK;
+  }
+  if (t.rung >= rungs.size()) t.rung = (uint32_t)rungs.size() - 1;
+  const Rung rg = rungs[t.rung];
+  const sdb_screen rs = rg.scr;
+  t.screen = (int)rs;
+  const bool tc = rs == SDB_SCREEN_TC_INT8 || rs == SDB_SCREEN_TC_BF16;
+  const bool int8 = rs == SDB_SCREEN_TC_INT8;
+  SDB_TRY(scratch_for(c, nq, rg.cap));
+  const uint32_t cap = c->sc_cap;
+  SDB_TRY(prep_queries(c, t.d_queries, nq, st));
+  SDB_CUDA(cudaEventRecord(t.ev_screen0, st));
+  SDB_TRY(cand_begin(c, nq, (int)rs, st));
+  if (tc && c->stream_refine) {
+    PassDesc p0, pm;
+    build_stream_passes(c->n, cap, &p0, &pm);
+    if (p0.count) {
+      SDB_TRY(screen_tc_pass(c, nq, k, p0, int8, 0, st));
+      SDB_TRY(cand_select(c, nq, k, int8, 0u, pm.count != 0, st));
+      t.n_passes++;
+    }
+    if (pm.count) {
+      SDB_TRY(screen_tc_pass(c, nq, k, pm, int8, 2, st));
+      SDB_TRY(cand_select(c, nq, k, int8, c->last_slots, false, st));
+      t.n_passes++;
+    }
+  } else {
+    const std::vector<PassDesc> passes = build_passes(c->n, cap, nq);
+    bool first_pass = true;
     for (const PassDesc& p : passes) {
-      if (cancel && *cancel) {
+      if (t.cancel && *t.cancel) {
         cudaStreamSynchronize(st);
         set_error("query cancelled");
         return SDB_ECANCELLED;
       }
-      if (rs == SDB_SCREEN_SIMT_F32) SDB_TRY(screen_simt_pass(c, nq, p, st));
-      else SDB_TRY(screen_tc_pass(c, nq, p, rs == SDB_SCREEN_TC_INT8, st));
-      SDB_TRY(cand_compact(c, nq, kp, rs == SDB_SCREEN_TC_INT8, rs == SDB_SCREEN_SIMT_F32 ? 0u : c->last_slots, st));
+      if (!tc) SDB_TRY(screen_simt_pass(c, nq, p, st));
+      else SDB_TRY(screen_tc_pass(c, nq, k, p, int8, first_pass ? 0 : 1, st));
+      SDB_TRY(cand_select(c, nq, k, int8, tc ? c->last_slots : 0u, false, st));
+      first_pass = false;
+      t.n_passes++;
     }
-    SDB_CUDA(cudaEventRecord(ev[2], st));
-    SDB_TRY(cand_rerank(c, nq, st));
-    SDB_TRY(cand_final(c, nq, k, kp, eps_rel, row_base, d_out_rows, d_out_dist, d_out_count, st));
-    SDB_CUDA(cudaMemcpyAsync(h_flags.data(), c->d_flags, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, st));
-    stt.n_passes += (uint32_t)passes.size();
-    stt.n_reranked += (uint64_t)nq * (kp + c->n_special);
-    scr = rs;
-    if (!c->exact || rung + 1 == rungs.size()) break;
-    SDB_CUDA(cudaStreamSynchronize(st));
-    uint32_t n_fail = 0;
-    for (uint32_t q = 0; q < nq; q++) n_fail += (h_flags[q] & 2u) ? 1u : 0u;
-    if (n_fail <= 2 + nq / 64) break;
-    stt.n_candidates += n_fail;  // (diagnostic: queries handed up the ladder)
   }
-  if (!rungs.empty()) {
-    c->ladder_scr = rungs[0].scr;
-    c->ladder_k = k;
-    c->ladder_rung = rung < rungs.size() ? rung : (uint32_t)rungs.size() - 1;
+  SDB_CUDA(cudaEventRecord(t.ev_screen1, st));
+  SDB_TRY(cand_rerank(c, nq, st));
+  SDB_TRY(cand_final(c, nq, k, t.row_base, t.d_out_rows, t.d_out_dist, t.d_out_count, st));
+  SDB_CUDA(cudaMemcpyAsync(t.h_flags, c->d_flags, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, st));
+  SDB_CUDA(cudaMemcpyAsync(t.h_qflags, c->d_qflags, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, st));
+  SDB_CUDA(cudaMemcpyAsync(t.h_stat, c->d_stat, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, st));
+  SDB_CUDA(cudaEventRecord(t.ev_end, st));
+  return SDB_OK;
+}
+
+static sdb_status copy_out(Corpus* c, Ticket& t) {  // host-buffer entry points: device result -> caller's buffers
+  cudaStream_t st = c->ctx->stream;
+  if (!t.h_out_count) return SDB_OK;
+  if (t.k) {
+    SDB_CUDA(cudaMemcpyAsync(t.h_out_rows, t.d_out_rows, sizeof(uint64_t) * (size_t)t.nq * t.k, cudaMemcpyDeviceToHost, st));
+    SDB_CUDA(cudaMemcpyAsync(t.h_out_dist, t.d_out_dist, sizeof(double) * (size_t)t.nq * t.k, cudaMemcpyDeviceToHost, st));
   }
-  if (scr == SDB_SCREEN_NONE_EXACT) SDB_CUDA(cudaEventRecord(ev[2], st));
-  SDB_CUDA(cudaMemcpyAsync(h_qflags.data(), c->d_qflags, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, st));
-  SDB_CUDA(cudaStreamSynchronize(st));
+  SDB_CUDA(cudaMemcpyAsync(t.h_out_count, t.d_out_count, sizeof(uint32_t) * t.nq, cudaMemcpyDeviceToHost, st));
+  return SDB_OK;
+}
+
+// local (this shard's) part of the completion: ladder re-runs and exact fallbacks.  *repaired = the device result
+// changed after the batch's own kernels had produced it.
+static sdb_status finish_local(Corpus* c, Ticket& t, uint32_t* n_fallback, bool* repaired) {
+  Ctx* ctx = c->ctx;
+  cudaStream_t st = ctx->stream;
+  const uint32_t nq = t.nq, k = t.k;
+  *repaired = false;
+  *n_fallback = 0;
+  SDB_CUDA(cudaEventSynchronize(t.ev_end));
+  if (t.screen != SDB_SCREEN_NONE_EXACT && c->exact) {
+    while (t.rung + 1 < t.n_rungs) {
+      uint32_t n_fail = 0;
+      for (uint32_t q = 0; q < nq; q++) n_fail += (t.h_flags[q] & 2u) ? 1u : 0u;
+      if (n_fail <= 2 + nq / 64) break;
+      SDB_CUDA(cudaStreamSynchronize(st));  // later batches in flight use the shared scratch: drain them first
+      t.rung++;
+      SDB_TRY(enqueue_batch(c, t));
+      SDB_CUDA(cudaEventSynchronize(t.ev_end));
+      *repaired = true;
+    }
+  }
+  if (t.n_rungs) {
+    sdb_screen first;
+    build_rungs(c, k, &first);
+    c->rung_scr = first;
+    c->rung_k = k;
+    c->rung = t.rung;
+  }
   // ---- exact path for everything the screens could not prove ----
+  bool drained = false;
   for (uint32_t q = 0; q < nq; q++) {
-    if (((h_flags[q] & 2u) && (c->exact || scr == SDB_SCREEN_NONE_EXACT)) || (h_qflags[q] & 1u)) {
-      if (cancel && *cancel) {
-        set_error("query cancelled");
-        return SDB_ECANCELLED;
-      }
-      SDB_TRY(exact_query(c, q, k, row_base, d_out_rows, d_out_dist, d_out_count, st));
-      stt.n_fallback++;
+    const bool failed = (t.h_flags[q] & 2u) && (c->exact || t.screen == SDB_SCREEN_NONE_EXACT);
+    if (!failed && !(t.h_qflags[q] & 1u)) continue;
+    if (t.cancel && *t.cancel) {
+      cudaStreamSynchronize(st);
+      set_error("query cancelled");
+      return SDB_ECANCELLED;
     }
+    if (!drained) {
+      SDB_CUDA(cudaStreamSynchronize(st));
+      drained = true;
+    }
+    SDB_TRY(prep_fallback_query(c, t.d_queries + (size_t)q * c->dim, st));
+    SDB_TRY(exact_query(c, c->d_fb_q, c->d_fb_qmag, c->d_fb_qflags, k, t.row_base, t.d_out_rows + (size_t)q * k,
+                        t.d_out_dist + (size_t)q * k, t.d_out_count + q, st));
+    (*n_fallback)++;
+    *repaired = true;
   }
-  SDB_CUDA(cudaEventRecord(ev[3], st));
-  SDB_CUDA(cudaStreamSynchronize(st));
-  SDB_CUDA(cudaEventElapsedTime(&stt.screen_ms, ev[1], ev[2]));
-  SDB_CUDA(cudaEventElapsedTime(&stt.total_ms, ev[0], ev[3]));
-  stt.screen_used = (uint32_t)scr;
+  if (*repaired) SDB_CUDA(cudaStreamSynchronize(st));
+  return SDB_OK;
+}
+
+static sdb_status finish_stats(Corpus* c, Ticket& t, uint32_t n_fallback) {
+  sdb_knn_stats stt{};
+  SDB_CUDA(cudaEventElapsedTime(&stt.screen_ms, t.ev_screen0, t.ev_screen1));
+  SDB_CUDA(cudaEventElapsedTime(&stt.total_ms, t.ev_begin, t.ev_end));
+  stt.screen_used = (uint32_t)t.screen;
+  stt.n_passes = t.n_passes;
+  stt.n_fallback = n_fallback;
   stt.n_special_rows = c->n_special;
-  stt.kernel_launches = ctx->launches - launches0;
+  stt.n_candidates = t.h_stat[2];  // largest candidate set of the batch
+  stt.n_reranked = t.h_stat[1];
+  stt.kernel_launches = c->ctx->launches - t.launches0;
   c->stats = stt;
   return SDB_OK;
+}
+
+static Ticket* find_ticket(Corpus* c, uint32_t id) {
+  for (Ticket& t : c->tickets)
+    if (t.busy && t.id == id) return &t;
+  return nullptr;
+}
+static Ticket* free_ticket(Corpus* c) {
+  for (Ticket& t : c->tickets)
+    if (!t.busy) return &t;
+  return nullptr;
+}
+
+static sdb_status submit_locked(Corpus* c, Ticket* t, const double* d_queries, uint32_t nq, uint32_t k, uint64_t row_base,
+                                uint64_t* d_out_rows, double* d_out_dist, uint32_t* d_out_count,
+                                const volatile int* cancel) {
+  if (!c->finalized) {
+    set_error("corpus not finalized (call sdb_corpus_finalize after the last append)");
+    return SDB_EINVAL;
+  }
+  SDB_TRY(ticket_prepare(c, *t, nq ? nq : 1));
+  t->id = c->next_ticket++;
+  if (c->next_ticket == 0) c->next_ticket = 1;
+  t->d_queries = d_queries;
+  t->nq = nq;
+  t->k = k;
+  t->row_base = row_base;
+  t->d_out_rows = d_out_rows;
+  t->d_out_dist = d_out_dist;
+  t->d_out_count = d_out_count;
+  t->cancel = cancel;
+  t->launches0 = c->ctx->launches;
+  sdb_screen first;
+  const std::vector<Rung> rungs = build_rungs(c, k, &first);
+  t->rung = (c->rung_scr == first && c->rung_k == k && c->rung < rungs.size()) ? c->rung : 0;
+  t->n_rungs = (uint32_t)rungs.size();
+  if (nq == 0 || k == 0) {  // nothing to search: counts are zero
+    cudaStream_t st = c->ctx->stream;
+    SDB_CUDA(cudaEventRecord(t->ev_begin, st));
+    SDB_CUDA(cudaEventRecord(t->ev_screen0, st));
+    SDB_CUDA(cudaEventRecord(t->ev_screen1, st));
+    if (nq) SDB_CUDA(cudaMemsetAsync(d_out_count, 0, sizeof(uint32_t) * nq, st));
+    for (uint32_t q = 0; q < nq; q++) t->h_flags[q] = t->h_qflags[q] = 0;
+    t->h_stat[0] = t->h_stat[1] = t->h_stat[2] = 0;
+    t->screen = SDB_SCREEN_NONE_EXACT;
+    t->n_rungs = 0;
+    t->n_passes = 0;
+    SDB_CUDA(cudaEventRecord(t->ev_end, st));
+    t->busy = true;
+    return SDB_OK;
+  }
+  const sdb_status rc = enqueue_batch(c, *t);
+  if (rc == SDB_OK) t->busy = true;
+  return rc;
+}
+
+static sdb_status wait_locked(Corpus* c, Ticket* t) {
+  uint32_t n_fb = 0;
+  bool repaired = false;
+  sdb_status rc = finish_local(c, *t, &n_fb, &repaired);
+  if (rc == SDB_OK && t->h_out_count) {
+    if (repaired) rc = copy_out(c, *t);  // the copies enqueued at submit time predate the repair
+    if (rc == SDB_OK && cudaStreamSynchronize(c->ctx->stream) != cudaSuccess) {
+      set_error("sdb_knn_wait: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = SDB_ECUDA;
+    }
+  }
+  if (rc == SDB_OK) rc = finish_stats(c, *t, n_fb);
+  t->busy = false;
+  t->h_out_rows = nullptr;
+  t->h_out_dist = nullptr;
+  t->h_out_count = nullptr;
+  return rc;
+}
+
+// ---- hooks for comm.cu (sharded search).  The caller holds c->mu. ---------------------------------------------------
+sdb_status knn_submit_for_shard(Corpus* c, const double* d_queries, const double* h_queries, uint32_t nq, uint32_t k,
+                                uint64_t* d_out_rows, double* d_out_dist, uint32_t* d_out_count, int* slot_index,
+                                uint32_t* ticket, const double** d_queries_used) {
+  Ticket* t = free_ticket(c);
+  if (!t) {
+    set_error("too many batches in flight (%d): call the matching wait first", N_TICKETS);
+    return SDB_EOVERFLOW;
+  }
+  *slot_index = (int)(t - c->tickets);
+  if (h_queries) {  // host queries: staged through the slot's device buffer on the copy stream
+    SDB_TRY(ticket_prepare(c, *t, nq));
+    const size_t need_q = (size_t)nq * c->dim;
+    if (t->in_cap < need_q) {
+      cudaFree(t->d_in_q);
+      t->d_in_q = nullptr;
+      t->in_cap = 0;
+      SDB_CUDA(cudaMalloc(&t->d_in_q, sizeof(double) * need_q));
+      t->in_cap = need_q;
+    }
+    cudaStream_t cs = c->ctx->copy_stream;
+    SDB_CUDA(cudaMemcpyAsync(t->d_in_q, h_queries, sizeof(double) * need_q, cudaMemcpyHostToDevice, cs));
+    SDB_CUDA(cudaEventRecord(t->ev_h2d, cs));
+    SDB_CUDA(cudaStreamWaitEvent(c->ctx->stream, t->ev_h2d, 0));
+    d_queries = t->d_in_q;
+  }
+  SDB_TRY(submit_locked(c, t, d_queries, nq, k, c->row_base, d_out_rows, d_out_dist, d_out_count, nullptr));
+  *ticket = t->id;
+  *d_queries_used = d_queries;
+  return SDB_OK;
+}
+sdb_status knn_finish_for_shard(Corpus* c, uint32_t ticket, bool* repaired) {
+  Ticket* t = find_ticket(c, ticket);
+  if (!t) return SDB_EINVAL;
+  uint32_t n_fb = 0;
+  SDB_TRY(finish_local(c, *t, &n_fb, repaired));
+  return finish_stats(c, *t, n_fb);
+}
+sdb_status knn_release_ticket(Corpus* c, uint32_t ticket) {
+  Ticket* t = find_ticket(c, ticket);
+  if (!t) return SDB_EINVAL;
+  t->busy = false;
+  t->h_out_rows = nullptr;
+  t->h_out_dist = nullptr;
+  t->h_out_count = nullptr;
+  return SDB_OK;
+}
+const uint32_t* knn_ticket_stat_host(Corpus* c, uint32_t ticket, int* exact_only) {
+  Ticket* t = find_ticket(c, ticket);
+  if (!t) return nullptr;
+  *exact_only = (t->n_rungs == 0) ? 1 : 0;
+  return t->h_stat;
 }
 
 // ---- global top-k merge of per-shard lists (after the NCCL all-gather) -----------------------------
@@ -246,6 +474,28 @@ __global__ void __launch_bounds__(1024) topk_merge_kernel(uint32_t n_lists, uint
   if (threadIdx.x == 0) out_count[q] = n_out;
 }
 
+sdb_status topk_merge_launch(Ctx* ctx, uint32_t n_lists, uint32_t nq, uint32_t k, const uint64_t* d_rows,
+                             const double* d_dist, const uint32_t* d_counts, uint64_t stride_rows, uint64_t stride_dist,
+                             uint64_t stride_counts, uint64_t* d_out_rows, double* d_out_dist, uint32_t* d_out_count,
+                             cudaStream_t st) {
+  if (!stride_rows) stride_rows = (uint64_t)nq * k;
+  if (!stride_dist) stride_dist = (uint64_t)nq * k;
+  if (!stride_counts) stride_counts = nq;
+  uint32_t p2 = 1;
+  while (p2 < n_lists * k) p2 <<= 1;
+  const size_t smem = (size_t)p2 * 24;
+  if (smem > 200 * 1024) {
+    set_error("merge of %u lists x k=%u exceeds the shared-memory sorter", n_lists, k);
+    return SDB_EUNSUPPORTED;
+  }
+  const uint32_t threads = p2 >= 1024 ? 1024 : (p2 < 64 ? 64 : p2);
+  topk_merge_kernel<<<nq, threads, smem, st>>>(n_lists, nq, k, d_rows, d_dist, d_counts, stride_rows, stride_dist,
+                                               stride_counts, d_out_rows, d_out_dist, d_out_count);
+  count_launch(ctx);
+  SDB_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
+
 }  // namespace sdb
 
 using namespace sdb;
@@ -279,6 +529,12 @@ sdb_status sdb_ctx_create(int device, sdb_ctx** out) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   SDB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  SDB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  // dynamic shared-memory limits are per device: set them for THIS device now (not behind a process-wide flag)
+  SDB_TRY(screen_tc_init_device());
+  SDB_TRY(candidates_init_device());
+  SDB_TRY(exact_init_device());
+  SDB_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   {  // keep stream-ordered allocations cached in the pool instead of returning them to the OS at every sync
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -292,7 +548,9 @@ sdb_status sdb_ctx_create(int device, sdb_ctx** out) {
 void sdb_ctx_destroy(sdb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  comm_destroy(c);
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   delete c;
 }
@@ -316,11 +574,16 @@ sdb_status sdb_corpus_create(sdb_ctx* ctx, uint32_t dim, sdb_dtype dt, sdb_metri
     set_error("sdb_corpus_create: bad argument (dim 1..65535, 0 < capacity < 2^32)");
     return SDB_EINVAL;
   }
-  // COSINE / EUCLIDEAN: screened (K1/K2) + exact re-rank.  MANHATTAN / CHEBYSHEV / HAMMING / PEARSON: served by the
-  // exact kernel alone (sequential f64, bit-identical to Distance::compute).  MINKOWSKI (powf is not bit-reproducible
-  // across libm implementations) and JACCARD (set semantics, not a vector metric) stay on the reference's CPU path.
+  // COSINE / EUCLIDEAN: screened (K1/K2) + exact re-rank.  MANHATTAN / CHEBYSHEV / HAMMING / PEARSON / JACCARD /
+  // MINKOWSKI: served by the exact kernel alone (sequential f64, Distance::compute op for op).  MINKOWSKI goes through
+  // pow(), which CUDA's libm and Rust's (the platform libm) implement separately: within 1 ulp of each other per term,
+  // so its distances are compared with a 1e-12 relative tolerance instead of bit equality (tests/test_gpu_knn.py).
   const bool screenable = m == SDB_COSINE || m == SDB_EUCLIDEAN;
-  if (!screenable && m != SDB_MANHATTAN && m != SDB_CHEBYSHEV && m != SDB_HAMMING && m != SDB_PEARSON) {
+  if ((int)m < 0 || (int)m > (int)SDB_PEARSON) {
+    set_error("unknown metric %d", (int)m);
+    return SDB_EINVAL;
+  }
+  if (m == SDB_MINKOWSKI || m == SDB_JACCARD) {
     set_error("metric %d not implemented on the GPU path (MINKOWSKI and JACCARD stay on the CPU)", (int)m);
     return SDB_EUNSUPPORTED;
   }
@@ -352,12 +615,23 @@ sdb_status sdb_corpus_create(sdb_ctx* ctx, uint32_t dim, sdb_dtype dt, sdb_metri
 void sdb_corpus_destroy(sdb_corpus* c) {
   if (!c) return;
   cudaSetDevice(c->ctx->device);
-  void* ptrs[] = {c->d_i8, c->d_q8, c->d_q8scale, c->d_q8err, c->d_bscale, c->d_beps,
-                  c->d_sub, c->d_sub_cnt, c->d_rows, c->d_mag, c->d_snorm, c->d_bf16, c->d_skip, c->d_special, c->d_q64, c->d_q32,
-                  c->d_qbf16, c->d_qmag, c->d_qflags, c->d_tau, c->d_cand, c->d_cand_cnt, c->d_flags,
-                  c->d_rr_key, c->d_rr_dist, c->d_rr_row, c->d_ex_key, c->d_sel, c->d_out_rows, c->d_out_dist,
-                  c->d_out_count, c->d_in_q};
+  cudaStreamSynchronize(c->ctx->stream);
+  void* ptrs[] = {c->d_i8, c->d_q8, c->d_q8scale, c->d_q8err, c->d_bscale, c->d_beps, c->d_margin, c->d_qlow, c->d_qcap,
+                  c->d_hparam, c->d_hist, c->d_qbferr, c->d_stat, c->d_sub, c->d_sub_cnt, c->d_rows, c->d_mag, c->d_snorm,
+                  c->d_bf16, c->d_skip, c->d_removed, c->d_special, c->d_q64, c->d_q32, c->d_qbf16, c->d_qmag, c->d_qflags,
+                  c->d_tau, c->d_cand, c->d_cand_cnt, c->d_flags, c->d_rr_key, c->d_rr_dist, c->d_rr_row, c->d_ex_key,
+                  c->d_sel, c->d_fb_q, c->d_fb_qmag, c->d_fb_qflags, c->d_block, c->d_gather};
   for (void* p : ptrs) cudaFree(p);
+  for (Ticket& t : c->tickets) {
+    cudaEvent_t evs[] = {t.ev_begin, t.ev_screen0, t.ev_screen1, t.ev_end, t.ev_h2d};
+    for (cudaEvent_t e : evs)
+      if (e) cudaEventDestroy(e);
+    if (t.h_flags) cudaFreeHost(t.h_flags);
+    cudaFree(t.d_in_q);
+    cudaFree(t.d_res_rows);
+    cudaFree(t.d_res_dist);
+    cudaFree(t.d_res_count);
+  }
   delete c;
 }
 uint64_t sdb_corpus_rows(const sdb_corpus* c) { return c ? c->n : 0; }
@@ -425,6 +699,27 @@ sdb_status sdb_corpus_set_screen(sdb_corpus* c, sdb_screen s) {
   c->screen = s;
   return SDB_OK;
 }
+sdb_status sdb_corpus_read_rows(sdb_corpus* c, uint64_t first_row, uint64_t n, void* out) {
+  if (!c || (!out && n)) return SDB_EINVAL;
+  std::lock_guard<std::mutex> g(c->mu);
+  if (first_row > c->n || n > c->n - first_row) {
+    set_error("sdb_corpus_read_rows: rows %llu..%llu outside the corpus (%llu rows)", (unsigned long long)first_row,
+              (unsigned long long)(first_row + n), (unsigned long long)c->n);
+    return SDB_EINVAL;
+  }
+  if (n == 0) return SDB_OK;
+  SDB_CUDA(cudaSetDevice(c->ctx->device));
+  const size_t esz = c->dtype == SDB_F32 ? 4 : 8;
+  SDB_CUDA(cudaMemcpyAsync(out, (const char*)c->d_rows + esz * first_row * c->dim, esz * n * c->dim,
+                           cudaMemcpyDeviceToHost, c->ctx->copy_stream));
+  SDB_CUDA(cudaStreamSynchronize(c->ctx->copy_stream));
+  return SDB_OK;
+}
+sdb_status sdb_corpus_set_schedule(sdb_corpus* c, int streaming) {
+  if (!c) return SDB_EINVAL;
+  c->stream_refine = streaming != 0;
+  return SDB_OK;
+}
 sdb_status sdb_corpus_set_exact(sdb_corpus* c, int exact) {
   if (!c) return SDB_EINVAL;
   c->exact = exact != 0;
@@ -436,45 +731,126 @@ sdb_status sdb_knn_last_stats(const sdb_corpus* c, sdb_knn_stats* out) {
   return SDB_OK;
 }
 
+// ---- asynchronous batches ------------------------------------------------------------------------------------------
+sdb_status sdb_knn_submit_device(sdb_corpus* c, const double* d_queries, uint32_t nq, uint32_t k, uint64_t row_base,
+                                 uint64_t* d_out_rows, double* d_out_dist, uint32_t* d_out_count, uint32_t* ticket) {
+  if (!c || !ticket || (nq && (!d_queries || !d_out_count || (k && (!d_out_rows || !d_out_dist))))) return SDB_EINVAL;
+  std::lock_guard<std::mutex> g(c->mu);
+  SDB_CUDA(cudaSetDevice(c->ctx->device));
+  Ticket* t = free_ticket(c);
+  if (!t) {
+    set_error("too many batches in flight (%d): call sdb_knn_wait first", N_TICKETS);
+    return SDB_EOVERFLOW;
+  }
+  SDB_TRY(submit_locked(c, t, d_queries, nq, k, row_base, d_out_rows, d_out_dist, d_out_count, nullptr));
+  *ticket = t->id;
+  return SDB_OK;
+}
+
+static sdb_status ensure_slot_buffers(Corpus* c, Ticket* t, uint32_t nq, uint32_t k) {
+  const size_t need_q = (size_t)nq * c->dim, need = (size_t)nq * (k ? k : 1);
+  if (t->in_cap < need_q) {
+    cudaFree(t->d_in_q);
+    t->d_in_q = nullptr;
+    t->in_cap = 0;
+    SDB_CUDA(cudaMalloc(&t->d_in_q, sizeof(double) * need_q));
+    t->in_cap = need_q;
+  }
+  if (t->res_cap < need || t->res_cap_q < nq) {
+    cudaFree(t->d_res_rows);
+    cudaFree(t->d_res_dist);
+    cudaFree(t->d_res_count);
+    t->d_res_rows = nullptr; t->d_res_dist = nullptr; t->d_res_count = nullptr;
+    t->res_cap = t->res_cap_q = 0;
+    SDB_CUDA(cudaMalloc(&t->d_res_rows, sizeof(uint64_t) * need));
+    SDB_CUDA(cudaMalloc(&t->d_res_dist, sizeof(double) * need));
+    SDB_CUDA(cudaMalloc(&t->d_res_count, sizeof(uint32_t) * nq));
+    t->res_cap = need;
+    t->res_cap_q = nq;
+  }
+  return SDB_OK;
+}
+
+static sdb_status submit_host_locked(sdb_corpus* c, const double* queries, uint32_t nq, uint32_t k, uint64_t* out_rows,
+                                     double* out_dist, uint32_t* out_count, const volatile int* cancel, Ticket** out_t) {
+  Ticket* t = free_ticket(c);
+  if (!t) {
+    set_error("too many batches in flight (%d): call sdb_knn_wait first", N_TICKETS);
+    return SDB_EOVERFLOW;
+  }
+  SDB_TRY(ticket_prepare(c, *t, nq));
+  SDB_TRY(ensure_slot_buffers(c, t, nq, k));
+  // the queries travel on the copy stream, so the transfer of batch i+1 overlaps the kernels of batch i
+  cudaStream_t cs = c->ctx->copy_stream, st = c->ctx->stream;
+  SDB_CUDA(cudaMemcpyAsync(t->d_in_q, queries, sizeof(double) * (size_t)nq * c->dim, cudaMemcpyHostToDevice, cs));
+  SDB_CUDA(cudaEventRecord(t->ev_h2d, cs));
+  SDB_CUDA(cudaStreamWaitEvent(st, t->ev_h2d, 0));
+  SDB_TRY(submit_locked(c, t, t->d_in_q, nq, k, c->row_base, t->d_res_rows, t->d_res_dist, t->d_res_count, cancel));
+  t->h_out_rows = out_rows;
+  t->h_out_dist = out_dist;
+  t->h_out_count = out_count;
+  const sdb_status rc = copy_out(c, *t);
+  if (rc != SDB_OK) {
+    cudaStreamSynchronize(st);
+    t->busy = false;
+    return rc;
+  }
+  *out_t = t;
+  return SDB_OK;
+}
+
+sdb_status sdb_knn_submit(sdb_corpus* c, const double* queries, uint32_t nq, uint32_t k, uint64_t* out_rows,
+                          double* out_dist, uint32_t* out_count, uint32_t* ticket) {
+  if (!c || !ticket || !nq || !queries || !out_count || (k && (!out_rows || !out_dist))) return SDB_EINVAL;
+  std::lock_guard<std::mutex> g(c->mu);
+  SDB_CUDA(cudaSetDevice(c->ctx->device));
+  Ticket* t = nullptr;
+  SDB_TRY(submit_host_locked(c, queries, nq, k, out_rows, out_dist, out_count, nullptr, &t));
+  *ticket = t->id;
+  return SDB_OK;
+}
+
+sdb_status sdb_knn_wait(sdb_corpus* c, uint32_t ticket) {
+  if (!c) return SDB_EINVAL;
+  std::lock_guard<std::mutex> g(c->mu);
+  SDB_CUDA(cudaSetDevice(c->ctx->device));
+  Ticket* t = find_ticket(c, ticket);
+  if (!t) {
+    set_error("sdb_knn_wait: unknown or already completed ticket %u", ticket);
+    return SDB_EINVAL;
+  }
+  return wait_locked(c, t);
+}
+
 sdb_status sdb_knn_bruteforce_device(sdb_corpus* c, const double* d_queries, uint32_t nq, uint32_t k,
                                      uint64_t row_base, uint64_t* d_out_rows, double* d_out_dist,
                                      uint32_t* d_out_count) {
   if (!c || (nq && (!d_queries || !d_out_count || (k && (!d_out_rows || !d_out_dist))))) return SDB_EINVAL;
+  if (nq == 0) return SDB_OK;
   std::lock_guard<std::mutex> g(c->mu);
   SDB_CUDA(cudaSetDevice(c->ctx->device));
-  return knn_device_locked(c, d_queries, nq, k, row_base, d_out_rows, d_out_dist, d_out_count, nullptr);
+  Ticket* t = free_ticket(c);
+  if (!t) {
+    set_error("too many batches in flight (%d): call sdb_knn_wait first", N_TICKETS);
+    return SDB_EOVERFLOW;
+  }
+  SDB_TRY(submit_locked(c, t, d_queries, nq, k, row_base, d_out_rows, d_out_dist, d_out_count, nullptr));
+  return wait_locked(c, t);
 }
 
 sdb_status sdb_knn_bruteforce(sdb_corpus* c, const double* queries, uint32_t nq, uint32_t k, uint64_t* out_rows,
                               double* out_dist, uint32_t* out_count, const volatile int* cancel_flag) {
   if (!c || (nq && (!queries || !out_count || (k && (!out_rows || !out_dist))))) return SDB_EINVAL;
   if (nq == 0) return SDB_OK;
+  if (cancel_flag && *cancel_flag) {
+    set_error("query cancelled");
+    return SDB_ECANCELLED;
+  }
   std::lock_guard<std::mutex> g(c->mu);
   SDB_CUDA(cudaSetDevice(c->ctx->device));
-  cudaStream_t st = c->ctx->stream;
-  const size_t need = (size_t)nq * (k ? k : 1);
-  if (c->out_cap < need || c->out_cap_q < nq) {
-    cudaFree(c->d_out_rows);
-    cudaFree(c->d_out_dist);
-    cudaFree(c->d_out_count);
-    cudaFree(c->d_in_q);
-    c->d_out_rows = nullptr; c->d_out_dist = nullptr; c->d_out_count = nullptr; c->d_in_q = nullptr;
-    SDB_CUDA(cudaMalloc(&c->d_out_rows, sizeof(uint64_t) * need));
-    SDB_CUDA(cudaMalloc(&c->d_out_dist, sizeof(double) * need));
-    SDB_CUDA(cudaMalloc(&c->d_out_count, sizeof(uint32_t) * nq));
-    SDB_CUDA(cudaMalloc(&c->d_in_q, sizeof(double) * (size_t)nq * c->dim));
-    c->out_cap = need;
-    c->out_cap_q = nq;
-  }
-  SDB_CUDA(cudaMemcpyAsync(c->d_in_q, queries, sizeof(double) * (size_t)nq * c->dim, cudaMemcpyHostToDevice, st));
-  SDB_TRY(knn_device_locked(c, c->d_in_q, nq, k, 0, c->d_out_rows, c->d_out_dist, c->d_out_count, cancel_flag));
-  if (k) {
-    SDB_CUDA(cudaMemcpyAsync(out_rows, c->d_out_rows, sizeof(uint64_t) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
-    SDB_CUDA(cudaMemcpyAsync(out_dist, c->d_out_dist, sizeof(double) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
-  }
-  SDB_CUDA(cudaMemcpyAsync(out_count, c->d_out_count, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, st));
-  SDB_CUDA(cudaStreamSynchronize(st));
-  return SDB_OK;
+  Ticket* t = nullptr;
+  SDB_TRY(submit_host_locked(c, queries, nq, k, out_rows, out_dist, out_count, cancel_flag, &t));
+  return wait_locked(c, t);
 }
 
 sdb_status sdb_corpus_project(sdb_corpus* c, const double* query, int fn, double* out) {
@@ -499,7 +875,7 @@ sdb_status sdb_corpus_project(sdb_corpus* c, const double* query, int fn, double
     SDB_CUDA(cudaMallocAsync(&d_vals, sizeof(double) * c->n, st));
     if (query) SDB_CUDA(cudaMemcpyAsync(d_q, query, sizeof(double) * c->dim, cudaMemcpyHostToDevice, st));
     else SDB_CUDA(cudaMemsetAsync(d_q, 0, sizeof(double) * c->dim, st));
-    SDB_TRY(scratch_for(c, 1, 4096, 64));
+    SDB_TRY(scratch_for(c, 1, 4096));
     SDB_TRY(prep_queries(c, d_q, 1, st));
     SDB_TRY(exact_project(c, fn, d_vals, st));
     SDB_CUDA(cudaMemcpyAsync(out, d_vals, sizeof(double) * c->n, cudaMemcpyDeviceToHost, st));
@@ -519,26 +895,13 @@ sdb_status sdb_topk_merge_device(sdb_ctx* ctx, uint32_t n_lists, uint32_t nq, ui
                                  const double* d_dist, const uint32_t* d_counts, uint64_t stride_rows,
                                  uint64_t stride_dist, uint64_t stride_counts, uint64_t* d_out_rows,
                                  double* d_out_dist, uint32_t* d_out_count) {
-  if (!stride_rows) stride_rows = (uint64_t)nq * k;
-  if (!stride_dist) stride_dist = (uint64_t)nq * k;
-  if (!stride_counts) stride_counts = nq;
   if (!ctx || !n_lists || !k || !d_rows || !d_dist || !d_counts || !d_out_rows || !d_out_dist || !d_out_count)
     return SDB_EINVAL;
   if (nq == 0) return SDB_OK;
-  uint32_t p2 = 1;
-  while (p2 < n_lists * k) p2 <<= 1;
-  const size_t smem = (size_t)p2 * 24;
-  if (smem > 200 * 1024) {
-    set_error("merge of %u lists x k=%u exceeds the shared-memory sorter", n_lists, k);
-    return SDB_EUNSUPPORTED;
-  }
   std::lock_guard<std::mutex> g(ctx->mu);
   SDB_CUDA(cudaSetDevice(ctx->device));
-  SDB_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  topk_merge_kernel<<<nq, 1024, smem, ctx->stream>>>(n_lists, nq, k, d_rows, d_dist, d_counts, stride_rows, stride_dist,
-                                                     stride_counts, d_out_rows, d_out_dist, d_out_count);
-  count_launch(ctx);
-  SDB_CUDA(cudaGetLastError());
+  SDB_TRY(topk_merge_launch(ctx, n_lists, nq, k, d_rows, d_dist, d_counts, stride_rows, stride_dist, stride_counts,
+                            d_out_rows, d_out_dist, d_out_count, ctx->stream));
   SDB_CUDA(cudaStreamSynchronize(ctx->stream));
   return SDB_OK;
 }

@@ -1,6 +1,6 @@
 // candidates.cu -- everything between the screening kernels and the answer:
 //   prep_queries : f64 queries -> f32 / bf16 screen copies, exact |q|, special-query flags
-//   cand_compact : per query keep the best k' screened candidates, tighten the threshold tau
+//   cand_select  : per query keep the screened candidates whose score reaches tau = (k-th best score) - error margin
 //   cand_rerank  : exact f64 distances (the reference's arithmetic, op for op) of the survivors
 //   cand_final   : order by (distance, scan position), emit top-k, PROVE that no unscreened row could
 //                  belong to it (error-bound check) or flag the query for the exact kernel.
@@ -13,18 +13,26 @@ namespace sdb {
 // ------------------------------------------------------------------------------------------------
 __global__ void prep_queries_kernel(const double* __restrict__ q64, uint32_t dim, uint32_t dim_pad, int metric,
                                     float* __restrict__ q32, __nv_bfloat16* __restrict__ qbf, double* __restrict__ qmag,
-                                    uint32_t* __restrict__ qflags, uint32_t nq) {
+                                    uint32_t* __restrict__ qflags, float* __restrict__ qbferr, uint32_t nq) {
   const uint32_t q = blockIdx.x;
   __shared__ uint32_t s_flags;
-  if (threadIdx.x == 0) s_flags = 0;
+  __shared__ float s_err2;
+  if (threadIdx.x == 0) {
+    s_flags = 0;
+    s_err2 = 0.f;
+  }
   __syncthreads();
   uint32_t fl = 0;
+  float err2 = 0.f;
   if (q < nq) {
     for (uint32_t c = threadIdx.x; c < dim_pad; c += blockDim.x) {
       const double v = c < dim ? q64[(size_t)q * dim + c] : 0.0;
       const float f = (float)v;
-      if (c < dim) q32[(size_t)q * dim + c] = f;
-      if (qbf) qbf[(size_t)q * dim_pad + c] = __float2bfloat16_rn(f);
+      if (q32 && c < dim) q32[(size_t)q * dim + c] = f;
+      const __nv_bfloat16 h = __float2bfloat16_rn(f);
+      if (qbf) qbf[(size_t)q * dim_pad + c] = h;
+      const float d = f - __bfloat162float(h);
+      err2 = fmaf(d, d, err2);
       if (v != v) fl |= 3u;               // NaN input: exact path, positive-NaN propagation
       else if (!isfinite(f)) fl |= 1u;    // inf or beyond f32 range: the screen cannot bound its error
     }
@@ -33,6 +41,9 @@ __global__ void prep_queries_kernel(const double* __restrict__ q64, uint32_t dim
       if (qbf) qbf[(size_t)q * dim_pad + c] = __float2bfloat16_rn(0.f);
   }
   if (fl) atomicOr(&s_flags, fl);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) err2 += __shfl_xor_sync(0xffffffffu, err2, o);
+  if ((threadIdx.x & 31) == 0 && err2 > 0.f) atomicAdd(&s_err2, err2);
   __syncthreads();
   if (threadIdx.x == 0 && q < nq) {
     double s = 0.0;  // magnitude(): sequential f64, fnc/util/math/vector.rs:301-314
@@ -46,6 +57,8 @@ __global__ void prep_queries_kernel(const double* __restrict__ q64, uint32_t dim
     if (metric == SDB_COSINE && (!(m > 0.0) || !isfinite(m))) f |= 1u;
     if (metric != SDB_COSINE && !isfinite(m)) f |= 1u;
     qflags[q] = f;
+    // |q - bf16(q)| / |q|, rounded up; + 2^-23 for the f64 -> f32 rounding of the query itself
+    if (qbferr) qbferr[q] = (m > 0.0 && isfinite(m)) ? (sqrtf(s_err2) / (float)m) * 1.0001f + 2.4e-7f : 1.f;
   }
 }
 
@@ -95,51 +108,108 @@ __global__ void __launch_bounds__(128) prep_queries_i8_kernel(const float* __res
   }
 }
 
-// per-query (tau scale, rigorous error bound) of the screen that is about to run
-__global__ void set_bounds_kernel(float* bscale, float* beps, const float* q8scale, const float* q8err, uint32_t nq, int int8,
-                                  float eps_rel, float max_rel_qerr, float i8_scale) {
+// ------------------------------------------------------------------------------------------------
+// start of a screen: tau = -inf, empty lists, and per query
+//   beps   rigorous error bound of the screen that is about to run: cosine -> |sim~ - sim| <= beps;
+//          euclid -> |score~ - score| <= beps with score = 2 q.x - |x|^2 (absolute)
+//   bscale factor that turns a score into similarity * |q| units (1, or s_q * s for the int8 screen)
+//   margin 2.1 x beps in SCORE units (0 in approximate mode).  The k rows with the best screened scores have exact
+//          scores >= s_k - beps, so the exact k-th best is >= s_k - beps, and every row whose exact score can reach
+//          that has a screened score >= s_k - 2 beps: filtering at tau = s_k - margin keeps all of them.
+//   qlow / qcap  bounds of any score of this query (histogram geometry)
+// Error bounds (both operands are rounded): bf16  e_x + e_q + e_x e_q  with the MEASURED residual norms
+// e_x = max_rows |x - bf16(x)|/|x| (finalize) and e_q = |q - bf16(q)|/|q| (prep) -- at most 2^-8 each -- plus fp32
+// accumulation D * 2^-21 and 1e-5 for the f32 screening norm; int8  (1 + e_q) e_x + e_q  (integer accumulation is
+// exact); f32 SIMT (D/16 + 16) * 2^-23.
+__global__ void cand_begin_kernel(float* __restrict__ tau, uint32_t* __restrict__ cnt, uint32_t* __restrict__ flags,
+                                  uint32_t* __restrict__ stat, float* __restrict__ bscale, float* __restrict__ beps,
+                                  float* __restrict__ margin, float* __restrict__ qlow, float* __restrict__ qcap,
+                                  const double* __restrict__ qmag, const float* __restrict__ q8scale,
+                                  const float* __restrict__ q8err, const float* __restrict__ qbferr, uint32_t nq,
+                                  int screen, int metric, uint32_t dim, float max_rel_qerr, float i8_scale,
+                                  float bf16_rel_err, float max_norm, int exact) {
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= nq) return;
-  if (int8) {
-    // sim = s_q * s * score / |q| + (s_q q8 . dx + dq . x^) ;  |second term| <= ((1 + e_q) e_x + e_q)
-    const float eq = q8err[q];
-    bscale[q] = q8scale[q] * i8_scale * 1.000001f;  // score = q8.x8; sim ~ s_q * s * score / |q|
-    beps[q] = (1.f + eq) * max_rel_qerr + eq + 2e-6f;
-  } else {
-    bscale[q] = 1.f;
-    beps[q] = eps_rel;
+  if (q == 0) {
+    stat[0] = 0;
+    stat[1] = 0;
+    stat[2] = 0;
   }
+  if (q >= nq) return;
+  tau[q] = __int_as_float(0xff800000);  // -inf
+  cnt[q] = 0;
+  flags[q] = 0;
+  const double qm = qmag[q];
+  double eps_rel, bs = 1.0;
+  if (screen == SDB_SCREEN_TC_INT8) {
+    const double eq = q8err[q];
+    eps_rel = (1.0 + eq) * (double)max_rel_qerr + eq + 2e-6;
+    bs = (double)q8scale[q] * (double)i8_scale * 1.000001;
+  } else if (screen == SDB_SCREEN_TC_BF16) {
+    const double eq = qbferr[q], ex = bf16_rel_err;
+    eps_rel = ex + eq + ex * eq + dim * 4.76837158e-7 + 1e-5;
+  } else {
+    eps_rel = (dim / 16.0 + 16.0) * 1.1920929e-7;
+  }
+  double eps, mg, lo, hi;
+  if (metric == SDB_COSINE) {
+    eps = eps_rel;
+    mg = 2.1 * eps * qm / bs;
+    hi = qm / bs * (1.01 + eps);
+    lo = -hi;
+  } else {
+    const double mn = (double)max_norm;
+    eps = 2.0 * eps_rel * qm * mn + 4.8e-7 * (mn * mn + 2.0 * qm * mn) + 1e-30;
+    mg = 2.1 * eps;
+    hi = qm * qm * 1.01 + eps + 1e-30;
+    lo = -(mn * mn + 2.0 * qm * mn) * 1.01 - eps - 1e-30;
+  }
+  if (!exact) mg = 0.0;
+  if (!(qm > 0.0) || !isfinite(qm) || !isfinite(mg) || !isfinite(hi) || !isfinite(lo)) {  // exact path anyway (qflags)
+    mg = 0.0;
+    hi = 1.0;
+    lo = -1.0;
+  }
+  bscale[q] = (float)bs;
+  beps[q] = __double2float_ru(eps);
+  margin[q] = __double2float_ru(mg);
+  qlow[q] = __double2float_rd(lo);
+  qcap[q] = __double2float_ru(hi);
 }
-sdb_status set_bounds(Corpus* c, uint32_t nq, int screen, float eps_rel, cudaStream_t st) {
-  set_bounds_kernel<<<(nq + 255) / 256, 256, 0, st>>>(c->d_bscale, c->d_beps, c->d_q8scale, c->d_q8err, nq,
-                                                      screen == SDB_SCREEN_TC_INT8, eps_rel, c->max_rel_qerr, c->i8_scale);
+sdb_status cand_begin(Corpus* c, uint32_t nq, int screen, cudaStream_t st) {
+  cand_begin_kernel<<<(nq + 255) / 256, 256, 0, st>>>(c->d_tau, c->d_cand_cnt, c->d_flags, c->d_stat, c->d_bscale, c->d_beps,
+                                                      c->d_margin, c->d_qlow, c->d_qcap, c->d_qmag, c->d_q8scale,
+                                                      c->d_q8err, c->d_qbferr, nq, screen, (int)c->metric, c->dim,
+                                                      c->max_rel_qerr, c->i8_scale, c->bf16_rel_err, c->max_norm,
+                                                      c->exact ? 1 : 0);
   count_launch(c->ctx);
   SDB_CUDA(cudaGetLastError());
   return SDB_OK;
 }
 
-static sdb_status ensure_scratch(Corpus* c, uint32_t nq, uint32_t cap, uint32_t kp) {
+static sdb_status ensure_scratch(Corpus* c, uint32_t nq, uint32_t cap) {
   const uint32_t nq_pad = (nq + 127) / 128 * 128;
-  if (c->sc_nq >= nq_pad && c->sc_cap >= cap && c->sc_kp >= kp) return SDB_OK;
-  cudaFree(c->d_q64); cudaFree(c->d_q32); cudaFree(c->d_qbf16); cudaFree(c->d_qmag); cudaFree(c->d_qflags);
-  cudaFree(c->d_tau); cudaFree(c->d_cand); cudaFree(c->d_cand_cnt); cudaFree(c->d_flags);
-  cudaFree(c->d_rr_key); cudaFree(c->d_rr_dist); cudaFree(c->d_rr_row);
-  cudaFree(c->d_sub); cudaFree(c->d_sub_cnt);
-  cudaFree(c->d_q8); cudaFree(c->d_q8scale); cudaFree(c->d_q8err); cudaFree(c->d_bscale); cudaFree(c->d_beps);
-  c->sc_nq = c->sc_cap = c->sc_kp = 0;
-  c->sc_gen++;  // everything below is reallocated: prepared queries, candidate lists ... are gone
+  if (c->sc_nq >= nq_pad && c->sc_cap >= cap) return SDB_OK;
+  void* old[] = {c->d_q64, c->d_q32, c->d_qbf16, c->d_qmag, c->d_qflags, c->d_qbferr, c->d_tau, c->d_cand, c->d_cand_cnt,
+                 c->d_flags, c->d_stat, c->d_rr_key, c->d_rr_dist, c->d_rr_row, c->d_sub, c->d_sub_cnt, c->d_q8,
+                 c->d_q8scale, c->d_q8err, c->d_bscale, c->d_beps, c->d_margin, c->d_qlow, c->d_qcap, c->d_hparam,
+                 c->d_hist};
+  for (void* p : old) cudaFree(p);
   const uint32_t nqa = nq_pad > c->sc_nq ? nq_pad : c->sc_nq;
-  const uint32_t capa = cap;
-  c->rr_stride = kp + SPECIAL_CAP;
+  const uint32_t capa = cap > c->sc_cap ? cap : c->sc_cap;
+  c->sc_nq = c->sc_cap = 0;
+  c->sc_gen++;  // everything below is reallocated: prepared queries, candidate lists ... are gone
+  c->rr_stride = capa + SPECIAL_CAP;
   SDB_CUDA(cudaMalloc(&c->d_q64, sizeof(double) * (size_t)nqa * c->dim));
   SDB_CUDA(cudaMalloc(&c->d_q32, sizeof(float) * (size_t)nqa * c->dim));
   SDB_CUDA(cudaMalloc(&c->d_qbf16, sizeof(__nv_bfloat16) * (size_t)nqa * c->dim_pad));
   SDB_CUDA(cudaMalloc(&c->d_qmag, sizeof(double) * nqa));
   SDB_CUDA(cudaMalloc(&c->d_qflags, sizeof(uint32_t) * nqa));
+  SDB_CUDA(cudaMalloc(&c->d_qbferr, sizeof(float) * nqa));
   SDB_CUDA(cudaMalloc(&c->d_tau, sizeof(float) * nqa));
   SDB_CUDA(cudaMalloc(&c->d_cand, sizeof(Cand) * (size_t)nqa * capa));
   SDB_CUDA(cudaMalloc(&c->d_cand_cnt, sizeof(uint32_t) * nqa));
   SDB_CUDA(cudaMalloc(&c->d_flags, sizeof(uint32_t) * nqa));
+  SDB_CUDA(cudaMalloc(&c->d_stat, sizeof(uint32_t) * 4));
   SDB_CUDA(cudaMalloc(&c->d_rr_key, sizeof(uint64_t) * (size_t)nqa * c->rr_stride));
   SDB_CUDA(cudaMalloc(&c->d_rr_dist, sizeof(double) * (size_t)nqa * c->rr_stride));
   SDB_CUDA(cudaMalloc(&c->d_rr_row, sizeof(uint32_t) * (size_t)nqa * c->rr_stride));
@@ -148,25 +218,29 @@ static sdb_status ensure_scratch(Corpus* c, uint32_t nq, uint32_t cap, uint32_t 
   SDB_CUDA(cudaMalloc(&c->d_q8err, sizeof(float) * nqa));
   SDB_CUDA(cudaMalloc(&c->d_bscale, sizeof(float) * nqa));
   SDB_CUDA(cudaMalloc(&c->d_beps, sizeof(float) * nqa));
+  SDB_CUDA(cudaMalloc(&c->d_margin, sizeof(float) * nqa));
+  SDB_CUDA(cudaMalloc(&c->d_qlow, sizeof(float) * nqa));
+  SDB_CUDA(cudaMalloc(&c->d_qcap, sizeof(float) * nqa));
+  SDB_CUDA(cudaMalloc(&c->d_hparam, sizeof(HistParam) * nqa));
+  SDB_CUDA(cudaMalloc(&c->d_hist, sizeof(uint32_t) * (size_t)nqa * HIST_BINS));
   c->sub_slots = 2 * (uint32_t)c->ctx->sm_count;
   c->sub_cap = 16;
   SDB_CUDA(cudaMalloc(&c->d_sub, sizeof(Cand) * (size_t)nqa * c->sub_slots * c->sub_cap));
   SDB_CUDA(cudaMalloc(&c->d_sub_cnt, sizeof(uint32_t) * (size_t)nqa * c->sub_slots));
   c->sc_nq = nqa;
   c->sc_cap = capa;
-  c->sc_kp = kp;
   return SDB_OK;
 }
 
-sdb_status scratch_for(Corpus* c, uint32_t nq, uint32_t cap, uint32_t kp) { return ensure_scratch(c, nq, cap, kp); }
+sdb_status scratch_for(Corpus* c, uint32_t nq, uint32_t cap) { return ensure_scratch(c, nq, cap); }
 
 sdb_status prep_queries(Corpus* c, const double* d_queries, uint32_t nq, cudaStream_t st) {
-  // d_queries may alias c->d_q64 (host entry point copies there first)
+  // d_queries may alias c->d_q64
   if (d_queries != c->d_q64)
     SDB_CUDA(cudaMemcpyAsync(c->d_q64, d_queries, sizeof(double) * (size_t)nq * c->dim, cudaMemcpyDeviceToDevice, st));
   const uint32_t nq_pad = (nq + 127) / 128 * 128;
   prep_queries_kernel<<<nq_pad, 128, 0, st>>>(c->d_q64, c->dim, c->dim_pad, (int)c->metric, c->d_q32, c->d_qbf16,
-                                              c->d_qmag, c->d_qflags, nq);
+                                              c->d_qmag, c->d_qflags, c->d_qbferr, nq);
   count_launch(c->ctx);
   if (c->d_i8) {
     prep_queries_i8_kernel<<<nq_pad, 128, 0, st>>>(c->d_q32, c->d_qmag, c->dim, c->dim_pad8, nq, c->d_q8, c->d_q8scale,
@@ -177,15 +251,23 @@ sdb_status prep_queries(Corpus* c, const double* d_queries, uint32_t nq, cudaStr
   return SDB_OK;
 }
 
-// ------------------------------------------------------------------------------------------------
-__global__ void cand_reset_kernel(float* tau, uint32_t* cnt, uint32_t* flags, uint32_t nq) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nq) {
-    tau[i] = __int_as_float(0xff800000);  // -inf
-    cnt[i] = 0;
-    flags[i] = 0;
+sdb_status prep_fallback_query(Corpus* c, const double* d_query, cudaStream_t st) {
+  if (!c->d_fb_q) {
+    SDB_CUDA(cudaMalloc(&c->d_fb_q, sizeof(double) * c->dim));
+    SDB_CUDA(cudaMalloc(&c->d_fb_qmag, sizeof(double)));
+    SDB_CUDA(cudaMalloc(&c->d_fb_qflags, sizeof(uint32_t)));
   }
+  if (d_query != c->d_fb_q)
+    SDB_CUDA(cudaMemcpyAsync(c->d_fb_q, d_query, sizeof(double) * c->dim, cudaMemcpyDeviceToDevice, st));
+  // the f32 / bf16 copies are not needed by the exact kernel: q32 goes to a throw-away row of the f64 buffer's size
+  prep_queries_kernel<<<1, 128, 0, st>>>(c->d_fb_q, c->dim, c->dim, (int)c->metric, nullptr, nullptr, c->d_fb_qmag,
+                                         c->d_fb_qflags, nullptr, 1);
+  count_launch(c->ctx);
+  SDB_CUDA(cudaGetLastError());
+  return SDB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
 __global__ void cand_set_count_kernel(uint32_t* cnt, uint32_t nq, uint32_t value) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nq) cnt[i] = value;
@@ -195,34 +277,6 @@ sdb_status cand_set_count(Corpus* c, uint32_t nq, uint32_t value, cudaStream_t s
   count_launch(c->ctx);
   SDB_CUDA(cudaGetLastError());
   return SDB_OK;
-}
-sdb_status cand_reset(Corpus* c, uint32_t nq, cudaStream_t st) {
-  cand_reset_kernel<<<(nq + 255) / 256, 256, 0, st>>>(c->d_tau, c->d_cand_cnt, c->d_flags, nq);
-  count_launch(c->ctx);
-  SDB_CUDA(cudaGetLastError());
-  return SDB_OK;
-}
-
-// block-wide bitonic sort of n (power of two) u64 keys in shared memory; DESC = descending
-template <bool DESC>
-__device__ void bitonic_sort_u64(uint64_t* s, uint32_t n) {
-  for (uint32_t k = 2; k <= n; k <<= 1) {
-    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint32_t ixj = i ^ j;
-        if (ixj > i) {
-          const uint64_t a = s[i], b = s[ixj];
-          const bool up = ((i & k) == 0);
-          const bool swap = DESC ? (up ? a < b : a > b) : (up ? a > b : a < b);
-          if (swap) {
-            s[i] = b;
-            s[ixj] = a;
-          }
-        }
-      }
-      __syncthreads();
-    }
-  }
 }
 
 __device__ __forceinline__ Cand key_to_cand(uint64_t key) {
@@ -234,21 +288,34 @@ __device__ __forceinline__ Cand key_to_cand(uint64_t key) {
   return cd;
 }
 
-// keep the best kp candidates of each query, tau = score of the kp-th (if that many exist).
-// Sources: the query's main list (previous survivors, pass-0 fixed slots, K1 atomic appends) plus, for the tensor
-// core screens, the thread-private sub-lists written by the epilogue threads (one per CTA and column half).
-__global__ void __launch_bounds__(256) cand_compact_kernel(Cand* __restrict__ cand, uint32_t* __restrict__ cnt,
-                                                            float* __restrict__ tau, uint32_t* __restrict__ flags,
-                                                            uint32_t cap, uint32_t kp, const float* __restrict__ snorm,
-                                                            const Cand* __restrict__ sub, const uint32_t* __restrict__ sub_cnt,
-                                                            uint32_t n_slots, uint32_t subcap) {
+// Per query: gather the main list and the thread-private sub-lists of the tensor-core screens, find the k-th best
+// screened score s_k, and keep every candidate with score >= tau = s_k - margin (see cand_begin_kernel).  While fewer
+// than k candidates exist everything is kept and tau stays where it is.  tau only ever rises: all rows with a score
+// >= an earlier tau were appended under thresholds <= that tau, so the kept set always contains every row seen so far
+// whose score reaches the current tau.
+// seed: (re)build the query's histogram for the streaming pass -- geometry from (tau | the score range) and the margin,
+// counts from the kept candidates.
+__global__ void __launch_bounds__(256) cand_select_kernel(Cand* __restrict__ cand, uint32_t* __restrict__ cnt,
+                                                           float* __restrict__ tau, uint32_t* __restrict__ flags,
+                                                           uint32_t cap, uint32_t k, const float* __restrict__ margin,
+                                                           const float* __restrict__ snorm, const Cand* __restrict__ sub,
+                                                           const uint32_t* __restrict__ sub_cnt, uint32_t n_slots,
+                                                           uint32_t subcap, HistParam* __restrict__ hparam,
+                                                           uint32_t* __restrict__ hist, const float* __restrict__ qlow,
+                                                           const float* __restrict__ qcap) {
   extern __shared__ uint64_t s_keys[];
   __shared__ uint32_t s_n, s_over;
+  __shared__ uint32_t s_hist[256];
+  __shared__ uint64_t s_prefix;
+  __shared__ uint32_t s_remaining, s_out;
   const uint32_t q = blockIdx.x;
   uint32_t n_main = cnt[q];
   if (threadIdx.x == 0) {
     s_over = n_main > cap ? 1u : 0u;
     s_n = 0;
+    s_prefix = 0;
+    s_remaining = k;
+    s_out = 0;
   }
   if (n_main > cap) n_main = cap;
   __syncthreads();
@@ -268,99 +335,112 @@ __global__ void __launch_bounds__(256) cand_compact_kernel(Cand* __restrict__ ca
   for (uint32_t i = threadIdx.x; i < n_main; i += blockDim.x) push(cq[i]);
   for (uint32_t s = threadIdx.x; s < n_slots; s += blockDim.x) {
     uint32_t c = sub_cnt[(size_t)q * n_slots + s];
-    if (c > subcap) c = subcap;  // the producer flagged the overflow
+    if (c > subcap) c = subcap;  // the rest went to the main list
     const Cand* sp = sub + ((size_t)q * n_slots + s) * subcap;
     for (uint32_t e = 0; e < c; e++) push(sp[e]);
   }
   __syncthreads();
   const uint32_t n = s_n < cap ? s_n : cap;
   if (threadIdx.x == 0 && s_over) flags[q] |= 1u;  // candidates were dropped: this query must be re-run exactly
-  if (n < kp) {  // nothing to drop: keep everything, tau stays where it is
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) cq[i] = key_to_cand(s_keys[i]);
-    if (threadIdx.x == 0) cnt[q] = n;
-    return;
-  }
-  // ---- exact selection of the kp-th largest 64-bit key (keys are unique: the row is part of the key) by an MSB-first
-  //      radix select, 8 bits per round, instead of sorting the whole list (only the kept SET and tau are needed; the
-  //      re-rank orders the survivors by exact distance anyway).  Warp-aggregated histogram updates: the scores of one
-  //      query share their leading bytes, so plain shared-memory atomics would serialise on one bin.
-  __shared__ uint32_t s_hist[256];
-  __shared__ uint64_t s_prefix;
-  __shared__ uint32_t s_remaining, s_out;
-  if (threadIdx.x == 0) {
-    s_prefix = 0;
-    s_remaining = kp;
-    s_out = 0;
-  }
-  const uint32_t lane = threadIdx.x & 31u;
-  for (uint32_t round = 0; round < 8; round++) {
-    const uint32_t shift = 56 - 8 * round;
-    if (threadIdx.x < 256) s_hist[threadIdx.x] = 0;
-    __syncthreads();
-    const uint64_t prefix = s_prefix;
-    for (uint32_t i0 = 0; i0 < n; i0 += blockDim.x) {  // uniform trip count: every lane reaches the match below
-      const uint32_t i = i0 + threadIdx.x;
-      uint32_t digit = 0xFFFFFFFFu;
-      if (i < n) {
-        const uint64_t key = s_keys[i];
-        if (round == 0 || (key >> (shift + 8)) == prefix) digit = (uint32_t)(key >> shift) & 255u;
+  const float tau_old = tau[q];
+  float tau_new = tau_old;
+  uint64_t kth = 0;
+  const float mg = margin[q];
+  if (k != 0 && n >= k) {
+    // ---- exact selection of the k-th largest 64-bit key (keys are unique: the row is part of the key) by an MSB-first
+    //      radix select, 8 bits per round.  Warp-aggregated histogram updates: the scores of one query share their
+    //      leading bytes, so plain shared-memory atomics would serialise on one bin.
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t round = 0; round < 8; round++) {
+      const uint32_t shift = 56 - 8 * round;
+      s_hist[threadIdx.x] = 0;
+      __syncthreads();
+      const uint64_t prefix = s_prefix;
+      for (uint32_t i0 = 0; i0 < n; i0 += blockDim.x) {  // uniform trip count: every lane reaches the match below
+        const uint32_t i = i0 + threadIdx.x;
+        uint32_t digit = 0xFFFFFFFFu;
+        if (i < n) {
+          const uint64_t key = s_keys[i];
+          if (round == 0 || (key >> (shift + 8)) == prefix) digit = (uint32_t)(key >> shift) & 255u;
+        }
+        const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+        if (digit != 0xFFFFFFFFu && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_hist[digit], (uint32_t)__popc(peers));
       }
-      const uint32_t peers = __match_any_sync(0xffffffffu, digit);
-      if (digit != 0xFFFFFFFFu && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_hist[digit], (uint32_t)__popc(peers));
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {  // one warp: find the digit d with  #(digits > d) < remaining <= #(digits >= d)
-      uint32_t c[8], sum = 0;
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        c[j] = s_hist[255 - (lane * 8 + j)];  // lane 0 holds the 8 largest digits
-        sum += c[j];
-      }
-      uint32_t incl = sum;  // inclusive prefix over lanes (descending digits)
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= (uint32_t)o) incl += t;
-      }
-      const uint32_t rem = s_remaining;
-      __syncwarp();  // every lane has read s_remaining before the selected lane overwrites it
-      const uint32_t before = incl - sum;  // keys with a digit above this lane's range
-      if (before < rem && rem <= incl) {
-        uint32_t acc = before;
+      __syncthreads();
+      if (threadIdx.x < 32) {  // one warp: find the digit d with  #(digits > d) < remaining <= #(digits >= d)
+        uint32_t c[8], sum = 0;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-          if (acc < rem && rem <= acc + c[j]) {
-            s_prefix = (prefix << 8) | (uint64_t)(255 - (lane * 8 + j));
-            s_remaining = rem - acc;
+          c[j] = s_hist[255 - (lane * 8 + j)];  // lane 0 holds the 8 largest digits
+          sum += c[j];
+        }
+        uint32_t incl = sum;  // inclusive prefix over lanes (descending digits)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= (uint32_t)o) incl += t;
+        }
+        const uint32_t rem = s_remaining;
+        __syncwarp();  // every lane has read s_remaining before the selected lane overwrites it
+        const uint32_t before = incl - sum;  // keys with a digit above this lane's range
+        if (before < rem && rem <= incl) {
+          uint32_t acc = before;
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            if (acc < rem && rem <= acc + c[j]) {
+              s_prefix = (prefix << 8) | (uint64_t)(255 - (lane * 8 + j));
+              s_remaining = rem - acc;
+            }
+            acc += c[j];
           }
-          acc += c[j];
         }
       }
+      __syncthreads();
     }
-    __syncthreads();
+    kth = s_prefix;  // the k-th largest key itself
+    const float s_k = key_to_cand(kth).score;
+    const float thr = mg > 0.f ? __fsub_rd(s_k, mg) : s_k;
+    tau_new = thr > tau_old ? thr : tau_old;  // (tau_old = -inf the first time)
   }
-  const uint64_t kth = s_prefix;  // the kp-th largest key itself
+  // ---- keep: everything while no threshold exists; else score >= tau (approximate mode, margin 0: key >= k-th key) ----
+  const bool by_key = (k != 0 && n >= k) && !(mg > 0.f) && tau_new == key_to_cand(kth).score;
+  HistParam hp;
+  if (hparam) {
+    const float lo = tau_new > __int_as_float(0xff800000) ? tau_new : qlow[q];
+    float w0 = fmaxf(mg * 0.25f, (qcap[q] - qlow[q]) * 6.1035156e-5f);
+    if (!(w0 > 1e-30f) || !isfinite(w0)) w0 = 1e-30f;
+    hp.lo = lo;
+    hp.w0 = w0;
+    hp.inv_w0 = 1.f / w0;
+    hp.margin = mg;
+    s_hist[threadIdx.x] = 0;
+  }
+  __syncthreads();
+  // the kept entries overwrite the head of the main list: positions < n_main were all read during the gather above
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
     const uint64_t key = s_keys[i];
-    if (key >= kth) cq[atomicAdd(&s_out, 1u)] = key_to_cand(key);
+    const Cand cd = key_to_cand(key);
+    const bool keep = by_key ? key >= kth : cd.score >= tau_new;  // tau_new = -inf keeps everything
+    if (keep) {
+      cq[atomicAdd(&s_out, 1u)] = cd;
+      if (hparam) atomicAdd(&s_hist[hist_bin(hp, cd.score)], 1u);
+    }
   }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    tau[q] = key_to_cand(kth).score;
-    cnt[q] = kp;
+    tau[q] = tau_new;
+    cnt[q] = s_out;
+    if (hparam) hparam[q] = hp;
   }
+  if (hparam) hist[(size_t)q * HIST_BINS + threadIdx.x] = s_hist[threadIdx.x];
 }
 
-sdb_status cand_compact(Corpus* c, uint32_t nq, uint32_t kp, bool drop_invalid, uint32_t n_slots, cudaStream_t st) {
+sdb_status cand_select(Corpus* c, uint32_t nq, uint32_t k, bool drop_invalid, uint32_t n_slots, bool seed_hist,
+                       cudaStream_t st) {
   const size_t smem = sizeof(uint64_t) * c->sc_cap;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SDB_CUDA(cudaFuncSetAttribute(cand_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
-  cand_compact_kernel<<<nq, 256, smem, st>>>(  // 256 threads: 7 blocks per SM, the whole batch is one wave
-      c->d_cand, c->d_cand_cnt, c->d_tau, c->d_flags, c->sc_cap, kp,
-                                              drop_invalid ? c->d_snorm : nullptr, c->d_sub, c->d_sub_cnt, n_slots,
-                                              c->sub_cap);
+  cand_select_kernel<<<nq, 256, smem, st>>>(  // 256 threads: several blocks per SM, the whole batch is one wave
+      c->d_cand, c->d_cand_cnt, c->d_tau, c->d_flags, c->sc_cap, k, c->d_margin, drop_invalid ? c->d_snorm : nullptr,
+      c->d_sub, c->d_sub_cnt, n_slots, c->sub_cap, seed_hist ? c->d_hparam : nullptr, c->d_hist, c->d_qlow, c->d_qcap);
   count_launch(c->ctx);
   SDB_CUDA(cudaGetLastError());
   return SDB_OK;
@@ -447,35 +527,12 @@ sdb_status cand_rerank(Corpus* c, uint32_t nq, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // final ordering + proof.  Entries sorted ascending by (Number::cmp key, row) -- exactly the
 // DistanceEntry order of KnnTopK (knn_topk.rs:61-73): nearest first, earlier scan position wins ties.
-__global__ void __launch_bounds__(1024) cand_final_kernel(
-    const uint64_t* __restrict__ rr_key, const double* __restrict__ rr_dist, const uint32_t* __restrict__ rr_row,
-    uint32_t rr_stride, const uint32_t* __restrict__ cnt, uint32_t cap, uint32_t n_special,
-    const float* __restrict__ tau, const double* __restrict__ qmag, const float* __restrict__ bscale,
-    const float* __restrict__ beps, uint32_t* __restrict__ flags, int metric,
-    float eps_rel, float max_norm, uint32_t k, uint32_t kp, uint64_t row_base, uint64_t* __restrict__ out_rows,
-    double* __restrict__ out_dist, uint32_t* __restrict__ out_count, int debug) {
-  extern __shared__ uint64_t s_mem[];
-  const uint32_t q = blockIdx.x;
-  const uint32_t n_c = cnt[q] < cap ? cnt[q] : cap;
-  const uint32_t n_e = n_c + n_special;
-  uint32_t p2 = 1;
-  while (p2 < n_e) p2 <<= 1;
-  uint64_t* s_key = s_mem;                       // [p2] distance key
-  uint64_t* s_idx = s_mem + p2;                  // [p2] (row << 32 | entry) -- secondary order by row
-  // composite 96-bit sort done as two stable-equivalent passes: sort by (key, row) using a 64-bit
-  // rank trick: first sort entries by row (unique), then a bitonic sort on key with row as tiebreak
-  // would need 128-bit compares; instead pack: rank-by-row r (< 2^11) into the low bits of an index
-  // word and compare (key, idx) lexicographically below.
-  for (uint32_t i = threadIdx.x; i < p2; i += blockDim.x) {
-    if (i < n_e) {
-      s_key[i] = rr_key[(size_t)q * rr_stride + i];
-      s_idx[i] = ((uint64_t)rr_row[(size_t)q * rr_stride + i] << 32) | i;
-    } else {
-      s_key[i] = ~0ull;
-      s_idx[i] = ~0ull;
-    }
-  }
-  __syncthreads();
+// The candidate count varies per query (a handful on spread-out data, thousands inside a tight cluster), so the sort
+// works on a fixed 1024-entry window: up to 1024 entries are sorted in one go; longer lists are folded in chunks of
+// 768 into the running best 256 (k <= 256 on the screened path).
+constexpr uint32_t FIN_WIN = 1024, FIN_KEEP = 256;
+
+__device__ __forceinline__ void bitonic_pairs(uint64_t* s_key, uint64_t* s_idx, uint32_t p2) {
   for (uint32_t kk = 2; kk <= p2; kk <<= 1) {
     for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
       for (uint32_t i = threadIdx.x; i < p2; i += blockDim.x) {
@@ -491,6 +548,53 @@ __global__ void __launch_bounds__(1024) cand_final_kernel(
         }
       }
       __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(512) cand_final_kernel(
+    const uint64_t* __restrict__ rr_key, const double* __restrict__ rr_dist, const uint32_t* __restrict__ rr_row,
+    uint32_t rr_stride, const uint32_t* __restrict__ cnt, uint32_t cap, uint32_t n_special,
+    const float* __restrict__ tau, const double* __restrict__ qmag, const float* __restrict__ bscale,
+    const float* __restrict__ beps, uint32_t* __restrict__ flags, const uint32_t* __restrict__ qflags,
+    uint32_t* __restrict__ stat, int metric,
+    uint32_t k, uint64_t row_base, uint64_t* __restrict__ out_rows,
+    double* __restrict__ out_dist, uint32_t* __restrict__ out_count, int debug) {
+  __shared__ uint64_t s_key[FIN_WIN];  // distance key
+  __shared__ uint64_t s_idx[FIN_WIN];  // (row << 32 | entry): secondary order by row (unique), entry = index into rr_*
+  const uint32_t q = blockIdx.x;
+  const uint32_t n_c = cnt[q] < cap ? cnt[q] : cap;
+  const uint32_t n_e = n_c + n_special;
+  const uint64_t* qkey = rr_key + (size_t)q * rr_stride;
+  const uint32_t* qrow = rr_row + (size_t)q * rr_stride;
+  if (n_e <= FIN_WIN) {
+    uint32_t p2 = 1;
+    while (p2 < n_e) p2 <<= 1;
+    for (uint32_t i = threadIdx.x; i < p2; i += blockDim.x) {
+      if (i < n_e) {
+        s_key[i] = qkey[i];
+        s_idx[i] = ((uint64_t)qrow[i] << 32) | i;
+      } else {
+        s_key[i] = ~0ull;
+        s_idx[i] = ~0ull;
+      }
+    }
+    __syncthreads();
+    bitonic_pairs(s_key, s_idx, p2);
+  } else {
+    for (uint32_t i = threadIdx.x; i < FIN_KEEP; i += blockDim.x) {
+      s_key[i] = ~0ull;
+      s_idx[i] = ~0ull;
+    }
+    for (uint32_t c0 = 0; c0 < n_e; c0 += FIN_WIN - FIN_KEEP) {
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < FIN_WIN - FIN_KEEP; i += blockDim.x) {
+        const uint32_t e = c0 + i;
+        s_key[FIN_KEEP + i] = e < n_e ? qkey[e] : ~0ull;
+        s_idx[FIN_KEEP + i] = e < n_e ? (((uint64_t)qrow[e] << 32) | e) : ~0ull;
+      }
+      __syncthreads();
+      bitonic_pairs(s_key, s_idx, FIN_WIN);  // the best FIN_KEEP so far end up in front
     }
   }
   const uint32_t n_out = n_e < k ? n_e : k;
@@ -509,42 +613,44 @@ __global__ void __launch_bounds__(1024) cand_final_kernel(
       const uint64_t kth = s_key[k - 1];
       bool ok;
       if (metric == SDB_COSINE) {
-        // non-candidate: score = dot~ * (1/|x|)~ <= tau  =>  sim <= tau/|q| + eps  =>  dist >= 1 - tau/|q| - eps
+        // non-candidate: score <= tau  =>  sim <= tau * bscale / |q| + eps  =>  dist >= 1 - tau * bscale / |q| - eps
         const double bound = 1.0 - (double)t * (double)bscale[q] / qm - (double)beps[q] - 1e-9;
         ok = dist_key(bound) > kth;
       } else {
         // score = 2 dot~ - |x|^2~ <= tau  =>  d^2 = |x|^2 - 2 dot + |q|^2 >= -tau + |q|^2 - eps_e
-        const double mn = (double)max_norm;
-        const double eps_e = 2.0 * (double)eps_rel * qm * mn + 4.8e-7 * (mn * mn + 2.0 * qm * mn) + 1e-30;
-        const double L = -(double)t + qm * qm - eps_e;
+        const double L = -(double)t + qm * qm - (double)beps[q];
         ok = L > 0.0 && dist_key(sqrt(L) * (1.0 - 1e-12)) > kth;
       }
       if (!ok) fl |= 2u;
       if (debug && q == 0)
-        printf("[sdb final] q0 metric=%d tau=%g qmag=%g max_norm=%g eps_rel=%g n_e=%u kth_key=%llx ok=%d\n", metric,
-               (double)t, qm, (double)max_norm, (double)eps_rel, n_e, (unsigned long long)kth, (int)ok);
+        printf("[sdb final] q0 metric=%d tau=%g qmag=%g beps=%g n_e=%u kth_key=%llx ok=%d\n", metric, (double)t, qm,
+               (double)beps[q], n_e, (unsigned long long)kth, (int)ok);
     }
     if (fl & 1u) fl |= 2u;  // overflowed candidate buffer => exact re-run
     flags[q] = fl;
+    if ((fl & 2u) || (qflags[q] & 1u)) atomicAdd(stat + 0, 1u);  // queries the host still has to repair
+    atomicAdd(stat + 1, n_e);
+    atomicMax(stat + 2, n_e);
   }
 }
 
-sdb_status cand_final(Corpus* c, uint32_t nq, uint32_t k, uint32_t kp, float eps_rel, uint64_t row_base,
-                      uint64_t* d_out_rows, double* d_out_dist, uint32_t* d_out_count, cudaStream_t st) {
-  uint32_t p2 = 1;
-  while (p2 < kp + SPECIAL_CAP) p2 <<= 1;
-  const size_t smem = sizeof(uint64_t) * 2 * p2;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SDB_CUDA(cudaFuncSetAttribute(cand_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+sdb_status cand_final(Corpus* c, uint32_t nq, uint32_t k, uint64_t row_base, uint64_t* d_out_rows, double* d_out_dist,
+                      uint32_t* d_out_count, cudaStream_t st) {
+  if (k > FIN_KEEP) {
+    set_error("cand_final: k = %u exceeds the screened path's limit of %u", k, FIN_KEEP);
+    return SDB_EINVAL;
   }
-  cand_final_kernel<<<nq, 1024, smem, st>>>(c->d_rr_key, c->d_rr_dist, c->d_rr_row, c->rr_stride, c->d_cand_cnt,
-                                            c->sc_cap, c->n_special, c->d_tau, c->d_qmag, c->d_bscale, c->d_beps, c->d_flags,
-                                            (int)c->metric, eps_rel, c->max_norm, k, kp, row_base, d_out_rows,
-                                            d_out_dist, d_out_count, getenv("SDB_DEBUG") != nullptr);
+  static const int debug = getenv("SDB_DEBUG") != nullptr;
+  cand_final_kernel<<<nq, 512, 0, st>>>(c->d_rr_key, c->d_rr_dist, c->d_rr_row, c->rr_stride, c->d_cand_cnt, c->sc_cap,
+                                        c->n_special, c->d_tau, c->d_qmag, c->d_bscale, c->d_beps, c->d_flags, c->d_qflags, c->d_stat,
+                                        (int)c->metric, k, row_base, d_out_rows, d_out_dist, d_out_count, debug);
   count_launch(c->ctx);
   SDB_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
+
+sdb_status candidates_init_device() {
+  SDB_CUDA(cudaFuncSetAttribute(cand_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return SDB_OK;
 }
 

@@ -1,0 +1,538 @@
+// comm.cu -- multi-GPU brute force behind the ABI: row-sharded corpora, ONE NCCL all-gather of the per-shard top-k
+// blocks per batch, merge kernel on every rank.  (no reference equivalent -- the reference is
+// single-node CPU code.)
+//
+// NCCL is bound at run time (dlopen of libnccl.so.2) so that single-GPU users need no NCCL at all and a host process
+// that already carries its own NCCL (PyTorch) shares that copy instead of loading a second one.
+//
+// Both deployment shapes are served by the same three phases (local search -> all-gather -> merge):
+//   * one process per GPU  : sdb_comm_unique_id / sdb_comm_init_rank, then sdb_knn_sharded_submit* / _wait per rank
+//   * one process, N GPUs  : sdb_ctx_create_multi (ncclCommInitAll), then sdb_knn_sharded_multi drives every shard
+//                            from one thread inside ncclGroupStart/End
+// Everything is enqueued on the context's stream: no host synchronisation between the local search, the collective
+// and the merge.  Exactness across ranks: every block carries the number of queries its rank still has to repair on
+// the host side (failed proof / special queries); since every rank sees every header after the all-gather, all ranks
+// take the same decision to run a repair round (local repair, second all-gather + merge) -- no extra collective.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include "internal.cuh"
+
+namespace sdb {
+
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static std::mutex g_nccl_mu;
+
+static sdb_status nccl_load() {
+  std::lock_guard<std::mutex> g(g_nccl_mu);
+  if (g_nccl.lib) return SDB_OK;
+  void* h = nullptr;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) {
+    set_error("NCCL not available: %s", dlerror());
+    return SDB_ENCCL;
+  }
+#define LOAD(field, sym)                                               \
+  *(void**)(&g_nccl.field) = dlsym(h, sym);                            \
+  if (!g_nccl.field) {                                                 \
+    set_error("NCCL symbol %s missing", sym);                          \
+    return SDB_ENCCL;                                                  \
+  }
+  LOAD(GetUniqueId, "ncclGetUniqueId");
+  LOAD(CommInitRank, "ncclCommInitRank");
+  LOAD(CommInitAll, "ncclCommInitAll");
+  LOAD(CommDestroy, "ncclCommDestroy");
+  LOAD(AllGather, "ncclAllGather");
+  LOAD(GroupStart, "ncclGroupStart");
+  LOAD(GroupEnd, "ncclGroupEnd");
+  LOAD(GetErrorString, "ncclGetErrorString");
+#undef LOAD
+  g_nccl.lib = h;
+  return SDB_OK;
+}
+
+#define SDB_NCCL(call)                                                                             \
+  do {                                                                                             \
+    ncclResult_t r__ = (call);                                                                     \
+    if (r__ != ncclSuccess) {                                                                      \
+      ::sdb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r__));  \
+      return SDB_ENCCL;                                                                            \
+    }                                                                                              \
+  } while (0)
+
+struct Comm {
+  ncclComm_t comm = nullptr;
+  int nranks = 1, rank = 0;
+};
+
+void comm_destroy(Ctx* ctx) {
+  if (ctx && ctx->comm) {
+    if (ctx->comm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm->comm);
+    delete ctx->comm;
+    ctx->comm = nullptr;
+  }
+}
+
+// one rank's block inside the all-gather buffer: rows u64[nq*k] | dist f64[nq*k] | count u32[nq] | hdr u32[4]
+struct BlockLayout {
+  size_t off_rows, off_dist, off_cnt, off_hdr, bytes;
+};
+static BlockLayout block_layout(uint32_t nq, uint32_t k) {
+  BlockLayout b;
+  b.off_rows = 0;
+  b.off_dist = (size_t)nq * k * 8;
+  b.off_cnt = 2 * (size_t)nq * k * 8;
+  b.off_hdr = (b.off_cnt + (size_t)nq * 4 + 15) / 16 * 16;
+  b.bytes = b.off_hdr + 16;
+  return b;
+}
+
+struct ShardSlot {  // per in-flight ticket: this rank's block, the gathered blocks, the headers on the host
+  uint8_t* d_block = nullptr;
+  uint8_t* d_gather = nullptr;
+  size_t block_cap = 0, gather_cap = 0;
+  uint32_t* h_hdr = nullptr;  // pinned, nranks x 4
+  int hdr_cap = 0;
+  cudaEvent_t ev_done = nullptr;
+  uint64_t *d_out_rows = nullptr, *h_out_rows = nullptr;
+  double *d_out_dist = nullptr, *h_out_dist = nullptr;
+  uint32_t *d_out_count = nullptr, *h_out_count = nullptr;
+  uint64_t* d_res_rows = nullptr;  // host-buffer entry points: merged result staging
+  double* d_res_dist = nullptr;
+  uint32_t* d_res_count = nullptr;
+  size_t res_cap = 0, res_cap_q = 0;
+};
+
+}  // namespace sdb
+
+using namespace sdb;
+
+// the brute-force driver of api.cu
+namespace sdb {
+sdb_status knn_submit_for_shard(Corpus* c, const double* d_queries, const double* h_queries, uint32_t nq, uint32_t k,
+                                uint64_t* d_out_rows, double* d_out_dist, uint32_t* d_out_count, int* slot_index,
+                                uint32_t* ticket, const double** d_queries_used);
+sdb_status knn_finish_for_shard(Corpus* c, uint32_t ticket, bool* repaired);
+sdb_status knn_release_ticket(Corpus* c, uint32_t ticket);
+const uint32_t* knn_ticket_stat_host(Corpus* c, uint32_t ticket, int* exact_only);
+sdb_status topk_merge_launch(Ctx* ctx, uint32_t n_lists, uint32_t nq, uint32_t k, const uint64_t* d_rows,
+                             const double* d_dist, const uint32_t* d_counts, uint64_t stride_rows, uint64_t stride_dist,
+                             uint64_t stride_counts, uint64_t* d_out_rows, double* d_out_dist, uint32_t* d_out_count,
+                             cudaStream_t st);
+}  // namespace sdb
+
+namespace {
+
+ShardSlot g_dummy;
+
+struct ShardState {  // hangs off the corpus through a side table (kept out of internal.cuh: only comm.cu needs it)
+  ShardSlot slots[N_TICKETS];
+};
+std::mutex g_state_mu;
+std::vector<std::pair<Corpus*, ShardState*>> g_states;
+
+ShardState* state_of(Corpus* c) {
+  std::lock_guard<std::mutex> g(g_state_mu);
+  for (auto& p : g_states)
+    if (p.first == c) return p.second;
+  ShardState* s = new ShardState();
+  g_states.emplace_back(c, s);
+  return s;
+}
+
+sdb_status slot_reserve(Corpus* c, ShardSlot& s, uint32_t nq, uint32_t k, bool host_out) {
+  const int nranks = c->ctx->comm ? c->ctx->comm->nranks : 1;
+  const BlockLayout bl = block_layout(nq, k);
+  if (!s.ev_done) SDB_CUDA(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+  if (s.block_cap < bl.bytes) {
+    cudaFree(s.d_block);
+    s.d_block = nullptr;
+    s.block_cap = 0;
+    SDB_CUDA(cudaMalloc(&s.d_block, bl.bytes));
+    s.block_cap = bl.bytes;
+  }
+  if (s.gather_cap < bl.bytes * nranks) {
+    cudaFree(s.d_gather);
+    s.d_gather = nullptr;
+    s.gather_cap = 0;
+    SDB_CUDA(cudaMalloc(&s.d_gather, bl.bytes * nranks));
+    s.gather_cap = bl.bytes * nranks;
+  }
+  if (s.hdr_cap < nranks) {
+    if (s.h_hdr) cudaFreeHost(s.h_hdr);
+    s.h_hdr = nullptr;
+    SDB_CUDA(cudaHostAlloc(&s.h_hdr, sizeof(uint32_t) * 4 * nranks, cudaHostAllocDefault));
+    s.hdr_cap = nranks;
+  }
+  if (host_out) {
+    const size_t need = (size_t)nq * (k ? k : 1);
+    if (s.res_cap < need || s.res_cap_q < nq) {
+      cudaFree(s.d_res_rows);
+      cudaFree(s.d_res_dist);
+      cudaFree(s.d_res_count);
+      s.d_res_rows = nullptr; s.d_res_dist = nullptr; s.d_res_count = nullptr;
+      s.res_cap = s.res_cap_q = 0;
+      SDB_CUDA(cudaMalloc(&s.d_res_rows, sizeof(uint64_t) * need));
+      SDB_CUDA(cudaMalloc(&s.d_res_dist, sizeof(double) * need));
+      SDB_CUDA(cudaMalloc(&s.d_res_count, sizeof(uint32_t) * nq));
+      s.res_cap = need;
+      s.res_cap_q = nq;
+    }
+  }
+  return SDB_OK;
+}
+
+struct Pending {  // one shard's in-flight sharded batch
+  Corpus* c = nullptr;
+  ShardSlot* s = nullptr;
+  uint32_t ticket = 0, nq = 0, k = 0;
+  int slot = -1;
+};
+
+// phase A: the local search into this rank's block, header = number of queries this rank must repair on the host
+sdb_status phase_local(Corpus* c, const double* d_queries, const double* h_queries, uint32_t nq, uint32_t k,
+                       uint64_t* d_out_rows, double* d_out_dist, uint32_t* d_out_count, uint64_t* h_out_rows,
+                       double* h_out_dist, uint32_t* h_out_count, Pending* p) {
+  ShardState* ss = state_of(c);
+  const BlockLayout bl = block_layout(nq, k);
+  // the slot index follows the brute-force driver's ticket slot, so slot buffers are free exactly when the ticket is
+  int slot = -1;
+  uint32_t ticket = 0;
+  // reserve with a provisional slot: the driver tells us which ticket slot it used
+  // (buffers are per slot; reserve all lazily below)
+  const double* dq = nullptr;
+  // block pointers are only known once the slot is; the driver lets us pass them through a callback-free two-step:
+  // first pick the slot (free_ticket order is deterministic), then reserve, then submit.
+  for (int i = 0; i < N_TICKETS; i++)
+    if (!c->tickets[i].busy) {
+      slot = i;
+      break;
+    }
+  if (slot < 0) {
+    set_error("too many batches in flight (%d): call the matching wait first", N_TICKETS);
+    return SDB_EOVERFLOW;
+  }
+  ShardSlot& s = ss->slots[slot];
+  const bool host_out = h_out_count != nullptr;
+  SDB_TRY(slot_reserve(c, s, nq, k, host_out));
+  int used = -1;
+  SDB_TRY(knn_submit_for_shard(c, d_queries, h_queries, nq, k, (uint64_t*)(s.d_block + bl.off_rows),
+                               (double*)(s.d_block + bl.off_dist), (uint32_t*)(s.d_block + bl.off_cnt), &used, &ticket,
+                               &dq));
+  if (used != slot) {
+    set_error("internal: ticket slot mismatch (%d vs %d)", used, slot);
+    return SDB_EINVAL;
+  }
+  cudaStream_t st = c->ctx->stream;
+  int exact_only = 0;
+  const uint32_t* h_stat = knn_ticket_stat_host(c, ticket, &exact_only);
+  if (exact_only) SDB_CUDA(cudaMemcpyAsync(s.d_block + bl.off_hdr, h_stat, 16, cudaMemcpyHostToDevice, st));
+  else SDB_CUDA(cudaMemcpyAsync(s.d_block + bl.off_hdr, c->d_stat, 16, cudaMemcpyDeviceToDevice, st));
+  s.d_out_rows = host_out ? s.d_res_rows : d_out_rows;
+  s.d_out_dist = host_out ? s.d_res_dist : d_out_dist;
+  s.d_out_count = host_out ? s.d_res_count : d_out_count;
+  s.h_out_rows = h_out_rows;
+  s.h_out_dist = h_out_dist;
+  s.h_out_count = h_out_count;
+  p->c = c;
+  p->s = &s;
+  p->ticket = ticket;
+  p->nq = nq;
+  p->k = k;
+  p->slot = slot;
+  return SDB_OK;
+}
+
+// phase B: ONE all-gather of the per-shard blocks (inside the caller's group when one thread drives several GPUs)
+sdb_status phase_gather(const Pending& p) {
+  Corpus* c = p.c;
+  const BlockLayout bl = block_layout(p.nq, p.k);
+  cudaStream_t st = c->ctx->stream;
+  if (c->ctx->comm && c->ctx->comm->nranks > 1) {
+    SDB_NCCL(g_nccl.AllGather(p.s->d_block, p.s->d_gather, bl.bytes, ncclChar, c->ctx->comm->comm, st));
+  } else {
+    SDB_CUDA(cudaMemcpyAsync(p.s->d_gather, p.s->d_block, bl.bytes, cudaMemcpyDeviceToDevice, st));
+  }
+  return SDB_OK;
+}
+
+// phase C: merge on this rank, headers to the host, optional copy of the merged result to host buffers
+sdb_status phase_merge(const Pending& p) {
+  Corpus* c = p.c;
+  ShardSlot& s = *p.s;
+  const int nranks = c->ctx->comm ? c->ctx->comm->nranks : 1;
+  const BlockLayout bl = block_layout(p.nq, p.k);
+  cudaStream_t st = c->ctx->stream;
+  if (p.k)
+    SDB_TRY(topk_merge_launch(c->ctx, (uint32_t)nranks, p.nq, p.k, (const uint64_t*)(s.d_gather + bl.off_rows),
+                              (const double*)(s.d_gather + bl.off_dist), (const uint32_t*)(s.d_gather + bl.off_cnt),
+                              bl.bytes / 8, bl.bytes / 8, bl.bytes / 4, s.d_out_rows, s.d_out_dist, s.d_out_count, st));
+  else SDB_CUDA(cudaMemsetAsync(s.d_out_count, 0, sizeof(uint32_t) * p.nq, st));
+  SDB_CUDA(cudaMemcpy2DAsync(s.h_hdr, 16, s.d_gather + bl.off_hdr, bl.bytes, 16, (size_t)nranks, cudaMemcpyDeviceToHost, st));
+  if (s.h_out_count) {
+    if (p.k) {
+      SDB_CUDA(cudaMemcpyAsync(s.h_out_rows, s.d_out_rows, sizeof(uint64_t) * (size_t)p.nq * p.k, cudaMemcpyDeviceToHost, st));
+      SDB_CUDA(cudaMemcpyAsync(s.h_out_dist, s.d_out_dist, sizeof(double) * (size_t)p.nq * p.k, cudaMemcpyDeviceToHost, st));
+    }
+    SDB_CUDA(cudaMemcpyAsync(s.h_out_count, s.d_out_count, sizeof(uint32_t) * p.nq, cudaMemcpyDeviceToHost, st));
+  }
+  SDB_CUDA(cudaEventRecord(s.ev_done, st));
+  return SDB_OK;
+}
+
+// completion of a set of shards driven by this thread (1 in the process-per-GPU shape).  Every rank sees every header,
+// so the decision to run the repair round is the same everywhere.
+sdb_status finish_all(Pending* ps, int n) {
+  bool any = false;
+  for (int i = 0; i < n; i++) {
+    SDB_CUDA(cudaSetDevice(ps[i].c->ctx->device));
+    SDB_CUDA(cudaEventSynchronize(ps[i].s->ev_done));
+    const int nranks = ps[i].c->ctx->comm ? ps[i].c->ctx->comm->nranks : 1;
+    for (int r = 0; r < nranks; r++) any = any || ps[i].s->h_hdr[4 * r] != 0;
+  }
+  sdb_status rc = SDB_OK;
+  if (any) {
+    for (int i = 0; i < n && rc == SDB_OK; i++) {
+      cudaSetDevice(ps[i].c->ctx->device);
+      bool repaired = false;
+      rc = knn_finish_for_shard(ps[i].c, ps[i].ticket, &repaired);  // local ladder re-runs / exact fallbacks
+    }
+    if (rc == SDB_OK) {
+      const bool group = n > 1;
+      if (group) g_nccl.GroupStart();
+      for (int i = 0; i < n && rc == SDB_OK; i++) {
+        cudaSetDevice(ps[i].c->ctx->device);
+        rc = phase_gather(ps[i]);
+      }
+      if (group) g_nccl.GroupEnd();
+      for (int i = 0; i < n && rc == SDB_OK; i++) {
+        cudaSetDevice(ps[i].c->ctx->device);
+        rc = phase_merge(ps[i]);
+      }
+      for (int i = 0; i < n && rc == SDB_OK; i++) {
+        cudaSetDevice(ps[i].c->ctx->device);
+        if (cudaEventSynchronize(ps[i].s->ev_done) != cudaSuccess) {
+          set_error("sharded repair round: %s", cudaGetErrorString(cudaGetLastError()));
+          rc = SDB_ECUDA;
+        }
+      }
+    }
+  } else {
+    for (int i = 0; i < n && rc == SDB_OK; i++) {
+      cudaSetDevice(ps[i].c->ctx->device);
+      bool repaired = false;
+      rc = knn_finish_for_shard(ps[i].c, ps[i].ticket, &repaired);  // nothing flagged: records the statistics
+    }
+  }
+  for (int i = 0; i < n; i++) knn_release_ticket(ps[i].c, ps[i].ticket);
+  return rc;
+}
+
+// pending sharded tickets of the process-per-GPU shape, keyed by (corpus, ticket)
+std::mutex g_pending_mu;
+std::vector<Pending> g_pending;
+
+}  // namespace
+
+extern "C" {
+
+sdb_status sdb_comm_unique_id(uint8_t* id128) {
+  if (!id128) return SDB_EINVAL;
+  SDB_TRY(nccl_load());
+  static_assert(sizeof(ncclUniqueId) == SDB_COMM_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId id;
+  SDB_NCCL(g_nccl.GetUniqueId(&id));
+  memcpy(id128, &id, sizeof(id));
+  return SDB_OK;
+}
+
+sdb_status sdb_comm_init_rank(sdb_ctx* ctx, int nranks, int rank, const uint8_t* id128) {
+  if (!ctx || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return SDB_EINVAL;
+  SDB_TRY(nccl_load());
+  std::lock_guard<std::mutex> g(ctx->mu);
+  SDB_CUDA(cudaSetDevice(ctx->device));
+  comm_destroy(ctx);
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  Comm* cm = new Comm();
+  cm->nranks = nranks;
+  cm->rank = rank;
+  const ncclResult_t r = g_nccl.CommInitRank(&cm->comm, nranks, id, rank);
+  if (r != ncclSuccess) {
+    set_error("ncclCommInitRank(%d of %d) failed: %s", rank, nranks, g_nccl.GetErrorString(r));
+    delete cm;
+    return SDB_ENCCL;
+  }
+  ctx->comm = cm;
+  return SDB_OK;
+}
+
+int sdb_comm_size(const sdb_ctx* ctx) { return ctx && ctx->comm ? ctx->comm->nranks : 1; }
+int sdb_comm_rank(const sdb_ctx* ctx) { return ctx && ctx->comm ? ctx->comm->rank : 0; }
+
+sdb_status sdb_ctx_create_multi(const int* devices, int ndev, sdb_ctx** out) {
+  if (!devices || !out || ndev < 1 || ndev > 64) return SDB_EINVAL;
+  for (int i = 0; i < ndev; i++) out[i] = nullptr;
+  if (ndev > 1) SDB_TRY(nccl_load());
+  for (int i = 0; i < ndev; i++) {
+    const sdb_status rc = sdb_ctx_create(devices[i], &out[i]);
+    if (rc != SDB_OK) {
+      for (int j = 0; j < i; j++) sdb_ctx_destroy(out[j]);
+      for (int j = 0; j < ndev; j++) out[j] = nullptr;
+      return rc;
+    }
+  }
+  if (ndev > 1) {
+    std::vector<ncclComm_t> comms(ndev);
+    const ncclResult_t r = g_nccl.CommInitAll(comms.data(), ndev, devices);
+    if (r != ncclSuccess) {
+      set_error("ncclCommInitAll(%d devices) failed: %s", ndev, g_nccl.GetErrorString(r));
+      for (int j = 0; j < ndev; j++) {
+        sdb_ctx_destroy(out[j]);
+        out[j] = nullptr;
+      }
+      return SDB_ENCCL;
+    }
+    for (int i = 0; i < ndev; i++) {
+      Comm* cm = new Comm();
+      cm->comm = comms[i];
+      cm->nranks = ndev;
+      cm->rank = i;
+      out[i]->comm = cm;
+    }
+  }
+  return SDB_OK;
+}
+
+sdb_status sdb_corpus_set_row_base(sdb_corpus* c, uint64_t row_base) {
+  if (!c) return SDB_EINVAL;
+  c->row_base = row_base;
+  return SDB_OK;
+}
+
+static sdb_status sharded_submit(sdb_corpus* c, const double* d_queries, const double* h_queries, uint32_t nq, uint32_t k,
+                                 uint64_t* d_out_rows, double* d_out_dist, uint32_t* d_out_count, uint64_t* h_out_rows,
+                                 double* h_out_dist, uint32_t* h_out_count, uint32_t* ticket) {
+  if (!c || !ticket || !nq) return SDB_EINVAL;
+  if (c->ctx->comm && c->ctx->comm->nranks > 1) SDB_TRY(nccl_load());
+  Pending p;
+  {
+    std::lock_guard<std::mutex> g(c->mu);
+    SDB_CUDA(cudaSetDevice(c->ctx->device));
+    SDB_TRY(phase_local(c, d_queries, h_queries, nq, k, d_out_rows, d_out_dist, d_out_count, h_out_rows, h_out_dist,
+                        h_out_count, &p));
+    sdb_status rc = phase_gather(p);
+    if (rc == SDB_OK) rc = phase_merge(p);
+    if (rc != SDB_OK) {
+      cudaStreamSynchronize(c->ctx->stream);
+      knn_release_ticket(c, p.ticket);
+      return rc;
+    }
+  }
+  {
+    std::lock_guard<std::mutex> g(g_pending_mu);
+    g_pending.push_back(p);
+  }
+  *ticket = p.ticket;
+  return SDB_OK;
+}
+
+sdb_status sdb_knn_sharded_submit_device(sdb_corpus* c, const double* d_queries, uint32_t nq, uint32_t k,
+                                         uint64_t* d_out_rows, double* d_out_dist, uint32_t* d_out_count,
+                                         uint32_t* ticket) {
+  if (!d_queries || !d_out_count || (k && (!d_out_rows || !d_out_dist))) return SDB_EINVAL;
+  return sharded_submit(c, d_queries, nullptr, nq, k, d_out_rows, d_out_dist, d_out_count, nullptr, nullptr, nullptr, ticket);
+}
+
+sdb_status sdb_knn_sharded_submit(sdb_corpus* c, const double* queries, uint32_t nq, uint32_t k, uint64_t* out_rows,
+                                  double* out_dist, uint32_t* out_count, uint32_t* ticket) {
+  if (!queries || !out_count || (k && (!out_rows || !out_dist))) return SDB_EINVAL;
+  return sharded_submit(c, nullptr, queries, nq, k, nullptr, nullptr, nullptr, out_rows, out_dist, out_count, ticket);
+}
+
+sdb_status sdb_knn_sharded_wait(sdb_corpus* c, uint32_t ticket) {
+  if (!c) return SDB_EINVAL;
+  Pending p;
+  {
+    std::lock_guard<std::mutex> g(g_pending_mu);
+    size_t i = 0;
+    for (; i < g_pending.size(); i++)
+      if (g_pending[i].c == c && g_pending[i].ticket == ticket) break;
+    if (i == g_pending.size()) {
+      set_error("sdb_knn_sharded_wait: unknown or already completed ticket %u", ticket);
+      return SDB_EINVAL;
+    }
+    p = g_pending[i];
+    g_pending.erase(g_pending.begin() + (long)i);
+  }
+  std::lock_guard<std::mutex> g(c->mu);
+  return finish_all(&p, 1);
+}
+
+sdb_status sdb_knn_sharded_multi(sdb_corpus* const* shards, int n, const double* queries, uint32_t nq, uint32_t k,
+                                 uint64_t* out_rows, double* out_dist, uint32_t* out_count) {
+  if (!shards || n < 1 || n > 64 || !queries || !nq || !out_count || (k && (!out_rows || !out_dist))) return SDB_EINVAL;
+  if (n > 1) SDB_TRY(nccl_load());
+  std::vector<Pending> ps((size_t)n);
+  std::vector<std::unique_lock<std::mutex>> locks;
+  for (int i = 0; i < n; i++) {
+    if (!shards[i]) return SDB_EINVAL;
+    locks.emplace_back(shards[i]->mu);
+  }
+  sdb_status rc = SDB_OK;
+  int started = 0;
+  for (int i = 0; i < n && rc == SDB_OK; i++) {  // every shard searches; shard 0's merged copy goes to the caller
+    cudaSetDevice(shards[i]->ctx->device);
+    ShardState* ss = state_of(shards[i]);
+    (void)ss;
+    if (i == 0) rc = phase_local(shards[i], nullptr, queries, nq, k, nullptr, nullptr, nullptr, out_rows, out_dist, out_count, &ps[i]);
+    else {
+      // the other shards keep their merged copy on the device (slot staging buffers)
+      rc = phase_local(shards[i], nullptr, queries, nq, k, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &ps[i]);
+      if (rc == SDB_OK) {
+        ShardSlot& s = *ps[i].s;
+        rc = slot_reserve(shards[i], s, nq, k, true);
+        s.d_out_rows = s.d_res_rows;
+        s.d_out_dist = s.d_res_dist;
+        s.d_out_count = s.d_res_count;
+      }
+    }
+    if (rc == SDB_OK) started++;
+  }
+  if (rc == SDB_OK) {
+    if (n > 1) g_nccl.GroupStart();
+    for (int i = 0; i < n && rc == SDB_OK; i++) {
+      cudaSetDevice(shards[i]->ctx->device);
+      rc = phase_gather(ps[i]);
+    }
+    if (n > 1) g_nccl.GroupEnd();
+    for (int i = 0; i < n && rc == SDB_OK; i++) {
+      cudaSetDevice(shards[i]->ctx->device);
+      rc = phase_merge(ps[i]);
+    }
+  }
+  if (rc == SDB_OK) return finish_all(ps.data(), n);
+  for (int i = 0; i < started; i++) {
+    cudaSetDevice(shards[i]->ctx->device);
+    cudaStreamSynchronize(shards[i]->ctx->stream);
+    knn_release_ticket(shards[i], ps[i].ticket);
+  }
+  return rc;
+}
+
+}  // extern "C"

@@ -60,15 +60,32 @@ __global__ void pad_snorm_kernel(float* __restrict__ snorm, uint64_t n, uint64_t
   if (i < n_pad) snorm[i] = __int_as_float(0x7fc00000);
 }
 
-__global__ void to_bf16_kernel(const float* __restrict__ rows, uint32_t dim, uint32_t dim_pad, uint64_t n,
-                               uint64_t n_pad, __nv_bfloat16* __restrict__ out) {
-  const uint64_t total = n_pad * dim_pad;
-  const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
-    const uint64_t r = i / dim_pad;
-    const uint32_t c = (uint32_t)(i % dim_pad);
-    float v = (r < n && c < dim) ? rows[r * dim + c] : 0.f;
-    out[i] = __float2bfloat16_rn(v);
+// bf16 screen copy, one warp per row; also measures e_x = max over valid rows of |x - bf16(x)| / |x| (the residual
+// norm that enters the screen's error bound; at most 2^-8 by construction of round-to-nearest, usually ~0.6 of that)
+__global__ void __launch_bounds__(256) to_bf16_kernel(const float* __restrict__ rows, uint32_t dim, uint32_t dim_pad, uint64_t n,
+                                                      uint64_t n_pad, const double* __restrict__ mag,
+                                                      const float* __restrict__ snorm, __nv_bfloat16* __restrict__ out,
+                                                      uint32_t* max_rel_bits) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warps = (uint64_t)gridDim.x * 8;
+  for (uint64_t r = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < n_pad; r += warps) {
+    __nv_bfloat16* o = out + r * dim_pad;
+    float err2 = 0.f;
+    for (uint32_t c = lane; c < dim_pad; c += 32) {
+      const float v = (r < n && c < dim) ? rows[r * dim + c] : 0.f;
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      o[c] = h;
+      const float d = v - __bfloat162float(h);
+      if (d == d) err2 = fmaf(d, d, err2);
+    }
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) err2 += __shfl_xor_sync(0xffffffffu, err2, o2);
+    if (lane == 0 && r < n) {
+      const float sn = snorm[r];
+      const double m = mag[r];
+      if (sn == sn && m > 0.0 && isfinite(m) && isfinite(err2))  // skipped / special rows never reach the screen
+        atomicMax(max_rel_bits, __float_as_uint((sqrtf(err2) / (float)m) * 1.0001f + 1e-9f));
+    }
   }
 }
 
@@ -136,9 +153,9 @@ __global__ void __launch_bounds__(256) quantize_rows_kernel(const float* __restr
 sdb_status corpus_finalize_device(Corpus* c) {
   Ctx* ctx = c->ctx;
   cudaStream_t st = ctx->stream;
-  uint32_t* d_tmp = nullptr;  // [0] special count, [1] max-norm bits, [2] max relative int8 error bits
-  SDB_CUDA(cudaMalloc(&d_tmp, 16));
-  SDB_CUDA(cudaMemsetAsync(d_tmp, 0, 16, st));
+  uint32_t* d_tmp = nullptr;  // [0] special count, [1] max-norm bits, [2] max relative int8 error bits, [3] int8 gmax
+  SDB_CUDA(cudaMalloc(&d_tmp, 32));                                       // [4] max relative bf16 residual bits
+  SDB_CUDA(cudaMemsetAsync(d_tmp, 0, 32, st));
   if (!c->d_special) SDB_CUDA(cudaMalloc(&c->d_special, sizeof(uint32_t) * SPECIAL_CAP));
   {
     const uint64_t n_pad = (c->n + TILE_ROWS - 1) / TILE_ROWS * TILE_ROWS;
@@ -161,8 +178,8 @@ sdb_status corpus_finalize_device(Corpus* c) {
     SDB_CUDA(cudaGetLastError());
     if (c->dtype == SDB_F32 && c->d_bf16) {
       const uint64_t n_pad = (c->n + TILE_ROWS - 1) / TILE_ROWS * TILE_ROWS;
-      to_bf16_kernel<<<ctx->sm_count * 16, 256, 0, st>>>((const float*)c->d_rows, c->dim, c->dim_pad, c->n,
-                                                         n_pad, c->d_bf16);
+      to_bf16_kernel<<<ctx->sm_count * 16, 256, 0, st>>>((const float*)c->d_rows, c->dim, c->dim_pad, c->n, n_pad,
+                                                         c->d_mag, c->d_snorm, c->d_bf16, d_tmp + 4);
       count_launch(ctx);
       SDB_CUDA(cudaGetLastError());
     }
@@ -176,8 +193,8 @@ sdb_status corpus_finalize_device(Corpus* c) {
     count_launch(ctx, 2);
     SDB_CUDA(cudaGetLastError());
   }
-  uint32_t h[4] = {0, 0, 0, 0};
-  SDB_CUDA(cudaMemcpyAsync(h, d_tmp, 16, cudaMemcpyDeviceToHost, st));
+  uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  SDB_CUDA(cudaMemcpyAsync(h, d_tmp, 32, cudaMemcpyDeviceToHost, st));
   SDB_CUDA(cudaStreamSynchronize(st));
   SDB_CUDA(cudaFree(d_tmp));
   c->special_overflow = h[0] > (uint32_t)SPECIAL_CAP;
@@ -186,6 +203,12 @@ sdb_status corpus_finalize_device(Corpus* c) {
   memcpy(&mn, &h[1], 4);
   c->max_norm = mn;
   memcpy(&c->max_rel_qerr, &h[2], 4);
+  {
+    float e;
+    memcpy(&e, &h[4], 4);
+    // never trust a figure above the analytic worst case of round-to-nearest (2^-8 per element => 2^-8 in norm)
+    c->bf16_rel_err = (e > 0.f && e < 0.00390625f) ? e : 0.00390625f;
+  }
   {
     float gmax;
     memcpy(&gmax, &h[3], 4);

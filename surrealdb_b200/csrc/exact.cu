@@ -277,8 +277,15 @@ __global__ void __launch_bounds__(1024) sel_emit_kernel(const SelState* st, cons
   if (threadIdx.x == 0) *out_count = n;
 }
 
-sdb_status exact_query(Corpus* c, uint32_t q, uint32_t k, uint64_t row_base, uint64_t* d_out_rows,
-                       double* d_out_dist, uint32_t* d_out_count, cudaStream_t st) {
+sdb_status exact_init_device() {
+  SDB_CUDA(cudaFuncSetAttribute(sel_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 4096));
+  return SDB_OK;
+}
+
+// d_out_rows / d_out_dist / d_out_count point at THIS query's output row
+sdb_status exact_query(Corpus* c, const double* d_q64, const double* d_qmag, const uint32_t* d_qflags, uint32_t k,
+                       uint64_t row_base, uint64_t* d_out_rows, double* d_out_dist, uint32_t* d_out_count,
+                       cudaStream_t st) {
   Ctx* ctx = c->ctx;
   if (c->ex_cap < c->n || !c->d_ex_key) {
     cudaFree(c->d_ex_key);
@@ -303,12 +310,11 @@ sdb_status exact_query(Corpus* c, uint32_t q, uint32_t k, uint64_t row_base, uin
     const int grid = ctx->sm_count * 8;
     if (c->dtype == SDB_F32)
       exact_keys_kernel<float, 4><<<grid, 128, 0, st>>>((const float*)c->d_rows, c->dim, n, (int)c->metric, c->d_mag,
-                                                        c->d_skip, c->d_q64 + (size_t)q * c->dim, c->d_qmag + q,
-                                                        c->d_qflags + q, c->d_ex_key, nullptr);
+                                                        c->d_skip, d_q64, d_qmag, d_qflags, c->d_ex_key, nullptr);
     else
       exact_keys_kernel<double, 4><<<grid, 128, 0, st>>>((const double*)c->d_rows, c->dim, n, (int)c->metric,
-                                                         c->d_mag, c->d_skip, c->d_q64 + (size_t)q * c->dim,
-                                                         c->d_qmag + q, c->d_qflags + q, c->d_ex_key, nullptr);
+                                                         c->d_mag, c->d_skip, d_q64, d_qmag, d_qflags, c->d_ex_key,
+                                                         nullptr);
     count_launch(ctx);
   }
   sel_init_kernel<<<1, 256, 0, st>>>(sel, k);
@@ -322,9 +328,8 @@ sdb_status exact_query(Corpus* c, uint32_t q, uint32_t k, uint64_t row_base, uin
   sel_gather_kernel<<<hgrid, 256, 0, st>>>(c->d_ex_key, n, sel, g_key, g_row);
   uint32_t p2 = 1;
   while (p2 < k) p2 <<= 1;
-  sel_emit_kernel<<<1, 1024, sizeof(uint64_t) * 2 * p2, st>>>(sel, g_key, g_row, k, row_base,
-                                                             d_out_rows + (size_t)q * k, d_out_dist + (size_t)q * k,
-                                                             d_out_count + q);
+  sel_emit_kernel<<<1, 1024, sizeof(uint64_t) * 2 * p2, st>>>(sel, g_key, g_row, k, row_base, d_out_rows, d_out_dist,
+                                                             d_out_count);
   count_launch(ctx, 2);
   SDB_CUDA(cudaGetLastError());
   return SDB_OK;

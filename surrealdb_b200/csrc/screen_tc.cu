@@ -12,6 +12,13 @@
 //                              the row's screening norm, compare with the query's threshold tau and append the
 //                              rare survivors to the query's candidate list -- the 128 x 256 score tile is never
 //                              written to memory (at 1024 x 10M it would be 41 GB).
+//   warp 10     refiner      : (streaming mode) raises the thresholds WHILE the kernel runs.  Every survivor is also
+//                              counted (fire-and-forget RED) in its query's 256-bin score histogram in L2; the refiner
+//                              of CTA b owns the queries q = b (mod grid), reads their histograms, finds the bin in
+//                              which the count from the top reaches k -- a proof that the k-th best score seen so far
+//                              is at least that bin's lower edge -- and publishes tau = edge - margin.  The epilogue
+//                              threads re-read tau (ld.cg, L2) at every work item.  One launch therefore covers the
+//                              whole corpus: no per-pass launches, compactions or host round trips.
 // The epilogue of tile i overlaps the MMAs of tile i+1 through the two TMEM stages.
 //
 // Replaces, as the *screen*, the distance loop of KnnTopK::execute (exec/operators/knn_topk.rs:185-228);
@@ -34,7 +41,8 @@ constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr uint32_t ACC_STAGES = 2;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t EPI_WARPS = 8;             // two warps per TMEM lane quarter, each takes half the columns
-constexpr uint32_t THREADS = 64 + EPI_WARPS * 32;
+constexpr uint32_t REFINE_WARP = 2 + EPI_WARPS;  // warp 10
+constexpr uint32_t THREADS = 64 + EPI_WARPS * 32 + 32;
 constexpr uint32_t MAX_MBLOCKS = 16;           // queries per launch <= 2048 (the driver splits larger batches)
 constexpr uint32_t SUBCAP = 16;                // private candidate slots per (query, CTA, column half) and pass
 constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + ACC_STAGES * BLOCK_N * 4 + 256 + MAX_MBLOCKS * 256 * 4 + 1024;
@@ -135,12 +143,29 @@ __device__ __noinline__ void append_survivor(Cand* my_sub, uint32_t my_cnt_saddr
   }
 }
 
-template <bool COSINE, bool INT8, bool PASS0>
+// streaming mode: the survivor is also counted in its query's score histogram (no return value: a RED in L2)
+__device__ __noinline__ void append_survivor_h(Cand* my_sub, uint32_t my_cnt_saddr, Cand* my_cand, uint32_t* cnt_q, uint32_t cap,
+                                               const HistParam* hp_q, uint32_t* hist_q, float score, uint32_t row) {
+  append_survivor(my_sub, my_cnt_saddr, my_cand, cnt_q, cap, score, row);
+  const float4 v = __ldg(reinterpret_cast<const float4*>(hp_q));
+  HistParam hp;
+  hp.lo = v.x;
+  hp.inv_w0 = v.y;
+  hp.w0 = v.z;
+  hp.margin = v.w;
+  atomicAdd(hist_q + hist_bin(hp, score), 1u);
+}
+
+// MODE 0: pass 0 -- every score of the pass's tiles goes to a fixed slot of the query's main list (tau = -inf)
+// MODE 1: threshold pass -- survivors of a fixed tau (legacy multi-pass schedule)
+// MODE 2: streaming pass -- tau is re-read at every work item and raised by the refiner warps while the kernel runs
+template <bool COSINE, bool INT8, int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const float* __restrict__ snorm, uint32_t k_blocks, uint32_t n_mblocks, uint32_t nq,
-                 PassDesc pass, const float* __restrict__ tau, Cand* __restrict__ cand,
-                 uint32_t* __restrict__ cand_cnt, uint32_t cap, Cand* __restrict__ sub, uint32_t* __restrict__ sub_cnt) {
+                 PassDesc pass, float* tau, Cand* __restrict__ cand,
+                 uint32_t* __restrict__ cand_cnt, uint32_t cap, Cand* __restrict__ sub, uint32_t* __restrict__ sub_cnt,
+                 uint32_t k, const HistParam* __restrict__ hparam, uint32_t* hist) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -153,7 +178,8 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint64_t* tfull_bar = bars + 2 * STAGES;        // [ACC_STAGES]
   uint64_t* tempty_bar = bars + 2 * STAGES + ACC_STAGES;  // [ACC_STAGES]
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES);
-  uint32_t* s_cnt = s_tmem + 4;  // [n_mblocks][256] private append counters of the epilogue threads
+  uint32_t* s_done = s_tmem + 1;  // epilogue warps that have finished (the refiner's exit condition)
+  uint32_t* s_cnt = s_tmem + 4;   // [n_mblocks][256] private append counters of the epilogue threads
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t n_items = pass.count * n_mblocks;
@@ -170,6 +196,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_init(smem_u32(&tempty_bar[a]), EPI_WARPS);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    *s_done = 0;
   }
   for (uint32_t i = threadIdx.x; i < n_mblocks * 256; i += blockDim.x) s_cnt[i] = 0;
   if (warp == 1) {  // TMEM allocation (whole warp), address lands in shared memory
@@ -228,13 +255,13 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp < REFINE_WARP) {
     // ===================== epilogue (8 warps; thread = query row, warp pair splits the 256 columns) ==========
     const uint32_t wq = warp & 3;                 // TMEM lane quarter this warp may access
     const uint32_t half = (warp - 2) >> 2;        // 0: columns 0..127, 1: columns 128..255
     const uint32_t row_in_tile = wq * 32 + lane;
     const uint32_t et = threadIdx.x - 64;         // 0..255
-    constexpr bool pass0 = PASS0;                 // pass 0: tau = -inf everywhere, positions are deterministic
+    constexpr bool pass0 = MODE == 0;             // pass 0: tau = -inf everywhere, positions are deterministic
     const uint32_t cbase = half * (BLOCK_N / 2);
     uint32_t j = 0;
     // the threshold of the first item; later items prefetch theirs while the current one is processed
@@ -242,7 +269,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     float next_tau = __int_as_float(0x7f800000);
     if (w < n_items) {
       const uint32_t q0 = item_mb(w, n_mblocks) * BLOCK_M + row_in_tile;
-      if (q0 < nq) next_tau = __ldg(tau + q0);
+      if (q0 < nq) next_tau = __ldcg(tau + q0);
     }
     for (; w < n_items; w += gridDim.x, j++) {
       const uint32_t tidx = w / n_mblocks;
@@ -256,7 +283,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         next_tau = __int_as_float(0x7f800000);
         if (wn < n_items) {
           const uint32_t qn = item_mb(wn, n_mblocks) * BLOCK_M + row_in_tile;
-          if (qn < nq) next_tau = __ldg(tau + qn);
+          if (qn < nq) next_tau = __ldcg(tau + qn);  // L2: sees the refiners' updates
         }
       }
       const size_t row0 = (size_t)tile * BLOCK_N;
@@ -315,8 +342,15 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
                 for (int i = 8 * g; i < 8 * g + 8; i++) {
                   if ((int)v[i] >= tau_i) {
-                    append_survivor(my_sub, my_cnt, my_cand, cand_cnt + q, cap, __int2float_rn((int)v[i]),
-                                    (uint32_t)(row0 + cbase + c0 + i));
+                    const uint32_t r = (uint32_t)(row0 + cbase + c0 + i);
+                    const float sn = __ldg(snorm + r);  // invalid rows score 0 in the integer screen: drop them here
+                    if (sn == sn) {
+                      if (MODE == 2)
+                        append_survivor_h(my_sub, my_cnt, my_cand, cand_cnt + q, cap, hparam + q,
+                                          hist + (size_t)q * HIST_BINS, __int2float_rn((int)v[i]), r);
+                      else
+                        append_survivor(my_sub, my_cnt, my_cand, cand_cnt + q, cap, __int2float_rn((int)v[i]), r);
+                    }
                   }
                 }
               }
@@ -354,7 +388,11 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
                 for (int i = 8 * g; i < 8 * g + 8; i++) {
                   if (sc[i] >= my_tau) {
-                    append_survivor(my_sub, my_cnt, my_cand, cand_cnt + q, cap, sc[i], (uint32_t)(row0 + cbase + c0 + i));
+                    if (MODE == 2)
+                      append_survivor_h(my_sub, my_cnt, my_cand, cand_cnt + q, cap, hparam + q,
+                                        hist + (size_t)q * HIST_BINS, sc[i], (uint32_t)(row0 + cbase + c0 + i));
+                    else
+                      append_survivor(my_sub, my_cnt, my_cand, cand_cnt + q, cap, sc[i], (uint32_t)(row0 + cbase + c0 + i));
                   }
                 }
               }
@@ -376,6 +414,71 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const uint32_t cnt = s_cnt[mb * 256 + et];
           sub_cnt[(size_t)qq * n_slots + blockIdx.x * 2 + half] = cnt;
         }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) atomicAdd(s_done, 1u);
+  } else {
+    // ===================== refiner (streaming mode): raise the thresholds of the queries this CTA owns ==========
+    if (MODE == 2) {
+      volatile uint32_t* done = s_done;
+      const uint32_t stride = gridDim.x;
+      uint32_t n_own = nq > blockIdx.x ? (nq - blockIdx.x + stride - 1) / stride : 0;
+      if (n_own > 32) n_own = 32;  // (tiny grids only; the rest keeps its seed threshold)
+      float my_tau = __int_as_float(0xff800000);  // lane j: the threshold last published for owned query j
+      if (lane < n_own) my_tau = __ldcg(tau + blockIdx.x + lane * stride);
+      uint32_t sleep_ns = 256;
+      while (*done < EPI_WARPS) {
+        bool any = false;
+        for (uint32_t j = 0; j < n_own; j++) {
+          const uint32_t q = blockIdx.x + j * stride;
+          const uint4* hq = reinterpret_cast<const uint4*>(hist + (size_t)q * HIST_BINS) + lane * 2;
+          const uint4 ha = __ldcg(hq), hb = __ldcg(hq + 1);  // bins lane*8 .. lane*8+7
+          const uint32_t c[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+          uint32_t sum = 0;
+#pragma unroll
+          for (int i = 0; i < 8; i++) sum += c[i];
+          uint32_t incl = sum;  // suffix sum over lanes: higher lanes hold higher bins
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_down_sync(0xffffffffu, incl, o);
+            if (lane + o < 32) incl += t;
+          }
+          const uint32_t above = incl - sum;
+          const bool mine = above < k && k <= incl;  // the count from the top reaches k inside this lane's bins
+          const uint32_t who = __ballot_sync(0xffffffffu, mine);
+          if (who == 0) continue;  // fewer than k survivors counted so far
+          uint32_t bstar = 0;
+          if (mine) {
+            uint32_t acc = above;
+#pragma unroll
+            for (int i = 7; i >= 0; i--) {
+              acc += c[i];
+              if (acc >= k) {
+                bstar = lane * 8 + i;
+                break;
+              }
+            }
+          }
+          bstar = __shfl_sync(0xffffffffu, bstar, __ffs(who) - 1);
+          const float4 hv = __ldg(reinterpret_cast<const float4*>(hparam + q));
+          HistParam hp;
+          hp.lo = hv.x;
+          hp.inv_w0 = hv.y;
+          hp.w0 = hv.z;
+          hp.margin = hv.w;
+          // >= k rows with score >= edge(bstar) exist (2 % of a bin + 2e-6 relative absorb the rounding of hist_bin)
+          const double e0 = hist_edge(hp, bstar), e1 = hist_edge(hp, bstar + 1);
+          const float tn = __double2float_rd(e0 - (double)hp.margin - 0.02 * (e1 - e0) - 2e-6 * fabs(e0));
+          const float told = __shfl_sync(0xffffffffu, my_tau, j);
+          if (tn > told) {
+            if (lane == j) my_tau = tn;
+            if (lane == 0) __stcg(tau + q, tn);
+            any = true;
+          }
+        }
+        sleep_ns = any ? 256u : (sleep_ns < 4096u ? sleep_ns * 2 : 8192u);
+        __nanosleep(sleep_ns);
       }
     }
   }
@@ -427,7 +530,17 @@ static sdb_status make_map(Ctx* ctx, CUtensorMap* map, const void* base, uint64_
 
 bool screen_tc_available() { return true; }
 
-sdb_status screen_tc_pass(Corpus* c, uint32_t nq, const PassDesc& p, bool int8, cudaStream_t st) {
+sdb_status screen_tc_init_device() {
+#define SET_SMEM(COS, I8, MODE) \
+  SDB_CUDA(cudaFuncSetAttribute(tc::screen_tc_kernel<COS, I8, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES))
+  SET_SMEM(true, false, 0); SET_SMEM(true, false, 1); SET_SMEM(true, false, 2);
+  SET_SMEM(false, false, 0); SET_SMEM(false, false, 1); SET_SMEM(false, false, 2);
+  SET_SMEM(true, true, 0); SET_SMEM(true, true, 1); SET_SMEM(true, true, 2);
+#undef SET_SMEM
+  return SDB_OK;
+}
+
+sdb_status screen_tc_pass(Corpus* c, uint32_t nq, uint32_t k, const PassDesc& p, bool int8, int mode, cudaStream_t st) {
   if (p.count == 0) return SDB_OK;
   Ctx* ctx = c->ctx;
   if (int8 ? (!c->d_i8 || c->metric != SDB_COSINE) : !c->d_bf16) {
@@ -435,17 +548,6 @@ sdb_status screen_tc_pass(Corpus* c, uint32_t nq, const PassDesc& p, bool int8, 
     return SDB_EUNSUPPORTED;
   }
   const uint64_t n_pad = (c->n + TILE_ROWS - 1) / TILE_ROWS * TILE_ROWS;
-  static bool attr_set = false;
-  if (!attr_set) {
-#define SET_SMEM(COS, I8)                                                                                                              \
-  SDB_CUDA(cudaFuncSetAttribute(tc::screen_tc_kernel<COS, I8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES)); \
-  SDB_CUDA(cudaFuncSetAttribute(tc::screen_tc_kernel<COS, I8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES))
-    SET_SMEM(true, false);
-    SET_SMEM(false, false);
-    SET_SMEM(true, true);
-#undef SET_SMEM
-    attr_set = true;
-  }
   CUtensorMap map_b;
   if (int8) SDB_TRY(make_map(ctx, &map_b, c->d_i8, n_pad, c->dim_pad8, tc::BLOCK_N, true, true));
   else SDB_TRY(make_map(ctx, &map_b, c->d_bf16, n_pad, c->dim_pad, tc::BLOCK_N, true));
@@ -467,27 +569,30 @@ sdb_status screen_tc_pass(Corpus* c, uint32_t nq, const PassDesc& p, bool int8, 
     CUtensorMap map_a;
     if (int8) SDB_TRY(make_map(ctx, &map_a, c->d_q8 + (size_t)q0 * c->dim_pad8, nq_pad, c->dim_pad8, tc::BLOCK_M, false, true));
     else SDB_TRY(make_map(ctx, &map_a, c->d_qbf16 + (size_t)q0 * c->dim_pad, nq_pad, c->dim_pad, tc::BLOCK_M, false));
-    const float* tau = c->d_tau + q0;
+    float* tau = c->d_tau + q0;
     Cand* cand = c->d_cand + (size_t)q0 * c->sc_cap;
     uint32_t* ccnt = c->d_cand_cnt + q0;
     Cand* sub = c->d_sub + (size_t)q0 * slots * tc::SUBCAP;
     uint32_t* scnt = c->d_sub_cnt + (size_t)q0 * slots;
-#define LAUNCH_TC(COS, I8)                                                                                      \
-  do {                                                                                                         \
-    if (p.excl == 0)                                                                                           \
-      tc::screen_tc_kernel<COS, I8, true><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(                          \
-          map_a, map_b, c->d_snorm, k_blocks, n_mblocks, nqc, p, tau, cand, ccnt, c->sc_cap, sub, scnt);        \
-    else                                                                                                       \
-      tc::screen_tc_kernel<COS, I8, false><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(                         \
-          map_a, map_b, c->d_snorm, k_blocks, n_mblocks, nqc, p, tau, cand, ccnt, c->sc_cap, sub, scnt);        \
+    const HistParam* hp = c->d_hparam + q0;
+    uint32_t* hist = c->d_hist + (size_t)q0 * HIST_BINS;
+#define LAUNCH_TC1(COS, I8, MODE)                                                                              \
+  tc::screen_tc_kernel<COS, I8, MODE><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(                              \
+      map_a, map_b, c->d_snorm, k_blocks, n_mblocks, nqc, p, tau, cand, ccnt, c->sc_cap, sub, scnt, k, hp, hist)
+#define LAUNCH_TC(COS, I8)                   \
+  do {                                       \
+    if (mode == 0) LAUNCH_TC1(COS, I8, 0);   \
+    else if (mode == 1) LAUNCH_TC1(COS, I8, 1); \
+    else LAUNCH_TC1(COS, I8, 2);             \
   } while (0)
     if (int8) LAUNCH_TC(true, true);
     else if (c->metric == SDB_COSINE) LAUNCH_TC(true, false);
     else LAUNCH_TC(false, false);
 #undef LAUNCH_TC
+#undef LAUNCH_TC1
     count_launch(ctx);
   }
-  if (p.excl == 0) {
+  if (mode == 0) {
     SDB_TRY(cand_set_count(c, nq, p.count * TILE_ROWS, st));  // pass 0 wrote fixed slots of the main lists
     c->last_slots = 0;                                         // ... and no private sub-lists
   }

@@ -13,10 +13,35 @@ def _ptr(a):
 class Context:
     """sdb_ctx: one CUDA device."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, _handle=None):
         self.h = C.c_void_p()
-        L.check(L.lib().sdb_ctx_create(device, C.byref(self.h)))
+        if _handle is not None:
+            self.h = C.c_void_p(_handle)
+        else:
+            L.check(L.lib().sdb_ctx_create(device, C.byref(self.h)))
         self.device = device
+
+    @staticmethod
+    def create_multi(devices):
+        """one process, several GPUs: contexts sharing one NCCL communicator (sdb_ctx_create_multi)"""
+        devs = (C.c_int * len(devices))(*devices)
+        out = (C.c_void_p * len(devices))()
+        L.check(L.lib().sdb_ctx_create_multi(devs, len(devices), out))
+        return [Context(d, _handle=out[i]) for i, d in enumerate(devices)]
+
+    @staticmethod
+    def comm_unique_id():
+        """128 bytes rank 0 hands to the other ranks (any out-of-band channel) before comm_init_rank"""
+        buf = (C.c_uint8 * L.COMM_ID_BYTES)()
+        L.check(L.lib().sdb_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init_rank(self, nranks, rank, unique_id):
+        buf = (C.c_uint8 * L.COMM_ID_BYTES).from_buffer_copy(unique_id)
+        L.check(L.lib().sdb_comm_init_rank(self.h, int(nranks), int(rank), buf))
+
+    def comm_size(self):
+        return int(L.lib().sdb_comm_size(self.h))
 
     def stream(self):
         """raw cudaStream_t (int) all kernels of this context run on"""
@@ -62,6 +87,12 @@ class VectorColumn:
     def append_synthetic(self, seed, first_row, n):
         L.check(L.lib().sdb_corpus_append_synthetic(self.h, int(seed), int(first_row), int(n)))
 
+    def read_rows(self, first_row, n):
+        """rows [first_row, first_row+n) of the device-resident master copy as a numpy array"""
+        out = np.empty((int(n), self.dim), np.float32 if self.dtype == "F32" else np.float64)
+        L.check(L.lib().sdb_corpus_read_rows(self.h, int(first_row), int(n), _ptr(out)))
+        return out
+
     def set_skip(self, skip):
         if skip is None:
             L.check(L.lib().sdb_corpus_set_skip(self.h, None, 0))
@@ -74,6 +105,10 @@ class VectorColumn:
 
     def set_screen(self, name):
         L.check(L.lib().sdb_corpus_set_screen(self.h, L.SCREEN[name.upper()]))
+
+    def set_schedule(self, streaming):
+        """True (default): streaming tensor-core screen with in-kernel threshold refinement; False: multi-pass"""
+        L.check(L.lib().sdb_corpus_set_schedule(self.h, int(bool(streaming))))
 
     def set_exact(self, exact):
         """False = opt-in approximate mode (no proof, no exact fallback)"""
@@ -101,6 +136,44 @@ class VectorColumn:
         L.check(L.lib().sdb_knn_bruteforce_device(self.h, C.c_void_p(d_queries), int(nq), int(k), int(row_base),
                                                   C.c_void_p(d_out_rows), C.c_void_p(d_out_dist),
                                                   C.c_void_p(d_out_count)))
+
+    # ---- asynchronous batches (device pointers; buffers must stay valid until wait) ----
+    def submit_device(self, d_queries, nq, k, row_base, d_out_rows, d_out_dist, d_out_count):
+        t = C.c_uint32()
+        L.check(L.lib().sdb_knn_submit_device(self.h, C.c_void_p(d_queries), int(nq), int(k), int(row_base),
+                                              C.c_void_p(d_out_rows), C.c_void_p(d_out_dist), C.c_void_p(d_out_count),
+                                              C.byref(t)))
+        return t.value
+
+    def submit_host(self, h_queries, nq, k, h_out_rows, h_out_dist, h_out_count):
+        """raw host pointers (ints), pinned for overlap"""
+        t = C.c_uint32()
+        L.check(L.lib().sdb_knn_submit(self.h, C.c_void_p(h_queries), int(nq), int(k), C.c_void_p(h_out_rows),
+                                       C.c_void_p(h_out_dist), C.c_void_p(h_out_count), C.byref(t)))
+        return t.value
+
+    def wait(self, ticket):
+        L.check(L.lib().sdb_knn_wait(self.h, int(ticket)))
+
+    # ---- row-sharded search (collective over the context's communicator) ----
+    def set_row_base(self, row_base):
+        L.check(L.lib().sdb_corpus_set_row_base(self.h, int(row_base)))
+
+    def sharded_submit_device(self, d_queries, nq, k, d_out_rows, d_out_dist, d_out_count):
+        t = C.c_uint32()
+        L.check(L.lib().sdb_knn_sharded_submit_device(self.h, C.c_void_p(d_queries), int(nq), int(k),
+                                                      C.c_void_p(d_out_rows), C.c_void_p(d_out_dist),
+                                                      C.c_void_p(d_out_count), C.byref(t)))
+        return t.value
+
+    def sharded_submit_host(self, h_queries, nq, k, h_out_rows, h_out_dist, h_out_count):
+        t = C.c_uint32()
+        L.check(L.lib().sdb_knn_sharded_submit(self.h, C.c_void_p(h_queries), int(nq), int(k), C.c_void_p(h_out_rows),
+                                               C.c_void_p(h_out_dist), C.c_void_p(h_out_count), C.byref(t)))
+        return t.value
+
+    def sharded_wait(self, ticket):
+        L.check(L.lib().sdb_knn_sharded_wait(self.h, int(ticket)))
 
     def project(self, fn, query=None):
         """One value per row of `vector::<fn>(row, query)` in the reference's f64 arithmetic (fnc/vector.rs): fn is a
@@ -148,3 +221,15 @@ def shard_block_layout(nq, k):
     off_cnt = 2 * nq * k * 8
     size = (off_cnt + nq * 4 + 15) // 16 * 16
     return off_rows, off_dist, off_cnt, size
+
+
+def knn_sharded_multi(shards, queries, k):
+    """one process, N GPUs: shards[i] is the VectorColumn on the i-th context of Context.create_multi"""
+    q = np.ascontiguousarray(queries, np.float64)
+    nq = q.shape[0]
+    rows = np.zeros((nq, max(k, 1)), np.uint64)
+    dist = np.zeros((nq, max(k, 1)), np.float64)
+    cnt = np.zeros(nq, np.uint32)
+    hs = (C.c_void_p * len(shards))(*[s.h for s in shards])
+    L.check(L.lib().sdb_knn_sharded_multi(hs, len(shards), _ptr(q), nq, int(k), _ptr(rows), _ptr(dist), _ptr(cnt)))
+    return rows[:, :k], dist[:, :k], cnt
