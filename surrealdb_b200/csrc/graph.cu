@@ -19,6 +19,7 @@ struct Graph {
   uint64_t n_rows = 0, n_edges = 0;
   uint64_t* d_row_ptr = nullptr;
   uint32_t* d_col_idx = nullptr;
+  bool targets_in_rows = true;  // every col_idx < n_rows (required by +collect, which indexes per-row state by target)
   std::mutex mu;
 };
 
@@ -225,7 +226,9 @@ __global__ void collect_mark_kernel(const uint32_t* __restrict__ lvl, uint64_t n
   const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   const uint32_t v = lvl[p];
-  if (!seen[v]) atomicMin(first_pos + v, (uint32_t)p);
+  // hubs occur millions of times per level: only positions that could still lower the minimum issue the atomic
+  // (a plain load first -- positions are handed out in increasing order, so later duplicates almost always skip it)
+  if (!seen[v] && __ldcg(first_pos + v) > (uint32_t)p) atomicMin(first_pos + v, (uint32_t)p);
 }
 __global__ void collect_flag_kernel(const uint32_t* __restrict__ lvl, uint64_t n, const uint8_t* __restrict__ seen,
                                     const uint32_t* __restrict__ first_pos, uint64_t* __restrict__ keep) {
@@ -281,6 +284,16 @@ sdb_status sdb_graph_load_csr(sdb_ctx* ctx, uint64_t n_rows, const uint64_t* row
   if (n_edges)
     SDB_CUDA(cudaMemcpyAsync(g->d_col_idx, col_idx, sizeof(uint32_t) * n_edges, cudaMemcpyHostToDevice, ctx->stream));
   SDB_CUDA(cudaStreamSynchronize(ctx->stream));
+  {  // range check on the device copy: row_ptr consistent with the edge count; do targets stay inside the rows?
+    unsigned long long bad[2] = {0, 0};
+    const sdb_status rc = csr_check(ctx, g->d_row_ptr, g->d_col_idx, n_rows, n_edges, n_rows, bad, "sdb_graph_load_csr", ctx->stream);
+    if (rc != SDB_OK || bad[0]) {
+      if (rc == SDB_OK) set_error("sdb_graph_load_csr: malformed row_ptr (%llu violations)", bad[0]);
+      sdb_graph_destroy(g);
+      return rc != SDB_OK ? rc : SDB_EINVAL;
+    }
+    g->targets_in_rows = bad[1] == 0;  // targets of another table may exceed this table's rows: fine for plain hops
+  }
   *out = g;
   return SDB_OK;
 }
@@ -405,82 +418,129 @@ sdb_status sdb_graph_collect(sdb_graph* g, const uint32_t* start, uint64_t n_sta
   std::lock_guard<std::mutex> guard(ctx->mu);
   SDB_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
+  if (!g->targets_in_rows) {
+    set_error("graph collect: this CSR has targets outside its own rows (an edge table into another node table); "
+              "+collect needs source and target ids in one id space");
+    return SDB_EINVAL;
+  }
   for (uint64_t i = 0; i < n_start; i++)
     if (start[i] >= g->n_rows) {
       set_error("graph collect: start id out of range");
       return SDB_EINVAL;
     }
-  std::vector<uint32_t> result;
+  // stream-ordered temporaries are released on EVERY return path
+  struct Temps {
+    cudaStream_t st;
+    std::vector<void*> ptrs;
+    ~Temps() {
+      for (void* p : ptrs)
+        if (p) cudaFreeAsync(p, st);
+      cudaStreamSynchronize(st);
+    }
+    void drop(void* p) {
+      for (auto& q : ptrs)
+        if (q == p) q = nullptr;
+      if (p) cudaFreeAsync(p, st);
+    }
+  } tmp{st, {}};
+  auto dalloc = [&](void** p, size_t bytes) -> sdb_status {
+    SDB_CUDA(cudaMallocAsync(p, bytes ? bytes : 1, st));
+    tmp.ptrs.push_back(*p);
+    return SDB_OK;
+  };
+  const uint64_t nr = g->n_rows ? g->n_rows : 1;
   uint8_t* d_seen = nullptr;
-  uint32_t* d_first = nullptr;
-  SDB_CUDA(cudaMallocAsync(&d_seen, g->n_rows ? g->n_rows : 1, st));
-  SDB_CUDA(cudaMallocAsync(&d_first, sizeof(uint32_t) * (g->n_rows ? g->n_rows : 1), st));
-  SDB_CUDA(cudaMemsetAsync(d_seen, 0, g->n_rows ? g->n_rows : 1, st));
-  SDB_CUDA(cudaMemsetAsync(d_first, 0xFF, sizeof(uint32_t) * (g->n_rows ? g->n_rows : 1), st));
-  uint32_t* d_f = nullptr;
+  uint32_t *d_first = nullptr, *d_f = nullptr, *d_res = nullptr;
+  SDB_TRY(dalloc((void**)&d_seen, nr));
+  SDB_TRY(dalloc((void**)&d_first, sizeof(uint32_t) * nr));
+  // every node is emitted at most once (+ the start values): the result is accumulated on the device
+  const uint64_t res_cap = g->n_rows + n_start;
+  SDB_TRY(dalloc((void**)&d_res, sizeof(uint32_t) * res_cap));
+  uint64_t n_res = 0;
+  SDB_CUDA(cudaMemsetAsync(d_seen, 0, nr, st));
+  SDB_CUDA(cudaMemsetAsync(d_first, 0xFF, sizeof(uint32_t) * nr, st));
   uint64_t n_f = n_start;
   if (n_f) {
-    SDB_CUDA(cudaMallocAsync(&d_f, sizeof(uint32_t) * n_f, st));
+    SDB_TRY(dalloc((void**)&d_f, sizeof(uint32_t) * n_f));
     SDB_CUDA(cudaMemcpyAsync(d_f, start, sizeof(uint32_t) * n_f, cudaMemcpyHostToDevice, st));
   }
-  if (inclusive) {  // collect.rs:83-86: the start value is emitted and marked seen only when inclusive
+  if (inclusive && n_start) {  // collect.rs:83-86: the start value is emitted and marked seen only when inclusive
     const uint8_t one = 1;
-    for (uint64_t i = 0; i < n_start; i++) {
-      result.push_back(start[i]);
+    for (uint64_t i = 0; i < n_start; i++)
       SDB_CUDA(cudaMemcpyAsync(d_seen + start[i], &one, 1, cudaMemcpyHostToDevice, st));
-    }
-    SDB_CUDA(cudaStreamSynchronize(st));
+    SDB_CUDA(cudaMemcpyAsync(d_res, d_f, sizeof(uint32_t) * n_start, cudaMemcpyDeviceToDevice, st));
+    n_res = n_start;
+    SDB_CUDA(cudaStreamSynchronize(st));  // `one` lives on this stack frame
   }
   uint32_t depth = 0;
-  sdb_status rc = SDB_OK;
   while (n_f && (max_depth == 0 || depth < max_depth)) {
     uint32_t* d_lvl = nullptr;
     uint64_t n_lvl = 0;
-    rc = hop_device(g, d_f, n_f, 0, &d_lvl, &n_lvl, st);
-    cudaFreeAsync(d_f, st);
+    SDB_TRY(hop_device(g, d_f, n_f, 0, &d_lvl, &n_lvl, st));
+    tmp.ptrs.push_back(d_lvl);
+    tmp.drop(d_f);
     d_f = nullptr;
     n_f = 0;
-    if (rc != SDB_OK) break;
     if (n_lvl) {
       uint64_t* d_pos = nullptr;
-      SDB_CUDA(cudaMallocAsync(&d_pos, sizeof(uint64_t) * (n_lvl + 2), st));
+      SDB_TRY(dalloc((void**)&d_pos, sizeof(uint64_t) * (n_lvl + 2)));
       const unsigned grid = (unsigned)((n_lvl + 255) / 256);
       collect_mark_kernel<<<grid, 256, 0, st>>>(d_lvl, n_lvl, d_seen, d_first);
       collect_flag_kernel<<<grid, 256, 0, st>>>(d_lvl, n_lvl, d_seen, d_first, d_pos);
       count_launch(ctx, 2);
-      rc = exclusive_scan(ctx, d_pos, d_pos, n_lvl, d_pos + n_lvl, st);
-      if (rc != SDB_OK) break;
+      SDB_TRY(exclusive_scan(ctx, d_pos, d_pos, n_lvl, d_pos + n_lvl, st));
       uint64_t n_next = 0;
       SDB_CUDA(cudaMemcpyAsync(&n_next, d_pos + n_lvl, 8, cudaMemcpyDeviceToHost, st));
       SDB_CUDA(cudaStreamSynchronize(st));
       if (n_next) {
-        SDB_CUDA(cudaMallocAsync(&d_f, sizeof(uint32_t) * n_next, st));
+        SDB_TRY(dalloc((void**)&d_f, sizeof(uint32_t) * n_next));
         collect_compact_kernel<<<grid, 256, 0, st>>>(d_lvl, n_lvl, d_pos, d_seen, d_first, d_f);
         count_launch(ctx);
         n_f = n_next;
         if (depth + 1 >= min_depth) {  // nodes below min_depth are traversed but not emitted
-          const size_t o = result.size();
-          result.resize(o + n_next);
-          SDB_CUDA(cudaMemcpyAsync(result.data() + o, d_f, sizeof(uint32_t) * n_next, cudaMemcpyDeviceToHost, st));
-          SDB_CUDA(cudaStreamSynchronize(st));
+          if (n_res + n_next > res_cap) {
+            set_error("graph collect: internal result overflow");
+            return SDB_EOVERFLOW;
+          }
+          SDB_CUDA(cudaMemcpyAsync(d_res + n_res, d_f, sizeof(uint32_t) * n_next, cudaMemcpyDeviceToDevice, st));
+          n_res += n_next;
         }
       }
-      SDB_CUDA(cudaFreeAsync(d_pos, st));
-      SDB_CUDA(cudaFreeAsync(d_lvl, st));
+      tmp.drop(d_pos);
     }
+    tmp.drop(d_lvl);
     depth++;
   }
-  if (d_f) cudaFreeAsync(d_f, st);
-  cudaFreeAsync(d_seen, st);
-  cudaFreeAsync(d_first, st);
-  SDB_CUDA(cudaStreamSynchronize(st));
-  if (rc != SDB_OK) return rc;
-  if (!result.empty()) {
-    uint32_t* h_out = (uint32_t*)malloc(sizeof(uint32_t) * result.size());
+  SDB_CUDA(cudaGetLastError());
+  if (n_res) {
+    uint32_t* h_out = (uint32_t*)malloc(sizeof(uint32_t) * n_res);
     if (!h_out) return SDB_ENOMEM;
-    memcpy(h_out, result.data(), sizeof(uint32_t) * result.size());
+    // large results go through the context's pinned staging buffer (pageable D2H is several times slower)
+    const size_t bytes = sizeof(uint32_t) * n_res;
+    cudaError_t e = cudaSuccess;
+    if (bytes >= (1u << 20)) {
+      if (ctx->h_stage_bytes < bytes) {
+        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+        ctx->h_stage = nullptr;
+        ctx->h_stage_bytes = 0;
+        if (cudaHostAlloc(&ctx->h_stage, bytes, cudaHostAllocDefault) == cudaSuccess) ctx->h_stage_bytes = bytes;
+      }
+    }
+    if (ctx->h_stage_bytes >= bytes && bytes >= (1u << 20)) {
+      e = cudaMemcpyAsync(ctx->h_stage, d_res, bytes, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e == cudaSuccess) memcpy(h_out, ctx->h_stage, bytes);
+    } else {
+      e = cudaMemcpyAsync(h_out, d_res, bytes, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (e != cudaSuccess) {
+      free(h_out);
+      set_error("graph collect: result copy failed: %s", cudaGetErrorString(e));
+      return SDB_ECUDA;
+    }
     *out_ids = h_out;
-    *out_n = result.size();
+    *out_n = n_res;
   }
   return SDB_OK;
 }

@@ -15,6 +15,8 @@
 // shrinks), so they are dropped from the candidate array, which bounds it to 2*ef entries.
 //
 // Algorithmic bytes per query = visited * (4*dim + 4) + expanded * 4*deg, both counters are returned.
+#include <algorithm>
+
 #include "internal.cuh"
 #include "rowwalk.cuh"
 
@@ -481,6 +483,77 @@ __global__ void __launch_bounds__(128) hnsw_select_kernel(const float* __restric
   if (lane == 0) out_cnt[i] = acc;
 }
 
+// ---- load-time validation: adjacency supplied across the ABI is used for device indexing, so it is
+// range-checked once here instead of trusted.  bad[0] counts row_ptr violations (non-monotone / beyond the edge count),
+// bad[1] counts neighbour ids >= n_elems.
+__global__ void csr_validate_kernel(const uint64_t* __restrict__ rp, const uint32_t* __restrict__ ci, uint64_t n_rows,
+                                    uint64_t n_edges, uint64_t id_limit, unsigned long long* __restrict__ bad) {
+  const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t t0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint64_t r = t0; r < n_rows; r += step)
+    if (rp[r] > rp[r + 1] || rp[r + 1] > n_edges) atomicAdd(bad, 1ull);
+  if (t0 == 0 && n_rows && rp[0] != 0) atomicAdd(bad, 1ull);
+  for (uint64_t e = t0; e < n_edges; e += step)
+    if ((uint64_t)ci[e] >= id_limit) atomicAdd(bad + 1, 1ull);
+}
+
+sdb_status csr_check(Ctx* ctx, const uint64_t* d_rp, const uint32_t* d_ci, uint64_t n_rows, uint64_t n_edges,
+                     uint64_t id_limit, unsigned long long counts[2], const char* what, cudaStream_t st) {
+  unsigned long long* d_bad = nullptr;
+  SDB_CUDA(cudaMallocAsync(&d_bad, 16, st));
+  cudaMemsetAsync(d_bad, 0, 16, st);
+  const uint64_t work = n_rows > n_edges ? n_rows : n_edges;
+  const unsigned grid = (unsigned)std::min<uint64_t>((work + 255) / 256 + 1, (uint64_t)ctx->sm_count * 16);
+  csr_validate_kernel<<<grid, 256, 0, st>>>(d_rp, d_ci, n_rows, n_edges, id_limit, d_bad);
+  count_launch(ctx);
+  unsigned long long h_bad[2] = {0, 0};
+  cudaError_t e = cudaMemcpyAsync(h_bad, d_bad, 16, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFreeAsync(d_bad, st);
+  if (e != cudaSuccess) {
+    set_error("%s: validation failed to run: %s", what, cudaGetErrorString(e));
+    return SDB_ECUDA;
+  }
+  counts[0] = h_bad[0];
+  counts[1] = h_bad[1];
+  return SDB_OK;
+}
+sdb_status csr_validate(Ctx* ctx, const uint64_t* d_rp, const uint32_t* d_ci, uint64_t n_rows, uint64_t n_edges,
+                        uint64_t id_limit, const char* what, cudaStream_t st) {
+  unsigned long long h_bad[2] = {0, 0};
+  SDB_TRY(csr_check(ctx, d_rp, d_ci, n_rows, n_edges, id_limit, h_bad, what, st));
+  if (h_bad[0] || h_bad[1]) {
+    set_error("%s: malformed CSR (%llu row_ptr violations, %llu neighbour ids out of range)", what, h_bad[0], h_bad[1]);
+    return SDB_EINVAL;
+  }
+  return SDB_OK;
+}
+
+// ---- edges to elements without a vector: the reference marks such a neighbour visited and computes nothing
+// (elements.get_vector -> None, hnsw/layer.rs:204), which is equivalent to the edge not being there.  Staged loads
+// therefore drop them from the device CSR: count, scan, fill.
+__global__ void csr_present_degree_kernel(const uint64_t* __restrict__ rp, const uint32_t* __restrict__ ci,
+                                          const uint8_t* __restrict__ present, uint64_t n_rows,
+                                          uint64_t* __restrict__ deg) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > n_rows) return;
+  uint64_t d = 0;
+  if (r < n_rows && present[r])  // an absent element is never expanded either
+    for (uint64_t e = rp[r]; e < rp[r + 1]; e++) d += present[ci[e]] ? 1 : 0;
+  deg[r] = d;  // deg[n_rows] = 0: the scan's total
+}
+__global__ void csr_present_fill_kernel(const uint64_t* __restrict__ rp, const uint32_t* __restrict__ ci,
+                                        const uint8_t* __restrict__ present, uint64_t n_rows,
+                                        const uint64_t* __restrict__ rp2, uint32_t* __restrict__ ci2) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows || !present[r]) return;
+  uint64_t o = rp2[r];
+  for (uint64_t e = rp[r]; e < rp[r + 1]; e++) {
+    const uint32_t v = ci[e];
+    if (present[v]) ci2[o++] = v;  // stored order kept
+  }
+}
+
 }  // namespace sdb
 
 struct sdb_hnsw : sdb::Hnsw {};
@@ -538,6 +611,7 @@ sdb_status sdb_hnsw_load(sdb_ctx* ctx, uint32_t dim, sdb_metric metric, uint64_t
     return SDB_EUNSUPPORTED;
   }
   *out = nullptr;
+  std::lock_guard<std::mutex> guard(ctx->mu);
   SDB_CUDA(cudaSetDevice(ctx->device));
   sdb_hnsw* h = new sdb_hnsw();
   h->ctx = ctx;
@@ -566,6 +640,11 @@ sdb_status sdb_hnsw_load(sdb_ctx* ctx, uint32_t dim, sdb_metric metric, uint64_t
     h->ci.push_back(dci);
     SDB_CUDA(cudaMemcpyAsync(drp, row_ptr[l], sizeof(uint64_t) * (n_elems + 1), cudaMemcpyHostToDevice, st));
     if (e) SDB_CUDA(cudaMemcpyAsync(dci, col_idx[l], sizeof(uint32_t) * e, cudaMemcpyHostToDevice, st));
+    const sdb_status vrc = csr_validate(ctx, drp, dci, n_elems, e, n_elems, "sdb_hnsw_load", st);
+    if (vrc != SDB_OK) {
+      sdb_hnsw_destroy(h);
+      return vrc;
+    }
   }
   return hnsw_finish(h, out);
 }
@@ -583,6 +662,19 @@ sdb_status sdb_hnsw_load_staged(sdb_ctx* ctx, uint32_t dim, sdb_metric metric, u
     return SDB_EUNSUPPORTED;
   }
   *out = nullptr;
+  // The walk kernels implement the reference's typed metrics for VectorType::F32 only (idx/trees/vector.rs:243-289
+  // computes F64 / I64 / I32 / I16 vectors in their own arithmetic).  A value of another SerializedVector variant
+  // would load -- the decoder converts it -- but be searched with the wrong arithmetic, so the load refuses it instead
+  // of reporting success.  Header = revision varint (1) + variant varint: one byte each.
+  for (uint64_t v = 0; v < n_vec; v++) {
+    const uint64_t a = vec_off[v], b = vec_off[v + 1];
+    if (b >= a + 2 && vec_blob[a] == 1 && vec_blob[a + 1] != 1 && vec_blob[a + 1] <= 4) {
+      static const char* names[] = {"F64", "F32", "I64", "I32", "I16"};
+      set_error("sdb_hnsw_load_staged: He value %llu holds a %s vector; the GPU walk implements the F32 typed metrics only "
+                "(the index keeps the reference's CPU path)", (unsigned long long)v, names[vec_blob[a + 1]]);
+      return SDB_EUNSUPPORTED;
+    }
+  }
   std::lock_guard<std::mutex> guard(ctx->mu);
   SDB_CUDA(cudaSetDevice(ctx->device));
   sdb_hnsw* h = new sdb_hnsw();
@@ -596,6 +688,11 @@ sdb_status sdb_hnsw_load_staged(sdb_ctx* ctx, uint32_t dim, sdb_metric metric, u
   const uint64_t nn = n_elems ? n_elems : 1;
   uint64_t bad_total = 0, bad = 0;
   sdb_status rc = SDB_OK;
+  uint8_t* d_present = nullptr;
+  if (cudaMalloc(&d_present, nn) != cudaSuccess || cudaMemsetAsync(d_present, 0, nn, st) != cudaSuccess) {
+    set_error("hnsw load: present-mask allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    rc = SDB_ENOMEM;
+  }
   if (cudaMalloc(&h->d_vec, sizeof(float) * nn * dim) != cudaSuccess ||
       cudaMalloc(&h->d_sumsq, sizeof(float) * nn) != cudaSuccess) {
     set_error("hnsw load: vector allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -604,8 +701,9 @@ sdb_status sdb_hnsw_load_staged(sdb_ctx* ctx, uint32_t dim, sdb_metric metric, u
   // elements without an He value keep all-zero vectors; they are unreachable unless an Hn value names them
   if (rc == SDB_OK && cudaMemsetAsync(h->d_vec, 0, sizeof(float) * nn * dim, st) != cudaSuccess) rc = SDB_ECUDA;
   if (rc == SDB_OK)
-    rc = stage_decode_vectors(ctx, vec_blob, vec_off, vec_ids, n_vec, dim, SDB_F32, n_elems, h->d_vec, nullptr, &bad, st);
+    rc = stage_decode_vectors(ctx, vec_blob, vec_off, vec_ids, n_vec, dim, SDB_F32, n_elems, h->d_vec, d_present, &bad, st);
   bad_total += bad;
+  uint64_t n_dropped = 0;
   for (uint32_t l = 0; l < n_layers && rc == SDB_OK; l++) {
     uint64_t* drp = nullptr;
     uint32_t* dci = nullptr;
@@ -613,12 +711,54 @@ sdb_status sdb_hnsw_load_staged(sdb_ctx* ctx, uint32_t dim, sdb_metric metric, u
     bad = 0;
     rc = stage_decode_nodes(ctx, node_blob[l], node_off[l], node_ids[l], n_nodes[l], n_elems, &drp, &dci, &ne, &bad, st);
     if (rc == SDB_OK) {
-      h->rp.push_back(drp);
-      h->ci.push_back(dci);
       bad_total += bad;
+      // drop edges from / to elements that have no He value ("edge to an unknown element")
+      uint64_t *rp2 = nullptr, *d_tot = nullptr;
+      uint32_t* ci2 = nullptr;
+      uint64_t kept = 0;
+      const unsigned g1 = (unsigned)((n_elems + 1 + 255) / 256);
+      if (cudaMalloc(&rp2, 8 * (n_elems + 1)) != cudaSuccess || cudaMalloc(&d_tot, 8) != cudaSuccess) rc = SDB_ENOMEM;
+      if (rc == SDB_OK) {
+        csr_present_degree_kernel<<<g1, 256, 0, st>>>(drp, dci, d_present, n_elems, rp2);
+        count_launch(ctx);
+        rc = exclusive_scan(ctx, rp2, rp2, n_elems + 1, d_tot, st);
+      }
+      if (rc == SDB_OK && (cudaMemcpyAsync(&kept, d_tot, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                           cudaStreamSynchronize(st) != cudaSuccess))
+        rc = SDB_ECUDA;
+      if (rc == SDB_OK && cudaMalloc(&ci2, 4 * (kept ? kept : 1)) != cudaSuccess) rc = SDB_ENOMEM;
+      if (rc == SDB_OK && n_elems) {
+        csr_present_fill_kernel<<<g1, 256, 0, st>>>(drp, dci, d_present, n_elems, rp2, ci2);
+        count_launch(ctx);
+        if (cudaStreamSynchronize(st) != cudaSuccess) rc = SDB_ECUDA;
+      }
+      cudaFree(d_tot);
+      if (rc == SDB_OK) {
+        n_dropped += ne - kept;
+        cudaFree(drp);
+        cudaFree(dci);
+        h->rp.push_back(rp2);
+        h->ci.push_back(ci2);
+      } else {
+        if (rc == SDB_ENOMEM) set_error("hnsw load: CSR filter allocation failed");
+        cudaFree(rp2);
+        cudaFree(ci2);
+        cudaFree(drp);
+        cudaFree(dci);
+      }
     }
   }
+  bad_total += n_dropped;
   if (n_bad) *n_bad = bad_total;
+  uint8_t ep_present = 1;
+  if (rc == SDB_OK && entry_point >= 0 && n_elems &&
+      cudaMemcpy(&ep_present, d_present + entry_point, 1, cudaMemcpyDeviceToHost) != cudaSuccess)
+    rc = SDB_ECUDA;
+  cudaFree(d_present);
+  if (rc == SDB_OK && !ep_present) {
+    set_error("sdb_hnsw_load_staged: the entry point %lld has no He value", (long long)entry_point);
+    rc = SDB_EINVAL;
+  }
   if (rc != SDB_OK) {
     sdb_hnsw_destroy(h);
     return rc;

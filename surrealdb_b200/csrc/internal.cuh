@@ -285,6 +285,11 @@ sdb_status exact_query(Corpus* c, const double* d_q64, const double* d_qmag, con
 sdb_status exact_project(Corpus* c, int fn, double* d_vals, cudaStream_t st);
 sdb_status gen_fill_f32(Ctx* ctx, float* d_out, uint64_t seed, uint64_t first, uint64_t n, cudaStream_t st);
 
+// hnsw.cu: range / monotonicity check of a device CSR handed over the ABI (SDB_EINVAL with a message on violation)
+sdb_status csr_check(Ctx* ctx, const uint64_t* d_rp, const uint32_t* d_ci, uint64_t n_rows, uint64_t n_edges,
+                     uint64_t id_limit, unsigned long long counts[2], const char* what, cudaStream_t st);
+sdb_status csr_validate(Ctx* ctx, const uint64_t* d_rp, const uint32_t* d_ci, uint64_t n_rows, uint64_t n_edges,
+                        uint64_t id_limit, const char* what, cudaStream_t st);
 // graph.cu: out[0..n) = exclusive scan of in[0..n); *d_total = sum (in/out may alias)
 sdb_status exclusive_scan(Ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint64_t n, uint64_t* d_total, cudaStream_t st);
 // stage.cu: He / Hn value decoders (host blobs in, device arrays out)

@@ -220,4 +220,8 @@ class GraphEdgeScan:
         unknown = [s for s in sources if s not in self.store.idx]  # a record without edges has no graph keys: no output
         frontier = self.store.ids([s for s in sources if s in self.store.idx])
         del unknown
+        if self.limit == 0:
+            # with_limit(0): the per-source key stream is opened with limit Some(0) and yields nothing
+            # (scan/graph.rs:238 -> kvs/scanner.rs:160-172: ScanLimit::Count(min(batch, 0))); None = unlimited
+            return []
         return self.store.to_names(self.store.expand_snapshot(tables, d, frontier, self.limit or 0))
