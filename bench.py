@@ -350,7 +350,7 @@ def main():
         else:
             col.wait(t)
 
-    screen_ms, total_ms, cand_max, reranked = [], [], [], []
+    screen_ms, total_ms, cand_max, reranked, survivors = [], [], [], [], []
     fallbacks = [0]
 
     def note_stats():
@@ -359,6 +359,7 @@ def main():
         total_ms.append(s["total_ms"])
         cand_max.append(s["n_candidates"])
         reranked.append(s["n_reranked"])
+        survivors.append(s["n_survivors"])
         fallbacks[0] += s["n_fallback"]
 
     def run_pipelined(submit, first, last, collect):
@@ -566,7 +567,8 @@ def main():
                           "sharding": f"rows/{world}", "l2": "corpus shard (>= 0.9 GB of screen copy) is larger than L2; no flush needed",
                           "batches_in_flight": DEPTH, "fallback_queries_in_timed_region": int(fallbacks[0]),
                           "candidates_reranked_per_query_mean": float(np.mean(reranked)) / batch,
-                          "largest_candidate_set": int(max(cand_max)) if cand_max else 0},
+                          "largest_candidate_set": int(max(cand_max)) if cand_max else 0,
+                          "screen_survivors_per_query_mean": float(np.mean(survivors)) / batch if survivors else 0.0},
                "e2e": {"value": qps_e2e, "unit": "queries/s", "h2d_bytes_per_step": batch * dim * 8,
                        "d2h_bytes_per_step": batch * k * 16 + batch * 4, "ms_per_step": ms_e2e / args.steps,
                        "api": "sdb_knn_bruteforce (host buffers)" if world == 1 else "sdb_knn_sharded_submit + sdb_knn_sharded_wait (host buffers)",

@@ -83,6 +83,7 @@ typedef struct {
   uint64_t kernel_launches;  /* kernels launched by this call                                  */
   float screen_ms;           /* device time of the screening kernels (CUDA events)             */
   float total_ms;            /* device time of the whole call                                  */
+  uint64_t n_survivors;      /* screened rows that passed a threshold and were gathered (all queries) */
 } sdb_knn_stats;
 
 /* ---- context -------------------------------------------------------------------------------- */

@@ -56,31 +56,32 @@ static uint32_t gcd_u32(uint32_t a, uint32_t b) {
   }
   return a;
 }
-// streaming schedule: pass 0 scores a strided sample of <= cap rows completely (seed of the thresholds and of the
-// histograms), ONE streaming launch covers every other tile, visiting them in a golden-ratio stride order so that any
+// streaming schedule: a PROBE launch scores a few tiles spread over the corpus and keeps only chunk maxima (seed of the
+// thresholds), then ONE streaming launch covers every tile, visiting them in a golden-ratio stride order so that any
 // stretch of the launch samples the whole corpus (sorted / clustered corpora do not fool the early thresholds).
-static void build_stream_passes(uint64_t n_rows, uint32_t cand_cap, PassDesc* p0, PassDesc* main) {
+// Corpora that fit the candidate lists entirely are scored in one pass-0 launch instead.
+static void build_stream_passes(uint64_t n_rows, uint32_t cand_cap, uint32_t k, PassDesc* probe, PassDesc* main) {
   const uint64_t T = (n_rows + TILE_ROWS - 1) / TILE_ROWS;
   const uint64_t max0 = cand_cap / TILE_ROWS;
-  *p0 = PassDesc{1u, 0u, 0u, 0u};
+  *probe = PassDesc{1u, 0u, 0u, 0u};
   *main = PassDesc{1u, 0u, 0u, 0u};
   if (T == 0) return;
-  if (T <= max0) {
-    p0->count = (uint32_t)T;
+  if (T <= max0) {  // *probe doubles as the single pass-0 launch: main stays empty
+    probe->count = (uint32_t)T;
     return;
   }
-  uint64_t stride0 = (T + max0 - 1) / max0;
-  if (stride0 < 2) stride0 = 2;
-  const uint64_t n0 = (T + stride0 - 1) / stride0;
-  *p0 = PassDesc{(uint32_t)stride0, 0u, (uint32_t)n0, 0u};
-  const uint32_t cnt = (uint32_t)(T - n0);
+  const uint64_t P = k <= 32 ? 16 : PROBE_TILES_MAX;  // 8 chunk maxima per tile: 128 / 512 values >= 4 k / 2 k
+  const uint64_t stride = T / P;                       // T > max0 >= 16; for P = 64 and T < 64 every tile is probed
+  if (stride == 0) *probe = PassDesc{1u, 0u, (uint32_t)T, 0u};
+  else *probe = PassDesc{(uint32_t)stride, 0u, (uint32_t)P, 0u};
+  const uint32_t cnt = (uint32_t)T;
   uint32_t perm = 0;
   if (cnt >= 8 && !getenv("SDB_STREAM_INORDER")) {
     perm = (uint32_t)(cnt * 0.6180339887498949) | 1u;
     while (gcd_u32(perm, cnt) != 1) perm += 2;
     if (perm >= cnt) perm = 0;
   }
-  *main = PassDesc{1u, (uint32_t)stride0, cnt, perm};
+  *main = PassDesc{1u, 0u, cnt, perm};
 }
 
 struct Rung {
@@ -118,6 +119,7 @@ static sdb_status ticket_prepare(Corpus* c, Ticket& t, uint32_t nq) {
     SDB_CUDA(cudaEventCreate(&t.ev_screen1));
     SDB_CUDA(cudaEventCreate(&t.ev_end));
     SDB_CUDA(cudaEventCreateWithFlags(&t.ev_h2d, cudaEventDisableTiming));
+    SDB_CUDA(cudaEventCreateWithFlags(&t.ev_out, cudaEventDisableTiming));
   }
   if (t.h_cap < nq) {
     if (t.h_flags) cudaFreeHost(t.h_flags);
@@ -151,7 +153,7 @@ static sdb_status enqueue_batch(Corpus* c, Ticket& t) {
     SDB_CUDA(cudaMemcpyAsync(t.h_qflags, c->d_qflags, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, st));
     for (uint32_t q = 0; q < nq; q++) t.h_flags[q] = 2u;  // every query takes the exact kernel
     t.h_stat[0] = nq;
-    t.h_stat[1] = t.h_stat[2] = 0;
+    t.h_stat[1] = t.h_stat[2] = t.h_stat[3] = 0;
     SDB_CUDA(cudaEventRecord(t.ev_end, st));
     return SDB_OK;
   }
@@ -168,16 +170,17 @@ static sdb_status enqueue_batch(Corpus* c, Ticket& t) {
   SDB_TRY(cand_begin(c, nq, (int)rs, st));
   if (tc && c->stream_refine) {
     PassDesc p0, pm;
-    build_stream_passes(c->n, cap, &p0, &pm);
-    if (p0.count) {
+    build_stream_passes(c->n, cap, k, &p0, &pm);
+    if (p0.count && !pm.count) {  // the whole corpus fits the lists: score everything once
       SDB_TRY(screen_tc_pass(c, nq, k, p0, int8, 0, st));
-      SDB_TRY(cand_select(c, nq, k, int8, 0u, pm.count != 0, st));
+      SDB_TRY(cand_select(c, nq, k, int8, 0u, false, st));
       t.n_passes++;
-    }
-    if (pm.count) {
-      SDB_TRY(screen_tc_pass(c, nq, k, pm, int8, 2, st));
+    } else if (pm.count) {
+      SDB_TRY(screen_tc_pass(c, nq, k, p0, int8, 3, st));           // probe: chunk maxima of a few tiles
+      SDB_TRY(cand_seed_from_probe(c, nq, k, p0.count, st));         // thresholds + histogram geometry
+      SDB_TRY(screen_tc_pass(c, nq, k, pm, int8, 2, st));           // the streaming launch over every tile
       SDB_TRY(cand_select(c, nq, k, int8, c->last_slots, false, st));
-      t.n_passes++;
+      t.n_passes += 2;
     }
   } else {
     const std::vector<PassDesc> passes = build_passes(c->n, cap, nq);
@@ -213,6 +216,7 @@ static sdb_status copy_out(Corpus* c, Ticket& t) {  // host-buffer entry points:
     SDB_CUDA(cudaMemcpyAsync(t.h_out_dist, t.d_out_dist, sizeof(double) * (size_t)t.nq * t.k, cudaMemcpyDeviceToHost, st));
   }
   SDB_CUDA(cudaMemcpyAsync(t.h_out_count, t.d_out_count, sizeof(uint32_t) * t.nq, cudaMemcpyDeviceToHost, st));
+  SDB_CUDA(cudaEventRecord(t.ev_out, st));  // wait() blocks on THIS batch's copies, not on whatever was queued behind it
   return SDB_OK;
 }
 
@@ -278,6 +282,7 @@ static sdb_status finish_stats(Corpus* c, Ticket& t, uint32_t n_fallback) {
   stt.n_special_rows = c->n_special;
   stt.n_candidates = t.h_stat[2];  // largest candidate set of the batch
   stt.n_reranked = t.h_stat[1];
+  stt.n_survivors = t.h_stat[3];
   stt.kernel_launches = c->ctx->launches - t.launches0;
   c->stats = stt;
   return SDB_OK;
@@ -324,7 +329,7 @@ static sdb_status submit_locked(Corpus* c, Ticket* t, const double* d_queries, u
     SDB_CUDA(cudaEventRecord(t->ev_screen1, st));
     if (nq) SDB_CUDA(cudaMemsetAsync(d_out_count, 0, sizeof(uint32_t) * nq, st));
     for (uint32_t q = 0; q < nq; q++) t->h_flags[q] = t->h_qflags[q] = 0;
-    t->h_stat[0] = t->h_stat[1] = t->h_stat[2] = 0;
+    t->h_stat[0] = t->h_stat[1] = t->h_stat[2] = t->h_stat[3] = 0;
     t->screen = SDB_SCREEN_NONE_EXACT;
     t->n_rungs = 0;
     t->n_passes = 0;
@@ -343,7 +348,7 @@ static sdb_status wait_locked(Corpus* c, Ticket* t) {
   sdb_status rc = finish_local(c, *t, &n_fb, &repaired);
   if (rc == SDB_OK && t->h_out_count) {
     if (repaired) rc = copy_out(c, *t);  // the copies enqueued at submit time predate the repair
-    if (rc == SDB_OK && cudaStreamSynchronize(c->ctx->stream) != cudaSuccess) {
+    if (rc == SDB_OK && cudaEventSynchronize(t->ev_out) != cudaSuccess) {
       set_error("sdb_knn_wait: %s", cudaGetErrorString(cudaGetLastError()));
       rc = SDB_ECUDA;
     }
@@ -623,7 +628,7 @@ void sdb_corpus_destroy(sdb_corpus* c) {
                   c->d_sel, c->d_fb_q, c->d_fb_qmag, c->d_fb_qflags, c->d_block, c->d_gather};
   for (void* p : ptrs) cudaFree(p);
   for (Ticket& t : c->tickets) {
-    cudaEvent_t evs[] = {t.ev_begin, t.ev_screen0, t.ev_screen1, t.ev_end, t.ev_h2d};
+    cudaEvent_t evs[] = {t.ev_begin, t.ev_screen0, t.ev_screen1, t.ev_end, t.ev_h2d, t.ev_out};
     for (cudaEvent_t e : evs)
       if (e) cudaEventDestroy(e);
     if (t.h_flags) cudaFreeHost(t.h_flags);

@@ -133,6 +133,7 @@ __global__ void cand_begin_kernel(float* __restrict__ tau, uint32_t* __restrict_
     stat[0] = 0;
     stat[1] = 0;
     stat[2] = 0;
+    stat[3] = 0;
   }
   if (q >= nq) return;
   tau[q] = __int_as_float(0xff800000);  // -inf
@@ -192,7 +193,7 @@ static sdb_status ensure_scratch(Corpus* c, uint32_t nq, uint32_t cap) {
   void* old[] = {c->d_q64, c->d_q32, c->d_qbf16, c->d_qmag, c->d_qflags, c->d_qbferr, c->d_tau, c->d_cand, c->d_cand_cnt,
                  c->d_flags, c->d_stat, c->d_rr_key, c->d_rr_dist, c->d_rr_row, c->d_sub, c->d_sub_cnt, c->d_q8,
                  c->d_q8scale, c->d_q8err, c->d_bscale, c->d_beps, c->d_margin, c->d_qlow, c->d_qcap, c->d_hparam,
-                 c->d_hist};
+                 c->d_hist, c->d_probe};
   for (void* p : old) cudaFree(p);
   const uint32_t nqa = nq_pad > c->sc_nq ? nq_pad : c->sc_nq;
   const uint32_t capa = cap > c->sc_cap ? cap : c->sc_cap;
@@ -223,6 +224,7 @@ static sdb_status ensure_scratch(Corpus* c, uint32_t nq, uint32_t cap) {
   SDB_CUDA(cudaMalloc(&c->d_qcap, sizeof(float) * nqa));
   SDB_CUDA(cudaMalloc(&c->d_hparam, sizeof(HistParam) * nqa));
   SDB_CUDA(cudaMalloc(&c->d_hist, sizeof(uint32_t) * (size_t)nqa * HIST_BINS));
+  SDB_CUDA(cudaMalloc(&c->d_probe, sizeof(float) * (size_t)nqa * PROBE_STRIDE));
   c->sub_slots = 2 * (uint32_t)c->ctx->sm_count;
   c->sub_cap = 16;
   SDB_CUDA(cudaMalloc(&c->d_sub, sizeof(Cand) * (size_t)nqa * c->sub_slots * c->sub_cap));
@@ -288,6 +290,70 @@ __device__ __forceinline__ Cand key_to_cand(uint64_t key) {
   return cd;
 }
 
+// Seed of the streaming pass from a probe launch: the probe wrote, per query, the maximum score of every 32-row chunk
+// of a few tiles.  The chunks are disjoint row sets, so the k-th largest chunk maximum s is reached by at least k
+// different rows: the k-th best score of the corpus is >= s, and tau = s - margin is a valid first threshold.  Also
+// sets up the query's histogram (geometry, zero counts) and empties its lists.  One block of 128 threads per query.
+__global__ void __launch_bounds__(128) cand_seed_probe_kernel(const float* __restrict__ probe, uint32_t n_vals, uint32_t k,
+                                                              const float* __restrict__ margin,
+                                                              const float* __restrict__ qlow, const float* __restrict__ qcap,
+                                                              float* __restrict__ tau, uint32_t* __restrict__ cnt,
+                                                              HistParam* __restrict__ hparam, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t s_key[PROBE_STRIDE];
+  const uint32_t q = blockIdx.x;
+  uint32_t p2 = 1;
+  while (p2 < n_vals) p2 <<= 1;
+  for (uint32_t i = threadIdx.x; i < p2; i += blockDim.x) {
+    float v = __int_as_float(0xff800000);
+    if (i < n_vals) v = probe[(size_t)q * PROBE_STRIDE + i];
+    s_key[i] = (v == v) ? f32_key(v) : f32_key(__int_as_float(0xff800000));
+  }
+  __syncthreads();
+  for (uint32_t kk = 2; kk <= p2; kk <<= 1)  // descending bitonic sort of <= 512 keys
+    for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = threadIdx.x; i < p2; i += blockDim.x) {
+        const uint32_t ixj = i ^ j;
+        if (ixj > i) {
+          const uint32_t a = s_key[i], b = s_key[ixj];
+          const bool up = ((i & kk) == 0);
+          if (up ? a < b : a > b) {
+            s_key[i] = b;
+            s_key[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  for (uint32_t i = threadIdx.x; i < HIST_BINS; i += blockDim.x) hist[(size_t)q * HIST_BINS + i] = 0;
+  if (threadIdx.x == 0) {
+    float t = __int_as_float(0xff800000);
+    const float mg = margin[q];
+    if (k != 0 && k <= n_vals) {
+      uint32_t fk = s_key[k - 1];
+      fk = (fk >> 31) ? (fk & 0x7fffffffu) : ~fk;
+      const float s_k = __uint_as_float(fk);
+      if (s_k > __int_as_float(0xff800000)) t = mg > 0.f ? __fsub_rd(s_k, mg) : s_k;
+    }
+    HistParam hp;
+    hp.lo = t > __int_as_float(0xff800000) ? t : qlow[q];
+    float w0 = fmaxf(mg * 0.25f, (qcap[q] - qlow[q]) * 6.1035156e-5f);
+    if (!(w0 > 1e-30f) || !isfinite(w0)) w0 = 1e-30f;
+    hp.w0 = w0;
+    hp.inv_w0 = 1.f / w0;
+    hp.margin = mg;
+    hparam[q] = hp;
+    tau[q] = t;
+    cnt[q] = 0;
+  }
+}
+sdb_status cand_seed_from_probe(Corpus* c, uint32_t nq, uint32_t k, uint32_t n_tiles, cudaStream_t st) {
+  cand_seed_probe_kernel<<<nq, 128, 0, st>>>(c->d_probe, n_tiles * 8, k, c->d_margin, c->d_qlow, c->d_qcap, c->d_tau,
+                                             c->d_cand_cnt, c->d_hparam, c->d_hist);
+  count_launch(c->ctx);
+  SDB_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
+
 // Per query: gather the main list and the thread-private sub-lists of the tensor-core screens, find the k-th best
 // screened score s_k, and keep every candidate with score >= tau = s_k - margin (see cand_begin_kernel).  While fewer
 // than k candidates exist everything is kept and tau stays where it is.  tau only ever rises: all rows with a score
@@ -302,7 +368,7 @@ __global__ void __launch_bounds__(256) cand_select_kernel(Cand* __restrict__ can
                                                            const uint32_t* __restrict__ sub_cnt, uint32_t n_slots,
                                                            uint32_t subcap, HistParam* __restrict__ hparam,
                                                            uint32_t* __restrict__ hist, const float* __restrict__ qlow,
-                                                           const float* __restrict__ qcap) {
+                                                           const float* __restrict__ qcap, uint32_t* __restrict__ stat) {
   extern __shared__ uint64_t s_keys[];
   __shared__ uint32_t s_n, s_over;
   __shared__ uint32_t s_hist[256];
@@ -342,6 +408,7 @@ __global__ void __launch_bounds__(256) cand_select_kernel(Cand* __restrict__ can
   __syncthreads();
   const uint32_t n = s_n < cap ? s_n : cap;
   if (threadIdx.x == 0 && s_over) flags[q] |= 1u;  // candidates were dropped: this query must be re-run exactly
+  if (threadIdx.x == 0 && stat) atomicAdd(stat + 3, s_n);  // survivors gathered (diagnostics)
   const float tau_old = tau[q];
   float tau_new = tau_old;
   uint64_t kth = 0;
@@ -351,7 +418,10 @@ __global__ void __launch_bounds__(256) cand_select_kernel(Cand* __restrict__ can
     //      radix select, 8 bits per round.  Warp-aggregated histogram updates: the scores of one query share their
     //      leading bytes, so plain shared-memory atomics would serialise on one bin.
     const uint32_t lane = threadIdx.x & 31u;
-    for (uint32_t round = 0; round < 8; round++) {
+    // with a margin only the k-th SCORE matters (the keep rule is score >= s_k - margin): 4 rounds over the score half
+    // of the key; approximate mode keeps exactly k entries and needs the full (score, row) key: 8 rounds
+    const uint32_t n_rounds = mg > 0.f ? 4u : 8u;
+    for (uint32_t round = 0; round < n_rounds; round++) {
       const uint32_t shift = 56 - 8 * round;
       s_hist[threadIdx.x] = 0;
       __syncthreads();
@@ -397,7 +467,7 @@ __global__ void __launch_bounds__(256) cand_select_kernel(Cand* __restrict__ can
       }
       __syncthreads();
     }
-    kth = s_prefix;  // the k-th largest key itself
+    kth = n_rounds == 8 ? s_prefix : (s_prefix << 32);  // the k-th largest key itself (score half only with a margin)
     const float s_k = key_to_cand(kth).score;
     const float thr = mg > 0.f ? __fsub_rd(s_k, mg) : s_k;
     tau_new = thr > tau_old ? thr : tau_old;  // (tau_old = -inf the first time)
@@ -440,14 +510,21 @@ sdb_status cand_select(Corpus* c, uint32_t nq, uint32_t k, bool drop_invalid, ui
   const size_t smem = sizeof(uint64_t) * c->sc_cap;
   cand_select_kernel<<<nq, 256, smem, st>>>(  // 256 threads: several blocks per SM, the whole batch is one wave
       c->d_cand, c->d_cand_cnt, c->d_tau, c->d_flags, c->sc_cap, k, c->d_margin, drop_invalid ? c->d_snorm : nullptr,
-      c->d_sub, c->d_sub_cnt, n_slots, c->sub_cap, seed_hist ? c->d_hparam : nullptr, c->d_hist, c->d_qlow, c->d_qcap);
+      c->d_sub, c->d_sub_cnt, n_slots, c->sub_cap, seed_hist ? c->d_hparam : nullptr, c->d_hist, c->d_qlow, c->d_qcap,
+      c->d_stat);
   count_launch(c->ctx);
   SDB_CUDA(cudaGetLastError());
   return SDB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
-// exact re-rank: one block per query, each warp takes 32 entries (candidates, then the special rows)
+// exact re-rank.  Work unit = (query, group of 128 entries): block (x = query, y = group), each warp takes 32 entries
+// (candidates first, then the special rows) and walks their rows column-chunk by column-chunk: 32 coalesced 128-byte
+// row segments are requested back to back (all 32 loads in flight before the first is consumed -- the kernel is bound
+// by the latency of these gathers, not by the f64 arithmetic), transposed through shared memory, and every lane then
+// accumulates ITS row strictly left to right in the reference's arithmetic.  Candidate counts vary per query by
+// orders of magnitude (a handful ... a whole cluster), hence the flat (query, group) decomposition: groups beyond a
+// query's count exit at once.
 constexpr uint32_t QCHUNK = 1024;  // query columns staged in shared memory per step
 
 template <typename T, int WARPS>
@@ -462,63 +539,68 @@ __global__ void __launch_bounds__(WARPS * 32) cand_rerank_kernel(
   const uint32_t q = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t n_c = cnt[q] < cap ? cnt[q] : cap;
   const uint32_t n_e = n_c + n_special;
+  const uint32_t e_first = blockIdx.y * (WARPS * 32);
+  if (e_first >= n_e) return;  // uniform per block
   const bool q_nan = (qflags[q] & 2u) != 0;
   const double qm = qmag[q];
-  for (uint32_t e0 = 0; e0 < n_e; e0 += WARPS * 32) {  // uniform per block
-    const uint32_t e = e0 + warp * 32 + lane;
-    uint32_t my_row = NO_ROW;
-    if (e < n_c) my_row = cand[(size_t)q * cap + e].row;
-    else if (e < n_e) my_row = special[e - n_c];
-    ExactAcc acc;
-    for (uint32_t cb = 0; cb < dim; cb += QCHUNK) {
-      const uint32_t cw = dim - cb < QCHUNK ? dim - cb : QCHUNK;
-      __syncthreads();
-      for (uint32_t i = threadIdx.x; i < cw; i += blockDim.x) s_q[i] = q64[(size_t)q * dim + cb + i];
-      __syncthreads();
-      // walk columns [cb, cb+cw) of the 32 rows of this warp
-      const T* base = rows + cb;
-      for (uint32_t c0 = 0; c0 < cw; c0 += 32) {
-        const uint32_t c = c0 + lane;
-#pragma unroll 8
-        for (int r = 0; r < 32; r++) {
-          const uint32_t row = __shfl_sync(0xffffffffu, my_row, r);
-          T v = T(0);
-          if (row != NO_ROW && c < cw) v = __ldg(base + (size_t)row * dim + c);
-          tile[warp][r][lane] = v;
-        }
-        __syncwarp();
-        if (my_row != NO_ROW) {
-          const uint32_t lim = cw - c0 < 32u ? cw - c0 : 32u;
-          if (metric == SDB_COSINE) {
-            for (uint32_t j = 0; j < lim; j++) acc.cosine_step((double)tile[warp][lane][j], s_q[c0 + j]);
-          } else {
-            for (uint32_t j = 0; j < lim; j++) acc.euclid_step((double)tile[warp][lane][j], s_q[c0 + j]);
-          }
-        }
-        __syncwarp();
+  const uint32_t e = e_first + warp * 32 + lane;
+  uint32_t my_row = NO_ROW;
+  if (e < n_c) my_row = cand[(size_t)q * cap + e].row;
+  else if (e < n_e) my_row = special[e - n_c];
+  const bool warp_active = e_first + warp * 32 < n_e;
+  ExactAcc acc;
+  for (uint32_t cb = 0; cb < dim; cb += QCHUNK) {
+    const uint32_t cw = dim - cb < QCHUNK ? dim - cb : QCHUNK;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < cw; i += blockDim.x) s_q[i] = q64[(size_t)q * dim + cb + i];
+    __syncthreads();
+    if (!warp_active) continue;
+    const T* base = rows + cb;
+    for (uint32_t c0 = 0; c0 < cw; c0 += 32) {
+      const uint32_t c = c0 + lane;
+      T vals[32];
+#pragma unroll
+      for (int r = 0; r < 32; r++) {  // 32 independent gathers in flight
+        const uint32_t row = __shfl_sync(0xffffffffu, my_row, r);
+        vals[r] = (row != NO_ROW && c < cw) ? __ldg(base + (size_t)row * dim + c) : T(0);
       }
+#pragma unroll
+      for (int r = 0; r < 32; r++) tile[warp][r][lane] = vals[r];
+      __syncwarp();
+      if (my_row != NO_ROW) {
+        const uint32_t lim = cw - c0 < 32u ? cw - c0 : 32u;
+        if (metric == SDB_COSINE) {
+          for (uint32_t j = 0; j < lim; j++) acc.cosine_step((double)tile[warp][lane][j], s_q[c0 + j]);
+        } else {
+          for (uint32_t j = 0; j < lim; j++) acc.euclid_step((double)tile[warp][lane][j], s_q[c0 + j]);
+        }
+      }
+      __syncwarp();
     }
-    if (my_row != NO_ROW) {
-      const double d = metric == SDB_COSINE ? cosine_finish(acc, mag[my_row], qm, q_nan) : euclid_finish(acc, q_nan);
-      const size_t o = (size_t)q * rr_stride + e;
-      rr_key[o] = dist_key(d);
-      rr_dist[o] = d;
-      rr_row[o] = my_row;
-    }
+  }
+  if (my_row != NO_ROW) {
+    const double d = metric == SDB_COSINE ? cosine_finish(acc, mag[my_row], qm, q_nan) : euclid_finish(acc, q_nan);
+    const size_t o = (size_t)q * rr_stride + e;
+    rr_key[o] = dist_key(d);
+    rr_dist[o] = d;
+    rr_row[o] = my_row;
   }
 }
 
 sdb_status cand_rerank(Corpus* c, uint32_t nq, cudaStream_t st) {
+  // groups of 128 entries per query: enough for the longest possible list; empty groups return immediately
+  const uint32_t groups = (c->sc_cap + c->n_special + 127) / 128;
+  const dim3 grid(nq, groups ? groups : 1);
   if (c->dtype == SDB_F32)
-    cand_rerank_kernel<float, 4><<<nq, 128, 0, st>>>((const float*)c->d_rows, c->dim, (int)c->metric, c->d_mag,
-                                                     c->d_q64, c->d_qmag, c->d_qflags, c->d_cand, c->d_cand_cnt,
-                                                     c->sc_cap, c->d_special, c->n_special, c->d_rr_key,
-                                                     c->d_rr_dist, c->d_rr_row, c->rr_stride);
+    cand_rerank_kernel<float, 4><<<grid, 128, 0, st>>>((const float*)c->d_rows, c->dim, (int)c->metric, c->d_mag,
+                                                       c->d_q64, c->d_qmag, c->d_qflags, c->d_cand, c->d_cand_cnt,
+                                                       c->sc_cap, c->d_special, c->n_special, c->d_rr_key,
+                                                       c->d_rr_dist, c->d_rr_row, c->rr_stride);
   else
-    cand_rerank_kernel<double, 4><<<nq, 128, 0, st>>>((const double*)c->d_rows, c->dim, (int)c->metric, c->d_mag,
-                                                      c->d_q64, c->d_qmag, c->d_qflags, c->d_cand, c->d_cand_cnt,
-                                                      c->sc_cap, c->d_special, c->n_special, c->d_rr_key,
-                                                      c->d_rr_dist, c->d_rr_row, c->rr_stride);
+    cand_rerank_kernel<double, 4><<<grid, 128, 0, st>>>((const double*)c->d_rows, c->dim, (int)c->metric, c->d_mag,
+                                                        c->d_q64, c->d_qmag, c->d_qflags, c->d_cand, c->d_cand_cnt,
+                                                        c->sc_cap, c->d_special, c->n_special, c->d_rr_key,
+                                                        c->d_rr_dist, c->d_rr_row, c->rr_stride);
   count_launch(c->ctx);
   SDB_CUDA(cudaGetLastError());
   return SDB_OK;

@@ -93,23 +93,66 @@ __global__ void __launch_bounds__(256) to_bf16_kernel(const float* __restrict__ 
 // integer dot product q8.x8 is itself the screening score (no per-row weight in the epilogue):
 //   sim(q,x) = s_q * s * (q8.x8) / |q|  +  err,   |err| <= (1 + e_q) * e_x + e_q,   e_x = |x/|x| - s*x8|  (per row)
 // pass 1: gmax = max over valid rows of max_i |x_i| / |x|
+// It also keeps every row's figure (rmax[r]) and a 4096-bin histogram of them over the float bit pattern (8 exponent
+// + 4 mantissa bits), from which the host picks the scale: a handful of outlier rows (one dominant component) must not
+// dictate the quantisation step of the other ten million.
+constexpr uint32_t RMAX_BINS = 4096;
+__device__ __host__ inline uint32_t rmax_bin(float v) {  // v > 0
+  uint32_t u;
+#ifdef __CUDA_ARCH__
+  u = __float_as_uint(v);
+#else
+  memcpy(&u, &v, 4);
+#endif
+  return (u >> 19) & (RMAX_BINS - 1);
+}
 __global__ void __launch_bounds__(256) quantize_scan_kernel(const float* __restrict__ rows, uint32_t dim, uint64_t n,
                                                             const double* __restrict__ mag, const float* __restrict__ snorm,
-                                                            uint32_t* gmax_bits) {
+                                                            uint32_t* gmax_bits, float* __restrict__ rmax,
+                                                            uint32_t* __restrict__ hist) {
+  __shared__ uint32_t s_hist[RMAX_BINS];
+  for (uint32_t i = threadIdx.x; i < RMAX_BINS; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t warps = (uint64_t)gridDim.x * 8;
   float best = 0.f;
   for (uint64_t r = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < n; r += warps) {
     const float sn = snorm[r];
-    if (!(sn == sn)) continue;  // skipped / special
+    if (!(sn == sn)) {  // skipped / special
+      if (lane == 0) rmax[r] = 0.f;
+      continue;
+    }
     const float* x = rows + r * dim;
     float mx = 0.f;
     for (uint32_t c = lane; c < dim; c += 32) mx = fmaxf(mx, fabsf(x[c]));
 #pragma unroll
     for (int o2 = 16; o2 > 0; o2 >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o2));
-    best = fmaxf(best, mx / (float)mag[r]);
+    const float v = mx / (float)mag[r];
+    best = fmaxf(best, v);
+    if (lane == 0) {
+      rmax[r] = v;
+      if (v > 0.f && isfinite(v)) atomicAdd(&s_hist[rmax_bin(v)], 1u);
+    }
   }
   if (lane == 0 && best > 0.f) atomicMax(gmax_bits, __float_as_uint(best));
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < RMAX_BINS; i += blockDim.x)
+    if (s_hist[i]) atomicAdd(hist + i, s_hist[i]);
+}
+// rows whose largest normalised component reaches `thr` become special rows (ranked exactly on every query, never a
+// screen candidate): the int8 scale is then set by the remaining rows
+__global__ void mark_outliers_kernel(const float* __restrict__ rmax, uint64_t n, float thr, float* __restrict__ snorm,
+                                     uint32_t* __restrict__ special, uint32_t* special_cnt) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  if (rmax[r] >= thr) {
+    const float sn = snorm[r];
+    if (sn == sn) {
+      const uint32_t pos = atomicAdd(special_cnt, 1u);
+      if (pos < (uint32_t)SPECIAL_CAP) special[pos] = (uint32_t)r;
+      snorm[r] = __int_as_float(0x7fc00000);
+    }
+  }
 }
 // pass 2: x8 = clamp(rn(x / (|x| s)), +-127), e_x accumulated exactly as the residual norm (clipping included)
 __global__ void __launch_bounds__(256) quantize_rows_kernel(const float* __restrict__ rows, uint32_t dim, uint32_t dim_pad8,
@@ -184,13 +227,52 @@ sdb_status corpus_finalize_device(Corpus* c) {
       SDB_CUDA(cudaGetLastError());
     }
   }
+  c->n_outliers = 0;
   if (c->n && c->dtype == SDB_F32 && c->d_i8 && c->metric == SDB_COSINE) {
     const uint64_t n_pad = (c->n + TILE_ROWS - 1) / TILE_ROWS * TILE_ROWS;
+    float* d_rmax = nullptr;
+    uint32_t* d_hist = nullptr;
+    SDB_CUDA(cudaMallocAsync(&d_rmax, sizeof(float) * c->n, st));
+    SDB_CUDA(cudaMallocAsync(&d_hist, sizeof(uint32_t) * RMAX_BINS, st));
+    SDB_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * RMAX_BINS, st));
     quantize_scan_kernel<<<ctx->sm_count * 8, 256, 0, st>>>((const float*)c->d_rows, c->dim, c->n, c->d_mag, c->d_snorm,
-                                                            d_tmp + 3);
+                                                            d_tmp + 3, d_rmax, d_hist);
+    count_launch(ctx);
+    // ---- pick the scale: if at most 64 rows sit far above the rest (their largest normalised component is more
+    //      than 1.5 x that of the 65th), make THEM special rows and quantise for the others ----
+    std::vector<uint32_t> h_hist(RMAX_BINS);
+    uint32_t h4[4] = {0, 0, 0, 0};
+    SDB_CUDA(cudaMemcpyAsync(h_hist.data(), d_hist, sizeof(uint32_t) * RMAX_BINS, cudaMemcpyDeviceToHost, st));
+    SDB_CUDA(cudaMemcpyAsync(h4, d_tmp, 16, cudaMemcpyDeviceToHost, st));
+    SDB_CUDA(cudaStreamSynchronize(st));
+    float gmax;
+    memcpy(&gmax, &h4[3], 4);
+    if (gmax > 0.f && !getenv("SDB_NO_OUTLIER_ROWS")) {
+      uint32_t cum = 0;
+      int b = (int)RMAX_BINS - 1;
+      for (; b >= 0; b--) {
+        if (cum + h_hist[b] > 64u) break;
+        cum += h_hist[b];
+      }
+      // every row in bins above b is an outlier candidate (cum <= 64 of them); thr = lower edge of bin b + 1
+      if (b >= 0 && b + 1 < (int)RMAX_BINS && cum > 0 && h4[0] + cum <= (uint32_t)SPECIAL_CAP) {
+        const uint32_t u = (uint32_t)(b + 1) << 19;
+        float thr;
+        memcpy(&thr, &u, 4);
+        if (thr > 0.f && gmax > 1.5f * thr) {
+          mark_outliers_kernel<<<(unsigned)((c->n + 255) / 256), 256, 0, st>>>(d_rmax, c->n, thr, c->d_snorm, c->d_special, d_tmp);
+          count_launch(ctx);
+          SDB_CUDA(cudaMemcpyAsync(d_tmp + 3, &thr, 4, cudaMemcpyHostToDevice, st));  // scale from the remaining rows
+          SDB_CUDA(cudaStreamSynchronize(st));  // `thr` lives on this stack frame
+          c->n_outliers = cum;
+        }
+      }
+    }
     quantize_rows_kernel<<<ctx->sm_count * 8, 256, 0, st>>>((const float*)c->d_rows, c->dim, c->dim_pad8, c->n, n_pad,
                                                             c->d_mag, c->d_snorm, d_tmp + 3, c->d_i8, d_tmp + 2);
-    count_launch(ctx, 2);
+    count_launch(ctx);
+    SDB_CUDA(cudaFreeAsync(d_rmax, st));
+    SDB_CUDA(cudaFreeAsync(d_hist, st));
     SDB_CUDA(cudaGetLastError());
   }
   uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -70,6 +70,8 @@ __host__ __device__ inline uint32_t f32_key(float f) {  // ascending key of a fl
 // bin() is monotone and edge(bin(s)) <= s up to float rounding (the refiner subtracts a guard), so
 // "suffix count from the top reaches k at bin b" proves that the k-th best score seen so far is >= edge(b).
 constexpr uint32_t HIST_BINS = 256;
+constexpr uint32_t PROBE_TILES_MAX = 64;                   // tiles scored by the probe launch
+constexpr uint32_t PROBE_STRIDE = PROBE_TILES_MAX * 8;     // chunk maxima per query (8 chunks of 32 rows per tile)
 struct HistParam {
   float lo;      // floor: tau at the time the histogram was seeded
   float inv_w0;  // 1 / w0
@@ -159,7 +161,7 @@ struct Ticket {
   cudaEvent_t ev_begin = nullptr, ev_screen0 = nullptr, ev_screen1 = nullptr, ev_end = nullptr;
   uint32_t* h_flags = nullptr;   // pinned: per query, bit0 overflow, bit1 proof failed
   uint32_t* h_qflags = nullptr;  // pinned: per query, bit0 needs the exact path, bit1 NaN input
-  uint32_t* h_stat = nullptr;    // pinned: [0] queries flagged, [1] candidates re-ranked (low 32 bits), [2] max per query
+  uint32_t* h_stat = nullptr;    // pinned: [0] queries flagged, [1] candidates re-ranked, [2] max per query, [3] survivors gathered
   uint32_t h_cap = 0;
   // host-buffer entry points: per-slot device staging
   double* d_in_q = nullptr;
@@ -167,7 +169,7 @@ struct Ticket {
   double* d_res_dist = nullptr;
   uint32_t* d_res_count = nullptr;
   size_t in_cap = 0, res_cap = 0, res_cap_q = 0;
-  cudaEvent_t ev_h2d = nullptr;
+  cudaEvent_t ev_h2d = nullptr, ev_out = nullptr;
 };
 constexpr int N_TICKETS = 4;
 
@@ -201,6 +203,7 @@ struct Corpus {
   uint64_t n_removed = 0;
   uint32_t* d_special = nullptr;    // rows ranked exactly on every query
   uint32_t n_special = 0;
+  uint32_t n_outliers = 0;          // of those: rows made special because one component dominates (int8 scale)
   bool special_overflow = false;
   float max_norm = 0.f;
   // ---- search scratch (grown on demand) ----
@@ -224,11 +227,12 @@ struct Corpus {
   float* d_qcap = nullptr;
   HistParam* d_hparam = nullptr; // per query histogram geometry of the streaming screen
   uint32_t* d_hist = nullptr;    // [nq][HIST_BINS]
+  float* d_probe = nullptr;      // [nq][PROBE_STRIDE] chunk maxima of the probe launch
   float* d_tau = nullptr;
   Cand* d_cand = nullptr;
   uint32_t* d_cand_cnt = nullptr;
   uint32_t* d_flags = nullptr;   // per query: bit0 overflow, bit1 verification failed
-  uint32_t* d_stat = nullptr;    // [0] queries flagged by cand_final, [1] candidates re-ranked, [2] max per query
+  uint32_t* d_stat = nullptr;    // [0] queries flagged by cand_final, [1] candidates re-ranked, [2] max per query, [3] gathered
   uint64_t* d_rr_key = nullptr;  // re-rank results: nq x rr_stride
   double* d_rr_dist = nullptr;
   uint32_t* d_rr_row = nullptr;
@@ -258,7 +262,7 @@ sdb_status corpus_finalize_device(Corpus* c);
 sdb_status screen_simt_pass(Corpus* c, uint32_t nq, const PassDesc& p, cudaStream_t st);
 // screen_tc.cu
 // mode 0: pass 0 (every score of the pass's tiles written to fixed slots), 1: threshold pass, 2: streaming pass with
-// in-kernel threshold refinement (histogram + refiner warp)
+// in-kernel threshold refinement (histogram + refiner warp), 3: probe (chunk maxima of a few tiles, no candidates)
 sdb_status screen_tc_pass(Corpus* c, uint32_t nq, uint32_t k, const PassDesc& p, bool int8, int mode, cudaStream_t st);
 bool screen_tc_available();
 // candidates.cu
@@ -274,6 +278,8 @@ sdb_status cand_set_count(Corpus* c, uint32_t nq, uint32_t value, cudaStream_t s
 // query's histogram (geometry + counts of the kept candidates) for the streaming pass that follows.
 sdb_status cand_select(Corpus* c, uint32_t nq, uint32_t k, bool drop_invalid, uint32_t n_slots, bool seed_hist,
                        cudaStream_t st);
+// after a probe launch over n_tiles tiles: tau = (k-th largest chunk maximum) - margin, histogram geometry, empty lists
+sdb_status cand_seed_from_probe(Corpus* c, uint32_t nq, uint32_t k, uint32_t n_tiles, cudaStream_t st);
 sdb_status cand_rerank(Corpus* c, uint32_t nq, cudaStream_t st);
 sdb_status cand_final(Corpus* c, uint32_t nq, uint32_t k, uint64_t row_base, uint64_t* d_out_rows, double* d_out_dist,
                       uint32_t* d_out_count, cudaStream_t st);

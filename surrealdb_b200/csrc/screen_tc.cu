@@ -159,13 +159,18 @@ __device__ __noinline__ void append_survivor_h(Cand* my_sub, uint32_t my_cnt_sad
 // MODE 0: pass 0 -- every score of the pass's tiles goes to a fixed slot of the query's main list (tau = -inf)
 // MODE 1: threshold pass -- survivors of a fixed tau (legacy multi-pass schedule)
 // MODE 2: streaming pass -- tau is re-read at every work item and raised by the refiner warps while the kernel runs
+// MODE 3: probe -- nothing is appended; every epilogue thread writes the maximum of each 32-column chunk it sees
+//         (probe[q][tile * 8 + chunk]).  The chunk maxima belong to DISJOINT row sets, so the k-th largest of them is a
+//         lower bound of the k-th best score of the corpus: the seed of the streaming pass's thresholds, at the cost
+//         of one round of MMAs and no candidate traffic.
 template <bool COSINE, bool INT8, int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const float* __restrict__ snorm, uint32_t k_blocks, uint32_t n_mblocks, uint32_t nq,
                  PassDesc pass, float* tau, Cand* __restrict__ cand,
                  uint32_t* __restrict__ cand_cnt, uint32_t cap, Cand* __restrict__ sub, uint32_t* __restrict__ sub_cnt,
-                 uint32_t k, const HistParam* __restrict__ hparam, uint32_t* hist) {
+                 uint32_t k, const HistParam* __restrict__ hparam, uint32_t* hist, float* __restrict__ probe,
+                 uint32_t probe_stride) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -288,7 +293,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
       const size_t row0 = (size_t)tile * BLOCK_N;
       float* sn = s_snorm + a * BLOCK_N;
-      if (!INT8) {
+      if (!INT8 || MODE == 3) {
         // stage this tile's screening norms (safe: every epilogue thread passed the named barrier of item j-1
         // only after finishing item j-2, the previous user of s_snorm[a])
         sn[et] = __ldg(snorm + row0 + et);
@@ -325,7 +330,18 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int i = 1; i < 8; i++) gm[g] = max(gm[g], (int)v[8 * g + i]);
           }
           const int m = max(max(gm[0], gm[1]), max(gm[2], gm[3]));
-          if (pass0) {
+          if (MODE == 3) {
+            // invalid rows (NaN screening norm) score 0 in the integer screen: they must not pose as a real score
+            int pm = (int)0x80000000;
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+              const float snv = sn[cbase + c0 + i];
+              if (snv == snv) pm = max(pm, (int)v[i]);
+            }
+            if (q < nq)
+              probe[(size_t)q * probe_stride + tidx * 8 + half * 4 + cc] =
+                  pm == (int)0x80000000 ? __int_as_float(0xff800000) : __int2float_rd(pm);
+          } else if (pass0) {
             if (q < nq) {
 #pragma unroll
               for (int i = 0; i < 32; i++) {
@@ -371,7 +387,9 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             gmf[i >> 3] = fmaxf(gmf[i >> 3], fmaxf(fmaxf(sc[i + 0], sc[i + 1]), fmaxf(sc[i + 2], sc[i + 3])));  // fmaxf drops NaNs
           }
           const float m = fmaxf(fmaxf(gmf[0], gmf[1]), fmaxf(gmf[2], gmf[3]));
-          if (pass0) {
+          if (MODE == 3) {
+            if (q < nq) probe[(size_t)q * probe_stride + tidx * 8 + half * 4 + cc] = m;  // -inf: no valid row in the chunk
+          } else if (pass0) {
             if (q < nq) {  // every (finite or NaN) score goes to its fixed slot; compaction drops the NaNs
 #pragma unroll
               for (int i = 0; i < 32; i++) {
@@ -406,7 +424,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[a]));
     }
     // publish the private append counters: slot (CTA, column half) of every query this thread served
-    if (!pass0) {
+    if (MODE == 1 || MODE == 2) {
       const uint32_t n_slots = gridDim.x * 2;
       for (uint32_t mb = 0; mb < n_mblocks; mb++) {
         const uint32_t qq = mb * BLOCK_M + row_in_tile;
@@ -533,9 +551,9 @@ bool screen_tc_available() { return true; }
 sdb_status screen_tc_init_device() {
 #define SET_SMEM(COS, I8, MODE) \
   SDB_CUDA(cudaFuncSetAttribute(tc::screen_tc_kernel<COS, I8, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES))
-  SET_SMEM(true, false, 0); SET_SMEM(true, false, 1); SET_SMEM(true, false, 2);
-  SET_SMEM(false, false, 0); SET_SMEM(false, false, 1); SET_SMEM(false, false, 2);
-  SET_SMEM(true, true, 0); SET_SMEM(true, true, 1); SET_SMEM(true, true, 2);
+  SET_SMEM(true, false, 0); SET_SMEM(true, false, 1); SET_SMEM(true, false, 2); SET_SMEM(true, false, 3);
+  SET_SMEM(false, false, 0); SET_SMEM(false, false, 1); SET_SMEM(false, false, 2); SET_SMEM(false, false, 3);
+  SET_SMEM(true, true, 0); SET_SMEM(true, true, 1); SET_SMEM(true, true, 2); SET_SMEM(true, true, 3);
 #undef SET_SMEM
   return SDB_OK;
 }
@@ -560,8 +578,12 @@ sdb_status screen_tc_pass(Corpus* c, uint32_t nq, uint32_t k, const PassDesc& p,
     const uint64_t items0 = (uint64_t)p.count * ((nq0 + tc::BLOCK_M - 1) / tc::BLOCK_M);
     if (grid > items0) grid = (uint32_t)items0;
   }
-  c->last_slots = grid * 2;
-  const uint32_t slots = c->last_slots;
+  if (mode == 3 && p.count * 8 > PROBE_STRIDE) {
+    set_error("screen_tc_pass: probe of %u tiles exceeds the probe buffer", p.count);
+    return SDB_EINVAL;
+  }
+  if (mode != 3) c->last_slots = grid * 2;
+  const uint32_t slots = grid * 2;
   for (uint32_t q0 = 0; q0 < nq; q0 += chunk_q) {
     const uint32_t nqc = nq - q0 < chunk_q ? nq - q0 : chunk_q;
     const uint32_t nq_pad = (nqc + tc::BLOCK_M - 1) / tc::BLOCK_M * tc::BLOCK_M;
@@ -578,12 +600,14 @@ sdb_status screen_tc_pass(Corpus* c, uint32_t nq, uint32_t k, const PassDesc& p,
     uint32_t* hist = c->d_hist + (size_t)q0 * HIST_BINS;
 #define LAUNCH_TC1(COS, I8, MODE)                                                                              \
   tc::screen_tc_kernel<COS, I8, MODE><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(                              \
-      map_a, map_b, c->d_snorm, k_blocks, n_mblocks, nqc, p, tau, cand, ccnt, c->sc_cap, sub, scnt, k, hp, hist)
+      map_a, map_b, c->d_snorm, k_blocks, n_mblocks, nqc, p, tau, cand, ccnt, c->sc_cap, sub, scnt, k, hp, hist,  \
+      c->d_probe + (size_t)q0 * PROBE_STRIDE, PROBE_STRIDE)
 #define LAUNCH_TC(COS, I8)                   \
   do {                                       \
     if (mode == 0) LAUNCH_TC1(COS, I8, 0);   \
     else if (mode == 1) LAUNCH_TC1(COS, I8, 1); \
-    else LAUNCH_TC1(COS, I8, 2);             \
+    else if (mode == 2) LAUNCH_TC1(COS, I8, 2); \
+    else LAUNCH_TC1(COS, I8, 3);             \
   } while (0)
     if (int8) LAUNCH_TC(true, true);
     else if (c->metric == SDB_COSINE) LAUNCH_TC(true, false);

@@ -124,6 +124,23 @@ def test_bf16_rounding_midpoints_do_not_break_the_proof(ctx):
     check_queries(col, corpus, queries, "EUCLIDEAN", 10, range(8))
 
 
+def test_outlier_rows_do_not_dictate_the_int8_scale(ctx):
+    # a few rows with one dominant component: they become special rows (ranked exactly on every query) and the int8
+    # copy is scaled for the others, so AUTO keeps the int8 screen; an outlier that IS the nearest neighbour is found
+    rng = np.random.default_rng(23)
+    n, dim, k = 50_000, 64, 10
+    corpus = rng.normal(0, 1, (n, dim)).astype(np.float32)
+    out_rows = [7, 1234, 49_999]
+    for r in out_rows:
+        corpus[r, 5] *= 80.0
+    queries = rng.normal(0, 1, (6, dim))
+    queries[0] = corpus[1234].astype(np.float64) * 1.01  # nearest neighbour = an outlier row
+    col = make_col(ctx, corpus, "COSINE")  # AUTO
+    check_queries(col, corpus, queries, "COSINE", k, range(6))
+    st = col.stats()
+    assert st["screen_used"] == 4 and st["n_special_rows"] == len(out_rows) and st["n_fallback"] == 0, st
+
+
 def test_filtered_and_tiny_samples(ctx):
     # a skip mask that leaves fewer than k valid rows in the scored sample: the thresholds start at -inf and the
     # histograms are seeded from the score range instead
