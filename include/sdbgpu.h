@@ -223,6 +223,23 @@ sdb_status sdb_hnsw_search_filtered(sdb_hnsw*, const float* queries, uint32_t nq
                                     const uint8_t* truthy, uint64_t* out_elems, double* out_dist, uint32_t* out_count,
                                     uint64_t* out_counters);
 
+/* Search while pending updates exist: Hnsw::knn_search(.., pending_docs = Some(bitmap)) (hnsw/mod.rs:459-482).
+ * all_docs_pending[e] != 0 iff EVERY document of element e is in the pending bitmap that
+ * HnswIndex::search_pendings (hnsw/index.rs:372-420) returned (are_all_docs_in_pending, hnsw/layer.rs:320-339),
+ * evaluated by the caller per element (host, n_elems bytes).  Such an element still enters the result window but is
+ * never expanded (layer.rs:209), in every layer.  The filtered search needs no extra entry point: add_if_truthy
+ * ignores those elements (layer.rs:287-296), i.e. the caller clears their bits in the `truthy` mask. */
+sdb_status sdb_hnsw_search_pending(sdb_hnsw*, const float* queries, uint32_t nq, uint32_t k, uint32_t ef,
+                                   const uint8_t* all_docs_pending, uint64_t* out_elems, double* out_dist,
+                                   uint32_t* out_count, uint64_t* out_counters);
+
+/* Distance::calculate for VectorType::F32 vectors (idx/trees/vector.rs:243-289,659-672) applied to vectors that are
+ * not part of the graph: the new_vectors of pending updates, which HnswIndex::search_pendings ranks by brute force
+ * (hnsw/index.rs:398-404).  query: dim floats, vectors: n x dim floats, out: n doubles (all host memory).  Same
+ * arithmetic as the walk kernel (f32 8-lane accumulation, f64 finish). */
+sdb_status sdb_vec_distance_f32(sdb_ctx*, sdb_metric, uint32_t dim, const float* query, const float* vectors, uint64_t n,
+                                double* out);
+
 /* ---- staging: the reference's persisted HNSW state -> device.  These replace the per-key
  *      decode loops of HnswLayer::load (idx/trees/hnsw/layer.rs:526-540, UndirectedGraph::load_node
  *      idx/trees/graph.rs:117-126) and HnswElements::get_vector (hnsw/elements.rs:95-128, Vector::from(
@@ -272,6 +289,16 @@ sdb_status sdb_hnsw_select_neighbors(sdb_ctx*, const float* d_vectors, uint32_t 
  *      (exec/operators/recursion/collect.rs:74-143) -------------------------------------------- */
 sdb_status sdb_graph_load_csr(sdb_ctx*, uint64_t n_rows, const uint64_t* row_ptr, const uint32_t* col_idx,
                               sdb_graph** out);
+/* Row-sharded adjacency ("one exchange per hop"): this rank holds rows [row_lo, row_hi) of the
+ * n_rows_total-row CSR -- row_ptr has row_hi - row_lo + 1 entries rebased to row_ptr[0] = 0, col_idx the matching
+ * slice.  sdb_graph_expand / _device / sdb_graph_collect on shard handles are COLLECTIVE over the context's
+ * communicator (sdb_comm_init_rank / sdb_ctx_create_multi): every rank passes the same frontier and receives the
+ * complete result, identical -- order and duplicates included -- to the unsharded call.  Per hop every rank expands
+ * the sources it owns into their positions of the global output (positions = prefix sum of the all-reduced degree
+ * array) and one all-reduce assembles the next frontier; +collect de-duplicates the assembled level on every rank.
+ * One thread (or process) per rank: the calls synchronise with the host between hops. */
+sdb_status sdb_graph_load_csr_shard(sdb_ctx*, uint64_t n_rows_total, uint64_t row_lo, uint64_t row_hi,
+                                    const uint64_t* row_ptr, const uint32_t* col_idx, sdb_graph** out);
 void sdb_graph_destroy(sdb_graph*);
 /* applies hops[0..n_hops) in order to the frontier (multiset semantics: duplicates kept, frontier
  * order preserved, per-source limit honoured; 0 = no limit).  *out_ids is library-owned host

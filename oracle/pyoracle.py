@@ -316,9 +316,10 @@ class Hnsw:
                 "metric": self.metric}
 
 
-def hnsw_search_csr(graph, q, k, ef, truthy=None):
+def hnsw_search_csr(graph, q, k, ef, truthy=None, all_docs_pending=None):
     """Hnsw::knn_search (truthy=None) / knn_search_with_filter (truthy = one byte per element) over an
-    exported/imported graph. -> (ids, dist, (visited, expanded))"""
+    exported/imported graph. -> (ids, dist, (visited, expanded)).  all_docs_pending: the pending-docs bitmap of
+    HnswIndex::knn_search evaluated per element (unfiltered search only; the filtered search folds it into truthy)."""
     vec = np.ascontiguousarray(graph["vectors"], np.float32)
     n, dim = vec.shape
     nl = len(graph["layers"])
@@ -330,6 +331,16 @@ def hnsw_search_csr(graph, q, k, ef, truthy=None):
     ids = np.zeros(max(k, 1), np.uint64)
     dist = np.zeros(max(k, 1), np.float64)
     cnt = np.zeros(2, np.uint64)
+    if all_docs_pending is not None and truthy is None:
+        t = np.ascontiguousarray(all_docs_pending, np.uint8)
+        assert t.size == n
+        lib().orc_hnsw_search_csr_pending.restype = C.c_size_t
+        c = lib().orc_hnsw_search_csr_pending(_p(vec, C.c_float), C.c_size_t(n), C.c_size_t(dim),
+                                              C.c_int(METRICS[graph["metric"]]), C.c_size_t(nl), RP, CI,
+                                              C.c_int64(graph["entry_point"]), _p(q, C.c_float), C.c_size_t(k),
+                                              C.c_size_t(ef), _p(t, C.c_uint8), _p(ids, C.c_uint64),
+                                              _p(dist, C.c_double), _p(cnt, C.c_uint64))
+        return ids[:c].copy(), dist[:c].copy(), (int(cnt[0]), int(cnt[1]))
     if truthy is not None:
         t = np.ascontiguousarray(truthy, np.uint8)
         assert t.size == n

@@ -871,6 +871,10 @@ static inline size_t adj_get(const adj_src* a, uint64_t id, const uint32_t** out
 }
 
 /* HnswLayer::search  layer.rs:184-223 (pending_docs = None => are_all_docs_in_pending is false) */
+/* pending_docs of HnswLayer::search (layer.rs:184-223) evaluated ahead of time per element: all_docs_pending[e] != 0
+ * iff every document of element e is in the pending bitmap (are_all_docs_in_pending, layer.rs:320-339).  Set only for
+ * the duration of orc_hnsw_search_csr_pending (the oracle is single-threaded test infrastructure). */
+static const uint8_t* g_all_docs_pending = NULL;
 static void layer_search(const float* vectors, size_t dim, int metric, const adj_src* adj, const float* q,
                          orc_dpq* candidates, vset* visited, orc_dpq* w, size_t ef, uint64_t* counters) {
   double fq = 1.7976931348623157e308; /* f64::MAX */
@@ -889,7 +893,8 @@ static void layer_search(const float* vectors, size_t dim, int metric, const adj
       double ed = orc_vec_distance_f32(metric, vectors + e * dim, q, dim);
       if (counters) counters[0]++;
       if (ed < fq || w->n < ef) {
-        dpq_push(candidates, ed, e);
+        /* layer.rs:209: an element whose documents ALL have pending updates still enters w, but is not expanded */
+        if (!g_all_docs_pending || !g_all_docs_pending[e]) dpq_push(candidates, ed, e);
         dpq_push(w, ed, e);
         if (w->n > ef) {
           double dd;
@@ -1194,6 +1199,17 @@ size_t orc_hnsw_search_csr(const float* vectors, size_t n, size_t dim, int metri
   size_t r = hnsw_search_csr_vs(vectors, n, dim, metric, n_layers, row_ptr, col_idx, entry_point, q, k, ef,
                                 out_ids, out_dist, counters, &lv);
   free(lv.stamp);
+  return r;
+}
+/* Hnsw::knn_search with pending_docs = Some(..)  hnsw/mod.rs:459-482 (search_ep passes the bitmap down too) */
+size_t orc_hnsw_search_csr_pending(const float* vectors, size_t n, size_t dim, int metric, size_t n_layers,
+                                   const uint64_t* const* row_ptr, const uint32_t* const* col_idx, int64_t entry_point,
+                                   const float* q, size_t k, size_t ef, const uint8_t* all_docs_pending,
+                                   uint64_t* out_ids, double* out_dist, uint64_t* counters) {
+  g_all_docs_pending = all_docs_pending;
+  size_t r = orc_hnsw_search_csr(vectors, n, dim, metric, n_layers, row_ptr, col_idx, entry_point, q, k, ef, out_ids,
+                                 out_dist, counters);
+  g_all_docs_pending = NULL;
   return r;
 }
 static size_t hnsw_search_csr_vs(const float* vectors, size_t n, size_t dim, int metric, size_t n_layers,

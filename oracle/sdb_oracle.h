@@ -156,6 +156,12 @@ size_t orc_hnsw_search_csr_filtered(const float* vectors, size_t n, size_t dim, 
                                     const uint64_t* const* row_ptr, const uint32_t* const* col_idx,
                                     int64_t entry_point, const float* q, size_t k, size_t ef, const uint8_t* truthy,
                                     uint64_t* out_ids, double* out_dist, uint64_t* counters /* [2] nullable */);
+/* Hnsw::knn_search with a pending-docs bitmap (hnsw/mod.rs:459-482, layer.rs:209,320-339): all_docs_pending[e] != 0
+ * iff every document of element e has a pending update -- such an element enters w but is never expanded */
+size_t orc_hnsw_search_csr_pending(const float* vectors, size_t n, size_t dim, int metric, size_t n_layers,
+                                   const uint64_t* const* row_ptr, const uint32_t* const* col_idx, int64_t entry_point,
+                                   const float* q, size_t k, size_t ef, const uint8_t* all_docs_pending,
+                                   uint64_t* out_ids, double* out_dist, uint64_t* counters /* [2] nullable */);
 /* TestCollection::knn  hnsw/mod.rs:1186-1197: brute force through KnnResultBuilder, docs = row ids */
 size_t orc_vec_knn_f32(const float* corpus, size_t n, size_t dim, int metric, const float* q, size_t k,
                        uint64_t* out_ids, double* out_dist);

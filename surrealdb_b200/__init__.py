@@ -6,7 +6,7 @@ hand-written sm_100a CUDA in surrealdb_b200/csrc.
 """
 from ._lib import SdbError, SO_PATH  # noqa: F401
 from .engine import Context, VectorColumn  # noqa: F401
-from .operators import Distance, KnnBruteForceLegacy, KnnContext, KnnTopK  # noqa: F401
+from .operators import Distance, KnnBruteForceLegacy, KnnContext, KnnScan, KnnTopK  # noqa: F401
 from .graph import CsrGraph, GraphEdgeScan, GraphStore  # noqa: F401
 from .hnsw import HnswIndex  # noqa: F401
 

@@ -98,14 +98,15 @@ static std::vector<Rung> build_rungs(Corpus* c, uint32_t k, sdb_screen* first) {
   sdb_screen scr = c->screen;
   if (scr == SDB_SCREEN_AUTO)
     scr = !screen_tc_available() ? SDB_SCREEN_SIMT_F32
-                                 : (int8_ok && c->max_rel_qerr <= 0.012f ? SDB_SCREEN_TC_INT8 : SDB_SCREEN_TC_BF16);
+                                 : (int8_ok && c->max_rel_qerr <= 0.02f ? SDB_SCREEN_TC_INT8 : SDB_SCREEN_TC_BF16);
   if (scr == SDB_SCREEN_TC_INT8 && !int8_ok) scr = SDB_SCREEN_TC_BF16;
   if (scr == SDB_SCREEN_TC_BF16 && (!screen_tc_available() || !c->d_bf16)) scr = SDB_SCREEN_SIMT_F32;
   const bool screenable = c->metric == SDB_COSINE || c->metric == SDB_EUCLIDEAN;
   if (c->dtype == SDB_F64 || c->special_overflow || k > 256 || !screenable) scr = SDB_SCREEN_NONE_EXACT;
   *first = scr;
   std::vector<Rung> r;
-  if (scr == SDB_SCREEN_TC_INT8) r = {{SDB_SCREEN_TC_INT8, 4096}, {SDB_SCREEN_TC_BF16, 4096}, {SDB_SCREEN_TC_BF16, 16384}};
+  if (scr == SDB_SCREEN_TC_INT8)
+    r = {{SDB_SCREEN_TC_INT8, 4096}, {SDB_SCREEN_TC_INT8, 16384}, {SDB_SCREEN_TC_BF16, 4096}, {SDB_SCREEN_TC_BF16, 16384}};
   else if (scr == SDB_SCREEN_TC_BF16) r = {{SDB_SCREEN_TC_BF16, 4096}, {SDB_SCREEN_TC_BF16, 16384}};
   else if (scr == SDB_SCREEN_SIMT_F32) r = {{SDB_SCREEN_SIMT_F32, 4096}};
   return r;

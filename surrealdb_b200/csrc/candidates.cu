@@ -518,89 +518,94 @@ sdb_status cand_select(Corpus* c, uint32_t nq, uint32_t k, bool drop_invalid, ui
 }
 
 // ------------------------------------------------------------------------------------------------
-// exact re-rank.  Work unit = (query, group of 128 entries): block (x = query, y = group), each warp takes 32 entries
-// (candidates first, then the special rows) and walks their rows column-chunk by column-chunk: 32 coalesced 128-byte
-// row segments are requested back to back (all 32 loads in flight before the first is consumed -- the kernel is bound
-// by the latency of these gathers, not by the f64 arithmetic), transposed through shared memory, and every lane then
-// accumulates ITS row strictly left to right in the reference's arithmetic.  Candidate counts vary per query by
-// orders of magnitude (a handful ... a whole cluster), hence the flat (query, group) decomposition: groups beyond a
-// query's count exit at once.
+// exact re-rank.  Work unit = (query, group of 128 entries): blocks (x = query, y = 0..3) stride over the groups of
+// their query; each warp takes 32 entries (candidates first, then the special rows) and walks their rows 64 columns at
+// a time: 64 coalesced 128-byte row segments are requested back to back (all in flight before the first is consumed --
+// the kernel is bound by the latency of these gathers, not by the f64 arithmetic), transposed through shared memory,
+// and every lane then accumulates ITS row strictly left to right in the reference's arithmetic.  Candidate counts
+// vary per query by orders of magnitude (a handful ... a whole cluster).
 constexpr uint32_t QCHUNK = 1024;  // query columns staged in shared memory per step
 
-template <typename T, int WARPS>
+constexpr uint32_t RR_GROUPS_Y = 4;  // blocks per query; block y takes the groups y, y + 4, ... of its query
+
+template <typename T, int WARPS, int COLS>
 __global__ void __launch_bounds__(WARPS * 32) cand_rerank_kernel(
     const T* __restrict__ rows, uint32_t dim, int metric, const double* __restrict__ mag,
     const double* __restrict__ q64, const double* __restrict__ qmag, const uint32_t* __restrict__ qflags,
     const Cand* __restrict__ cand, const uint32_t* __restrict__ cnt, uint32_t cap, const uint32_t* __restrict__ special,
     uint32_t n_special, uint64_t* __restrict__ rr_key, double* __restrict__ rr_dist, uint32_t* __restrict__ rr_row,
     uint32_t rr_stride) {
-  __shared__ T tile[WARPS][32][33];
+  constexpr int NL = COLS / 32;  // 128-byte segments per row and step
+  __shared__ T tile[WARPS][32][COLS + 1];
   __shared__ double s_q[QCHUNK];
   const uint32_t q = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t n_c = cnt[q] < cap ? cnt[q] : cap;
   const uint32_t n_e = n_c + n_special;
-  const uint32_t e_first = blockIdx.y * (WARPS * 32);
-  if (e_first >= n_e) return;  // uniform per block
   const bool q_nan = (qflags[q] & 2u) != 0;
   const double qm = qmag[q];
-  const uint32_t e = e_first + warp * 32 + lane;
-  uint32_t my_row = NO_ROW;
-  if (e < n_c) my_row = cand[(size_t)q * cap + e].row;
-  else if (e < n_e) my_row = special[e - n_c];
-  const bool warp_active = e_first + warp * 32 < n_e;
-  ExactAcc acc;
-  for (uint32_t cb = 0; cb < dim; cb += QCHUNK) {
-    const uint32_t cw = dim - cb < QCHUNK ? dim - cb : QCHUNK;
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < cw; i += blockDim.x) s_q[i] = q64[(size_t)q * dim + cb + i];
-    __syncthreads();
-    if (!warp_active) continue;
-    const T* base = rows + cb;
-    for (uint32_t c0 = 0; c0 < cw; c0 += 32) {
-      const uint32_t c = c0 + lane;
-      T vals[32];
+  for (uint32_t e_first = blockIdx.y * (WARPS * 32); e_first < n_e; e_first += gridDim.y * (WARPS * 32)) {  // uniform per block
+    const uint32_t e = e_first + warp * 32 + lane;
+    uint32_t my_row = NO_ROW;
+    if (e < n_c) my_row = cand[(size_t)q * cap + e].row;
+    else if (e < n_e) my_row = special[e - n_c];
+    const bool warp_active = e_first + warp * 32 < n_e;
+    ExactAcc acc;
+    for (uint32_t cb = 0; cb < dim; cb += QCHUNK) {
+      const uint32_t cw = dim - cb < QCHUNK ? dim - cb : QCHUNK;
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < cw; i += blockDim.x) s_q[i] = q64[(size_t)q * dim + cb + i];
+      __syncthreads();
+      if (!warp_active) continue;
+      const T* base = rows + cb;
+      for (uint32_t c0 = 0; c0 < cw; c0 += COLS) {
+        T vals[32 * NL];
 #pragma unroll
-      for (int r = 0; r < 32; r++) {  // 32 independent gathers in flight
-        const uint32_t row = __shfl_sync(0xffffffffu, my_row, r);
-        vals[r] = (row != NO_ROW && c < cw) ? __ldg(base + (size_t)row * dim + c) : T(0);
-      }
+        for (int r = 0; r < 32; r++) {  // 32 x NL independent 128-byte gathers in flight
+          const uint32_t row = __shfl_sync(0xffffffffu, my_row, r);
 #pragma unroll
-      for (int r = 0; r < 32; r++) tile[warp][r][lane] = vals[r];
-      __syncwarp();
-      if (my_row != NO_ROW) {
-        const uint32_t lim = cw - c0 < 32u ? cw - c0 : 32u;
-        if (metric == SDB_COSINE) {
-          for (uint32_t j = 0; j < lim; j++) acc.cosine_step((double)tile[warp][lane][j], s_q[c0 + j]);
-        } else {
-          for (uint32_t j = 0; j < lim; j++) acc.euclid_step((double)tile[warp][lane][j], s_q[c0 + j]);
+          for (int h = 0; h < NL; h++) {
+            const uint32_t c = c0 + h * 32 + lane;
+            vals[r * NL + h] = (row != NO_ROW && c < cw) ? __ldg(base + (size_t)row * dim + c) : T(0);
+          }
         }
+#pragma unroll
+        for (int r = 0; r < 32; r++)
+#pragma unroll
+          for (int h = 0; h < NL; h++) tile[warp][r][h * 32 + lane] = vals[r * NL + h];
+        __syncwarp();
+        if (my_row != NO_ROW) {
+          const uint32_t lim = cw - c0 < (uint32_t)COLS ? cw - c0 : (uint32_t)COLS;
+          if (metric == SDB_COSINE) {
+            for (uint32_t j = 0; j < lim; j++) acc.cosine_step((double)tile[warp][lane][j], s_q[c0 + j]);
+          } else {
+            for (uint32_t j = 0; j < lim; j++) acc.euclid_step((double)tile[warp][lane][j], s_q[c0 + j]);
+          }
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
-  }
-  if (my_row != NO_ROW) {
-    const double d = metric == SDB_COSINE ? cosine_finish(acc, mag[my_row], qm, q_nan) : euclid_finish(acc, q_nan);
-    const size_t o = (size_t)q * rr_stride + e;
-    rr_key[o] = dist_key(d);
-    rr_dist[o] = d;
-    rr_row[o] = my_row;
+    if (my_row != NO_ROW) {
+      const double d = metric == SDB_COSINE ? cosine_finish(acc, mag[my_row], qm, q_nan) : euclid_finish(acc, q_nan);
+      const size_t o = (size_t)q * rr_stride + e;
+      rr_key[o] = dist_key(d);
+      rr_dist[o] = d;
+      rr_row[o] = my_row;
+    }
   }
 }
 
 sdb_status cand_rerank(Corpus* c, uint32_t nq, cudaStream_t st) {
-  // groups of 128 entries per query: enough for the longest possible list; empty groups return immediately
-  const uint32_t groups = (c->sc_cap + c->n_special + 127) / 128;
-  const dim3 grid(nq, groups ? groups : 1);
+  const dim3 grid(nq, RR_GROUPS_Y);
   if (c->dtype == SDB_F32)
-    cand_rerank_kernel<float, 4><<<grid, 128, 0, st>>>((const float*)c->d_rows, c->dim, (int)c->metric, c->d_mag,
-                                                       c->d_q64, c->d_qmag, c->d_qflags, c->d_cand, c->d_cand_cnt,
-                                                       c->sc_cap, c->d_special, c->n_special, c->d_rr_key,
-                                                       c->d_rr_dist, c->d_rr_row, c->rr_stride);
+    cand_rerank_kernel<float, 4, 64><<<grid, 128, 0, st>>>((const float*)c->d_rows, c->dim, (int)c->metric, c->d_mag,
+                                                           c->d_q64, c->d_qmag, c->d_qflags, c->d_cand, c->d_cand_cnt,
+                                                           c->sc_cap, c->d_special, c->n_special, c->d_rr_key,
+                                                           c->d_rr_dist, c->d_rr_row, c->rr_stride);
   else
-    cand_rerank_kernel<double, 4><<<grid, 128, 0, st>>>((const double*)c->d_rows, c->dim, (int)c->metric, c->d_mag,
-                                                        c->d_q64, c->d_qmag, c->d_qflags, c->d_cand, c->d_cand_cnt,
-                                                        c->sc_cap, c->d_special, c->n_special, c->d_rr_key,
-                                                        c->d_rr_dist, c->d_rr_row, c->rr_stride);
+    cand_rerank_kernel<double, 4, 32><<<grid, 128, 0, st>>>((const double*)c->d_rows, c->dim, (int)c->metric, c->d_mag,
+                                                            c->d_q64, c->d_qmag, c->d_qflags, c->d_cand, c->d_cand_cnt,
+                                                            c->sc_cap, c->d_special, c->n_special, c->d_rr_key,
+                                                            c->d_rr_dist, c->d_rr_row, c->rr_stride);
   count_launch(c->ctx);
   SDB_CUDA(cudaGetLastError());
   return SDB_OK;

@@ -27,6 +27,7 @@ struct NcclApi {
   ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -58,6 +59,7 @@ static sdb_status nccl_load() {
   LOAD(CommInitAll, "ncclCommInitAll");
   LOAD(CommDestroy, "ncclCommDestroy");
   LOAD(AllGather, "ncclAllGather");
+  LOAD(AllReduce, "ncclAllReduce");
   LOAD(GroupStart, "ncclGroupStart");
   LOAD(GroupEnd, "ncclGroupEnd");
   LOAD(GetErrorString, "ncclGetErrorString");
@@ -79,6 +81,17 @@ struct Comm {
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;
 };
+
+int comm_size(const Ctx* ctx) { return ctx && ctx->comm ? ctx->comm->nranks : 1; }
+int comm_rank(const Ctx* ctx) { return ctx && ctx->comm ? ctx->comm->rank : 0; }
+
+// in-place sum over the ranks of the context's communicator (no-op on a single rank); elem_bytes 4 (u32) or 8 (u64)
+sdb_status comm_allreduce_sum(Ctx* ctx, void* d_buf, size_t count, int elem_bytes, cudaStream_t st) {
+  if (!ctx->comm || ctx->comm->nranks <= 1 || count == 0) return SDB_OK;
+  SDB_TRY(nccl_load());
+  SDB_NCCL(g_nccl.AllReduce(d_buf, d_buf, count, elem_bytes == 8 ? ncclUint64 : ncclUint32, ncclSum, ctx->comm->comm, st));
+  return SDB_OK;
+}
 
 void comm_destroy(Ctx* ctx) {
   if (ctx && ctx->comm) {

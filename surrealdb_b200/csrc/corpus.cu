@@ -248,23 +248,42 @@ sdb_status corpus_finalize_device(Corpus* c) {
     float gmax;
     memcpy(&gmax, &h4[3], 4);
     if (gmax > 0.f && !getenv("SDB_NO_OUTLIER_ROWS")) {
+      // walk the occupied bins from the top while at most 64 rows lie above; an outlier group ends at a GAP: the next
+      // occupied bin below starts at less than 2/3 of the group's lowest bin.  The lowest such gap wins (largest
+      // group of rows that are all clearly detached from the bulk); without a gap nothing is special.
       uint32_t cum = 0;
-      int b = (int)RMAX_BINS - 1;
-      for (; b >= 0; b--) {
-        if (cum + h_hist[b] > 64u) break;
+      int cut = -1, below = -1;
+      int last = -1;  // lowest occupied bin seen so far
+      for (int b = (int)RMAX_BINS - 1; b >= 0; b--) {
+        if (!h_hist[b]) continue;
+        if (last >= 0 && cum <= 64u) {
+          // edges: bin x covers [edge(x), edge(x+1)); gap test between the top of bin b and the bottom of bin `last`
+          uint32_t ul = (uint32_t)last << 19, ub = (uint32_t)(b + 1) << 19;
+          float lo_last, hi_b;
+          memcpy(&lo_last, &ul, 4);
+          memcpy(&hi_b, &ub, 4);
+          if (lo_last > 1.5f * hi_b) {
+            cut = last;
+            below = b;
+          }
+        }
         cum += h_hist[b];
+        if (cum > 64u) break;
+        last = b;
       }
-      // every row in bins above b is an outlier candidate (cum <= 64 of them); thr = lower edge of bin b + 1
-      if (b >= 0 && b + 1 < (int)RMAX_BINS && cum > 0 && h4[0] + cum <= (uint32_t)SPECIAL_CAP) {
-        const uint32_t u = (uint32_t)(b + 1) << 19;
-        float thr;
-        memcpy(&thr, &u, 4);
-        if (thr > 0.f && gmax > 1.5f * thr) {
+      if (cut >= 0) {
+        uint32_t n_out = 0;
+        for (int b = cut; b < (int)RMAX_BINS; b++) n_out += h_hist[b];
+        if (n_out > 0 && h4[0] + n_out <= (uint32_t)SPECIAL_CAP) {
+          const uint32_t ut = (uint32_t)cut << 19, us = (uint32_t)(below + 1) << 19;
+          float thr, new_gmax;
+          memcpy(&thr, &ut, 4);        // rows with rmax >= thr are the outliers
+          memcpy(&new_gmax, &us, 4);   // every remaining row has rmax < this: the scale of the int8 copy
           mark_outliers_kernel<<<(unsigned)((c->n + 255) / 256), 256, 0, st>>>(d_rmax, c->n, thr, c->d_snorm, c->d_special, d_tmp);
           count_launch(ctx);
-          SDB_CUDA(cudaMemcpyAsync(d_tmp + 3, &thr, 4, cudaMemcpyHostToDevice, st));  // scale from the remaining rows
-          SDB_CUDA(cudaStreamSynchronize(st));  // `thr` lives on this stack frame
-          c->n_outliers = cum;
+          SDB_CUDA(cudaMemcpyAsync(d_tmp + 3, &new_gmax, 4, cudaMemcpyHostToDevice, st));
+          SDB_CUDA(cudaStreamSynchronize(st));  // `new_gmax` lives on this stack frame
+          c->n_outliers = n_out;
         }
       }
     }

@@ -20,6 +20,10 @@ struct Graph {
   uint64_t* d_row_ptr = nullptr;
   uint32_t* d_col_idx = nullptr;
   bool targets_in_rows = true;  // every col_idx < n_rows (required by +collect, which indexes per-row state by target)
+  // row-sharded adjacency: this rank holds rows [row_lo, row_hi) of the n_rows-row CSR; d_row_ptr is the
+  // slice rebased to 0.  An unsharded graph is the shard [0, n_rows).
+  uint64_t row_lo = 0, row_hi = 0;
+  bool sharded = false;
   std::mutex mu;
 };
 
@@ -100,8 +104,11 @@ sdb_status exclusive_scan(Ctx* ctx, const uint64_t* d_in, uint64_t* d_out, uint6
 }
 
 // ---- one hop -----------------------------------------------------------------------------------------
-__global__ void degree_kernel(const uint64_t* __restrict__ row_ptr, uint64_t n_rows, const uint32_t* __restrict__ frontier,
-                              uint64_t n_f, uint32_t limit, uint64_t* __restrict__ deg, uint32_t* __restrict__ err) {
+// row_ptr is this rank's slice [row_lo, row_hi) rebased to 0; sources owned by another rank contribute 0 here and
+// their degree arrives through the all-reduce
+__global__ void degree_kernel(const uint64_t* __restrict__ row_ptr, uint64_t n_rows, uint64_t row_lo, uint64_t row_hi,
+                              const uint32_t* __restrict__ frontier, uint64_t n_f, uint32_t limit,
+                              uint64_t* __restrict__ deg, uint32_t* __restrict__ err) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_f) return;
   const uint32_t v = frontier[i];
@@ -110,8 +117,11 @@ __global__ void degree_kernel(const uint64_t* __restrict__ row_ptr, uint64_t n_r
     deg[i] = 0;
     return;
   }
-  uint64_t d = row_ptr[v + 1] - row_ptr[v];
-  if (limit && d > limit) d = limit;
+  uint64_t d = 0;
+  if (v >= row_lo && v < row_hi) {
+    d = row_ptr[v - row_lo + 1] - row_ptr[v - row_lo];
+    if (limit && d > limit) d = limit;
+  }
   deg[i] = d;
 }
 
@@ -133,7 +143,8 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(const uint64_t* __r
                                                              const uint32_t* __restrict__ col_idx,
                                                              const uint32_t* __restrict__ frontier, uint64_t n_f,
                                                              const uint64_t* __restrict__ off /* n_f + 1 */,
-                                                             uint64_t total, uint32_t* __restrict__ out) {
+                                                             uint64_t total, uint32_t* __restrict__ out,
+                                                             uint64_t row_lo, uint64_t row_hi) {
   __shared__ uint64_t s_off[EXP_SRC_MAX];
   __shared__ uint64_t s_row[EXP_SRC_MAX];
   __shared__ uint64_t s_i0, s_i1;
@@ -150,7 +161,12 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(const uint64_t* __r
     for (uint64_t t = threadIdx.x; t < i1 - i0 + 2; t += EXP_THREADS) {
       const uint64_t i = i0 + t;
       s_off[t] = off[i];  // i <= i1 + 1 <= n_f
-      s_row[t] = i < n_f ? row_ptr[frontier[i]] : 0;
+      uint64_t rb = ~0ull;  // ~0: the source belongs to another rank's rows -- its output slots stay zero here
+      if (i < n_f) {
+        const uint64_t v = frontier[i];
+        if (v >= row_lo && v < row_hi) rb = row_ptr[v - row_lo];
+      }
+      s_row[t] = rb;
     }
   }
   __syncthreads();
@@ -167,9 +183,10 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_kernel(const uint64_t* __r
     } else {  // pathological: thousands of zero-degree sources inside this slice
       src = upper_bound_minus1(off, i0, i1 + 2, o);
       start = off[src];
-      rbeg = row_ptr[frontier[src]];
+      const uint64_t v = frontier[src];
+      rbeg = (v >= row_lo && v < row_hi) ? row_ptr[v - row_lo] : ~0ull;
     }
-    out[o] = __ldg(col_idx + rbeg + (o - start));
+    if (rbeg != ~0ull) out[o] = __ldg(col_idx + rbeg + (o - start));
     (void)src;
   }
 }
@@ -187,8 +204,12 @@ static sdb_status hop_device(Graph* g, const uint32_t* d_frontier, uint64_t n_f,
   d_total = d_off + n_f;  // off[n_f] = total: exactly the sentinel the expand kernel wants
   SDB_CUDA(cudaMallocAsync(&d_err, 4, st));
   SDB_CUDA(cudaMemsetAsync(d_err, 0, 4, st));
-  degree_kernel<<<(unsigned)((n_f + 255) / 256), 256, 0, st>>>(g->d_row_ptr, g->n_rows, d_frontier, n_f, limit, d_off, d_err);
+  degree_kernel<<<(unsigned)((n_f + 255) / 256), 256, 0, st>>>(g->d_row_ptr, g->n_rows, g->row_lo, g->row_hi, d_frontier, n_f,
+                                                               limit, d_off, d_err);
   count_launch(ctx);
+  // sharded adjacency: every source is owned by exactly one rank, so the SUM over ranks is the full degree array
+  const bool multi = g->sharded && comm_size(ctx) > 1;
+  if (multi) SDB_TRY(comm_allreduce_sum(ctx, d_off, n_f, 8, st));
   SDB_TRY(exclusive_scan(ctx, d_off, d_off, n_f, d_total, st));
   uint64_t total = 0;
   uint32_t err = 0;
@@ -209,9 +230,13 @@ static sdb_status hop_device(Graph* g, const uint32_t* d_frontier, uint64_t n_f,
   }
   if (total) {
     SDB_CUDA(cudaMallocAsync(d_out, sizeof(uint32_t) * total, st));
-    expand_kernel<<<(unsigned)((total + EXP_TILE - 1) / EXP_TILE), EXP_THREADS, 0, st>>>(g->d_row_ptr, g->d_col_idx, d_frontier,
-                                                                                       n_f, d_off, total, *d_out);
+    if (multi) SDB_CUDA(cudaMemsetAsync(*d_out, 0, sizeof(uint32_t) * total, st));
+    expand_kernel<<<(unsigned)((total + EXP_TILE - 1) / EXP_TILE), EXP_THREADS, 0, st>>>(
+        g->d_row_ptr, g->d_col_idx, d_frontier, n_f, d_off, total, *d_out, g->row_lo, g->row_hi);
     count_launch(ctx);
+    // every output slot was written by exactly one rank (the owner of its source), the others hold 0: the sum over
+    // ranks IS the next frontier, in the reference's order, on every rank -- ONE exchange per hop
+    if (multi) SDB_TRY(comm_allreduce_sum(ctx, *d_out, total, 4, st));
   }
   SDB_CUDA(cudaFreeAsync(d_off, st));
   SDB_CUDA(cudaFreeAsync(d_err, st));
@@ -257,36 +282,47 @@ using namespace sdb;
 
 extern "C" {
 
-sdb_status sdb_graph_load_csr(sdb_ctx* ctx, uint64_t n_rows, const uint64_t* row_ptr, const uint32_t* col_idx,
-                              sdb_graph** out) {
-  if (!ctx || !out || !row_ptr || n_rows >= 0xFFFFFFF0ull) return SDB_EINVAL;
+void sdb_graph_destroy(sdb_graph* g);
+
+static sdb_status graph_load(sdb_ctx* ctx, uint64_t n_rows, uint64_t row_lo, uint64_t row_hi, const uint64_t* row_ptr,
+                             const uint32_t* col_idx, bool sharded, sdb_graph** out) {
+  if (!ctx || !out || !row_ptr || n_rows >= 0xFFFFFFF0ull || row_lo > row_hi || row_hi > n_rows) return SDB_EINVAL;
   *out = nullptr;
-  const uint64_t n_edges = row_ptr[n_rows];
+  const uint64_t n_local = row_hi - row_lo;
+  if (row_ptr[0] != 0) {
+    set_error("graph load: row_ptr[0] must be 0 (a shard's slice is rebased to its first row)");
+    return SDB_EINVAL;
+  }
+  const uint64_t n_edges = row_ptr[n_local];
   if (n_edges && !col_idx) return SDB_EINVAL;
-  for (uint64_t i = 0; i < n_rows; i++)
+  for (uint64_t i = 0; i < n_local; i++)
     if (row_ptr[i + 1] < row_ptr[i]) {
       set_error("row_ptr is not non-decreasing at %llu", (unsigned long long)i);
       return SDB_EINVAL;
     }
+  std::lock_guard<std::mutex> guard(ctx->mu);
   SDB_CUDA(cudaSetDevice(ctx->device));
   sdb_graph* g = new sdb_graph();
   g->ctx = ctx;
   g->n_rows = n_rows;
   g->n_edges = n_edges;
-  cudaError_t e = cudaMalloc(&g->d_row_ptr, sizeof(uint64_t) * (n_rows + 1));
+  g->row_lo = row_lo;
+  g->row_hi = row_hi;
+  g->sharded = sharded;
+  cudaError_t e = cudaMalloc(&g->d_row_ptr, sizeof(uint64_t) * (n_local + 1));
   if (e == cudaSuccess) e = cudaMalloc(&g->d_col_idx, sizeof(uint32_t) * (n_edges ? n_edges : 1));
   if (e != cudaSuccess) {
     set_error("graph allocation failed: %s", cudaGetErrorString(e));
     sdb_graph_destroy(g);
     return SDB_ENOMEM;
   }
-  SDB_CUDA(cudaMemcpyAsync(g->d_row_ptr, row_ptr, sizeof(uint64_t) * (n_rows + 1), cudaMemcpyHostToDevice, ctx->stream));
+  SDB_CUDA(cudaMemcpyAsync(g->d_row_ptr, row_ptr, sizeof(uint64_t) * (n_local + 1), cudaMemcpyHostToDevice, ctx->stream));
   if (n_edges)
     SDB_CUDA(cudaMemcpyAsync(g->d_col_idx, col_idx, sizeof(uint32_t) * n_edges, cudaMemcpyHostToDevice, ctx->stream));
   SDB_CUDA(cudaStreamSynchronize(ctx->stream));
   {  // range check on the device copy: row_ptr consistent with the edge count; do targets stay inside the rows?
     unsigned long long bad[2] = {0, 0};
-    const sdb_status rc = csr_check(ctx, g->d_row_ptr, g->d_col_idx, n_rows, n_edges, n_rows, bad, "sdb_graph_load_csr", ctx->stream);
+    const sdb_status rc = csr_check(ctx, g->d_row_ptr, g->d_col_idx, n_local, n_edges, n_rows, bad, "sdb_graph_load_csr", ctx->stream);
     if (rc != SDB_OK || bad[0]) {
       if (rc == SDB_OK) set_error("sdb_graph_load_csr: malformed row_ptr (%llu violations)", bad[0]);
       sdb_graph_destroy(g);
@@ -296,6 +332,16 @@ sdb_status sdb_graph_load_csr(sdb_ctx* ctx, uint64_t n_rows, const uint64_t* row
   }
   *out = g;
   return SDB_OK;
+}
+
+sdb_status sdb_graph_load_csr(sdb_ctx* ctx, uint64_t n_rows, const uint64_t* row_ptr, const uint32_t* col_idx,
+                              sdb_graph** out) {
+  return graph_load(ctx, n_rows, 0, n_rows, row_ptr, col_idx, false, out);
+}
+
+sdb_status sdb_graph_load_csr_shard(sdb_ctx* ctx, uint64_t n_rows_total, uint64_t row_lo, uint64_t row_hi,
+                                    const uint64_t* row_ptr, const uint32_t* col_idx, sdb_graph** out) {
+  return graph_load(ctx, n_rows_total, row_lo, row_hi, row_ptr, col_idx, true, out);
 }
 
 void sdb_graph_destroy(sdb_graph* g) {

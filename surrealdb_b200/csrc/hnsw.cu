@@ -68,6 +68,51 @@ __global__ void hnsw_sumsq_kernel(const float* __restrict__ vec, uint32_t dim, u
   out[r] = s;
 }
 
+// Distance::calculate for VectorType::F32 (idx/trees/vector.rs:243-289,659-672), one thread per vector: the typed
+// metric of the walk applied to vectors that are NOT part of the graph -- the new_vectors of pending updates that
+// HnswIndex::search_pendings ranks by brute force (hnsw/index.rs:398-404).  Same lane structure as the walk, so a
+// vector gets the same distance whether it is reached through the graph or through the pending log.
+template <bool COSINE>
+__global__ void typed_distance_kernel(const float* __restrict__ q, const float* __restrict__ vecs, uint32_t dim, uint64_t n,
+                                      double* __restrict__ out) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const float* a = vecs + r * dim;
+  if (COSINE) {
+    float p[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pa[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t i = 0;
+    for (; i + 8 <= dim; i += 8)
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        p[j] = __fadd_rn(p[j], __fmul_rn(a[i + j], q[i + j]));
+        pa[j] = __fadd_rn(pa[j], __fmul_rn(a[i + j], a[i + j]));
+        pq[j] = __fadd_rn(pq[j], __fmul_rn(q[i + j], q[i + j]));
+      }
+    float dot = 0.f, sa = 0.f, sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      dot = __fadd_rn(dot, __fadd_rn(p[j], p[j + 4]));
+      sa = __fadd_rn(sa, __fadd_rn(pa[j], pa[j + 4]));
+      sq = __fadd_rn(sq, __fadd_rn(pq[j], pq[j + 4]));
+    }
+    for (; i < dim; i++) {
+      dot = __fadd_rn(dot, __fmul_rn(a[i], q[i]));
+      sa = __fadd_rn(sa, __fmul_rn(a[i], a[i]));
+      sq = __fadd_rn(sq, __fmul_rn(q[i], q[i]));
+    }
+    const double na = __dsqrt_rn((double)sa), nb = __dsqrt_rn((double)sq);
+    // calculate(a = search.pt, b = vector): dot and the product of norms are symmetric
+    out[r] = __dsub_rn(1.0, __ddiv_rn((double)dot, __dmul_rn(na, nb)));
+  } else {
+    float s = 0.f;
+    for (uint32_t i = 0; i < dim; i++) {
+      const float d = __fsub_rn(a[i], q[i]);
+      s = __fadd_rn(s, __fmul_rn(d, d));
+    }
+    out[r] = __dsqrt_rn((double)s);
+  }
+}
+
 // distance of this lane's row (or NO_ROW) to the query held in shared memory; all 32 lanes must call.
 template <bool COSINE>
 __device__ __forceinline__ double warp_distance(const float* __restrict__ vec, const float* __restrict__ sumsq,
@@ -197,6 +242,8 @@ struct HnswParams {
   uint32_t nq, k, ef;
   uint32_t ccap;          // capacity of the candidate window (entries)
   const uint8_t* truthy;  // non-null: knn_search_with_filter -- one byte per element (layer 0 only)
+  const uint8_t* noexp;   // non-null: pending docs -- noexp[e] != 0: every document of element e has a pending update;
+                          // the element still enters w but is never expanded (layer.rs:209, every layer)
   uint64_t* visited;
   uint32_t table_log2;
   uint32_t gen_base, gens_per_warp;
@@ -341,7 +388,7 @@ __global__ void __launch_bounds__(HN_WARPS * 32) hnsw_search_kernel(HnswParams P
                     *P.overflow = 2;
                   }
                 }
-                cn = sorted_insert(c_key, c_id, head, cn, key, idi);
+                if (!P.noexp || !P.noexp[idi]) cn = sorted_insert(c_key, c_id, head, cn, key, idi);
                 if (!truthy || truthy[idi]) {  // add_if_truthy  layer.rs:277-306
                   wn = sorted_insert(w_key, w_id, 0, wn, key, idi);
                   if (wn > ef) wn--;  // pop_last
@@ -785,8 +832,8 @@ sdb_status sdb_hnsw_select_neighbors(sdb_ctx* ctx, const float* d_vectors, uint3
 }
 
 static sdb_status hnsw_search_impl(sdb_hnsw* h, const float* queries, uint32_t nq, uint32_t k, uint32_t ef,
-                                   const uint8_t* truthy, uint64_t* out_elems, double* out_dist, uint32_t* out_count,
-                                   uint64_t* out_counters) {
+                                   const uint8_t* truthy, const uint8_t* noexp, uint64_t* out_elems, double* out_dist,
+                                   uint32_t* out_count, uint64_t* out_counters) {
   if (!h || (nq && (!queries || !out_count)) || (nq && k && (!out_elems || !out_dist))) return SDB_EINVAL;
   if (nq == 0) return SDB_OK;
   if (k == 0 || ef == 0) {  // to_vec_limit(0) underflows in the reference; we return nothing
@@ -860,6 +907,11 @@ static sdb_status hnsw_search_impl(sdb_hnsw* h, const float* queries, uint32_t n
   SDB_CUDA(cudaMallocAsync(&d_ovf, 4, st));
   SDB_CUDA(cudaMemsetAsync(d_ovf, 0, 4, st));
   SDB_CUDA(cudaMemcpyAsync(d_q, queries, sizeof(float) * (size_t)nq * h->dim, cudaMemcpyHostToDevice, st));
+  uint8_t* d_noexp = nullptr;
+  if (noexp) {
+    SDB_CUDA(cudaMallocAsync(&d_noexp, h->n ? h->n : 1, st));
+    SDB_CUDA(cudaMemcpyAsync(d_noexp, noexp, h->n, cudaMemcpyHostToDevice, st));
+  }
   uint8_t* d_truthy = nullptr;
   if (truthy) {
     SDB_CUDA(cudaMallocAsync(&d_truthy, h->n ? h->n : 1, st));
@@ -868,6 +920,7 @@ static sdb_status hnsw_search_impl(sdb_hnsw* h, const float* queries, uint32_t n
   HnswParams P;
   P.ccap = ccap;
   P.truthy = d_truthy;
+  P.noexp = d_noexp;
   P.vec = h->d_vec;
   P.sumsq = h->d_sumsq;
   P.rp = h->d_rp;
@@ -905,6 +958,7 @@ static sdb_status hnsw_search_impl(sdb_hnsw* h, const float* queries, uint32_t n
   cudaFreeAsync(d_ctr, st);
   cudaFreeAsync(d_ovf, st);
   if (d_truthy) cudaFreeAsync(d_truthy, st);
+  if (d_noexp) cudaFreeAsync(d_noexp, st);
   SDB_CUDA(cudaStreamSynchronize(st));
   SDB_CUDA(cudaGetLastError());
   if (ovf == 1) {
@@ -918,9 +972,56 @@ static sdb_status hnsw_search_impl(sdb_hnsw* h, const float* queries, uint32_t n
   return SDB_OK;
 }
 
+sdb_status sdb_vec_distance_f32(sdb_ctx* ctx, sdb_metric metric, uint32_t dim, const float* query, const float* vectors,
+                                uint64_t n, double* out) {
+  if (!ctx || !dim || (n && (!query || !vectors || !out))) return SDB_EINVAL;
+  if (metric != SDB_COSINE && metric != SDB_EUCLIDEAN) {
+    set_error("sdb_vec_distance_f32: metric %d not implemented on the GPU path", (int)metric);
+    return SDB_EUNSUPPORTED;
+  }
+  if (n == 0) return SDB_OK;
+  std::lock_guard<std::mutex> guard(ctx->mu);
+  SDB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  float *d_q = nullptr, *d_v = nullptr;
+  double* d_o = nullptr;
+  auto run = [&]() -> sdb_status {
+    SDB_CUDA(cudaMallocAsync(&d_q, sizeof(float) * dim, st));
+    SDB_CUDA(cudaMallocAsync(&d_v, sizeof(float) * n * dim, st));
+    SDB_CUDA(cudaMallocAsync(&d_o, sizeof(double) * n, st));
+    SDB_CUDA(cudaMemcpyAsync(d_q, query, sizeof(float) * dim, cudaMemcpyHostToDevice, st));
+    SDB_CUDA(cudaMemcpyAsync(d_v, vectors, sizeof(float) * n * dim, cudaMemcpyHostToDevice, st));
+    if (metric == SDB_COSINE) typed_distance_kernel<true><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_q, d_v, dim, n, d_o);
+    else typed_distance_kernel<false><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_q, d_v, dim, n, d_o);
+    count_launch(ctx);
+    SDB_CUDA(cudaGetLastError());
+    SDB_CUDA(cudaMemcpyAsync(out, d_o, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    return SDB_OK;
+  };
+  const sdb_status rc = run();
+  if (d_q) cudaFreeAsync(d_q, st);
+  if (d_v) cudaFreeAsync(d_v, st);
+  if (d_o) cudaFreeAsync(d_o, st);
+  if (cudaStreamSynchronize(st) != cudaSuccess && rc == SDB_OK) {
+    set_error("sdb_vec_distance_f32: %s", cudaGetErrorString(cudaGetLastError()));
+    return SDB_ECUDA;
+  }
+  return rc;
+}
+
 sdb_status sdb_hnsw_search(sdb_hnsw* h, const float* queries, uint32_t nq, uint32_t k, uint32_t ef, uint64_t* out_elems,
                            double* out_dist, uint32_t* out_count, uint64_t* out_counters) {
-  return hnsw_search_impl(h, queries, nq, k, ef, nullptr, out_elems, out_dist, out_count, out_counters);
+  return hnsw_search_impl(h, queries, nq, k, ef, nullptr, nullptr, out_elems, out_dist, out_count, out_counters);
+}
+
+sdb_status sdb_hnsw_search_pending(sdb_hnsw* h, const float* queries, uint32_t nq, uint32_t k, uint32_t ef,
+                                   const uint8_t* all_docs_pending, uint64_t* out_elems, double* out_dist,
+                                   uint32_t* out_count, uint64_t* out_counters) {
+  if (!all_docs_pending) {
+    set_error("sdb_hnsw_search_pending: the pending mask is NULL (use sdb_hnsw_search)");
+    return SDB_EINVAL;
+  }
+  return hnsw_search_impl(h, queries, nq, k, ef, nullptr, all_docs_pending, out_elems, out_dist, out_count, out_counters);
 }
 
 sdb_status sdb_hnsw_search_filtered(sdb_hnsw* h, const float* queries, uint32_t nq, uint32_t k, uint32_t ef,
@@ -930,7 +1031,7 @@ sdb_status sdb_hnsw_search_filtered(sdb_hnsw* h, const float* queries, uint32_t 
     set_error("sdb_hnsw_search_filtered: truthy mask is NULL (use sdb_hnsw_search)");
     return SDB_EINVAL;
   }
-  return hnsw_search_impl(h, queries, nq, k, ef, truthy, out_elems, out_dist, out_count, out_counters);
+  return hnsw_search_impl(h, queries, nq, k, ef, truthy, nullptr, out_elems, out_dist, out_count, out_counters);
 }
 
 }  // extern "C"

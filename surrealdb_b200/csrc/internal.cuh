@@ -137,6 +137,9 @@ sdb_status screen_tc_init_device();
 sdb_status candidates_init_device();
 sdb_status exact_init_device();
 void comm_destroy(Ctx* ctx);  // comm.cu
+int comm_size(const Ctx* ctx);
+int comm_rank(const Ctx* ctx);
+sdb_status comm_allreduce_sum(Ctx* ctx, void* d_buf, size_t count, int elem_bytes, cudaStream_t st);
 
 struct Cand {  // one screened candidate
   float score; // larger = closer

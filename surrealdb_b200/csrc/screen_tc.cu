@@ -359,8 +359,14 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 for (int i = 8 * g; i < 8 * g + 8; i++) {
                   if ((int)v[i] >= tau_i) {
                     const uint32_t r = (uint32_t)(row0 + cbase + c0 + i);
-                    const float sn = __ldg(snorm + r);  // invalid rows score 0 in the integer screen: drop them here
-                    if (sn == sn) {
+                    // invalid rows (skipped / special / padding) are all-zero in the int8 copy and score exactly 0:
+                    // only a zero score needs the look-up of the row's screening norm (a DRAM-latency gather)
+                    bool valid = true;
+                    if ((int)v[i] == 0) {
+                      const float sn = __ldg(snorm + r);
+                      valid = sn == sn;
+                    }
+                    if (valid) {
                       if (MODE == 2)
                         append_survivor_h(my_sub, my_cnt, my_cand, cand_cnt + q, cap, hparam + q,
                                           hist + (size_t)q * HIST_BINS, __int2float_rn((int)v[i]), r);

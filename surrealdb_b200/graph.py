@@ -40,6 +40,24 @@ class CsrGraph:
             pass
 
 
+class CsrGraphShard(CsrGraph):
+    """rows [row_lo, row_hi) of an n_rows_total-row CSR on this context's GPU (sdb_graph_load_csr_shard).  `row_ptr` /
+    `col_idx` are the WHOLE graph's arrays (host): the slice is cut and rebased here.  expand / expand_device / collect
+    on shard handles are collective over the context's communicator -- one thread or process per rank."""
+
+    def __init__(self, ctx, row_ptr, col_idx, row_lo, row_hi):
+        self.ctx = ctx
+        rp_all = np.asarray(row_ptr, np.uint64)
+        self.n_rows = rp_all.size - 1
+        e0, e1 = int(rp_all[row_lo]), int(rp_all[row_hi])
+        rp = np.ascontiguousarray(rp_all[row_lo:row_hi + 1] - np.uint64(e0))
+        ci = np.ascontiguousarray(np.asarray(col_idx, np.uint32)[e0:e1])
+        self.row_lo, self.row_hi = int(row_lo), int(row_hi)
+        self.h = C.c_void_p()
+        L.check(L.lib().sdb_graph_load_csr_shard(ctx.h, self.n_rows, self.row_lo, self.row_hi, C.c_void_p(rp.ctypes.data),
+                                                 C.c_void_p(ci.ctypes.data) if ci.size else None, C.byref(self.h)))
+
+
 def _take(out, n):
     if not out or n.value == 0:
         return np.zeros(0, np.uint32)

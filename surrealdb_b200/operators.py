@@ -7,6 +7,7 @@ meaning and error behaviour, on top of the same C ABI:
   KnnTopK(input, field, query_vector, k, distance)   core/exec/operators/knn_topk.rs:100-118
       .execute()  -> records nearest-first           knn_topk.rs:166-267
       .name() / .attrs()                              knn_topk.rs:133-144   (EXPLAIN output)
+  KnnScan(index, vector, k, ef, table_name, ...)      core/exec/operators/scan/knn.rs:68-118,135-347 (HNSW-backed)
   KnnContext: record id -> distance hand-back         core/exec/function/index.rs:289-314
 
 Records are dicts with an "id"; `input` is any iterable yielding them in scan (record-key) order, i.e.
@@ -155,5 +156,56 @@ class KnnBruteForceLegacy(KnnTopK):
             rec = self._records[int(rows[0, j])]
             if self.knn_context is not None and isinstance(rec, dict) and "id" in rec:
                 self.knn_context.insert(rec["id"], float(dist[0, j]))
+            out.append(rec)
+        return out
+
+
+class KnnScan:
+    """HNSW-backed KNN scan operator: `WHERE emb <|k,ef|> $q` with an HNSW index (scan/knn.rs:68-118,135-347).
+    `index` is the device-resident index (surrealdb_b200.hnsw.HnswIndex) with `.name`; `records` maps a vector id
+    (doc id / record key) to the record the scan yields (HnswDocs::get_thing + fetch_and_filter_records_batch).
+    residual_cond: optional predicate over records pushed into the search so that rows failing it do not consume top-k
+    slots (scan/knn.rs:265-273 -> HnswIndex::knn_search cond_filter)."""
+
+    def __init__(self, index, vector, k, ef, table_name, records, knn_context=None, residual_cond=None,
+                 index_name=None, state_value=None):
+        self.index, self.vector = index, [float(x) for x in vector]
+        self.k, self.ef, self.table_name = int(k), int(ef), table_name
+        self.records, self.knn_context, self.residual_cond = records, knn_context, residual_cond
+        self.index_name = index_name or getattr(index, "name", "idx")
+        self.state_value = state_value
+
+    def name(self):
+        return "KnnScan"
+
+    def attrs(self):  # scan/knn.rs:110-117
+        return [("index", self.index_name), ("k", str(self.k)), ("ef", str(self.ef)),
+                ("dimension", str(len(self.vector)))]
+
+    def cardinality_hint(self):  # CardinalityHint::Bounded(k)
+        return ("Bounded", self.k)
+
+    def access_mode(self):
+        return "ReadOnly"
+
+    def execute(self):
+        from . import _lib as L
+        # check_state: the device copy must match the persisted layer versions (scan/knn.rs:258-262)
+        if self.state_value is not None and not self.index.check_state(self.state_value):
+            raise L.SdbError(L.SDB_EINVAL, "Failed to check HNSW index state: the device copy is stale (reload it)")
+        if len(self.vector) != self.index.dim:  # Vector::check_dimension  idx/trees/vector.rs:643-652
+            raise L.SdbError(L.SDB_EDIM, f"Incorrect vector dimension ({len(self.vector)}). Expected a vector of "
+                                         f"{self.index.dim} dimension.")
+        truthy = None
+        if self.residual_cond is not None:
+            truthy = {vid for vid, rec in self.records.items() if self.residual_cond(rec)}
+        res = self.index.knn_search(self.vector, self.k, self.ef, truthy_docs=truthy)
+        out = []
+        for vid, dist in res:
+            rec = self.records.get(vid)
+            if rec is None:  # HnswDocs::get_thing returned None: the doc vanished
+                continue
+            if self.knn_context is not None:
+                self.knn_context.insert(rec["id"], dist)
             out.append(rec)
         return out

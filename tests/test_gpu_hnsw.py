@@ -193,3 +193,70 @@ def test_language_test_hnsw_goldens_through_gpu(ctx):
     g = h.export()
     idx = HnswIndex(ctx, g["vectors"], g["layers"], g["entry_point"], "EUCLIDEAN", elem_docs=[[1], [2], [3]])
     assert idx.knn_search([2.0, 3.0, 4.0, 5.0], 2, 100) == [(1, 2.0), (2, 4.0)]
+
+
+def test_pending_updates_and_knn_scan_operator(ctx):
+    # HnswIndex::knn_search with a pending log (hnsw/index.rs:270-335,372-420): pending new vectors are ranked by brute
+    # force with the typed metric, the graph search receives the pending-docs bitmap (an element whose docs are all
+    # pending enters w but is not expanded, layer.rs:209), results merge in a BTreeSet<(dist, VectorId)> capped at k.
+    from surrealdb_b200 import KnnContext
+    from surrealdb_b200.hnsw import HnswIndex
+    from surrealdb_b200.operators import KnnScan
+    rng = np.random.default_rng(77)
+    dim, n = 24, 900
+    data = rng.uniform(-5, 5, (n, dim)).astype(np.float32)
+    for metric in ("euclidean", "cosine"):
+        g = build(data, metric, m=8, efc=60)
+        idx = HnswIndex(ctx, g["vectors"], g["layers"], g["entry_point"], metric)
+        q = rng.uniform(-5, 5, dim).astype(np.float32)
+        k, ef = 10, 40
+        # the 30 nearest elements get pending updates (so the bitmap matters), doc 5 is deleted, a new record arrives
+        near = np.argsort(np.linalg.norm(data - q, axis=1))[:30]
+        moved = {int(e): (data[e] + rng.normal(0, 0.05, dim)).astype(np.float32) for e in near[::2]}
+        for e, v in moved.items():
+            idx.add_pending(e, [data[e]], [v])
+        idx.add_pending(5, [data[5]], [])
+        idx.add_pending("person:new", [], [q + np.float32(0.01)])
+        idx.add_pending("person:gone", [], [q])        # added ...
+        idx.add_pending("person:gone", [q], [])        # ... and deleted again before being indexed
+        got = idx.knn_search(q, k, ef)
+        # ---- the same flow restated with the oracle's pieces ----
+        pend_docs = set(moved) | {5}
+        entries = set()
+        key = HnswIndex._vid_key
+
+        def offer(d, vid):
+            if len(entries) >= k and d > max(e[0] for e in entries):
+                return
+            entries.add((d, key(vid), vid))
+            while len(entries) > k:
+                entries.remove(max(entries, key=lambda e: (e[0], e[1])))
+        for vid, v in list(moved.items()) + [("person:new", q + np.float32(0.01))]:
+            offer(O.vec_distance_f32(metric, q, v), vid)
+        mask = np.zeros(n, np.uint8)
+        mask[list(pend_docs)] = 1
+        oi, od, _ = O.hnsw_search_csr(g, q, k, ef, all_docs_pending=mask)
+        for e, d in zip(oi, od):
+            offer(float(d), int(e))
+        want = [(vid, d) for d, _, vid in sorted(entries, key=lambda e: (e[0], e[1]))]
+        assert got == want, (metric, got, want)
+        assert any(vid == "person:new" for vid, _ in got) and all(vid != "person:gone" for vid, _ in got)
+        # ---- KnnScan operator over it (scan/knn.rs:106-118,135-347) ----
+        records = {i: {"id": f"pts:{i}"} for i in range(n)}
+        records["person:new"] = {"id": "person:new"}
+        kc = KnnContext()
+        op = KnnScan(idx, q, k, ef, "pts", records, knn_context=kc, index_name="idx_emb")
+        assert op.name() == "KnnScan" and op.cardinality_hint() == ("Bounded", k)
+        assert op.attrs() == [("index", "idx_emb"), ("k", str(k)), ("ef", str(ef)), ("dimension", str(dim))]
+        out = op.execute()
+        assert [r["id"] for r in out] == [records[vid]["id"] for vid, _ in want]
+        assert [kc[r["id"]] for r in out] == [d for _, d in want]
+        with pytest.raises(Exception, match="Incorrect vector dimension"):
+            KnnScan(idx, q[:5], k, ef, "pts", records).execute()
+        # residual condition pushed into the search: only even documents are truthy
+        idx.clear_pendings()
+        cond = lambda rec: int(rec["id"].split(":")[1]) % 2 == 0 if rec["id"].startswith("pts:") else False
+        out = KnnScan(idx, q, k, ef, "pts", records, residual_cond=cond).execute()
+        truthy = (np.arange(n) % 2 == 0).astype(np.uint8)
+        fi, fd, _ = O.hnsw_search_csr(g, q, k, ef, truthy=truthy)
+        assert [r["id"] for r in out] == [f"pts:{int(e)}" for e in fi]

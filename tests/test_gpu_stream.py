@@ -128,9 +128,9 @@ def test_outlier_rows_do_not_dictate_the_int8_scale(ctx):
     # a few rows with one dominant component: they become special rows (ranked exactly on every query) and the int8
     # copy is scaled for the others, so AUTO keeps the int8 screen; an outlier that IS the nearest neighbour is found
     rng = np.random.default_rng(23)
-    n, dim, k = 50_000, 64, 10
+    n, dim, k = 20_000, 256, 10
     corpus = rng.normal(0, 1, (n, dim)).astype(np.float32)
-    out_rows = [7, 1234, 49_999]
+    out_rows = [7, 1234, 19_999]
     for r in out_rows:
         corpus[r, 5] *= 80.0
     queries = rng.normal(0, 1, (6, dim))
@@ -284,3 +284,69 @@ def test_one_process_two_gpus():
     for q in range(3):
         r, d = O.knn_topk(corpus, queries[q], "cosine", 100)
         assert list(rows[q]) == list(r) and dist[q].tobytes() == d.tobytes()
+
+
+def _rmat(rng, bits, n_edges):
+    src = np.zeros(n_edges, np.int64)
+    dst = np.zeros(n_edges, np.int64)
+    for _ in range(bits):
+        r = rng.uniform(0, 1, n_edges)
+        src = (src << 1) | (r >= 0.76)
+        dst = (dst << 1) | (((r >= 0.57) & (r < 0.76)) | (r >= 0.95))
+    key = np.unique(src * (1 << bits) + dst)
+    src, dst = key >> bits, key & ((1 << bits) - 1)
+    rp = np.zeros((1 << bits) + 1, np.uint64)
+    rp[1:] = np.cumsum(np.bincount(src, minlength=1 << bits))
+    return rp, dst.astype(np.uint32)
+
+
+def test_sharded_graph_on_one_rank(ctx):
+    # a shard covering a sub-range of the rows on a single rank: sources outside the range expand to nothing here
+    from surrealdb_b200.graph import CsrGraph, CsrGraphShard, expand
+    rng = np.random.default_rng(61)
+    rp, ci = _rmat(rng, 12, 40_000)
+    whole = CsrGraph(ctx, rp, ci)
+    full_shard = CsrGraphShard(ctx, rp, ci, 0, rp.size - 1)
+    frontier = rng.integers(0, rp.size - 1, 500).astype(np.uint32)
+    want = expand([whole, whole], frontier, 7)
+    assert np.array_equal(expand([full_shard, full_shard], frontier, 7), want)
+    assert np.array_equal(want, O.graph_hop(rp, ci, O.graph_hop(rp, ci, frontier, 7), 7))
+
+
+def test_sharded_graph_two_gpus_threads():
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import threading
+    from surrealdb_b200 import Context
+    from surrealdb_b200.graph import CsrGraphShard, collect, expand
+    rng = np.random.default_rng(62)
+    rp, ci = _rmat(rng, 13, 90_000)
+    n = rp.size - 1
+    frontier = rng.integers(0, n, 300).astype(np.uint32)
+    want = frontier
+    for _ in range(3):
+        want = O.graph_hop(rp, ci, want, 5)
+    want_collect = O.graph_collect(rp, ci, frontier[:2], 1, 4, False) if hasattr(O, "graph_collect") else None
+    ctxs = Context.create_multi([0, 1])
+    cut = n // 3  # uneven shards
+    out, errs = [None, None], []
+
+    def run(r):
+        try:
+            lo, hi = (0, cut) if r == 0 else (cut, n)
+            g = CsrGraphShard(ctxs[r], rp, ci, lo, hi)
+            res = expand([g, g, g], frontier, 5)
+            col = collect(g, frontier[:2], 1, 4, False)
+            out[r] = (res, col)
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    [t.start() for t in th]
+    [t.join(120) for t in th]
+    assert not errs, errs
+    for r in range(2):
+        assert np.array_equal(out[r][0], want)
+        if want_collect is not None:
+            assert np.array_equal(out[r][1], want_collect)
+    assert np.array_equal(out[0][1], out[1][1])
