@@ -93,6 +93,13 @@ const char* sdb_last_error(void); /* thread-local; valid until the next call on 
 const char* sdb_version(void);
 void* sdb_pinned_alloc(size_t bytes); /* cudaHostAlloc: staging buffers for append / queries */
 void sdb_pinned_free(void*);
+/* Cancellation of whatever runs on this context, from any thread: the counterpart of the reference's ctx.is_done()
+ * polls (exec/operators/knn_topk.rs:186, idx/trees/hnsw/index.rs:437, hnsw/layer.rs:533).  Brute force polls between
+ * kernel phases and before every exact fallback, the HNSW walk before every query (inside the kernel), graph expansion
+ * before every hop / BFS level.  A cancelled call returns SDB_ECANCELLED and its outputs are undefined.  The flag stays
+ * up until sdb_ctx_cancel_reset.  (sdb_knn_bruteforce additionally takes a per-call flag.) */
+void sdb_ctx_cancel(sdb_ctx*);
+void sdb_ctx_cancel_reset(sdb_ctx*);
 /* total kernels launched through this context since creation (bench's gpu_launches) */
 uint64_t sdb_ctx_kernel_launches(const sdb_ctx*);
 /* the cudaStream_t every kernel of this context is launched on (so a harness can bracket calls with
@@ -114,6 +121,13 @@ sdb_status sdb_corpus_append_synthetic(sdb_corpus*, uint64_t seed, uint64_t firs
  * extract_vector, knn_topk.rs:274-288; residual WHERE filter, planner/select.rs:1642-1652).
  * skip[i] != 0 excludes row i.  May be called again to change the mask. */
 sdb_status sdb_corpus_set_skip(sdb_corpus*, const uint8_t* skip, uint64_t n);
+/* Tombstones: the rows (scan positions) are excluded from every later search, as if the reference's TableScan no
+ * longer yielded them (a DELETE, or the old version of an UPDATE whose new version is appended at the end of the
+ * column).  Works on a finalized corpus without re-finalizing (skip mask + NaN screening norm + zeroed int8 row) and
+ * before finalize (skip mask only).  Must not race with searches.  Row numbers of the remaining rows do not change;
+ * the caller compacts (new corpus) when the tombstones pile up, or when the table version moved (KnnTopK has no
+ * persistent state of its own: the cached column is keyed by (ns, db, table, field, table version)). */
+sdb_status sdb_corpus_remove(sdb_corpus*, const uint64_t* row_ids, uint64_t n);
 /* builds per-row exact f64 magnitudes, f32 screening norms, the bf16 screen copy and the special-row
  * list.  Must be called after the last append and before searching. */
 sdb_status sdb_corpus_finalize(sdb_corpus*);
@@ -121,6 +135,11 @@ uint64_t sdb_corpus_rows(const sdb_corpus*);
 /* copies rows [first_row, first_row + n) of the device-resident master copy back to host memory (n x dim of the
  * corpus dtype): lets a harness check results against exactly the bytes the kernels read */
 sdb_status sdb_corpus_read_rows(sdb_corpus*, uint64_t first_row, uint64_t n, void* out);
+/* order p of Distance::Minkowski(p) (catalog/schema/index.rs:247-284; fnc/util/math/vector.rs:163-174); default 3.
+ * MINKOWSKI goes through pow(): CUDA's libm here, the platform libm in the reference -- each call agrees to within an
+ * ulp or two, so Minkowski distances are equal to ~1e-14 relative rather than bit for bit (every other metric is
+ * bit-exact). */
+sdb_status sdb_corpus_set_minkowski_order(sdb_corpus*, double order);
 sdb_status sdb_corpus_set_screen(sdb_corpus*, sdb_screen);
 /* schedule of the tensor-core screens (results are identical; tuning / A-B only).  streaming = 1 (default): a scored
  * sample seeds the thresholds, then ONE launch streams the rest of the corpus while refiner warps raise the thresholds
@@ -189,7 +208,7 @@ sdb_status sdb_knn_sharded_multi(sdb_corpus* const* shards, int n_shards, const 
  *      vector::distance::* / vector::similarity::* / vector::dot / vector::magnitude (fnc/vector.rs:25-143,
  *      fnc/util/math/vector.rs:61-314) in `SELECT vector::similarity::cosine(emb, $q) FROM t`.
  * fn: an sdb_metric id (= what Distance::compute returns for it: COSINE -> cosine DISTANCE, PEARSON -> the
- * similarity; MINKOWSKI / JACCARD unsupported) or one of sdb_vector_fn.  out: host, one f64 per row in scan order,
+ * similarity, JACCARD -> the similarity, MINKOWSKI with the corpus' order) or one of sdb_vector_fn.  out: host, one f64 per row in scan order,
  * bit-identical to the reference's sequential f64 arithmetic; skipped rows get NaN.  query: host, dim doubles
  * (ignored for SDB_FN_MAGNITUDE). */
 typedef enum { SDB_FN_SIMILARITY_COSINE = 16, SDB_FN_DOT = 17, SDB_FN_MAGNITUDE = 18 } sdb_vector_fn;

@@ -283,6 +283,8 @@ DEF_FAST(orc_f32row_cosine_distance, orc_f32row_euclidean, orc_f32row_magnitude,
 
 /* all-Float fast paths of the remaining Distance::compute metrics (same op order as orc_num_* on Floats);
  * `row` is f32 or f64, `q` f64.  Used by orc_knn_topk for the metrics the GPU serves through its exact kernel. */
+static double g_minkowski_p = 3.0;
+void orc_set_minkowski_order(double p) { g_minkowski_p = p; }
 #define DEF_MORE(SUFFIX, T)                                                                      \
   static double fast_manhattan_##SUFFIX(const T* a, const double* b, size_t n) {                 \
     double s = 0.0;                                                                              \
@@ -312,6 +314,30 @@ DEF_FAST(orc_f32row_cosine_distance, orc_f32row_euclidean, orc_f32row_magnitude,
     const double sd1 = n == 0 ? NAN : (n == 1 ? 0.0 : sqrt(d1 / (double)n));                     \
     const double sd2 = n == 0 ? NAN : (n == 1 ? 0.0 : sqrt(d2 / (double)n));                     \
     return covar / (sd1 * sd2);                                                                  \
+  }                                                                                              \
+  /* vector.rs:163-174: sum |a-b|^p, then ^(1/p); p = the Distance::Minkowski(order) of the index / operator */        \
+  static double fast_minkowski_##SUFFIX(const T* a, const double* b, size_t n) {                 \
+    double s = 0.0;                                                                              \
+    for (size_t i = 0; i < n; i++) s += pow(fabs((double)a[i] - b[i]), g_minkowski_p);           \
+    return pow(s, 1.0 / g_minkowski_p);                                                          \
+  }                                                                                              \
+  /* vector.rs:121-127 on Floats: union = set(a); every x of b already in the (growing) union counts */               \
+  static double fast_jaccard_##SUFFIX(const T* a, const double* b, size_t n) {                   \
+    double* set = (double*)malloc(sizeof(double) * (2 * n + 1));                                 \
+    size_t ns = 0, inter = 0;                                                                    \
+    for (size_t i = 0; i < n; i++) {                                                             \
+      int found = 0;                                                                             \
+      for (size_t j = 0; j < ns && !found; j++) found = N_eq(N_f(set[j]), N_f((double)a[i]));    \
+      if (!found) set[ns++] = (double)a[i];                                                      \
+    }                                                                                            \
+    for (size_t i = 0; i < n; i++) {                                                             \
+      int found = 0;                                                                             \
+      for (size_t j = 0; j < ns && !found; j++) found = N_eq(N_f(set[j]), N_f(b[i]));            \
+      if (found) inter++;                                                                        \
+      else set[ns++] = b[i];                                                                     \
+    }                                                                                            \
+    free(set);                                                                                   \
+    return (double)inter / (double)ns;                                                           \
   }
 DEF_MORE(f64, double)
 DEF_MORE(f32, float)
@@ -323,6 +349,8 @@ double orc_f64_metric(int metric, const double* a, const double* b, size_t n) {
     case ORC_CHEBYSHEV: return fast_chebyshev_f64(a, b, n);
     case ORC_HAMMING: return fast_hamming_f64(a, b, n);
     case ORC_PEARSON: return fast_pearson_f64(a, b, n);
+    case ORC_MINKOWSKI: return fast_minkowski_f64(a, b, n);
+    case ORC_JACCARD: return fast_jaccard_f64(a, b, n);
   }
   return NAN;
 }
@@ -355,6 +383,8 @@ static double row_distance(const void* corpus, int is_f64, size_t r, size_t dim,
     case ORC_CHEBYSHEV: return fast_chebyshev_f32(row, q, dim);
     case ORC_HAMMING: return fast_hamming_f32(row, q, dim);
     case ORC_PEARSON: return fast_pearson_f32(row, q, dim);
+    case ORC_MINKOWSKI: return fast_minkowski_f32(row, q, dim);
+    case ORC_JACCARD: return fast_jaccard_f32(row, q, dim);
   }
   return NAN;
 }

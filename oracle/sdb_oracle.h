@@ -64,6 +64,8 @@ int orc_num_minkowski(const orc_num* a, size_t na, const orc_num* b, size_t nb, 
 int orc_num_pearson(const orc_num* a, size_t na, const orc_num* b, size_t nb, orc_num* out);
 int orc_num_jaccard(const orc_num* a, size_t na, const orc_num* b, size_t nb, orc_num* out);
 /* Distance::compute  catalog/schema/index.rs:287-303 */
+/* order of Distance::Minkowski used by the all-Float fast paths (orc_f64_metric / orc_knn_topk); default 3 */
+void orc_set_minkowski_order(double p);
 int orc_num_distance(int metric, double minkowski_p, const orc_num* a, size_t na, const orc_num* b,
                      size_t nb, orc_num* out);
 /* Number::cmp (Int/Float only)  val/number.rs:620-680 ; returns -1/0/1 */

@@ -23,9 +23,9 @@ SCREEN = {"AUTO": 0, "SIMT_F32": 1, "TC_BF16": 2, "NONE_EXACT": 3, "TC_INT8": 4}
 # every symbol include/sdbgpu.h declares (tests/test_abi_symbols.py cross-checks this list with the header)
 ABI_SYMBOLS = [
     "sdb_ctx_create", "sdb_ctx_destroy", "sdb_last_error", "sdb_version", "sdb_pinned_alloc", "sdb_pinned_free",
-    "sdb_ctx_kernel_launches", "sdb_ctx_stream", "sdb_corpus_create", "sdb_corpus_destroy", "sdb_corpus_append",
-    "sdb_corpus_append_device", "sdb_corpus_append_synthetic", "sdb_corpus_set_skip", "sdb_corpus_finalize",
-    "sdb_corpus_rows", "sdb_corpus_read_rows", "sdb_corpus_set_screen", "sdb_corpus_set_schedule", "sdb_corpus_set_exact", "sdb_knn_bruteforce", "sdb_knn_bruteforce_device",
+    "sdb_ctx_cancel", "sdb_ctx_cancel_reset", "sdb_ctx_kernel_launches", "sdb_ctx_stream", "sdb_corpus_create", "sdb_corpus_destroy", "sdb_corpus_append",
+    "sdb_corpus_append_device", "sdb_corpus_append_synthetic", "sdb_corpus_set_skip", "sdb_corpus_remove", "sdb_corpus_finalize",
+    "sdb_corpus_rows", "sdb_corpus_read_rows", "sdb_corpus_set_minkowski_order", "sdb_corpus_set_screen", "sdb_corpus_set_schedule", "sdb_corpus_set_exact", "sdb_knn_bruteforce", "sdb_knn_bruteforce_device",
     "sdb_knn_last_stats", "sdb_knn_submit", "sdb_knn_submit_device", "sdb_knn_wait", "sdb_comm_unique_id",
     "sdb_comm_init_rank", "sdb_comm_size", "sdb_comm_rank", "sdb_ctx_create_multi", "sdb_corpus_set_row_base",
     "sdb_knn_sharded_submit", "sdb_knn_sharded_submit_device", "sdb_knn_sharded_wait", "sdb_knn_sharded_multi",
@@ -67,6 +67,10 @@ def lib():
     L.sdb_pinned_free.argtypes = [vp]
     L.sdb_ctx_create.argtypes = [i32, C.POINTER(vp)]
     L.sdb_ctx_destroy.argtypes = [vp]
+    L.sdb_ctx_cancel.argtypes = [vp]
+    L.sdb_ctx_cancel.restype = None
+    L.sdb_ctx_cancel_reset.argtypes = [vp]
+    L.sdb_ctx_cancel_reset.restype = None
     L.sdb_ctx_kernel_launches.restype = u64
     L.sdb_ctx_kernel_launches.argtypes = [vp]
     L.sdb_ctx_stream.restype = vp
@@ -77,12 +81,14 @@ def lib():
     L.sdb_corpus_append_device.argtypes = [vp, vp, u64]
     L.sdb_corpus_append_synthetic.argtypes = [vp, u64, u64, u64]
     L.sdb_corpus_set_skip.argtypes = [vp, vp, u64]
+    L.sdb_corpus_remove.argtypes = [vp, vp, u64]
     L.sdb_corpus_finalize.argtypes = [vp]
     L.sdb_corpus_rows.restype = u64
     L.sdb_corpus_rows.argtypes = [vp]
     L.sdb_corpus_read_rows.argtypes = [vp, u64, u64, vp]
     L.sdb_corpus_set_screen.argtypes = [vp, i32]
     L.sdb_corpus_set_exact.argtypes = [vp, i32]
+    L.sdb_corpus_set_minkowski_order.argtypes = [vp, C.c_double]
     L.sdb_corpus_set_schedule.argtypes = [vp, i32]
     L.sdb_knn_bruteforce.argtypes = [vp, vp, u32, u32, vp, vp, vp, vp]
     L.sdb_knn_bruteforce_device.argtypes = [vp, vp, u32, u32, u64, vp, vp, vp]

@@ -187,7 +187,7 @@ static sdb_status enqueue_batch(Corpus* c, Ticket& t) {
     const std::vector<PassDesc> passes = build_passes(c->n, cap, nq);
     bool first_pass = true;
     for (const PassDesc& p : passes) {
-      if (t.cancel && *t.cancel) {
+      if ((t.cancel && *t.cancel) || ctx_cancelled(ctx)) {
         cudaStreamSynchronize(st);
         set_error("query cancelled");
         return SDB_ECANCELLED;
@@ -254,7 +254,7 @@ static sdb_status finish_local(Corpus* c, Ticket& t, uint32_t* n_fallback, bool*
   for (uint32_t q = 0; q < nq; q++) {
     const bool failed = (t.h_flags[q] & 2u) && (c->exact || t.screen == SDB_SCREEN_NONE_EXACT);
     if (!failed && !(t.h_qflags[q] & 1u)) continue;
-    if (t.cancel && *t.cancel) {
+    if ((t.cancel && *t.cancel) || ctx_cancelled(ctx)) {
       cudaStreamSynchronize(st);
       set_error("query cancelled");
       return SDB_ECANCELLED;
@@ -306,6 +306,10 @@ static sdb_status submit_locked(Corpus* c, Ticket* t, const double* d_queries, u
   if (!c->finalized) {
     set_error("corpus not finalized (call sdb_corpus_finalize after the last append)");
     return SDB_EINVAL;
+  }
+  if ((cancel && *cancel) || ctx_cancelled(c->ctx)) {  // the poll of knn_topk.rs:186 before any work is queued
+    set_error("query cancelled");
+    return SDB_ECANCELLED;
   }
   SDB_TRY(ticket_prepare(c, *t, nq ? nq : 1));
   t->id = c->next_ticket++;
@@ -536,6 +540,13 @@ sdb_status sdb_ctx_create(int device, sdb_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   SDB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   SDB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  {
+    int* hc = nullptr;
+    SDB_CUDA(cudaHostAlloc(&hc, sizeof(int), cudaHostAllocMapped));
+    *hc = 0;
+    c->h_cancel = hc;
+    SDB_CUDA(cudaHostGetDevicePointer(&c->d_cancel, hc, 0));
+  }
   // dynamic shared-memory limits are per device: set them for THIS device now (not behind a process-wide flag)
   SDB_TRY(screen_tc_init_device());
   SDB_TRY(candidates_init_device());
@@ -558,7 +569,14 @@ void sdb_ctx_destroy(sdb_ctx* c) {
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->h_stage) cudaFreeHost(c->h_stage);
+  if (c->h_cancel) cudaFreeHost((void*)c->h_cancel);
   delete c;
+}
+void sdb_ctx_cancel(sdb_ctx* c) {
+  if (c && c->h_cancel) *c->h_cancel = 1;
+}
+void sdb_ctx_cancel_reset(sdb_ctx* c) {
+  if (c && c->h_cancel) *c->h_cancel = 0;
 }
 uint64_t sdb_ctx_kernel_launches(const sdb_ctx* c) { return c ? c->launches : 0; }
 void* sdb_ctx_stream(const sdb_ctx* c) { return c ? (void*)c->stream : nullptr; }
@@ -588,10 +606,6 @@ sdb_status sdb_corpus_create(sdb_ctx* ctx, uint32_t dim, sdb_dtype dt, sdb_metri
   if ((int)m < 0 || (int)m > (int)SDB_PEARSON) {
     set_error("unknown metric %d", (int)m);
     return SDB_EINVAL;
-  }
-  if (m == SDB_MINKOWSKI || m == SDB_JACCARD) {
-    set_error("metric %d not implemented on the GPU path (MINKOWSKI and JACCARD stay on the CPU)", (int)m);
-    return SDB_EUNSUPPORTED;
   }
   if (dt != SDB_F32 && dt != SDB_F64) return SDB_EINVAL;
   SDB_CUDA(cudaSetDevice(ctx->device));
@@ -689,9 +703,26 @@ sdb_status sdb_corpus_set_skip(sdb_corpus* c, const uint8_t* skip, uint64_t n) {
     if (!c->d_skip) SDB_CUDA(cudaMalloc(&c->d_skip, c->cap));
     SDB_CUDA(cudaMemsetAsync(c->d_skip, 0, c->cap, c->ctx->stream));
     SDB_CUDA(cudaMemcpyAsync(c->d_skip, skip, n, cudaMemcpyHostToDevice, c->ctx->stream));
-    SDB_CUDA(cudaStreamSynchronize(c->ctx->stream));
   }
+  SDB_TRY(corpus_reapply_tombstones(c, c->ctx->stream));  // rows removed earlier stay removed
+  SDB_CUDA(cudaStreamSynchronize(c->ctx->stream));
   c->finalized = false;
+  return SDB_OK;
+}
+sdb_status sdb_corpus_remove(sdb_corpus* c, const uint64_t* row_ids, uint64_t n) {
+  if (!c || (n && !row_ids)) return SDB_EINVAL;
+  if (n == 0) return SDB_OK;
+  std::lock_guard<std::mutex> g(c->mu);
+  for (uint64_t i = 0; i < n; i++)
+    if (row_ids[i] >= c->n) {
+      set_error("sdb_corpus_remove: row %llu outside the corpus (%llu rows)", (unsigned long long)row_ids[i],
+                (unsigned long long)c->n);
+      return SDB_EINVAL;
+    }
+  SDB_CUDA(cudaSetDevice(c->ctx->device));
+  SDB_CUDA(cudaStreamSynchronize(c->ctx->stream));  // no batch may be in flight while rows disappear
+  SDB_TRY(corpus_remove_device(c, row_ids, n));
+  c->n_removed += n;
   return SDB_OK;
 }
 sdb_status sdb_corpus_finalize(sdb_corpus* c) {
@@ -719,6 +750,11 @@ sdb_status sdb_corpus_read_rows(sdb_corpus* c, uint64_t first_row, uint64_t n, v
   SDB_CUDA(cudaMemcpyAsync(out, (const char*)c->d_rows + esz * first_row * c->dim, esz * n * c->dim,
                            cudaMemcpyDeviceToHost, c->ctx->copy_stream));
   SDB_CUDA(cudaStreamSynchronize(c->ctx->copy_stream));
+  return SDB_OK;
+}
+sdb_status sdb_corpus_set_minkowski_order(sdb_corpus* c, double order) {
+  if (!c || !(order == order)) return SDB_EINVAL;
+  c->minkowski_p = order;
   return SDB_OK;
 }
 sdb_status sdb_corpus_set_schedule(sdb_corpus* c, int streaming) {
@@ -861,7 +897,7 @@ sdb_status sdb_knn_bruteforce(sdb_corpus* c, const double* queries, uint32_t nq,
 
 sdb_status sdb_corpus_project(sdb_corpus* c, const double* query, int fn, double* out) {
   const bool is_metric = fn == SDB_COSINE || fn == SDB_EUCLIDEAN || fn == SDB_MANHATTAN || fn == SDB_CHEBYSHEV ||
-                         fn == SDB_HAMMING || fn == SDB_PEARSON;
+                         fn == SDB_HAMMING || fn == SDB_PEARSON || fn == SDB_MINKOWSKI || fn == SDB_JACCARD;
   if (!c || !out || (!query && fn != SDB_FN_MAGNITUDE)) return SDB_EINVAL;
   if (!is_metric && fn != SDB_FN_SIMILARITY_COSINE && fn != SDB_FN_DOT && fn != SDB_FN_MAGNITUDE) {
     set_error("vector function %d not implemented on the GPU path", fn);

@@ -4,6 +4,8 @@
 //   bf16   [cap][dim_pad]    bf16     screen copy, K-major rows = tcgen05 "B" operand via TMA
 //   mag    [cap]             f64      sqrt(sum x^2), the reference's `magnitude()` arithmetic
 //   snorm  [cap]             f32      cosine: 1/|x|, euclid: |x|^2, NaN => row never screened in
+#include <algorithm>
+
 #include "internal.cuh"
 #include "rowwalk.cuh"
 
@@ -191,6 +193,77 @@ __global__ void __launch_bounds__(256) quantize_rows_kernel(const float* __restr
     // + 2^-22: the f32 normalisation x * (1/|x|) is itself rounded; the whole figure is rounded up
     if (lane == 0) atomicMax(max_rel_bits, __float_as_uint(sqrtf(err2) * 1.0001f + 5e-7f));
   }
+}
+
+// tombstones (sdb_corpus_remove): the row is skipped by every path from now on -- skip mask for the exact kernel, NaN
+// screening norm for the screens and the re-rank's special list, and an all-zero int8 row so that the integer screen
+// scores it exactly 0 (the only score for which that screen looks up a row's validity).  No re-finalize needed.
+__global__ void or_mask_kernel(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && src[i]) dst[i] = 1;
+}
+sdb_status corpus_reapply_tombstones(Corpus* c, cudaStream_t st) {  // after the caller replaced the skip mask
+  if (!c->d_removed || !c->n) return SDB_OK;
+  if (!c->d_skip) {
+    SDB_CUDA(cudaMalloc(&c->d_skip, c->cap));
+    SDB_CUDA(cudaMemsetAsync(c->d_skip, 0, c->cap, st));
+  }
+  or_mask_kernel<<<(unsigned)((c->n + 255) / 256), 256, 0, st>>>(c->d_skip, c->d_removed, c->n);
+  count_launch(c->ctx);
+  SDB_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
+__global__ void remove_rows_kernel(const uint64_t* __restrict__ ids, uint64_t n, uint8_t* __restrict__ skip,
+                                   uint8_t* __restrict__ removed, float* __restrict__ snorm, int8_t* __restrict__ i8,
+                                   uint32_t dim_pad8) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= n) return;
+  const uint64_t r = ids[w];
+  if (lane == 0) {
+    skip[r] = 1;
+    removed[r] = 1;
+    if (snorm) snorm[r] = __int_as_float(0x7fc00000);
+  }
+  if (i8)
+    for (uint32_t c = lane; c < dim_pad8; c += 32) i8[r * dim_pad8 + c] = 0;
+}
+sdb_status corpus_remove_device(Corpus* c, const uint64_t* h_ids, uint64_t n) {
+  Ctx* ctx = c->ctx;
+  cudaStream_t st = ctx->stream;
+  if (!c->d_skip) {
+    SDB_CUDA(cudaMalloc(&c->d_skip, c->cap));
+    SDB_CUDA(cudaMemsetAsync(c->d_skip, 0, c->cap, st));
+  }
+  if (!c->d_removed) {
+    SDB_CUDA(cudaMalloc(&c->d_removed, c->cap));
+    SDB_CUDA(cudaMemsetAsync(c->d_removed, 0, c->cap, st));
+  }
+  uint64_t* d_ids = nullptr;
+  SDB_CUDA(cudaMallocAsync(&d_ids, sizeof(uint64_t) * n, st));
+  SDB_CUDA(cudaMemcpyAsync(d_ids, h_ids, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, st));
+  remove_rows_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(d_ids, n, c->d_skip, c->d_removed, c->finalized ? c->d_snorm : nullptr,
+                                                                       c->finalized ? c->d_i8 : nullptr, c->dim_pad8);
+  count_launch(ctx);
+  SDB_CUDA(cudaFreeAsync(d_ids, st));
+  if (c->finalized && c->n_special) {  // a removed special row leaves the always-exact list
+    std::vector<uint32_t> sp(c->n_special);
+    SDB_CUDA(cudaMemcpyAsync(sp.data(), c->d_special, sizeof(uint32_t) * c->n_special, cudaMemcpyDeviceToHost, st));
+    SDB_CUDA(cudaStreamSynchronize(st));
+    std::vector<uint64_t> sorted(h_ids, h_ids + n);
+    std::sort(sorted.begin(), sorted.end());
+    std::vector<uint32_t> keep;
+    for (uint32_t r : sp)
+      if (!std::binary_search(sorted.begin(), sorted.end(), (uint64_t)r)) keep.push_back(r);
+    if (keep.size() != sp.size()) {
+      if (!keep.empty())
+        SDB_CUDA(cudaMemcpyAsync(c->d_special, keep.data(), sizeof(uint32_t) * keep.size(), cudaMemcpyHostToDevice, st));
+      c->n_special = (uint32_t)keep.size();
+    }
+  }
+  SDB_CUDA(cudaStreamSynchronize(st));
+  SDB_CUDA(cudaGetLastError());
+  return SDB_OK;
 }
 
 sdb_status corpus_finalize_device(Corpus* c) {

@@ -22,7 +22,8 @@ __global__ void __launch_bounds__(WARPS * 32) exact_keys_kernel(const T* __restr
                                                                 const double* __restrict__ qmag_p,
                                                                 const uint32_t* __restrict__ qflags_p,
                                                                 uint64_t* __restrict__ keys,
-                                                                double* __restrict__ vals /* non-null: projection */) {
+                                                                double* __restrict__ vals /* non-null: projection */,
+                                                                double mink_p) {
   __shared__ T tile[WARPS][32][33];
   __shared__ double s_q[EX_QCHUNK];
   __shared__ double s_qstat[2];  // pearson: mean and (population) deviation of the query
@@ -92,6 +93,9 @@ __global__ void __launch_bounds__(WARPS * 32) exact_keys_kernel(const T* __restr
               case SDB_HAMMING:
                 for (uint32_t j = 0; j < lim; j++) acc.hamming_step((double)t[j], s_q[c0 + j]);
                 break;
+              case SDB_MINKOWSKI:
+                for (uint32_t j = 0; j < lim; j++) acc.minkowski_step((double)t[j], s_q[c0 + j], mink_p);
+                break;
               default:  // SDB_PEARSON
                 if (phase == 0) {
                   for (uint32_t j = 0; j < lim; j++) acc.sum_step((double)t[j]);
@@ -126,6 +130,7 @@ __global__ void __launch_bounds__(WARPS * 32) exact_keys_kernel(const T* __restr
           case SDB_FN_MAGNITUDE: d = mag[r]; break;                             // vector.rs:301-314
           case SDB_EUCLIDEAN: d = euclid_finish(acc, q_nan); break;
           case SDB_MANHATTAN: d = canon_nan(acc.acc, acc.nan_in || q_nan); break;
+          case SDB_MINKOWSKI: d = canon_nan(pow(acc.acc, __ddiv_rn(1.0, mink_p)), acc.nan_in || q_nan); break;
           case SDB_CHEBYSHEV:
           case SDB_HAMMING: d = acc.acc; break;
           default: {  // pearson: covar/len / (sd1 * sd2)
@@ -140,6 +145,83 @@ __global__ void __launch_bounds__(WARPS * 32) exact_keys_kernel(const T* __restr
       if (keys) keys[r] = key;
     }
   }
+}
+
+// ---- Jaccard (vector.rs:121-127): set semantics over the VALUES of the two vectors, so it needs a whole row and the
+// whole query at once instead of a column stream.  union = set(row); every query element already present in the
+// (growing) union counts towards the intersection; result = |intersection| / |union|.  Restated without a hash set:
+//   in_row[j]  = q_j equals some row element            dup[j] = q_j equals an earlier query element (per query, once)
+//   inter = #{j : in_row[j] or dup[j]}                  union = distinct(row) + #{j : not in_row[j] and not dup[j]}
+// Number equality on floats: same bits, or both zero (val/number.rs PartialEq; NaN == NaN when the payloads agree).
+// One warp per row, O(dim^2 / 32) comparisons per lane: a niche metric served for completeness, not for speed.
+__device__ __forceinline__ bool num_eq_f64(double a, double b) {
+  return __double_as_longlong(a) == __double_as_longlong(b) || (a == 0.0 && b == 0.0);
+}
+__global__ void jaccard_qdup_kernel(const double* __restrict__ q64, uint32_t dim, uint8_t* __restrict__ dup) {
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < dim; j += gridDim.x * blockDim.x) {
+    bool d = false;
+    for (uint32_t i = 0; i < j && !d; i++) d = num_eq_f64(q64[i], q64[j]);
+    dup[j] = d ? 1 : 0;
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(128) jaccard_keys_kernel(const T* __restrict__ rows, uint32_t dim, uint64_t n,
+                                                           const uint8_t* __restrict__ skip,
+                                                           const double* __restrict__ q64, const uint8_t* __restrict__ qdup,
+                                                           uint64_t* __restrict__ keys, double* __restrict__ vals) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t r = warp0; r < n; r += n_warps) {
+    if (skip && skip[r]) {
+      if (lane == 0) {
+        if (keys) keys[r] = KEY_SKIPPED;
+        if (vals) vals[r] = __longlong_as_double(0x7FF8000000000000ll);
+      }
+      continue;
+    }
+    const T* x = rows + r * dim;
+    uint32_t distinct = 0, inter = 0, fresh = 0;
+    for (uint32_t i = lane; i < dim; i += 32) {
+      const double xi = (double)x[i];
+      bool seen = false;
+      for (uint32_t i2 = 0; i2 < i && !seen; i2++) seen = num_eq_f64((double)x[i2], xi);
+      distinct += seen ? 0 : 1;
+    }
+    for (uint32_t j = lane; j < dim; j += 32) {
+      const double qj = q64[j];
+      bool in_row = false;
+      for (uint32_t i = 0; i < dim && !in_row; i++) in_row = num_eq_f64((double)x[i], qj);
+      if (in_row || qdup[j]) inter++;
+      else fresh++;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      distinct += __shfl_xor_sync(0xffffffffu, distinct, o);
+      inter += __shfl_xor_sync(0xffffffffu, inter, o);
+      fresh += __shfl_xor_sync(0xffffffffu, fresh, o);
+    }
+    if (lane == 0) {
+      const double d = __ddiv_rn((double)inter, (double)(distinct + fresh));  // (intersection_size / union.len() as f64)
+      if (keys) keys[r] = dist_key(d);
+      if (vals) vals[r] = d;
+    }
+  }
+}
+static sdb_status jaccard_launch(Corpus* c, const double* d_q64, uint64_t* d_keys, double* d_vals, cudaStream_t st) {
+  Ctx* ctx = c->ctx;
+  uint8_t* d_dup = nullptr;
+  SDB_CUDA(cudaMallocAsync(&d_dup, c->dim, st));
+  jaccard_qdup_kernel<<<(c->dim + 127) / 128, 128, 0, st>>>(d_q64, c->dim, d_dup);
+  const int grid = ctx->sm_count * 16;
+  if (c->dtype == SDB_F32)
+    jaccard_keys_kernel<float><<<grid, 128, 0, st>>>((const float*)c->d_rows, c->dim, c->n, c->d_skip, d_q64, d_dup, d_keys, d_vals);
+  else
+    jaccard_keys_kernel<double><<<grid, 128, 0, st>>>((const double*)c->d_rows, c->dim, c->n, c->d_skip, d_q64, d_dup, d_keys, d_vals);
+  count_launch(ctx, 2);
+  SDB_CUDA(cudaFreeAsync(d_dup, st));
+  SDB_CUDA(cudaGetLastError());
+  return SDB_OK;
 }
 
 // ---- exact radix select over the 96-bit composite (key, row), MSB first, 12 passes of 8 bits --------
@@ -306,15 +388,17 @@ sdb_status exact_query(Corpus* c, const double* d_q64, const double* d_qmag, con
   uint64_t* g_key = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(c->d_sel) + ((sizeof(SelState) + 63) / 64) * 64);
   uint32_t* g_row = reinterpret_cast<uint32_t*>(g_key + 4096);
   const uint64_t n = c->n;
-  if (n) {
+  if (n && c->metric == SDB_JACCARD) {
+    SDB_TRY(jaccard_launch(c, d_q64, c->d_ex_key, nullptr, st));
+  } else if (n) {
     const int grid = ctx->sm_count * 8;
     if (c->dtype == SDB_F32)
       exact_keys_kernel<float, 4><<<grid, 128, 0, st>>>((const float*)c->d_rows, c->dim, n, (int)c->metric, c->d_mag,
-                                                        c->d_skip, d_q64, d_qmag, d_qflags, c->d_ex_key, nullptr);
+                                                        c->d_skip, d_q64, d_qmag, d_qflags, c->d_ex_key, nullptr, c->minkowski_p);
     else
       exact_keys_kernel<double, 4><<<grid, 128, 0, st>>>((const double*)c->d_rows, c->dim, n, (int)c->metric,
                                                          c->d_mag, c->d_skip, d_q64, d_qmag, d_qflags, c->d_ex_key,
-                                                         nullptr);
+                                                         nullptr, c->minkowski_p);
     count_launch(ctx);
   }
   sel_init_kernel<<<1, 256, 0, st>>>(sel, k);
@@ -341,13 +425,14 @@ sdb_status exact_project(Corpus* c, int fn, double* d_vals, cudaStream_t st) {
   Ctx* ctx = c->ctx;
   const uint64_t n = c->n;
   if (!n) return SDB_OK;
+  if (fn == SDB_JACCARD) return jaccard_launch(c, c->d_q64, nullptr, d_vals, st);
   const int grid = ctx->sm_count * 8;
   if (c->dtype == SDB_F32)
     exact_keys_kernel<float, 4><<<grid, 128, 0, st>>>((const float*)c->d_rows, c->dim, n, fn, c->d_mag, c->d_skip,
-                                                      c->d_q64, c->d_qmag, c->d_qflags, nullptr, d_vals);
+                                                      c->d_q64, c->d_qmag, c->d_qflags, nullptr, d_vals, c->minkowski_p);
   else
     exact_keys_kernel<double, 4><<<grid, 128, 0, st>>>((const double*)c->d_rows, c->dim, n, fn, c->d_mag, c->d_skip,
-                                                       c->d_q64, c->d_qmag, c->d_qflags, nullptr, d_vals);
+                                                       c->d_q64, c->d_qmag, c->d_qflags, nullptr, d_vals, c->minkowski_p);
   count_launch(ctx);
   SDB_CUDA(cudaGetLastError());
   return SDB_OK;

@@ -37,6 +37,12 @@ struct ExactAcc {
     const bool eq = (__double_as_longlong(x) == __double_as_longlong(q)) || (x == 0.0 && q == 0.0);
     acc = __dadd_rn(acc, eq ? 0.0 : 1.0);  // exact: an integer count below 2^53
   }
+  //   minkowski: vector.rs:163-174   acc = acc + |x - q|^p ; finish: acc^(1/p).  pow() is CUDA's libm here and the
+  //              platform libm in the reference: each call agrees to within an ulp or two, not bit for bit.
+  __device__ __forceinline__ void minkowski_step(double x, double q, double p) {
+    nan_in |= (x != x);
+    acc = __dadd_rn(acc, pow(fabs(__dsub_rn(x, q)), p));
+  }
   //   pearson  : vector.rs:133-146   pass A: sum x ; pass B: covar += (x-m1)*(q-m2), dev += (x-m1)^2
   __device__ __forceinline__ void sum_step(double x) {
     nan_in |= (x != x);

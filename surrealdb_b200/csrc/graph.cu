@@ -362,6 +362,11 @@ static sdb_status graph_expand_dev(sdb_graph* const* hops, uint32_t n_hops, cons
   for (uint32_t h = 0; h < n_hops && n_f; h++) {
     uint32_t* d_next = nullptr;
     uint64_t n_next = 0;
+    if (ctx_cancelled(hops[h]->ctx)) {  // polled once per hop
+      if (owned) cudaFreeAsync(d_f, st);
+      set_error("query cancelled");
+      return SDB_ECANCELLED;
+    }
     sdb_status s = hop_device(hops[h], cur, n_f, per_source_limit, &d_next, &n_next, st);
     if (owned) cudaFreeAsync(d_f, st);
     if (s != SDB_OK) {
@@ -520,6 +525,10 @@ sdb_status sdb_graph_collect(sdb_graph* g, const uint32_t* start, uint64_t n_sta
   }
   uint32_t depth = 0;
   while (n_f && (max_depth == 0 || depth < max_depth)) {
+    if (ctx_cancelled(ctx)) {  // polled once per BFS level
+      set_error("query cancelled");
+      return SDB_ECANCELLED;
+    }
     uint32_t* d_lvl = nullptr;
     uint64_t n_lvl = 0;
     SDB_TRY(hop_device(g, d_f, n_f, 0, &d_lvl, &n_lvl, st));

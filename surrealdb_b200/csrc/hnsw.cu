@@ -252,6 +252,7 @@ struct HnswParams {
   uint32_t* out_count;
   uint64_t* out_counters;
   uint32_t* overflow;
+  const int* cancel;  // mapped host flag (sdb_ctx_cancel): polled before every query
 };
 
 template <bool COSINE>
@@ -276,6 +277,7 @@ __global__ void __launch_bounds__(HN_WARPS * 32) hnsw_search_kernel(HnswParams P
   uint32_t gen = P.gen_base + gwarp * P.gens_per_warp;
 
   for (uint32_t q = gwarp; q < P.nq; q += n_warps) {
+    if (*reinterpret_cast<const volatile int*>(P.cancel)) break;  // uniform per warp: every lane reads the same word
     // stage the query, its 8-lane sum of squares (cosine)
     for (uint32_t c = lane; c < P.dim; c += 32) s_q[c] = P.queries[(size_t)q * P.dim + c];
     __syncwarp();
@@ -936,6 +938,7 @@ static sdb_status hnsw_search_impl(sdb_hnsw* h, const float* queries, uint32_t n
   P.table_log2 = tl;
   P.gen_base = h->gen;
   P.gens_per_warp = gens_per_warp;
+  P.cancel = ctx->d_cancel;
   P.out_elems = d_elems;
   P.out_dist = d_dist;
   P.out_count = d_cnt;
@@ -961,6 +964,10 @@ static sdb_status hnsw_search_impl(sdb_hnsw* h, const float* queries, uint32_t n
   if (d_noexp) cudaFreeAsync(d_noexp, st);
   SDB_CUDA(cudaStreamSynchronize(st));
   SDB_CUDA(cudaGetLastError());
+  if (ctx_cancelled(ctx)) {  // warps stop taking new queries once the flag is up: the outputs are incomplete
+    set_error("query cancelled");
+    return SDB_ECANCELLED;
+  }
   if (ovf == 1) {
     set_error("hnsw: visited table overflow (ef too large, or filter too selective, for the per-query table)");
     return SDB_EOVERFLOW;

@@ -128,7 +128,12 @@ struct Ctx {
   void* h_stage = nullptr;       // pinned staging buffer for large device->host results (grow-only)
   size_t h_stage_bytes = 0;
   Comm* comm = nullptr;
+  // cancellation (sdb_ctx_cancel): one int in mapped pinned memory -- the host side polls it between kernel phases,
+  // long-running kernels (the HNSW walk) poll it per query through the device alias
+  volatile int* h_cancel = nullptr;
+  int* d_cancel = nullptr;
 };
+inline bool ctx_cancelled(const Ctx* ctx) { return ctx->h_cancel && *ctx->h_cancel != 0; }
 
 // per-device kernel attributes (dynamic shared-memory limits).  cudaFuncSetAttribute is per DEVICE, so these run in
 // sdb_ctx_create after cudaSetDevice -- never behind a process-wide flag (a second context on another GPU of the same
@@ -261,6 +266,8 @@ struct Corpus {
 // ---- launch wrappers (defined in the .cu files) ---------------------------------------------------
 // corpus.cu
 sdb_status corpus_finalize_device(Corpus* c);
+sdb_status corpus_remove_device(Corpus* c, const uint64_t* h_ids, uint64_t n);
+sdb_status corpus_reapply_tombstones(Corpus* c, cudaStream_t st);
 // screen_simt.cu
 sdb_status screen_simt_pass(Corpus* c, uint32_t nq, const PassDesc& p, cudaStream_t st);
 // screen_tc.cu

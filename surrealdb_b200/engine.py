@@ -47,6 +47,13 @@ class Context:
         """raw cudaStream_t (int) all kernels of this context run on"""
         return int(L.lib().sdb_ctx_stream(self.h) or 0)
 
+    def cancel(self):
+        """raise the context's cancel flag (any thread); running / later calls return SDB_ECANCELLED until cancel_reset"""
+        L.lib().sdb_ctx_cancel(self.h)
+
+    def cancel_reset(self):
+        L.lib().sdb_ctx_cancel_reset(self.h)
+
     def kernel_launches(self):
         return int(L.lib().sdb_ctx_kernel_launches(self.h))
 
@@ -100,11 +107,19 @@ class VectorColumn:
             s = np.ascontiguousarray(skip, np.uint8)
             L.check(L.lib().sdb_corpus_set_skip(self.h, _ptr(s), s.size))
 
+    def remove(self, row_ids):
+        """tombstone rows (scan positions): excluded from every later search, no re-finalize needed"""
+        ids = np.ascontiguousarray(row_ids, np.uint64)
+        L.check(L.lib().sdb_corpus_remove(self.h, _ptr(ids), ids.size))
+
     def finalize(self):
         L.check(L.lib().sdb_corpus_finalize(self.h))
 
     def set_screen(self, name):
         L.check(L.lib().sdb_corpus_set_screen(self.h, L.SCREEN[name.upper()]))
+
+    def set_minkowski_order(self, order):
+        L.check(L.lib().sdb_corpus_set_minkowski_order(self.h, float(order)))
 
     def set_schedule(self, streaming):
         """True (default): streaming tensor-core screen with in-kernel threshold refinement; False: multi-pass"""

@@ -26,8 +26,8 @@ class Distance:
     Chebyshev = "Chebyshev"
     Hamming = "Hamming"
     Pearson = "Pearson"
-    Minkowski = "Minkowski"      # not on the GPU path: VectorColumn raises SDB_EUNSUPPORTED
-    Jaccard = "Jaccard"          # idem
+    Minkowski = "Minkowski"      # exact kernel, order via VectorColumn.set_minkowski_order (pow(): ~1e-14 relative)
+    Jaccard = "Jaccard"          # exact kernel, set semantics over the values
 
 
 class KnnContext(dict):

@@ -245,11 +245,43 @@ def test_other_distance_metrics_through_the_exact_kernel(ctx, metric, dtype):
         assert col.stats()["n_fallback"] == 2
 
 
-def test_unsupported_metrics_fail_loudly(ctx):
+def test_minkowski_and_jaccard_through_the_exact_kernel(ctx):
+    # the last two catalog::Distance variants (fnc/util/math/vector.rs:120-130,163-174)
+    import ctypes as C
+    rng = np.random.default_rng(46)
+    for dim in (3, 17, 96):
+        n = 2500
+        # Jaccard: set semantics over the VALUES -> small integer alphabets give non-trivial sets and many ties
+        corpus = rng.integers(0, 12, (n, dim)).astype(np.float32)
+        corpus[3, 0] = -0.0
+        queries = rng.integers(0, 12, (3, dim)).astype(np.float64)
+        col = make_col(ctx, corpus, "JACCARD")
+        for k in (1, 10, 200):
+            check(col, corpus, queries, "JACCARD", k)   # bit-exact, ties by scan order
+        # Minkowski of order p: pow() differs by an ulp or two between CUDA's and the host's libm -> same rows
+        # (no near-ties in random data), distances equal to 1e-12 relative
+        corpus = rng.uniform(-20, 20, (n, dim)).astype(np.float32)
+        queries = rng.uniform(-20, 20, (3, dim))
+        for order in (3.0, 1.5):
+            O.lib().orc_set_minkowski_order(C.c_double(order))
+            col = make_col(ctx, corpus, "MINKOWSKI")
+            col.set_minkowski_order(order)
+            rows, dist, cnt = col.knn(queries, 10)
+            for q in range(3):
+                r, d = O.knn_topk(corpus, queries[q], "minkowski", 10)
+                assert list(rows[q]) == list(r), (dim, order, q)
+                assert np.allclose(dist[q], d, rtol=1e-12, atol=0.0)
+        O.lib().orc_set_minkowski_order(C.c_double(3.0))
+    # the reference's own KATs (surrealdb/core/tests/function.rs:3585-3593) through the column projection
+    col = make_col(ctx, np.array([[1.1, 2.2, 3.0]], np.float64), "MINKOWSKI")
+    col.set_minkowski_order(3)
+    assert abs(col.project("MINKOWSKI", np.array([4.0, 5.5, 6.6]))[0] - 4.3267487109222245) < 1e-14
+    col = make_col(ctx, np.array([[10, 20, 15, 10, 5]], np.float64), "MINKOWSKI")
+    col.set_minkowski_order(2)
+    assert abs(col.project("MINKOWSKI", np.array([12.0, 24, 18, 8, 7]))[0] - 6.082762530298219) < 1e-14
     from surrealdb_b200 import VectorColumn
-    for metric in ("MINKOWSKI", "JACCARD"):
-        with pytest.raises(Exception, match="not implemented on the GPU path"):
-            VectorColumn(ctx, 4, metric, "F32", capacity=4)
+    with pytest.raises(Exception):
+        VectorColumn(ctx, 4, "NOT_A_METRIC", "F32", capacity=4)
 
 
 def test_legacy_two_pass_bruteforce_returns_table_order(ctx):

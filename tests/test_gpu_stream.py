@@ -141,6 +141,40 @@ def test_outlier_rows_do_not_dictate_the_int8_scale(ctx):
     assert st["screen_used"] == 4 and st["n_special_rows"] == len(out_rows) and st["n_fallback"] == 0, st
 
 
+def test_tombstones_without_refinalize(ctx):
+    # sdb_corpus_remove: rows disappear from every later search (all screens and the exact kernel) without a re-finalize
+    rng = np.random.default_rng(29)
+    n, dim, k = 30_000, 48, 10
+    corpus = rng.uniform(-1, 1, (n, dim)).astype(np.float32)
+    corpus[11] = 0.0  # a special row (zero norm)
+    queries = rng.uniform(-1, 1, (4, dim))
+    for metric, screens in (("COSINE", ("TC_INT8", "TC_BF16", "SIMT_F32", "NONE_EXACT")), ("EUCLIDEAN", ("TC_BF16", "NONE_EXACT"))):
+        col = make_col(ctx, corpus, metric)
+        rows0, _, _ = col.knn(queries, k)
+        gone = np.unique(np.concatenate([rows0[:, :3].ravel(), [11, 0, n - 1]])).astype(np.uint64)
+        col.remove(gone)
+        skip = np.zeros(n, np.uint8)
+        skip[gone] = 1
+        for screen in screens:
+            col.set_screen(screen)
+            rows, dist, cnt = col.knn(queries, k)
+            for q in range(4):
+                r, d = O.knn_topk(corpus, queries[q], metric.lower(), k, skip=skip)
+                assert list(rows[q, : cnt[q]]) == list(r), (metric, screen, q)
+                assert dist[q, : cnt[q]].tobytes() == d.tobytes()
+        # a later skip mask does not resurrect the removed rows, and finalize keeps them out
+        extra = np.zeros(n, np.uint8)
+        extra[100:200] = 1
+        col.set_skip(extra)
+        col.finalize()
+        col.set_screen("AUTO")
+        both = skip | extra
+        rows, dist, cnt = col.knn(queries, k)
+        for q in range(4):
+            r, d = O.knn_topk(corpus, queries[q], metric.lower(), k, skip=both)
+            assert list(rows[q, : cnt[q]]) == list(r) and dist[q, : cnt[q]].tobytes() == d.tobytes()
+
+
 def test_filtered_and_tiny_samples(ctx):
     # a skip mask that leaves fewer than k valid rows in the scored sample: the thresholds start at -inf and the
     # histograms are seeded from the score range instead
@@ -239,6 +273,36 @@ def test_sharded_entry_points_on_one_rank(ctx):
         r, d = O.knn_topk(corpus, queries[q], "cosine", k)
         assert list(hr.numpy()[q].astype(np.uint64) - np.uint64(5_000_000_000)) == list(r)
         assert hd.numpy()[q].tobytes() == d.tobytes()
+
+
+def test_context_cancellation_flag():
+    # sdb_ctx_cancel: brute force, HNSW walk and graph expansion all observe the context's flag (ctx.is_done() polls)
+    from surrealdb_b200 import Context
+    from surrealdb_b200.graph import CsrGraph, collect, expand
+    from surrealdb_b200.hnsw import HnswIndex
+    c2 = Context(0)
+    rng = np.random.default_rng(71)
+    corpus = rng.uniform(-1, 1, (5000, 16)).astype(np.float32)
+    col = make_col(c2, corpus, "COSINE")
+    q = rng.uniform(-1, 1, (3, 16))
+    rp, ci = _rmat(rng, 10, 6000)
+    g = CsrGraph(c2, rp, ci)
+    layers = [(np.arange(5001, dtype=np.uint64) * 0, np.zeros(0, np.uint32))]
+    layers[0] = (np.concatenate([[0], np.cumsum(np.full(5000, 2))]).astype(np.uint64),
+                 np.stack([(np.arange(5000) + 1) % 5000, (np.arange(5000) + 7) % 5000], 1).ravel().astype(np.uint32))
+    idx = HnswIndex(c2, corpus, layers, 0, "euclidean")
+    want = col.knn(q, 5)
+    c2.cancel()
+    for call in (lambda: col.knn(q, 5), lambda: expand([g, g], np.arange(50, dtype=np.uint32), 0),
+                 lambda: collect(g, np.arange(2, dtype=np.uint32), 1, 3, False),
+                 lambda: idx.search_graph(corpus[:4], 3, 8)):
+        with pytest.raises(Exception, match="SDB_ECANCELLED"):
+            call()
+    c2.cancel_reset()
+    got = col.knn(q, 5)
+    assert got[0].tobytes() == want[0].tobytes() and got[1].tobytes() == want[1].tobytes()
+    assert expand([g], np.arange(5, dtype=np.uint32), 0).size >= 0
+    assert idx.search_graph(corpus[:4], 3, 8)[2].tolist() == [3, 3, 3, 3]
 
 
 def _gpu_count():
