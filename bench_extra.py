@@ -113,49 +113,109 @@ def bench_hnsw(a):
 
 
 def bench_graph(a):
+    """BASELINE config 5: R-MAT graph, 3-hop ->edge->node multiset expansion (+ one +collect BFS).  Under torchrun
+    (WORLD_SIZE > 1) the CSR is row-sharded (1-D source ranges) and every hop is the library's collective:
+    all-reduce of the degree array, local expansion into global positions, all-reduce of the level."""
     import torch
     from surrealdb_b200 import Context
-    from surrealdb_b200.graph import CsrGraph, collect, device_free, expand, expand_device
-    ctx = Context(0)
-    dev = torch.device("cuda", 0)
+    from surrealdb_b200.graph import CsrGraph, CsrGraphShard, collect, device_free, expand, expand_device
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ctx = Context(local)
+    if world > 1:
+        import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(Context.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        ctx.comm_init_rank(world, rank, bytes(uid.cpu().numpy().tobytes()))
     g = torch.Generator(device=dev).manual_seed(0x5DB00005)
-    bits, E = a.log2_nodes, a.edges
-    n_nodes = 1 << bits
-    src = torch.zeros(E, dtype=torch.int64, device=dev)
-    dst = torch.zeros(E, dtype=torch.int64, device=dev)
-    for b in range(bits):  # R-MAT a,b,c,d = .57,.19,.19,.05
-        r = torch.rand(E, generator=g, device=dev)
-        src = (src << 1) | (r >= 0.76).long()
-        dst = (dst << 1) | (((r >= 0.57) & (r < 0.76)) | (r >= 0.95)).long()
-    key = torch.unique(src * n_nodes + dst)  # one edge per (src,dst); edge ids in (src,dst) order => KV order
+    n_nodes = a.nodes if a.nodes else (1 << a.log2_nodes)
+    bits = max(1, int(np.ceil(np.log2(n_nodes))))
+    E = a.edges
+    t_gen = time.perf_counter()
+    keys = []
+    chunk = 1 << 27
+    for e0 in range(0, E, chunk):  # R-MAT a,b,c,d = .57,.19,.19,.05, generated in chunks (identical on every rank)
+        ne = min(chunk, E - e0)
+        src = torch.zeros(ne, dtype=torch.int64, device=dev)
+        dst = torch.zeros(ne, dtype=torch.int64, device=dev)
+        for b in range(bits):
+            r = torch.rand(ne, generator=g, device=dev)
+            src = (src << 1) | (r >= 0.76).long()
+            dst = (dst << 1) | (((r >= 0.57) & (r < 0.76)) | (r >= 0.95)).long()
+        if n_nodes != (1 << bits):
+            src, dst = src % n_nodes, dst % n_nodes
+        keys.append(src * n_nodes + dst)
+        del src, dst, r
+    key = torch.unique(torch.cat(keys))  # one edge per (src,dst); edge ids in (src,dst) order => KV order
+    del keys
     src, dst = key // n_nodes, key % n_nodes
     E = int(key.numel())
+    del key
     row_ptr = torch.zeros(n_nodes + 1, dtype=torch.int64, device=dev)
     row_ptr[1:] = torch.cumsum(torch.bincount(src, minlength=n_nodes), 0)
+    del src
+    # contiguous source ranges with (roughly) equal edge counts per rank
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(int(torch.searchsorted(row_ptr, torch.tensor(E * r // world, device=dev)).item()))
+    cuts.append(n_nodes)
+    cuts = [min(max(c, 0), n_nodes) for c in cuts]
+    lo, hi = cuts[rank], cuts[rank + 1]
     rp = row_ptr.cpu().numpy().astype(np.uint64)
-    ci = dst.to(torch.int32).cpu().numpy().astype(np.uint32)
-    del src, dst, key
-    graph = CsrGraph(ctx, rp, ci)
+    e0, e1 = int(rp[lo]), int(rp[hi])
+    ci_local = dst[e0:e1].to(torch.int32).cpu().numpy().astype(np.uint32)
+    t_gen = time.perf_counter() - t_gen
+    if world == 1:
+        ci = ci_local
+        graph = CsrGraph(ctx, rp, ci)
+    else:
+        graph = CsrGraphShard.__new__(CsrGraphShard)  # (the full col_idx never exists on the host: hand the slice over)
+        import ctypes as C
+        from surrealdb_b200 import _lib as L
+        graph.ctx, graph.n_rows, graph.row_lo, graph.row_hi, graph.h = ctx, n_nodes, lo, hi, C.c_void_p()
+        rps = np.ascontiguousarray(rp[lo:hi + 1] - np.uint64(e0))
+        L.check(L.lib().sdb_graph_load_csr_shard(ctx.h, n_nodes, lo, hi, C.c_void_p(rps.ctypes.data),
+                                                 C.c_void_p(ci_local.ctypes.data) if ci_local.size else None, C.byref(graph.h)))
+    del dst
+    torch.cuda.empty_cache()
     deg = np.diff(rp.astype(np.int64))
     rng = np.random.default_rng(11)
     sources = rng.choice(np.nonzero(deg > 0)[0], a.sources, replace=False).astype(np.uint32)
-    expand([graph] * a.hops, sources, a.limit)  # warm-up at full size (memory pools, pinned staging)
-    best = None
-    for _ in range(3):
-        out_ids, ms, wall = dev_time_ms(ctx, lambda: expand([graph] * a.hops, sources, a.limit))
-        best = (ms, wall) if best is None or wall < best[1] else best
-    ms, wall = best
-    # device-resident variant (frontier and result stay in HBM): isolates the degree/scan/expand kernels
+
+    def tmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
     d_src = torch.from_numpy(sources.astype(np.int32)).to(dev)
     torch.cuda.synchronize()
-    p0, _ = expand_device(ctx, [graph] * a.hops, d_src.data_ptr(), sources.size, a.limit)
+    p0, _ = expand_device(ctx, [graph] * a.hops, d_src.data_ptr(), sources.size, a.limit)  # warm-up at full size
     device_free(ctx, p0)
     ms_dev = None
     for _ in range(3):
+        if world > 1:
+            dist.barrier()
         (pd, nd), m1, _w = dev_time_ms(ctx, lambda: expand_device(ctx, [graph] * a.hops, d_src.data_ptr(), sources.size, a.limit))
         device_free(ctx, pd)
+        m1 = tmax(m1)
         ms_dev = m1 if ms_dev is None or m1 < ms_dev else ms_dev
-    # per-hop sizes for the algorithmic byte count
+    # end to end with host buffers (result copied back), and the per-hop sizes for the algorithmic byte count
+    best = None
+    for _ in range(2):
+        out_ids, ms, wall = dev_time_ms(ctx, lambda: expand([graph] * a.hops, sources, a.limit))
+        wall = tmax(wall)
+        best = wall if best is None or wall < best else best
+    wall = best
     sizes = [int(sources.size)]
     fr = sources
     for h in range(a.hops - 1):
@@ -164,19 +224,27 @@ def bench_graph(a):
     sizes.append(int(out_ids.size))
     byts = sum(16.0 * sizes[h] + 8.0 * sizes[h + 1] for h in range(a.hops))
     (coll, cms, cwall) = dev_time_ms(ctx, lambda: collect(graph, sources[:1], 1, a.hops, False))
+    cms = tmax(cms)
+    if rank != 0:
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     peak, srcp = peaks()
     res = {"bench": "graph_expand", "metric": f"{a.hops}-hop ->edge->node multiset expansion, traversed edges/sec",
-           "value": sum(sizes[1:]) / (ms_dev * 1e-3), "unit": "edges/s", "device_ms": ms_dev,
+           "value": sum(sizes[1:]) / (ms_dev * 1e-3), "unit": "edges/s", "device_ms": ms_dev, "n_gpus": world,
            "e2e": {"value": sum(sizes[1:]) / (wall * 1e-3), "unit": "edges/s", "call_wall_ms": wall,
                    "h2d_bytes": int(sources.size * 4), "d2h_bytes": int(out_ids.size * 4)},
            "config": {"nodes": n_nodes, "edges": E, "sources": int(sources.size), "hops": a.hops, "per_source_limit": a.limit, "frontier_sizes": sizes,
                       "graph": "R-MAT (.57,.19,.19,.05), integer ids, adjacency in (src,dst)=edge-id order",
+                      "sharding": "none" if world == 1 else f"1-D source ranges, {world} shards with equal edge counts; one all-reduce pair per hop",
+                      "generation_s": t_gen,
                       "collect_bfs_from_1_source": {"device_ms": cms, "nodes": int(coll.size)}},
            "roofline": {"bound": "hbm", "kernel": "expand_kernel (+degree/scan)", "achieved": byts / (ms_dev * 1e-3) / 1e9,
                         "peak": peak, "unit": "GB/s", "frac": byts / (ms_dev * 1e-3) / 1e9 / peak, "peak_source": srcp,
                         "algorithmic_bytes": byts, "traffic": None,
-                        "note": "device_ms = hops x (degree, scan, expand) incl. one 8-byte size read-back per hop; frontier and result resident in HBM"}}
-    if not a.no_cpu:
+                        "note": "device_ms = hops x (degree, scan, expand [+ 2 all-reduces when sharded]) incl. one 8-byte size "
+                                "read-back per hop; frontier and result resident in HBM; max over ranks"}}
+    if not a.no_cpu and world == 1:
         from oracle import pyoracle as O
         t0 = time.perf_counter()
         fr = sources
@@ -186,7 +254,14 @@ def bench_graph(a):
         res["cpu_baseline"] = {"value": sum(sizes[1:]) / dt, "unit": "edges/s", "cores": 1, "kind": "port",
                                "sample": f"same frontier, {a.hops} hops, single thread (the reference expands one "
                                          f"lookup chain per task), {dt:.3f}s; identical output: {bool(np.array_equal(fr, out_ids))}"}
+    if a.checksum:
+        res["result_checksum"] = {"n": int(out_ids.size), "sum": int(out_ids.astype(np.uint64).sum()),
+                                  "xor_fold": int(np.bitwise_xor.reduce(out_ids.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.arange(out_ids.size, dtype=np.uint64))),
+                                  "collect_sum": int(coll.astype(np.uint64).sum())}
     print(json.dumps(res), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def bench_stage(a):
@@ -263,6 +338,8 @@ if __name__ == "__main__":
     ap.add_argument("--prefix", action="store_true", help="insertion-order (prefix) candidate sets in the batch builder")
     ap.add_argument("--log2-nodes", type=int, default=24)
     ap.add_argument("--edges", type=int, default=160_000_000)
+    ap.add_argument("--nodes", type=int, default=0, help="node count (not a power of two: R-MAT ids are folded mod nodes)")
+    ap.add_argument("--checksum", action="store_true", help="print order-sensitive checksums of the result (1 vs N GPUs)")
     ap.add_argument("--sources", type=int, default=1024)
     ap.add_argument("--hops", type=int, default=3)
     ap.add_argument("--limit", type=int, default=32, help="GraphEdgeScan per-source limit (0 = none)")

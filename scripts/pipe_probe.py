@@ -1,5 +1,6 @@
 """where does the time go in the pipelined host-buffer path?  (1M x 768, B = 1024)"""
-import time
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 from surrealdb_b200 import Context, VectorColumn

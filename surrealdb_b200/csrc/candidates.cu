@@ -594,10 +594,101 @@ __global__ void __launch_bounds__(WARPS * 32) cand_rerank_kernel(
   }
 }
 
+// f32 rows whose length is a multiple of 4 (16-byte aligned rows): the gathers are issued ROW-contiguously -- one
+// LDG.128 per lane covers 512 consecutive bytes of ONE row, so DRAM sees 512-byte bursts per candidate row instead of
+// 128-byte pieces of 32 different rows (random 128-byte gathers reach ~2 TB/s on HBM3e, page-friendly ones several
+// times that).  The 32 x 128 tile is then walked per lane with conflict-free LDS.128 (row stride 132 floats).
+constexpr uint32_t RRV_COLS = 128, RRV_STRIDE = RRV_COLS + 4;
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) cand_rerank_v4_kernel(
+    const float* __restrict__ rows, uint32_t dim, int metric, const double* __restrict__ mag,
+    const double* __restrict__ q64, const double* __restrict__ qmag, const uint32_t* __restrict__ qflags,
+    const Cand* __restrict__ cand, const uint32_t* __restrict__ cnt, uint32_t cap, const uint32_t* __restrict__ special,
+    uint32_t n_special, uint64_t* __restrict__ rr_key, double* __restrict__ rr_dist, uint32_t* __restrict__ rr_row,
+    uint32_t rr_stride) {
+  extern __shared__ __align__(16) uint8_t rr_smem[];
+  double* s_q = reinterpret_cast<double*>(rr_smem);                                   // [QCHUNK]
+  float* tiles = reinterpret_cast<float*>(rr_smem + sizeof(double) * QCHUNK);          // [WARPS][32][RRV_STRIDE]
+  const uint32_t q = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* tile = tiles + (size_t)warp * 32 * RRV_STRIDE;
+  const uint32_t n_c = cnt[q] < cap ? cnt[q] : cap;
+  const uint32_t n_e = n_c + n_special;
+  const bool q_nan = (qflags[q] & 2u) != 0;
+  const double qm = qmag[q];
+  for (uint32_t e_first = blockIdx.y * (WARPS * 32); e_first < n_e; e_first += gridDim.y * (WARPS * 32)) {  // uniform per block
+    const uint32_t e = e_first + warp * 32 + lane;
+    uint32_t my_row = NO_ROW;
+    if (e < n_c) my_row = cand[(size_t)q * cap + e].row;
+    else if (e < n_e) my_row = special[e - n_c];
+    const bool warp_active = e_first + warp * 32 < n_e;
+    ExactAcc acc;
+    for (uint32_t cb = 0; cb < dim; cb += QCHUNK) {
+      const uint32_t cw = dim - cb < QCHUNK ? dim - cb : QCHUNK;  // multiple of 4
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < cw; i += blockDim.x) s_q[i] = q64[(size_t)q * dim + cb + i];
+      __syncthreads();
+      if (!warp_active) continue;
+      for (uint32_t c0 = 0; c0 < cw; c0 += RRV_COLS) {
+        const uint32_t c = c0 + lane * 4;  // this lane's 4 columns of every row
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+          float4 vals[16];
+#pragma unroll
+          for (int r = 0; r < 16; r++) {  // 16 independent 512-byte row bursts in flight
+            const uint32_t row = __shfl_sync(0xffffffffu, my_row, half * 16 + r);
+            vals[r] = (row != NO_ROW && c < cw) ? __ldg(reinterpret_cast<const float4*>(rows + (size_t)row * dim + cb + c))
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int r = 0; r < 16; r++)
+            *reinterpret_cast<float4*>(tile + (size_t)(half * 16 + r) * RRV_STRIDE + lane * 4) = vals[r];
+        }
+        __syncwarp();
+        if (my_row != NO_ROW) {
+          const uint32_t lim = cw - c0 < RRV_COLS ? cw - c0 : RRV_COLS;  // multiple of 4
+          const float* mine = tile + (size_t)lane * RRV_STRIDE;
+          if (metric == SDB_COSINE) {
+            for (uint32_t j = 0; j < lim; j += 4) {
+              const float4 v = *reinterpret_cast<const float4*>(mine + j);
+              acc.cosine_step((double)v.x, s_q[c0 + j]);
+              acc.cosine_step((double)v.y, s_q[c0 + j + 1]);
+              acc.cosine_step((double)v.z, s_q[c0 + j + 2]);
+              acc.cosine_step((double)v.w, s_q[c0 + j + 3]);
+            }
+          } else {
+            for (uint32_t j = 0; j < lim; j += 4) {
+              const float4 v = *reinterpret_cast<const float4*>(mine + j);
+              acc.euclid_step((double)v.x, s_q[c0 + j]);
+              acc.euclid_step((double)v.y, s_q[c0 + j + 1]);
+              acc.euclid_step((double)v.z, s_q[c0 + j + 2]);
+              acc.euclid_step((double)v.w, s_q[c0 + j + 3]);
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (my_row != NO_ROW) {
+      const double d = metric == SDB_COSINE ? cosine_finish(acc, mag[my_row], qm, q_nan) : euclid_finish(acc, q_nan);
+      const size_t o = (size_t)q * rr_stride + e;
+      rr_key[o] = dist_key(d);
+      rr_dist[o] = d;
+      rr_row[o] = my_row;
+    }
+  }
+}
+constexpr size_t RRV_SMEM = sizeof(double) * QCHUNK + sizeof(float) * 4 * 32 * RRV_STRIDE;  // 4 warps: 75.8 KB
+
 sdb_status cand_rerank(Corpus* c, uint32_t nq, cudaStream_t st) {
   const dim3 grid(nq, RR_GROUPS_Y);
-  if (c->dtype == SDB_F32)
-    cand_rerank_kernel<float, 4, 64><<<grid, 128, 0, st>>>((const float*)c->d_rows, c->dim, (int)c->metric, c->d_mag,
+  static const bool no_v4 = getenv("SDB_RERANK_SCALAR") != nullptr;
+  if (c->dtype == SDB_F32 && c->dim % 4 == 0 && !no_v4)
+    cand_rerank_v4_kernel<4><<<grid, 128, RRV_SMEM, st>>>((const float*)c->d_rows, c->dim, (int)c->metric, c->d_mag, c->d_q64,
+                                                          c->d_qmag, c->d_qflags, c->d_cand, c->d_cand_cnt, c->sc_cap,
+                                                          c->d_special, c->n_special, c->d_rr_key, c->d_rr_dist,
+                                                          c->d_rr_row, c->rr_stride);
+  else if (c->dtype == SDB_F32)
+    cand_rerank_kernel<float, 4, 32><<<grid, 128, 0, st>>>((const float*)c->d_rows, c->dim, (int)c->metric, c->d_mag,
                                                            c->d_q64, c->d_qmag, c->d_qflags, c->d_cand, c->d_cand_cnt,
                                                            c->sc_cap, c->d_special, c->n_special, c->d_rr_key,
                                                            c->d_rr_dist, c->d_rr_row, c->rr_stride);
@@ -738,6 +829,7 @@ sdb_status cand_final(Corpus* c, uint32_t nq, uint32_t k, uint64_t row_base, uin
 
 sdb_status candidates_init_device() {
   SDB_CUDA(cudaFuncSetAttribute(cand_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  SDB_CUDA(cudaFuncSetAttribute(cand_rerank_v4_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RRV_SMEM));
   return SDB_OK;
 }
 

@@ -273,9 +273,10 @@ def test_minkowski_and_jaccard_through_the_exact_kernel(ctx):
                 assert np.allclose(dist[q], d, rtol=1e-12, atol=0.0)
         O.lib().orc_set_minkowski_order(C.c_double(3.0))
     # the reference's own KATs (surrealdb/core/tests/function.rs:3585-3593) through the column projection
-    col = make_col(ctx, np.array([[1.1, 2.2, 3.0]], np.float64), "MINKOWSKI")
+    col = make_col(ctx, np.array([[1.1, 2.2, 3.0], [1.0, 2.0, 3.0]], np.float64), "MINKOWSKI")
     col.set_minkowski_order(3)
-    assert abs(col.project("MINKOWSKI", np.array([4.0, 5.5, 6.6]))[0] - 4.3267487109222245) < 1e-14
+    assert abs(col.project("MINKOWSKI", np.array([4.0, 5.5, 6.6]))[0] - 4.747193170917638) < 1e-14
+    assert abs(col.project("MINKOWSKI", np.array([4.0, 5.0, 6.0]))[1] - 4.3267487109222245) < 1e-14
     col = make_col(ctx, np.array([[10, 20, 15, 10, 5]], np.float64), "MINKOWSKI")
     col.set_minkowski_order(2)
     assert abs(col.project("MINKOWSKI", np.array([12.0, 24, 18, 8, 7]))[0] - 6.082762530298219) < 1e-14

@@ -84,7 +84,7 @@ def test_streaming_on_sorted_and_clustered_corpora(ctx):
         col = make_col(ctx, corpus, "COSINE", screen)
         check_queries(col, corpus, queries, "COSINE", k, (0, 13, 63))
         st = col.stats()
-        assert st["n_fallback"] <= 2, st      # big candidate sets are re-ranked, not sent to the exact kernel
+        assert st["n_fallback"] <= 2 + nq // 64, st  # big candidate sets are re-ranked, not sent to the exact kernel
         assert st["n_candidates"] > 200, st   # ... and they ARE big here (2000 rows per cluster)
     # the same through the multi-pass schedule
     col = make_col(ctx, corpus, "COSINE", "TC_BF16", streaming=False)
