@@ -70,7 +70,11 @@ static void build_stream_passes(uint64_t n_rows, uint32_t cand_cap, uint32_t k, 
     probe->count = (uint32_t)T;
     return;
   }
-  const uint64_t P = k <= 32 ? 16 : PROBE_TILES_MAX;  // 8 chunk maxima per tile: 128 / 512 values >= 4 k / 2 k
+  uint64_t P = k <= 32 ? 16 : PROBE_TILES_MAX;  // 8 chunk maxima per tile: 128 / 512 values >= 4 k / 2 k
+  if (const char* e = getenv("SDB_PROBE_TILES")) {  // tuning knob: a larger probe starts the thresholds higher
+    const int v = atoi(e);
+    if (v >= (int)P && v <= (int)PROBE_TILES_MAX) P = (uint64_t)v;
+  }
   const uint64_t stride = T / P;                       // T > max0 >= 16; for P = 64 and T < 64 every tile is probed
   if (stride == 0) *probe = PassDesc{1u, 0u, (uint32_t)T, 0u};
   else *probe = PassDesc{(uint32_t)stride, 0u, (uint32_t)P, 0u};
@@ -200,6 +204,12 @@ static sdb_status enqueue_batch(Corpus* c, Ticket& t) {
     }
   }
   SDB_CUDA(cudaEventRecord(t.ev_screen1, st));
+  // stage B: the coarse screens' candidates are re-scored in f32 and narrowed before the (FP64-bound) exact re-rank
+  static const bool no_refine = getenv("SDB_NO_REFINE") != nullptr;
+  if (tc && c->exact && c->dtype == SDB_F32 && !no_refine) {
+    SDB_TRY(cand_refine(c, nq, st));
+    SDB_TRY(cand_select(c, nq, k, false, 0u, false, st, 1));
+  }
   SDB_TRY(cand_rerank(c, nq, st));
   SDB_TRY(cand_final(c, nq, k, t.row_base, t.d_out_rows, t.d_out_dist, t.d_out_count, st));
   SDB_CUDA(cudaMemcpyAsync(t.h_flags, c->d_flags, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, st));

@@ -123,7 +123,8 @@ __global__ void __launch_bounds__(128) prep_queries_i8_kernel(const float* __res
 // exact); f32 SIMT (D/16 + 16) * 2^-23.
 __global__ void cand_begin_kernel(float* __restrict__ tau, uint32_t* __restrict__ cnt, uint32_t* __restrict__ flags,
                                   uint32_t* __restrict__ stat, float* __restrict__ bscale, float* __restrict__ beps,
-                                  float* __restrict__ margin, float* __restrict__ qlow, float* __restrict__ qcap,
+                                  float* __restrict__ margin, float* __restrict__ margin2, float* __restrict__ beps2,
+                                  float* __restrict__ tau2, float* __restrict__ qlow, float* __restrict__ qcap,
                                   const double* __restrict__ qmag, const float* __restrict__ q8scale,
                                   const float* __restrict__ q8err, const float* __restrict__ qbferr, uint32_t nq,
                                   int screen, int metric, uint32_t dim, float max_rel_qerr, float i8_scale,
@@ -170,15 +171,33 @@ __global__ void cand_begin_kernel(float* __restrict__ tau, uint32_t* __restrict_
     hi = 1.0;
     lo = -1.0;
   }
+  // stage B (cand_refine: f32 re-score of the candidates with the f32 rows and the f32 query): any summation order of
+  // D products in f32 with FMA stays within (D + 16) * 2^-24 of sum |q_i x_i| <= |q||x| (the +16 covers the f64 -> f32
+  // rounding of the query, the f32 screening norm and the final scaling)
+  const double e2_rel = (dim + 16.0) * 5.9604645e-8;
+  double e2, mg2;
+  if (metric == SDB_COSINE) {
+    e2 = e2_rel;
+    mg2 = 2.1 * e2 * qm;
+  } else {
+    const double mn = (double)max_norm;
+    e2 = 2.0 * e2_rel * qm * mn + 2.4e-7 * mn * mn + 1e-30;
+    mg2 = 2.1 * e2;
+  }
+  if (!exact || !(qm > 0.0) || !isfinite(qm) || !isfinite(mg2)) mg2 = 0.0;
   bscale[q] = (float)bs;
   beps[q] = __double2float_ru(eps);
   margin[q] = __double2float_ru(mg);
+  margin2[q] = __double2float_ru(mg2);
+  beps2[q] = __double2float_ru(e2);
+  tau2[q] = __int_as_float(0xff800000);
   qlow[q] = __double2float_rd(lo);
   qcap[q] = __double2float_ru(hi);
 }
 sdb_status cand_begin(Corpus* c, uint32_t nq, int screen, cudaStream_t st) {
   cand_begin_kernel<<<(nq + 255) / 256, 256, 0, st>>>(c->d_tau, c->d_cand_cnt, c->d_flags, c->d_stat, c->d_bscale, c->d_beps,
-                                                      c->d_margin, c->d_qlow, c->d_qcap, c->d_qmag, c->d_q8scale,
+                                                      c->d_margin, c->d_margin2, c->d_beps2, c->d_tau2, c->d_qlow, c->d_qcap,
+                                                      c->d_qmag, c->d_q8scale,
                                                       c->d_q8err, c->d_qbferr, nq, screen, (int)c->metric, c->dim,
                                                       c->max_rel_qerr, c->i8_scale, c->bf16_rel_err, c->max_norm,
                                                       c->exact ? 1 : 0);
@@ -193,7 +212,7 @@ static sdb_status ensure_scratch(Corpus* c, uint32_t nq, uint32_t cap) {
   void* old[] = {c->d_q64, c->d_q32, c->d_qbf16, c->d_qmag, c->d_qflags, c->d_qbferr, c->d_tau, c->d_cand, c->d_cand_cnt,
                  c->d_flags, c->d_stat, c->d_rr_key, c->d_rr_dist, c->d_rr_row, c->d_sub, c->d_sub_cnt, c->d_q8,
                  c->d_q8scale, c->d_q8err, c->d_bscale, c->d_beps, c->d_margin, c->d_qlow, c->d_qcap, c->d_hparam,
-                 c->d_hist, c->d_probe};
+                 c->d_hist, c->d_probe, c->d_margin2, c->d_beps2, c->d_tau2};
   for (void* p : old) cudaFree(p);
   const uint32_t nqa = nq_pad > c->sc_nq ? nq_pad : c->sc_nq;
   const uint32_t capa = cap > c->sc_cap ? cap : c->sc_cap;
@@ -220,6 +239,9 @@ static sdb_status ensure_scratch(Corpus* c, uint32_t nq, uint32_t cap) {
   SDB_CUDA(cudaMalloc(&c->d_bscale, sizeof(float) * nqa));
   SDB_CUDA(cudaMalloc(&c->d_beps, sizeof(float) * nqa));
   SDB_CUDA(cudaMalloc(&c->d_margin, sizeof(float) * nqa));
+  SDB_CUDA(cudaMalloc(&c->d_margin2, sizeof(float) * nqa));
+  SDB_CUDA(cudaMalloc(&c->d_beps2, sizeof(float) * nqa));
+  SDB_CUDA(cudaMalloc(&c->d_tau2, sizeof(float) * nqa));
   SDB_CUDA(cudaMalloc(&c->d_qlow, sizeof(float) * nqa));
   SDB_CUDA(cudaMalloc(&c->d_qcap, sizeof(float) * nqa));
   SDB_CUDA(cudaMalloc(&c->d_hparam, sizeof(HistParam) * nqa));
@@ -506,12 +528,90 @@ __global__ void __launch_bounds__(256) cand_select_kernel(Cand* __restrict__ can
 }
 
 sdb_status cand_select(Corpus* c, uint32_t nq, uint32_t k, bool drop_invalid, uint32_t n_slots, bool seed_hist,
-                       cudaStream_t st) {
+                       cudaStream_t st, int stage) {
   const size_t smem = sizeof(uint64_t) * c->sc_cap;
+  if (stage == 1) {  // stage B: the lists hold f32 scores now; own threshold / margin, nothing else to gather
+    cand_select_kernel<<<nq, 256, smem, st>>>(c->d_cand, c->d_cand_cnt, c->d_tau2, c->d_flags, c->sc_cap, k, c->d_margin2,
+                                              nullptr, c->d_sub, c->d_sub_cnt, 0u, c->sub_cap, nullptr, c->d_hist, c->d_qlow,
+                                              c->d_qcap, nullptr);
+    count_launch(c->ctx);
+    SDB_CUDA(cudaGetLastError());
+    return SDB_OK;
+  }
   cand_select_kernel<<<nq, 256, smem, st>>>(  // 256 threads: several blocks per SM, the whole batch is one wave
       c->d_cand, c->d_cand_cnt, c->d_tau, c->d_flags, c->sc_cap, k, c->d_margin, drop_invalid ? c->d_snorm : nullptr,
       c->d_sub, c->d_sub_cnt, n_slots, c->sub_cap, seed_hist ? c->d_hparam : nullptr, c->d_hist, c->d_qlow, c->d_qcap,
       c->d_stat);
+  count_launch(c->ctx);
+  SDB_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage B: f32 re-score of the candidates.  FP64 is the scarce resource of this part (the sequential-f64 re-rank is
+// bound by the FP64 pipe, not by memory), so the candidates of the coarse screen -- everything within the int8 / bf16
+// error margin of the k-th best, ~100 rows per query on spread-out data, thousands inside a tight cluster -- are first
+// re-scored with the f32 master rows and the f32 query on the FP32 pipe: one warp per row, row-contiguous LDG.128,
+// shuffle reduction.  The error of that score is bounded rigorously (cand_begin_kernel: beps2), so the same rule
+// "keep everything within 2.1 x the bound of the k-th best" (cand_select, stage 1) shrinks the set to k plus a few
+// near-ties, and only those reach the f64 kernel.
+template <bool COSINE>
+__global__ void __launch_bounds__(256) cand_refine_f32_kernel(const float* __restrict__ rows, uint32_t dim,
+                                                               const float* __restrict__ snorm,
+                                                               const float* __restrict__ q32, Cand* __restrict__ cand,
+                                                               const uint32_t* __restrict__ cnt, uint32_t cap) {
+  const uint32_t q = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t n_c = cnt[q] < cap ? cnt[q] : cap;
+  const float* qv = q32 + (size_t)q * dim;
+  Cand* cq = cand + (size_t)q * cap;
+  const uint32_t warps_total = gridDim.y * 8;
+  const bool vec4 = (dim & 3u) == 0;
+  for (uint32_t e0 = (blockIdx.y * 8 + warp) * 2; e0 < n_c; e0 += warps_total * 2) {  // two rows per warp in flight
+    const uint32_t r0 = cq[e0].row;
+    const bool has1 = e0 + 1 < n_c;
+    const uint32_t r1 = has1 ? cq[e0 + 1].row : r0;
+    const float* x0 = rows + (size_t)r0 * dim;
+    const float* x1 = rows + (size_t)r1 * dim;
+    float a0 = 0.f, a1 = 0.f;
+    if (vec4) {
+      for (uint32_t c = lane * 4; c < dim; c += 128) {
+        const float4 u = __ldg(reinterpret_cast<const float4*>(x0 + c));
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x1 + c));
+        const float4 w = __ldg(reinterpret_cast<const float4*>(qv + c));
+        a0 = fmaf(u.x, w.x, a0); a0 = fmaf(u.y, w.y, a0); a0 = fmaf(u.z, w.z, a0); a0 = fmaf(u.w, w.w, a0);
+        a1 = fmaf(v.x, w.x, a1); a1 = fmaf(v.y, w.y, a1); a1 = fmaf(v.z, w.z, a1); a1 = fmaf(v.w, w.w, a1);
+      }
+    } else {
+      for (uint32_t c = lane; c < dim; c += 32) {
+        const float w = __ldg(qv + c);
+        a0 = fmaf(__ldg(x0 + c), w, a0);
+        a1 = fmaf(__ldg(x1 + c), w, a1);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    if (lane == 0) {
+      const float s0 = __ldg(snorm + r0);
+      cq[e0].score = COSINE ? a0 * s0 : fmaf(2.f, a0, -s0);
+      if (has1) {
+        const float s1 = __ldg(snorm + r1);
+        cq[e0 + 1].score = COSINE ? a1 * s1 : fmaf(2.f, a1, -s1);
+      }
+    }
+  }
+}
+sdb_status cand_refine(Corpus* c, uint32_t nq, cudaStream_t st) {
+  if (c->dtype != SDB_F32) return SDB_OK;
+  const dim3 grid(nq, 4);
+  if (c->metric == SDB_COSINE)
+    cand_refine_f32_kernel<true><<<grid, 256, 0, st>>>((const float*)c->d_rows, c->dim, c->d_snorm, c->d_q32, c->d_cand,
+                                                       c->d_cand_cnt, c->sc_cap);
+  else
+    cand_refine_f32_kernel<false><<<grid, 256, 0, st>>>((const float*)c->d_rows, c->dim, c->d_snorm, c->d_q32, c->d_cand,
+                                                        c->d_cand_cnt, c->sc_cap);
   count_launch(c->ctx);
   SDB_CUDA(cudaGetLastError());
   return SDB_OK;
@@ -734,8 +834,8 @@ __global__ void __launch_bounds__(512) cand_final_kernel(
     const uint64_t* __restrict__ rr_key, const double* __restrict__ rr_dist, const uint32_t* __restrict__ rr_row,
     uint32_t rr_stride, const uint32_t* __restrict__ cnt, uint32_t cap, uint32_t n_special,
     const float* __restrict__ tau, const double* __restrict__ qmag, const float* __restrict__ bscale,
-    const float* __restrict__ beps, uint32_t* __restrict__ flags, const uint32_t* __restrict__ qflags,
-    uint32_t* __restrict__ stat, int metric,
+    const float* __restrict__ beps, const float* __restrict__ tau2, const float* __restrict__ beps2,
+    uint32_t* __restrict__ flags, const uint32_t* __restrict__ qflags, uint32_t* __restrict__ stat, int metric,
     uint32_t k, uint64_t row_base, uint64_t* __restrict__ out_rows,
     double* __restrict__ out_dist, uint32_t* __restrict__ out_count, int debug) {
   __shared__ uint64_t s_key[FIN_WIN];  // distance key
@@ -799,6 +899,17 @@ __global__ void __launch_bounds__(512) cand_final_kernel(
         const double L = -(double)t + qm * qm - (double)beps[q];
         ok = L > 0.0 && dist_key(sqrt(L) * (1.0 - 1e-12)) > kth;
       }
+      // stage B dropped candidates whose f32 score is below tau2: the same proof with the f32 bound
+      const float t2 = tau2[q];
+      if (ok && t2 > __int_as_float(0xff800000)) {
+        if (metric == SDB_COSINE) {
+          const double bound2 = 1.0 - (double)t2 / qm - (double)beps2[q] - 1e-9;
+          ok = dist_key(bound2) > kth;
+        } else {
+          const double L2 = -(double)t2 + qm * qm - (double)beps2[q];
+          ok = L2 > 0.0 && dist_key(sqrt(L2) * (1.0 - 1e-12)) > kth;
+        }
+      }
       if (!ok) fl |= 2u;
       if (debug && q == 0)
         printf("[sdb final] q0 metric=%d tau=%g qmag=%g beps=%g n_e=%u kth_key=%llx ok=%d\n", metric, (double)t, qm,
@@ -820,7 +931,7 @@ sdb_status cand_final(Corpus* c, uint32_t nq, uint32_t k, uint64_t row_base, uin
   }
   static const int debug = getenv("SDB_DEBUG") != nullptr;
   cand_final_kernel<<<nq, 512, 0, st>>>(c->d_rr_key, c->d_rr_dist, c->d_rr_row, c->rr_stride, c->d_cand_cnt, c->sc_cap,
-                                        c->n_special, c->d_tau, c->d_qmag, c->d_bscale, c->d_beps, c->d_flags, c->d_qflags, c->d_stat,
+                                        c->n_special, c->d_tau, c->d_qmag, c->d_bscale, c->d_beps, c->d_tau2, c->d_beps2, c->d_flags, c->d_qflags, c->d_stat,
                                         (int)c->metric, k, row_base, d_out_rows, d_out_dist, d_out_count, debug);
   count_launch(c->ctx);
   SDB_CUDA(cudaGetLastError());

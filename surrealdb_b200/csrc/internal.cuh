@@ -231,6 +231,9 @@ struct Corpus {
   float* d_bscale = nullptr;     // per query: factor that turns tau into similarity*|q| units (1 or q8scale * i8_scale)
   float* d_beps = nullptr;       // per query: rigorous screen error bound (cosine units / relative dot error)
   float* d_margin = nullptr;     // per query: 2.1 x that bound in score units (0 in approximate mode)
+  float* d_margin2 = nullptr;    // stage B (f32 re-score of the candidates): margin, error bound, threshold
+  float* d_beps2 = nullptr;
+  float* d_tau2 = nullptr;
   float* d_qlow = nullptr;       // per query: lower / upper bound of any score (histogram geometry)
   float* d_qcap = nullptr;
   HistParam* d_hparam = nullptr; // per query histogram geometry of the streaming screen
@@ -287,7 +290,10 @@ sdb_status cand_set_count(Corpus* c, uint32_t nq, uint32_t value, cudaStream_t s
 // score >= tau = s_k - margin (all of them while fewer than k exist), publish tau.  seed_hist: also (re)build the
 // query's histogram (geometry + counts of the kept candidates) for the streaming pass that follows.
 sdb_status cand_select(Corpus* c, uint32_t nq, uint32_t k, bool drop_invalid, uint32_t n_slots, bool seed_hist,
-                       cudaStream_t st);
+                       cudaStream_t st, int stage = 0);
+// stage B: re-score every kept candidate in f32 (master rows x f32 query) so that cand_select(stage 1) can shrink the
+// set before the FP64-bound exact re-rank
+sdb_status cand_refine(Corpus* c, uint32_t nq, cudaStream_t st);
 // after a probe launch over n_tiles tiles: tau = (k-th largest chunk maximum) - margin, histogram geometry, empty lists
 sdb_status cand_seed_from_probe(Corpus* c, uint32_t nq, uint32_t k, uint32_t n_tiles, cudaStream_t st);
 sdb_status cand_rerank(Corpus* c, uint32_t nq, cudaStream_t st);

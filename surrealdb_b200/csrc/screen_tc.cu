@@ -143,16 +143,16 @@ __device__ __noinline__ void append_survivor(Cand* my_sub, uint32_t my_cnt_saddr
   }
 }
 
-// streaming mode: the survivor is also counted in its query's score histogram (no return value: a RED in L2)
+// streaming mode: the survivor is also counted in its query's score histogram (no return value: a RED in L2).  The
+// histogram geometry (lo, 1/w0) was prefetched with the item's threshold: no dependent global load on this path.
 __device__ __noinline__ void append_survivor_h(Cand* my_sub, uint32_t my_cnt_saddr, Cand* my_cand, uint32_t* cnt_q, uint32_t cap,
-                                               const HistParam* hp_q, uint32_t* hist_q, float score, uint32_t row) {
+                                               float hp_lo, float hp_inv_w0, uint32_t* hist_q, float score, uint32_t row) {
   append_survivor(my_sub, my_cnt_saddr, my_cand, cnt_q, cap, score, row);
-  const float4 v = __ldg(reinterpret_cast<const float4*>(hp_q));
   HistParam hp;
-  hp.lo = v.x;
-  hp.inv_w0 = v.y;
-  hp.w0 = v.z;
-  hp.margin = v.w;
+  hp.lo = hp_lo;
+  hp.inv_w0 = hp_inv_w0;
+  hp.w0 = 0.f;
+  hp.margin = 0.f;
   atomicAdd(hist_q + hist_bin(hp, score), 1u);
 }
 
@@ -170,7 +170,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                  PassDesc pass, float* tau, Cand* __restrict__ cand,
                  uint32_t* __restrict__ cand_cnt, uint32_t cap, Cand* __restrict__ sub, uint32_t* __restrict__ sub_cnt,
                  uint32_t k, const HistParam* __restrict__ hparam, uint32_t* hist, float* __restrict__ probe,
-                 uint32_t probe_stride) {
+                 uint32_t probe_stride, uint32_t sleep_min_ns, uint32_t sleep_max_ns) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -272,9 +272,13 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // the threshold of the first item; later items prefetch theirs while the current one is processed
     uint32_t w = blockIdx.x;
     float next_tau = __int_as_float(0x7f800000);
+    float2 next_hp = make_float2(0.f, 0.f);  // streaming mode: (lo, 1/w0) of the query's histogram
     if (w < n_items) {
       const uint32_t q0 = item_mb(w, n_mblocks) * BLOCK_M + row_in_tile;
-      if (q0 < nq) next_tau = __ldcg(tau + q0);
+      if (q0 < nq) {
+        next_tau = __ldcg(tau + q0);
+        if (MODE == 2) next_hp = __ldg(reinterpret_cast<const float2*>(hparam + q0));
+      }
     }
     for (; w < n_items; w += gridDim.x, j++) {
       const uint32_t tidx = w / n_mblocks;
@@ -283,12 +287,16 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint32_t a = j % ACC_STAGES, pa = (j / ACC_STAGES) & 1;
       const uint32_t q = mb * BLOCK_M + row_in_tile;
       const float my_tau = next_tau;
+      const float2 my_hp = next_hp;
       {  // prefetch the next item's threshold (a global load whose latency would otherwise sit in front of the wait)
         const uint32_t wn = w + gridDim.x;
         next_tau = __int_as_float(0x7f800000);
         if (wn < n_items) {
           const uint32_t qn = item_mb(wn, n_mblocks) * BLOCK_M + row_in_tile;
-          if (qn < nq) next_tau = __ldcg(tau + qn);  // L2: sees the refiners' updates
+          if (qn < nq) {
+            next_tau = __ldcg(tau + qn);  // L2: sees the refiners' updates
+            if (MODE == 2) next_hp = __ldg(reinterpret_cast<const float2*>(hparam + qn));
+          }
         }
       }
       const size_t row0 = (size_t)tile * BLOCK_N;
@@ -368,7 +376,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     }
                     if (valid) {
                       if (MODE == 2)
-                        append_survivor_h(my_sub, my_cnt, my_cand, cand_cnt + q, cap, hparam + q,
+                        append_survivor_h(my_sub, my_cnt, my_cand, cand_cnt + q, cap, my_hp.x, my_hp.y,
                                           hist + (size_t)q * HIST_BINS, __int2float_rn((int)v[i]), r);
                       else
                         append_survivor(my_sub, my_cnt, my_cand, cand_cnt + q, cap, __int2float_rn((int)v[i]), r);
@@ -413,7 +421,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 for (int i = 8 * g; i < 8 * g + 8; i++) {
                   if (sc[i] >= my_tau) {
                     if (MODE == 2)
-                      append_survivor_h(my_sub, my_cnt, my_cand, cand_cnt + q, cap, hparam + q,
+                      append_survivor_h(my_sub, my_cnt, my_cand, cand_cnt + q, cap, my_hp.x, my_hp.y,
                                         hist + (size_t)q * HIST_BINS, sc[i], (uint32_t)(row0 + cbase + c0 + i));
                     else
                       append_survivor(my_sub, my_cnt, my_cand, cand_cnt + q, cap, sc[i], (uint32_t)(row0 + cbase + c0 + i));
@@ -451,7 +459,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if (n_own > 32) n_own = 32;  // (tiny grids only; the rest keeps its seed threshold)
       float my_tau = __int_as_float(0xff800000);  // lane j: the threshold last published for owned query j
       if (lane < n_own) my_tau = __ldcg(tau + blockIdx.x + lane * stride);
-      uint32_t sleep_ns = 256;
+      uint32_t sleep_ns = sleep_min_ns;
       while (*done < EPI_WARPS) {
         bool any = false;
         for (uint32_t j = 0; j < n_own; j++) {
@@ -501,7 +509,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             any = true;
           }
         }
-        sleep_ns = any ? 256u : (sleep_ns < 4096u ? sleep_ns * 2 : 8192u);
+        sleep_ns = any ? sleep_min_ns : (sleep_ns * 2 < sleep_max_ns ? sleep_ns * 2 : sleep_max_ns);
         __nanosleep(sleep_ns);
       }
     }
@@ -572,6 +580,13 @@ sdb_status screen_tc_pass(Corpus* c, uint32_t nq, uint32_t k, const PassDesc& p,
     return SDB_EUNSUPPORTED;
   }
   const uint64_t n_pad = (c->n + TILE_ROWS - 1) / TILE_ROWS * TILE_ROWS;
+  // refiner pacing (tuning knobs): it re-reads its queries' histograms at most every sleep_min ns while thresholds
+  // move, backing off to sleep_max when they do not
+  uint32_t sleep_min = 512, sleep_max = 8192;
+  if (const char* e = getenv("SDB_REFINE_SLEEP_MIN")) sleep_min = (uint32_t)atoi(e);
+  if (const char* e = getenv("SDB_REFINE_SLEEP_MAX")) sleep_max = (uint32_t)atoi(e);
+  if (sleep_min < 32) sleep_min = 32;
+  if (sleep_max < sleep_min) sleep_max = sleep_min;
   CUtensorMap map_b;
   if (int8) SDB_TRY(make_map(ctx, &map_b, c->d_i8, n_pad, c->dim_pad8, tc::BLOCK_N, true, true));
   else SDB_TRY(make_map(ctx, &map_b, c->d_bf16, n_pad, c->dim_pad, tc::BLOCK_N, true));
@@ -607,7 +622,7 @@ sdb_status screen_tc_pass(Corpus* c, uint32_t nq, uint32_t k, const PassDesc& p,
 #define LAUNCH_TC1(COS, I8, MODE)                                                                              \
   tc::screen_tc_kernel<COS, I8, MODE><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(                              \
       map_a, map_b, c->d_snorm, k_blocks, n_mblocks, nqc, p, tau, cand, ccnt, c->sc_cap, sub, scnt, k, hp, hist,  \
-      c->d_probe + (size_t)q0 * PROBE_STRIDE, PROBE_STRIDE)
+      c->d_probe + (size_t)q0 * PROBE_STRIDE, PROBE_STRIDE, sleep_min, sleep_max)
 #define LAUNCH_TC(COS, I8)                   \
   do {                                       \
     if (mode == 0) LAUNCH_TC1(COS, I8, 0);   \
