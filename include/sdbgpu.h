@@ -231,6 +231,16 @@ sdb_status sdb_topk_merge_device(sdb_ctx*, uint32_t n_lists, uint32_t nq, uint32
 sdb_status sdb_hnsw_load(sdb_ctx*, uint32_t dim, sdb_metric, uint64_t n_elems, const float* vectors,
                          uint32_t n_layers, const uint64_t* const* row_ptr, const uint32_t* const* col_idx,
                          int64_t entry_point, sdb_hnsw** out);
+/* Device-resident variants for index construction: vectors and per-layer CSR arrays are DEVICE pointers
+ * that the handle BORROWS (nothing is copied; the caller keeps them alive and unchanged while the handle exists), and
+ * the search takes device queries / writes device results.  The incremental builder re-wraps the growing graph with
+ * sdb_hnsw_load_device after every insertion batch and uses the walk kernel itself as the insertion search
+ * (Hnsw::insert -> HnswLayer::search_multi with efc, hnsw/mod.rs:297-377, hnsw/layer.rs:342-387). */
+sdb_status sdb_hnsw_load_device(sdb_ctx*, uint32_t dim, sdb_metric, uint64_t n_elems, const float* d_vectors,
+                                uint32_t n_layers, const uint64_t* const* d_row_ptr, const uint32_t* const* d_col_idx,
+                                int64_t entry_point, sdb_hnsw** out);
+sdb_status sdb_hnsw_search_device(sdb_hnsw*, const float* d_queries, uint32_t nq, uint32_t k, uint32_t ef,
+                                  uint64_t* d_out_elems, double* d_out_dist, uint32_t* d_out_count);
 void sdb_hnsw_destroy(sdb_hnsw*);
 /* Filtered search: replaces Hnsw::knn_search_with_filter (hnsw/mod.rs:488-515; HnswLayer::search_single_with_filter /
  * search_with_filter / add_if_truthy, hnsw/layer.rs:111-149,226-306) when the WHERE condition has been evaluated
@@ -302,6 +312,13 @@ sdb_status sdb_hnsw_search(sdb_hnsw*, const float* queries, uint32_t nq, uint32_
 sdb_status sdb_hnsw_select_neighbors(sdb_ctx*, const float* d_vectors, uint32_t dim, sdb_metric, uint64_t row0, uint64_t n,
                                      const uint64_t* d_cand, const uint32_t* d_cand_cnt, uint32_t kc, uint32_t m_max,
                                      int presorted, uint32_t* d_out, uint32_t* d_out_cnt);
+
+/* the same selection for an explicit list of elements (d_elem_ids[i] = row of element i in d_vectors): the re-selection
+ * of over-full neighbours after a batch of insertions (hnsw/layer.rs:362-378) touches scattered elements */
+sdb_status sdb_hnsw_select_neighbors_ids(sdb_ctx*, const float* d_vectors, uint32_t dim, sdb_metric,
+                                         const uint32_t* d_elem_ids, uint64_t n, const uint64_t* d_cand,
+                                         const uint32_t* d_cand_cnt, uint32_t kc, uint32_t m_max, int presorted,
+                                         uint32_t* d_out, uint32_t* d_out_cnt);
 
 /* ---- graph expansion: replaces GraphEdgeScan::execute (exec/operators/scan/graph.rs:168-283)
  *      driven by LookupPart (exec/parts/lookup.rs:139-170) and the +collect recursion

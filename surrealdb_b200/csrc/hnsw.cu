@@ -38,6 +38,7 @@ struct Hnsw {
   uint64_t* d_visited = nullptr;
   uint32_t table_log2 = 0, n_tables = 0;
   uint32_t gen = 1;  // generations consumed so far (each warp uses gen_base + its own counter)
+  bool borrowed = false;  // sdb_hnsw_load_device: vectors and CSR arrays belong to the caller
   std::mutex mu;
 };
 
@@ -454,6 +455,7 @@ __device__ __forceinline__ float warp_pair_dist(const float* a_smem, float a_n2,
 
 template <bool COSINE>
 __global__ void __launch_bounds__(128) hnsw_select_kernel(const float* __restrict__ vec, uint32_t dim, uint64_t row0, uint64_t n,
+                                                          const uint32_t* __restrict__ elem_ids,
                                                           const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cand_cnt,
                                                           uint32_t kc, uint32_t m_max, int presorted, uint32_t* __restrict__ out,
                                                           uint32_t* __restrict__ out_cnt) {
@@ -465,7 +467,7 @@ __global__ void __launch_bounds__(128) hnsw_select_kernel(const float* __restric
   uint32_t* s_ord = reinterpret_cast<uint32_t*>(s_d + kc);  // [kc] visiting order
   const uint64_t i = (uint64_t)blockIdx.x * 4 + warp;  // element index inside this batch
   if (i >= n) return;
-  const uint64_t self = row0 + i;
+  const uint64_t self = elem_ids ? (uint64_t)elem_ids[i] : row0 + i;
   const float* q = vec + self * dim;
   float qn2 = 0.f;
   for (uint32_t c = lane; c < dim; c += 32) {
@@ -639,10 +641,12 @@ extern "C" {
 void sdb_hnsw_destroy(sdb_hnsw* h) {
   if (!h) return;
   cudaSetDevice(h->ctx->device);
-  cudaFree(h->d_vec);
+  if (!h->borrowed) {
+    cudaFree(h->d_vec);
+    for (auto p : h->rp) cudaFree(p);
+    for (auto p : h->ci) cudaFree(p);
+  }
   cudaFree(h->d_sumsq);
-  for (auto p : h->rp) cudaFree(p);
-  for (auto p : h->ci) cudaFree(p);
   cudaFree(h->d_rp);
   cudaFree(h->d_ci);
   cudaFree(h->d_visited);
@@ -694,6 +698,40 @@ sdb_status sdb_hnsw_load(sdb_ctx* ctx, uint32_t dim, sdb_metric metric, uint64_t
       sdb_hnsw_destroy(h);
       return vrc;
     }
+  }
+  return hnsw_finish(h, out);
+}
+
+sdb_status sdb_hnsw_load_device(sdb_ctx* ctx, uint32_t dim, sdb_metric metric, uint64_t n_elems, const float* d_vectors,
+                                uint32_t n_layers, const uint64_t* const* d_row_ptr, const uint32_t* const* d_col_idx,
+                                int64_t entry_point, sdb_hnsw** out) {
+  if (!ctx || !out || dim == 0 || dim > 65535 || n_elems >= 0xFFFFFFF0ull || (n_elems && !d_vectors) || !n_layers ||
+      !d_row_ptr || !d_col_idx || entry_point >= (int64_t)n_elems)
+    return SDB_EINVAL;
+  if (metric != SDB_COSINE && metric != SDB_EUCLIDEAN) {
+    set_error("hnsw: metric %d not implemented on the GPU path", (int)metric);
+    return SDB_EUNSUPPORTED;
+  }
+  *out = nullptr;
+  std::lock_guard<std::mutex> guard(ctx->mu);
+  SDB_CUDA(cudaSetDevice(ctx->device));
+  sdb_hnsw* h = new sdb_hnsw();
+  h->ctx = ctx;
+  h->dim = dim;
+  h->metric = metric;
+  h->n = n_elems;
+  h->n_layers = n_layers;
+  h->entry = entry_point;
+  h->borrowed = true;  // nothing is copied: the caller keeps vectors and adjacency alive while the handle exists
+  h->d_vec = const_cast<float*>(d_vectors);
+  for (uint32_t l = 0; l < n_layers; l++) {
+    h->rp.push_back(const_cast<uint64_t*>(d_row_ptr[l]));
+    h->ci.push_back(const_cast<uint32_t*>(d_col_idx[l]));
+  }
+  if (cudaMalloc(&h->d_sumsq, sizeof(float) * (n_elems ? n_elems : 1)) != cudaSuccess) {
+    set_error("hnsw load: sumsq allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    sdb_hnsw_destroy(h);
+    return SDB_ENOMEM;
   }
   return hnsw_finish(h, out);
 }
@@ -826,7 +864,26 @@ sdb_status sdb_hnsw_select_neighbors(sdb_ctx* ctx, const float* d_vectors, uint3
   const size_t smem = sizeof(float) * (2 * (size_t)dim + 2 * kc) * 4;
   auto kern = metric == SDB_COSINE ? hnsw_select_kernel<true> : hnsw_select_kernel<false>;
   SDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)((n + 3) / 4), 128, smem, ctx->stream>>>(d_vectors, dim, row0, n, d_cand, d_cand_cnt, kc, m_max, presorted, d_out, d_out_cnt);
+  kern<<<(unsigned)((n + 3) / 4), 128, smem, ctx->stream>>>(d_vectors, dim, row0, n, nullptr, d_cand, d_cand_cnt, kc, m_max, presorted, d_out, d_out_cnt);
+  count_launch(ctx);
+  SDB_CUDA(cudaGetLastError());
+  SDB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SDB_OK;
+}
+
+sdb_status sdb_hnsw_select_neighbors_ids(sdb_ctx* ctx, const float* d_vectors, uint32_t dim, sdb_metric metric,
+                                         const uint32_t* d_elem_ids, uint64_t n, const uint64_t* d_cand,
+                                         const uint32_t* d_cand_cnt, uint32_t kc, uint32_t m_max, int presorted,
+                                         uint32_t* d_out, uint32_t* d_out_cnt) {
+  if (!ctx || !d_vectors || !d_elem_ids || !d_cand || !d_cand_cnt || !d_out || !d_out_cnt || !dim || !kc || !m_max) return SDB_EINVAL;
+  if (metric != SDB_COSINE && metric != SDB_EUCLIDEAN) return SDB_EUNSUPPORTED;
+  if (n == 0) return SDB_OK;
+  std::lock_guard<std::mutex> guard(ctx->mu);
+  SDB_CUDA(cudaSetDevice(ctx->device));
+  const size_t smem = sizeof(float) * (2 * (size_t)dim + 2 * kc) * 4;
+  auto kern = metric == SDB_COSINE ? hnsw_select_kernel<true> : hnsw_select_kernel<false>;
+  SDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)((n + 3) / 4), 128, smem, ctx->stream>>>(d_vectors, dim, 0, n, d_elem_ids, d_cand, d_cand_cnt, kc, m_max, presorted, d_out, d_out_cnt);
   count_launch(ctx);
   SDB_CUDA(cudaGetLastError());
   SDB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -835,11 +892,17 @@ sdb_status sdb_hnsw_select_neighbors(sdb_ctx* ctx, const float* d_vectors, uint3
 
 static sdb_status hnsw_search_impl(sdb_hnsw* h, const float* queries, uint32_t nq, uint32_t k, uint32_t ef,
                                    const uint8_t* truthy, const uint8_t* noexp, uint64_t* out_elems, double* out_dist,
-                                   uint32_t* out_count, uint64_t* out_counters) {
+                                   uint32_t* out_count, uint64_t* out_counters, bool device_io = false) {
   if (!h || (nq && (!queries || !out_count)) || (nq && k && (!out_elems || !out_dist))) return SDB_EINVAL;
   if (nq == 0) return SDB_OK;
   if (k == 0 || ef == 0) {  // to_vec_limit(0) underflows in the reference; we return nothing
-    memset(out_count, 0, sizeof(uint32_t) * nq);
+    if (device_io) {
+      SDB_CUDA(cudaSetDevice(h->ctx->device));
+      SDB_CUDA(cudaMemsetAsync(out_count, 0, sizeof(uint32_t) * nq, h->ctx->stream));
+      SDB_CUDA(cudaStreamSynchronize(h->ctx->stream));
+    } else {
+      memset(out_count, 0, sizeof(uint32_t) * nq);
+    }
     return SDB_OK;
   }
   if (ef > 4096) {
@@ -901,14 +964,21 @@ static sdb_status hnsw_search_impl(sdb_hnsw* h, const float* queries, uint32_t n
   uint32_t* d_cnt = nullptr;
   uint64_t* d_ctr = nullptr;
   uint32_t* d_ovf = nullptr;
-  SDB_CUDA(cudaMallocAsync(&d_q, sizeof(float) * (size_t)nq * h->dim, st));
-  SDB_CUDA(cudaMallocAsync(&d_elems, sizeof(uint64_t) * (size_t)nq * k, st));
-  SDB_CUDA(cudaMallocAsync(&d_dist, sizeof(double) * (size_t)nq * k, st));
-  SDB_CUDA(cudaMallocAsync(&d_cnt, sizeof(uint32_t) * nq, st));
+  if (device_io) {  // queries and outputs already live on the device (index construction): no staging
+    d_q = const_cast<float*>(queries);
+    d_elems = out_elems;
+    d_dist = out_dist;
+    d_cnt = out_count;
+  } else {
+    SDB_CUDA(cudaMallocAsync(&d_q, sizeof(float) * (size_t)nq * h->dim, st));
+    SDB_CUDA(cudaMallocAsync(&d_elems, sizeof(uint64_t) * (size_t)nq * k, st));
+    SDB_CUDA(cudaMallocAsync(&d_dist, sizeof(double) * (size_t)nq * k, st));
+    SDB_CUDA(cudaMallocAsync(&d_cnt, sizeof(uint32_t) * nq, st));
+    SDB_CUDA(cudaMemcpyAsync(d_q, queries, sizeof(float) * (size_t)nq * h->dim, cudaMemcpyHostToDevice, st));
+  }
   SDB_CUDA(cudaMallocAsync(&d_ctr, sizeof(uint64_t) * 2 * nq, st));
   SDB_CUDA(cudaMallocAsync(&d_ovf, 4, st));
   SDB_CUDA(cudaMemsetAsync(d_ovf, 0, 4, st));
-  SDB_CUDA(cudaMemcpyAsync(d_q, queries, sizeof(float) * (size_t)nq * h->dim, cudaMemcpyHostToDevice, st));
   uint8_t* d_noexp = nullptr;
   if (noexp) {
     SDB_CUDA(cudaMallocAsync(&d_noexp, h->n ? h->n : 1, st));
@@ -948,16 +1018,20 @@ static sdb_status hnsw_search_impl(sdb_hnsw* h, const float* queries, uint32_t n
   count_launch(ctx);
   h->gen += gens_per_warp * n_tables;
   uint32_t ovf = 0;
-  SDB_CUDA(cudaMemcpyAsync(out_elems, d_elems, sizeof(uint64_t) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
-  SDB_CUDA(cudaMemcpyAsync(out_dist, d_dist, sizeof(double) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
-  SDB_CUDA(cudaMemcpyAsync(out_count, d_cnt, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, st));
+  if (!device_io) {
+    SDB_CUDA(cudaMemcpyAsync(out_elems, d_elems, sizeof(uint64_t) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
+    SDB_CUDA(cudaMemcpyAsync(out_dist, d_dist, sizeof(double) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
+    SDB_CUDA(cudaMemcpyAsync(out_count, d_cnt, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, st));
+  }
   if (out_counters)
-    SDB_CUDA(cudaMemcpyAsync(out_counters, d_ctr, sizeof(uint64_t) * 2 * nq, cudaMemcpyDeviceToHost, st));
+    SDB_CUDA(cudaMemcpyAsync(out_counters, d_ctr, sizeof(uint64_t) * 2 * nq, device_io ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
   SDB_CUDA(cudaMemcpyAsync(&ovf, d_ovf, 4, cudaMemcpyDeviceToHost, st));
-  cudaFreeAsync(d_q, st);
-  cudaFreeAsync(d_elems, st);
-  cudaFreeAsync(d_dist, st);
-  cudaFreeAsync(d_cnt, st);
+  if (!device_io) {
+    cudaFreeAsync(d_q, st);
+    cudaFreeAsync(d_elems, st);
+    cudaFreeAsync(d_dist, st);
+    cudaFreeAsync(d_cnt, st);
+  }
   cudaFreeAsync(d_ctr, st);
   cudaFreeAsync(d_ovf, st);
   if (d_truthy) cudaFreeAsync(d_truthy, st);
@@ -1019,6 +1093,11 @@ sdb_status sdb_vec_distance_f32(sdb_ctx* ctx, sdb_metric metric, uint32_t dim, c
 sdb_status sdb_hnsw_search(sdb_hnsw* h, const float* queries, uint32_t nq, uint32_t k, uint32_t ef, uint64_t* out_elems,
                            double* out_dist, uint32_t* out_count, uint64_t* out_counters) {
   return hnsw_search_impl(h, queries, nq, k, ef, nullptr, nullptr, out_elems, out_dist, out_count, out_counters);
+}
+
+sdb_status sdb_hnsw_search_device(sdb_hnsw* h, const float* d_queries, uint32_t nq, uint32_t k, uint32_t ef,
+                                  uint64_t* d_out_elems, double* d_out_dist, uint32_t* d_out_count) {
+  return hnsw_search_impl(h, d_queries, nq, k, ef, nullptr, nullptr, d_out_elems, d_out_dist, d_out_count, nullptr, true);
 }
 
 sdb_status sdb_hnsw_search_pending(sdb_hnsw* h, const float* queries, uint32_t nq, uint32_t k, uint32_t ef,

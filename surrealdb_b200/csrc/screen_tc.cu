@@ -45,7 +45,8 @@ constexpr uint32_t REFINE_WARP = 2 + EPI_WARPS;  // warp 10
 constexpr uint32_t THREADS = 64 + EPI_WARPS * 32 + 32;
 constexpr uint32_t MAX_MBLOCKS = 16;           // queries per launch <= 2048 (the driver splits larger batches)
 constexpr uint32_t SUBCAP = 16;                // private candidate slots per (query, CTA, column half) and pass
-constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + ACC_STAGES * BLOCK_N * 4 + 256 + MAX_MBLOCKS * 256 * 4 + 1024;
+constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + ACC_STAGES * BLOCK_N * 4 + 256 + MAX_MBLOCKS * 256 * 4 +
+                                EPI_WARPS * 32 * 4 /* survivor scratch */ + 1024;
 static_assert(BLOCK_N == TILE_ROWS, "screen tile must match the pass schedule tile");
 
 // instruction descriptor (cute::UMMA::InstrDescriptor bit layout): D=f32, A=B=bf16, both K-major
@@ -127,33 +128,73 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 
-// out-of-line survivor append: keeps the (rare) slow path out of the unrolled epilogue body
-__device__ __noinline__ void append_survivor(Cand* my_sub, uint32_t my_cnt_saddr, Cand* my_cand, uint32_t* cnt_q, uint32_t cap,
-                                             float score, uint32_t row) {
-  // thread-private counter in shared memory (explicit shared-space access): no atomics, no round trip
-  uint32_t pos;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(pos) : "r"(my_cnt_saddr));
-  asm volatile("st.shared.u32 [%0], %1;" ::"r"(my_cnt_saddr), "r"(pos + 1));
-  const uint2 cd = make_uint2(__float_as_uint(score), row);  // = Cand{score, row}, one 8-byte store
-  if (pos < SUBCAP) {
-    *reinterpret_cast<uint2*>(my_sub + pos) = cd;
-  } else {  // private slots full (small passes run few CTAs): spill to the query's shared list
-    const uint32_t p2 = atomicAdd(cnt_q, 1u);
-    if (p2 < cap) *reinterpret_cast<uint2*>(my_cand + p2) = cd;
+// ---- survivors: warp-cooperative, control-flow uniform --------------------------------------------------------------
+// A chunk is 32 columns (corpus rows) of ONE query per lane.  When some lane's chunk maximum reaches its threshold the
+// whole warp handles that lane's chunk together: the lane publishes its 32 values to a 128-byte scratch line, every
+// lane picks up one column, compares it with the owner's threshold, and the survivors (ballot) are written side by
+// side into the owner query's private sub-list (position = popcount prefix), each also counted in the query's
+// histogram (streaming mode; a fire-and-forget RED).  No per-lane divergent scan, no calls: an event costs ~40 warp
+// instructions whatever the number of survivors -- the per-lane version cost ~130 per survivor, and since the
+// accumulator stage is released only when the slowest of the 8 epilogue warps is done, that doubled the time of a
+// short (1.25M-row) launch.
+// vals: this lane's 32 values (int accumulators or scaled float scores as bits); all 32 lanes must call.
+template <bool INT8, int MODE>
+__device__ __forceinline__ void warp_survivors(uint32_t hits, const uint32_t (&vals)[32], uint32_t* scratch /* [32] per warp */,
+                                               uint32_t lane, float my_tau, int tau_i, float2 my_hp, uint32_t q_base,
+                                               uint32_t row_first, const float* __restrict__ snorm, Cand* __restrict__ cand,
+                                               uint32_t* __restrict__ cand_cnt, uint32_t cap, Cand* __restrict__ sub,
+                                               uint32_t n_slots, uint32_t slot, uint32_t* s_cnt_warp /* [32] */,
+                                               uint32_t* hist) {
+  while (hits) {
+    const uint32_t L = __ffs(hits) - 1;
+    hits &= hits - 1;
+    if (lane == L) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)
+        *reinterpret_cast<uint4*>(scratch + i) = make_uint4(vals[i], vals[i + 1], vals[i + 2], vals[i + 3]);
+    }
+    __syncwarp();
+    const uint32_t xb = scratch[lane];  // column `lane` of the owner's chunk
+    const float tau_f = __shfl_sync(0xffffffffu, my_tau, L);
+    const int tau_n = __shfl_sync(0xffffffffu, tau_i, L);
+    const float hp_lo = __shfl_sync(0xffffffffu, my_hp.x, L);  // the owner query's histogram geometry (streaming mode)
+    const float hp_inv = __shfl_sync(0xffffffffu, my_hp.y, L);
+    const uint32_t qL = q_base + L;
+    const uint32_t r = row_first + lane;
+    bool surv = INT8 ? ((int)xb >= tau_n) : (__uint_as_float(xb) >= tau_f);  // NaN scores never pass
+    if (INT8 && surv && (int)xb == 0) {
+      // invalid rows (skipped / special / padding) are all-zero in the int8 copy and score exactly 0: only a zero
+      // score needs the look-up of the row's screening norm
+      const float sn = __ldg(snorm + r);
+      surv = sn == sn;
+    }
+    const uint32_t smask = __ballot_sync(0xffffffffu, surv);
+    if (smask) {  // uniform
+      const uint32_t base = s_cnt_warp[L];  // broadcast read: appends of this (query, CTA, column half) so far
+      if (surv) {
+        const uint32_t pos = base + __popc(smask & ((1u << lane) - 1u));
+        const float score = INT8 ? __int2float_rn((int)xb) : __uint_as_float(xb);
+        const uint2 cd = make_uint2(__float_as_uint(score), r);
+        if (pos < SUBCAP) {
+          *reinterpret_cast<uint2*>(sub + ((size_t)qL * n_slots + slot) * SUBCAP + pos) = cd;
+        } else {  // private slots full: spill to the query's shared list
+          const uint32_t p2 = atomicAdd(cand_cnt + qL, 1u);
+          if (p2 < cap) *reinterpret_cast<uint2*>(cand + (size_t)qL * cap + p2) = cd;
+        }
+        if (MODE == 2) {
+          HistParam hp;
+          hp.lo = hp_lo;
+          hp.inv_w0 = hp_inv;
+          hp.w0 = 0.f;
+          hp.margin = 0.f;
+          atomicAdd(hist + (size_t)qL * HIST_BINS + hist_bin(hp, score), 1u);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) s_cnt_warp[L] = base + __popc(smask);
+    }
+    __syncwarp();  // scratch and counter are reused by the next event
   }
-}
-
-// streaming mode: the survivor is also counted in its query's score histogram (no return value: a RED in L2).  The
-// histogram geometry (lo, 1/w0) was prefetched with the item's threshold: no dependent global load on this path.
-__device__ __noinline__ void append_survivor_h(Cand* my_sub, uint32_t my_cnt_saddr, Cand* my_cand, uint32_t* cnt_q, uint32_t cap,
-                                               float hp_lo, float hp_inv_w0, uint32_t* hist_q, float score, uint32_t row) {
-  append_survivor(my_sub, my_cnt_saddr, my_cand, cnt_q, cap, score, row);
-  HistParam hp;
-  hp.lo = hp_lo;
-  hp.inv_w0 = hp_inv_w0;
-  hp.w0 = 0.f;
-  hp.margin = 0.f;
-  atomicAdd(hist_q + hist_bin(hp, score), 1u);
 }
 
 // MODE 0: pass 0 -- every score of the pass's tiles goes to a fixed slot of the query's main list (tau = -inf)
@@ -185,6 +226,7 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES);
   uint32_t* s_done = s_tmem + 1;  // epilogue warps that have finished (the refiner's exit condition)
   uint32_t* s_cnt = s_tmem + 4;   // [n_mblocks][256] private append counters of the epilogue threads
+  uint32_t* s_scratch = s_cnt + MAX_MBLOCKS * 256;  // [EPI_WARPS][32] one chunk of one lane, for the survivor hand-over
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t n_items = pass.count * n_mblocks;
@@ -359,32 +401,12 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 my_cand[(size_t)tidx * BLOCK_N + cbase + c0 + i] = cd;
               }
             }
-          } else if (m >= tau_i) {  // rare
-#pragma unroll
-            for (int g = 0; g < 4; g++) {
-              if (gm[g] >= tau_i) {
-#pragma unroll
-                for (int i = 8 * g; i < 8 * g + 8; i++) {
-                  if ((int)v[i] >= tau_i) {
-                    const uint32_t r = (uint32_t)(row0 + cbase + c0 + i);
-                    // invalid rows (skipped / special / padding) are all-zero in the int8 copy and score exactly 0:
-                    // only a zero score needs the look-up of the row's screening norm (a DRAM-latency gather)
-                    bool valid = true;
-                    if ((int)v[i] == 0) {
-                      const float sn = __ldg(snorm + r);
-                      valid = sn == sn;
-                    }
-                    if (valid) {
-                      if (MODE == 2)
-                        append_survivor_h(my_sub, my_cnt, my_cand, cand_cnt + q, cap, my_hp.x, my_hp.y,
-                                          hist + (size_t)q * HIST_BINS, __int2float_rn((int)v[i]), r);
-                      else
-                        append_survivor(my_sub, my_cnt, my_cand, cand_cnt + q, cap, __int2float_rn((int)v[i]), r);
-                    }
-                  }
-                }
-              }
-            }
+          } else {
+            const uint32_t hits = __ballot_sync(0xffffffffu, m >= tau_i);
+            if (hits)  // rare, uniform across the warp
+              warp_survivors<true, MODE>(hits, v, s_scratch + (warp - 2) * 32, lane, my_tau, tau_i, my_hp,
+                                         mb * BLOCK_M + wq * 32, (uint32_t)(row0 + cbase + c0), snorm, cand, cand_cnt, cap,
+                                         sub, gridDim.x * 2, blockIdx.x * 2 + half, s_cnt + mb * 256 + (et - lane), hist);
           }
         } else {
           float sc[32];
@@ -413,21 +435,15 @@ screen_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 my_cand[(size_t)tidx * BLOCK_N + cbase + c0 + i] = cd;
               }
             }
-          } else if (m >= my_tau) {  // rare: some element of this chunk survives the threshold
+          } else {
+            const uint32_t hits = __ballot_sync(0xffffffffu, m >= my_tau);
+            if (hits) {  // rare, uniform across the warp
+              uint32_t sb[32];
 #pragma unroll
-            for (int g = 0; g < 4; g++) {
-              if (gmf[g] >= my_tau) {
-#pragma unroll
-                for (int i = 8 * g; i < 8 * g + 8; i++) {
-                  if (sc[i] >= my_tau) {
-                    if (MODE == 2)
-                      append_survivor_h(my_sub, my_cnt, my_cand, cand_cnt + q, cap, my_hp.x, my_hp.y,
-                                        hist + (size_t)q * HIST_BINS, sc[i], (uint32_t)(row0 + cbase + c0 + i));
-                    else
-                      append_survivor(my_sub, my_cnt, my_cand, cand_cnt + q, cap, sc[i], (uint32_t)(row0 + cbase + c0 + i));
-                  }
-                }
-              }
+              for (int i = 0; i < 32; i++) sb[i] = __float_as_uint(sc[i]);
+              warp_survivors<false, MODE>(hits, sb, s_scratch + (warp - 2) * 32, lane, my_tau, 0, my_hp,
+                                          mb * BLOCK_M + wq * 32, (uint32_t)(row0 + cbase + c0), snorm, cand, cand_cnt, cap,
+                                          sub, gridDim.x * 2, blockIdx.x * 2 + half, s_cnt + mb * 256 + (et - lane), hist);
             }
           }
         }
