@@ -66,16 +66,30 @@ def bench_hnsw(a):
             now = time.perf_counter()
             print(f"[build] layer {l} stage {a1} value {b1} +{now - tl[0]:.1f}s", file=sys.stderr, flush=True)
             tl[0] = now
-    layers, entry, levels = build_layers(ctx, x, n, dim, a.metric.upper(), m=a.m, m0=2 * a.m, seed=7, progress=prog, prefix=a.prefix)
-    print(f"[build] done {time.perf_counter() - t0:.1f}s", file=sys.stderr, flush=True)
-    build_s = time.perf_counter() - t0
-    xh = x.cpu().numpy()
+    if a.builder == "incremental":
+        from surrealdb_b200.hnsw_build import build_incremental
+        res = build_incremental(ctx, x, a.metric.upper(), m=a.m, m0=2 * a.m, efc=a.efc, seed=7, growth=a.growth, progress=prog)
+        x = res["x"]  # re-ordered by level: element ids below are the NEW ids (rows of this tensor)
+        layers = [(rp.cpu().numpy().astype(np.uint64), ci.cpu().numpy().astype(np.uint32)) for rp, ci in res["layers_dev"]] if not a.no_cpu else None
+        entry = res["entry"]
+        print(f"[build] done {time.perf_counter() - t0:.1f}s", file=sys.stderr, flush=True)
+        build_s = time.perf_counter() - t0
+        idx = HnswIndex.from_device(ctx, x, res["layers_dev"], entry, a.metric.upper())
+        n_layers = len(res["layers_dev"])
+        deg0 = float(res["layers_dev"][0][1].numel()) / n
+        xh = x.cpu().numpy() if not a.no_cpu else None
+    else:
+        layers, entry, levels = build_layers(ctx, x, n, dim, a.metric.upper(), m=a.m, m0=2 * a.m, seed=7, progress=prog, prefix=a.prefix)
+        print(f"[build] done {time.perf_counter() - t0:.1f}s", file=sys.stderr, flush=True)
+        build_s = time.perf_counter() - t0
+        xh = x.cpu().numpy()
+        idx = HnswIndex(ctx, xh, layers, entry, a.metric.upper())
+        n_layers = len(layers)
+        deg0 = float(np.diff(layers[0][0].astype(np.int64)).mean())
     qh = queries.cpu().numpy()
-    idx = HnswIndex(ctx, xh, layers, entry, a.metric.upper())
     print(f"[load] index on device {time.perf_counter() - t0:.1f}s", file=sys.stderr, flush=True)
     idx.search_graph(qh[:256], a.k, a.ef)  # warm-up
     (ids, dist, cnt, ctr), ms, wall = dev_time_ms(ctx, lambda: idx.search_graph(qh, a.k, a.ef, counters=True))
-    deg0 = float(np.diff(layers[0][0].astype(np.int64)).mean())
     visited, expanded = int(ctr[:, 0].sum()), int(ctr[:, 1].sum())
     byts = visited * (4.0 * dim + 4.0) + expanded * deg0 * 4.0
     # recall@k against exact brute force (f64 reference arithmetic) on the same corpus
@@ -90,8 +104,8 @@ def bench_hnsw(a):
     out = {"bench": "hnsw_search", "metric": f"HNSW KNN queries/sec (M={a.m}, M0={2*a.m}, ef={a.ef}, k={a.k})",
            "value": a.queries / (wall * 1e-3), "unit": "queries/s", "device_ms": ms, "call_wall_ms": wall,
            "recall_at_k": recall, "config": {"rows": n, "dim": dim, "queries": a.queries, "metric": a.metric.lower(), "data": f"4096 unit-norm centroids + gaussian noise of total norm {a.sigma}",
-                                              "graph": "GPU batch-built layers (hnsw_build.py): kNN candidates" + (" from id prefixes" if a.prefix else "") + " + Heuristic::select + bidirectional re-selection", "build_s": build_s,
-                                              "layers": len(layers), "visited_per_query": visited / a.queries,
+                                              "graph": ("GPU batched true insertion (hnsw_build.build_incremental): walk kernel as insertion search (efc=%d), Heuristic::select, bidirectional linking, re-selection of over-full nodes; batches grow by %.2fx" % (a.efc, a.growth)) if a.builder == "incremental" else "GPU batch-built layers (hnsw_build.py): kNN candidates" + (" from id prefixes" if a.prefix else "") + " + Heuristic::select + bidirectional re-selection", "build_s": build_s,
+                                              "layers": n_layers, "visited_per_query": visited / a.queries,
                                               "expanded_per_query": expanded / a.queries},
            "roofline": {"bound": "hbm", "kernel": "hnsw_search_kernel", "achieved": byts / (ms * 1e-3) / 1e9, "peak": peak,
                         "unit": "GB/s", "frac": byts / (ms * 1e-3) / 1e9 / peak, "peak_source": src,
@@ -336,6 +350,9 @@ if __name__ == "__main__":
     ap.add_argument("--metric", default="euclidean", choices=["euclidean", "cosine"])
     ap.add_argument("--sigma", type=float, default=0.15)
     ap.add_argument("--prefix", action="store_true", help="insertion-order (prefix) candidate sets in the batch builder")
+    ap.add_argument("--builder", default="batch", choices=["batch", "incremental"])
+    ap.add_argument("--efc", type=int, default=150)
+    ap.add_argument("--growth", type=float, default=0.25)
     ap.add_argument("--log2-nodes", type=int, default=24)
     ap.add_argument("--edges", type=int, default=160_000_000)
     ap.add_argument("--nodes", type=int, default=0, help="node count (not a power of two: R-MAT ids are folded mod nodes)")

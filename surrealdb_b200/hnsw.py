@@ -59,6 +59,24 @@ class HnswIndex:
                                       RP, CI, int(entry_point), C.byref(self.h)))
 
     @classmethod
+    def from_device(cls, ctx, x_dev, layers_dev, entry_point, metric="EUCLIDEAN", elem_docs=None):
+        """wraps device-resident vectors and CSR layers WITHOUT copying them (sdb_hnsw_load_device): x_dev is a torch CUDA
+        float32 (n, dim) tensor, layers_dev = [(row_ptr int64 (n+1), col_idx int32)] layer 0 first.  The tensors must
+        stay alive (they are kept on the object)."""
+        self = cls.__new__(cls)
+        self.ctx, self.metric, self.elem_docs = ctx, metric.upper(), elem_docs
+        self.n, self.dim = int(x_dev.shape[0]), int(x_dev.shape[1])
+        self.pendings, self.versions = [], None
+        self._keep = (x_dev, layers_dev)
+        nl = len(layers_dev)
+        RP = (C.c_void_p * nl)(*[t[0].data_ptr() for t in layers_dev])
+        CI = (C.c_void_p * nl)(*[t[1].data_ptr() for t in layers_dev])
+        self.h = C.c_void_p()
+        L.check(L.lib().sdb_hnsw_load_device(ctx.h, self.dim, L.METRIC[self.metric], self.n, C.c_void_p(x_dev.data_ptr()), nl,
+                                             RP, CI, int(entry_point), C.byref(self.h)))
+        return self
+
+    @classmethod
     def from_kv(cls, ctx, dim, state_value, he_items, hn_items_per_layer, metric="EUCLIDEAN", elem_docs=None):
         """Loads the index straight from raw KV values (staging.py): `state_value` = the Hs value, `he_items` =
         [(element id, He value)], `hn_items_per_layer[l]` = [(node id, Hn value)] of layer l (0 first), each in key

@@ -62,7 +62,7 @@ def _merge_reverse(fwd, cnt, m_max, cap=None):
 
 
 def build_layers(ctx, vectors_dev, n, dim, metric="EUCLIDEAN", m=16, m0=32, seed=1, batch=4096, progress=None,
-                 heuristic=True, prefix=False, efc=150, rev_factor=4):
+                 heuristic=True, prefix=False, efc=150, rev_factor=4, levels=None):
     """vectors_dev: torch CUDA float32 tensor (n, dim).  -> (layers, entry_point, levels) with
     layers = [(row_ptr u64[n+1], col_idx u32[e]), ...] (layer 0 first), element id = row index.
     heuristic=True: candidates = 2*m_max nearest, pruned by Heuristic::select on the GPU
@@ -72,7 +72,7 @@ def build_layers(ctx, vectors_dev, n, dim, metric="EUCLIDEAN", m=16, m0=32, seed
     import ctypes as C
     import torch
     from . import _lib as L
-    levels = assign_levels(n, m, seed)
+    levels = assign_levels(n, m, seed) if levels is None else np.asarray(levels, np.int64)
     top = int(levels.max()) if n else 0
     layers = []
     dev = vectors_dev.device
@@ -160,3 +160,140 @@ def build_layers(ctx, vectors_dev, n, dim, metric="EUCLIDEAN", m=16, m0=32, seed
         layers.append((row_ptr, col_idx))
     entry = int(np.argmax(levels)) if n else -1
     return layers, entry, levels
+
+
+def build_incremental(ctx, x, metric="COSINE", m=16, m0=32, efc=150, seed=1, growth=0.25, boot_min=65536,
+                      search_chunk=1 << 16, rev_extra=32, progress=None):
+    """Batched TRUE insertion: the reference inserts one element at a time -- search the current graph
+    with efc, select <= m_max neighbours with the heuristic, link both ways, re-select over-full neighbours
+    (hnsw/mod.rs:297-377, hnsw/layer.rs:342-387).  Here the same four steps run for a whole BATCH of new elements
+    against the graph built so far, with the layer-walk kernel itself as the insertion search
+    (sdb_hnsw_load_device + sdb_hnsw_search_device), Heuristic::select on the GPU (sdb_hnsw_select_neighbors[_ids]) and
+    the linking as a handful of device-side scatter operations.  Batches grow geometrically (`growth` x the current
+    size), so every element is inserted into a graph at least 1 / (1 + growth) of the size it would have seen in the
+    serial algorithm; elements of one batch do not see each other.
+
+    Elements are first re-ordered by level (highest first, random inside a level -- ids are assumed exchangeable), so
+    the upper layers and a bootstrap prefix are complete before the bulk of layer 0 arrives; that prefix (every element
+    of level >= 1, at least `boot_min`) is built by the kNN batch builder above.
+
+    x: torch CUDA float32 (n, dim).  Returns a dict: x (re-ordered copy, device), order (new -> original index, numpy),
+    layers_dev [(row_ptr int64 (n+1), col_idx int32)] layer 0 first (device tensors, CSR over NEW ids), entry (new id),
+    levels (new order)."""
+    import ctypes as C
+    import torch
+    from . import _lib as L
+    n, dim = x.shape
+    dev = x.device
+    levels = assign_levels(n, m, seed)
+    order = np.argsort(-levels, kind="stable")
+    levels = levels[order]
+    x = x.index_select(0, torch.from_numpy(order).to(dev)).contiguous()
+    n_up = int((levels >= 1).sum())
+    n_boot = min(n, max(n_up, boot_min))
+    torch.cuda.synchronize()
+    boot_layers, entry, _ = build_layers(ctx, x[:n_boot], n_boot, dim, metric, m=m, m0=m0, seed=seed, prefix=True, efc=efc,
+                                         levels=levels[:n_boot], progress=progress)
+    n_layers = len(boot_layers)
+    # upper layers are final: CSR over all n ids (rows >= n_boot are empty)
+    upper = []
+    for l in range(1, n_layers):
+        rp, ci = boot_layers[l]
+        rp_full = np.full(n + 1, rp[-1], np.int64)
+        rp_full[: n_boot + 1] = rp.astype(np.int64)
+        upper.append((torch.from_numpy(rp_full).to(dev), torch.from_numpy(ci.astype(np.int32) if ci.size else np.zeros(1, np.int32)).to(dev)))
+    # layer 0 as fixed-width adjacency while it grows
+    adj0 = torch.full((n, m0), -1, dtype=torch.int32, device=dev)
+    deg0 = torch.zeros(n, dtype=torch.int32, device=dev)
+    rp0, ci0 = boot_layers[0]
+    d0 = np.diff(rp0.astype(np.int64))
+    rows = np.repeat(np.arange(n_boot), d0)
+    cols = np.arange(ci0.size) - np.repeat(rp0[:-1].astype(np.int64), d0)
+    adj0[torch.from_numpy(rows).to(dev), torch.from_numpy(cols).to(dev)] = torch.from_numpy(ci0.astype(np.int32)).to(dev)
+    deg0[:n_boot] = torch.from_numpy(d0.astype(np.int32)).to(dev)
+    mcode = L.METRIC[metric.upper()]
+    col_ids = torch.arange(m0, device=dev, dtype=torch.int32)[None, :]
+
+    def csr0():
+        rp = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        rp[1:] = torch.cumsum(deg0.to(torch.int64), 0)
+        ci = adj0[col_ids < deg0[:, None]]
+        if ci.numel() == 0:
+            ci = torch.zeros(1, dtype=torch.int32, device=dev)
+        return rp, ci.contiguous()
+
+    n_cur = n_boot
+    while n_cur < n:
+        b = int(min(n - n_cur, max(4096, int(n_cur * growth))))
+        rp, ci = csr0()
+        lay = [(rp, ci)] + upper
+        RP = (C.c_void_p * n_layers)(*[t[0].data_ptr() for t in lay])
+        CI = (C.c_void_p * n_layers)(*[t[1].data_ptr() for t in lay])
+        h = C.c_void_p()
+        torch.cuda.synchronize()
+        L.check(L.lib().sdb_hnsw_load_device(ctx.h, dim, mcode, n, C.c_void_p(x.data_ptr()), n_layers, RP, CI, int(entry), C.byref(h)))
+        sel = torch.empty((b, m0), dtype=torch.int32, device=dev)
+        scnt = torch.empty((b,), dtype=torch.int32, device=dev)
+        try:
+            for c0 in range(0, b, search_chunk):
+                c1 = min(b, c0 + search_chunk)
+                nqc = c1 - c0
+                cand = torch.empty((nqc, efc), dtype=torch.int64, device=dev)
+                cdist = torch.empty((nqc, efc), dtype=torch.float64, device=dev)
+                ccnt = torch.empty((nqc,), dtype=torch.int32, device=dev)
+                torch.cuda.synchronize()
+                L.check(L.lib().sdb_hnsw_search_device(h, C.c_void_p(x[n_cur + c0].data_ptr()), nqc, efc, efc,
+                                                       C.c_void_p(cand.data_ptr()), C.c_void_p(cdist.data_ptr()),
+                                                       C.c_void_p(ccnt.data_ptr())))
+                L.check(L.lib().sdb_hnsw_select_neighbors(ctx.h, C.c_void_p(x.data_ptr()), dim, mcode, n_cur + c0, nqc,
+                                                          C.c_void_p(cand.data_ptr()), C.c_void_p(ccnt.data_ptr()), efc, m0, 1,
+                                                          C.c_void_p(sel[c0:c1].data_ptr()), C.c_void_p(scnt[c0:c1].data_ptr())))
+                del cand, cdist, ccnt
+        finally:
+            L.lib().sdb_hnsw_destroy(h)
+        # ---- link: forward edges of the new elements, then the reverse edges into the existing graph ----
+        valid = col_ids < scnt[:, None]
+        adj0[n_cur:n_cur + b] = torch.where(valid, sel, torch.full_like(sel, -1))
+        deg0[n_cur:n_cur + b] = scnt
+        src = torch.arange(n_cur, n_cur + b, device=dev, dtype=torch.int32)[:, None].expand(b, m0)[valid]
+        dst = sel[valid].to(torch.int64)
+        dst_s, perm = torch.sort(dst, stable=True)
+        src_s = src[perm]
+        uniq, counts = torch.unique_consecutive(dst_s, return_counts=True)
+        start = torch.cumsum(counts, 0) - counts
+        rank = torch.arange(dst_s.numel(), device=dev) - torch.repeat_interleave(start, counts)
+        pos = deg0[dst_s].to(torch.int64) + rank
+        ok = pos < m0
+        adj0[dst_s[ok], pos[ok]] = src_s[ok]
+        new_deg = deg0[uniq].to(torch.int64) + counts
+        deg0[uniq] = torch.clamp(new_deg, max=m0).to(torch.int32)
+        over = new_deg > m0
+        ov_nodes = uniq[over]
+        n_ov = int(ov_nodes.numel())
+        if n_ov:
+            # re-select the over-full nodes among their m0 current edges + the reverse edges that did not fit
+            kc = m0 + rev_extra
+            union = torch.full((n_ov, kc), 0, dtype=torch.int64, device=dev)
+            union[:, :m0] = adj0[ov_nodes].to(torch.int64)
+            node_slot = torch.full((n,), -1, dtype=torch.int64, device=dev)
+            node_slot[ov_nodes] = torch.arange(n_ov, device=dev)
+            ex_dst, ex_src, ex_rank = dst_s[~ok], src_s[~ok], (pos[~ok] - m0)
+            keep = ex_rank < rev_extra
+            union[node_slot[ex_dst[keep]], m0 + ex_rank[keep]] = ex_src[keep].to(torch.int64)
+            ucnt = (m0 + torch.clamp(new_deg[over] - m0, max=rev_extra)).to(torch.int32)
+            out = torch.empty((n_ov, m0), dtype=torch.int32, device=dev)
+            ocnt = torch.empty((n_ov,), dtype=torch.int32, device=dev)
+            ids32 = ov_nodes.to(torch.int32).contiguous()
+            torch.cuda.synchronize()
+            L.check(L.lib().sdb_hnsw_select_neighbors_ids(ctx.h, C.c_void_p(x.data_ptr()), dim, mcode, C.c_void_p(ids32.data_ptr()),
+                                                          n_ov, C.c_void_p(union.data_ptr()), C.c_void_p(ucnt.data_ptr()), kc, m0, 0,
+                                                          C.c_void_p(out.data_ptr()), C.c_void_p(ocnt.data_ptr())))
+            v2 = col_ids < ocnt[:, None]
+            adj0[ov_nodes] = torch.where(v2, out, torch.full_like(out, -1))
+            deg0[ov_nodes] = ocnt
+            del union, node_slot, out, ocnt
+        if progress:
+            progress(0, n_cur + b, n)
+        n_cur += b
+    rp, ci = csr0()
+    return {"x": x, "order": order, "layers_dev": [(rp, ci)] + upper, "entry": int(entry), "levels": levels}

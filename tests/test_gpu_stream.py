@@ -85,7 +85,8 @@ def test_streaming_on_sorted_and_clustered_corpora(ctx):
         check_queries(col, corpus, queries, "COSINE", k, (0, 13, 63))
         st = col.stats()
         assert st["n_fallback"] <= 2 + nq // 64, st  # big candidate sets are re-ranked, not sent to the exact kernel
-        assert st["n_candidates"] > 200, st   # ... and they ARE big here (2000 rows per cluster)
+        assert st["n_survivors"] > 200 * nq, st  # ... and they ARE big here (2000 rows per cluster); the f32 stage
+        assert st["n_candidates"] < 200, st      # then narrows them to a few near-ties before the f64 re-rank
     # the same through the multi-pass schedule
     col = make_col(ctx, corpus, "COSINE", "TC_BF16", streaming=False)
     check_queries(col, corpus, queries, "COSINE", k, (5, 40))
