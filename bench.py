@@ -312,6 +312,7 @@ def main():
         # stdout carries exactly ONE JSON line: NCCL_DEBUG=VERSION would print a banner there at communicator creation
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # the version banner / warnings must not land on stdout
         dist.init_process_group("nccl", device_id=dev)
         # the library owns its NCCL communicator: rank 0's unique id travels over the launcher's process group
         uid = torch.zeros(128, dtype=torch.uint8, device=dev)

@@ -143,6 +143,7 @@ def bench_graph(a):
         import torch.distributed as dist
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # the version banner / warnings must not land on stdout
         dist.init_process_group("nccl", device_id=dev)
         uid = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:

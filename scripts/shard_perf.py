@@ -55,11 +55,9 @@ def run(label, env=None, schedule=True, screen="AUTO", depth=2):
         os.environ.pop(kk, None)
 
 
-run("streaming (default)")
-run("probe 64 tiles", env={"SDB_PROBE_TILES": "64"})
-run("refiner sleep 2048..16384", env={"SDB_REFINE_SLEEP_MIN": "2048", "SDB_REFINE_SLEEP_MAX": "16384"})
-run("probe 64 + sleep 2048", env={"SDB_PROBE_TILES": "64", "SDB_REFINE_SLEEP_MIN": "2048", "SDB_REFINE_SLEEP_MAX": "16384"})
-run("refiner sleep 128..2048", env={"SDB_REFINE_SLEEP_MIN": "128", "SDB_REFINE_SLEEP_MAX": "2048"})
+run("streaming, 2 streams (default)")
+run("one stream", env={"SDB_ONE_STREAM": "1"})
+run("2 streams depth 3", depth=3)
+run("2 streams depth 1", depth=1)
 run("multipass", schedule=False)
-run("streaming bf16", screen="TC_BF16")
-run("streaming (default) again")
+run("streaming, 2 streams again")

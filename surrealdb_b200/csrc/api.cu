@@ -116,6 +116,19 @@ static std::vector<Rung> build_rungs(Corpus* c, uint32_t k, sdb_screen* first) {
   return r;
 }
 
+// swap the ticket's scratch set into the corpus' active fields (see Scratch in internal.cuh)
+static void activate_set(Corpus* c, int set) {
+  if (c->active_set == set) return;
+  c->sets[c->active_set] = static_cast<Scratch&>(*c);
+  static_cast<Scratch&>(*c) = c->sets[set];
+  c->active_set = set;
+}
+static cudaError_t drain(Ctx* ctx) {  // both batch streams idle
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  const cudaError_t e2 = cudaStreamSynchronize(ctx->stream2);
+  return e != cudaSuccess ? e : e2;
+}
+
 // ---- one batch = enqueue (no host synchronisation) + finish (event wait, ladder, exact fallbacks) ----------------
 static sdb_status ticket_prepare(Corpus* c, Ticket& t, uint32_t nq) {
   if (!t.ev_begin) {
@@ -141,7 +154,8 @@ static sdb_status ticket_prepare(Corpus* c, Ticket& t, uint32_t nq) {
 
 static sdb_status enqueue_batch(Corpus* c, Ticket& t) {
   Ctx* ctx = c->ctx;
-  cudaStream_t st = ctx->stream;
+  cudaStream_t st = t.stream;
+  activate_set(c, t.set);
   const uint32_t nq = t.nq, k = t.k;
   sdb_screen first;
   const std::vector<Rung> rungs = build_rungs(c, k, &first);
@@ -206,11 +220,13 @@ static sdb_status enqueue_batch(Corpus* c, Ticket& t) {
   SDB_CUDA(cudaEventRecord(t.ev_screen1, st));
   // stage B: the coarse screens' candidates are re-scored in f32 and narrowed before the (FP64-bound) exact re-rank
   static const bool no_refine = getenv("SDB_NO_REFINE") != nullptr;
+  bool refined = false;
   if (tc && c->exact && c->dtype == SDB_F32 && !no_refine) {
     SDB_TRY(cand_refine(c, nq, st));
     SDB_TRY(cand_select(c, nq, k, false, 0u, false, st, 1));
+    refined = true;
   }
-  SDB_TRY(cand_rerank(c, nq, st));
+  SDB_TRY(cand_rerank(c, nq, st, refined));
   SDB_TRY(cand_final(c, nq, k, t.row_base, t.d_out_rows, t.d_out_dist, t.d_out_count, st));
   SDB_CUDA(cudaMemcpyAsync(t.h_flags, c->d_flags, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, st));
   SDB_CUDA(cudaMemcpyAsync(t.h_qflags, c->d_qflags, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, st));
@@ -220,7 +236,7 @@ static sdb_status enqueue_batch(Corpus* c, Ticket& t) {
 }
 
 static sdb_status copy_out(Corpus* c, Ticket& t) {  // host-buffer entry points: device result -> caller's buffers
-  cudaStream_t st = c->ctx->stream;
+  cudaStream_t st = t.stream;
   if (!t.h_out_count) return SDB_OK;
   if (t.k) {
     SDB_CUDA(cudaMemcpyAsync(t.h_out_rows, t.d_out_rows, sizeof(uint64_t) * (size_t)t.nq * t.k, cudaMemcpyDeviceToHost, st));
@@ -235,7 +251,7 @@ static sdb_status copy_out(Corpus* c, Ticket& t) {  // host-buffer entry points:
 // changed after the batch's own kernels had produced it.
 static sdb_status finish_local(Corpus* c, Ticket& t, uint32_t* n_fallback, bool* repaired) {
   Ctx* ctx = c->ctx;
-  cudaStream_t st = ctx->stream;
+  cudaStream_t st = t.stream;
   const uint32_t nq = t.nq, k = t.k;
   *repaired = false;
   *n_fallback = 0;
@@ -245,7 +261,7 @@ static sdb_status finish_local(Corpus* c, Ticket& t, uint32_t* n_fallback, bool*
       uint32_t n_fail = 0;
       for (uint32_t q = 0; q < nq; q++) n_fail += (t.h_flags[q] & 2u) ? 1u : 0u;
       if (n_fail <= 2 + nq / 64) break;
-      SDB_CUDA(cudaStreamSynchronize(st));  // later batches in flight use the shared scratch: drain them first
+      SDB_CUDA(drain(ctx));  // later batches in flight share scratch sets and the ladder state: drain them first
       t.rung++;
       SDB_TRY(enqueue_batch(c, t));
       SDB_CUDA(cudaEventSynchronize(t.ev_end));
@@ -270,7 +286,7 @@ static sdb_status finish_local(Corpus* c, Ticket& t, uint32_t* n_fallback, bool*
       return SDB_ECANCELLED;
     }
     if (!drained) {
-      SDB_CUDA(cudaStreamSynchronize(st));
+      SDB_CUDA(drain(ctx));  // the exact kernel's scratch (keys, fallback query) is shared by all batches
       drained = true;
     }
     SDB_TRY(prep_fallback_query(c, t.d_queries + (size_t)q * c->dim, st));
@@ -322,6 +338,14 @@ static sdb_status submit_locked(Corpus* c, Ticket* t, const double* d_queries, u
     return SDB_ECANCELLED;
   }
   SDB_TRY(ticket_prepare(c, *t, nq ? nq : 1));
+  {  // slot parity picks the stream and the scratch set: consecutive batches overlap (screen of i+1 || tail of i)
+    const int slot = (int)(t - c->tickets);
+    const bool one_stream = getenv("SDB_ONE_STREAM") != nullptr;  // (A/B knob)
+    t->set = one_stream ? 0 : (slot & 1);
+    t->stream = t->set ? c->ctx->stream2 : c->ctx->stream;
+    if (t->wait_h2d) SDB_CUDA(cudaStreamWaitEvent(t->stream, t->ev_h2d, 0));
+    t->wait_h2d = false;
+  }
   t->id = c->next_ticket++;
   if (c->next_ticket == 0) c->next_ticket = 1;
   t->d_queries = d_queries;
@@ -338,7 +362,7 @@ static sdb_status submit_locked(Corpus* c, Ticket* t, const double* d_queries, u
   t->rung = (c->rung_scr == first && c->rung_k == k && c->rung < rungs.size()) ? c->rung : 0;
   t->n_rungs = (uint32_t)rungs.size();
   if (nq == 0 || k == 0) {  // nothing to search: counts are zero
-    cudaStream_t st = c->ctx->stream;
+    cudaStream_t st = t->stream;
     SDB_CUDA(cudaEventRecord(t->ev_begin, st));
     SDB_CUDA(cudaEventRecord(t->ev_screen0, st));
     SDB_CUDA(cudaEventRecord(t->ev_screen1, st));
@@ -386,6 +410,7 @@ sdb_status knn_submit_for_shard(Corpus* c, const double* d_queries, const double
     return SDB_EOVERFLOW;
   }
   *slot_index = (int)(t - c->tickets);
+  bool h2d_pending = false;
   if (h_queries) {  // host queries: staged through the slot's device buffer on the copy stream
     SDB_TRY(ticket_prepare(c, *t, nq));
     const size_t need_q = (size_t)nq * c->dim;
@@ -399,13 +424,18 @@ sdb_status knn_submit_for_shard(Corpus* c, const double* d_queries, const double
     cudaStream_t cs = c->ctx->copy_stream;
     SDB_CUDA(cudaMemcpyAsync(t->d_in_q, h_queries, sizeof(double) * need_q, cudaMemcpyHostToDevice, cs));
     SDB_CUDA(cudaEventRecord(t->ev_h2d, cs));
-    SDB_CUDA(cudaStreamWaitEvent(c->ctx->stream, t->ev_h2d, 0));
     d_queries = t->d_in_q;
+    h2d_pending = true;
   }
+  t->wait_h2d = h2d_pending;
   SDB_TRY(submit_locked(c, t, d_queries, nq, k, c->row_base, d_out_rows, d_out_dist, d_out_count, nullptr));
   *ticket = t->id;
   *d_queries_used = d_queries;
   return SDB_OK;
+}
+cudaStream_t knn_ticket_stream(Corpus* c, uint32_t ticket) {
+  Ticket* t = find_ticket(c, ticket);
+  return t ? t->stream : c->ctx->stream;
 }
 sdb_status knn_finish_for_shard(Corpus* c, uint32_t ticket, bool* repaired) {
   Ticket* t = find_ticket(c, ticket);
@@ -549,6 +579,7 @@ sdb_status sdb_ctx_create(int device, sdb_ctx** out) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   SDB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  SDB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
   SDB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   {
     int* hc = nullptr;
@@ -577,6 +608,7 @@ void sdb_ctx_destroy(sdb_ctx* c) {
   cudaSetDevice(c->device);
   comm_destroy(c);
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->h_cancel) cudaFreeHost((void*)c->h_cancel);
@@ -645,9 +677,18 @@ sdb_status sdb_corpus_create(sdb_ctx* ctx, uint32_t dim, sdb_dtype dt, sdb_metri
 void sdb_corpus_destroy(sdb_corpus* c) {
   if (!c) return;
   cudaSetDevice(c->ctx->device);
-  cudaStreamSynchronize(c->ctx->stream);
+  drain(c->ctx);
+  for (int si = 0; si < 2; si++) {  // the parked scratch set
+    if (si == c->active_set) continue;
+    Scratch& z = c->sets[si];
+    void* sp[] = {z.d_q64, z.d_q32, z.d_qbf16, z.d_qmag, z.d_qflags, z.d_qbferr, z.d_q8, z.d_q8scale, z.d_q8err, z.d_sub,
+                  z.d_sub_cnt, z.d_bscale, z.d_beps, z.d_margin, z.d_margin2, z.d_beps2, z.d_tau2, z.d_qlow, z.d_qcap,
+                  z.d_hparam, z.d_hist, z.d_probe, z.d_tau, z.d_cand, z.d_cand_cnt, z.d_flags, z.d_stat, z.d_rr_key,
+                  z.d_rr_dist, z.d_rr_row};
+    for (void* p : sp) cudaFree(p);
+  }
   void* ptrs[] = {c->d_i8, c->d_q8, c->d_q8scale, c->d_q8err, c->d_bscale, c->d_beps, c->d_margin, c->d_qlow, c->d_qcap,
-                  c->d_hparam, c->d_hist, c->d_qbferr, c->d_stat, c->d_sub, c->d_sub_cnt, c->d_rows, c->d_mag, c->d_snorm,
+                  c->d_hparam, c->d_hist, c->d_qbferr, c->d_stat, c->d_probe, c->d_margin2, c->d_beps2, c->d_tau2, c->d_sub, c->d_sub_cnt, c->d_rows, c->d_mag, c->d_snorm,
                   c->d_bf16, c->d_skip, c->d_removed, c->d_special, c->d_q64, c->d_q32, c->d_qbf16, c->d_qmag, c->d_qflags,
                   c->d_tau, c->d_cand, c->d_cand_cnt, c->d_flags, c->d_rr_key, c->d_rr_dist, c->d_rr_row, c->d_ex_key,
                   c->d_sel, c->d_fb_q, c->d_fb_qmag, c->d_fb_qflags, c->d_block, c->d_gather};
@@ -730,7 +771,7 @@ sdb_status sdb_corpus_remove(sdb_corpus* c, const uint64_t* row_ids, uint64_t n)
       return SDB_EINVAL;
     }
   SDB_CUDA(cudaSetDevice(c->ctx->device));
-  SDB_CUDA(cudaStreamSynchronize(c->ctx->stream));  // no batch may be in flight while rows disappear
+  SDB_CUDA(drain(c->ctx));  // no batch may be in flight while rows disappear
   SDB_TRY(corpus_remove_device(c, row_ids, n));
   c->n_removed += n;
   return SDB_OK;
@@ -833,17 +874,17 @@ static sdb_status submit_host_locked(sdb_corpus* c, const double* queries, uint3
   SDB_TRY(ticket_prepare(c, *t, nq));
   SDB_TRY(ensure_slot_buffers(c, t, nq, k));
   // the queries travel on the copy stream, so the transfer of batch i+1 overlaps the kernels of batch i
-  cudaStream_t cs = c->ctx->copy_stream, st = c->ctx->stream;
+  cudaStream_t cs = c->ctx->copy_stream;
   SDB_CUDA(cudaMemcpyAsync(t->d_in_q, queries, sizeof(double) * (size_t)nq * c->dim, cudaMemcpyHostToDevice, cs));
   SDB_CUDA(cudaEventRecord(t->ev_h2d, cs));
-  SDB_CUDA(cudaStreamWaitEvent(st, t->ev_h2d, 0));
+  t->wait_h2d = true;  // submit_locked makes the batch's stream wait for the transfer
   SDB_TRY(submit_locked(c, t, t->d_in_q, nq, k, c->row_base, t->d_res_rows, t->d_res_dist, t->d_res_count, cancel));
   t->h_out_rows = out_rows;
   t->h_out_dist = out_dist;
   t->h_out_count = out_count;
   const sdb_status rc = copy_out(c, *t);
   if (rc != SDB_OK) {
-    cudaStreamSynchronize(st);
+    cudaStreamSynchronize(t->stream);
     t->busy = false;
     return rc;
   }
@@ -920,6 +961,7 @@ sdb_status sdb_corpus_project(sdb_corpus* c, const double* query, int fn, double
   }
   if (c->n == 0) return SDB_OK;
   SDB_CUDA(cudaSetDevice(c->ctx->device));
+  SDB_CUDA(drain(c->ctx));  // borrows the active scratch set for the prepared query
   cudaStream_t st = c->ctx->stream;
   double *d_q = nullptr, *d_vals = nullptr;
   auto run = [&]() -> sdb_status {

@@ -303,6 +303,8 @@ sdb_status cand_set_count(Corpus* c, uint32_t nq, uint32_t value, cudaStream_t s
   return SDB_OK;
 }
 
+constexpr uint32_t SEL_SMEM_KEYS = 1408;  // 11 KB: cand_select fits beside a resident screen CTA (15 KB are free)
+
 __device__ __forceinline__ Cand key_to_cand(uint64_t key) {
   uint32_t fk = (uint32_t)(key >> 32);
   fk = (fk >> 31) ? (fk & 0x7fffffffu) : ~fk;
@@ -390,8 +392,12 @@ __global__ void __launch_bounds__(256) cand_select_kernel(Cand* __restrict__ can
                                                            const uint32_t* __restrict__ sub_cnt, uint32_t n_slots,
                                                            uint32_t subcap, HistParam* __restrict__ hparam,
                                                            uint32_t* __restrict__ hist, const float* __restrict__ qlow,
-                                                           const float* __restrict__ qcap, uint32_t* __restrict__ stat) {
-  extern __shared__ uint64_t s_keys[];
+                                                           const float* __restrict__ qcap, uint32_t* __restrict__ stat,
+                                                           uint64_t* __restrict__ g_keys, uint32_t g_stride) {
+  // keys live in a small shared-memory window (the kernel must fit next to a resident screen CTA: 12 KB); a query that
+  // gathered more -- a tight cluster -- sorts in its row of the (still unused) re-rank key buffer instead
+  __shared__ uint64_t s_keys_win[SEL_SMEM_KEYS];
+  __shared__ uint32_t s_upper;
   __shared__ uint32_t s_n, s_over;
   __shared__ uint32_t s_hist[256];
   __shared__ uint64_t s_prefix;
@@ -404,9 +410,22 @@ __global__ void __launch_bounds__(256) cand_select_kernel(Cand* __restrict__ can
     s_prefix = 0;
     s_remaining = k;
     s_out = 0;
+    s_upper = n_main > cap ? cap : n_main;
   }
   if (n_main > cap) n_main = cap;
   __syncthreads();
+  {  // upper bound of what the gather can produce decides where the keys go (uniform per block)
+    uint32_t part = 0;
+    for (uint32_t s = threadIdx.x; s < n_slots; s += blockDim.x) {
+      const uint32_t c = sub_cnt[(size_t)q * n_slots + s];
+      part += c > subcap ? subcap : c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31u) == 0 && part) atomicAdd(&s_upper, part);
+  }
+  __syncthreads();
+  uint64_t* s_keys = s_upper > SEL_SMEM_KEYS ? g_keys + (size_t)q * g_stride : s_keys_win;
   auto push = [&](Cand cd) {
     float sc = cd.score;
     if (snorm) {  // integer screens score invalid rows 0: the row's NaN screening norm marks them
@@ -529,19 +548,18 @@ __global__ void __launch_bounds__(256) cand_select_kernel(Cand* __restrict__ can
 
 sdb_status cand_select(Corpus* c, uint32_t nq, uint32_t k, bool drop_invalid, uint32_t n_slots, bool seed_hist,
                        cudaStream_t st, int stage) {
-  const size_t smem = sizeof(uint64_t) * c->sc_cap;
   if (stage == 1) {  // stage B: the lists hold f32 scores now; own threshold / margin, nothing else to gather
-    cand_select_kernel<<<nq, 256, smem, st>>>(c->d_cand, c->d_cand_cnt, c->d_tau2, c->d_flags, c->sc_cap, k, c->d_margin2,
-                                              nullptr, c->d_sub, c->d_sub_cnt, 0u, c->sub_cap, nullptr, c->d_hist, c->d_qlow,
-                                              c->d_qcap, nullptr);
+    cand_select_kernel<<<nq, 256, 0, st>>>(c->d_cand, c->d_cand_cnt, c->d_tau2, c->d_flags, c->sc_cap, k, c->d_margin2,
+                                           nullptr, c->d_sub, c->d_sub_cnt, 0u, c->sub_cap, nullptr, c->d_hist, c->d_qlow,
+                                           c->d_qcap, nullptr, c->d_rr_key, c->rr_stride);
     count_launch(c->ctx);
     SDB_CUDA(cudaGetLastError());
     return SDB_OK;
   }
-  cand_select_kernel<<<nq, 256, smem, st>>>(  // 256 threads: several blocks per SM, the whole batch is one wave
+  cand_select_kernel<<<nq, 256, 0, st>>>(  // 256 threads: several blocks per SM, the whole batch is one wave
       c->d_cand, c->d_cand_cnt, c->d_tau, c->d_flags, c->sc_cap, k, c->d_margin, drop_invalid ? c->d_snorm : nullptr,
       c->d_sub, c->d_sub_cnt, n_slots, c->sub_cap, seed_hist ? c->d_hparam : nullptr, c->d_hist, c->d_qlow, c->d_qcap,
-      c->d_stat);
+      c->d_stat, c->d_rr_key, c->rr_stride);
   count_launch(c->ctx);
   SDB_CUDA(cudaGetLastError());
   return SDB_OK;
@@ -556,7 +574,7 @@ sdb_status cand_select(Corpus* c, uint32_t nq, uint32_t k, bool drop_invalid, ui
 // "keep everything within 2.1 x the bound of the k-th best" (cand_select, stage 1) shrinks the set to k plus a few
 // near-ties, and only those reach the f64 kernel.
 template <bool COSINE>
-__global__ void __launch_bounds__(256) cand_refine_f32_kernel(const float* __restrict__ rows, uint32_t dim,
+__global__ void __launch_bounds__(128) cand_refine_f32_kernel(const float* __restrict__ rows, uint32_t dim,
                                                                const float* __restrict__ snorm,
                                                                const float* __restrict__ q32, Cand* __restrict__ cand,
                                                                const uint32_t* __restrict__ cnt, uint32_t cap) {
@@ -564,9 +582,9 @@ __global__ void __launch_bounds__(256) cand_refine_f32_kernel(const float* __res
   const uint32_t n_c = cnt[q] < cap ? cnt[q] : cap;
   const float* qv = q32 + (size_t)q * dim;
   Cand* cq = cand + (size_t)q * cap;
-  const uint32_t warps_total = gridDim.y * 8;
+  const uint32_t warps_total = gridDim.y * 4;
   const bool vec4 = (dim & 3u) == 0;
-  for (uint32_t e0 = (blockIdx.y * 8 + warp) * 2; e0 < n_c; e0 += warps_total * 2) {  // two rows per warp in flight
+  for (uint32_t e0 = (blockIdx.y * 4 + warp) * 2; e0 < n_c; e0 += warps_total * 2) {  // two rows per warp in flight
     const uint32_t r0 = cq[e0].row;
     const bool has1 = e0 + 1 < n_c;
     const uint32_t r1 = has1 ? cq[e0 + 1].row : r0;
@@ -605,12 +623,12 @@ __global__ void __launch_bounds__(256) cand_refine_f32_kernel(const float* __res
 }
 sdb_status cand_refine(Corpus* c, uint32_t nq, cudaStream_t st) {
   if (c->dtype != SDB_F32) return SDB_OK;
-  const dim3 grid(nq, 4);
+  const dim3 grid(nq, 8);  // 128-thread blocks (register budget beside a resident screen CTA)
   if (c->metric == SDB_COSINE)
-    cand_refine_f32_kernel<true><<<grid, 256, 0, st>>>((const float*)c->d_rows, c->dim, c->d_snorm, c->d_q32, c->d_cand,
+    cand_refine_f32_kernel<true><<<grid, 128, 0, st>>>((const float*)c->d_rows, c->dim, c->d_snorm, c->d_q32, c->d_cand,
                                                        c->d_cand_cnt, c->sc_cap);
   else
-    cand_refine_f32_kernel<false><<<grid, 256, 0, st>>>((const float*)c->d_rows, c->dim, c->d_snorm, c->d_q32, c->d_cand,
+    cand_refine_f32_kernel<false><<<grid, 128, 0, st>>>((const float*)c->d_rows, c->dim, c->d_snorm, c->d_q32, c->d_cand,
                                                         c->d_cand_cnt, c->sc_cap);
   count_launch(c->ctx);
   SDB_CUDA(cudaGetLastError());
@@ -628,7 +646,7 @@ constexpr uint32_t QCHUNK = 1024;  // query columns staged in shared memory per 
 
 constexpr uint32_t RR_GROUPS_Y = 4;  // blocks per query; block y takes the groups y, y + 4, ... of its query
 
-template <typename T, int WARPS, int COLS>
+template <typename T, int WARPS, int COLS, int QC = QCHUNK>
 __global__ void __launch_bounds__(WARPS * 32) cand_rerank_kernel(
     const T* __restrict__ rows, uint32_t dim, int metric, const double* __restrict__ mag,
     const double* __restrict__ q64, const double* __restrict__ qmag, const uint32_t* __restrict__ qflags,
@@ -637,7 +655,7 @@ __global__ void __launch_bounds__(WARPS * 32) cand_rerank_kernel(
     uint32_t rr_stride) {
   constexpr int NL = COLS / 32;  // 128-byte segments per row and step
   __shared__ T tile[WARPS][32][COLS + 1];
-  __shared__ double s_q[QCHUNK];
+  __shared__ double s_q[QC];
   const uint32_t q = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t n_c = cnt[q] < cap ? cnt[q] : cap;
   const uint32_t n_e = n_c + n_special;
@@ -650,8 +668,8 @@ __global__ void __launch_bounds__(WARPS * 32) cand_rerank_kernel(
     else if (e < n_e) my_row = special[e - n_c];
     const bool warp_active = e_first + warp * 32 < n_e;
     ExactAcc acc;
-    for (uint32_t cb = 0; cb < dim; cb += QCHUNK) {
-      const uint32_t cw = dim - cb < QCHUNK ? dim - cb : QCHUNK;
+    for (uint32_t cb = 0; cb < dim; cb += QC) {
+      const uint32_t cw = dim - cb < (uint32_t)QC ? dim - cb : (uint32_t)QC;
       __syncthreads();
       for (uint32_t i = threadIdx.x; i < cw; i += blockDim.x) s_q[i] = q64[(size_t)q * dim + cb + i];
       __syncthreads();
@@ -779,10 +797,17 @@ __global__ void __launch_bounds__(WARPS * 32) cand_rerank_v4_kernel(
 }
 constexpr size_t RRV_SMEM = sizeof(double) * QCHUNK + sizeof(float) * 4 * 32 * RRV_STRIDE;  // 4 warps: 75.8 KB
 
-sdb_status cand_rerank(Corpus* c, uint32_t nq, cudaStream_t st) {
+sdb_status cand_rerank(Corpus* c, uint32_t nq, cudaStream_t st, bool small_sets) {
   const dim3 grid(nq, RR_GROUPS_Y);
   static const bool no_v4 = getenv("SDB_RERANK_SCALAR") != nullptr;
-  if (c->dtype == SDB_F32 && c->dim % 4 == 0 && !no_v4)
+  if (small_sets && c->dtype == SDB_F32)
+    // after the f32 stage a query keeps k plus a few near-ties: the kernel is FP64-bound whatever its shape, so it is
+    // kept small (one warp, 6 KB of shared memory) and runs beside the next batch's screen
+    cand_rerank_kernel<float, 1, 32, 256><<<grid, 32, 0, st>>>((const float*)c->d_rows, c->dim, (int)c->metric, c->d_mag,
+                                                               c->d_q64, c->d_qmag, c->d_qflags, c->d_cand, c->d_cand_cnt,
+                                                               c->sc_cap, c->d_special, c->n_special, c->d_rr_key,
+                                                               c->d_rr_dist, c->d_rr_row, c->rr_stride);
+  else if (c->dtype == SDB_F32 && c->dim % 4 == 0 && !no_v4)
     cand_rerank_v4_kernel<4><<<grid, 128, RRV_SMEM, st>>>((const float*)c->d_rows, c->dim, (int)c->metric, c->d_mag, c->d_q64,
                                                           c->d_qmag, c->d_qflags, c->d_cand, c->d_cand_cnt, c->sc_cap,
                                                           c->d_special, c->n_special, c->d_rr_key, c->d_rr_dist,
@@ -806,9 +831,9 @@ sdb_status cand_rerank(Corpus* c, uint32_t nq, cudaStream_t st) {
 // final ordering + proof.  Entries sorted ascending by (Number::cmp key, row) -- exactly the
 // DistanceEntry order of KnnTopK (knn_topk.rs:61-73): nearest first, earlier scan position wins ties.
 // The candidate count varies per query (a handful on spread-out data, thousands inside a tight cluster), so the sort
-// works on a fixed 1024-entry window: up to 1024 entries are sorted in one go; longer lists are folded in chunks of
-// 768 into the running best 256 (k <= 256 on the screened path).
-constexpr uint32_t FIN_WIN = 1024, FIN_KEEP = 256;
+// works on a fixed 512-entry window: up to 512 entries are sorted in one go; longer lists are folded in chunks of
+// 256 into the running best 256 (k <= 256 on the screened path).
+constexpr uint32_t FIN_WIN = 512, FIN_KEEP = 256;  // 8 KB of shared memory, 256 threads: co-resident with a screen CTA
 
 __device__ __forceinline__ void bitonic_pairs(uint64_t* s_key, uint64_t* s_idx, uint32_t p2) {
   for (uint32_t kk = 2; kk <= p2; kk <<= 1) {
@@ -830,7 +855,7 @@ __device__ __forceinline__ void bitonic_pairs(uint64_t* s_key, uint64_t* s_idx, 
   }
 }
 
-__global__ void __launch_bounds__(512) cand_final_kernel(
+__global__ void __launch_bounds__(256) cand_final_kernel(
     const uint64_t* __restrict__ rr_key, const double* __restrict__ rr_dist, const uint32_t* __restrict__ rr_row,
     uint32_t rr_stride, const uint32_t* __restrict__ cnt, uint32_t cap, uint32_t n_special,
     const float* __restrict__ tau, const double* __restrict__ qmag, const float* __restrict__ bscale,
@@ -930,7 +955,7 @@ sdb_status cand_final(Corpus* c, uint32_t nq, uint32_t k, uint64_t row_base, uin
     return SDB_EINVAL;
   }
   static const int debug = getenv("SDB_DEBUG") != nullptr;
-  cand_final_kernel<<<nq, 512, 0, st>>>(c->d_rr_key, c->d_rr_dist, c->d_rr_row, c->rr_stride, c->d_cand_cnt, c->sc_cap,
+  cand_final_kernel<<<nq, 256, 0, st>>>(c->d_rr_key, c->d_rr_dist, c->d_rr_row, c->rr_stride, c->d_cand_cnt, c->sc_cap,
                                         c->n_special, c->d_tau, c->d_qmag, c->d_bscale, c->d_beps, c->d_tau2, c->d_beps2, c->d_flags, c->d_qflags, c->d_stat,
                                         (int)c->metric, k, row_base, d_out_rows, d_out_dist, d_out_count, debug);
   count_launch(c->ctx);
@@ -939,7 +964,6 @@ sdb_status cand_final(Corpus* c, uint32_t nq, uint32_t k, uint64_t row_base, uin
 }
 
 sdb_status candidates_init_device() {
-  SDB_CUDA(cudaFuncSetAttribute(cand_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   SDB_CUDA(cudaFuncSetAttribute(cand_rerank_v4_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RRV_SMEM));
   return SDB_OK;
 }

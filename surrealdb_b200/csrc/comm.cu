@@ -143,6 +143,7 @@ sdb_status knn_submit_for_shard(Corpus* c, const double* d_queries, const double
 sdb_status knn_finish_for_shard(Corpus* c, uint32_t ticket, bool* repaired);
 sdb_status knn_release_ticket(Corpus* c, uint32_t ticket);
 const uint32_t* knn_ticket_stat_host(Corpus* c, uint32_t ticket, int* exact_only);
+cudaStream_t knn_ticket_stream(Corpus* c, uint32_t ticket);
 sdb_status topk_merge_launch(Ctx* ctx, uint32_t n_lists, uint32_t nq, uint32_t k, const uint64_t* d_rows,
                              const double* d_dist, const uint32_t* d_counts, uint64_t stride_rows, uint64_t stride_dist,
                              uint64_t stride_counts, uint64_t* d_out_rows, double* d_out_dist, uint32_t* d_out_count,
@@ -251,7 +252,7 @@ sdb_status phase_local(Corpus* c, const double* d_queries, const double* h_queri
     set_error("internal: ticket slot mismatch (%d vs %d)", used, slot);
     return SDB_EINVAL;
   }
-  cudaStream_t st = c->ctx->stream;
+  cudaStream_t st = knn_ticket_stream(c, ticket);
   int exact_only = 0;
   const uint32_t* h_stat = knn_ticket_stat_host(c, ticket, &exact_only);
   if (exact_only) SDB_CUDA(cudaMemcpyAsync(s.d_block + bl.off_hdr, h_stat, 16, cudaMemcpyHostToDevice, st));
@@ -275,7 +276,7 @@ sdb_status phase_local(Corpus* c, const double* d_queries, const double* h_queri
 sdb_status phase_gather(const Pending& p) {
   Corpus* c = p.c;
   const BlockLayout bl = block_layout(p.nq, p.k);
-  cudaStream_t st = c->ctx->stream;
+  cudaStream_t st = knn_ticket_stream(c, p.ticket);
   if (c->ctx->comm && c->ctx->comm->nranks > 1) {
     SDB_NCCL(g_nccl.AllGather(p.s->d_block, p.s->d_gather, bl.bytes, ncclChar, c->ctx->comm->comm, st));
   } else {
@@ -290,7 +291,7 @@ sdb_status phase_merge(const Pending& p) {
   ShardSlot& s = *p.s;
   const int nranks = c->ctx->comm ? c->ctx->comm->nranks : 1;
   const BlockLayout bl = block_layout(p.nq, p.k);
-  cudaStream_t st = c->ctx->stream;
+  cudaStream_t st = knn_ticket_stream(c, p.ticket);
   if (p.k)
     SDB_TRY(topk_merge_launch(c->ctx, (uint32_t)nranks, p.nq, p.k, (const uint64_t*)(s.d_gather + bl.off_rows),
                               (const double*)(s.d_gather + bl.off_dist), (const uint32_t*)(s.d_gather + bl.off_cnt),
@@ -453,6 +454,7 @@ static sdb_status sharded_submit(sdb_corpus* c, const double* d_queries, const d
     if (rc == SDB_OK) rc = phase_merge(p);
     if (rc != SDB_OK) {
       cudaStreamSynchronize(c->ctx->stream);
+      cudaStreamSynchronize(c->ctx->stream2);
       knn_release_ticket(c, p.ticket);
       return rc;
     }
@@ -543,6 +545,7 @@ sdb_status sdb_knn_sharded_multi(sdb_corpus* const* shards, int n, const double*
   for (int i = 0; i < started; i++) {
     cudaSetDevice(shards[i]->ctx->device);
     cudaStreamSynchronize(shards[i]->ctx->stream);
+    cudaStreamSynchronize(shards[i]->ctx->stream2);
     knn_release_ticket(shards[i], ps[i].ticket);
   }
   return rc;

@@ -121,6 +121,7 @@ struct Ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;      // odd ticket slots: batch i+1 runs here, so its screen overlaps batch i's tail
   cudaStream_t copy_stream = nullptr;  // host<->device copies of the asynchronous entry points
   uint64_t launches = 0;
   std::mutex mu;
@@ -162,6 +163,8 @@ struct Ticket {
   double *d_out_dist = nullptr, *h_out_dist = nullptr;
   uint32_t *d_out_count = nullptr, *h_out_count = nullptr;
   const volatile int* cancel = nullptr;
+  cudaStream_t stream = nullptr;  // every kernel / copy of this batch (slot parity picks the context's stream)
+  int set = 0;                    // scratch set of this batch
   int screen = 0;       // sdb_screen this batch ran
   uint32_t rung = 0, n_rungs = 0;
   uint32_t n_passes = 0;
@@ -178,43 +181,16 @@ struct Ticket {
   uint32_t* d_res_count = nullptr;
   size_t in_cap = 0, res_cap = 0, res_cap_q = 0;
   cudaEvent_t ev_h2d = nullptr, ev_out = nullptr;
+  bool wait_h2d = false;  // the batch's stream still has to wait for ev_h2d (queries travelling on the copy stream)
 };
 constexpr int N_TICKETS = 4;
 
-struct Corpus {
-  Ctx* ctx = nullptr;
-  uint32_t dim = 0, dim_pad = 0;  // dim_pad: bf16 screen copy row length (multiple of 64)
-  sdb_dtype dtype = SDB_F32;
-  sdb_metric metric = SDB_COSINE;
-  sdb_screen screen = SDB_SCREEN_AUTO;
-  bool exact = true;   // false: skip the proof / exact fallback (approximate mode)
-  bool stream_refine = true;  // tensor-core screens: one streaming launch with in-kernel threshold refinement
-  double minkowski_p = 3.0;   // order of SDB_MINKOWSKI
-  sdb_screen rung_scr = SDB_SCREEN_AUTO;  // the first-choice screen the remembered rung belongs to
-  uint32_t rung_k = 0;                    // ... and the k it was learnt for
-  uint32_t rung = 0;                      // rung of the precision ladder the last batch settled on (api.cu)
-  uint32_t sc_gen = 0;                    // bumped whenever the per-query scratch is reallocated
-  uint64_t cap = 0, n = 0;
-  uint64_t row_base = 0;            // global id of row 0 (row-sharded corpora)
-  bool finalized = false;
-  void* d_rows = nullptr;           // master copy, cap x dim (f32 or f64)
-  double* d_mag = nullptr;          // exact f64 magnitude per row (reference arithmetic)
-  float* d_snorm = nullptr;         // cosine: 1/|x| ; euclid: |x|^2 ; NaN = never a screen candidate
-  __nv_bfloat16* d_bf16 = nullptr;  // screen copy cap_pad x dim_pad (rows padded to TILE_ROWS)
-  float bf16_rel_err = 0.00390625f; // max over rows of |x - bf16(x)| / |x| (measured at finalize, rounded up)
-  int8_t* d_i8 = nullptr;           // int8 screen copy cap_pad x dim_pad8 of the normalised rows (one global scale), cosine only
-  uint32_t dim_pad8 = 0;            // multiple of 128
-  float max_rel_qerr = 0.f;         // max over rows of |x/|x| - s * x8|
-  float i8_scale = 1.f;             // global scale s of the int8 copy
-  uint8_t* d_skip = nullptr;        // optional skip mask
-  uint8_t* d_removed = nullptr;     // tombstones (sdb_corpus_remove); OR-ed with the skip mask at finalize
-  uint64_t n_removed = 0;
-  uint32_t* d_special = nullptr;    // rows ranked exactly on every query
-  uint32_t n_special = 0;
-  uint32_t n_outliers = 0;          // of those: rows made special because one component dominates (int8 scale)
-  bool special_overflow = false;
-  float max_norm = 0.f;
-  // ---- search scratch (grown on demand) ----
+// Per-batch search scratch.  Two sets exist per corpus: consecutive batches alternate between them (and between the
+// context's two streams), so the screen of batch i+1 can run while the tail of batch i (candidate selection, f32
+// re-score, exact re-rank, final ordering, all-gather + merge) is still in flight.  The Corpus object itself carries
+// the ACTIVE set's fields (it derives from Scratch): enqueue_batch swaps the ticket's set in before it launches
+// anything, and every launch captures the pointers by value.
+struct Scratch {
   uint32_t sc_nq = 0, sc_cap = 0;
   double* d_q64 = nullptr;
   float* d_q32 = nullptr;
@@ -248,6 +224,41 @@ struct Corpus {
   double* d_rr_dist = nullptr;
   uint32_t* d_rr_row = nullptr;
   uint32_t rr_stride = 0;
+  uint32_t sc_gen = 0;           // bumped whenever this set is reallocated
+};
+
+struct Corpus : Scratch {
+  Ctx* ctx = nullptr;
+  uint32_t dim = 0, dim_pad = 0;  // dim_pad: bf16 screen copy row length (multiple of 64)
+  sdb_dtype dtype = SDB_F32;
+  sdb_metric metric = SDB_COSINE;
+  sdb_screen screen = SDB_SCREEN_AUTO;
+  bool exact = true;   // false: skip the proof / exact fallback (approximate mode)
+  bool stream_refine = true;  // tensor-core screens: one streaming launch with in-kernel threshold refinement
+  double minkowski_p = 3.0;   // order of SDB_MINKOWSKI
+  sdb_screen rung_scr = SDB_SCREEN_AUTO;  // the first-choice screen the remembered rung belongs to
+  uint32_t rung_k = 0;                    // ... and the k it was learnt for
+  uint32_t rung = 0;                      // rung of the precision ladder the last batch settled on (api.cu)
+  uint64_t cap = 0, n = 0;
+  uint64_t row_base = 0;            // global id of row 0 (row-sharded corpora)
+  bool finalized = false;
+  void* d_rows = nullptr;           // master copy, cap x dim (f32 or f64)
+  double* d_mag = nullptr;          // exact f64 magnitude per row (reference arithmetic)
+  float* d_snorm = nullptr;         // cosine: 1/|x| ; euclid: |x|^2 ; NaN = never a screen candidate
+  __nv_bfloat16* d_bf16 = nullptr;  // screen copy cap_pad x dim_pad (rows padded to TILE_ROWS)
+  float bf16_rel_err = 0.00390625f; // max over rows of |x - bf16(x)| / |x| (measured at finalize, rounded up)
+  int8_t* d_i8 = nullptr;           // int8 screen copy cap_pad x dim_pad8 of the normalised rows (one global scale), cosine only
+  uint32_t dim_pad8 = 0;            // multiple of 128
+  float max_rel_qerr = 0.f;         // max over rows of |x/|x| - s * x8|
+  float i8_scale = 1.f;             // global scale s of the int8 copy
+  uint8_t* d_skip = nullptr;        // optional skip mask
+  uint8_t* d_removed = nullptr;     // tombstones (sdb_corpus_remove); OR-ed with the skip mask at finalize
+  uint64_t n_removed = 0;
+  uint32_t* d_special = nullptr;    // rows ranked exactly on every query
+  uint32_t n_special = 0;
+  uint32_t n_outliers = 0;          // of those: rows made special because one component dominates (int8 scale)
+  bool special_overflow = false;
+  float max_norm = 0.f;
   // exact path scratch
   uint64_t* d_ex_key = nullptr;  // N keys
   uint32_t* d_sel = nullptr;     // radix-select state
@@ -255,6 +266,8 @@ struct Corpus {
   double* d_fb_q = nullptr;      // fallback query scratch (one query: f64 copy, |q|, flags)
   double* d_fb_qmag = nullptr;
   uint32_t* d_fb_qflags = nullptr;
+  Scratch sets[2];  // the inactive set's fields are parked here (see Scratch)
+  int active_set = 0;
   // asynchronous batches
   Ticket tickets[N_TICKETS];
   uint32_t next_ticket = 1;
@@ -296,7 +309,7 @@ sdb_status cand_select(Corpus* c, uint32_t nq, uint32_t k, bool drop_invalid, ui
 sdb_status cand_refine(Corpus* c, uint32_t nq, cudaStream_t st);
 // after a probe launch over n_tiles tiles: tau = (k-th largest chunk maximum) - margin, histogram geometry, empty lists
 sdb_status cand_seed_from_probe(Corpus* c, uint32_t nq, uint32_t k, uint32_t n_tiles, cudaStream_t st);
-sdb_status cand_rerank(Corpus* c, uint32_t nq, cudaStream_t st);
+sdb_status cand_rerank(Corpus* c, uint32_t nq, cudaStream_t st, bool small_sets = false);
 sdb_status cand_final(Corpus* c, uint32_t nq, uint32_t k, uint64_t row_base, uint64_t* d_out_rows, double* d_out_dist,
                       uint32_t* d_out_count, cudaStream_t st);
 // exact.cu: query vector / |q| / flags are passed explicitly (batch scratch row or the fallback scratch)
