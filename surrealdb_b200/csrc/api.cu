@@ -138,6 +138,7 @@ static sdb_status ticket_prepare(Corpus* c, Ticket& t, uint32_t nq) {
     SDB_CUDA(cudaEventCreate(&t.ev_end));
     SDB_CUDA(cudaEventCreateWithFlags(&t.ev_h2d, cudaEventDisableTiming));
     SDB_CUDA(cudaEventCreateWithFlags(&t.ev_out, cudaEventDisableTiming));
+    SDB_CUDA(cudaEventCreateWithFlags(&t.ev_main, cudaEventDisableTiming));
   }
   if (t.h_cap < nq) {
     if (t.h_flags) cudaFreeHost(t.h_flags);
@@ -187,17 +188,25 @@ static sdb_status enqueue_batch(Corpus* c, Ticket& t) {
   SDB_TRY(prep_queries(c, t.d_queries, nq, st));
   SDB_CUDA(cudaEventRecord(t.ev_screen0, st));
   SDB_TRY(cand_begin(c, nq, (int)rs, st));
+  // Screens are persistent one-CTA-per-SM kernels: two of them in flight on different streams would split the SMs,
+  // run in two waves and starve the refiners of the CTAs that are not resident yet.  So the screen of this batch waits
+  // for the end of the previous batch's screen -- only the TAIL of the previous batch overlaps with it.
+  if (c->last_main && c->last_main != t.ev_main) SDB_CUDA(cudaStreamWaitEvent(st, c->last_main, 0));
   if (tc && c->stream_refine) {
     PassDesc p0, pm;
     build_stream_passes(c->n, cap, k, &p0, &pm);
     if (p0.count && !pm.count) {  // the whole corpus fits the lists: score everything once
       SDB_TRY(screen_tc_pass(c, nq, k, p0, int8, 0, st));
+      SDB_CUDA(cudaEventRecord(t.ev_main, st));
+      c->last_main = t.ev_main;
       SDB_TRY(cand_select(c, nq, k, int8, 0u, false, st));
       t.n_passes++;
     } else if (pm.count) {
       SDB_TRY(screen_tc_pass(c, nq, k, p0, int8, 3, st));           // probe: chunk maxima of a few tiles
       SDB_TRY(cand_seed_from_probe(c, nq, k, p0.count, st));         // thresholds + histogram geometry
       SDB_TRY(screen_tc_pass(c, nq, k, pm, int8, 2, st));           // the streaming launch over every tile
+      SDB_CUDA(cudaEventRecord(t.ev_main, st));
+      c->last_main = t.ev_main;
       SDB_TRY(cand_select(c, nq, k, int8, c->last_slots, false, st));
       t.n_passes += 2;
     }
@@ -216,6 +225,8 @@ static sdb_status enqueue_batch(Corpus* c, Ticket& t) {
       first_pass = false;
       t.n_passes++;
     }
+    SDB_CUDA(cudaEventRecord(t.ev_main, st));
+    c->last_main = t.ev_main;
   }
   SDB_CUDA(cudaEventRecord(t.ev_screen1, st));
   // stage B: the coarse screens' candidates are re-scored in f32 and narrowed before the (FP64-bound) exact re-rank
@@ -694,7 +705,7 @@ void sdb_corpus_destroy(sdb_corpus* c) {
                   c->d_sel, c->d_fb_q, c->d_fb_qmag, c->d_fb_qflags, c->d_block, c->d_gather};
   for (void* p : ptrs) cudaFree(p);
   for (Ticket& t : c->tickets) {
-    cudaEvent_t evs[] = {t.ev_begin, t.ev_screen0, t.ev_screen1, t.ev_end, t.ev_h2d, t.ev_out};
+    cudaEvent_t evs[] = {t.ev_begin, t.ev_screen0, t.ev_screen1, t.ev_end, t.ev_h2d, t.ev_out, t.ev_main};
     for (cudaEvent_t e : evs)
       if (e) cudaEventDestroy(e);
     if (t.h_flags) cudaFreeHost(t.h_flags);

@@ -181,6 +181,7 @@ struct Ticket {
   uint32_t* d_res_count = nullptr;
   size_t in_cap = 0, res_cap = 0, res_cap_q = 0;
   cudaEvent_t ev_h2d = nullptr, ev_out = nullptr;
+  cudaEvent_t ev_main = nullptr;  // recorded after this batch's last screen launch (the next batch's screen waits for it)
   bool wait_h2d = false;  // the batch's stream still has to wait for ev_h2d (queries travelling on the copy stream)
 };
 constexpr int N_TICKETS = 4;
@@ -268,6 +269,7 @@ struct Corpus : Scratch {
   uint32_t* d_fb_qflags = nullptr;
   Scratch sets[2];  // the inactive set's fields are parked here (see Scratch)
   int active_set = 0;
+  cudaEvent_t last_main = nullptr;  // ev_main of the batch whose screen was enqueued last
   // asynchronous batches
   Ticket tickets[N_TICKETS];
   uint32_t next_ticket = 1;
