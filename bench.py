@@ -455,6 +455,7 @@ def main():
     # ---- warm-up (both paths) ----
     run_pipelined(submit_dev, 0, args.warmup, False)
     run_sync_calls(0, min(2, args.warmup))
+    run_pipelined(submit_host, 0, min(4, args.warmup), False)  # (allocates the per-slot staging buffers of the host path)
     # ---- timed: device-resident inputs (`value`) ----
     sampler = ClockSampler(local)
     if rank == 0:

@@ -186,12 +186,12 @@ static sdb_status enqueue_batch(Corpus* c, Ticket& t) {
   SDB_TRY(scratch_for(c, nq, rg.cap));
   const uint32_t cap = c->sc_cap;
   SDB_TRY(prep_queries(c, t.d_queries, nq, st));
-  SDB_CUDA(cudaEventRecord(t.ev_screen0, st));
   SDB_TRY(cand_begin(c, nq, (int)rs, st));
   // Screens are persistent one-CTA-per-SM kernels: two of them in flight on different streams would split the SMs,
   // run in two waves and starve the refiners of the CTAs that are not resident yet.  So the screen of this batch waits
   // for the end of the previous batch's screen -- only the TAIL of the previous batch overlaps with it.
   if (c->last_main && c->last_main != t.ev_main) SDB_CUDA(cudaStreamWaitEvent(st, c->last_main, 0));
+  SDB_CUDA(cudaEventRecord(t.ev_screen0, st));  // after the wait: screen_ms is this batch's screen, not the queueing
   if (tc && c->stream_refine) {
     PassDesc p0, pm;
     build_stream_passes(c->n, cap, k, &p0, &pm);

@@ -115,27 +115,131 @@ __global__ void typed_distance_kernel(const float* __restrict__ q, const float* 
 }
 
 // distance of this lane's row (or NO_ROW) to the query held in shared memory; all 32 lanes must call.
+// Scratch of the distance phase, per warp.  Euclid: a 32 x 33 float transposing tile.  Cosine: 32 compacted row ids +
+// 32 f64 results (the rows are read straight from global memory, see warp_distance<true>).
+__host__ __device__ constexpr size_t hn_tile_bytes(bool cosine) { return cosine ? 32 * 4 + 32 * 8 : sizeof(float) * 32 * 33; }
+
+// COSINE.  ndarray's f32 dot (a6; oracle orc_nd_dot_f32) keeps 8 running sums p_j over the columns 8i+j, each one a
+// strictly sequential chain over i, and folds them as ((((0+(p0+p4))+(p1+p5))+(p2+p6))+(p3+p7)) followed by the <8
+// tail columns.  The 8 chains of a row are independent, so a row is given to 8 LANES (lane j = chain j) and a warp
+// works on 4 rows at a time -- two such quads interleaved when more than 4 rows are new, so every lane carries two
+// independent chains.  Lane (g, j) reads x[row_g][8i+j] directly from global memory: the 8 lanes of a row cover one 32-byte
+// sector and the 4 rows of a quad 4 sectors, i.e. a request moves as many bytes as a fully coalesced one; no shared-memory
+// transposition, 8 x fewer dependent steps per row than one lane per row (the walk was bound by issue latency: ncu r1,
+// 30 % issue-active at 13 cycles per instruction, ~6.7k instructions per expanded node).
 template <bool COSINE>
 __device__ __forceinline__ double warp_distance(const float* __restrict__ vec, const float* __restrict__ sumsq,
                                                 uint32_t dim, uint32_t my_row, const float* s_q, float q_sumsq,
-                                                float (*tile)[33]) {
+                                                float (*tile)[33]);
+
+template <>
+__device__ __forceinline__ double warp_distance<true>(const float* __restrict__ vec, const float* __restrict__ sumsq,
+                                                      uint32_t dim, uint32_t my_row, const float* s_q, float q_sumsq,
+                                                      float (*tile)[33]) {
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t d8 = dim & ~7u;
-  float p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0, p5 = 0, p6 = 0, p7 = 0, s = 0.f;
-  const uint32_t lim_all = COSINE ? d8 : dim;
+  const uint32_t d8 = dim & ~7u, steps = dim >> 3;
+  uint32_t* ids = reinterpret_cast<uint32_t*>(tile);
+  double* res = reinterpret_cast<double*>(ids + 32);
+  const uint32_t vmask = __ballot_sync(0xffffffffu, my_row != NO_ROW);
+  const uint32_t n_rows = __popc(vmask);
+  const uint32_t ci = __popc(vmask & ((1u << lane) - 1u));  // compact index of this lane's row
+  if (my_row != NO_ROW) ids[ci] = my_row;
+  __syncwarp();
+  {  // ask L2 for every line of every new row up front: the rows stream in while the first quads are consumed
+    const uint32_t row_bytes = dim * 4u;
+    for (uint32_t r = 0; r < n_rows; r++) {
+      const char* base = reinterpret_cast<const char*>(vec + (size_t)ids[r] * dim);
+      for (uint32_t off = lane * 128u; off < row_bytes; off += 32u * 128u)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+    }
+  }
+  const uint32_t grp = lane >> 3, j = lane & 7u;
+  const float* qj = s_q + j;
+  const double nb = __dsqrt_rn((double)q_sumsq);
+  for (uint32_t g0 = 0; g0 < n_rows; g0 += 8) {
+    const uint32_t ia = g0 + grp, ib = g0 + 4 + grp;
+    const bool va = ia < n_rows, vb = ib < n_rows;
+    const uint32_t ra = va ? ids[ia] : 0u, rb = vb ? ids[ib] : 0u;
+    const float* xa = vec + (size_t)ra * dim + j;
+    const float* xb = vec + (size_t)rb * dim + j;
+    float na2 = 0.f, nb2 = 0.f;
+    if (va && j == 0) na2 = __ldg(sumsq + ra);
+    if (vb && j == 0) nb2 = __ldg(sumsq + rb);
+    float pa = 0.f, pb = 0.f;
+    uint32_t i = 0;
+    if (g0 + 4 < n_rows) {  // (warp-uniform) two quads
+      for (; i + 8 <= steps; i += 8) {
+        float a[8], b[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          a[u] = va ? __ldg(xa + 8u * (i + u)) : 0.f;
+          b[u] = vb ? __ldg(xb + 8u * (i + u)) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const float qv = qj[8u * (i + u)];
+          pa = __fadd_rn(pa, __fmul_rn(a[u], qv));
+          pb = __fadd_rn(pb, __fmul_rn(b[u], qv));
+        }
+      }
+      for (; i < steps; i++) {
+        const float qv = qj[8u * i];
+        pa = __fadd_rn(pa, __fmul_rn(va ? __ldg(xa + 8u * i) : 0.f, qv));
+        pb = __fadd_rn(pb, __fmul_rn(vb ? __ldg(xb + 8u * i) : 0.f, qv));
+      }
+    } else {  // one quad: deeper unroll for the same number of loads in flight
+      for (; i + 16 <= steps; i += 16) {
+        float a[16];
+#pragma unroll
+        for (int u = 0; u < 16; u++) a[u] = va ? __ldg(xa + 8u * (i + u)) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 16; u++) pa = __fadd_rn(pa, __fmul_rn(a[u], qj[8u * (i + u)]));
+      }
+      for (; i < steps; i++) pa = __fadd_rn(pa, __fmul_rn(va ? __ldg(xa + 8u * i) : 0.f, qj[8u * i]));
+    }
+    // fold: s_j = p_j + p_(j+4) on lanes j < 4, then the sequential sum on the quad's lane 0
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const float p = h ? pb : pa;
+      const float sj = __fadd_rn(p, __shfl_down_sync(0xffffffffu, p, 4));
+      const float s1 = __shfl_down_sync(0xffffffffu, sj, 1);
+      const float s2 = __shfl_down_sync(0xffffffffu, sj, 2);
+      const float s3 = __shfl_down_sync(0xffffffffu, sj, 3);
+      const bool v = h ? vb : va;
+      if (v && j == 0) {
+        const uint32_t row = h ? rb : ra;
+        float dot = __fadd_rn(0.f, sj);
+        dot = __fadd_rn(dot, s1);
+        dot = __fadd_rn(dot, s2);
+        dot = __fadd_rn(dot, s3);
+        for (uint32_t c = d8; c < dim; c++) dot = __fadd_rn(dot, __fmul_rn(__ldg(vec + (size_t)row * dim + c), s_q[c]));
+        const double na = __dsqrt_rn((double)(h ? nb2 : na2));
+        res[h ? ib : ia] = __dsub_rn(1.0, __ddiv_rn((double)dot, __dmul_rn(na, nb)));
+      }
+    }
+  }
+  __syncwarp();
+  return my_row != NO_ROW ? res[ci] : 0.0;
+}
+
+// EUCLID.  ndarray-stats' l2_dist folds (a-b)^2 strictly sequentially over the columns: one chain per row, so a row
+// stays on ONE lane and the rows of a round are transposed through shared memory (coalesced fetches, 64 columns a step).
+template <>
+__device__ __forceinline__ double warp_distance<false>(const float* __restrict__ vec, const float* __restrict__ sumsq,
+                                                       uint32_t dim, uint32_t my_row, const float* s_q, float q_sumsq,
+                                                       float (*tile)[33]) {
+  const uint32_t lane = threadIdx.x & 31u;
+  float s = 0.f;
   // Only a handful of the <=32 neighbours of an expanded node are new (6 on average): the valid rows are compacted and
   // handled in rounds of 16; the 32 x 33 float scratch is viewed as 16 rows x (64 columns + 2 padding words), so one
   // step moves 64 columns of every row of the round -- up to 32 independent loads per lane in flight per wait instead
-  // of 4 (the walk is bound by the latency of these fetches, see below).  The padding words park the compacted row ids.
+  // of 4.  The padding words park the compacted row ids.
   float(*t)[66] = reinterpret_cast<float(*)[66]>(tile);
   const uint32_t vmask = __ballot_sync(0xffffffffu, my_row != NO_ROW);
   const uint32_t n_rows = __popc(vmask);
   const uint32_t ci = __popc(vmask & ((1u << lane) - 1u));  // compact index of this lane's row
   if (my_row != NO_ROW) t[ci & 15u][64 + (ci >> 4)] = __uint_as_float(my_row);
   __syncwarp();
-  // ncu: ~85 % of the stall samples of the walk sit on the first use of the fetched vector elements, and the step loop
-  // would pay that latency once per step.  Ask for every line of every new row up front: the rows stream into L2 back
-  // to back (one DRAM page / TLB entry per row) while the first steps are consumed.
   {
     const uint32_t row_bytes = dim * 4u;
     for (uint32_t r = 0; r < n_rows; r++) {
@@ -148,8 +252,8 @@ __device__ __forceinline__ double warp_distance(const float* __restrict__ vec, c
     const uint32_t nr = n_rows - g0 < 16u ? n_rows - g0 : 16u;
     const bool mine = my_row != NO_ROW && (ci >> 4) == (g0 >> 4);
     const float* x = t[ci & 15u];
-    for (uint32_t c0 = 0; c0 < lim_all; c0 += 64) {
-      const bool in0 = c0 + lane < lim_all, in1 = c0 + 32 + lane < lim_all;
+    for (uint32_t c0 = 0; c0 < dim; c0 += 64) {
+      const bool in0 = c0 + lane < dim, in1 = c0 + 32 + lane < dim;
 #pragma unroll 4
       for (uint32_t r = 0; r < nr; r++) {
         const float* src = vec + (size_t)__float_as_uint(t[r][64 + (g0 >> 4)]) * dim + c0 + lane;  // broadcast id read
@@ -160,41 +264,16 @@ __device__ __forceinline__ double warp_distance(const float* __restrict__ vec, c
       }
       __syncwarp();
       if (mine) {
-        const uint32_t lim = lim_all - c0 < 64u ? lim_all - c0 : 64u;
-        if (COSINE) {
-          for (uint32_t jj = 0; jj < lim; jj += 8) {  // lim is a multiple of 8 here
-            const float* q = s_q + c0 + jj;
-            p0 = __fadd_rn(p0, __fmul_rn(x[jj + 0], q[0]));
-            p1 = __fadd_rn(p1, __fmul_rn(x[jj + 1], q[1]));
-            p2 = __fadd_rn(p2, __fmul_rn(x[jj + 2], q[2]));
-            p3 = __fadd_rn(p3, __fmul_rn(x[jj + 3], q[3]));
-            p4 = __fadd_rn(p4, __fmul_rn(x[jj + 4], q[4]));
-            p5 = __fadd_rn(p5, __fmul_rn(x[jj + 5], q[5]));
-            p6 = __fadd_rn(p6, __fmul_rn(x[jj + 6], q[6]));
-            p7 = __fadd_rn(p7, __fmul_rn(x[jj + 7], q[7]));
-          }
-        } else {
-          for (uint32_t j = 0; j < lim; j++) {
-            const float d = __fsub_rn(x[j], s_q[c0 + j]);
-            s = __fadd_rn(s, __fmul_rn(d, d));
-          }
+        const uint32_t lim = dim - c0 < 64u ? dim - c0 : 64u;
+        for (uint32_t jj = 0; jj < lim; jj++) {
+          const float d = __fsub_rn(x[jj], s_q[c0 + jj]);
+          s = __fadd_rn(s, __fmul_rn(d, d));
         }
       }
       __syncwarp();
     }
   }
   if (my_row == NO_ROW) return 0.0;
-  if (COSINE) {
-    float dot = 0.f;
-    dot = __fadd_rn(dot, __fadd_rn(p0, p4));
-    dot = __fadd_rn(dot, __fadd_rn(p1, p5));
-    dot = __fadd_rn(dot, __fadd_rn(p2, p6));
-    dot = __fadd_rn(dot, __fadd_rn(p3, p7));
-    for (uint32_t c = d8; c < dim; c++) dot = __fadd_rn(dot, __fmul_rn(__ldg(vec + (size_t)my_row * dim + c), s_q[c]));
-    const double na = __dsqrt_rn((double)__ldg(sumsq + my_row));
-    const double nb = __dsqrt_rn((double)q_sumsq);
-    return __dsub_rn(1.0, __ddiv_rn((double)dot, __dmul_rn(na, nb)));
-  }
   return __dsqrt_rn((double)s);
 }
 
@@ -204,8 +283,7 @@ __device__ __forceinline__ uint32_t sorted_insert(uint64_t* keys, uint32_t* ids,
   const uint32_t lane = threadIdx.x & 31u;
   uint32_t cnt = 0;
   for (uint32_t i = head + lane; i < n; i += 32) cnt += keys[i] <= key;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
   const uint32_t pos = head + cnt;
   for (uint32_t hi = n; hi > pos;) {  // shift [pos, n) up by one, top chunk first
     const uint32_t lo = hi - pos > 32u ? hi - 32u : pos;
@@ -256,18 +334,18 @@ struct HnswParams {
   const int* cancel;  // mapped host flag (sdb_ctx_cancel): polled before every query
 };
 
-template <bool COSINE>
-__global__ void __launch_bounds__(HN_WARPS * 32) hnsw_search_kernel(HnswParams P) {
+template <bool COSINE, int MINB>
+__global__ void __launch_bounds__(HN_WARPS * 32, MINB) hnsw_search_kernel(HnswParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ccap = P.ccap, wcap = P.ef + 2;
   // per-warp shared layout
-  const size_t per_warp = sizeof(float) * ((P.dim + 3) & ~3u) + sizeof(float) * 32 * 33 + (sizeof(uint64_t) + sizeof(uint32_t)) * (ccap + wcap) + 64;
+  const size_t per_warp = sizeof(float) * ((P.dim + 3) & ~3u) + hn_tile_bytes(COSINE) + (sizeof(uint64_t) + sizeof(uint32_t)) * (ccap + wcap) + 64;
   uint8_t* base = smem_raw + (size_t)warp * ((per_warp + 15) & ~size_t(15));
   uint64_t* c_key = reinterpret_cast<uint64_t*>(base);
   uint64_t* w_key = c_key + ccap;
   float(*tile)[33] = reinterpret_cast<float(*)[33]>(w_key + wcap);
-  float* s_q = reinterpret_cast<float*>(tile) + 32 * 33;
+  float* s_q = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tile) + hn_tile_bytes(COSINE));
   uint32_t* c_id = reinterpret_cast<uint32_t*>(s_q + ((P.dim + 3) & ~3u));
   uint32_t* w_id = c_id + ccap;
 
@@ -920,18 +998,21 @@ static sdb_status hnsw_search_impl(sdb_hnsw* h, const float* queries, uint32_t n
   if (truthy) {
     ccap = 16 * ef + 34;
     if (ccap < 1024) ccap = 1024;
-    const size_t fixed = sizeof(float) * ((h->dim + 3) & ~3u) + sizeof(float) * 32 * 33 + 12 * (size_t)wcap + 64 + 16;
+    const size_t fixed = sizeof(float) * ((h->dim + 3) & ~3u) + hn_tile_bytes(h->metric == SDB_COSINE) + 12 * (size_t)wcap + 64 + 16;
     const size_t room = (220 * 1024) / HN_WARPS;
     if (fixed + 12 * (size_t)ccap > room) ccap = room > fixed + 12 * (2 * (size_t)ef + 34) ? (uint32_t)((room - fixed) / 12) : 2 * ef + 34;
   }
-  size_t per_warp = sizeof(float) * ((h->dim + 3) & ~3u) + sizeof(float) * 32 * 33 + 12 * (size_t)(ccap + wcap) + 64;
+  size_t per_warp = sizeof(float) * ((h->dim + 3) & ~3u) + hn_tile_bytes(h->metric == SDB_COSINE) + 12 * (size_t)(ccap + wcap) + 64;
   per_warp = (per_warp + 15) & ~size_t(15);
   const size_t smem = per_warp * HN_WARPS;
   if (smem > 220 * 1024) {
     set_error("hnsw: dim %u / ef %u need %zu bytes of shared memory per block", h->dim, ef, smem);
     return SDB_EUNSUPPORTED;
   }
-  auto kern = h->metric == SDB_COSINE ? hnsw_search_kernel<true> : hnsw_search_kernel<false>;
+  // cosine: 8 lanes per row keep ~16 loads in flight per lane; 80 registers (6 blocks per SM) holds that without spills
+  const int occ = getenv("SDB_HNSW_OCC") ? atoi(getenv("SDB_HNSW_OCC")) : 6;
+  auto kern = h->metric == SDB_COSINE ? (occ >= 8 ? hnsw_search_kernel<true, 8> : occ <= 4 ? hnsw_search_kernel<true, 4> : hnsw_search_kernel<true, 6>)
+                                      : hnsw_search_kernel<false, 1>;
   SDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   SDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, HN_WARPS * 32, smem));

@@ -163,7 +163,7 @@ def build_layers(ctx, vectors_dev, n, dim, metric="EUCLIDEAN", m=16, m0=32, seed
 
 
 def build_incremental(ctx, x, metric="COSINE", m=16, m0=32, efc=150, seed=1, growth=0.25, boot_min=65536,
-                      search_chunk=1 << 16, rev_extra=32, progress=None):
+                      search_chunk=1 << 16, rev_extra=32, progress=None, settle=True):
     """Batched TRUE insertion: the reference inserts one element at a time -- search the current graph
     with efc, select <= m_max neighbours with the heuristic, link both ways, re-select over-full neighbours
     (hnsw/mod.rs:297-377, hnsw/layer.rs:342-387).  Here the same four steps run for a whole BATCH of new elements
@@ -222,9 +222,9 @@ def build_incremental(ctx, x, metric="COSINE", m=16, m0=32, efc=150, seed=1, gro
             ci = torch.zeros(1, dtype=torch.int32, device=dev)
         return rp, ci.contiguous()
 
-    n_cur = n_boot
-    while n_cur < n:
-        b = int(min(n - n_cur, max(4096, int(n_cur * growth))))
+    def search_select(lo, hi, drop_self):
+        """insertion search of elements [lo, hi) on the current graph + Heuristic::select -> (sel (b, m0) int32, count)"""
+        b = hi - lo
         rp, ci = csr0()
         lay = [(rp, ci)] + upper
         RP = (C.c_void_p * n_layers)(*[t[0].data_ptr() for t in lay])
@@ -242,21 +242,41 @@ def build_incremental(ctx, x, metric="COSINE", m=16, m0=32, efc=150, seed=1, gro
                 cdist = torch.empty((nqc, efc), dtype=torch.float64, device=dev)
                 ccnt = torch.empty((nqc,), dtype=torch.int32, device=dev)
                 torch.cuda.synchronize()
-                L.check(L.lib().sdb_hnsw_search_device(h, C.c_void_p(x[n_cur + c0].data_ptr()), nqc, efc, efc,
+                L.check(L.lib().sdb_hnsw_search_device(h, C.c_void_p(x[lo + c0].data_ptr()), nqc, efc, efc,
                                                        C.c_void_p(cand.data_ptr()), C.c_void_p(cdist.data_ptr()),
                                                        C.c_void_p(ccnt.data_ptr())))
-                L.check(L.lib().sdb_hnsw_select_neighbors(ctx.h, C.c_void_p(x.data_ptr()), dim, mcode, n_cur + c0, nqc,
+                if drop_self:  # the element is part of the graph by now: take it out of its own candidate list (order kept)
+                    me = torch.arange(lo + c0, lo + c1, device=dev, dtype=torch.int64)[:, None]
+                    live = torch.arange(efc, device=dev)[None, :] < ccnt[:, None]
+                    is_me = (cand == me) & live
+                    key = torch.arange(efc, device=dev)[None, :] + is_me.to(torch.int64) * efc  # self goes last
+                    cand = torch.gather(cand, 1, torch.argsort(key, dim=1, stable=True)).contiguous()
+                    ccnt = (ccnt - is_me.sum(1).to(torch.int32)).contiguous()
+                    torch.cuda.synchronize()
+                L.check(L.lib().sdb_hnsw_select_neighbors(ctx.h, C.c_void_p(x.data_ptr()), dim, mcode, lo + c0, nqc,
                                                           C.c_void_p(cand.data_ptr()), C.c_void_p(ccnt.data_ptr()), efc, m0, 1,
                                                           C.c_void_p(sel[c0:c1].data_ptr()), C.c_void_p(scnt[c0:c1].data_ptr())))
                 del cand, cdist, ccnt
         finally:
             L.lib().sdb_hnsw_destroy(h)
-        # ---- link: forward edges of the new elements, then the reverse edges into the existing graph ----
+        return sel, scnt
+
+    def link(lo, hi, sel, scnt, dedup):
+        """forward edges of [lo, hi) := sel; reverse edges into the targets, re-selecting the nodes that overflow m0"""
+        b = hi - lo
         valid = col_ids < scnt[:, None]
-        adj0[n_cur:n_cur + b] = torch.where(valid, sel, torch.full_like(sel, -1))
-        deg0[n_cur:n_cur + b] = scnt
-        src = torch.arange(n_cur, n_cur + b, device=dev, dtype=torch.int32)[:, None].expand(b, m0)[valid]
+        adj0[lo:hi] = torch.where(valid, sel, torch.full_like(sel, -1))
+        deg0[lo:hi] = scnt
+        src = torch.arange(lo, hi, device=dev, dtype=torch.int32)[:, None].expand(b, m0)[valid]
         dst = sel[valid].to(torch.int64)
+        if dedup and dst.numel():  # the target may hold this edge already (second pass over the same elements)
+            keep = torch.ones(dst.numel(), dtype=torch.bool, device=dev)
+            for e0 in range(0, dst.numel(), 1 << 22):
+                e1 = min(dst.numel(), e0 + (1 << 22))
+                keep[e0:e1] = ~(adj0[dst[e0:e1]] == src[e0:e1, None]).any(1)
+            src, dst = src[keep], dst[keep]
+        if not dst.numel():
+            return
         dst_s, perm = torch.sort(dst, stable=True)
         src_s = src[perm]
         uniq, counts = torch.unique_consecutive(dst_s, return_counts=True)
@@ -291,7 +311,18 @@ def build_incremental(ctx, x, metric="COSINE", m=16, m0=32, efc=150, seed=1, gro
             v2 = col_ids < ocnt[:, None]
             adj0[ov_nodes] = torch.where(v2, out, torch.full_like(out, -1))
             deg0[ov_nodes] = ocnt
-            del union, node_slot, out, ocnt
+
+    n_cur = n_boot
+    while n_cur < n:
+        b = int(min(n - n_cur, max(4096, int(n_cur * growth))))
+        sel, scnt = search_select(n_cur, n_cur + b, False)
+        link(n_cur, n_cur + b, sel, scnt, False)
+        if settle:
+            # Elements of one batch did not see each other.  Second pass: the same insertion search on the graph that now
+            # holds the whole batch, so close neighbours that arrived together get linked (serial insertion would have
+            # linked the later one to the earlier one).
+            sel, scnt = search_select(n_cur, n_cur + b, True)
+            link(n_cur, n_cur + b, sel, scnt, True)
         if progress:
             progress(0, n_cur + b, n)
         n_cur += b

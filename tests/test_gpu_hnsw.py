@@ -265,3 +265,45 @@ def test_pending_updates_and_knn_scan_operator(ctx):
         truthy = (np.arange(n) % 2 == 0).astype(np.uint8)
         fi, fd, _ = O.hnsw_search_csr(g, q, k, ef, truthy=truthy)
         assert [r["id"] for r in out] == [f"pts:{int(e)}" for e in fi]
+
+
+def test_incremental_builder_recall_next_to_a_reference_style_graph(ctx):
+    # Batched true insertion on the GPU (hnsw_build.build_incremental) vs the oracle's serial insertion (a restatement of
+    # Hnsw::insert) on the same clustered data: recall@10 against exact brute force must be on par.  The walk on either
+    # graph is the same kernel; what is compared is the GRAPH QUALITY of the two builders.
+    import torch
+    from surrealdb_b200.hnsw import HnswIndex
+    from surrealdb_b200.hnsw_build import build_incremental
+    rng = np.random.default_rng(314)
+    n, dim, k, ef = 30_000, 32, 10, 64
+    cent = rng.normal(0, 1, (200, dim))
+    cent /= np.linalg.norm(cent, axis=1, keepdims=True)
+    data = (cent[rng.integers(0, 200, n)] + rng.normal(0, 0.15 / np.sqrt(dim), (n, dim))).astype(np.float32)
+    queries = (cent[rng.integers(0, 200, 300)] + rng.normal(0, 0.15 / np.sqrt(dim), (300, dim))).astype(np.float32)
+    x = torch.from_numpy(data).cuda()
+    res = build_incremental(ctx, x, "COSINE", m=16, m0=32, efc=150, seed=3, growth=0.25, boot_min=4096)
+    idx = HnswIndex.from_device(ctx, res["x"], res["layers_dev"], res["entry"], "COSINE")
+    ids, dist, cnt = idx.search_graph(queries, k, ef)
+    order = res["order"]
+    recall = 0.0
+    for i in range(queries.shape[0]):
+        bi, _ = O.vec_knn_f32(data, queries[i], "cosine", k)
+        got = set(order[ids[i, : cnt[i]].astype(np.int64)].tolist())  # new ids -> original rows
+        recall += len(got & set(bi.tolist())) / k
+    recall /= queries.shape[0]
+    # reference-style graph on a subset (serial insertion is slow): the same data distribution, same parameters
+    sub = data[:6000]
+    g = build(sub, "cosine", m=16, efc=150)
+    idx2 = HnswIndex(ctx, g["vectors"], g["layers"], g["entry_point"], "cosine")
+    ids2, _, cnt2 = idx2.search_graph(queries, k, ef)
+    ref_recall = 0.0
+    for i in range(queries.shape[0]):
+        bi, _ = O.vec_knn_f32(sub, queries[i], "cosine", k)
+        ref_recall += len(set(ids2[i, : cnt2[i]].tolist()) & set(bi.tolist())) / k
+    ref_recall /= queries.shape[0]
+    assert recall >= 0.95 and recall >= ref_recall - 0.03, (recall, ref_recall)
+    # structural properties the reference asserts for its own graph (hnsw/mod.rs check_hnsw_properties): degree caps
+    rp0 = res["layers_dev"][0][0].cpu().numpy()
+    assert int(np.diff(rp0).max()) <= 32
+    for rp, _ in res["layers_dev"][1:]:
+        assert int(np.diff(rp.cpu().numpy()).max()) <= 16
