@@ -597,7 +597,9 @@ sdb_status sdb_ctx_create(int device, sdb_ctx** out) {
     SDB_CUDA(cudaHostAlloc(&hc, sizeof(int), cudaHostAllocMapped));
     *hc = 0;
     c->h_cancel = hc;
-    SDB_CUDA(cudaHostGetDevicePointer(&c->d_cancel, hc, 0));
+    SDB_CUDA(cudaMalloc(&c->d_cancel, sizeof(int)));
+    SDB_CUDA(cudaMemset(c->d_cancel, 0, sizeof(int)));
+    SDB_CUDA(cudaStreamCreateWithFlags(&c->cancel_stream, cudaStreamNonBlocking));
   }
   // dynamic shared-memory limits are per device: set them for THIS device now (not behind a process-wide flag)
   SDB_TRY(screen_tc_init_device());
@@ -623,13 +625,25 @@ void sdb_ctx_destroy(sdb_ctx* c) {
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   if (c->h_cancel) cudaFreeHost((void*)c->h_cancel);
+  if (c->d_cancel) cudaFree(c->d_cancel);
+  if (c->cancel_stream) cudaStreamDestroy(c->cancel_stream);
   delete c;
 }
+static void push_cancel_word(sdb_ctx* c) {  // any host thread; its own stream, so it overtakes running kernels
+  if (!c->d_cancel || !c->cancel_stream) return;
+  if (cudaSetDevice(c->device) != cudaSuccess) return;
+  cudaMemcpyAsync(c->d_cancel, (const void*)c->h_cancel, sizeof(int), cudaMemcpyHostToDevice, c->cancel_stream);
+  cudaStreamSynchronize(c->cancel_stream);
+}
 void sdb_ctx_cancel(sdb_ctx* c) {
-  if (c && c->h_cancel) *c->h_cancel = 1;
+  if (!c || !c->h_cancel) return;
+  *c->h_cancel = 1;
+  push_cancel_word(c);
 }
 void sdb_ctx_cancel_reset(sdb_ctx* c) {
-  if (c && c->h_cancel) *c->h_cancel = 0;
+  if (!c || !c->h_cancel) return;
+  *c->h_cancel = 0;
+  push_cancel_word(c);
 }
 uint64_t sdb_ctx_kernel_launches(const sdb_ctx* c) { return c ? c->launches : 0; }
 void* sdb_ctx_stream(const sdb_ctx* c) { return c ? (void*)c->stream : nullptr; }

@@ -9,7 +9,17 @@
 //   * one process per GPU  : sdb_comm_unique_id / sdb_comm_init_rank, then sdb_knn_sharded_submit* / _wait per rank
 //   * one process, N GPUs  : sdb_ctx_create_multi (ncclCommInitAll), then sdb_knn_sharded_multi drives every shard
 //                            from one thread inside ncclGroupStart/End
-// Everything is enqueued on the context's stream: no host synchronisation between the local search, the collective
+// The exchange itself does NOT go through an NCCL kernel by default.  The screen of the next batch is a persistent
+// kernel that owns every SM (one 217 KB CTA per SM), so an NCCL all-gather kernel queued behind the tail of batch i
+// cannot become resident until the screen of batch i+1 retires: measured on 8 GPUs, the step time doubled (2.06 ms
+// instead of ~0.95 ms).  Instead every rank keeps an exchange ARENA (gather buffers + flag words) that its peers map
+// (CUDA IPC between processes, peer access inside one process); after the local search a small kernel stores this
+// rank's block straight into every peer's gather buffer over NVLink and publishes a sequence number (release, system
+// scope); the merge is preceded by a one-warp kernel that waits for all ranks' sequence numbers, and followed by one
+// that acknowledges the slot so a peer can overwrite it four batches later.  These kernels need no shared memory and a
+// warp or two, so they run beside the resident screen.  NCCL remains the bootstrap (handle exchange), the fallback
+// when peer mapping is unavailable (SDB_EXCHANGE=nccl forces it) and the graph path's all-reduce.
+// Everything is enqueued on the batch's stream: no host synchronisation between the local search, the exchange
 // and the merge.  Exactness across ranks: every block carries the number of queries its rank still has to repair on
 // the host side (failed proof / special queries); since every rank sees every header after the all-gather, all ranks
 // take the same decision to run a repair round (local repair, second all-gather + merge) -- no extra collective.
@@ -80,6 +90,7 @@ static sdb_status nccl_load() {
 struct Comm {
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;
+  bool single_process = false;  // sdb_ctx_create_multi: every rank lives in this process (peer access, no IPC)
 };
 
 int comm_size(const Ctx* ctx) { return ctx && ctx->comm ? ctx->comm->nranks : 1; }
@@ -117,7 +128,9 @@ static BlockLayout block_layout(uint32_t nq, uint32_t k) {
 
 struct ShardSlot {  // per in-flight ticket: this rank's block, the gathered blocks, the headers on the host
   uint8_t* d_block = nullptr;
-  uint8_t* d_gather = nullptr;
+  uint8_t* d_gather = nullptr;   // NCCL path: own allocation
+  uint8_t* gather = nullptr;     // where this batch's blocks are merged from (arena slot or d_gather)
+  size_t stride = 0;             // distance between two ranks' blocks inside `gather`
   size_t block_cap = 0, gather_cap = 0;
   uint32_t* h_hdr = nullptr;  // pinned, nranks x 4
   int hdr_cap = 0;
@@ -154,8 +167,10 @@ namespace {
 
 ShardSlot g_dummy;
 
+struct Arena;
 struct ShardState {  // hangs off the corpus through a side table (kept out of internal.cuh: only comm.cu needs it)
   ShardSlot slots[N_TICKETS];
+  Arena* arena = nullptr;
 };
 std::mutex g_state_mu;
 std::vector<std::pair<Corpus*, ShardState*>> g_states;
@@ -209,6 +224,76 @@ sdb_status slot_reserve(Corpus* c, ShardSlot& s, uint32_t nq, uint32_t k, bool h
     }
   }
   return SDB_OK;
+}
+
+
+// ---- peer-to-peer exchange arena ------------------------------------------------------------------------------------
+constexpr int MAX_P2P_RANKS = 16;
+struct PeerTable {
+  uint8_t* base[MAX_P2P_RANKS];
+};
+struct Arena {
+  uint8_t* base = nullptr;  // this rank's arena (cudaMalloc: IPC-exportable)
+  size_t block_cap = 0;     // bytes reserved per (slot, rank) block
+  size_t flags_off = 0, acks_off = 0, ctr_off = 0, bytes = 0;
+  int nranks = 0;
+  PeerTable peers{};        // peers.base[r] = rank r's arena as mapped into this process (own base for r == rank)
+  bool mapped[MAX_P2P_RANKS] = {};
+  bool ok = false;          // peers mapped: the P2P path is in use
+  size_t failed_need = 0;   // a collective attempt for this size failed: stay on NCCL until a larger request retries
+  uint32_t seq = 0;                      // exchanges so far (identical on every rank)
+  uint32_t slot_seq[N_TICKETS] = {};     // sequence number of the last exchange through each slot
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// grid (nranks, S): CTA (p, s) stores its share of this rank's block into peer p's gather slot, the last of the S CTAs
+// publishes `seq` in p's flag word.  Before the first store thread 0 makes sure p has consumed the previous content of
+// the slot (p's acknowledgement lands in OUR arena).
+__global__ void __launch_bounds__(512) exch_push_kernel(PeerTable pt, uint8_t* my_base, const uint4* __restrict__ src,
+                                                        size_t n16, size_t gather_off, size_t flag_off, size_t ack_off,
+                                                        size_t ctr_off, uint32_t need_ack, uint32_t seq) {
+  const uint32_t p = blockIdx.x, S = gridDim.y, sidx = blockIdx.y;
+  if (threadIdx.x == 0) {
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(my_base + ack_off) + p;
+    while ((int32_t)(ld_acquire_sys(a) - need_ack) < 0) __nanosleep(64);
+  }
+  __syncthreads();
+  uint4* dst = reinterpret_cast<uint4*>(pt.base[p] + gather_off);
+  const size_t per = (n16 + S - 1) / S;
+  const size_t lo = per * sidx, hi = lo + per < n16 ? lo + per : n16;
+  for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t* ctr = reinterpret_cast<uint32_t*>(my_base + ctr_off) + p;
+    const uint32_t old = S > 1 ? atomicAdd(ctr, 1u) : 0u;
+    if (old == S - 1) {
+      if (S > 1) {
+        *ctr = 0;
+        __threadfence_system();
+      }
+      st_release_sys(reinterpret_cast<uint32_t*>(pt.base[p] + flag_off), seq);
+    }
+  }
+}
+// one warp: wait until every rank's block of exchange `seq` has landed in this rank's slot
+__global__ void exch_wait_kernel(const uint8_t* my_base, size_t flags_off, int nranks, uint32_t seq) {
+  if ((int)threadIdx.x < nranks) {
+    const uint32_t* f = reinterpret_cast<const uint32_t*>(my_base + flags_off) + threadIdx.x;
+    while ((int32_t)(ld_acquire_sys(f) - seq) < 0) __nanosleep(64);
+  }
+}
+// one warp: tell every rank that this rank is done with the slot's content of exchange `seq`
+__global__ void exch_ack_kernel(PeerTable pt, size_t ack_off, int nranks, uint32_t seq) {
+  if ((int)threadIdx.x < nranks) st_release_sys(reinterpret_cast<uint32_t*>(pt.base[threadIdx.x] + ack_off), seq);
 }
 
 struct Pending {  // one shard's in-flight sharded batch

@@ -31,6 +31,7 @@ struct Hnsw {
   int64_t entry = -1;
   float* d_vec = nullptr;
   float* d_sumsq = nullptr;
+  double* d_norm = nullptr;  // sqrt((double)sumsq): the per-element factor of the cosine denominator (vector.rs:246)
   std::vector<uint64_t*> rp;
   std::vector<uint32_t*> ci;
   const uint64_t** d_rp = nullptr;
@@ -50,23 +51,37 @@ __device__ __forceinline__ double key_to_double(uint64_t key) {
   return __longlong_as_double((long long)b);
 }
 
-// ndarray-style 8-lane f32 sum of squares of one row (used at load time for every element, and per query)
-__global__ void hnsw_sumsq_kernel(const float* __restrict__ vec, uint32_t dim, uint64_t n, float* __restrict__ out) {
-  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n) return;
-  const float* a = vec + r * dim;
-  float p[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  uint32_t i = 0;
-  for (; i + 8 <= dim; i += 8)
-#pragma unroll
-    for (int j = 0; j < 8; j++) p[j] = __fadd_rn(p[j], __fmul_rn(a[i + j], a[i + j]));
-  float s = 0.f;
-  s = __fadd_rn(s, __fadd_rn(p[0], p[4]));
-  s = __fadd_rn(s, __fadd_rn(p[1], p[5]));
-  s = __fadd_rn(s, __fadd_rn(p[2], p[6]));
-  s = __fadd_rn(s, __fadd_rn(p[3], p[7]));
-  for (; i < dim; i++) s = __fadd_rn(s, __fmul_rn(a[i], a[i]));
-  out[r] = s;
+// ndarray-style 8-lane f32 sum of squares of every row (load time).  8 threads per row, thread j owns the partial sum
+// over the columns 8i+j (a sequential chain, as in ndarray's unrolled fold); the 8 threads of a row read one 32-byte
+// sector per step.  Also writes sqrt((double)sumsq), the element's factor of the cosine denominator.
+__global__ void hnsw_sumsq_kernel(const float* __restrict__ vec, uint32_t dim, uint64_t n, float* __restrict__ out,
+                                  double* __restrict__ norm) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t r = t >> 3;
+  const uint32_t j = (uint32_t)t & 7u;
+  const bool valid = r < n;
+  const float* a = vec + (valid ? r : 0) * dim + j;
+  const uint32_t steps = dim >> 3;
+  float p = 0.f;
+  if (valid)
+    for (uint32_t i = 0; i < steps; i++) {
+      const float v = __ldg(a + 8u * i);
+      p = __fadd_rn(p, __fmul_rn(v, v));
+    }
+  const float sj = __fadd_rn(p, __shfl_down_sync(0xffffffffu, p, 4));
+  const float s1 = __shfl_down_sync(0xffffffffu, sj, 1);
+  const float s2 = __shfl_down_sync(0xffffffffu, sj, 2);
+  const float s3 = __shfl_down_sync(0xffffffffu, sj, 3);
+  if (valid && j == 0) {
+    float sum = __fadd_rn(0.f, sj);
+    sum = __fadd_rn(sum, s1);
+    sum = __fadd_rn(sum, s2);
+    sum = __fadd_rn(sum, s3);
+    const float* row = vec + r * dim;
+    for (uint32_t c = dim & ~7u; c < dim; c++) sum = __fadd_rn(sum, __fmul_rn(__ldg(row + c), __ldg(row + c)));
+    out[r] = sum;
+    if (norm) norm[r] = __dsqrt_rn((double)sum);
+  }
 }
 
 // Distance::calculate for VectorType::F32 (idx/trees/vector.rs:243-289,659-672), one thread per vector: the typed
@@ -128,16 +143,24 @@ __host__ __device__ constexpr size_t hn_tile_bytes(bool cosine) { return cosine 
 // transposition, 8 x fewer dependent steps per row than one lane per row (the walk was bound by issue latency: ncu r1,
 // 30 % issue-active at 13 cycles per instruction, ~6.7k instructions per expanded node).
 template <bool COSINE>
-__device__ __forceinline__ double warp_distance(const float* __restrict__ vec, const float* __restrict__ sumsq,
-                                                uint32_t dim, uint32_t my_row, const float* s_q, float q_sumsq,
+__device__ __forceinline__ double warp_distance(const float* __restrict__ vec, const double* __restrict__ norm,
+                                                uint32_t dim, uint32_t my_row, const float* s_q, double q_norm,
                                                 float (*tile)[33]);
 
+// Cosine keeps the query TRANSPOSED in shared memory: qT[j * qs + i] = q[8i + j] (chain j contiguous), qs = hn_q_stride
+// = 4 mod 32 words so the 8 lanes of a row read 8 different bank groups with one LDS.128 per 4 steps; the < 8 tail
+// columns follow at qT[8 * qs ...].
+__host__ __device__ constexpr uint32_t hn_q_stride(uint32_t dim) { return (((dim >> 3) + 27u) / 32u) * 32u + 4u; }
+__host__ __device__ constexpr size_t hn_q_floats(uint32_t dim, bool cosine) {
+  return cosine ? (size_t)8 * hn_q_stride(dim) + 8 : (size_t)((dim + 3) & ~3u);
+}
+
 template <>
-__device__ __forceinline__ double warp_distance<true>(const float* __restrict__ vec, const float* __restrict__ sumsq,
-                                                      uint32_t dim, uint32_t my_row, const float* s_q, float q_sumsq,
+__device__ __forceinline__ double warp_distance<true>(const float* __restrict__ vec, const double* __restrict__ norm,
+                                                      uint32_t dim, uint32_t my_row, const float* s_q, double q_norm,
                                                       float (*tile)[33]) {
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t d8 = dim & ~7u, steps = dim >> 3;
+  const uint32_t d8 = dim & ~7u, steps = dim >> 3, qs = hn_q_stride(dim);
   uint32_t* ids = reinterpret_cast<uint32_t*>(tile);
   double* res = reinterpret_cast<double*>(ids + 32);
   const uint32_t vmask = __ballot_sync(0xffffffffu, my_row != NO_ROW);
@@ -145,26 +168,26 @@ __device__ __forceinline__ double warp_distance<true>(const float* __restrict__ 
   const uint32_t ci = __popc(vmask & ((1u << lane) - 1u));  // compact index of this lane's row
   if (my_row != NO_ROW) ids[ci] = my_row;
   __syncwarp();
-  {  // ask L2 for every line of every new row up front: the rows stream in while the first quads are consumed
-    const uint32_t row_bytes = dim * 4u;
-    for (uint32_t r = 0; r < n_rows; r++) {
-      const char* base = reinterpret_cast<const char*>(vec + (size_t)ids[r] * dim);
-      for (uint32_t off = lane * 128u; off < row_bytes; off += 32u * 128u)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
-    }
-  }
   const uint32_t grp = lane >> 3, j = lane & 7u;
-  const float* qj = s_q + j;
-  const double nb = __dsqrt_rn((double)q_sumsq);
+  const float* qj = s_q + j * qs;
+  const uint32_t row_bytes = dim * 4u;
   for (uint32_t g0 = 0; g0 < n_rows; g0 += 8) {
     const uint32_t ia = g0 + grp, ib = g0 + 4 + grp;
     const bool va = ia < n_rows, vb = ib < n_rows;
     const uint32_t ra = va ? ids[ia] : 0u, rb = vb ? ids[ib] : 0u;
     const float* xa = vec + (size_t)ra * dim + j;
     const float* xb = vec + (size_t)rb * dim + j;
-    float na2 = 0.f, nb2 = 0.f;
-    if (va && j == 0) na2 = __ldg(sumsq + ra);
-    if (vb && j == 0) nb2 = __ldg(sumsq + rb);
+    // ask L2 for every line of the rows of this round up front (lane j: lines j, j+8, ...): the first loads below pay
+    // the DRAM latency once, the later ones find their sectors in L2
+    if (va)
+      for (uint32_t off = j * 128u; off < row_bytes; off += 8u * 128u)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(xa - j) + off));
+    if (vb)
+      for (uint32_t off = j * 128u; off < row_bytes; off += 8u * 128u)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(xb - j) + off));
+    double na = 0.0, nb = 0.0;
+    if (va && j == 0) na = __ldg(norm + ra);
+    if (vb && j == 0) nb = __ldg(norm + rb);
     float pa = 0.f, pb = 0.f;
     uint32_t i = 0;
     if (g0 + 4 < n_rows) {  // (warp-uniform) two quads
@@ -175,15 +198,16 @@ __device__ __forceinline__ double warp_distance<true>(const float* __restrict__ 
           a[u] = va ? __ldg(xa + 8u * (i + u)) : 0.f;
           b[u] = vb ? __ldg(xb + 8u * (i + u)) : 0.f;
         }
+        const float4 q0 = *reinterpret_cast<const float4*>(qj + i), q1 = *reinterpret_cast<const float4*>(qj + i + 4);
+        const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-          const float qv = qj[8u * (i + u)];
-          pa = __fadd_rn(pa, __fmul_rn(a[u], qv));
-          pb = __fadd_rn(pb, __fmul_rn(b[u], qv));
+          pa = __fadd_rn(pa, __fmul_rn(a[u], qv[u]));
+          pb = __fadd_rn(pb, __fmul_rn(b[u], qv[u]));
         }
       }
       for (; i < steps; i++) {
-        const float qv = qj[8u * i];
+        const float qv = qj[i];
         pa = __fadd_rn(pa, __fmul_rn(va ? __ldg(xa + 8u * i) : 0.f, qv));
         pb = __fadd_rn(pb, __fmul_rn(vb ? __ldg(xb + 8u * i) : 0.f, qv));
       }
@@ -193,9 +217,15 @@ __device__ __forceinline__ double warp_distance<true>(const float* __restrict__ 
 #pragma unroll
         for (int u = 0; u < 16; u++) a[u] = va ? __ldg(xa + 8u * (i + u)) : 0.f;
 #pragma unroll
-        for (int u = 0; u < 16; u++) pa = __fadd_rn(pa, __fmul_rn(a[u], qj[8u * (i + u)]));
+        for (int v4 = 0; v4 < 4; v4++) {
+          const float4 q4 = *reinterpret_cast<const float4*>(qj + i + 4 * v4);
+          pa = __fadd_rn(pa, __fmul_rn(a[4 * v4 + 0], q4.x));
+          pa = __fadd_rn(pa, __fmul_rn(a[4 * v4 + 1], q4.y));
+          pa = __fadd_rn(pa, __fmul_rn(a[4 * v4 + 2], q4.z));
+          pa = __fadd_rn(pa, __fmul_rn(a[4 * v4 + 3], q4.w));
+        }
       }
-      for (; i < steps; i++) pa = __fadd_rn(pa, __fmul_rn(va ? __ldg(xa + 8u * i) : 0.f, qj[8u * i]));
+      for (; i < steps; i++) pa = __fadd_rn(pa, __fmul_rn(va ? __ldg(xa + 8u * i) : 0.f, qj[i]));
     }
     // fold: s_j = p_j + p_(j+4) on lanes j < 4, then the sequential sum on the quad's lane 0
 #pragma unroll
@@ -212,9 +242,9 @@ __device__ __forceinline__ double warp_distance<true>(const float* __restrict__ 
         dot = __fadd_rn(dot, s1);
         dot = __fadd_rn(dot, s2);
         dot = __fadd_rn(dot, s3);
-        for (uint32_t c = d8; c < dim; c++) dot = __fadd_rn(dot, __fmul_rn(__ldg(vec + (size_t)row * dim + c), s_q[c]));
-        const double na = __dsqrt_rn((double)(h ? nb2 : na2));
-        res[h ? ib : ia] = __dsub_rn(1.0, __ddiv_rn((double)dot, __dmul_rn(na, nb)));
+        for (uint32_t c = d8; c < dim; c++)
+          dot = __fadd_rn(dot, __fmul_rn(__ldg(vec + (size_t)row * dim + c), s_q[8u * qs + (c - d8)]));
+        res[h ? ib : ia] = __dsub_rn(1.0, __ddiv_rn((double)dot, __dmul_rn(h ? nb : na, q_norm)));
       }
     }
   }
@@ -225,8 +255,8 @@ __device__ __forceinline__ double warp_distance<true>(const float* __restrict__ 
 // EUCLID.  ndarray-stats' l2_dist folds (a-b)^2 strictly sequentially over the columns: one chain per row, so a row
 // stays on ONE lane and the rows of a round are transposed through shared memory (coalesced fetches, 64 columns a step).
 template <>
-__device__ __forceinline__ double warp_distance<false>(const float* __restrict__ vec, const float* __restrict__ sumsq,
-                                                       uint32_t dim, uint32_t my_row, const float* s_q, float q_sumsq,
+__device__ __forceinline__ double warp_distance<false>(const float* __restrict__ vec, const double* __restrict__ norm,
+                                                       uint32_t dim, uint32_t my_row, const float* s_q, double q_norm,
                                                        float (*tile)[33]) {
   const uint32_t lane = threadIdx.x & 31u;
   float s = 0.f;
@@ -277,29 +307,34 @@ __device__ __forceinline__ double warp_distance<false>(const float* __restrict__
   return __dsqrt_rn((double)s);
 }
 
-// sorted (ascending key, FIFO inside a key) array insert by the whole warp; entries live in [head, n)
+// sorted (ascending key, FIFO inside a key) array insert by the whole warp; entries live in [head, n).  One pass from
+// the top: every 32-entry chunk above the insertion point moves up by one; the chunk that holds an entry <= key fixes the
+// position (the new entry goes AFTER its equals).
 __device__ __forceinline__ uint32_t sorted_insert(uint64_t* keys, uint32_t* ids, uint32_t head, uint32_t n, uint64_t key,
                                                   uint32_t id) {
   const uint32_t lane = threadIdx.x & 31u;
-  uint32_t cnt = 0;
-  for (uint32_t i = head + lane; i < n; i += 32) cnt += keys[i] <= key;
-  cnt = __reduce_add_sync(0xffffffffu, cnt);
-  const uint32_t pos = head + cnt;
-  for (uint32_t hi = n; hi > pos;) {  // shift [pos, n) up by one, top chunk first
-    const uint32_t lo = hi - pos > 32u ? hi - 32u : pos;
+  uint32_t pos = head;
+  for (uint32_t hi = n; hi > head;) {
+    const uint32_t lo = hi - head > 32u ? hi - 32u : head;
     const uint32_t i = lo + lane;
     uint64_t k = 0;
     uint32_t v = 0;
-    if (i < hi) {
+    const bool in = i < hi;
+    if (in) {
       k = keys[i];
       v = ids[i];
     }
-    __syncwarp();
-    if (i < hi) {
+    const uint32_t le = __ballot_sync(0xffffffffu, in && k <= key);
+    __syncwarp();  // every lane has read its entry before a neighbour overwrites it
+    if (in && k > key) {
       keys[i + 1] = k;
       ids[i + 1] = v;
     }
     __syncwarp();
+    if (le) {
+      pos = lo + __popc(le);
+      break;
+    }
     hi = lo;
   }
   if (lane == 0) {
@@ -312,7 +347,7 @@ __device__ __forceinline__ uint32_t sorted_insert(uint64_t* keys, uint32_t* ids,
 
 struct HnswParams {
   const float* vec;
-  const float* sumsq;
+  const double* norm;     // sqrt((double)sumsq) per element (cosine)
   const uint64_t* const* rp;
   const uint32_t* const* ci;
   uint32_t dim, n_layers;
@@ -340,13 +375,14 @@ __global__ void __launch_bounds__(HN_WARPS * 32, MINB) hnsw_search_kernel(HnswPa
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ccap = P.ccap, wcap = P.ef + 2;
   // per-warp shared layout
-  const size_t per_warp = sizeof(float) * ((P.dim + 3) & ~3u) + hn_tile_bytes(COSINE) + (sizeof(uint64_t) + sizeof(uint32_t)) * (ccap + wcap) + 64;
+  const size_t per_warp = sizeof(float) * hn_q_floats(P.dim, COSINE) + hn_tile_bytes(COSINE) + (sizeof(uint64_t) + sizeof(uint32_t)) * (ccap + wcap) + 64;
   uint8_t* base = smem_raw + (size_t)warp * ((per_warp + 15) & ~size_t(15));
-  uint64_t* c_key = reinterpret_cast<uint64_t*>(base);
+  // query first (16-byte aligned: LDS.128), then the distance scratch, the 8-byte keys, the 4-byte ids
+  float* s_q = reinterpret_cast<float*>(base);
+  float(*tile)[33] = reinterpret_cast<float(*)[33]>(s_q + ((hn_q_floats(P.dim, COSINE) + 3) & ~size_t(3)));
+  uint64_t* c_key = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(tile) + hn_tile_bytes(COSINE));
   uint64_t* w_key = c_key + ccap;
-  float(*tile)[33] = reinterpret_cast<float(*)[33]>(w_key + wcap);
-  float* s_q = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tile) + hn_tile_bytes(COSINE));
-  uint32_t* c_id = reinterpret_cast<uint32_t*>(s_q + ((P.dim + 3) & ~3u));
+  uint32_t* c_id = reinterpret_cast<uint32_t*>(w_key + wcap);
   uint32_t* w_id = c_id + ccap;
 
   const uint32_t gwarp = blockIdx.x * HN_WARPS + warp;
@@ -357,27 +393,45 @@ __global__ void __launch_bounds__(HN_WARPS * 32, MINB) hnsw_search_kernel(HnswPa
 
   for (uint32_t q = gwarp; q < P.nq; q += n_warps) {
     if (*reinterpret_cast<const volatile int*>(P.cancel)) break;  // uniform per warp: every lane reads the same word
-    // stage the query, its 8-lane sum of squares (cosine)
-    for (uint32_t c = lane; c < P.dim; c += 32) s_q[c] = P.queries[(size_t)q * P.dim + c];
-    __syncwarp();
-    float q_sumsq = 0.f;
+    // stage the query (cosine: transposed, see hn_q_stride) and its 8-lane sum of squares
+    double q_norm = 0.0;
     if (COSINE) {
-      float p[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      uint32_t i = 0;
-      for (; i + 8 <= P.dim; i += 8)
-#pragma unroll
-        for (int j = 0; j < 8; j++) p[j] = __fadd_rn(p[j], __fmul_rn(s_q[i + j], s_q[i + j]));
-      q_sumsq = __fadd_rn(q_sumsq, __fadd_rn(p[0], p[4]));
-      q_sumsq = __fadd_rn(q_sumsq, __fadd_rn(p[1], p[5]));
-      q_sumsq = __fadd_rn(q_sumsq, __fadd_rn(p[2], p[6]));
-      q_sumsq = __fadd_rn(q_sumsq, __fadd_rn(p[3], p[7]));
-      for (; i < P.dim; i++) q_sumsq = __fadd_rn(q_sumsq, __fmul_rn(s_q[i], s_q[i]));
+      const uint32_t qs = hn_q_stride(P.dim), d8 = P.dim & ~7u, steps = P.dim >> 3;
+      const float* qg = P.queries + (size_t)q * P.dim;
+      for (uint32_t c = lane; c < P.dim; c += 32) {
+        const float v = qg[c];
+        if (c < d8) s_q[(c & 7u) * qs + (c >> 3)] = v;
+        else s_q[8u * qs + (c - d8)] = v;
+      }
+      __syncwarp();
+      float p = 0.f;
+      if (lane < 8)
+        for (uint32_t i = 0; i < steps; i++) {
+          const float v = s_q[lane * qs + i];
+          p = __fadd_rn(p, __fmul_rn(v, v));
+        }
+      const float sj = __fadd_rn(p, __shfl_down_sync(0xffffffffu, p, 4));
+      const float s1 = __shfl_down_sync(0xffffffffu, sj, 1);
+      const float s2 = __shfl_down_sync(0xffffffffu, sj, 2);
+      const float s3 = __shfl_down_sync(0xffffffffu, sj, 3);
+      float q_sumsq = __fadd_rn(0.f, sj);
+      q_sumsq = __fadd_rn(q_sumsq, s1);
+      q_sumsq = __fadd_rn(q_sumsq, s2);
+      q_sumsq = __fadd_rn(q_sumsq, s3);
+      for (uint32_t c = d8; c < P.dim; c++) {
+        const float v = s_q[8u * qs + (c - d8)];
+        q_sumsq = __fadd_rn(q_sumsq, __fmul_rn(v, v));
+      }
+      q_norm = __dsqrt_rn((double)__shfl_sync(0xffffffffu, q_sumsq, 0));
+    } else {
+      for (uint32_t c = lane; c < P.dim; c += 32) s_q[c] = P.queries[(size_t)q * P.dim + c];
+      __syncwarp();
     }
     uint64_t n_visited = 0, n_expanded = 0;
     uint32_t n_out = 0;
     if (P.entry >= 0) {
       uint32_t ep = (uint32_t)P.entry;
-      double ep_d = warp_distance<COSINE>(P.vec, P.sumsq, P.dim, lane == 0 ? ep : NO_ROW, s_q, q_sumsq, tile);
+      double ep_d = warp_distance<COSINE>(P.vec, P.norm, P.dim, lane == 0 ? ep : NO_ROW, s_q, q_norm, tile);
       ep_d = __shfl_sync(0xffffffffu, ep_d, 0);
       n_visited++;
       for (int32_t layer = (int32_t)P.n_layers - 1; layer >= 0; layer--) {
@@ -440,7 +494,7 @@ __global__ void __launch_bounds__(HN_WARPS * 32, MINB) hnsw_search_kernel(HnswPa
             const uint32_t new_mask = __ballot_sync(0xffffffffu, is_new);
             if (!new_mask) continue;
             n_visited += __popc(new_mask);
-            const double d = warp_distance<COSINE>(P.vec, P.sumsq, P.dim, is_new ? nb : NO_ROW, s_q, q_sumsq, tile);
+            const double d = warp_distance<COSINE>(P.vec, P.norm, P.dim, is_new ? nb : NO_ROW, s_q, q_norm, tile);
             // admission in stored order                                     layer.rs:205-217
             uint32_t m = new_mask;
             while (m) {
@@ -706,7 +760,8 @@ static sdb_status hnsw_finish(sdb_hnsw* h, sdb_hnsw** out) {
       cudaMemcpyAsync(h->d_ci, h->ci.data(), sizeof(void*) * n_layers, cudaMemcpyHostToDevice, st) != cudaSuccess)
     return fail("layer table copy", SDB_ECUDA);
   if (h->n) {
-    hnsw_sumsq_kernel<<<(unsigned)((h->n + 127) / 128), 128, 0, st>>>(h->d_vec, h->dim, h->n, h->d_sumsq);
+    if (cudaMalloc(&h->d_norm, sizeof(double) * h->n) != cudaSuccess) return fail("norms", SDB_ENOMEM);
+    hnsw_sumsq_kernel<<<(unsigned)((h->n * 8 + 127) / 128), 128, 0, st>>>(h->d_vec, h->dim, h->n, h->d_sumsq, h->d_norm);
     count_launch(ctx);
   }
   if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) return fail("finish", SDB_ECUDA);
@@ -725,6 +780,7 @@ void sdb_hnsw_destroy(sdb_hnsw* h) {
     for (auto p : h->ci) cudaFree(p);
   }
   cudaFree(h->d_sumsq);
+  cudaFree(h->d_norm);
   cudaFree(h->d_rp);
   cudaFree(h->d_ci);
   cudaFree(h->d_visited);
@@ -998,11 +1054,11 @@ static sdb_status hnsw_search_impl(sdb_hnsw* h, const float* queries, uint32_t n
   if (truthy) {
     ccap = 16 * ef + 34;
     if (ccap < 1024) ccap = 1024;
-    const size_t fixed = sizeof(float) * ((h->dim + 3) & ~3u) + hn_tile_bytes(h->metric == SDB_COSINE) + 12 * (size_t)wcap + 64 + 16;
+    const size_t fixed = sizeof(float) * hn_q_floats(h->dim, h->metric == SDB_COSINE) + hn_tile_bytes(h->metric == SDB_COSINE) + 12 * (size_t)wcap + 64 + 16;
     const size_t room = (220 * 1024) / HN_WARPS;
     if (fixed + 12 * (size_t)ccap > room) ccap = room > fixed + 12 * (2 * (size_t)ef + 34) ? (uint32_t)((room - fixed) / 12) : 2 * ef + 34;
   }
-  size_t per_warp = sizeof(float) * ((h->dim + 3) & ~3u) + hn_tile_bytes(h->metric == SDB_COSINE) + 12 * (size_t)(ccap + wcap) + 64;
+  size_t per_warp = sizeof(float) * hn_q_floats(h->dim, h->metric == SDB_COSINE) + hn_tile_bytes(h->metric == SDB_COSINE) + 12 * (size_t)(ccap + wcap) + 64;
   per_warp = (per_warp + 15) & ~size_t(15);
   const size_t smem = per_warp * HN_WARPS;
   if (smem > 220 * 1024) {
@@ -1014,6 +1070,9 @@ static sdb_status hnsw_search_impl(sdb_hnsw* h, const float* queries, uint32_t n
   auto kern = h->metric == SDB_COSINE ? (occ >= 8 ? hnsw_search_kernel<true, 8> : occ <= 4 ? hnsw_search_kernel<true, 4> : hnsw_search_kernel<true, 6>)
                                       : hnsw_search_kernel<false, 1>;
   SDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // the walk gets nothing from L1 (0.7 % hit rate): give the whole array to shared memory, or the driver's default
+  // carve-out (135 KB) caps the kernel at 5 blocks per SM
+  SDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   int per_sm = 1;
   SDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, HN_WARPS * 32, smem));
   if (per_sm < 1) per_sm = 1;
@@ -1075,7 +1134,7 @@ static sdb_status hnsw_search_impl(sdb_hnsw* h, const float* queries, uint32_t n
   P.truthy = d_truthy;
   P.noexp = d_noexp;
   P.vec = h->d_vec;
-  P.sumsq = h->d_sumsq;
+  P.norm = h->d_norm;
   P.rp = h->d_rp;
   P.ci = h->d_ci;
   P.dim = h->dim;

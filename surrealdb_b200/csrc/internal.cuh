@@ -129,10 +129,13 @@ struct Ctx {
   void* h_stage = nullptr;       // pinned staging buffer for large device->host results (grow-only)
   size_t h_stage_bytes = 0;
   Comm* comm = nullptr;
-  // cancellation (sdb_ctx_cancel): one int in mapped pinned memory -- the host side polls it between kernel phases,
-  // long-running kernels (the HNSW walk) poll it per query through the device alias
+  // cancellation (sdb_ctx_cancel): one int in pinned memory that the host side polls between kernel phases, mirrored
+  // into a word in DEVICE memory (copied on its own stream by sdb_ctx_cancel) that long-running kernels (the HNSW walk)
+  // poll per query -- polling the pinned word itself from thousands of warps is a PCIe read each (ncu r2: 8 % of the
+  // walk's stall samples)
   volatile int* h_cancel = nullptr;
   int* d_cancel = nullptr;
+  cudaStream_t cancel_stream = nullptr;
 };
 inline bool ctx_cancelled(const Ctx* ctx) { return ctx->h_cancel && *ctx->h_cancel != 0; }
 
