@@ -84,6 +84,9 @@ typedef struct {
   float screen_ms;           /* device time of the screening kernels (CUDA events)             */
   float total_ms;            /* device time of the whole call                                  */
   uint64_t n_survivors;      /* screened rows that passed a threshold and were gathered (all queries) */
+  uint32_t n_repaired;       /* queries whose proof failed on the batch's screen and succeeded on a finer one
+                                (re-screened as a small batch of their own; never reached the exact kernel) */
+  uint32_t reserved0;
 } sdb_knn_stats;
 
 /* ---- context -------------------------------------------------------------------------------- */

@@ -44,7 +44,7 @@ class KnnStats(C.Structure):
     _fields_ = [("screen_used", C.c_uint32), ("n_passes", C.c_uint32), ("n_fallback", C.c_uint32),
                 ("n_special_rows", C.c_uint32), ("n_candidates", C.c_uint64), ("n_reranked", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("screen_ms", C.c_float), ("total_ms", C.c_float),
-                ("n_survivors", C.c_uint64)]
+                ("n_survivors", C.c_uint64), ("n_repaired", C.c_uint32), ("reserved0", C.c_uint32)]
 
 
 _lib = None

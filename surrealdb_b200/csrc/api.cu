@@ -113,7 +113,15 @@ static std::vector<Rung> build_rungs(Corpus* c, uint32_t k, sdb_screen* first) {
     r = {{SDB_SCREEN_TC_INT8, 4096}, {SDB_SCREEN_TC_INT8, 16384}, {SDB_SCREEN_TC_BF16, 4096}, {SDB_SCREEN_TC_BF16, 16384}};
   else if (scr == SDB_SCREEN_TC_BF16) r = {{SDB_SCREEN_TC_BF16, 4096}, {SDB_SCREEN_TC_BF16, 16384}};
   else if (scr == SDB_SCREEN_SIMT_F32) r = {{SDB_SCREEN_SIMT_F32, 4096}};
+  // the f32 stream (error bound ~500x tighter than bf16) as the last rung before the exact kernel -- only ever used
+  // for the few queries of a batch that every tensor-core rung failed to prove (finish_local), never for a whole batch
+  if (!r.empty() && r.back().scr != SDB_SCREEN_SIMT_F32 && c->dtype == SDB_F32) r.push_back({SDB_SCREEN_SIMT_F32, 4096});
   return r;
+}
+static uint32_t n_batch_rungs(const std::vector<Rung>& r) {  // rungs a WHOLE batch may be re-screened on
+  uint32_t n = (uint32_t)r.size();
+  if (n > 1 && r.back().scr == SDB_SCREEN_SIMT_F32) n--;
+  return n;
 }
 
 // swap the ticket's scratch set into the corpus' active fields (see Scratch in internal.cuh)
@@ -268,7 +276,7 @@ static sdb_status finish_local(Corpus* c, Ticket& t, uint32_t* n_fallback, bool*
   *n_fallback = 0;
   SDB_CUDA(cudaEventSynchronize(t.ev_end));
   if (t.screen != SDB_SCREEN_NONE_EXACT && c->exact) {
-    while (t.rung + 1 < t.n_rungs) {
+    while (t.rung + 1 < t.n_batch_rungs) {  // many failures: the whole batch moves up one rung (and stays there)
       uint32_t n_fail = 0;
       for (uint32_t q = 0; q < nq; q++) n_fail += (t.h_flags[q] & 2u) ? 1u : 0u;
       if (n_fail <= 2 + nq / 64) break;
@@ -286,19 +294,87 @@ static sdb_status finish_local(Corpus* c, Ticket& t, uint32_t* n_fallback, bool*
     c->rung_k = k;
     c->rung = t.rung;
   }
-  // ---- exact path for everything the screens could not prove ----
-  bool drained = false;
+  // ---- what the batch's rung could not prove ----
+  std::vector<uint32_t> fails, exacts;
   for (uint32_t q = 0; q < nq; q++) {
-    const bool failed = (t.h_flags[q] & 2u) && (c->exact || t.screen == SDB_SCREEN_NONE_EXACT);
-    if (!failed && !(t.h_qflags[q] & 1u)) continue;
+    if (t.h_qflags[q] & 1u) exacts.push_back(q);  // zero / non-finite query norm: ranked by the exact kernel
+    else if ((t.h_flags[q] & 2u) && (c->exact || t.screen == SDB_SCREEN_NONE_EXACT)) fails.push_back(q);
+  }
+  if (fails.empty() && exacts.empty()) return SDB_OK;
+  SDB_CUDA(drain(ctx));  // the repair below shares scratch (and the exact kernel's keys) with every batch in flight
+  // A few failures: only THOSE queries climb the remaining rungs, as a small batch of their own (a bf16 pass over the
+  // corpus costs about as much for 60 queries as for 1, and far less than one sequential-f64 pass per query); the f32
+  // stream is the last rung.  Whatever is still unproven after that goes to the exact kernel.
+  if (!fails.empty() && t.screen != SDB_SCREEN_NONE_EXACT && c->exact && k) {
+    const uint32_t save_rung = t.rung, save_nq = t.nq, save_passes = t.n_passes;
+    const int save_screen = t.screen;
+    const double* save_q = t.d_queries;
+    uint64_t* save_rows = t.d_out_rows;
+    double* save_dist = t.d_out_dist;
+    uint32_t* save_cnt = t.d_out_count;
+    uint32_t save_stat[4] = {t.h_stat[0], t.h_stat[1], t.h_stat[2], t.h_stat[3]};
+    sdb_status rc = SDB_OK;
+    for (uint32_t rung = save_rung + 1; rung < t.n_rungs && !fails.empty() && rc == SDB_OK; rung++) {
+      if ((t.cancel && *t.cancel) || ctx_cancelled(ctx)) break;
+      const uint32_t nf = (uint32_t)fails.size();
+      const size_t need_q = (size_t)nf * c->dim, need_o = (size_t)nf * k;
+      if (c->rp_cap_q < need_q || c->rp_cap_o < need_o || c->rp_cap_n < nf) {
+        cudaFree(c->d_rp_q); cudaFree(c->d_rp_rows); cudaFree(c->d_rp_dist); cudaFree(c->d_rp_cnt);
+        c->d_rp_q = nullptr; c->d_rp_rows = nullptr; c->d_rp_dist = nullptr; c->d_rp_cnt = nullptr;
+        c->rp_cap_q = c->rp_cap_o = c->rp_cap_n = 0;
+        if (cudaMalloc(&c->d_rp_q, sizeof(double) * need_q) != cudaSuccess || cudaMalloc(&c->d_rp_rows, sizeof(uint64_t) * need_o) != cudaSuccess ||
+            cudaMalloc(&c->d_rp_dist, sizeof(double) * need_o) != cudaSuccess || cudaMalloc(&c->d_rp_cnt, sizeof(uint32_t) * nf) != cudaSuccess) {
+          set_error("repair buffers: %s", cudaGetErrorString(cudaGetLastError()));
+          rc = SDB_ENOMEM;
+          break;
+        }
+        c->rp_cap_q = need_q; c->rp_cap_o = need_o; c->rp_cap_n = nf;
+      }
+      for (uint32_t i = 0; i < nf; i++)
+        cudaMemcpyAsync(c->d_rp_q + (size_t)i * c->dim, save_q + (size_t)fails[i] * c->dim, sizeof(double) * c->dim, cudaMemcpyDeviceToDevice, st);
+      t.d_queries = c->d_rp_q;
+      t.nq = nf;
+      t.d_out_rows = c->d_rp_rows;
+      t.d_out_dist = c->d_rp_dist;
+      t.d_out_count = c->d_rp_cnt;
+      t.rung = rung;
+      rc = enqueue_batch(c, t);
+      if (rc == SDB_OK && cudaEventSynchronize(t.ev_end) != cudaSuccess) rc = SDB_ECUDA;
+      if (rc != SDB_OK) break;
+      std::vector<uint32_t> still;
+      for (uint32_t i = 0; i < nf; i++) {
+        const uint32_t q = fails[i];
+        if ((t.h_flags[i] & 2u) || (t.h_qflags[i] & 1u)) {
+          still.push_back(q);
+          continue;
+        }
+        cudaMemcpyAsync(save_rows + (size_t)q * k, c->d_rp_rows + (size_t)i * k, sizeof(uint64_t) * k, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(save_dist + (size_t)q * k, c->d_rp_dist + (size_t)i * k, sizeof(double) * k, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(save_cnt + q, c->d_rp_cnt + i, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
+        t.n_repaired++;
+      }
+      SDB_CUDA(cudaStreamSynchronize(st));
+      fails.swap(still);
+      *repaired = true;
+    }
+    t.d_queries = save_q;
+    t.nq = save_nq;
+    t.d_out_rows = save_rows;
+    t.d_out_dist = save_dist;
+    t.d_out_count = save_cnt;
+    t.rung = save_rung;
+    t.screen = save_screen;
+    t.n_passes = save_passes;
+    for (int i = 0; i < 4; i++) t.h_stat[i] = save_stat[i];
+    SDB_TRY(rc);
+  }
+  // ---- exact kernel: special queries and whatever no screen could prove ----
+  exacts.insert(exacts.end(), fails.begin(), fails.end());
+  for (uint32_t q : exacts) {
     if ((t.cancel && *t.cancel) || ctx_cancelled(ctx)) {
       cudaStreamSynchronize(st);
       set_error("query cancelled");
       return SDB_ECANCELLED;
-    }
-    if (!drained) {
-      SDB_CUDA(drain(ctx));  // the exact kernel's scratch (keys, fallback query) is shared by all batches
-      drained = true;
     }
     SDB_TRY(prep_fallback_query(c, t.d_queries + (size_t)q * c->dim, st));
     SDB_TRY(exact_query(c, c->d_fb_q, c->d_fb_qmag, c->d_fb_qflags, k, t.row_base, t.d_out_rows + (size_t)q * k,
@@ -317,6 +393,7 @@ static sdb_status finish_stats(Corpus* c, Ticket& t, uint32_t n_fallback) {
   stt.screen_used = (uint32_t)t.screen;
   stt.n_passes = t.n_passes;
   stt.n_fallback = n_fallback;
+  stt.n_repaired = t.n_repaired;
   stt.n_special_rows = c->n_special;
   stt.n_candidates = t.h_stat[2];  // largest candidate set of the batch
   stt.n_reranked = t.h_stat[1];
@@ -368,10 +445,12 @@ static sdb_status submit_locked(Corpus* c, Ticket* t, const double* d_queries, u
   t->d_out_count = d_out_count;
   t->cancel = cancel;
   t->launches0 = c->ctx->launches;
+  t->n_repaired = 0;
   sdb_screen first;
   const std::vector<Rung> rungs = build_rungs(c, k, &first);
-  t->rung = (c->rung_scr == first && c->rung_k == k && c->rung < rungs.size()) ? c->rung : 0;
+  t->rung = (c->rung_scr == first && c->rung_k == k && c->rung < n_batch_rungs(rungs)) ? c->rung : 0;
   t->n_rungs = (uint32_t)rungs.size();
+  t->n_batch_rungs = n_batch_rungs(rungs);
   if (nq == 0 || k == 0) {  // nothing to search: counts are zero
     cudaStream_t st = t->stream;
     SDB_CUDA(cudaEventRecord(t->ev_begin, st));
@@ -535,6 +614,67 @@ __global__ void __launch_bounds__(1024) topk_merge_kernel(uint32_t n_lists, uint
   if (threadIdx.x == 0) out_count[q] = n_out;
 }
 
+
+// <= 32 lists: one warp per query, lane l walks list l (each list is already in (distance, row) order).  Every step takes
+// the warp-wide minimum head.  No shared memory and 128-thread blocks, so the merge runs beside the resident screen of
+// the next batch (the sorter above needs 24 bytes of shared memory per entry and up to 1024 threads).
+__global__ void __launch_bounds__(128) topk_kway_merge_kernel(uint32_t n_lists, uint32_t nq, uint32_t k,
+                                                              const uint64_t* __restrict__ rows,
+                                                              const double* __restrict__ dist,
+                                                              const uint32_t* __restrict__ counts, uint64_t st_rows,
+                                                              uint64_t st_dist, uint64_t st_cnt,
+                                                              uint64_t* __restrict__ out_rows, double* __restrict__ out_dist,
+                                                              uint32_t* __restrict__ out_count) {
+  const uint32_t q = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+  if (q >= nq) return;
+  uint32_t cnt = 0, pos = 0;
+  const uint64_t* lr = nullptr;
+  const double* ld = nullptr;
+  if (lane < n_lists) {
+    cnt = counts[(size_t)lane * st_cnt + q];
+    if (cnt > k) cnt = k;
+    lr = rows + (size_t)lane * st_rows + (size_t)q * k;
+    ld = dist + (size_t)lane * st_dist + (size_t)q * k;
+  }
+  uint64_t key = ~0ull, row = ~0ull;
+  double d = 0.0;
+  if (pos < cnt) {
+    d = ld[0];
+    key = dist_key(d);
+    row = lr[0];
+  }
+  uint32_t n_out = 0;
+  for (; n_out < k; n_out++) {
+    uint64_t bk = key, br = row;
+    uint32_t bl = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const uint64_t ok = __shfl_xor_sync(0xffffffffu, bk, o), orow = __shfl_xor_sync(0xffffffffu, br, o);
+      const uint32_t ol = __shfl_xor_sync(0xffffffffu, bl, o);
+      if (ok < bk || (ok == bk && (orow < br || (orow == br && ol < bl)))) {
+        bk = ok;
+        br = orow;
+        bl = ol;
+      }
+    }
+    if (bk == ~0ull && br == ~0ull) break;  // every list exhausted
+    if (lane == bl) {
+      out_rows[(size_t)q * k + n_out] = row;
+      out_dist[(size_t)q * k + n_out] = d;
+      pos++;
+      if (pos < cnt) {
+        d = ld[pos];
+        key = dist_key(d);
+        row = lr[pos];
+      } else {
+        key = ~0ull;
+        row = ~0ull;
+      }
+    }
+  }
+  if (lane == 0) out_count[q] = n_out;
+}
+
 sdb_status topk_merge_launch(Ctx* ctx, uint32_t n_lists, uint32_t nq, uint32_t k, const uint64_t* d_rows,
                              const double* d_dist, const uint32_t* d_counts, uint64_t stride_rows, uint64_t stride_dist,
                              uint64_t stride_counts, uint64_t* d_out_rows, double* d_out_dist, uint32_t* d_out_count,
@@ -542,6 +682,13 @@ sdb_status topk_merge_launch(Ctx* ctx, uint32_t n_lists, uint32_t nq, uint32_t k
   if (!stride_rows) stride_rows = (uint64_t)nq * k;
   if (!stride_dist) stride_dist = (uint64_t)nq * k;
   if (!stride_counts) stride_counts = nq;
+  if (n_lists <= 32) {
+    topk_kway_merge_kernel<<<(nq + 3) / 4, 128, 0, st>>>(n_lists, nq, k, d_rows, d_dist, d_counts, stride_rows, stride_dist,
+                                                       stride_counts, d_out_rows, d_out_dist, d_out_count);
+    count_launch(ctx);
+    SDB_CUDA(cudaGetLastError());
+    return SDB_OK;
+  }
   uint32_t p2 = 1;
   while (p2 < n_lists * k) p2 <<= 1;
   const size_t smem = (size_t)p2 * 24;
@@ -703,6 +850,7 @@ void sdb_corpus_destroy(sdb_corpus* c) {
   if (!c) return;
   cudaSetDevice(c->ctx->device);
   drain(c->ctx);
+  comm_corpus_released(c);
   for (int si = 0; si < 2; si++) {  // the parked scratch set
     if (si == c->active_set) continue;
     Scratch& z = c->sets[si];
@@ -716,7 +864,8 @@ void sdb_corpus_destroy(sdb_corpus* c) {
                   c->d_hparam, c->d_hist, c->d_qbferr, c->d_stat, c->d_probe, c->d_margin2, c->d_beps2, c->d_tau2, c->d_sub, c->d_sub_cnt, c->d_rows, c->d_mag, c->d_snorm,
                   c->d_bf16, c->d_skip, c->d_removed, c->d_special, c->d_q64, c->d_q32, c->d_qbf16, c->d_qmag, c->d_qflags,
                   c->d_tau, c->d_cand, c->d_cand_cnt, c->d_flags, c->d_rr_key, c->d_rr_dist, c->d_rr_row, c->d_ex_key,
-                  c->d_sel, c->d_fb_q, c->d_fb_qmag, c->d_fb_qflags, c->d_block, c->d_gather};
+                  c->d_sel, c->d_fb_q, c->d_fb_qmag, c->d_fb_qflags, c->d_block, c->d_gather, c->d_rp_q, c->d_rp_rows,
+                  c->d_rp_dist, c->d_rp_cnt};
   for (void* p : ptrs) cudaFree(p);
   for (Ticket& t : c->tickets) {
     cudaEvent_t evs[] = {t.ev_begin, t.ev_screen0, t.ev_screen1, t.ev_end, t.ev_h2d, t.ev_out, t.ev_main};

@@ -257,7 +257,7 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
 // grid (nranks, S): CTA (p, s) stores its share of this rank's block into peer p's gather slot, the last of the S CTAs
 // publishes `seq` in p's flag word.  Before the first store thread 0 makes sure p has consumed the previous content of
 // the slot (p's acknowledgement lands in OUR arena).
-__global__ void __launch_bounds__(512) exch_push_kernel(PeerTable pt, uint8_t* my_base, const uint4* __restrict__ src,
+__global__ void __launch_bounds__(256) exch_push_kernel(PeerTable pt, uint8_t* my_base, const uint4* __restrict__ src,
                                                         size_t n16, size_t gather_off, size_t flag_off, size_t ack_off,
                                                         size_t ctr_off, uint32_t need_ack, uint32_t seq) {
   const uint32_t p = blockIdx.x, S = gridDim.y, sidx = blockIdx.y;
@@ -302,6 +302,208 @@ struct Pending {  // one shard's in-flight sharded batch
   uint32_t ticket = 0, nq = 0, k = 0;
   int slot = -1;
 };
+
+
+static bool exchange_forced_nccl() {
+  static const bool v = [] {
+    const char* e = getenv("SDB_EXCHANGE");
+    return e && (e[0] == 'n' || e[0] == 'N');
+  }();
+  return v;
+}
+
+static void arena_unmap(Arena* a, int self) {
+  for (int r = 0; r < MAX_P2P_RANKS; r++) {
+    if (a->mapped[r] && r != self && a->peers.base[r]) cudaIpcCloseMemHandle(a->peers.base[r]);
+    a->mapped[r] = false;
+    a->peers.base[r] = nullptr;
+  }
+  a->ok = false;
+}
+
+// (re)allocate this rank's arena for blocks of `need` bytes; the peers are mapped by the callers below
+static sdb_status arena_alloc_local(Corpus* c, Arena* a, size_t need) {
+  const int R = c->ctx->comm->nranks;
+  cudaFree(a->base);
+  a->base = nullptr;
+  a->block_cap = (need + 65535) / 65536 * 65536;
+  a->nranks = R;
+  const size_t gather_bytes = (size_t)N_TICKETS * R * a->block_cap;
+  a->flags_off = gather_bytes;
+  a->acks_off = a->flags_off + 256 * ((sizeof(uint32_t) * N_TICKETS * R + 255) / 256);
+  a->ctr_off = a->acks_off + 256 * ((sizeof(uint32_t) * N_TICKETS * R + 255) / 256);
+  a->bytes = a->ctr_off + 256;
+  SDB_CUDA(cudaMalloc(&a->base, a->bytes));
+  SDB_CUDA(cudaMemset(a->base, 0, a->bytes));
+  SDB_CUDA(cudaDeviceSynchronize());
+  a->seq = 0;
+  for (int i = 0; i < N_TICKETS; i++) a->slot_seq[i] = 0;
+  return SDB_OK;
+}
+
+// one process per GPU: collective (every rank reaches this with the same `need`, because every rank submits the same
+// batches in the same order).  IPC handles travel through one NCCL all-gather; a second tiny all-reduce makes the
+// outcome unanimous, so either every rank uses the P2P path or every rank stays on NCCL.
+static sdb_status arena_ensure_ipc(Corpus* c, ShardState* ss, size_t need) {
+  Ctx* ctx = c->ctx;
+  Comm* cm = ctx->comm;
+  if (!ss->arena) ss->arena = new Arena();
+  Arena* a = ss->arena;
+  if (a->ok && a->block_cap >= need) return SDB_OK;
+  if (!a->ok && a->failed_need && need <= a->failed_need) return SDB_OK;  // stays on NCCL
+  const int R = cm->nranks;
+  // quiesce: batches in flight still exchange through the old arena
+  SDB_CUDA(cudaStreamSynchronize(ctx->stream));
+  SDB_CUDA(cudaStreamSynchronize(ctx->stream2));
+  arena_unmap(a, cm->rank);
+  uint32_t good = 1;
+  if (arena_alloc_local(c, a, need) != SDB_OK) good = 0;
+  cudaIpcMemHandle_t mine{};
+  if (good && cudaIpcGetMemHandle(&mine, a->base) != cudaSuccess) {
+    cudaGetLastError();
+    good = 0;
+  }
+  uint8_t* d_h = nullptr;
+  SDB_CUDA(cudaMalloc(&d_h, sizeof(cudaIpcMemHandle_t) * (R + 1) + 16));
+  std::vector<cudaIpcMemHandle_t> all((size_t)R);
+  cudaStream_t st = ctx->stream;
+  auto bail = [&](sdb_status rc) {
+    cudaFree(d_h);
+    return rc;
+  };
+  if (cudaMemcpyAsync(d_h + sizeof(mine) * R, &mine, sizeof(mine), cudaMemcpyHostToDevice, st) != cudaSuccess) return bail(SDB_ECUDA);
+  if (g_nccl.AllGather(d_h + sizeof(mine) * R, d_h, sizeof(mine), ncclChar, cm->comm, st) != ncclSuccess) {
+    set_error("exchange arena: ncclAllGather of the IPC handles failed");
+    return bail(SDB_ENCCL);
+  }
+  if (cudaMemcpyAsync(all.data(), d_h, sizeof(mine) * R, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+      cudaStreamSynchronize(st) != cudaSuccess)
+    return bail(SDB_ECUDA);
+  if (good) {
+    for (int r = 0; r < R && good; r++) {
+      if (r == cm->rank) {
+        a->peers.base[r] = a->base;
+        continue;
+      }
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        good = 0;
+        break;
+      }
+      a->peers.base[r] = (uint8_t*)ptr;
+      a->mapped[r] = true;
+    }
+  }
+  // unanimous?
+  uint32_t* d_flag = reinterpret_cast<uint32_t*>(d_h + sizeof(mine) * (R + 1));
+  if (cudaMemcpyAsync(d_flag, &good, 4, cudaMemcpyHostToDevice, st) != cudaSuccess) return bail(SDB_ECUDA);
+  if (g_nccl.AllReduce(d_flag, d_flag, 1, ncclUint32, ncclMin, cm->comm, st) != ncclSuccess) {
+    set_error("exchange arena: ncclAllReduce failed");
+    return bail(SDB_ENCCL);
+  }
+  uint32_t all_good = 0;
+  if (cudaMemcpyAsync(&all_good, d_flag, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+    return bail(SDB_ECUDA);
+  cudaFree(d_h);
+  if (all_good) {
+    a->ok = true;
+    a->failed_need = 0;
+  } else {
+    arena_unmap(a, cm->rank);
+    a->failed_need = need;
+  }
+  return SDB_OK;
+}
+
+// one process, N GPUs: the arenas of all shards are (re)built together and mapped through peer access
+static sdb_status arena_ensure_multi(sdb_corpus* const* shards, int n, size_t need) {
+  bool all_ok = true;
+  for (int i = 0; i < n; i++) {
+    ShardState* ss = state_of(shards[i]);
+    if (!ss->arena) ss->arena = new Arena();
+    all_ok = all_ok && ss->arena->ok && ss->arena->block_cap >= need;
+  }
+  if (all_ok) return SDB_OK;
+  Arena* a0 = state_of(shards[0])->arena;
+  if (!a0->ok && a0->failed_need && need <= a0->failed_need) return SDB_OK;
+  bool good = n <= MAX_P2P_RANKS;
+  for (int i = 0; i < n; i++) {
+    Ctx* ctx = shards[i]->ctx;
+    SDB_CUDA(cudaSetDevice(ctx->device));
+    SDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    SDB_CUDA(cudaStreamSynchronize(ctx->stream2));
+  }
+  for (int i = 0; i < n && good; i++) {
+    Ctx* ctx = shards[i]->ctx;
+    SDB_CUDA(cudaSetDevice(ctx->device));
+    for (int j = 0; j < n && good; j++) {
+      if (j == i || shards[j]->ctx->device == ctx->device) continue;
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, ctx->device, shards[j]->ctx->device) != cudaSuccess || !can) good = false;
+      else {
+        const cudaError_t e = cudaDeviceEnablePeerAccess(shards[j]->ctx->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) good = false;
+        cudaGetLastError();
+      }
+    }
+    Arena* a = state_of(shards[i])->arena;
+    for (int r = 0; r < MAX_P2P_RANKS; r++) {
+      a->mapped[r] = false;
+      a->peers.base[r] = nullptr;
+    }
+    a->ok = false;
+    if (good && arena_alloc_local(shards[i], a, need) != SDB_OK) good = false;
+  }
+  for (int i = 0; i < n; i++) {
+    Arena* a = state_of(shards[i])->arena;
+    if (good) {
+      for (int j = 0; j < n; j++) a->peers.base[shards[j]->ctx->comm->rank] = state_of(shards[j])->arena->base;
+      a->ok = true;
+      a->failed_need = 0;
+    } else {
+      a->failed_need = need;
+    }
+  }
+  return SDB_OK;
+}
+
+}  // namespace
+namespace sdb {
+void comm_corpus_released(Corpus* c) {
+  ShardState* ss = nullptr;
+  {
+    std::lock_guard<std::mutex> g(g_state_mu);
+    for (size_t i = 0; i < g_states.size(); i++)
+      if (g_states[i].first == c) {
+        ss = g_states[i].second;
+        g_states.erase(g_states.begin() + (long)i);
+        break;
+      }
+  }
+  if (!ss) return;
+  for (ShardSlot& s : ss->slots) {
+    cudaFree(s.d_block);
+    cudaFree(s.d_gather);
+    cudaFree(s.d_res_rows);
+    cudaFree(s.d_res_dist);
+    cudaFree(s.d_res_count);
+    if (s.h_hdr) cudaFreeHost(s.h_hdr);
+    if (s.ev_done) cudaEventDestroy(s.ev_done);
+  }
+  if (ss->arena) {
+    arena_unmap(ss->arena, c->ctx->comm ? c->ctx->comm->rank : 0);
+    cudaFree(ss->arena->base);
+    delete ss->arena;
+  }
+  delete ss;
+}
+}  // namespace sdb
+namespace {
+
+static bool use_p2p(Corpus* c, ShardState* ss) {
+  return c->ctx->comm && c->ctx->comm->nranks > 1 && ss->arena && ss->arena->ok && !exchange_forced_nccl();
+}
 
 // phase A: the local search into this rank's block, header = number of queries this rank must repair on the host
 sdb_status phase_local(Corpus* c, const double* d_queries, const double* h_queries, uint32_t nq, uint32_t k,
@@ -357,15 +559,42 @@ sdb_status phase_local(Corpus* c, const double* d_queries, const double* h_queri
   return SDB_OK;
 }
 
-// phase B: ONE all-gather of the per-shard blocks (inside the caller's group when one thread drives several GPUs)
+// phase B: the exchange of the per-shard blocks.  P2P: this rank's block is stored into every peer's arena slot and a
+// one-warp kernel waits for everybody else's; NCCL: ONE all-gather (inside the caller's group when one thread drives
+// several GPUs).
 sdb_status phase_gather(const Pending& p) {
   Corpus* c = p.c;
+  ShardSlot& s = *p.s;
+  ShardState* ss = state_of(c);
   const BlockLayout bl = block_layout(p.nq, p.k);
   cudaStream_t st = knn_ticket_stream(c, p.ticket);
+  if (use_p2p(c, ss)) {
+    Arena* a = ss->arena;
+    const int R = a->nranks, me = c->ctx->comm->rank;
+    const uint32_t seq = ++a->seq;
+    const uint32_t need_ack = a->slot_seq[p.slot];
+    a->slot_seq[p.slot] = seq;
+    const size_t gather_off = ((size_t)p.slot * R + me) * a->block_cap;
+    const size_t flag_off = a->flags_off + sizeof(uint32_t) * ((size_t)p.slot * R + me);
+    const size_t ack_off = a->acks_off + sizeof(uint32_t) * ((size_t)p.slot * R);
+    const size_t n16 = bl.bytes / 16;
+    unsigned S = (unsigned)((bl.bytes + (128u << 10) - 1) / (128u << 10));  // 256-thread CTAs: they fit beside a screen CTA
+    if (S > 16) S = 16;
+    if (S < 1) S = 1;
+    exch_push_kernel<<<dim3((unsigned)R, S), 256, 0, st>>>(a->peers, a->base, reinterpret_cast<const uint4*>(s.d_block), n16,
+                                                            gather_off, flag_off, ack_off, a->ctr_off, need_ack, seq);
+    exch_wait_kernel<<<1, 32, 0, st>>>(a->base, a->flags_off + sizeof(uint32_t) * ((size_t)p.slot * R), R, seq);
+    SDB_CUDA(cudaGetLastError());
+    s.gather = a->base + (size_t)p.slot * R * a->block_cap;
+    s.stride = a->block_cap;
+    return SDB_OK;
+  }
+  s.gather = s.d_gather;
+  s.stride = bl.bytes;
   if (c->ctx->comm && c->ctx->comm->nranks > 1) {
-    SDB_NCCL(g_nccl.AllGather(p.s->d_block, p.s->d_gather, bl.bytes, ncclChar, c->ctx->comm->comm, st));
+    SDB_NCCL(g_nccl.AllGather(s.d_block, s.d_gather, bl.bytes, ncclChar, c->ctx->comm->comm, st));
   } else {
-    SDB_CUDA(cudaMemcpyAsync(p.s->d_gather, p.s->d_block, bl.bytes, cudaMemcpyDeviceToDevice, st));
+    SDB_CUDA(cudaMemcpyAsync(s.d_gather, s.d_block, bl.bytes, cudaMemcpyDeviceToDevice, st));
   }
   return SDB_OK;
 }
@@ -374,15 +603,22 @@ sdb_status phase_gather(const Pending& p) {
 sdb_status phase_merge(const Pending& p) {
   Corpus* c = p.c;
   ShardSlot& s = *p.s;
+  ShardState* ss = state_of(c);
   const int nranks = c->ctx->comm ? c->ctx->comm->nranks : 1;
   const BlockLayout bl = block_layout(p.nq, p.k);
   cudaStream_t st = knn_ticket_stream(c, p.ticket);
   if (p.k)
-    SDB_TRY(topk_merge_launch(c->ctx, (uint32_t)nranks, p.nq, p.k, (const uint64_t*)(s.d_gather + bl.off_rows),
-                              (const double*)(s.d_gather + bl.off_dist), (const uint32_t*)(s.d_gather + bl.off_cnt),
-                              bl.bytes / 8, bl.bytes / 8, bl.bytes / 4, s.d_out_rows, s.d_out_dist, s.d_out_count, st));
+    SDB_TRY(topk_merge_launch(c->ctx, (uint32_t)nranks, p.nq, p.k, (const uint64_t*)(s.gather + bl.off_rows),
+                              (const double*)(s.gather + bl.off_dist), (const uint32_t*)(s.gather + bl.off_cnt),
+                              s.stride / 8, s.stride / 8, s.stride / 4, s.d_out_rows, s.d_out_dist, s.d_out_count, st));
   else SDB_CUDA(cudaMemsetAsync(s.d_out_count, 0, sizeof(uint32_t) * p.nq, st));
-  SDB_CUDA(cudaMemcpy2DAsync(s.h_hdr, 16, s.d_gather + bl.off_hdr, bl.bytes, 16, (size_t)nranks, cudaMemcpyDeviceToHost, st));
+  SDB_CUDA(cudaMemcpy2DAsync(s.h_hdr, 16, s.gather + bl.off_hdr, s.stride, 16, (size_t)nranks, cudaMemcpyDeviceToHost, st));
+  if (use_p2p(c, ss)) {  // the slot's blocks have been consumed: peers may overwrite them (four batches from now)
+    Arena* a = ss->arena;
+    const int R = a->nranks, me = c->ctx->comm->rank;
+    exch_ack_kernel<<<1, 32, 0, st>>>(a->peers, a->acks_off + sizeof(uint32_t) * ((size_t)p.slot * R + me), R, a->slot_seq[p.slot]);
+    SDB_CUDA(cudaGetLastError());
+  }
   if (s.h_out_count) {
     if (p.k) {
       SDB_CUDA(cudaMemcpyAsync(s.h_out_rows, s.d_out_rows, sizeof(uint64_t) * (size_t)p.nq * p.k, cudaMemcpyDeviceToHost, st));
@@ -512,6 +748,7 @@ sdb_status sdb_ctx_create_multi(const int* devices, int ndev, sdb_ctx** out) {
       cm->comm = comms[i];
       cm->nranks = ndev;
       cm->rank = i;
+      cm->single_process = true;
       out[i]->comm = cm;
     }
   }
@@ -533,6 +770,13 @@ static sdb_status sharded_submit(sdb_corpus* c, const double* d_queries, const d
   {
     std::lock_guard<std::mutex> g(c->mu);
     SDB_CUDA(cudaSetDevice(c->ctx->device));
+    if (c->ctx->comm && c->ctx->comm->nranks > 1 && c->ctx->comm->nranks <= MAX_P2P_RANKS && !exchange_forced_nccl()) {
+      if (c->ctx->comm->single_process) {
+        set_error("contexts of sdb_ctx_create_multi are driven through sdb_knn_sharded_multi");
+        return SDB_EINVAL;
+      }
+      SDB_TRY(arena_ensure_ipc(c, state_of(c), block_layout(nq, k).bytes));
+    }
     SDB_TRY(phase_local(c, d_queries, h_queries, nq, k, d_out_rows, d_out_dist, d_out_count, h_out_rows, h_out_dist,
                         h_out_count, &p));
     sdb_status rc = phase_gather(p);
@@ -596,6 +840,8 @@ sdb_status sdb_knn_sharded_multi(sdb_corpus* const* shards, int n, const double*
   }
   sdb_status rc = SDB_OK;
   int started = 0;
+  if (n > 1 && shards[0]->ctx->comm && shards[0]->ctx->comm->single_process && !exchange_forced_nccl())
+    SDB_TRY(arena_ensure_multi(shards, n, block_layout(nq, k).bytes));
   for (int i = 0; i < n && rc == SDB_OK; i++) {  // every shard searches; shard 0's merged copy goes to the caller
     cudaSetDevice(shards[i]->ctx->device);
     ShardState* ss = state_of(shards[i]);

@@ -146,6 +146,7 @@ sdb_status screen_tc_init_device();
 sdb_status candidates_init_device();
 sdb_status exact_init_device();
 void comm_destroy(Ctx* ctx);  // comm.cu
+void comm_corpus_released(struct Corpus* c);  // comm.cu: drops the corpus's sharded-search state (slot buffers, arena)
 int comm_size(const Ctx* ctx);
 int comm_rank(const Ctx* ctx);
 sdb_status comm_allreduce_sum(Ctx* ctx, void* d_buf, size_t count, int elem_bytes, cudaStream_t st);
@@ -169,7 +170,7 @@ struct Ticket {
   cudaStream_t stream = nullptr;  // every kernel / copy of this batch (slot parity picks the context's stream)
   int set = 0;                    // scratch set of this batch
   int screen = 0;       // sdb_screen this batch ran
-  uint32_t rung = 0, n_rungs = 0;
+  uint32_t rung = 0, n_rungs = 0, n_batch_rungs = 0, n_repaired = 0;
   uint32_t n_passes = 0;
   uint64_t launches0 = 0;
   cudaEvent_t ev_begin = nullptr, ev_screen0 = nullptr, ev_screen1 = nullptr, ev_end = nullptr;
@@ -268,6 +269,11 @@ struct Corpus : Scratch {
   uint32_t* d_sel = nullptr;     // radix-select state
   uint64_t ex_cap = 0;
   double* d_fb_q = nullptr;      // fallback query scratch (one query: f64 copy, |q|, flags)
+  double* d_rp_q = nullptr;      // repair sub-batch: the failed queries of a batch, gathered, and their results
+  uint64_t* d_rp_rows = nullptr;
+  double* d_rp_dist = nullptr;
+  uint32_t* d_rp_cnt = nullptr;
+  size_t rp_cap_q = 0, rp_cap_o = 0, rp_cap_n = 0;
   double* d_fb_qmag = nullptr;
   uint32_t* d_fb_qflags = nullptr;
   Scratch sets[2];  // the inactive set's fields are parked here (see Scratch)
