@@ -52,10 +52,14 @@ def bench_hnsw(a):
     n, dim = a.rows, a.dim
     centers = torch.nn.functional.normalize(torch.randn((4096, dim), generator=g, device=dev), dim=1)
     def sample(cnt):
-        c = torch.randint(0, 4096, (cnt,), generator=g, device=dev)
         # sigma = TOTAL noise norm relative to the unit-norm centroid (per-coordinate sigma / sqrt(dim)); a per-coordinate
         # 0.15 would bury the centroids under isotropic noise in high dimension and make every ANN method degenerate
-        return (centers[c] + (a.sigma / dim ** 0.5) * torch.randn((cnt, dim), generator=g, device=dev)).contiguous()
+        out = torch.empty((cnt, dim), dtype=torch.float32, device=dev)
+        for r0 in range(0, cnt, 1 << 20):  # in slabs: 10M x 768 would otherwise need three 31 GB temporaries
+            r1 = min(cnt, r0 + (1 << 20))
+            c = torch.randint(0, 4096, (r1 - r0,), generator=g, device=dev)
+            out[r0:r1] = centers[c] + (a.sigma / dim ** 0.5) * torch.randn((r1 - r0, dim), generator=g, device=dev)
+        return out
     x = sample(n)
     queries = sample(a.queries)
     torch.cuda.synchronize()
@@ -68,7 +72,8 @@ def bench_hnsw(a):
             tl[0] = now
     if a.builder == "incremental":
         from surrealdb_b200.hnsw_build import build_incremental
-        res = build_incremental(ctx, x, a.metric.upper(), m=a.m, m0=2 * a.m, efc=a.efc, seed=7, growth=a.growth, progress=prog)
+        res = build_incremental(ctx, x, a.metric.upper(), m=a.m, m0=2 * a.m, efc=a.efc, seed=7, growth=a.growth, progress=prog,
+                                settle=not a.no_settle)
         x = res["x"]  # re-ordered by level: element ids below are the NEW ids (rows of this tensor)
         layers = [(rp.cpu().numpy().astype(np.uint64), ci.cpu().numpy().astype(np.uint32)) for rp, ci in res["layers_dev"]] if not a.no_cpu else None
         entry = res["entry"]
@@ -89,9 +94,26 @@ def bench_hnsw(a):
     qh = queries.cpu().numpy()
     print(f"[load] index on device {time.perf_counter() - t0:.1f}s", file=sys.stderr, flush=True)
     idx.search_graph(qh[:256], a.k, a.ef)  # warm-up
-    (ids, dist, cnt, ctr), ms, wall = dev_time_ms(ctx, lambda: idx.search_graph(qh, a.k, a.ef, counters=True))
+    (ids, dist, cnt, ctr), ms_call, wall = dev_time_ms(ctx, lambda: idx.search_graph(qh, a.k, a.ef, counters=True))
     visited, expanded = int(ctr[:, 0].sum()), int(ctr[:, 1].sum())
     byts = visited * (4.0 * dim + 4.0) + expanded * deg0 * 4.0
+    # `value`: queries and results resident in HBM (sdb_hnsw_search_device); the host-buffer call above is the e2e figure
+    import ctypes as C
+    from surrealdb_b200 import _lib as L
+    d_ids = torch.empty((a.queries, a.k), dtype=torch.int64, device=dev)
+    d_dist = torch.empty((a.queries, a.k), dtype=torch.float64, device=dev)
+    d_cnt = torch.empty((a.queries,), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    def dev_search():
+        L.check(L.lib().sdb_hnsw_search_device(idx.h, C.c_void_p(queries.data_ptr()), a.queries, a.k, a.ef, C.c_void_p(d_ids.data_ptr()),
+                                               C.c_void_p(d_dist.data_ptr()), C.c_void_p(d_cnt.data_ptr())))
+    dev_search()
+    best = None
+    for _ in range(3):
+        _, m1, w1 = dev_time_ms(ctx, dev_search)
+        best = m1 if best is None or m1 < best else best
+    ms = best
+    same_dev = bool(np.array_equal(d_ids.cpu().numpy()[:, :1].astype(np.uint64), ids[:, :1]))
     # recall@k against exact brute force (f64 reference arithmetic) on the same corpus
     col = VectorColumn(ctx, dim, a.metric.upper(), "F32", capacity=n)
     torch.cuda.synchronize()
@@ -102,7 +124,10 @@ def bench_hnsw(a):
     recall = float(np.mean([len(set(rows[i].tolist()) & set(ids[i, : cnt[i]].tolist())) / a.k for i in range(nr)]))
     peak, src = peaks()
     out = {"bench": "hnsw_search", "metric": f"HNSW KNN queries/sec (M={a.m}, M0={2*a.m}, ef={a.ef}, k={a.k})",
-           "value": a.queries / (wall * 1e-3), "unit": "queries/s", "device_ms": ms, "call_wall_ms": wall,
+           "value": a.queries / (ms * 1e-3), "unit": "queries/s", "device_ms": ms,
+           "e2e": {"value": a.queries / (wall * 1e-3), "unit": "queries/s", "call_wall_ms": wall, "api": "sdb_hnsw_search (pageable host queries and results)",
+                   "h2d_bytes": int(a.queries * dim * 4), "d2h_bytes": int(a.queries * a.k * 16 + a.queries * 20)},
+           "device_results_equal_host_call": same_dev,
            "recall_at_k": recall, "config": {"rows": n, "dim": dim, "queries": a.queries, "metric": a.metric.lower(), "data": f"4096 unit-norm centroids + gaussian noise of total norm {a.sigma}",
                                               "graph": ("GPU batched true insertion (hnsw_build.build_incremental): walk kernel as insertion search (efc=%d), Heuristic::select, bidirectional linking, re-selection of over-full nodes; batches grow by %.2fx" % (a.efc, a.growth)) if a.builder == "incremental" else "GPU batch-built layers (hnsw_build.py): kNN candidates" + (" from id prefixes" if a.prefix else "") + " + Heuristic::select + bidirectional re-selection", "build_s": build_s,
                                               "layers": n_layers, "visited_per_query": visited / a.queries,
@@ -112,6 +137,8 @@ def bench_hnsw(a):
                         "algorithmic_bytes": byts, "traffic": None}}
     if not a.no_cpu:
         from oracle import pyoracle as O
+        if xh is None:
+            xh = x.cpu().numpy()
         graph = {"vectors": xh, "layers": layers, "entry_point": entry, "metric": a.metric.lower()}
         threads = os.cpu_count() or 1
         nqc = min(a.queries, 8 * threads)
@@ -238,7 +265,8 @@ def bench_graph(a):
         sizes.append(int(fr.size))
     sizes.append(int(out_ids.size))
     byts = sum(16.0 * sizes[h] + 8.0 * sizes[h + 1] for h in range(a.hops))
-    (coll, cms, cwall) = dev_time_ms(ctx, lambda: collect(graph, sources[:1], 1, a.hops, False))
+    collect(graph, sources[:1], 1, a.hops, False)  # warm-up: allocates the per-graph BFS state
+    (coll, cms, cwall) = dev_time_ms(ctx, lambda: collect(graph, sources[:a.collect_sources], 1, a.hops, False))
     cms = tmax(cms)
     if rank != 0:
         dist.barrier()
@@ -253,7 +281,7 @@ def bench_graph(a):
                       "graph": "R-MAT (.57,.19,.19,.05), integer ids, adjacency in (src,dst)=edge-id order",
                       "sharding": "none" if world == 1 else f"1-D source ranges, {world} shards with equal edge counts; one all-reduce pair per hop",
                       "generation_s": t_gen,
-                      "collect_bfs_from_1_source": {"device_ms": cms, "nodes": int(coll.size)}},
+                      "collect_bfs": {"sources": a.collect_sources, "device_ms": cms, "nodes": int(coll.size)}},
            "roofline": {"bound": "hbm", "kernel": "expand_kernel (+degree/scan)", "achieved": byts / (ms_dev * 1e-3) / 1e9,
                         "peak": peak, "unit": "GB/s", "frac": byts / (ms_dev * 1e-3) / 1e9 / peak, "peak_source": srcp,
                         "algorithmic_bytes": byts, "traffic": None,
@@ -354,12 +382,14 @@ if __name__ == "__main__":
     ap.add_argument("--builder", default="batch", choices=["batch", "incremental"])
     ap.add_argument("--efc", type=int, default=150)
     ap.add_argument("--growth", type=float, default=0.25)
+    ap.add_argument("--no-settle", action="store_true", help="incremental builder without the second pass per batch")
     ap.add_argument("--log2-nodes", type=int, default=24)
     ap.add_argument("--edges", type=int, default=160_000_000)
     ap.add_argument("--nodes", type=int, default=0, help="node count (not a power of two: R-MAT ids are folded mod nodes)")
     ap.add_argument("--checksum", action="store_true", help="print order-sensitive checksums of the result (1 vs N GPUs)")
     ap.add_argument("--sources", type=int, default=1024)
     ap.add_argument("--hops", type=int, default=3)
+    ap.add_argument("--collect-sources", type=int, default=1, help="start nodes of the +collect BFS")
     ap.add_argument("--limit", type=int, default=32, help="GraphEdgeScan per-source limit (0 = none)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--pageable", action="store_true", help="stage: keep the value blobs in pageable host memory")

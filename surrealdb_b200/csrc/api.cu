@@ -1,6 +1,8 @@
 // api.cu -- the extern "C" boundary (include/sdbgpu.h): contexts, corpus lifecycle, brute-force KNN driver.
 #include <cmath>
 
+#include <chrono>
+
 #include "internal.cuh"
 
 namespace sdb {
@@ -161,6 +163,40 @@ static sdb_status ticket_prepare(Corpus* c, Ticket& t, uint32_t nq) {
   return SDB_OK;
 }
 
+bool trace_enabled() {
+  static const bool on = getenv("SDB_TRACE") != nullptr;
+  return on;
+}
+void trace_mark(Ctx* ctx, Ticket& t, const char* name, cudaStream_t st) {
+  if (!trace_enabled()) return;
+  if (!ctx->trace_epoch) {
+    cudaEventCreate(&ctx->trace_epoch);
+    cudaEventRecord(ctx->trace_epoch, st);
+    cudaEventSynchronize(ctx->trace_epoch);
+    ctx->trace_host0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  }
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  t.trace.emplace_back(name, e);
+}
+void trace_host(Ctx* ctx, uint32_t ticket, const char* name) {
+  if (!trace_enabled() || !ctx->trace_epoch) return;
+  const double now = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  fprintf(stderr, "TRACE dev%d ticket%u host %-12s %10.3f\n", ctx->device, ticket, name, (now - ctx->trace_host0) * 1e3);
+}
+void trace_dump(Ctx* ctx, Ticket& t) {
+  if (!trace_enabled()) return;
+  for (auto& m : t.trace) {
+    float ms = 0.f;
+    cudaEventSynchronize(m.second);
+    cudaEventElapsedTime(&ms, ctx->trace_epoch, m.second);
+    fprintf(stderr, "TRACE dev%d ticket%u set%d %-12s %10.3f\n", ctx->device, t.id, t.set, m.first, ms);
+    cudaEventDestroy(m.second);
+  }
+  t.trace.clear();
+}
+
 static sdb_status enqueue_batch(Corpus* c, Ticket& t) {
   Ctx* ctx = c->ctx;
   cudaStream_t st = t.stream;
@@ -171,6 +207,7 @@ static sdb_status enqueue_batch(Corpus* c, Ticket& t) {
   t.n_rungs = (uint32_t)rungs.size();
   t.n_passes = 0;
   SDB_CUDA(cudaEventRecord(t.ev_begin, st));
+  trace_mark(ctx, t, "begin", st);
   if (rungs.empty()) {  // exact-only: the exact kernel needs the prepared queries (f64 copy, |q|, flags)
     t.screen = SDB_SCREEN_NONE_EXACT;
     SDB_TRY(scratch_for(c, nq, 4096));
@@ -200,6 +237,7 @@ static sdb_status enqueue_batch(Corpus* c, Ticket& t) {
   // for the end of the previous batch's screen -- only the TAIL of the previous batch overlaps with it.
   if (c->last_main && c->last_main != t.ev_main) SDB_CUDA(cudaStreamWaitEvent(st, c->last_main, 0));
   SDB_CUDA(cudaEventRecord(t.ev_screen0, st));  // after the wait: screen_ms is this batch's screen, not the queueing
+  trace_mark(ctx, t, "screen0", st);
   if (tc && c->stream_refine) {
     PassDesc p0, pm;
     build_stream_passes(c->n, cap, k, &p0, &pm);
@@ -212,7 +250,9 @@ static sdb_status enqueue_batch(Corpus* c, Ticket& t) {
     } else if (pm.count) {
       SDB_TRY(screen_tc_pass(c, nq, k, p0, int8, 3, st));           // probe: chunk maxima of a few tiles
       SDB_TRY(cand_seed_from_probe(c, nq, k, p0.count, st));         // thresholds + histogram geometry
+      trace_mark(ctx, t, "seeded", st);
       SDB_TRY(screen_tc_pass(c, nq, k, pm, int8, 2, st));           // the streaming launch over every tile
+      trace_mark(ctx, t, "main_end", st);
       SDB_CUDA(cudaEventRecord(t.ev_main, st));
       c->last_main = t.ev_main;
       SDB_TRY(cand_select(c, nq, k, int8, c->last_slots, false, st));
@@ -237,6 +277,7 @@ static sdb_status enqueue_batch(Corpus* c, Ticket& t) {
     c->last_main = t.ev_main;
   }
   SDB_CUDA(cudaEventRecord(t.ev_screen1, st));
+  trace_mark(ctx, t, "selected", st);
   // stage B: the coarse screens' candidates are re-scored in f32 and narrowed before the (FP64-bound) exact re-rank
   static const bool no_refine = getenv("SDB_NO_REFINE") != nullptr;
   bool refined = false;
@@ -244,13 +285,17 @@ static sdb_status enqueue_batch(Corpus* c, Ticket& t) {
     SDB_TRY(cand_refine(c, nq, st));
     SDB_TRY(cand_select(c, nq, k, false, 0u, false, st, 1));
     refined = true;
+    trace_mark(ctx, t, "refined", st);
   }
   SDB_TRY(cand_rerank(c, nq, st, refined));
+  trace_mark(ctx, t, "reranked", st);
   SDB_TRY(cand_final(c, nq, k, t.row_base, t.d_out_rows, t.d_out_dist, t.d_out_count, st));
+  trace_mark(ctx, t, "final", st);
   SDB_CUDA(cudaMemcpyAsync(t.h_flags, c->d_flags, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, st));
   SDB_CUDA(cudaMemcpyAsync(t.h_qflags, c->d_qflags, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, st));
   SDB_CUDA(cudaMemcpyAsync(t.h_stat, c->d_stat, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, st));
   SDB_CUDA(cudaEventRecord(t.ev_end, st));
+  trace_mark(ctx, t, "end", st);
   return SDB_OK;
 }
 
@@ -400,6 +445,8 @@ static sdb_status finish_stats(Corpus* c, Ticket& t, uint32_t n_fallback) {
   stt.n_survivors = t.h_stat[3];
   stt.kernel_launches = c->ctx->launches - t.launches0;
   c->stats = stt;
+  trace_host(c->ctx, t.id, "waited");
+  trace_dump(c->ctx, t);
   return SDB_OK;
 }
 
@@ -468,6 +515,7 @@ static sdb_status submit_locked(Corpus* c, Ticket* t, const double* d_queries, u
   }
   const sdb_status rc = enqueue_batch(c, *t);
   if (rc == SDB_OK) t->busy = true;
+  trace_host(c->ctx, t->id, "submitted");
   return rc;
 }
 
@@ -522,6 +570,10 @@ sdb_status knn_submit_for_shard(Corpus* c, const double* d_queries, const double
   *ticket = t->id;
   *d_queries_used = d_queries;
   return SDB_OK;
+}
+void knn_trace_mark(Corpus* c, uint32_t ticket, const char* name) {
+  Ticket* t = find_ticket(c, ticket);
+  if (t) trace_mark(c->ctx, *t, name, t->stream);
 }
 cudaStream_t knn_ticket_stream(Corpus* c, uint32_t ticket) {
   Ticket* t = find_ticket(c, ticket);
@@ -736,6 +788,10 @@ sdb_status sdb_ctx_create(int device, sdb_ctx** out) {
   sdb_ctx* c = new sdb_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
+  {
+    int least = 0, greatest = 0;
+    if (cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess) c->prio_high = greatest;
+  }
   SDB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   SDB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
   SDB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));

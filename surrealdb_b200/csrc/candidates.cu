@@ -797,12 +797,81 @@ __global__ void __launch_bounds__(WARPS * 32) cand_rerank_v4_kernel(
 }
 constexpr size_t RRV_SMEM = sizeof(double) * QCHUNK + sizeof(float) * 4 * 32 * RRV_STRIDE;  // 4 warps: 75.8 KB
 
+
+// After the f32 stage a query keeps k candidates plus a few near-ties (about 10 at k = 10), and the exact re-rank is one
+// strictly sequential f64 chain per candidate: FP64-issue-bound, nothing to gain from staging.  This variant uses NO
+// shared memory and 16 lanes per query (two queries per warp), so that (a) twice as many chains share every FP64
+// warp-instruction as with one query per warp, and (b) its blocks run beside the resident screen CTA of the next batch
+// (the staged variant's 6 KB per warp let only two warps per SM in, and the re-rank took 0.58 ms instead of 0.1 ms
+// whenever it overlapped a screen -- SDB_TRACE timeline, round 2).  Every lane streams its own row (16-byte loads; the
+// second half of each 32-byte sector comes from L1) and reads the query from global memory (one address per half-warp).
+template <bool COSINE>
+__global__ void __launch_bounds__(128) cand_rerank_packed_kernel(
+    const float* __restrict__ rows, uint32_t dim, const double* __restrict__ mag, const double* __restrict__ q64,
+    const double* __restrict__ qmag, const uint32_t* __restrict__ qflags, const Cand* __restrict__ cand,
+    const uint32_t* __restrict__ cnt, uint32_t cap, const uint32_t* __restrict__ special, uint32_t n_special, uint32_t nq,
+    uint64_t* __restrict__ rr_key, double* __restrict__ rr_dist, uint32_t* __restrict__ rr_row, uint32_t rr_stride) {
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const uint32_t q = (blockIdx.x * 4 + warp) * 2 + (lane >> 4), l16 = lane & 15u;
+  if (q >= nq) return;
+  const uint32_t n_c = cnt[q] < cap ? cnt[q] : cap;
+  const uint32_t n_e = n_c + n_special;
+  const bool q_nan = (qflags[q] & 2u) != 0;
+  const double qm = qmag[q];
+  const double* qv = q64 + (size_t)q * dim;
+  const bool vec4 = (dim & 3u) == 0;
+  for (uint32_t e = l16; e < n_e; e += 16) {
+    const uint32_t my_row = e < n_c ? cand[(size_t)q * cap + e].row : special[e - n_c];
+    const float* x = rows + (size_t)my_row * dim;
+    ExactAcc acc;
+    if (vec4) {
+#pragma unroll 2
+      for (uint32_t j = 0; j < dim; j += 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + j));
+        const double2 qa = __ldg(reinterpret_cast<const double2*>(qv + j));
+        const double2 qb = __ldg(reinterpret_cast<const double2*>(qv + j + 2));
+        if (COSINE) {
+          acc.cosine_step((double)v.x, qa.x);
+          acc.cosine_step((double)v.y, qa.y);
+          acc.cosine_step((double)v.z, qb.x);
+          acc.cosine_step((double)v.w, qb.y);
+        } else {
+          acc.euclid_step((double)v.x, qa.x);
+          acc.euclid_step((double)v.y, qa.y);
+          acc.euclid_step((double)v.z, qb.x);
+          acc.euclid_step((double)v.w, qb.y);
+        }
+      }
+    } else {
+      for (uint32_t j = 0; j < dim; j++) {
+        if (COSINE) acc.cosine_step((double)__ldg(x + j), __ldg(qv + j));
+        else acc.euclid_step((double)__ldg(x + j), __ldg(qv + j));
+      }
+    }
+    const double d = COSINE ? cosine_finish(acc, mag[my_row], qm, q_nan) : euclid_finish(acc, q_nan);
+    const size_t o = (size_t)q * rr_stride + e;
+    rr_key[o] = dist_key(d);
+    rr_dist[o] = d;
+    rr_row[o] = my_row;
+  }
+}
+
 sdb_status cand_rerank(Corpus* c, uint32_t nq, cudaStream_t st, bool small_sets) {
   const dim3 grid(nq, RR_GROUPS_Y);
   static const bool no_v4 = getenv("SDB_RERANK_SCALAR") != nullptr;
-  if (small_sets && c->dtype == SDB_F32)
-    // after the f32 stage a query keeps k plus a few near-ties: the kernel is FP64-bound whatever its shape, so it is
-    // kept small (one warp, 6 KB of shared memory) and runs beside the next batch's screen
+  static const bool no_packed = getenv("SDB_RERANK_STAGED") != nullptr;
+  if (small_sets && c->dtype == SDB_F32 && !no_packed && (c->metric == SDB_COSINE || c->metric == SDB_EUCLIDEAN)) {
+    const unsigned g = (nq + 7) / 8;
+    if (c->metric == SDB_COSINE)
+      cand_rerank_packed_kernel<true><<<g, 128, 0, st>>>((const float*)c->d_rows, c->dim, c->d_mag, c->d_q64, c->d_qmag, c->d_qflags,
+                                                        c->d_cand, c->d_cand_cnt, c->sc_cap, c->d_special, c->n_special, nq,
+                                                        c->d_rr_key, c->d_rr_dist, c->d_rr_row, c->rr_stride);
+    else
+      cand_rerank_packed_kernel<false><<<g, 128, 0, st>>>((const float*)c->d_rows, c->dim, c->d_mag, c->d_q64, c->d_qmag, c->d_qflags,
+                                                         c->d_cand, c->d_cand_cnt, c->sc_cap, c->d_special, c->n_special, nq,
+                                                         c->d_rr_key, c->d_rr_dist, c->d_rr_row, c->rr_stride);
+  } else if (small_sets && c->dtype == SDB_F32)
+    // (kept for A/B: one warp per query, rows transposed through 6 KB of shared memory)
     cand_rerank_kernel<float, 1, 32, 256><<<grid, 32, 0, st>>>((const float*)c->d_rows, c->dim, (int)c->metric, c->d_mag,
                                                                c->d_q64, c->d_qmag, c->d_qflags, c->d_cand, c->d_cand_cnt,
                                                                c->sc_cap, c->d_special, c->n_special, c->d_rr_key,

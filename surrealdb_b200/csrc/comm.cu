@@ -157,6 +157,7 @@ sdb_status knn_finish_for_shard(Corpus* c, uint32_t ticket, bool* repaired);
 sdb_status knn_release_ticket(Corpus* c, uint32_t ticket);
 const uint32_t* knn_ticket_stat_host(Corpus* c, uint32_t ticket, int* exact_only);
 cudaStream_t knn_ticket_stream(Corpus* c, uint32_t ticket);
+void knn_trace_mark(Corpus* c, uint32_t ticket, const char* name);
 sdb_status topk_merge_launch(Ctx* ctx, uint32_t n_lists, uint32_t nq, uint32_t k, const uint64_t* d_rows,
                              const double* d_dist, const uint32_t* d_counts, uint64_t stride_rows, uint64_t stride_dist,
                              uint64_t stride_counts, uint64_t* d_out_rows, double* d_out_dist, uint32_t* d_out_count,
@@ -585,6 +586,7 @@ sdb_status phase_gather(const Pending& p) {
                                                             gather_off, flag_off, ack_off, a->ctr_off, need_ack, seq);
     exch_wait_kernel<<<1, 32, 0, st>>>(a->base, a->flags_off + sizeof(uint32_t) * ((size_t)p.slot * R), R, seq);
     SDB_CUDA(cudaGetLastError());
+    knn_trace_mark(c, p.ticket, "exchanged");
     s.gather = a->base + (size_t)p.slot * R * a->block_cap;
     s.stride = a->block_cap;
     return SDB_OK;
@@ -627,6 +629,7 @@ sdb_status phase_merge(const Pending& p) {
     SDB_CUDA(cudaMemcpyAsync(s.h_out_count, s.d_out_count, sizeof(uint32_t) * p.nq, cudaMemcpyDeviceToHost, st));
   }
   SDB_CUDA(cudaEventRecord(s.ev_done, st));
+  knn_trace_mark(c, p.ticket, "merged");
   return SDB_OK;
 }
 

@@ -136,6 +136,9 @@ struct Ctx {
   volatile int* h_cancel = nullptr;
   int* d_cancel = nullptr;
   cudaStream_t cancel_stream = nullptr;
+  int prio_high = 0;  // greatest launch priority of the device (cudaDeviceGetStreamPriorityRange)
+  cudaEvent_t trace_epoch = nullptr;  // SDB_TRACE
+  double trace_host0 = 0.0;           // host clock (s) at the epoch
 };
 inline bool ctx_cancelled(const Ctx* ctx) { return ctx->h_cancel && *ctx->h_cancel != 0; }
 
@@ -187,8 +190,14 @@ struct Ticket {
   cudaEvent_t ev_h2d = nullptr, ev_out = nullptr;
   cudaEvent_t ev_main = nullptr;  // recorded after this batch's last screen launch (the next batch's screen waits for it)
   bool wait_h2d = false;  // the batch's stream still has to wait for ev_h2d (queries travelling on the copy stream)
+  // SDB_TRACE=1: named timestamps of this batch on its stream, printed at wait time relative to the context's epoch
+  std::vector<std::pair<const char*, cudaEvent_t>> trace;
 };
 constexpr int N_TICKETS = 4;
+bool trace_enabled();
+void trace_mark(Ctx* ctx, Ticket& t, const char* name, cudaStream_t st);  // api.cu
+void trace_dump(Ctx* ctx, Ticket& t);
+void trace_host(Ctx* ctx, uint32_t ticket, const char* name);  // host-side timestamp on the same time base
 
 // Per-batch search scratch.  Two sets exist per corpus: consecutive batches alternate between them (and between the
 // context's two streams), so the screen of batch i+1 can run while the tail of batch i (candidate selection, f32

@@ -635,10 +635,26 @@ sdb_status screen_tc_pass(Corpus* c, uint32_t nq, uint32_t k, const PassDesc& p,
     uint32_t* scnt = c->d_sub_cnt + (size_t)q0 * slots;
     const HistParam* hp = c->d_hparam + q0;
     uint32_t* hist = c->d_hist + (size_t)q0 * HIST_BINS;
-#define LAUNCH_TC1(COS, I8, MODE)                                                                              \
-  tc::screen_tc_kernel<COS, I8, MODE><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(                              \
-      map_a, map_b, c->d_snorm, k_blocks, n_mblocks, nqc, p, tau, cand, ccnt, c->sc_cap, sub, scnt, k, hp, hist,  \
-      c->d_probe + (size_t)q0 * PROBE_STRIDE, PROBE_STRIDE, sleep_min, sleep_max)
+    // the screen is launched at the highest priority: when the previous batch's screen retires, the blocks of THIS
+    // launch are placed before the queued blocks of that batch's tail kernels (which fit beside a screen CTA anyway),
+    // instead of waiting behind two 13 KB selection blocks per SM
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(tc::THREADS);
+    cfg.dynamicSmemBytes = tc::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributePriority;
+    attr[0].val.priority = ctx->prio_high;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    float* probe_ptr = c->d_probe + (size_t)q0 * PROBE_STRIDE;
+    const uint32_t probe_stride = PROBE_STRIDE, cap_arg = c->sc_cap;
+    const float* snorm_arg = c->d_snorm;
+#define LAUNCH_TC1(COS, I8, MODE)                                                                                    \
+  SDB_CUDA(cudaLaunchKernelEx(&cfg, tc::screen_tc_kernel<COS, I8, MODE>, map_a, map_b, snorm_arg, k_blocks, n_mblocks, \
+                              nqc, p, tau, cand, ccnt, cap_arg, sub, scnt, k, hp, hist, probe_ptr, probe_stride,       \
+                              sleep_min, sleep_max))
 #define LAUNCH_TC(COS, I8)                   \
   do {                                       \
     if (mode == 0) LAUNCH_TC1(COS, I8, 0);   \
