@@ -62,8 +62,10 @@ typedef enum {
  * values are f32-representable (the BASELINE configs) and enables the low-precision screen. */
 typedef enum { SDB_F32 = 0, SDB_F64 = 1 } sdb_dtype;
 
-/* which screening kernel sdb_knn_bruteforce uses (results are identical for all; this only moves
- * the performance point).  AUTO: tcgen05 bf16 (HBM-bound on half the bytes for small batches, tensor-bound for large ones). */
+/* which screening kernel sdb_knn_bruteforce uses (results are identical for all; this only moves the performance
+ * point).  AUTO: cosine corpora whose normalised rows quantise well (largest relative int8 error <= 0.02 once the few
+ * outlier rows are set aside) start on the int8 tensor-core screen, everything else on the bf16 one; queries whose
+ * proof fails climb to finer screens (bf16, then the f32 stream) before the exact kernel. */
 typedef enum {
   SDB_SCREEN_AUTO = 0,
   SDB_SCREEN_SIMT_F32 = 1,   /* f32 streaming SIMT kernel                                             */
@@ -78,7 +80,7 @@ typedef struct {
   uint32_t n_passes;         /* threshold-refinement passes of the screen                      */
   uint32_t n_fallback;       /* queries re-run through the exact kernel (verification failed)  */
   uint32_t n_special_rows;   /* rows with zero / non-finite norm (always exact-ranked)         */
-  uint64_t n_candidates;     /* largest candidate set of any query of the batch                */
+  uint64_t n_candidates;     /* largest candidate set of any query that reached the exact re-rank */
   uint64_t n_reranked;       /* exact f64 distances computed by the re-rank kernel             */
   uint64_t kernel_launches;  /* kernels launched by this call                                  */
   float screen_ms;           /* device time of the screening kernels (CUDA events)             */

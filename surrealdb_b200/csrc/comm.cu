@@ -257,7 +257,10 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
 
 // grid (nranks, S): CTA (p, s) stores its share of this rank's block into peer p's gather slot, the last of the S CTAs
 // publishes `seq` in p's flag word.  Before the first store thread 0 makes sure p has consumed the previous content of
-// the slot (p's acknowledgement lands in OUR arena).
+// the slot (p's acknowledgement lands in OUR arena).  ctr_off addresses the arrival counters of THIS SLOT (one per
+// peer): pushes of different slots run concurrently on the two batch streams and must not share a counter -- with one
+// counter per peer a push could publish its flag before its second CTA had copied, and the other push never published
+// (a hang of the 50-step 8-GPU run, round 2); two pushes through the same slot are ordered by the ticket's life cycle.
 __global__ void __launch_bounds__(256) exch_push_kernel(PeerTable pt, uint8_t* my_base, const uint4* __restrict__ src,
                                                         size_t n16, size_t gather_off, size_t flag_off, size_t ack_off,
                                                         size_t ctr_off, uint32_t need_ack, uint32_t seq) {
@@ -333,7 +336,7 @@ static sdb_status arena_alloc_local(Corpus* c, Arena* a, size_t need) {
   a->flags_off = gather_bytes;
   a->acks_off = a->flags_off + 256 * ((sizeof(uint32_t) * N_TICKETS * R + 255) / 256);
   a->ctr_off = a->acks_off + 256 * ((sizeof(uint32_t) * N_TICKETS * R + 255) / 256);
-  a->bytes = a->ctr_off + 256;
+  a->bytes = a->ctr_off + 256 * ((sizeof(uint32_t) * N_TICKETS * R + 255) / 256);
   SDB_CUDA(cudaMalloc(&a->base, a->bytes));
   SDB_CUDA(cudaMemset(a->base, 0, a->bytes));
   SDB_CUDA(cudaDeviceSynchronize());
@@ -582,8 +585,9 @@ sdb_status phase_gather(const Pending& p) {
     unsigned S = (unsigned)((bl.bytes + (128u << 10) - 1) / (128u << 10));  // 256-thread CTAs: they fit beside a screen CTA
     if (S > 16) S = 16;
     if (S < 1) S = 1;
+    const size_t ctr_off = a->ctr_off + sizeof(uint32_t) * ((size_t)p.slot * R);
     exch_push_kernel<<<dim3((unsigned)R, S), 256, 0, st>>>(a->peers, a->base, reinterpret_cast<const uint4*>(s.d_block), n16,
-                                                            gather_off, flag_off, ack_off, a->ctr_off, need_ack, seq);
+                                                            gather_off, flag_off, ack_off, ctr_off, need_ack, seq);
     exch_wait_kernel<<<1, 32, 0, st>>>(a->base, a->flags_off + sizeof(uint32_t) * ((size_t)p.slot * R), R, seq);
     SDB_CUDA(cudaGetLastError());
     knn_trace_mark(c, p.ticket, "exchanged");

@@ -415,3 +415,32 @@ def test_sharded_graph_two_gpus_threads():
         if want_collect is not None:
             assert np.array_equal(out[r][1], want_collect)
     assert np.array_equal(out[0][1], out[1][1])
+
+
+def test_failed_queries_climb_the_rungs_as_a_small_batch(ctx):
+    # Two queries sit on a crowd of 6000 near-duplicates: all of them fall inside the int8 margin, the 4096-entry lists
+    # overflow and the proof cannot succeed on the batch's rung.  Only THESE queries are re-screened on the finer rungs
+    # (a small batch of their own) -- the rest of the batch is untouched, nothing reaches the exact kernel, and the
+    # answers are the oracle's bit for bit.
+    rng = np.random.default_rng(77)
+    n, dim, nq, k = 80_000, 128, 256, 10
+    corpus = rng.uniform(-1, 1, (n, dim)).astype(np.float32)
+    center = rng.uniform(-1, 1, dim)
+    corpus[1000:7000] = (center[None, :] + rng.normal(0, 2e-3, (6000, dim))).astype(np.float32)
+    queries = rng.uniform(-1, 1, (nq, dim))
+    queries[5] = center
+    queries[77] = center + rng.normal(0, 1e-3, dim)
+    col = make_col(ctx, corpus, "COSINE", screen="TC_INT8")
+    rows, dist, cnt = check_queries(col, corpus, queries, "COSINE", k, (0, 5, 77, 100, 255))
+    st = col.stats()
+    assert st["screen_used"] == 4, st
+    assert st["n_repaired"] + st["n_fallback"] >= 2, st  # the two crowd queries cannot be proven on the batch's rung
+    # the same through the asynchronous entry points with another batch in flight
+    qa, qb = np.ascontiguousarray(queries), np.ascontiguousarray(queries[::-1])
+    outs = [(np.zeros((nq, k), np.uint64), np.zeros((nq, k), np.float64), np.zeros(nq, np.uint32)) for _ in range(2)]
+    t1 = col.submit_host(qa.ctypes.data, nq, k, outs[0][0].ctypes.data, outs[0][1].ctypes.data, outs[0][2].ctypes.data)
+    t2 = col.submit_host(qb.ctypes.data, nq, k, outs[1][0].ctypes.data, outs[1][1].ctypes.data, outs[1][2].ctypes.data)
+    col.wait(t1)
+    col.wait(t2)
+    assert outs[0][0].tobytes() == rows.astype(np.uint64).tobytes() and outs[0][1].tobytes() == dist.tobytes()
+    assert outs[1][0][::-1].tobytes() == rows.astype(np.uint64).tobytes()
