@@ -308,6 +308,24 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     ctx = Context(local)
+    # Watchdog: a multi-rank run whose ranks fall out of step must END (non-zero exit), not sit in a collective until
+    # somebody's time limit kills the box.  The main thread bumps `progress` at every step; 300 s without a bump = abort.
+    import threading
+    progress = [time.monotonic(), "start"]
+
+    def tick(what):
+        progress[0] = time.monotonic()
+        progress[1] = what
+
+    def watchdog():
+        while True:
+            time.sleep(5.0)
+            if time.monotonic() - progress[0] > 300.0:
+                sys.stderr.write(f"bench.py rank {rank}: no progress for 300 s in phase '{progress[1]}' -- aborting\n")
+                sys.stderr.flush()
+                os._exit(3)
+
+    threading.Thread(target=watchdog, daemon=True).start()
     if world > 1:
         # stdout carries exactly ONE JSON line: NCCL_DEBUG=VERSION would print a banner there at communicator creation
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
@@ -321,6 +339,7 @@ def main():
         dist.broadcast(uid, 0)
         ctx.comm_init_rank(world, rank, bytes(uid.cpu().numpy().tobytes()))
 
+    tick("corpus")
     # ---- shard the corpus row-wise (contiguous blocks, tile aligned); global row id = base + local ----
     base, n_local = shard_range(rows, world, rank)
     col = VectorColumn(ctx, dim, "COSINE", "F32", capacity=max(n_local, 1))
@@ -364,6 +383,7 @@ def main():
     col.set_row_base(base)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
 
+    tick("queries")
     # ---- query batches: pinned host copies (e2e) and device-resident copies (value) ----
     q_host = [torch.from_numpy(q).pin_memory() for q in q_np]
     q_dev = [q.to(dev) for q in q_host]
@@ -407,6 +427,7 @@ def main():
     def run_pipelined(submit, first, last, collect):
         pending = []
         for b in range(first, last):
+            tick(f"pipelined batch {b}")
             pending.append(submit(b, b % DEPTH))
             if len(pending) == DEPTH:
                 wait(pending.pop(0))
@@ -421,6 +442,7 @@ def main():
         # one synchronous plugin call per step: sdb_knn_bruteforce (host buffers) / sharded submit + wait
         o = h_out[0]
         for b in range(first, last):
+            tick(f"synchronous call {b}")
             if world > 1:
                 wait(submit_host(b, 0))
             else:
@@ -452,10 +474,12 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0]), float(t[1])
 
+    tick("warm-up")
     # ---- warm-up (both paths) ----
     run_pipelined(submit_dev, 0, args.warmup, False)
     run_sync_calls(0, min(2, args.warmup))
     run_pipelined(submit_host, 0, min(4, args.warmup), False)  # (allocates the per-slot staging buffers of the host path)
+    tick("timed value")
     # ---- timed: device-resident inputs (`value`) ----
     sampler = ClockSampler(local)
     if rank == 0:
@@ -464,12 +488,14 @@ def main():
     ms_value, wall_value = timed(lambda: run_pipelined(submit_dev, args.warmup, n_batches, True))
     launches = ctx.kernel_launches() - launches0
     stats = col.stats()
+    tick("timed e2e")
     # ---- timed: end to end through the host-buffer plugin call (`e2e`) ----
     ms_e2e, wall_e2e = timed(lambda: run_sync_calls(args.warmup, n_batches))
     e2e_last = (h_out[0][0].numpy().copy(), h_out[0][1].numpy().copy(), h_out[0][2].numpy().copy())
     ms_e2e_pipe, wall_e2e_pipe = timed(lambda: run_pipelined(submit_host, args.warmup, n_batches, False))
     clocks = sampler.stop() if rank == 0 else None
 
+    tick("parity")
     # ---- parity of the last timed batch (results of the e2e pass, rows/dist on the host) ----
     parity = {"checked": 0}
     if not args.no_parity:
@@ -534,6 +560,7 @@ def main():
             print(json.dumps({"error": "parity check failed", "parity": parity}), flush=True)
             sys.exit(3)
 
+    tick("extras")
     # ---- HBM-bound regime (small batches), reported next to the headline: f32 streaming kernel and tensor-core screens ----
     hbm_regime = []
     int8_peak = None
@@ -629,6 +656,7 @@ def main():
             h["frac_of_measured_hbm_peak"] = h["GBps"] / pk["hbm_gbs"]
         out["hbm_bound_regime"] = hbm_regime
         if world == 1 and not args.no_cpu_baseline:
+            tick("cpu baseline")
             subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"])
             out["cpu_baseline"], _ = cpu_baseline(rows, dim, k)
         print(json.dumps(out), flush=True)

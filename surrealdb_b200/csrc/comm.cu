@@ -206,7 +206,8 @@ sdb_status slot_reserve(Corpus* c, ShardSlot& s, uint32_t nq, uint32_t k, bool h
   if (s.hdr_cap < nranks) {
     if (s.h_hdr) cudaFreeHost(s.h_hdr);
     s.h_hdr = nullptr;
-    SDB_CUDA(cudaHostAlloc(&s.h_hdr, sizeof(uint32_t) * 4 * nranks, cudaHostAllocDefault));
+    SDB_CUDA(cudaHostAlloc(&s.h_hdr, sizeof(uint32_t) * (4 * nranks + 4), cudaHostAllocDefault));
+    memset(s.h_hdr, 0, sizeof(uint32_t) * (4 * nranks + 4));  // [4 * nranks]: exchange error word (peer-to-peer path)
     s.hdr_cap = nranks;
   }
   if (host_out) {
@@ -236,7 +237,7 @@ struct PeerTable {
 struct Arena {
   uint8_t* base = nullptr;  // this rank's arena (cudaMalloc: IPC-exportable)
   size_t block_cap = 0;     // bytes reserved per (slot, rank) block
-  size_t flags_off = 0, acks_off = 0, ctr_off = 0, bytes = 0;
+  size_t flags_off = 0, acks_off = 0, ctr_off = 0, err_off = 0, bytes = 0;
   int nranks = 0;
   PeerTable peers{};        // peers.base[r] = rank r's arena as mapped into this process (own base for r == rank)
   bool mapped[MAX_P2P_RANKS] = {};
@@ -254,6 +255,24 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Every wait on a peer is bounded: a rank that never arrives (crashed process, mismatched call sequence) must surface
+// as SDB_ENCCL on the host, not as a kernel that spins until the watchdog takes the GPU away.
+constexpr uint64_t EXCH_TIMEOUT_NS = 30ull * 1000ull * 1000ull * 1000ull;
+// spin until *p has reached `target` (sequence numbers, compared modulo 2^32); false = timed out
+__device__ __forceinline__ bool spin_until_reached(const uint32_t* p, uint32_t target) {
+  if ((int32_t)(ld_acquire_sys(p) - target) >= 0) return true;
+  const uint64_t t0 = global_timer_ns();
+  for (;;) {
+    __nanosleep(64);
+    if ((int32_t)(ld_acquire_sys(p) - target) >= 0) return true;
+    if (global_timer_ns() - t0 > EXCH_TIMEOUT_NS) return false;
+  }
+}
 
 // grid (nranks, S): CTA (p, s) stores its share of this rank's block into peer p's gather slot, the last of the S CTAs
 // publishes `seq` in p's flag word.  Before the first store thread 0 makes sure p has consumed the previous content of
@@ -263,11 +282,11 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
 // (a hang of the 50-step 8-GPU run, round 2); two pushes through the same slot are ordered by the ticket's life cycle.
 __global__ void __launch_bounds__(256) exch_push_kernel(PeerTable pt, uint8_t* my_base, const uint4* __restrict__ src,
                                                         size_t n16, size_t gather_off, size_t flag_off, size_t ack_off,
-                                                        size_t ctr_off, uint32_t need_ack, uint32_t seq) {
+                                                        size_t ctr_off, size_t err_off, uint32_t need_ack, uint32_t seq) {
   const uint32_t p = blockIdx.x, S = gridDim.y, sidx = blockIdx.y;
   if (threadIdx.x == 0) {
     const uint32_t* a = reinterpret_cast<const uint32_t*>(my_base + ack_off) + p;
-    while ((int32_t)(ld_acquire_sys(a) - need_ack) < 0) __nanosleep(64);
+    if (!spin_until_reached(a, need_ack)) atomicMax(reinterpret_cast<uint32_t*>(my_base + err_off), 1u);
   }
   __syncthreads();
   uint4* dst = reinterpret_cast<uint4*>(pt.base[p] + gather_off);
@@ -289,10 +308,10 @@ __global__ void __launch_bounds__(256) exch_push_kernel(PeerTable pt, uint8_t* m
   }
 }
 // one warp: wait until every rank's block of exchange `seq` has landed in this rank's slot
-__global__ void exch_wait_kernel(const uint8_t* my_base, size_t flags_off, int nranks, uint32_t seq) {
+__global__ void exch_wait_kernel(uint8_t* my_base, size_t flags_off, size_t err_off, int nranks, uint32_t seq) {
   if ((int)threadIdx.x < nranks) {
     const uint32_t* f = reinterpret_cast<const uint32_t*>(my_base + flags_off) + threadIdx.x;
-    while ((int32_t)(ld_acquire_sys(f) - seq) < 0) __nanosleep(64);
+    if (!spin_until_reached(f, seq)) atomicMax(reinterpret_cast<uint32_t*>(my_base + err_off), 2u);
   }
 }
 // one warp: tell every rank that this rank is done with the slot's content of exchange `seq`
@@ -336,7 +355,8 @@ static sdb_status arena_alloc_local(Corpus* c, Arena* a, size_t need) {
   a->flags_off = gather_bytes;
   a->acks_off = a->flags_off + 256 * ((sizeof(uint32_t) * N_TICKETS * R + 255) / 256);
   a->ctr_off = a->acks_off + 256 * ((sizeof(uint32_t) * N_TICKETS * R + 255) / 256);
-  a->bytes = a->ctr_off + 256 * ((sizeof(uint32_t) * N_TICKETS * R + 255) / 256);
+  a->err_off = a->ctr_off + 256 * ((sizeof(uint32_t) * N_TICKETS * R + 255) / 256);
+  a->bytes = a->err_off + 256;
   SDB_CUDA(cudaMalloc(&a->base, a->bytes));
   SDB_CUDA(cudaMemset(a->base, 0, a->bytes));
   SDB_CUDA(cudaDeviceSynchronize());
@@ -587,8 +607,8 @@ sdb_status phase_gather(const Pending& p) {
     if (S < 1) S = 1;
     const size_t ctr_off = a->ctr_off + sizeof(uint32_t) * ((size_t)p.slot * R);
     exch_push_kernel<<<dim3((unsigned)R, S), 256, 0, st>>>(a->peers, a->base, reinterpret_cast<const uint4*>(s.d_block), n16,
-                                                            gather_off, flag_off, ack_off, ctr_off, need_ack, seq);
-    exch_wait_kernel<<<1, 32, 0, st>>>(a->base, a->flags_off + sizeof(uint32_t) * ((size_t)p.slot * R), R, seq);
+                                                            gather_off, flag_off, ack_off, ctr_off, a->err_off, need_ack, seq);
+    exch_wait_kernel<<<1, 32, 0, st>>>(a->base, a->flags_off + sizeof(uint32_t) * ((size_t)p.slot * R), a->err_off, R, seq);
     SDB_CUDA(cudaGetLastError());
     knn_trace_mark(c, p.ticket, "exchanged");
     s.gather = a->base + (size_t)p.slot * R * a->block_cap;
@@ -624,6 +644,7 @@ sdb_status phase_merge(const Pending& p) {
     const int R = a->nranks, me = c->ctx->comm->rank;
     exch_ack_kernel<<<1, 32, 0, st>>>(a->peers, a->acks_off + sizeof(uint32_t) * ((size_t)p.slot * R + me), R, a->slot_seq[p.slot]);
     SDB_CUDA(cudaGetLastError());
+    SDB_CUDA(cudaMemcpyAsync(s.h_hdr + 4 * nranks, a->base + a->err_off, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   }
   if (s.h_out_count) {
     if (p.k) {
@@ -645,6 +666,13 @@ sdb_status finish_all(Pending* ps, int n) {
     SDB_CUDA(cudaSetDevice(ps[i].c->ctx->device));
     SDB_CUDA(cudaEventSynchronize(ps[i].s->ev_done));
     const int nranks = ps[i].c->ctx->comm ? ps[i].c->ctx->comm->nranks : 1;
+    if (use_p2p(ps[i].c, state_of(ps[i].c)) && ps[i].s->h_hdr[4 * nranks] != 0) {
+      set_error("sharded search: a peer did not %s within 30 s (rank %d of %d) -- every rank must submit the same batches in "
+                "the same order", ps[i].s->h_hdr[4 * nranks] == 1 ? "acknowledge a slot" : "deliver its block",
+                ps[i].c->ctx->comm->rank, nranks);
+      for (int j = 0; j < n; j++) knn_release_ticket(ps[j].c, ps[j].ticket);
+      return SDB_ENCCL;
+    }
     for (int r = 0; r < nranks; r++) any = any || ps[i].s->h_hdr[4 * r] != 0;
   }
   sdb_status rc = SDB_OK;
