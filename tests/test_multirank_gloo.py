@@ -98,3 +98,76 @@ def test_numpy_generator_matches_oracle_generator():
     a = O.gen_f32(0x5DB00002, 123456789012, 50000)
     b = gen_f32(0x5DB00002, 123456789012, 50000)
     assert a.tobytes() == b.tobytes()
+
+
+# ---- sharded graph expansion (graph.cu, round 2): the collective protocol of one hop, restated with gloo ---------------
+G_NODES, G_EDGES, G_LIMIT = 400, 3000, 5
+
+
+def _rmat_csr(seed):
+    rng = np.random.default_rng(seed)
+    src = rng.integers(0, G_NODES, G_EDGES)
+    dst = rng.integers(0, G_NODES, G_EDGES)
+    key = np.unique(src.astype(np.int64) * G_NODES + dst)  # (src, dst) order = edge-key order of the KV range
+    src, dst = key // G_NODES, key % G_NODES
+    row_ptr = np.zeros(G_NODES + 1, np.uint64)
+    row_ptr[1:] = np.cumsum(np.bincount(src, minlength=G_NODES))
+    return row_ptr, dst.astype(np.uint32)
+
+
+def graph_worker(rank, world, port, q):
+    """One hop as hop_device does it on a 1-D source-range shard: (1) degree of every frontier element this rank owns
+    (0 for the others), all-reduce(sum) -> the global degree array; (2) exclusive scan -> the position of every source's
+    neighbours in the level; (3) this rank writes its sources' neighbours into a ZERO-filled level; (4) all-reduce(sum)
+    assembles the level.  Order and duplicates must equal the unsharded per-source scans."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    row_ptr, col_idx = _rmat_csr(11)
+    lo, hi = (0, G_NODES // 3) if rank == 0 else (G_NODES // 3, G_NODES)  # deliberately uneven ranges
+    rp_local = row_ptr[lo:hi + 1] - row_ptr[lo]
+    ci_local = col_idx[int(row_ptr[lo]):int(row_ptr[hi])]
+    rng = np.random.default_rng(5)
+    frontier = rng.integers(0, G_NODES, 64).astype(np.uint32)  # duplicates on purpose: LookupPart keeps them
+    levels = []
+    for _hop in range(3):
+        deg = np.zeros(frontier.size, np.int64)
+        mine = (frontier >= lo) & (frontier < hi)
+        d = (rp_local[frontier[mine] - lo + 1] - rp_local[frontier[mine] - lo]).astype(np.int64)
+        deg[mine] = np.minimum(d, G_LIMIT) if G_LIMIT else d
+        t = torch.from_numpy(deg)
+        dist.all_reduce(t)  # (1)
+        offs = np.concatenate([[0], np.cumsum(t.numpy())])  # (2)
+        level = np.zeros(int(offs[-1]), np.int64)
+        for i in np.nonzero(mine)[0]:  # (3)
+            s = int(frontier[i]) - lo
+            nb = ci_local[int(rp_local[s]):int(rp_local[s]) + int(deg[i])]
+            level[offs[i]:offs[i] + nb.size] = nb
+        t2 = torch.from_numpy(level)
+        dist.all_reduce(t2)  # (4)
+        frontier = t2.numpy().astype(np.uint32)
+        levels.append(frontier.copy())
+    if rank == 0:
+        q.put(levels)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_graph_hop_protocol_equals_unsharded_oracle():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=graph_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    levels = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    row_ptr, col_idx = _rmat_csr(11)
+    frontier = np.random.default_rng(5).integers(0, G_NODES, 64).astype(np.uint32)
+    for h in range(3):
+        frontier = O.graph_hop(row_ptr, col_idx, frontier, G_LIMIT)
+        assert levels[h].tolist() == frontier.tolist(), h
