@@ -106,6 +106,13 @@ void sdb_pinned_free(void*);
 void sdb_ctx_cancel(sdb_ctx*);
 void sdb_ctx_cancel_reset(sdb_ctx*);
 /* total kernels launched through this context since creation (bench's gpu_launches) */
+/* Host-only diagnostic (needs no GPU): the sequence of corpus tiles (256 rows each) the screen of one batch visits --
+ * the streaming schedule's main launch (its probe tiles are returned separately) or, with streaming = 0, the passes of
+ * the multi-pass schedule.  No reference seam; exists so that "every tile is screened exactly once" can be tested on
+ * the CPU for any corpus size.  out_tiles / out_probe_tiles may be NULL (counts only). */
+sdb_status sdb_debug_schedule(uint64_t n_rows, uint32_t cand_cap, uint32_t k, uint32_t nq, int streaming,
+                              uint32_t* out_tiles, uint64_t cap_tiles, uint64_t* out_n, uint32_t* out_probe_tiles,
+                              uint32_t cap_probe, uint32_t* out_n_probe);
 uint64_t sdb_ctx_kernel_launches(const sdb_ctx*);
 /* the cudaStream_t every kernel of this context is launched on (so a harness can bracket calls with
  * CUDA events on the launching stream) */

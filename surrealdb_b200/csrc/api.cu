@@ -1122,6 +1122,40 @@ static sdb_status submit_host_locked(sdb_corpus* c, const double* queries, uint3
   return SDB_OK;
 }
 
+// Host-only diagnostic (no GPU needed): the corpus tiles (TILE_ROWS rows each) a screened search visits, in order.
+// Every row that is not visited can never become a candidate and the exactness proof would not know, so "every tile
+// exactly once" is a safety property of the schedules; tests/test_schedule_cover.py checks it exhaustively on the CPU.
+sdb_status sdb_debug_schedule(uint64_t n_rows, uint32_t cand_cap, uint32_t k, uint32_t nq, int streaming,
+                              uint32_t* out_tiles, uint64_t cap_tiles, uint64_t* out_n, uint32_t* out_probe_tiles,
+                              uint32_t cap_probe, uint32_t* out_n_probe) {
+  if (!out_n || !out_n_probe || cand_cap < TILE_ROWS) return SDB_EINVAL;
+  uint64_t n = 0;
+  uint32_t np = 0;
+  auto emit = [&](uint32_t tile) {
+    if (out_tiles && n < cap_tiles) out_tiles[n] = tile;
+    n++;
+  };
+  if (streaming) {
+    PassDesc p0, pm;
+    build_stream_passes(n_rows, cand_cap, k, &p0, &pm);
+    if (p0.count && !pm.count) {
+      for (uint32_t i = 0; i < p0.count; i++) emit(pass_tile(p0, i));  // pass 0 scores everything
+    } else {
+      for (uint32_t i = 0; i < p0.count; i++) {
+        if (out_probe_tiles && np < cap_probe) out_probe_tiles[np] = pass_tile(p0, i);
+        np++;
+      }
+      for (uint32_t i = 0; i < pm.count; i++) emit(pass_tile(pm, i));
+    }
+  } else {
+    for (const PassDesc& p : build_passes(n_rows, cand_cap, nq))
+      for (uint32_t i = 0; i < p.count; i++) emit(pass_tile(p, i));
+  }
+  *out_n = n;
+  *out_n_probe = np;
+  return SDB_OK;
+}
+
 sdb_status sdb_knn_submit(sdb_corpus* c, const double* queries, uint32_t nq, uint32_t k, uint64_t* out_rows,
                           double* out_dist, uint32_t* out_count, uint32_t* ticket) {
   if (!c || !ticket || !nq || !queries || !out_count || (k && (!out_rows || !out_dist))) return SDB_EINVAL;
