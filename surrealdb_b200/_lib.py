@@ -23,7 +23,7 @@ SCREEN = {"AUTO": 0, "SIMT_F32": 1, "TC_BF16": 2, "NONE_EXACT": 3, "TC_INT8": 4}
 # every symbol include/sdbgpu.h declares (tests/test_abi_symbols.py cross-checks this list with the header)
 ABI_SYMBOLS = [
     "sdb_ctx_create", "sdb_ctx_destroy", "sdb_last_error", "sdb_version", "sdb_pinned_alloc", "sdb_pinned_free",
-    "sdb_ctx_cancel", "sdb_ctx_cancel_reset", "sdb_ctx_kernel_launches", "sdb_ctx_stream", "sdb_corpus_create", "sdb_corpus_destroy", "sdb_corpus_append",
+    "sdb_ctx_cancel", "sdb_ctx_cancel_reset", "sdb_debug_schedule", "sdb_ctx_kernel_launches", "sdb_ctx_stream", "sdb_corpus_create", "sdb_corpus_destroy", "sdb_corpus_append",
     "sdb_corpus_append_device", "sdb_corpus_append_synthetic", "sdb_corpus_set_skip", "sdb_corpus_remove", "sdb_corpus_finalize",
     "sdb_corpus_rows", "sdb_corpus_read_rows", "sdb_corpus_set_minkowski_order", "sdb_corpus_set_screen", "sdb_corpus_set_schedule", "sdb_corpus_set_exact", "sdb_knn_bruteforce", "sdb_knn_bruteforce_device",
     "sdb_knn_last_stats", "sdb_knn_submit", "sdb_knn_submit_device", "sdb_knn_wait", "sdb_comm_unique_id",
