@@ -115,3 +115,20 @@ def test_c_driver_runs_the_three_paths_on_the_gpu(tmp_path):
     exe = _build_c_driver(tmp_path)
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ABI_DRIVER_OK" in out.stdout, (out.stdout, out.stderr)
+
+
+def test_stats_struct_layout_matches_the_header(tmp_path):
+    # sdb_knn_last_stats writes through a caller-provided struct: the ctypes mirror must have the C layout exactly
+    import ctypes as C
+    import subprocess
+    from surrealdb_b200 import _lib
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "sdbgpu.h"\n'
+                   'int main(){printf("%zu", sizeof(sdb_knn_stats));\n'
+                   + "".join(f'printf(" %zu", offsetof(sdb_knn_stats, {name}));\n' for name, _ in _lib.KnnStats._fields_)
+                   + 'return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    vals = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert vals[0] == C.sizeof(_lib.KnnStats)
+    assert vals[1:] == [getattr(_lib.KnnStats, name).offset for name, _ in _lib.KnnStats._fields_]
